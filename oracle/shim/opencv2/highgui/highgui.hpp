@@ -1,0 +1,3 @@
+// ORACLE SCAFFOLDING (test infrastructure).
+#pragma once
+#include <opencv2/core/core.hpp>
