@@ -197,6 +197,23 @@ int ref_pyramid(const uint8_t* img, int w, int h, int octaves, uint8_t* out, int
   return (int)ss.pyramid_.size();
 }
 
+// Final state of every layer's lazy score cache after GetKeypoints (debug aid
+// for the order-dependent cache semantics); layers concatenated.
+int ref_agast_cache_dump(const uint8_t* img, int w, int h, int thresh, int octaves, uint8_t* out) {
+  cv::Mat m = WrapCopy(img, w, h);
+  brisk::BriskScaleSpace ss((uint8_t)octaves, true);
+  ss.ConstructPyramid(m, (unsigned char)thresh);
+  std::vector<cv::KeyPoint> kps;
+  ss.GetKeypoints(&kps);
+  size_t off = 0;
+  for (size_t i = 0; i < ss.pyramid_.size(); ++i) {
+    const cv::Mat& sc = ss.pyramid_[i].scores();
+    memcpy(out + off, sc.data, (size_t)sc.cols * sc.rows);
+    off += (size_t)sc.cols * sc.rows;
+  }
+  return (int)kps.size();
+}
+
 // brisk::BriskFeatureDetector(thresh, octaves, suppress).detect(image, mask)
 int ref_agast_detect(const uint8_t* img, int w, int h, int thresh, int octaves, int suppress,
                      const uint8_t* mask, RefKeyPoint* out, int cap) {

@@ -1,0 +1,170 @@
+"""ctypes binding of oracle/_build/libbrisk_oracle.so -- our CPU restatement of
+the reference algorithm (TEST INFRASTRUCTURE ONLY).  Same Python surface as
+oracle/ref.py so tests can swap one for the other."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from .ref import KP_DTYPE
+
+_DIR = Path(__file__).resolve().parent
+_LIB_PATH = _DIR / "_build" / "libbrisk_oracle.so"
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", str(_DIR), "oracle"], check=True, capture_output=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            build()
+        _lib = C.CDLL(str(_LIB_PATH))
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _img(img):
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    assert img.ndim == 2
+    return img, img.shape[1], img.shape[0]
+
+
+def halfsample8(img):
+    img, w, h = _img(img)
+    out = np.zeros((h // 2, w // 2), np.uint8)
+    lib().orc_halfsample8(_p(img), w, h, _p(out))
+    return out
+
+
+def twothirdsample8(img):
+    img, w, h = _img(img)
+    out = np.zeros((2 * (h // 3), 2 * (w // 3)), np.uint8)
+    lib().orc_twothirdsample8(_p(img), w, h, _p(out))
+    return out
+
+
+def thrmap(img):
+    img, w, h = _img(img)
+    out = np.zeros((h, w), np.uint8)
+    lib().orc_thrmap(_p(img), w, h, _p(out))
+    return out
+
+
+def layer_dump(img, thresh, lower=10, cap=1 << 20):
+    img, w, h = _img(img)
+    c = np.zeros((cap, 3), np.int32)
+    n = lib().orc_layer_corners(_p(img), w, h, int(thresh), int(lower), _p(c), cap)
+    assert n <= cap
+    return thrmap(img), c[:n].copy()
+
+
+def dense_scores(img):
+    img, w, h = _img(img)
+    a = np.zeros((h, w), np.uint8)
+    b = np.zeros((h, w), np.uint8)
+    lib().orc_dense_scores(_p(img), w, h, _p(a), _p(b))
+    return a, b
+
+
+def pyramid(img, octaves):
+    img, w, h = _img(img)
+    nl = max(1, 2 * octaves)
+    dims = np.zeros((nl, 2), np.int32)
+    so = np.zeros((nl, 2), np.float32)
+    buf = np.zeros(w * h * 3, np.uint8)
+    n = lib().orc_pyramid(_p(img), w, h, int(octaves), _p(buf), _p(dims), _p(so))
+    out, off = [], 0
+    for i in range(n):
+        cw, ch = int(dims[i, 0]), int(dims[i, 1])
+        out.append(buf[off:off + cw * ch].reshape(ch, cw).copy())
+        off += cw * ch
+    return out, so[:n]
+
+
+def agast_detect(img, thresh, octaves=3, suppress=True, mask=None, cap=1 << 18):
+    img, w, h = _img(img)
+    kps = np.zeros(cap, KP_DTYPE)
+    if mask is not None:
+        mask = np.ascontiguousarray(mask, np.uint8)
+    n = lib().orc_agast_detect(_p(img), w, h, int(thresh), int(octaves), int(bool(suppress)), _p(mask), _p(kps), cap)
+    assert n <= cap
+    return kps[:n].copy()
+
+
+def harris_detect(img, octaves, radius, abs_thr=0.0, max_kpt=-1, cap=1 << 18):
+    img, w, h = _img(img)
+    kps = np.zeros(cap, KP_DTYPE)
+    n = lib().orc_harris_detect(_p(img), w, h, int(octaves), C.c_double(radius), C.c_double(abs_thr),
+                                C.c_int64(max_kpt), _p(kps), cap)
+    assert n <= cap
+    return kps[:n].copy()
+
+
+def harris_scores(img):
+    img, w, h = _img(img)
+    out = np.zeros((h, w), np.int32)
+    lib().orc_harris_scores(_p(img), w, h, _p(out))
+    return out
+
+
+def harris_maxima(img, abs_thr, cap=1 << 20):
+    img, w, h = _img(img)
+    out = np.zeros((cap, 3), np.int32)
+    n = lib().orc_harris_maxima(_p(img), w, h, int(abs_thr), _p(out), cap)
+    assert n <= cap
+    return out[:n].copy()
+
+
+def integral8(img):
+    img, w, h = _img(img)
+    out = np.zeros((h + 1, w + 1), np.int32)
+    lib().orc_integral8(_p(img), w, h, _p(out))
+    return out
+
+
+def describe(img, kps, rot=True, scale=True, version=2, pattern_scale=1.0):
+    img, w, h = _img(img)
+    k = np.ascontiguousarray(kps, KP_DTYPE).copy()
+    nb = C.c_int32(0)
+    flat = np.zeros(max(len(k), 1) * 256, np.uint8)
+    n = lib().orc_describe(_p(img), w, h, _p(k), len(k), int(rot), int(scale), int(version),
+                           C.c_float(pattern_scale), _p(flat), C.byref(nb))
+    return k[:n].copy(), flat[:n * nb.value].reshape(n, nb.value).copy()
+
+
+def pattern_dump(version=2, pattern_scale=1.0):
+    counts = np.zeros(4, np.int32)
+    lib().orc_pattern_dump(int(version), C.c_float(pattern_scale), _p(counts), None, None, None, None, None)
+    P, ns, nl, strings = (int(v) for v in counts)
+    pts = np.zeros((64, 1024, P, 3), np.float32)
+    scale_list = np.zeros(64, np.float32)
+    size_list = np.zeros(64, np.uint32)
+    sp = np.zeros((ns, 2), np.uint32)
+    lp = np.zeros((nl, 4), np.int32)
+    lib().orc_pattern_dump(int(version), C.c_float(pattern_scale), _p(counts), _p(pts), _p(scale_list),
+                           _p(size_list), _p(sp), _p(lp))
+    return dict(points=P, strings=strings, pts=pts, scale_list=scale_list, size_list=size_list,
+                short_pairs=sp, long_pairs=lp)
+
+
+def hamming(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_hamming(_p(a), _p(b), a.size)
+
+
+def knn(q, t, k):
+    q = np.ascontiguousarray(q, np.uint8)
+    t = np.ascontiguousarray(t, np.uint8)
+    idx = np.zeros((len(q), k), np.int32)
+    dist = np.zeros((len(q), k), np.int32)
+    lib().orc_knn(_p(q), C.c_int64(len(q)), _p(t), C.c_int64(len(t)), q.shape[1], int(k), _p(idx), _p(dist))
+    return idx, dist
