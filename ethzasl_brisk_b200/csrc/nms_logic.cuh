@@ -1,0 +1,482 @@
+// Scale-space non-maximum suppression and refinement of the AGAST path
+// (reference brisk/src/brisk-scale-space.cc:92-1099), reformulated so that it
+// can run data-parallel.
+//
+// The reference evaluates FAST scores lazily and caches them in a byte map
+// (brisk-layer.cc:118-132); a cached value > 2 is returned whatever threshold
+// is asked, so its results depend on the order in which pixels were first
+// looked at.  Observations that remove the sequential replay:
+//
+//  * Every look-up with threshold 1 returns a pure function of the image:
+//    T(q) at a detected corner, else F(q) = fast916 score if F >= 1, else 0.
+//    All of Refine3D / GetScoreMaxAbove / GetScoreMaxBelow use threshold 1, so
+//    their VALUES are order independent; only their cache FOOTPRINT matters.
+//  * IsMax2D's eight comparisons `center < s` are order independent as well
+//    (a cached neighbour returns F, an uncached one F or 0, and both compare the
+//    same against center).  What depends on the cache is only the tie path: the
+//    smoothed-centre comparison reads raw cache bytes.
+//  * The cache state of pixel q of layer i at the time corner c is examined is
+//    a function of (a) whether the layer below touched q (all of that happens
+//    before layer i is processed), and (b) the look-ups made by raster-earlier
+//    corners of layer i within 2 pixels of q: their IsMax2D neighbour look-ups
+//    (threshold = their own score) and, if they were accepted, their
+//    threshold-1 patch look-ups.
+//
+// So: `nms_prefix` (parallel) runs the eight comparisons for every corner,
+// `nms_checks` (parallel) runs the scale-space checks without side effects,
+// `nms_tie_decide` resolves the tying corners of a layer in raster order using
+// only byte look-ups, `mark_above` (parallel) records the cache footprint a
+// layer leaves on the layer above, and `refine_emit` (parallel) produces the
+// key points.  All functions are __host__ __device__ so that tests can run the
+// very same code on the CPU against the oracle.
+#pragma once
+#include "brisk_math.cuh"
+
+namespace briskb200 {
+
+struct LayerView {
+  const uint8_t* img;  // layer image
+  uint16_t* cm;        // corner map (see brisk_common.cuh)
+  uint8_t* bm;         // 1 where the layer below looked the pixel up (threshold 1)
+  int w, h, pitch;
+  float scale, offset;
+};
+
+enum LayerMode { kModeMid = 0, kModeLast = 1, kModeSingle = 2 };
+
+// Neighbour order of IsMax2D's look-ups (brisk-scale-space.cc:439-461).
+BRISK_HD void isMax2dOffset(int j, int* dx, int* dy) {
+  // (-1,0) (1,0) (0,-1) (0,1) (-1,1) (1,1) (1,-1) (-1,-1)
+  switch (j) {
+    case 0: *dx = -1; *dy = 0; break;
+    case 1: *dx = 1; *dy = 0; break;
+    case 2: *dx = 0; *dy = -1; break;
+    case 3: *dx = 0; *dy = 1; break;
+    case 4: *dx = -1; *dy = 1; break;
+    case 5: *dx = 1; *dy = 1; break;
+    case 6: *dx = 1; *dy = -1; break;
+    default: *dx = -1; *dy = -1; break;
+  }
+}
+
+// Index in that order of the neighbour at offset (dx, dy) in [-1,1]^2 \ (0,0).
+BRISK_HD int isMax2dIndex(int dx, int dy) {
+  // row dy=-1: (-1,-1)->7 (0,-1)->2 (1,-1)->6 ; dy=0: (-1,0)->0 (1,0)->1 ; dy=1: (-1,1)->4 (0,1)->3 (1,1)->5
+  const int code = (dy + 1) * 3 + (dx + 1);
+  switch (code) {
+    case 0: return 7;
+    case 1: return 2;
+    case 2: return 6;
+    case 3: return 0;
+    case 5: return 1;
+    case 6: return 4;
+    case 7: return 3;
+    default: return 5;
+  }
+}
+
+BRISK_HD bool in_border(const LayerView& L, int x, int y) { return x < 3 || y < 3 || x >= L.w - 3 || y >= L.h - 3; }
+
+// FAST score clipped at 0 (values <= 0 are indistinguishable for every use).
+BRISK_HD int fastF(const LayerView& L, int x, int y) {
+  const int f = fast916(L.img, L.pitch, x, y);
+  return f < 0 ? 0 : f;
+}
+
+// Value of BriskLayer::GetAgastScore(x, y, 1) (brisk-layer.cc:118-132): pure.
+template <bool MARK>
+BRISK_HD int score1(const LayerView& L, int x, int y) {
+  if (in_border(L, x, y)) return 0;
+  const long long o = (long long)y * L.pitch + x;
+  if (MARK) L.bm[o] = 1;
+  const int t = L.cm[o] & kCmT;
+  if (t) return t;
+  return fastF(L, x, y);  // F >= 1 ? F : 0
+}
+
+// BriskLayer::GetAgastScore(float, float, 1) (brisk-layer.cc:147-161).
+template <bool MARK>
+BRISK_HD int score1f(const LayerView& L, float xf, float yf) {
+  const int x = (int)xf;
+  const float rx1 = xf - (float)x;
+  const float rx = 1.0f - rx1;
+  const int y = (int)yf;
+  const float ry1 = yf - (float)y;
+  const float ry = 1.0f - ry1;
+  const int s00 = score1<MARK>(L, x, y), s10 = score1<MARK>(L, x + 1, y);
+  const int s01 = score1<MARK>(L, x, y + 1), s11 = score1<MARK>(L, x + 1, y + 1);
+  const float v = ((((rx * ry) * (float)s00 + (rx1 * ry) * (float)s10) + (rx * ry1) * (float)s01) + (rx1 * ry1) * (float)s11);
+  return (int)(uint8_t)v;
+}
+
+// BriskLayer::GetAgastScore_5_8(x, y, 1) (brisk-layer.cc:134-145).
+BRISK_HD int score58(const LayerView& L, int x, int y) {
+  if (x < 2 || y < 2 || x >= L.w - 2 || y >= L.h - 2) return 0;
+  const int f = fast58(L.img, L.pitch, x, y);
+  return f < 1 ? 0 : f;
+}
+
+template <bool MARK>
+BRISK_HD float patch3x3(const LayerView& L, int x, int y, float* dx, float* dy, int* center) {
+  const int s00 = score1<MARK>(L, x - 1, y - 1), s10 = score1<MARK>(L, x, y - 1), s20 = score1<MARK>(L, x + 1, y - 1);
+  const int s21 = score1<MARK>(L, x + 1, y), s11 = score1<MARK>(L, x, y), s01 = score1<MARK>(L, x - 1, y);
+  const int s02 = score1<MARK>(L, x - 1, y + 1), s12 = score1<MARK>(L, x, y + 1), s22 = score1<MARK>(L, x + 1, y + 1);
+  if (center) *center = s11;
+  return subpixel2d(s00, s01, s02, s10, s11, s12, s20, s21, s22, dx, dy);
+}
+
+// Shared scan of GetScoreMaxAbove (brisk-scale-space.cc:757-863) and
+// GetScoreMaxBelow (:917-1047) over the patch [x_1,x1]x[y_1,y1] of the
+// neighbouring layer.  Returns false when a score above `threshold` is met (not
+// tested on the bottom row, as in the reference).  BELOW adds the tie rule of
+// :987-1010 on interior pixels.
+template <bool MARK, bool BELOW>
+BRISK_HD bool scan_patch(const LayerView& nb, float x_1, float x1, float y_1, float y1, int threshold, float* max_out,
+                         int* mx, int* my) {
+  int max_x = (int)(x_1 + 1), max_y = (int)(y_1 + 1);
+  float tmp;
+  float max = (float)score1f<MARK>(nb, x_1, y_1);
+  if (max > (float)threshold) return false;
+  const int xb = (int)(x_1 + 1), xe = (int)x1, yb = (int)(y_1 + 1), ye = (int)y1;
+  for (int x = xb; x <= xe; ++x) {
+    tmp = (float)score1f<MARK>(nb, (float)x, y_1);
+    if (tmp > (float)threshold) return false;
+    if (tmp > max) { max = tmp; max_x = x; }
+  }
+  tmp = (float)score1f<MARK>(nb, x1, y_1);
+  if (tmp > (float)threshold) return false;
+  if (tmp > max) { max = tmp; max_x = xe; }
+  for (int y = yb; y <= ye; ++y) {
+    tmp = (float)score1f<MARK>(nb, x_1, (float)y);
+    if (tmp > (float)threshold) return false;
+    if (tmp > max) { max = tmp; max_x = xb; max_y = y; }
+    for (int x = xb; x <= xe; ++x) {
+      tmp = (float)score1<MARK>(nb, x, y);
+      if (tmp > (float)threshold) return false;
+      if (BELOW && tmp == max) {
+        const int t1 = 2 * (score1<MARK>(nb, x - 1, y) + score1<MARK>(nb, x + 1, y) + score1<MARK>(nb, x, y + 1) + score1<MARK>(nb, x, y - 1)) +
+                       (score1<MARK>(nb, x + 1, y + 1) + score1<MARK>(nb, x - 1, y + 1) + score1<MARK>(nb, x + 1, y - 1) + score1<MARK>(nb, x - 1, y - 1));
+        const int t2 = 2 * (score1<MARK>(nb, max_x - 1, max_y) + score1<MARK>(nb, max_x + 1, max_y) + score1<MARK>(nb, max_x, max_y + 1) + score1<MARK>(nb, max_x, max_y - 1)) +
+                       (score1<MARK>(nb, max_x + 1, max_y + 1) + score1<MARK>(nb, max_x - 1, max_y + 1) + score1<MARK>(nb, max_x + 1, max_y - 1) + score1<MARK>(nb, max_x - 1, max_y - 1));
+        if (t1 > t2) { max_x = x; max_y = y; }
+      }
+      if (tmp > max) { max = tmp; max_x = x; max_y = y; }
+    }
+    tmp = (float)score1f<MARK>(nb, x1, (float)y);
+    if (tmp > (float)threshold) return false;
+    if (tmp > max) { max = tmp; max_x = xe; max_y = y; }
+  }
+  tmp = (float)score1f<MARK>(nb, x_1, y1);
+  if (tmp > max) { max = tmp; max_x = xb; max_y = ye; }
+  for (int x = xb; x <= xe; ++x) {
+    tmp = (float)score1f<MARK>(nb, (float)x, y1);
+    if (tmp > max) { max = tmp; max_x = x; max_y = ye; }
+  }
+  tmp = (float)score1f<MARK>(nb, x1, y1);
+  if (tmp > max) { max = tmp; max_x = xe; max_y = ye; }
+  *max_out = max; *mx = max_x; *my = max_y;
+  return true;
+}
+
+BRISK_HD bool saturate1(float* dx, float* dy) {
+  bool inside = true;
+  if (*dx > 1.0f) { *dx = 1.0f; inside = false; }
+  if (*dx < -1.0f) { *dx = -1.0f; inside = false; }
+  if (*dy > 1.0f) { *dy = 1.0f; inside = false; }
+  if (*dy < -1.0f) { *dy = -1.0f; inside = false; }
+  return inside;
+}
+
+// GetScoreMaxAbove (brisk-scale-space.cc:757-915).  `layer` is the index of
+// the corner's own layer, `nb` the layer above it.
+template <bool MARK>
+BRISK_HD float score_max_above(const LayerView& nb, int layer, int x, int y, int thr, bool* ismax, float* dx, float* dy) {
+  *ismax = false;
+  float x_1, x1, y_1, y1;
+  if ((layer & 1) == 0) {
+    x_1 = (float)((double)(float)(4 * x - 1 - 2) / 6.0); x1 = (float)((double)(float)(4 * x - 1 + 2) / 6.0);
+    y_1 = (float)((double)(float)(4 * y - 1 - 2) / 6.0); y1 = (float)((double)(float)(4 * y - 1 + 2) / 6.0);
+  } else {
+    x_1 = (float)(6 * x - 1 - 3) / 8.0f; x1 = (float)(6 * x - 1 + 3) / 8.0f;
+    y_1 = (float)(6 * y - 1 - 3) / 8.0f; y1 = (float)(6 * y - 1 + 3) / 8.0f;
+  }
+  float max; int mx, my;
+  if (!scan_patch<MARK, false>(nb, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my)) return 0.0f;
+  float dx1, dy1;
+  const float refined = patch3x3<MARK>(nb, mx, my, &dx1, &dy1, nullptr);
+  const float rx = (float)mx + dx1, ry = (float)my + dy1;
+  if ((layer & 1) == 0) {
+    *dx = (rx * 6.0f + 1.0f) / 4.0f - (float)x;
+    *dy = (ry * 6.0f + 1.0f) / 4.0f - (float)y;
+  } else {
+    *dx = (float)(((double)rx * 8.0 + 1.0) / 6.0 - (double)(float)x);
+    *dy = (float)(((double)ry * 8.0 + 1.0) / 6.0 - (double)(float)y);
+  }
+  const bool inside = saturate1(dx, dy);
+  *ismax = true;
+  return inside ? (refined > max ? refined : max) : max;
+}
+
+// GetScoreMaxBelow (brisk-scale-space.cc:917-1099); `nb` is the layer below.
+// Its look-ups land on a layer whose own NMS is already finished, so its cache
+// footprint is never observed and is not recorded.
+BRISK_HD float score_max_below(const LayerView& nb, int layer, int x, int y, int thr, bool* ismax, float* dx, float* dy) {
+  *ismax = false;
+  float x_1, x1, y_1, y1;
+  if ((layer & 1) == 0) {
+    x_1 = (float)((double)(float)(8 * x + 1 - 4) / 6.0); x1 = (float)((double)(float)(8 * x + 1 + 4) / 6.0);
+    y_1 = (float)((double)(float)(8 * y + 1 - 4) / 6.0); y1 = (float)((double)(float)(8 * y + 1 + 4) / 6.0);
+  } else {
+    x_1 = (float)((double)(float)(6 * x + 1 - 3) / 4.0); x1 = (float)((double)(float)(6 * x + 1 + 3) / 4.0);
+    y_1 = (float)((double)(float)(6 * y + 1 - 3) / 4.0); y1 = (float)((double)(float)(6 * y + 1 + 3) / 4.0);
+  }
+  float max; int mx, my;
+  if (!scan_patch<false, true>(nb, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my)) return 0.0f;
+  float dx1, dy1;
+  const float refined = patch3x3<false>(nb, mx, my, &dx1, &dy1, nullptr);
+  const float rx = (float)mx + dx1, ry = (float)my + dy1;
+  if ((layer & 1) == 0) {
+    *dx = (float)(((double)rx * 6.0 + 1.0) / 8.0 - (double)(float)x);
+    *dy = (float)(((double)ry * 6.0 + 1.0) / 8.0 - (double)(float)y);
+  } else {
+    *dx = (float)(((double)rx * 4.0 - 1.0) / 6.0 - (double)(float)x);
+    *dy = (float)(((double)ry * 4.0 - 1.0) / 6.0 - (double)(float)y);
+  }
+  const bool inside = saturate1(dx, dy);
+  *ismax = true;
+  return inside ? (refined > max ? refined : max) : max;
+}
+
+// ---------------------------------------------------------------------------
+// Phase 1: the eight comparisons of IsMax2D (brisk-scale-space.cc:437-462).
+// Order independent.  Updates the corner's map entry; for tying corners also
+// stores the FAST scores of the 5x5 neighbourhood (row-major, clipped at 0;
+// entries of border pixels and of corners are unused) for phase 3.
+// ---------------------------------------------------------------------------
+BRISK_HD void nms_prefix(const LayerView& L, int x, int y, uint8_t fwin[25]) {
+  const long long o = (long long)y * L.pitch + x;
+  const int center = L.cm[o] & kCmT;
+  int calls = 8;
+  bool tie = false, rejected = false;
+  int f8[8];
+  for (int j = 0; j < 8; ++j) {
+    int dx, dy;
+    isMax2dOffset(j, &dx, &dy);
+    const int qx = x + dx, qy = y + dy;
+    int v;
+    if (in_border(L, qx, qy)) v = 0;
+    else {
+      const int t = L.cm[(long long)qy * L.pitch + qx] & kCmT;
+      v = t ? t : fastF(L, qx, qy);
+    }
+    f8[j] = v;
+    if (v > center) { calls = j + 1; rejected = true; break; }
+    if (v == center) tie = true;
+  }
+  uint16_t e = (uint16_t)(center | (calls << kCmCallsShift));
+  if (rejected) e |= kCmDecided;
+  else if (!tie) e |= (uint16_t)(kCmDecided | kCmAccept);
+  else e |= kCmTie;
+  L.cm[o] = e;
+  if (!rejected && tie) {
+    for (int wy = -2; wy <= 2; ++wy)
+      for (int wx = -2; wx <= 2; ++wx) {
+        const int qx = x + wx, qy = y + wy;
+        int v;
+        if (wx >= -1 && wx <= 1 && wy >= -1 && wy <= 1 && (wx || wy)) v = f8[isMax2dIndex(wx, wy)];
+        else if ((wx == 0 && wy == 0) || in_border(L, qx, qy)) v = 0;
+        else v = (L.cm[(long long)qy * L.pitch + qx] & kCmT) ? 0 : fastF(L, qx, qy);
+        fwin[(wy + 2) * 5 + wx + 2] = (uint8_t)v;
+      }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Phase 2: scale-space checks of a corner that passed phase 1 (tying or not),
+// without side effects.  Results are kept for refine_emit.
+// ---------------------------------------------------------------------------
+struct CheckResult {
+  float max_above, dxa, dya;
+  float max_below, dxb, dyb;
+};
+
+// Returns true when Refine3D (mid layers) / the last-layer branch of
+// GetKeypoints reaches its own-layer 3x3 patch.
+BRISK_HD bool nms_checks(const LayerView* layers, int n_layers, int layer, int x, int y, CheckResult* r) {
+  const LayerView& L = layers[layer];
+  const int center = L.cm[(long long)y * L.pitch + x] & kCmT;
+  r->max_above = 0; r->dxa = 0; r->dya = 0; r->max_below = 0; r->dxb = 0; r->dyb = 0;
+  if (n_layers == 1) return true;
+  bool ismax;
+  if (layer == n_layers - 1) {
+    r->max_below = score_max_below(layers[layer - 1], layer, x, y, center, &ismax, &r->dxb, &r->dyb);
+    return ismax;
+  }
+  r->max_above = score_max_above<false>(layers[layer + 1], layer, x, y, center, &ismax, &r->dxa, &r->dya);
+  if (!ismax) return false;
+  if (layer == 0) {
+    // guess the virtual intra-octave below octave 0 with the 5-8 mask (:558-592)
+    const int s00 = score58(L, x - 1, y - 1), s10 = score58(L, x, y - 1), s20 = score58(L, x + 1, y - 1);
+    const int s21 = score58(L, x + 1, y), s11 = score58(L, x, y), s01 = score58(L, x - 1, y);
+    const int s02 = score58(L, x - 1, y + 1), s12 = score58(L, x, y + 1), s22 = score58(L, x + 1, y + 1);
+    int best = imax(imax(imax(s00, s10), imax(s20, s21)), imax(imax(s11, s01), imax(imax(s02, s12), s22)));
+    subpixel2d(s00, s01, s02, s10, s11, s12, s20, s21, s22, &r->dxb, &r->dyb);
+    r->max_below = (float)best;
+    return true;
+  }
+  r->max_below = score_max_below(layers[layer - 1], layer, x, y, center, &ismax, &r->dxb, &r->dyb);
+  return ismax;
+}
+
+// ---------------------------------------------------------------------------
+// Phase 3: the tie path of IsMax2D (brisk-scale-space.cc:464-530) for one
+// corner, given that every raster-earlier corner of the layer is decided.
+// ---------------------------------------------------------------------------
+
+// Raw cache byte the reference would hold at pixel (qx,qy) just before corner
+// (cx,cy) runs IsMax2D.  F is the pixel's FAST score clipped at 0.
+BRISK_HD int cache_state(const LayerView& L, int mode, int qx, int qy, int F, int cx, int cy) {
+  if (in_border(L, qx, qy)) return 0;
+  const long long qo = (long long)qy * L.pitch + qx;
+  const int tq = L.cm[qo] & kCmT;
+  if (tq) return tq;  // a detected corner holds its threshold-map value (> 2)
+  if (F < 1) return 0;
+  bool sticky = false;
+  int last = 0;  // threshold of the most recent look-up, 0 = none
+  if (L.bm[qo]) { sticky = true; last = 1; }
+  // look-ups by raster-earlier corners of this layer whose footprint holds q
+  for (int py = qy - 2; py <= qy + 1; ++py) {
+    if (py < 3 || py > cy) continue;
+    for (int px = qx - 2; px <= qx + 1; ++px) {
+      if (px < 3 || px >= L.w - 3) continue;
+      if (py == cy && px >= cx) continue;  // not earlier than (cx, cy)
+      const uint16_t e = L.cm[(long long)py * L.pitch + px];
+      if (!(e & kCmT)) continue;
+      const int ox = qx - px, oy = qy - py;  // in [-1,2]^2
+      if (ox <= 1 && oy <= 1) {
+        // IsMax2D neighbour look-up with threshold T(p), if p got that far
+        const int j = isMax2dIndex(ox, oy);
+        if (j < ((e & kCmCalls) >> kCmCallsShift)) {
+          const int t = e & kCmT;
+          if (t <= F) sticky = true;
+          last = t;
+        }
+      }
+      if (e & kCmAccept) {
+        bool touched;
+        if (mode == kModeSingle) touched = true;                                       // 4x4 float-accessor patch
+        else if (mode == kModeLast) touched = (ox >= 0 && oy >= 0 && ox <= 1 && oy <= 1) || (e & kCmChecks);  // 2x2 centre read, then 4x4 patch
+        else touched = (e & kCmChecks) && ox <= 1 && oy <= 1;                           // int 3x3 patch of Refine3D
+        if (touched) { sticky = true; last = 1; }
+      }
+    }
+  }
+  if (F > 2) return sticky ? F : 0;
+  return (last != 0 && last <= F) ? F : 0;
+}
+
+// Returns the IsMax2D verdict of the tying corner (x,y).
+BRISK_HD bool nms_tie_decide(const LayerView& L, int mode, int x, int y, const uint8_t fwin[25]) {
+  const int center = L.cm[(long long)y * L.pitch + x] & kCmT;
+  int s[8];
+  for (int j = 0; j < 8; ++j) {
+    int dx, dy;
+    isMax2dOffset(j, &dx, &dy);
+    const int qx = x + dx, qy = y + dy;
+    const int F = fwin[(dy + 2) * 5 + dx + 2];  // T(q) when q is a corner
+    if (!in_border(L, qx, qy) && (L.cm[(long long)qy * L.pitch + qx] & kCmT)) { s[j] = F; continue; }
+    const int st = cache_state(L, mode, qx, qy, F, x, y);
+    s[j] = st > 2 ? st : (F >= center ? F : 0);
+  }
+  const int smoothed = 4 * center + 2 * (s[0] + s[1] + s[2] + s[3]) + s[7] + s[6] + s[4] + s[5];
+  // ties in the reference's order: (-1,-1) (0,-1) (1,-1) (-1,0) (1,0) (-1,1) (0,1) (1,1)
+  for (int k = 0; k < 8; ++k) {
+    const int ty = (k < 3) ? -1 : (k < 5 ? 0 : 1);
+    const int tx = (k < 3) ? k - 1 : (k < 5 ? (k == 3 ? -1 : 1) : k - 6);
+    if (s[isMax2dIndex(tx, ty)] != center) continue;
+    int other = 0;
+    for (int wy = -1; wy <= 1; ++wy)
+      for (int wx = -1; wx <= 1; ++wx) {
+        const int ox = tx + wx, oy = ty + wy;  // offset from the corner, in [-2,2]^2
+        int v;
+        if (ox == 0 && oy == 0) v = center;
+        else if (ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1) v = s[isMax2dIndex(ox, oy)];
+        else v = cache_state(L, mode, x + ox, y + oy, fwin[(oy + 2) * 5 + ox + 2], x, y);
+        const int wgt = (wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1);
+        other += wgt * v;
+      }
+    if (other > smoothed) return false;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// Phase 4: cache footprint an accepted corner of `layer` leaves on the layer
+// above (its GetScoreMaxAbove look-ups), recorded in that layer's touch map.
+// ---------------------------------------------------------------------------
+BRISK_HD void mark_above(const LayerView* layers, int layer, int x, int y) {
+  const LayerView& L = layers[layer];
+  const int center = L.cm[(long long)y * L.pitch + x] & kCmT;
+  bool ismax; float dx, dy;
+  score_max_above<true>(layers[layer + 1], layer, x, y, center, &ismax, &dx, &dy);
+}
+
+// ---------------------------------------------------------------------------
+// Phase 5: refinement of an accepted corner (Refine3D :598-754 after the
+// checks, and the single / last-layer branches of GetKeypoints :172-256).
+// Returns false when the corner is discarded on the scale axis.
+// ---------------------------------------------------------------------------
+BRISK_HD bool refine_emit(const LayerView* layers, int n_layers, int layer, int x, int y, const CheckResult& r,
+                          KeyPoint* kp) {
+  const LayerView& L = layers[layer];
+  float dxl, dyl;
+  int s11;
+  const float max_layer = patch3x3<false>(L, x, y, &dxl, &dyl, &s11);
+  kp->angle = -1.0f; kp->class_id = -1; kp->octave = layer;
+  if (n_layers == 1) {
+    kp->x = (float)x + dxl; kp->y = (float)y + dyl; kp->size = 12.0f; kp->response = max_layer; kp->octave = 0;
+    return true;
+  }
+  if (layer == n_layers - 1) {
+    kp->x = ((float)x + dxl) * L.scale + L.offset; kp->y = ((float)y + dyl) * L.scale + L.offset;
+    kp->size = 12.0f * L.scale; kp->response = max_layer;
+    return true;
+  }
+  const int center = s11;  // == T at the corner
+  const bool octave = (layer & 1) == 0;
+  bool refine_scale = true;
+  if (layer == 0) {
+    if (s11 - kMaxThreshold <= (int)r.max_above) refine_scale = false;
+  } else if ((float)(s11 - kMaxThreshold) < r.max_above || (float)(s11 - kMaxThreshold) < r.max_below) {
+    if ((float)(s11 - kMinDrop) > r.max_above || (float)(s11 - kMinDrop) > r.max_below) refine_scale = false;
+    else return false;
+  }
+  float scale, max;
+  if (refine_scale) {
+    const int kind = octave ? (layer == 0 ? 2 : 0) : 1;
+    const float c = (float)center;
+    scale = refine1d(kind, r.max_below, c > max_layer ? c : max_layer, r.max_above, &max);
+  } else {
+    scale = 1.0f;
+    max = max_layer;
+  }
+  float r0, ox, oy;
+  if (octave) {
+    if (scale > 1.0f) { r0 = (float)((1.5 - (double)scale) / .5); ox = r.dxa; oy = r.dya; }
+    else if (layer == 0) { r0 = (float)(((double)scale - 0.5) / 0.5); ox = r.dxb; oy = r.dyb; }
+    else { r0 = (float)(((double)scale - 0.75) / 0.25); ox = r.dxb; oy = r.dyb; }
+  } else {
+    if (scale > 1.0f) { r0 = (float)(4.0 - (double)scale * 3.0); ox = r.dxa; oy = r.dya; }
+    else { r0 = (float)((double)scale * 3.0 - 2.0); ox = r.dxb; oy = r.dyb; }
+  }
+  const float r1 = (float)(1.0 - (double)r0);
+  const float px = (r0 * dxl + r1 * ox) + (float)x;
+  const float py = (r0 * dyl + r1 * oy) + (float)y;
+  if (layer == 0 && !(scale > 1.0f)) { kp->x = px; kp->y = py; }
+  else { kp->x = px * L.scale + L.offset; kp->y = py * L.scale + L.offset; }
+  kp->size = 12.0f * (scale * L.scale);
+  kp->response = max;
+  return true;
+}
+
+}  // namespace briskb200

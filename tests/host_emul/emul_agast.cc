@@ -1,0 +1,116 @@
+// TEST HARNESS: compiles the product's __host__ __device__ NMS / refinement
+// logic (ethzasl_brisk_b200/csrc/*.cuh) for the CPU and runs the kernels'
+// phases serially, so the data-parallel reformulation of the order-dependent
+// reference algorithm can be checked against the oracle without a GPU.  This
+// is a test of product device code, not a CPU fallback: nothing in the product
+// links it.
+#include <stdint.h>
+#include <string.h>
+#include <vector>
+
+#include "../../ethzasl_brisk_b200/csrc/nms_logic.cuh"
+
+using namespace briskb200;
+
+namespace {
+struct HostLayer {
+  int w, h, pitch;
+  std::vector<uint8_t> img, bm;
+  std::vector<uint16_t> cm;
+  float scale, offset;
+  std::vector<int> cx, cy;  // raster-ordered corners
+};
+}  // namespace
+
+extern "C" int emul_agast_detect(const uint8_t* image, int w, int h, int thresh, int octaves, KeyPoint* out, int cap) {
+  const int n = octaves == 0 ? 1 : 2 * octaves;
+  std::vector<HostLayer> H(n);
+  auto alloc = [](HostLayer& l, int w_, int h_) {
+    l.w = w_; l.h = h_; l.pitch = (w_ + 15) / 16 * 16;
+    l.img.assign((size_t)l.pitch * h_, 0); l.bm.assign((size_t)l.pitch * h_, 0); l.cm.assign((size_t)l.pitch * h_, 0);
+  };
+  alloc(H[0], w, h);
+  for (int y = 0; y < h; ++y) memcpy(&H[0].img[(size_t)y * H[0].pitch], image + (size_t)y * w, w);
+  H[0].scale = 1.0f; H[0].offset = 0.0f;
+  for (int i = 1; i < n; ++i) {
+    const HostLayer& s = (i == 1) ? H[0] : H[i - 2];
+    HostLayer& d = H[i];
+    if (i == 1) {
+      alloc(d, 2 * (s.w / 3), 2 * (s.h / 3));
+      for (int R = 0; R < s.h / 3; ++R)
+        for (int T = 0; T < s.w / 3; ++T) {
+          int p[9], o[4];
+          for (int k = 0; k < 9; ++k) p[k] = s.img[(size_t)(3 * R + k / 3) * s.pitch + 3 * T + k % 3];
+          twothird_block(p, T, s.w, o);
+          d.img[(size_t)(2 * R) * d.pitch + 2 * T] = (uint8_t)o[0]; d.img[(size_t)(2 * R) * d.pitch + 2 * T + 1] = (uint8_t)o[1];
+          d.img[(size_t)(2 * R + 1) * d.pitch + 2 * T] = (uint8_t)o[2]; d.img[(size_t)(2 * R + 1) * d.pitch + 2 * T + 1] = (uint8_t)o[3];
+        }
+      d.scale = (float)(s.scale * 1.5);
+    } else {
+      alloc(d, s.w / 2, s.h / 2);
+      for (int r = 0; r < d.h; ++r)
+        for (int c = 0; c < d.w; ++c) {
+          const uint8_t* a = &s.img[(size_t)(2 * r) * s.pitch + 2 * c];
+          d.img[(size_t)r * d.pitch + c] = (uint8_t)halfsample_px(a[0], a[1], a[s.pitch], a[s.pitch + 1], c, s.w);
+        }
+      d.scale = s.scale * 2;
+    }
+    d.offset = (float)(0.5 * d.scale - 0.5);
+  }
+  std::vector<LayerView> V(n);
+  for (int i = 0; i < n; ++i) {
+    HostLayer& l = H[i];
+    V[i] = LayerView{l.img.data(), l.cm.data(), l.bm.data(), l.w, l.h, l.pitch, l.scale, l.offset};
+    // detect kernel: threshold map + segment test -> corner map, raster order
+    for (int y = 3; y < l.h - 3; ++y)
+      for (int x = 3; x < l.w - 3; ++x) {
+        const int T = thrmap_px(l.img.data(), l.pitch, x, y);
+        if (agast_is_corner(l.img.data(), l.pitch, x, y, T, thresh)) {
+          l.cm[(size_t)y * l.pitch + x] = (uint16_t)T;
+          l.cx.push_back(x); l.cy.push_back(y);
+        }
+      }
+  }
+  // phase 1 + 2 (parallel on the GPU)
+  std::vector<std::vector<uint8_t>> fwin(n);
+  std::vector<std::vector<CheckResult>> chk(n);
+  for (int i = 0; i < n; ++i) {
+    const size_t nc = H[i].cx.size();
+    fwin[i].assign(nc * 25, 0);
+    chk[i].resize(nc);
+    for (size_t k = 0; k < nc; ++k) nms_prefix(V[i], H[i].cx[k], H[i].cy[k], &fwin[i][k * 25]);
+  }
+  for (int i = 0; i < n; ++i)
+    for (size_t k = 0; k < H[i].cx.size(); ++k) {
+      uint16_t& e = H[i].cm[(size_t)H[i].cy[k] * H[i].pitch + H[i].cx[k]];
+      if ((e & kCmDecided) && !(e & kCmAccept)) continue;
+      if (nms_checks(V.data(), n, i, H[i].cx[k], H[i].cy[k], &chk[i][k])) e |= kCmChecks;
+    }
+  // phase 3 + 4 (per frame: layers in order)
+  for (int i = 0; i < n; ++i) {
+    const int mode = n == 1 ? kModeSingle : (i == n - 1 ? kModeLast : kModeMid);
+    for (size_t k = 0; k < H[i].cx.size(); ++k) {
+      uint16_t& e = H[i].cm[(size_t)H[i].cy[k] * H[i].pitch + H[i].cx[k]];
+      if (e & kCmDecided) continue;
+      const bool ok = nms_tie_decide(V[i], mode, H[i].cx[k], H[i].cy[k], &fwin[i][k * 25]);
+      e |= (uint16_t)(kCmDecided | (ok ? kCmAccept : 0));
+    }
+    if (mode == kModeMid)
+      for (size_t k = 0; k < H[i].cx.size(); ++k) {
+        const uint16_t e = H[i].cm[(size_t)H[i].cy[k] * H[i].pitch + H[i].cx[k]];
+        if (e & kCmAccept) mark_above(V.data(), i, H[i].cx[k], H[i].cy[k]);
+      }
+  }
+  // phase 5 + ordered compaction
+  int total = 0;
+  for (int i = 0; i < n; ++i)
+    for (size_t k = 0; k < H[i].cx.size(); ++k) {
+      const uint16_t e = H[i].cm[(size_t)H[i].cy[k] * H[i].pitch + H[i].cx[k]];
+      if (!(e & kCmAccept) || !(e & kCmChecks)) continue;
+      KeyPoint kp;
+      if (!refine_emit(V.data(), n, i, H[i].cx[k], H[i].cy[k], chk[i][k], &kp)) continue;
+      if (total < cap) out[total] = kp;
+      ++total;
+    }
+  return total;
+}
