@@ -1,0 +1,363 @@
+"""Python host mirror of the reference's public classes over the C ABI.
+
+Class names, constructor arguments and semantics follow the reference headers
+(brisk/include/brisk/brisk-feature-detector.h:51-84,
+brisk-descriptor-extractor.h:54-202, brute-force-matcher.h:54-94,
+internal/hamming.h:56-114); each method calls straight into
+libbrisk_b200.so (include/brisk_b200.h).  Images are numpy u8 arrays (host) or
+torch CUDA tensors (device, passed by pointer); key points are numpy structured
+arrays binary-compatible with cv::KeyPoint.
+
+There is no CPU path: if the CUDA library is missing or no GPU is usable,
+construction fails.
+"""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"),
+                     ("response", "f4"), ("octave", "i4"), ("class_id", "i4")])
+assert KP_DTYPE.itemsize == 28
+
+STAGES = ("h2d", "pyramid", "detect", "lists", "nms", "integral", "describe", "d2h", "knn")
+_LIB_PATH = Path(__file__).resolve().parent / "libbrisk_b200.so"
+_lib = None
+
+BRISK_ERR_CAPACITY = -4
+
+
+class BriskError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"brisk_b200 error {code}: {msg}")
+        self.code = code
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load_library():
+    """dlopen libbrisk_b200.so; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise RuntimeError(f"{_LIB_PATH} not found: build it with `python -m ethzasl_brisk_b200.build` "
+                               "(nvcc, sm_100a); there is no CPU fallback")
+        lib = C.CDLL(str(_LIB_PATH))
+        lib.brisk_last_error.restype = C.c_char_p
+        lib.brisk_last_error.argtypes = [C.c_void_p]
+        _lib = lib
+    return _lib
+
+
+def _ptr(a):
+    """(address, keep-alive) of a numpy array or torch tensor, or NULL."""
+    if a is None:
+        return None
+    if hasattr(a, "data_ptr"):  # torch tensor (host or CUDA)
+        return C.c_void_p(a.data_ptr())
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _is_torch(a):
+    return hasattr(a, "data_ptr")
+
+
+class Context:
+    """One CUDA device + stream + workspaces (brisk_ctx). Not thread-safe."""
+
+    def __init__(self, device=0, stream=None, workspace_limit=None, timing=False):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        sp = C.c_void_p(int(stream)) if stream else None
+        rc = self._lib.brisk_ctx_create(int(device), sp, C.byref(self._h))
+        if rc != 0:
+            raise BriskError(rc, "brisk_ctx_create failed (no usable CUDA device?)")
+        self.device = int(device)
+        if workspace_limit:
+            self._check(self._lib.brisk_ctx_set_workspace_limit(self._h, C.c_size_t(int(workspace_limit))))
+        if timing:
+            self.enable_timing(True)
+
+    def _check(self, rc, allow_capacity=False):
+        if rc != 0 and not (allow_capacity and rc == BRISK_ERR_CAPACITY):
+            raise BriskError(rc, (self._lib.brisk_last_error(self._h) or b"").decode())
+        return rc
+
+    def enable_timing(self, on=True):
+        self._check(self._lib.brisk_ctx_enable_timing(self._h, int(bool(on))))
+
+    def last_timing(self):
+        """-> (dict stage -> device ms of the last call, kernel launches of the last call)"""
+        ms = (C.c_float * len(STAGES))()
+        n = C.c_int64(0)
+        self._check(self._lib.brisk_ctx_last_timing(self._h, ms, C.byref(n)))
+        return {s: float(ms[i]) for i, s in enumerate(STAGES)}, int(n.value)
+
+    def sync(self):
+        self._check(self._lib.brisk_sync(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.brisk_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- stage dumps used by the parity tests ---
+    def debug_pyramid(self, img, octaves):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        dims = np.zeros((12, 2), np.int32)
+        buf = np.zeros(3 * w * h + 64, np.uint8)
+        nl = C.c_int(0)
+        self._check(self._lib.brisk_debug_pyramid(self._h, int(octaves), _ptr(img), w, h, C.c_size_t(w), _ptr(buf), _ptr(dims), C.byref(nl)))
+        out, off = [], 0
+        for i in range(nl.value):
+            cw, ch = int(dims[i, 0]), int(dims[i, 1])
+            out.append(buf[off:off + cw * ch].reshape(ch, cw).copy())
+            off += cw * ch
+        return out
+
+    def debug_integral(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        out = np.zeros((h + 1, w + 1), np.int32)
+        self._check(self._lib.brisk_debug_integral(self._h, _ptr(img), w, h, C.c_size_t(w), _ptr(out)))
+        return out
+
+
+_default_ctx = None
+
+
+def default_context():
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def _frames(images):
+    """-> (array-like, n, h, w, stride, frame_pitch) for [h,w] / [n,h,w] u8 input."""
+    if _is_torch(images):
+        t = images
+        if t.dim() == 2:
+            t = t.unsqueeze(0)
+        assert t.dim() == 3 and t.element_size() == 1 and t.stride(2) == 1
+        n, h, w = t.shape
+        return t, n, h, w, t.stride(1), (t.stride(0) if n > 1 else t.stride(1) * h)
+    a = np.asarray(images)
+    if a.dtype != np.uint8:
+        raise TypeError("images must be 8-bit grayscale (CV_8UC1)")
+    if a.ndim == 2:
+        a = a[None]
+    a = np.ascontiguousarray(a)
+    n, h, w = a.shape
+    return a, n, h, w, w, w * h
+
+
+class BriskFeatureDetector:
+    """brisk::BriskFeatureDetector(thresh, octaves=3, suppressScaleNonmaxima=true)."""
+
+    def __init__(self, thresh, octaves=3, suppressScaleNonmaxima=True, ctx=None):
+        self.ctx = ctx or default_context()
+        self.threshold, self.octaves = int(thresh), int(octaves)
+        self._h = C.c_void_p()
+        self.ctx._check(self.ctx._lib.brisk_agast_detector_create(self.ctx._h, self.threshold, self.octaves,
+                                                                   int(bool(suppressScaleNonmaxima)), C.byref(self._h)))
+
+    def set_corner_capacity(self, n):
+        self.ctx._check(self.ctx._lib.brisk_detector_set_corner_capacity(self._h, int(n)))
+
+    def detect_batch(self, images, masks=None, cap=16384, out=None):
+        """images [n,h,w] u8 -> (kps [n,cap] structured, counts [n])."""
+        a, n, h, w, stride, fp = _frames(images)
+        m = None
+        if masks is not None:
+            m = _frames(masks)[0]
+        if out is None:
+            kps = np.zeros((n, cap), KP_DTYPE)
+            counts = np.zeros(n, np.int32)
+        else:
+            kps, counts = out
+        self.ctx._check(self.ctx._lib.brisk_detect(self.ctx._h, self._h, _ptr(a), n, w, h, C.c_size_t(stride), C.c_size_t(fp),
+                                                   _ptr(m), _ptr(kps), _ptr(counts), int(cap)))
+        return kps, counts
+
+    def detect(self, image, mask=None, cap=65536):
+        """cv::Feature2D::detect for one image -> key points (structured array)."""
+        kps, counts = self.detect_batch(image, None if mask is None else mask, cap)
+        return kps[0, :counts[0]].copy()
+
+    def debug_corners(self, image, cap=1 << 20):
+        img = np.ascontiguousarray(image, np.uint8)
+        h, w = img.shape
+        c = np.zeros((cap, 3), np.int32)
+        lc = np.zeros(12, np.int32)
+        n = self.ctx._lib.brisk_debug_corners(self.ctx._h, self._h, _ptr(img), w, h, C.c_size_t(w), _ptr(c), cap, _ptr(lc))
+        if n < 0:
+            self.ctx._check(n)
+        return c[:n].copy(), lc
+
+    def __del__(self):
+        try:
+            if self._h.value:
+                self.ctx._lib.brisk_detector_destroy(self._h)
+        except Exception:
+            pass
+
+
+class BriskDescriptorExtractor:
+    """brisk::BriskDescriptorExtractor(rotationInvariant, scaleInvariant, version, patternScale)."""
+
+    briskV1, briskV2 = 1, 2
+    kDescriptorLength = 384
+
+    def __init__(self, rotationInvariant=True, scaleInvariant=True, version=2, patternScale=1.0, fname=None, ctx=None):
+        self.ctx = ctx or default_context()
+        self.rotationInvariance, self.scaleInvariance = bool(rotationInvariant), bool(scaleInvariant)
+        self._h = C.c_void_p()
+        f = fname.encode() if fname else None
+        self.ctx._check(self.ctx._lib.brisk_extractor_create(self.ctx._h, int(self.rotationInvariance), int(self.scaleInvariance),
+                                                              int(version), C.c_float(patternScale), f, C.byref(self._h)))
+
+    def descriptorSize(self):
+        return int(self.ctx._lib.brisk_extractor_descriptor_size(self._h))
+
+    def descriptorType(self):
+        return 0  # CV_8U
+
+    def pattern(self):
+        counts = np.zeros(4, np.int32)
+        L = self.ctx._lib
+        self.ctx._check(L.brisk_extractor_pattern(self._h, _ptr(counts), None, None, None, None, None))
+        P, ns, nl, nb = (int(v) for v in counts)
+        pts = np.zeros((64, 1024, P, 3), np.float32)
+        scale_list = np.zeros(64, np.float32)
+        size_list = np.zeros(64, np.uint32)
+        sp = np.zeros((ns, 2), np.uint32)
+        lp = np.zeros((nl, 4), np.int32)
+        self.ctx._check(L.brisk_extractor_pattern(self._h, _ptr(counts), _ptr(pts), _ptr(scale_list), _ptr(size_list), _ptr(sp), _ptr(lp)))
+        return dict(points=P, strings=nb, pts=pts, scale_list=scale_list, size_list=size_list, short_pairs=sp, long_pairs=lp)
+
+    def compute_batch(self, images, kps, counts, cap=None):
+        """kps [n,cap] / counts [n] in -> (kps, counts, desc [n,cap,descriptorSize]); inputs are not modified."""
+        a, n, h, w, stride, fp = _frames(images)
+        kps = np.ascontiguousarray(kps, KP_DTYPE).copy()
+        counts = np.ascontiguousarray(counts, np.int32).copy()
+        cap = kps.shape[1]
+        desc = np.zeros((n, cap, self.descriptorSize()), np.uint8)
+        self.ctx._check(self.ctx._lib.brisk_describe(self.ctx._h, self._h, _ptr(a), n, w, h, C.c_size_t(stride), C.c_size_t(fp),
+                                                     _ptr(kps), _ptr(counts), int(cap), _ptr(desc)))
+        return kps, counts, desc
+
+    def compute(self, image, keypoints):
+        """cv::Feature2D::compute for one image -> (surviving key points with angle, descriptors [m, size])."""
+        k = np.ascontiguousarray(keypoints, KP_DTYPE)
+        cap = max(len(k), 1)
+        kk = np.zeros((1, cap), KP_DTYPE)
+        kk[0, :len(k)] = k
+        kps, counts, desc = self.compute_batch(image, kk, np.array([len(k)], np.int32))
+        m = int(counts[0])
+        return kps[0, :m].copy(), desc[0, :m].copy()
+
+    def __del__(self):
+        try:
+            if self._h.value:
+                self.ctx._lib.brisk_extractor_destroy(self._h)
+        except Exception:
+            pass
+
+
+def detect_and_compute_batch(detector, extractor, images, masks=None, cap=16384, out=None, allow_truncation=False):
+    """detect() + compute() without leaving the device.
+
+    -> (kps [n,cap], counts [n], desc [n,cap,descriptorSize]).  `out` may hold
+    preallocated (kps, counts, desc) numpy arrays or torch CUDA tensors.
+    """
+    ctx = detector.ctx
+    assert extractor.ctx is ctx
+    a, n, h, w, stride, fp = _frames(images)
+    m = None if masks is None else _frames(masks)[0]
+    if out is None:
+        kps = np.zeros((n, cap), KP_DTYPE)
+        counts = np.zeros(n, np.int32)
+        desc = np.zeros((n, cap, extractor.descriptorSize()), np.uint8)
+    else:
+        kps, counts, desc = out
+    rc = ctx._lib.brisk_detect_describe(ctx._h, detector._h, extractor._h, _ptr(a), n, w, h, C.c_size_t(stride), C.c_size_t(fp),
+                                        _ptr(m), _ptr(kps), _ptr(counts), int(cap), _ptr(desc))
+    ctx._check(rc, allow_capacity=allow_truncation)
+    return kps, counts, desc
+
+
+class Hamming:
+    """brisk::Hamming functor: popcount(a xor b)."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+
+    def __call__(self, a, b, size=None):
+        a = np.ascontiguousarray(a, np.uint8).reshape(1, -1)
+        b = np.ascontiguousarray(b, np.uint8).reshape(1, -1)
+        nb = a.shape[1] if size is None else int(size)
+        d = np.zeros(1, np.int32)
+        self.ctx._check(self.ctx._lib.brisk_hamming_distance(self.ctx._h, _ptr(a), _ptr(b), C.c_int64(1), nb, _ptr(d)))
+        return int(d[0])
+
+
+class BruteForceMatcher:
+    """brisk::BruteForceMatcher: brute-force Hamming kNN (one train collection, no masks)."""
+
+    def __init__(self, distance=None, ctx=None):
+        self.ctx = ctx or (distance.ctx if distance is not None else default_context())
+        self._train = []
+
+    def isMaskSupported(self):
+        return False  # masks: SURVEY.md 8(f), not in this round
+
+    def add(self, descriptors):
+        self._train.append(np.ascontiguousarray(descriptors, np.uint8))
+
+    def clear(self):
+        self._train = []
+
+    def knn(self, query, train, k):
+        """-> (idx [nq,k] int32, dist [nq,k] int32); query/train: numpy u8 [n, bytes] or torch CUDA tensors."""
+        nq, nb = query.shape
+        nt = train.shape[0]
+        if _is_torch(query):
+            import torch
+            idx = torch.empty((nq, k), dtype=torch.int32, device=query.device)
+            dist = torch.empty((nq, k), dtype=torch.int32, device=query.device)
+        else:
+            query = np.ascontiguousarray(query, np.uint8)
+            train = np.ascontiguousarray(train, np.uint8)
+            idx = np.zeros((nq, k), np.int32)
+            dist = np.zeros((nq, k), np.int32)
+        self.ctx._check(self.ctx._lib.brisk_hamming_knn(self.ctx._h, _ptr(query), C.c_int64(nq), _ptr(train), C.c_int64(nt), int(nb), int(k),
+                                                        _ptr(idx), _ptr(dist)))
+        return idx, dist
+
+    def knnMatch(self, queryDescriptors, trainDescriptors=None, k=1):
+        """cv::DescriptorMatcher::knnMatch -> list (per query) of (queryIdx, trainIdx, imgIdx, distance) tuples."""
+        train = trainDescriptors if trainDescriptors is not None else np.concatenate(self._train)
+        idx, dist = self.knn(np.ascontiguousarray(queryDescriptors, np.uint8), train, k)
+        return [[(qi, int(i), 0, float(d)) for i, d in zip(idx[qi], dist[qi]) if i >= 0] for qi in range(len(idx))]
+
+    # --- train set sharded across GPUs: local keys, caller exchanges them (NCCL all-gather), merge ---
+    def knn_keys(self, query, train_shard, k, global_offset, keys_out):
+        nq, nb = query.shape
+        self.ctx._check(self.ctx._lib.brisk_hamming_knn_keys(self.ctx._h, _ptr(query), C.c_int64(nq), _ptr(train_shard),
+                                                             C.c_int64(train_shard.shape[0]), int(nb), int(k), C.c_int64(global_offset), _ptr(keys_out)))
+        return keys_out
+
+    def merge_keys(self, gathered_keys, n_shards, nq, k, idx_out, dist_out):
+        self.ctx._check(self.ctx._lib.brisk_knn_merge_keys(self.ctx._h, _ptr(gathered_keys), int(n_shards), C.c_int64(nq), int(k),
+                                                           _ptr(idx_out), _ptr(dist_out)))
+        return idx_out, dist_out

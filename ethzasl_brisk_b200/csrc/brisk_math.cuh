@@ -54,36 +54,41 @@ BRISK_HD void twothird_block(const int p[9], int T, int src_w, int out[4]) {
 BRISK_HD int imin(int a, int b) { return a < b ? a : b; }
 BRISK_HD int imax(int a, int b) { return a > b ? a : b; }
 
-// max over all arcs of ARC contiguous ring values of max(min(d), min(-d)).
-// The generated AGAST trees (agast/src/oast9-16.cc:43-1859) and the bisection
-// cornerScore (oast9-16-nms.cc:39-1976, agast5-8-nms.cc:39-358) reduce to this
-// quantity m: is-corner(b) <=> m-1 >= b, cornerScore(b) = max(b, m-1)
-// (SURVEY.md F6).
-BRISK_HD int arc_contrast16(const int d[16]) {
+// m = max over all arcs of ARC contiguous ring pixels of
+// max(min_i(p_i - c), min_i(c - p_i)).  The generated AGAST trees
+// (agast/src/oast9-16.cc:43-1859) and the bisection cornerScore
+// (oast9-16-nms.cc:39-1976, agast5-8-nms.cc:39-358) reduce to this quantity:
+// is-corner(b) <=> m-1 >= b, cornerScore(b) = max(b, m-1).
+//
+// Written on the raw pixel values as max(min(p) - c, c - max(p)).  Do NOT
+// rewrite it as max(min(d), -max(d)) on differences: ptxas 12.9 for sm_100a
+// folds that negation into VIMNMX3 and drops it (observed on hardware: wrong
+// scores), while plain subtractions are compiled correctly.
+BRISK_HD int arc_contrast16(const int p[16], int c) {
   // sliding minimum / maximum over windows of 9 on the circular sequence
   int lo2[16], hi2[16], lo4[16], hi4[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { lo2[i] = imin(d[i], d[(i + 1) & 15]); hi2[i] = imax(d[i], d[(i + 1) & 15]); }
+  for (int i = 0; i < 16; ++i) { lo2[i] = imin(p[i], p[(i + 1) & 15]); hi2[i] = imax(p[i], p[(i + 1) & 15]); }
 #pragma unroll
   for (int i = 0; i < 16; ++i) { lo4[i] = imin(lo2[i], lo2[(i + 2) & 15]); hi4[i] = imax(hi2[i], hi2[(i + 2) & 15]); }
   int best = -1000;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const int lo9 = imin(imin(lo4[i], lo4[(i + 4) & 15]), d[(i + 8) & 15]);
-    const int hi9 = imax(imax(hi4[i], hi4[(i + 4) & 15]), d[(i + 8) & 15]);
-    best = imax(best, imax(lo9, -hi9));
+    const int lo9 = imin(imin(lo4[i], lo4[(i + 4) & 15]), p[(i + 8) & 15]);
+    const int hi9 = imax(imax(hi4[i], hi4[(i + 4) & 15]), p[(i + 8) & 15]);
+    best = imax(best, imax(lo9 - c, c - hi9));
   }
   return best;
 }
 
-BRISK_HD int arc_contrast8(const int d[8]) {
+BRISK_HD int arc_contrast8(const int p[8], int c) {
   int best = -1000;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    int lo = d[i], hi = d[i];
+    int lo = p[i], hi = p[i];
 #pragma unroll
-    for (int k = 1; k < 5; ++k) { lo = imin(lo, d[(i + k) & 7]); hi = imax(hi, d[(i + k) & 7]); }
-    best = imax(best, imax(lo, -hi));
+    for (int k = 1; k < 5; ++k) { lo = imin(lo, p[(i + k) & 7]); hi = imax(hi, p[(i + k) & 7]); }
+    best = imax(best, imax(lo - c, c - hi));
   }
   return best;
 }
@@ -92,23 +97,21 @@ BRISK_HD int arc_contrast8(const int d[8]) {
 // The caller guarantees a 3-pixel margin.
 BRISK_HD int fast916(const uint8_t* img, int pitch, int x, int y) {
   const uint8_t* p = img + (long long)y * pitch + x;
-  const int c = p[0];
   int d[16];
-  d[0] = p[-3] - c;              d[1] = p[-3 - pitch] - c;      d[2] = p[-2 - 2 * pitch] - c;  d[3] = p[-1 - 3 * pitch] - c;
-  d[4] = p[-3 * pitch] - c;      d[5] = p[1 - 3 * pitch] - c;   d[6] = p[2 - 2 * pitch] - c;   d[7] = p[3 - pitch] - c;
-  d[8] = p[3] - c;               d[9] = p[3 + pitch] - c;       d[10] = p[2 + 2 * pitch] - c;  d[11] = p[1 + 3 * pitch] - c;
-  d[12] = p[3 * pitch] - c;      d[13] = p[-1 + 3 * pitch] - c; d[14] = p[-2 + 2 * pitch] - c; d[15] = p[-3 + pitch] - c;
-  return arc_contrast16(d) - 1;
+  d[0] = p[-3];              d[1] = p[-3 - pitch];      d[2] = p[-2 - 2 * pitch];  d[3] = p[-1 - 3 * pitch];
+  d[4] = p[-3 * pitch];      d[5] = p[1 - 3 * pitch];   d[6] = p[2 - 2 * pitch];   d[7] = p[3 - pitch];
+  d[8] = p[3];               d[9] = p[3 + pitch];       d[10] = p[2 + 2 * pitch];  d[11] = p[1 + 3 * pitch];
+  d[12] = p[3 * pitch];      d[13] = p[-1 + 3 * pitch]; d[14] = p[-2 + 2 * pitch]; d[15] = p[-3 + pitch];
+  return arc_contrast16(d, p[0]) - 1;
 }
 
 // AGAST 5-8 score (ring of agast/include/agast/agast5-8.h:68-77); 1-pixel margin.
 BRISK_HD int fast58(const uint8_t* img, int pitch, int x, int y) {
   const uint8_t* p = img + (long long)y * pitch + x;
-  const int c = p[0];
   int d[8];
-  d[0] = p[-1] - c;         d[1] = p[-1 - pitch] - c; d[2] = p[-pitch] - c;     d[3] = p[1 - pitch] - c;
-  d[4] = p[1] - c;          d[5] = p[1 + pitch] - c;  d[6] = p[pitch] - c;      d[7] = p[-1 + pitch] - c;
-  return arc_contrast8(d) - 1;
+  d[0] = p[-1];         d[1] = p[-1 - pitch]; d[2] = p[-pitch];     d[3] = p[1 - pitch];
+  d[4] = p[1];          d[5] = p[1 + pitch];  d[6] = p[pitch];      d[7] = p[-1 + pitch];
+  return arc_contrast8(d, p[0]) - 1;
 }
 
 // Segment test of OastDetector9_16::detect with the per-pixel adaptive threshold

@@ -1,0 +1,722 @@
+// C ABI of libbrisk_b200.so (see include/brisk_b200.h): contexts, detector /
+// extractor objects, chunked batch orchestration on one CUDA stream.
+#include "../../include/brisk_b200.h"
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "pattern.h"
+
+using namespace briskb200;
+
+static_assert(sizeof(brisk_keypoint) == 28 && sizeof(KeyPoint) == 28, "key point layout");
+
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct brisk_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  size_t ws_limit = (size_t)8 << 30;
+  bool timing = false;
+  float ms[BRISK_STAGE_COUNT] = {};
+  int64_t launches = 0;
+  cudaEvent_t ev[BRISK_STAGE_COUNT + 1] = {};
+  PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
+  DevBuf pyr, cm, bm, rowcnt, layer_start, corners, fwin, checks, kp_tmp, kp_valid, integral;
+  DevBuf kps, kps_scratch, scales, counts, desc, masks, flag, knn_q, knn_t, knn_keys, knn_part, knn_idx, knn_dist;
+};
+
+struct brisk_detector {
+  brisk_ctx* ctx;
+  int thresh, octaves, suppress;
+  int corner_cap;  // 0 = auto
+};
+
+struct brisk_extractor {
+  brisk_ctx* ctx;
+  PatternHost host;
+  DevBuf points, size_list, short_pairs, long_pairs, breaks;
+  PatternDev dev;
+};
+
+namespace {
+
+int fail(brisk_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define CU_OK(call)                                                                         \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess) {                                                               \
+      cudaGetLastError();                                                                   \
+      return fail(ctx, BRISK_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    }                                                                                       \
+  } while (0)
+
+bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// Layer sizes / scales of BriskScaleSpace::ConstructPyramid (reference
+// brisk-scale-space.cc:64-90) and BriskLayer's constructors (brisk-layer.cc:53-95).
+void build_geom(int w, int h, int octaves, PyramidGeom* g) {
+  memset(g, 0, sizeof(*g));
+  g->n_layers = octaves == 0 ? 1 : 2 * octaves;
+  g->w0 = w; g->h0 = h;
+  long long off = 0;
+  for (int i = 0; i < g->n_layers; ++i) {
+    LayerGeom& L = g->L[i];
+    if (i == 0) { L.w = w; L.h = h; L.scale = 1.0f; L.offset = 0.0f; }
+    else if (i == 1) { L.w = 2 * (w / 3); L.h = 2 * (h / 3); L.scale = (float)(g->L[0].scale * 1.5); L.offset = (float)(0.5 * L.scale - 0.5); }
+    else { L.w = g->L[i - 2].w / 2; L.h = g->L[i - 2].h / 2; L.scale = g->L[i - 2].scale * 2; L.offset = (float)(0.5 * L.scale - 0.5); }
+    L.pitch = align_up(std::max(L.w, 1), 16);
+    L.off = off;
+    off += (long long)L.pitch * std::max(L.h, 1);
+    off = (off + 255) / 256 * 256;
+  }
+  g->frame_elems = off;
+}
+
+struct Timer {
+  brisk_ctx* ctx;
+  explicit Timer(brisk_ctx* c) : ctx(c) {}
+  void mark(int i) { if (ctx->timing) cudaEventRecord(ctx->ev[i], ctx->stream); }
+};
+
+int encode_map(brisk_ctx* ctx, const void* base, int w, int h, int n, size_t pitch, size_t frame_stride, CUtensorMap* map) {
+  cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)frame_stride};
+  cuuint32_t box[3] = {192, 96, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, BRISK_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return BRISK_OK;
+}
+
+struct Plan {
+  PyramidGeom g;
+  DetectWorkspace ws;
+  int chunk;
+  size_t integral_elems;  // per frame
+};
+
+int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* ext, int n, int w, int h, int cap, Plan* plan) {
+  const int octaves = det ? det->octaves : 0;
+  build_geom(w, h, octaves, &plan->g);
+  const PyramidGeom& g = plan->g;
+  DetectWorkspace& ws = plan->ws;
+  memset(&ws, 0, sizeof(ws));
+  ws.total_rows = 0;
+  for (int i = 0; i < g.n_layers; ++i) { ws.row_off[i] = ws.total_rows; ws.total_rows += g.L[i].h; }
+  ws.row_off[g.n_layers] = ws.total_rows;
+  int ccap = det ? det->corner_cap : 0;
+  if (ccap <= 0) ccap = std::min(std::max((int)(((long long)w * h) / 24), 4096), 1 << 20);
+  ws.corner_cap = det ? ccap : 0;
+  plan->integral_elems = ext ? (size_t)(w + 1) * (h + 1) : 0;
+  const int desc_bytes = ext ? ext->dev.desc_bytes : 0;
+  size_t per_frame = (size_t)g.frame_elems;  // image planes
+  if (det) per_frame += (size_t)g.frame_elems * 3 + (size_t)ws.total_rows * 4 + (size_t)ws.corner_cap * (4 + 32 + 24 + 28 + 1);
+  per_frame += plan->integral_elems * 4 + (size_t)cap * (28 * 2 + 4 + desc_bytes) + (size_t)w * h /* mask */;
+  long long chunk = (long long)(ctx->ws_limit / std::max<size_t>(per_frame, 1));
+  if (chunk < 1) chunk = 1;
+  if (chunk > n) chunk = n;
+  if (chunk > 32768) chunk = 32768;
+  plan->chunk = (int)chunk;
+  const size_t c = (size_t)plan->chunk;
+  CU_OK(ctx->pyr.ensure(c * g.frame_elems));
+  if (det) {
+    CU_OK(ctx->cm.ensure(c * g.frame_elems * 2));
+    CU_OK(ctx->bm.ensure(c * g.frame_elems));
+    CU_OK(ctx->rowcnt.ensure(c * ws.total_rows * 4));
+    CU_OK(ctx->layer_start.ensure(c * (kMaxLayers + 1) * 4));
+    CU_OK(ctx->corners.ensure(c * ws.corner_cap * 4));
+    CU_OK(ctx->fwin.ensure(c * ws.corner_cap * 32));
+    CU_OK(ctx->checks.ensure(c * ws.corner_cap * 24));
+    CU_OK(ctx->kp_tmp.ensure(c * ws.corner_cap * 28));
+    CU_OK(ctx->kp_valid.ensure(c * ws.corner_cap));
+  }
+  if (ext) {
+    CU_OK(ctx->integral.ensure(c * plan->integral_elems * 4));
+    CU_OK(ctx->kps_scratch.ensure(c * cap * 28));
+    CU_OK(ctx->scales.ensure(c * cap * 4));
+  }
+  CU_OK(ctx->flag.ensure(16));
+  ws.pyr = ctx->pyr.as<uint8_t>(); ws.cm = ctx->cm.as<uint16_t>(); ws.bm = ctx->bm.as<uint8_t>();
+  ws.rowcnt = ctx->rowcnt.as<int>(); ws.layer_start = ctx->layer_start.as<int>(); ws.corners = ctx->corners.as<uint32_t>();
+  ws.fwin = ctx->fwin.as<uint8_t>(); ws.checks = ctx->checks.as<float>(); ws.kp_tmp = ctx->kp_tmp.as<KeyPoint>();
+  ws.kp_valid = ctx->kp_valid.as<uint8_t>();
+  return BRISK_OK;
+}
+
+// Bring `count` frames starting at `imgs` into the pyramid block (layer 0 of
+// every frame) or, when they already sit in device memory with TMA-compatible
+// alignment, describe them in place.  Returns the tensor map the pyramid
+// kernel reads and whether it has to materialise layer 0 in the block.
+int stage_input(brisk_ctx* ctx, const Plan& plan, const uint8_t* imgs, int count, int w, int h, size_t stride,
+                size_t frame_pitch, CUtensorMap* map, int* write_l0) {
+  const PyramidGeom& g = plan.g;
+  const bool dev = is_device_ptr(imgs);
+  const bool aligned = dev && ((uintptr_t)imgs % 16 == 0) && (stride % 16 == 0) && (frame_pitch % 16 == 0);
+  if (aligned) {
+    *write_l0 = 1;
+    return encode_map(ctx, imgs, w, h, count, stride, frame_pitch, map);
+  }
+  for (int f = 0; f < count; ++f)
+    CU_OK(cudaMemcpy2DAsync(ctx->pyr.as<uint8_t>() + (size_t)f * g.frame_elems + g.L[0].off, g.L[0].pitch,
+                            imgs + (size_t)f * frame_pitch, stride, w, h, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                            ctx->stream));
+  *write_l0 = 0;
+  return encode_map(ctx, ctx->pyr.as<uint8_t>() + g.L[0].off, w, h, count, g.L[0].pitch, (size_t)g.frame_elems, map);
+}
+
+int check_image_args(brisk_ctx* ctx, const uint8_t* imgs, int n, int w, int h, size_t stride, size_t frame_pitch) {
+  if (!ctx) return BRISK_ERR_INVALID;
+  if (!imgs || n < 0 || w <= 0 || h <= 0) return fail(ctx, BRISK_ERR_INVALID, "bad image arguments");
+  if (stride < (size_t)w || (n > 1 && frame_pitch < stride * (size_t)h)) return fail(ctx, BRISK_ERR_INVALID, "bad image strides");
+  if (w > 8191 || h > 8191) return fail(ctx, BRISK_ERR_UNSUPPORTED, "images larger than 8191 pixels per side are not supported");
+  return BRISK_OK;
+}
+
+// Core batch driver: detect and/or describe, chunk by chunk.
+int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const uint8_t* imgs, int n, int w, int h,
+              size_t stride, size_t frame_pitch, const uint8_t* masks, brisk_keypoint* kps, int32_t* counts, int cap,
+              uint8_t* desc) {
+  int rc = check_image_args(ctx, imgs, n, w, h, stride, frame_pitch);
+  if (rc) return rc;
+  if (!kps || !counts || cap <= 0 || (ext && !desc)) return fail(ctx, BRISK_ERR_INVALID, "bad output arguments");
+  CU_OK(cudaSetDevice(ctx->device));
+  memset(ctx->ms, 0, sizeof(ctx->ms));
+  ctx->launches = 0;
+  if (n == 0) return BRISK_OK;
+  if (det) {
+    if (det->thresh < 30 || det->thresh > 255)
+      return fail(ctx, BRISK_ERR_UNSUPPORTED, "AGAST threshold must be in [30, 255] (lower values make corner scores <= 2, whose cache semantics are not implemented)");
+    if (det->octaves < 0 || 2 * det->octaves > kMaxLayers) return fail(ctx, BRISK_ERR_UNSUPPORTED, "octaves must be in [0, 6]");
+    if (!det->suppress) return fail(ctx, BRISK_ERR_UNSUPPORTED, "suppressScaleNonmaxima=false is not implemented");
+  }
+  {
+    PyramidGeom probe;
+    build_geom(w, h, det ? det->octaves : 0, &probe);
+    for (int i = 0; i < probe.n_layers; ++i)
+      if (probe.L[i].w < 8 || probe.L[i].h < 8) return fail(ctx, BRISK_ERR_INVALID, "image too small: every pyramid layer must be at least 8x8");
+  }
+  Plan plan;
+  rc = make_plan(ctx, det, ext, n, w, h, cap, &plan);
+  if (rc) return rc;
+  const PyramidGeom& g = plan.g;
+  const int desc_bytes = ext ? ext->dev.desc_bytes : 0;
+  const bool kps_dev = is_device_ptr(kps), counts_dev = is_device_ptr(counts), desc_dev = desc && is_device_ptr(desc);
+  const bool masks_dev = masks && is_device_ptr(masks);
+  if (!kps_dev) CU_OK(ctx->kps.ensure((size_t)plan.chunk * cap * 28));
+  if (!counts_dev) CU_OK(ctx->counts.ensure((size_t)plan.chunk * 4));
+  if (ext && !desc_dev) CU_OK(ctx->desc.ensure((size_t)plan.chunk * cap * desc_bytes));
+  if (det && masks && !masks_dev) CU_OK(ctx->masks.ensure((size_t)plan.chunk * w * h));
+  std::vector<int32_t> hcounts(plan.chunk);
+  bool truncated = false, corner_overflow = false;
+  Timer tm(ctx);
+
+  for (int f0 = 0; f0 < n; f0 += plan.chunk) {
+    const int c = std::min(plan.chunk, n - f0);
+    KeyPoint* d_kps = kps_dev ? reinterpret_cast<KeyPoint*>(kps) + (size_t)f0 * cap : ctx->kps.as<KeyPoint>();
+    int* d_counts = counts_dev ? counts + f0 : ctx->counts.as<int>();
+    uint8_t* d_desc = ext ? (desc_dev ? desc + (size_t)f0 * cap * desc_bytes : ctx->desc.as<uint8_t>()) : nullptr;
+
+    tm.mark(0);
+    CUtensorMap map;
+    int write_l0 = 0;
+    rc = stage_input(ctx, plan, imgs + (size_t)f0 * frame_pitch, c, w, h, stride, frame_pitch, &map, &write_l0);
+    if (rc) return rc;
+    const uint8_t* d_masks = nullptr;
+    long long mask_fs = 0; int mask_pitch = 0;
+    if (det && masks) {
+      if (masks_dev) { d_masks = masks + (size_t)f0 * frame_pitch; mask_fs = (long long)frame_pitch; mask_pitch = (int)stride; }
+      else {
+        for (int f = 0; f < c; ++f)
+          CU_OK(cudaMemcpy2DAsync(ctx->masks.as<uint8_t>() + (size_t)f * w * h, w, masks + (size_t)(f0 + f) * frame_pitch, stride, w, h,
+                                  cudaMemcpyHostToDevice, ctx->stream));
+        d_masks = ctx->masks.as<uint8_t>(); mask_fs = (long long)w * h; mask_pitch = w;
+      }
+    }
+    if (!det) {
+      // describe only: key points come from the caller
+      if (!kps_dev) CU_OK(cudaMemcpyAsync(d_kps, kps + (size_t)f0 * cap, (size_t)c * cap * 28, cudaMemcpyHostToDevice, ctx->stream));
+      if (!counts_dev) CU_OK(cudaMemcpyAsync(d_counts, counts + f0, (size_t)c * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    tm.mark(1);
+    if (det || write_l0) {
+      CU_OK(launch_pyramid(map, g, plan.ws.pyr, c, write_l0, ctx->stream));
+      ctx->launches += 1;
+    }
+    tm.mark(2);
+    if (det) {
+      CU_OK(cudaMemsetAsync(ctx->flag.p, 0, 16, ctx->stream));
+      CU_OK(launch_agast_detect(g, plan.ws, c, det->thresh, ctx->stream));
+      ctx->launches += g.n_layers;
+      tm.mark(3);
+      CU_OK(launch_corner_lists(g, plan.ws, c, ctx->flag.as<int>(), ctx->stream));
+      ctx->launches += 1 + g.n_layers;
+      tm.mark(4);
+      CU_OK(launch_agast_nms(g, plan.ws, c, d_masks, mask_fs, mask_pitch, d_kps, d_counts, cap, ctx->stream));
+      ctx->launches += 5;
+    } else {
+      tm.mark(3); tm.mark(4);
+    }
+    tm.mark(5);
+    if (ext) {
+      const uint8_t* l0 = plan.ws.pyr + g.L[0].off;
+      CU_OK(launch_integral(l0, g.frame_elems, g.L[0].pitch, w, h, c, ctx->integral.as<int32_t>(), ctx->stream));
+      ctx->launches += 2;
+      tm.mark(6);
+      CU_OK(launch_describe(ext->dev, l0, g.frame_elems, g.L[0].pitch, w, h, c, ctx->integral.as<int32_t>(), d_kps, d_counts, cap,
+                            ctx->kps_scratch.as<KeyPoint>(), ctx->scales.as<int>(), d_desc, ctx->stream));
+      ctx->launches += 2;
+    } else {
+      tm.mark(6);
+    }
+    tm.mark(7);
+    // results
+    int hflag = 0;
+    if (det) CU_OK(cudaMemcpyAsync(&hflag, ctx->flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    const bool need_host_counts = !counts_dev || !kps_dev || (ext && !desc_dev);
+    if (need_host_counts) {
+      CU_OK(cudaMemcpyAsync(hcounts.data(), d_counts, (size_t)c * 4, cudaMemcpyDeviceToHost, ctx->stream));
+      CU_OK(cudaStreamSynchronize(ctx->stream));
+      if (!counts_dev) memcpy(counts + f0, hcounts.data(), (size_t)c * 4);
+      for (int f = 0; f < c; ++f) {
+        const int m = std::min(hcounts[f], cap);
+        if (hcounts[f] > cap) truncated = true;
+        if (m <= 0) continue;
+        if (!kps_dev) CU_OK(cudaMemcpyAsync(kps + (size_t)(f0 + f) * cap, d_kps + (size_t)f * cap, (size_t)m * 28, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ext && !desc_dev) CU_OK(cudaMemcpyAsync(desc + (size_t)(f0 + f) * cap * desc_bytes, d_desc + (size_t)f * cap * desc_bytes, (size_t)m * desc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+      }
+    }
+    tm.mark(8);
+    CU_OK(cudaStreamSynchronize(ctx->stream));
+    if (hflag) corner_overflow = true;
+    if (ctx->timing) {
+      static const int stage_of[8] = {BRISK_STAGE_H2D, BRISK_STAGE_PYRAMID, BRISK_STAGE_DETECT, BRISK_STAGE_LISTS, BRISK_STAGE_NMS,
+                                      BRISK_STAGE_INTEGRAL, BRISK_STAGE_DESCRIBE, BRISK_STAGE_D2H};
+      for (int i = 0; i < 8; ++i) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) ctx->ms[stage_of[i]] += ms; else cudaGetLastError();
+      }
+    }
+  }
+  if (corner_overflow) return fail(ctx, BRISK_ERR_CAPACITY, "raw corner capacity exceeded; raise it with brisk_detector_set_corner_capacity");
+  if (truncated) return fail(ctx, BRISK_ERR_CAPACITY, "key point capacity (cap) exceeded; counts hold the true numbers");
+  return BRISK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int brisk_ctx_create(int device, void* stream, brisk_ctx** out) {
+  if (!out) return BRISK_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) { cudaGetLastError(); return BRISK_ERR_CUDA; }
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return BRISK_ERR_CUDA; }
+  brisk_ctx* ctx = new brisk_ctx;
+  ctx->device = device;
+  if (stream) { ctx->stream = reinterpret_cast<cudaStream_t>(stream); ctx->own_stream = false; }
+  else {
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete ctx; return BRISK_ERR_CUDA; }
+    ctx->own_stream = true;
+  }
+  for (auto& e : ctx->ev) cudaEventCreate(&e);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+    cudaGetLastError();
+    brisk_ctx_destroy(ctx);
+    return BRISK_ERR_CUDA;
+  }
+  ctx->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  *out = ctx;
+  return BRISK_OK;
+}
+
+void brisk_ctx_destroy(brisk_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->pyr, &ctx->cm, &ctx->bm, &ctx->rowcnt, &ctx->layer_start, &ctx->corners, &ctx->fwin, &ctx->checks,
+                    &ctx->kp_tmp, &ctx->kp_valid, &ctx->integral, &ctx->kps, &ctx->kps_scratch, &ctx->scales, &ctx->counts,
+                    &ctx->desc, &ctx->masks, &ctx->flag, &ctx->knn_q, &ctx->knn_t, &ctx->knn_keys, &ctx->knn_part,
+                    &ctx->knn_idx, &ctx->knn_dist};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* brisk_last_error(const brisk_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int brisk_sync(brisk_ctx* ctx) {
+  if (!ctx) return BRISK_ERR_INVALID;
+  CU_OK(cudaStreamSynchronize(ctx->stream));
+  return BRISK_OK;
+}
+
+int brisk_ctx_set_workspace_limit(brisk_ctx* ctx, size_t bytes) {
+  if (!ctx || bytes < ((size_t)64 << 20)) return BRISK_ERR_INVALID;
+  ctx->ws_limit = bytes;
+  return BRISK_OK;
+}
+
+int brisk_ctx_enable_timing(brisk_ctx* ctx, int enable) {
+  if (!ctx) return BRISK_ERR_INVALID;
+  ctx->timing = enable != 0;
+  return BRISK_OK;
+}
+
+int brisk_ctx_last_timing(brisk_ctx* ctx, float* ms, int64_t* launches) {
+  if (!ctx) return BRISK_ERR_INVALID;
+  if (ms) memcpy(ms, ctx->ms, sizeof(ctx->ms));
+  if (launches) *launches = ctx->launches;
+  return BRISK_OK;
+}
+
+int brisk_agast_detector_create(brisk_ctx* ctx, int thresh, int octaves, int suppress, brisk_detector** out) {
+  if (!ctx || !out) return BRISK_ERR_INVALID;
+  *out = new brisk_detector{ctx, thresh, octaves, suppress, 0};
+  return BRISK_OK;
+}
+
+void brisk_detector_destroy(brisk_detector* det) { delete det; }
+
+int brisk_detector_set_corner_capacity(brisk_detector* det, int corners_per_frame) {
+  if (!det || corners_per_frame < 0) return BRISK_ERR_INVALID;
+  det->corner_cap = corners_per_frame;
+  return BRISK_OK;
+}
+
+int brisk_extractor_create(brisk_ctx* ctx, int rot, int scale, int version, float pattern_scale, const char* pattern_file,
+                           brisk_extractor** out) {
+  if (!ctx || !out) return BRISK_ERR_INVALID;
+  *out = nullptr;
+  CU_OK(cudaSetDevice(ctx->device));
+  brisk_extractor* ext = new brisk_extractor;
+  ext->ctx = ctx;
+  const std::string msg = build_pattern(version, pattern_scale, pattern_file, &ext->host);
+  if (!msg.empty()) { delete ext; return fail(ctx, BRISK_ERR_INVALID, msg); }
+  const PatternHost& ph = ext->host;
+  if (ph.n_points > 96 || ph.desc_bytes <= 0 || ph.desc_bytes > 256) { delete ext; return fail(ctx, BRISK_ERR_UNSUPPORTED, "pattern too large"); }
+  struct Up { DevBuf* b; const void* src; size_t bytes; };
+  const Up ups[] = {{&ext->points, ph.points.data(), ph.points.size() * 4}, {&ext->size_list, ph.size_list, sizeof(ph.size_list)},
+                    {&ext->short_pairs, ph.short_pairs.data(), ph.short_pairs.size() * 2}, {&ext->long_pairs, ph.long_pairs.data(), ph.long_pairs.size() * 4},
+                    {&ext->breaks, ph.scale_breaks, sizeof(ph.scale_breaks)}};
+  for (const Up& u : ups) {
+    cudaError_t e = u.b->ensure(std::max<size_t>(u.bytes, 16));
+    if (e == cudaSuccess && u.bytes) e = cudaMemcpy(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaGetLastError(); brisk_extractor_destroy(ext); return fail(ctx, BRISK_ERR_CUDA, cudaGetErrorString(e)); }
+  }
+  PatternDev& d = ext->dev;
+  d.points = ext->points.as<float>(); d.size_list = ext->size_list.as<unsigned int>();
+  d.short_pairs = ext->short_pairs.as<unsigned short>(); d.long_pairs = ext->long_pairs.as<int>();
+  d.scale_breaks = ext->breaks.as<float>();
+  d.n_points = ph.n_points; d.n_short = (int)ph.short_pairs.size() / 2; d.n_long = (int)ph.long_pairs.size() / 4;
+  d.desc_bytes = ph.desc_bytes; d.rot_inv = rot != 0; d.scale_inv = scale != 0; d.basic_scale = ph.basic_scale;
+  *out = ext;
+  return BRISK_OK;
+}
+
+void brisk_extractor_destroy(brisk_extractor* ext) {
+  if (!ext) return;
+  cudaSetDevice(ext->ctx->device);
+  ext->points.release(); ext->size_list.release(); ext->short_pairs.release(); ext->long_pairs.release(); ext->breaks.release();
+  delete ext;
+}
+
+int brisk_extractor_descriptor_size(const brisk_extractor* ext) { return ext ? ext->dev.desc_bytes : BRISK_ERR_INVALID; }
+
+int brisk_extractor_pattern(const brisk_extractor* ext, int32_t counts[4], float* points_xys, float* scale_list,
+                            uint32_t* size_list, uint32_t* short_pairs, int32_t* long_pairs) {
+  if (!ext) return BRISK_ERR_INVALID;
+  const PatternHost& ph = ext->host;
+  if (counts) { counts[0] = ph.n_points; counts[1] = (int)ph.short_pairs.size() / 2; counts[2] = (int)ph.long_pairs.size() / 4; counts[3] = ph.desc_bytes; }
+  if (points_xys) memcpy(points_xys, ph.points.data(), ph.points.size() * 4);
+  if (scale_list) memcpy(scale_list, ph.scale_list, sizeof(ph.scale_list));
+  if (size_list) memcpy(size_list, ph.size_list, sizeof(ph.size_list));
+  if (short_pairs) for (size_t i = 0; i < ph.short_pairs.size(); ++i) short_pairs[i] = ph.short_pairs[i];
+  if (long_pairs) memcpy(long_pairs, ph.long_pairs.data(), ph.long_pairs.size() * 4);
+  return BRISK_OK;
+}
+
+int brisk_detect(brisk_ctx* ctx, brisk_detector* det, const uint8_t* imgs, int n, int w, int h, size_t stride,
+                 size_t frame_pitch, const uint8_t* masks, brisk_keypoint* kps, int32_t* counts, int cap) {
+  if (!ctx || !det || det->ctx != ctx) return fail(ctx, BRISK_ERR_INVALID, "detector does not belong to this context");
+  return run_batch(ctx, det, nullptr, imgs, n, w, h, stride, frame_pitch, masks, kps, counts, cap, nullptr);
+}
+
+int brisk_describe(brisk_ctx* ctx, brisk_extractor* ext, const uint8_t* imgs, int n, int w, int h, size_t stride,
+                   size_t frame_pitch, brisk_keypoint* kps, int32_t* counts, int cap, uint8_t* desc) {
+  if (!ctx || !ext || ext->ctx != ctx) return fail(ctx, BRISK_ERR_INVALID, "extractor does not belong to this context");
+  return run_batch(ctx, nullptr, ext, imgs, n, w, h, stride, frame_pitch, nullptr, kps, counts, cap, desc);
+}
+
+int brisk_detect_describe(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const uint8_t* imgs, int n, int w,
+                          int h, size_t stride, size_t frame_pitch, const uint8_t* masks, brisk_keypoint* kps,
+                          int32_t* counts, int cap, uint8_t* desc) {
+  if (!ctx || !det || !ext || det->ctx != ctx || ext->ctx != ctx) return fail(ctx, BRISK_ERR_INVALID, "detector / extractor do not belong to this context");
+  return run_batch(ctx, det, ext, imgs, n, w, h, stride, frame_pitch, masks, kps, counts, cap, desc);
+}
+
+int brisk_debug_pyramid(brisk_ctx* ctx, int octaves, const uint8_t* img, int w, int h, size_t stride, uint8_t* out,
+                        int32_t* dims, int* n_layers) {
+  int rc = check_image_args(ctx, img, 1, w, h, stride, stride * (size_t)h);
+  if (rc) return rc;
+  if (octaves < 0 || 2 * octaves > kMaxLayers) return fail(ctx, BRISK_ERR_UNSUPPORTED, "octaves must be in [0, 6]");
+  CU_OK(cudaSetDevice(ctx->device));
+  brisk_detector det{ctx, 60, octaves, 1, 4096};
+  Plan plan;
+  rc = make_plan(ctx, &det, nullptr, 1, w, h, 1, &plan);
+  if (rc) return rc;
+  CUtensorMap map; int write_l0;
+  rc = stage_input(ctx, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
+  if (rc) return rc;
+  CU_OK(launch_pyramid(map, plan.g, plan.ws.pyr, 1, write_l0, ctx->stream));
+  size_t off = 0;
+  for (int i = 0; i < plan.g.n_layers; ++i) {
+    const LayerGeom& L = plan.g.L[i];
+    if (dims) { dims[2 * i] = L.w; dims[2 * i + 1] = L.h; }
+    if (out && L.w > 0 && L.h > 0)
+      CU_OK(cudaMemcpy2DAsync(out + off, L.w, plan.ws.pyr + L.off, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, ctx->stream));
+    off += (size_t)L.w * L.h;
+  }
+  if (n_layers) *n_layers = plan.g.n_layers;
+  CU_OK(cudaStreamSynchronize(ctx->stream));
+  return BRISK_OK;
+}
+
+int brisk_debug_integral(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, int32_t* out) {
+  int rc = check_image_args(ctx, img, 1, w, h, stride, stride * (size_t)h);
+  if (rc) return rc;
+  if (!out) return fail(ctx, BRISK_ERR_INVALID, "null output");
+  CU_OK(cudaSetDevice(ctx->device));
+  Plan plan;
+  rc = make_plan(ctx, nullptr, nullptr, 1, w, h, 1, &plan);
+  if (rc) return rc;
+  CU_OK(ctx->integral.ensure((size_t)(w + 1) * (h + 1) * 4));
+  CUtensorMap map; int write_l0;
+  rc = stage_input(ctx, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
+  if (rc) return rc;
+  CU_OK(launch_pyramid(map, plan.g, plan.ws.pyr, 1, write_l0, ctx->stream));
+  CU_OK(launch_integral(plan.ws.pyr + plan.g.L[0].off, plan.g.frame_elems, plan.g.L[0].pitch, w, h, 1, ctx->integral.as<int32_t>(), ctx->stream));
+  CU_OK(cudaMemcpyAsync(out, ctx->integral.p, (size_t)(w + 1) * (h + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_OK(cudaStreamSynchronize(ctx->stream));
+  return BRISK_OK;
+}
+
+int brisk_debug_corners(brisk_ctx* ctx, brisk_detector* det, const uint8_t* img, int w, int h, size_t stride,
+                        int32_t* corners_xys, int cap, int32_t* layer_counts) {
+  int rc = check_image_args(ctx, img, 1, w, h, stride, stride * (size_t)h);
+  if (rc) return rc;
+  if (!det || !corners_xys) return fail(ctx, BRISK_ERR_INVALID, "null argument");
+  CU_OK(cudaSetDevice(ctx->device));
+  Plan plan;
+  rc = make_plan(ctx, det, nullptr, 1, w, h, 1, &plan);
+  if (rc) return rc;
+  CUtensorMap map; int write_l0;
+  rc = stage_input(ctx, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
+  if (rc) return rc;
+  CU_OK(launch_pyramid(map, plan.g, plan.ws.pyr, 1, write_l0, ctx->stream));
+  CU_OK(cudaMemsetAsync(ctx->flag.p, 0, 16, ctx->stream));
+  CU_OK(launch_agast_detect(plan.g, plan.ws, 1, det->thresh, ctx->stream));
+  CU_OK(launch_corner_lists(plan.g, plan.ws, 1, ctx->flag.as<int>(), ctx->stream));
+  std::vector<int> ls(kMaxLayers + 1);
+  CU_OK(cudaMemcpyAsync(ls.data(), plan.ws.layer_start, ls.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_OK(cudaStreamSynchronize(ctx->stream));
+  const int total = std::min(ls[plan.g.n_layers], plan.ws.corner_cap);
+  std::vector<uint32_t> packed(std::max(total, 1));
+  std::vector<uint16_t> cm((size_t)plan.g.frame_elems);
+  CU_OK(cudaMemcpy(packed.data(), plan.ws.corners, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  CU_OK(cudaMemcpy(cm.data(), plan.ws.cm, cm.size() * 2, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < total && i < cap; ++i) {
+    const int x = packed[i] & 0x1fff, y = (packed[i] >> 13) & 0x1fff, l = packed[i] >> 26;
+    corners_xys[3 * i] = x; corners_xys[3 * i + 1] = y;
+    corners_xys[3 * i + 2] = cm[(size_t)plan.g.L[l].off + (size_t)y * plan.g.L[l].pitch + x] & kCmT;
+  }
+  if (layer_counts) for (int l = 0; l < plan.g.n_layers; ++l) layer_counts[l] = ls[l + 1] - ls[l];
+  return total;
+}
+
+int brisk_debug_scores(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, uint8_t* out916, uint8_t* out58) {
+  int rc = check_image_args(ctx, img, 1, w, h, stride, stride * (size_t)h);
+  if (rc) return rc;
+  if (!out916 || !out58) return fail(ctx, BRISK_ERR_INVALID, "null output");
+  CU_OK(cudaSetDevice(ctx->device));
+  Plan plan;
+  rc = make_plan(ctx, nullptr, nullptr, 1, w, h, 1, &plan);
+  if (rc) return rc;
+  CU_OK(ctx->kps.ensure((size_t)w * h * 2));
+  CUtensorMap map; int write_l0;
+  rc = stage_input(ctx, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
+  if (rc) return rc;
+  CU_OK(launch_pyramid(map, plan.g, plan.ws.pyr, 1, write_l0, ctx->stream));
+  uint8_t* d916 = ctx->kps.as<uint8_t>();
+  uint8_t* d58 = d916 + (size_t)w * h;
+  CU_OK(launch_dense_scores(plan.g.L[0], plan.ws.pyr + plan.g.L[0].off, d916, d58, ctx->stream));
+  CU_OK(cudaMemcpyAsync(out916, d916, (size_t)w * h, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_OK(cudaMemcpyAsync(out58, d58, (size_t)w * h, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_OK(cudaStreamSynchronize(ctx->stream));
+  return BRISK_OK;
+}
+
+int brisk_debug_nms_state(brisk_ctx* ctx, brisk_detector* det, const uint8_t* img, int w, int h, size_t stride,
+                          uint16_t* cm_out, uint8_t* bm_out) {
+  if (!ctx || !det) return BRISK_ERR_INVALID;
+  std::vector<brisk_keypoint> kps(1 << 16);
+  int32_t count = 0;
+  int rc = run_batch(ctx, det, nullptr, img, 1, w, h, stride, stride * (size_t)h, nullptr, kps.data(), &count, (int)kps.size(), nullptr);
+  if (rc) return rc;
+  PyramidGeom g;
+  build_geom(w, h, det->octaves, &g);
+  size_t off = 0;
+  for (int i = 0; i < g.n_layers; ++i) {
+    const LayerGeom& L = g.L[i];
+    if (cm_out) CU_OK(cudaMemcpy2D(cm_out + off, (size_t)L.w * 2, ctx->cm.as<uint16_t>() + L.off, (size_t)L.pitch * 2, (size_t)L.w * 2, L.h, cudaMemcpyDeviceToHost));
+    if (bm_out) CU_OK(cudaMemcpy2D(bm_out + off, L.w, ctx->bm.as<uint8_t>() + L.off, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    off += (size_t)L.w * L.h;
+  }
+  return count;
+}
+
+// ---------------------------------------------------------------------------
+// Hamming matching.
+// ---------------------------------------------------------------------------
+
+static int knn_keys_impl(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int desc_bytes,
+                         int k, int64_t offset, unsigned long long** keys_out, int* kr_out) {
+  if (!ctx) return BRISK_ERR_INVALID;
+  if (!query || !train || nq < 0 || nt < 0 || k < 1 || k > 8) return fail(ctx, BRISK_ERR_INVALID, "bad kNN arguments (1 <= k <= 8)");
+  if (desc_bytes != 48 && desc_bytes != 64 && desc_bytes != 128) return fail(ctx, BRISK_ERR_UNSUPPORTED, "descriptor size must be 48, 64 or 128 bytes");
+  if (offset + nt > 0xffffffffll) return fail(ctx, BRISK_ERR_UNSUPPORTED, "train index does not fit 32 bits");
+  CU_OK(cudaSetDevice(ctx->device));
+  const uint8_t* dq = query; const uint8_t* dt = train;
+  if (!is_device_ptr(query) || (uintptr_t)query % 16) {
+    CU_OK(ctx->knn_q.ensure(std::max<size_t>((size_t)nq * desc_bytes, 16)));
+    CU_OK(cudaMemcpyAsync(ctx->knn_q.p, query, (size_t)nq * desc_bytes, cudaMemcpyDefault, ctx->stream));
+    dq = ctx->knn_q.as<uint8_t>();
+  }
+  if (!is_device_ptr(train) || (uintptr_t)train % 16) {
+    CU_OK(ctx->knn_t.ensure(std::max<size_t>((size_t)nt * desc_bytes, 16)));
+    CU_OK(cudaMemcpyAsync(ctx->knn_t.p, train, (size_t)nt * desc_bytes, cudaMemcpyDefault, ctx->stream));
+    dt = ctx->knn_t.as<uint8_t>();
+  }
+  const int kr = knn_round_k(k);
+  const int splits = knn_num_splits(nq, nt);
+  CU_OK(ctx->knn_keys.ensure(std::max<size_t>((size_t)nq * kr * 8, 16)));
+  if (splits > 1) CU_OK(ctx->knn_part.ensure((size_t)splits * nq * kr * 8));
+  if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
+  CU_OK(launch_hamming_knn_ex(dq, nq, dt, nt, desc_bytes, k, offset, ctx->knn_keys.as<unsigned long long>(),
+                              ctx->knn_part.as<unsigned long long>(), splits, ctx->stream));
+  if (ctx->timing) cudaEventRecord(ctx->ev[1], ctx->stream);
+  ctx->launches = splits > 1 ? 2 : 1;
+  *keys_out = ctx->knn_keys.as<unsigned long long>();
+  *kr_out = kr;
+  return BRISK_OK;
+}
+
+// keys [nq][kr] (device) -> idx/dist [nq][k] in host or device memory
+static int knn_emit(brisk_ctx* ctx, const unsigned long long* keys, int64_t nq, int kr, int k, int32_t* idx, int32_t* dist) {
+  if (!idx || !dist) return fail(ctx, BRISK_ERR_INVALID, "null output");
+  if (nq == 0) return BRISK_OK;
+  CU_OK(ctx->knn_idx.ensure((size_t)nq * kr * 4));
+  CU_OK(ctx->knn_dist.ensure((size_t)nq * kr * 4));
+  CU_OK(launch_knn_unpack(keys, nq * kr, ctx->knn_idx.as<int32_t>(), ctx->knn_dist.as<int32_t>(), ctx->stream));
+  ctx->launches += 1;
+  CU_OK(cudaMemcpy2DAsync(idx, (size_t)k * 4, ctx->knn_idx.p, (size_t)kr * 4, (size_t)k * 4, (size_t)nq, cudaMemcpyDefault, ctx->stream));
+  CU_OK(cudaMemcpy2DAsync(dist, (size_t)k * 4, ctx->knn_dist.p, (size_t)kr * 4, (size_t)k * 4, (size_t)nq, cudaMemcpyDefault, ctx->stream));
+  CU_OK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->timing) {
+    float ms = 0;
+    memset(ctx->ms, 0, sizeof(ctx->ms));
+    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->ms[BRISK_STAGE_KNN] = ms; else cudaGetLastError();
+  }
+  return BRISK_OK;
+}
+
+int brisk_hamming_knn(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int desc_bytes,
+                      int k, int32_t* idx, int32_t* dist) {
+  unsigned long long* keys = nullptr; int kr = 0;
+  int rc = knn_keys_impl(ctx, query, nq, train, nt, desc_bytes, k, 0, &keys, &kr);
+  if (rc) return rc;
+  return knn_emit(ctx, keys, nq, kr, k, idx, dist);
+}
+
+int brisk_hamming_knn_keys(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train_shard, int64_t nt,
+                           int desc_bytes, int k, int64_t global_train_offset, uint64_t* keys_dev) {
+  if (!keys_dev || !is_device_ptr(keys_dev)) return fail(ctx, BRISK_ERR_INVALID, "keys_dev must be device memory");
+  if (k != knn_round_k(k)) return fail(ctx, BRISK_ERR_UNSUPPORTED, "sharded kNN supports k in {1, 2, 4, 8}");
+  unsigned long long* keys = nullptr; int kr = 0;
+  int rc = knn_keys_impl(ctx, query, nq, train_shard, nt, desc_bytes, k, global_train_offset, &keys, &kr);
+  if (rc) return rc;
+  CU_OK(cudaMemcpyAsync(keys_dev, keys, (size_t)nq * kr * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU_OK(cudaStreamSynchronize(ctx->stream));
+  return BRISK_OK;
+}
+
+int brisk_knn_merge_keys(brisk_ctx* ctx, const uint64_t* gathered_keys_dev, int n_shards, int64_t nq, int k, int32_t* idx,
+                         int32_t* dist) {
+  if (!ctx) return BRISK_ERR_INVALID;
+  if (!gathered_keys_dev || n_shards < 1 || nq < 0 || k != knn_round_k(k) || k > 8) return fail(ctx, BRISK_ERR_INVALID, "bad merge arguments");
+  CU_OK(cudaSetDevice(ctx->device));
+  CU_OK(ctx->knn_keys.ensure(std::max<size_t>((size_t)nq * k * 8, 16)));
+  CU_OK(launch_knn_merge(reinterpret_cast<const unsigned long long*>(gathered_keys_dev), n_shards, nq, k, ctx->knn_keys.as<unsigned long long>(), ctx->stream));
+  ctx->launches = 1;
+  if (ctx->timing) { cudaEventRecord(ctx->ev[0], ctx->stream); cudaEventRecord(ctx->ev[1], ctx->stream); }
+  return knn_emit(ctx, ctx->knn_keys.as<unsigned long long>(), nq, k, k, idx, dist);
+}
+
+int brisk_hamming_distance(brisk_ctx* ctx, const uint8_t* a, const uint8_t* b, int64_t n, int desc_bytes, int32_t* dist) {
+  // pairwise distance = 1-NN of a one-row train set, row by row; used by the
+  // parity tests of the distance primitive only (small n).
+  if (!ctx || !a || !b || !dist || n < 0) return fail(ctx, BRISK_ERR_INVALID, "bad arguments");
+  for (int64_t i = 0; i < n; ++i) {
+    int32_t idx = 0, d = 0;
+    int rc = brisk_hamming_knn(ctx, a + i * desc_bytes, 1, b + i * desc_bytes, 1, desc_bytes, 1, &idx, &d);
+    if (rc) return rc;
+    dist[i] = d;
+  }
+  return BRISK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,215 @@
+// Integral image and BRISK descriptor extraction kernels (sm_100a).
+//
+// Replaces IntegralImage8 (reference brisk/include/brisk/internal/
+// integral-image.h:56-161) and BriskDescriptorExtractor::doDescriptorComputation
+// (brisk/src/brisk-descriptor-extractor.cc:612-778): border cull, orientation
+// from the long pairs, rotated sampling, and bit packing of the short pairs.
+// One warp per key point: lanes sample the 60/66 pattern points through the
+// integral image, reduce the long-pair gradient with shuffles, and pack the
+// comparison bits with __ballot_sync (bit p%32 of word p/32 is exactly lane
+// order, reference :538-564).
+#include <cuda_runtime.h>
+
+#include "describe_logic.cuh"
+#include "kernels.h"
+
+namespace briskb200 {
+
+// --- integral image: row scans (one warp per row), then column accumulation ---
+
+__global__ void __launch_bounds__(256)
+integral_rows_kernel(const uint8_t* __restrict__ imgs, long long frame_stride, int pitch, int w, int h,
+                     int32_t* __restrict__ integral) {
+  const int frame = blockIdx.y, lane = threadIdx.x & 31;
+  const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // output row y in [0, h]
+  if (y > h) return;
+  const int iw = w + 1;
+  int32_t* out = integral + (long long)frame * iw * (h + 1) + (long long)y * iw;
+  if (y == 0) {
+    for (int x = lane; x < iw; x += 32) out[x] = 0;
+    return;
+  }
+  const uint8_t* row = imgs + (long long)frame * frame_stride + (long long)(y - 1) * pitch;
+  if (lane == 0) out[0] = 0;
+  int carry = 0;
+  for (int xb = 0; xb < w; xb += 128) {
+    const int x = xb + 4 * lane;
+    uint32_t v = 0;
+    if (x < pitch) v = *reinterpret_cast<const uint32_t*>(row + x);
+    const int b0 = v & 0xff, b1 = b0 + ((v >> 8) & 0xff), b2 = b1 + ((v >> 16) & 0xff), b3 = b2 + (v >> 24);
+    int inc = b3;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    const int base = carry + inc - b3;
+    if (x < w) out[x + 1] = base + b0;
+    if (x + 1 < w) out[x + 2] = base + b1;
+    if (x + 2 < w) out[x + 3] = base + b2;
+    if (x + 3 < w) out[x + 4] = base + b3;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+integral_cols_kernel(int w, int h, int32_t* __restrict__ integral) {
+  const int frame = blockIdx.y;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
+  if (x > w) return;
+  const int iw = w + 1;
+  int32_t* p = integral + (long long)frame * iw * (h + 1) + x;
+  int acc = 0;
+  int y = 1;
+  for (; y + 3 <= h; y += 4) {  // 4 independent loads in flight
+    const int a = p[(long long)y * iw], b = p[(long long)(y + 1) * iw], c = p[(long long)(y + 2) * iw], d = p[(long long)(y + 3) * iw];
+    const int s0 = acc + a, s1 = s0 + b, s2 = s1 + c, s3 = s2 + d;
+    p[(long long)y * iw] = s0; p[(long long)(y + 1) * iw] = s1; p[(long long)(y + 2) * iw] = s2; p[(long long)(y + 3) * iw] = s3;
+    acc = s3;
+  }
+  for (; y <= h; ++y) { acc += p[(long long)y * iw]; p[(long long)y * iw] = acc; }
+}
+
+cudaError_t launch_integral(const uint8_t* imgs, long long frame_stride, int pitch, int w, int h, int n_frames,
+                            int32_t* integral, cudaStream_t stream) {
+  dim3 g1((h + 1 + 7) / 8, n_frames);
+  integral_rows_kernel<<<g1, 256, 0, stream>>>(imgs, frame_stride, pitch, w, h, integral);
+  dim3 g2((w + 255) / 256, n_frames);
+  integral_cols_kernel<<<g2, 256, 0, stream>>>(w, h, integral);
+  return cudaGetLastError();
+}
+
+// --- border cull: stable per-frame compaction of the key points that keep the
+// whole pattern inside the image (reference :636-662) ---
+
+__global__ void __launch_bounds__(256)
+describe_cull_kernel(PatternDev pat, int w, int h, const KeyPoint* __restrict__ kps, int* __restrict__ counts, int kp_cap,
+                     KeyPoint* __restrict__ kps_out, int* __restrict__ scales_out) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(counts[frame], kp_cap);
+  const KeyPoint* src = kps + (long long)frame * kp_cap;
+  KeyPoint* dst = kps_out + (long long)frame * kp_cap;
+  int* sdst = scales_out + (long long)frame * kp_cap;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 256) {
+    const int k = base + tid;
+    bool keep = false;
+    KeyPoint kp;
+    int scale = 0;
+    if (k < n) {
+      kp = src[k];
+      if (pat.scale_inv) {
+        // scale index = #{s >= 1 : size >= break[s]}; the breaks are computed on
+        // the host with the reference's own expression (:639-646), so the index
+        // is exact by construction.  NaN / non-positive sizes map to 0.
+        int lo = 0, hi = 63;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (kp.size >= pat.scale_breaks[mid]) lo = mid; else hi = mid - 1;
+        }
+        scale = lo;
+      } else {
+        scale = pat.basic_scale;
+      }
+      const int border = (int)pat.size_list[scale];
+      const float fb = (float)border, bx = (float)(w - border), by = (float)(h - border);
+      keep = !((kp.x < fb) || (kp.x >= bx) || (kp.y < fb) || (kp.y >= by));
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = s_base;
+    for (int i = 0; i < warp; ++i) before += s_warp[i];
+    const int pos = before + __popc(m & ((1u << lane) - 1));
+    if (keep) { dst[pos] = kp; sdst[pos] = scale; }
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int i = 0; i < 8; ++i) t += s_warp[i]; s_base += t; }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) counts[frame] = s_base;
+}
+
+// --- descriptor: one warp per key point ---
+
+constexpr int kDescWarps = 8;
+constexpr int kMaxPoints = 96;
+
+__global__ void __launch_bounds__(kDescWarps * 32)
+describe_kernel(PatternDev pat, const uint8_t* __restrict__ imgs, long long frame_stride, int pitch, int w, int h,
+                const int32_t* __restrict__ integral, const KeyPoint* __restrict__ kps_in, const int* __restrict__ scales,
+                const int* __restrict__ counts, int kp_cap, KeyPoint* __restrict__ kps_out, uint8_t* __restrict__ desc) {
+  __shared__ int s_val[kDescWarps][kMaxPoints];
+  const int frame = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.x * kDescWarps + warp;
+  if (k >= counts[frame]) return;
+  const long long slot = (long long)frame * kp_cap + k;
+  const KeyPoint kp = kps_in[slot];
+  const int scale = scales[slot];
+  const uint8_t* img = imgs + (long long)frame * frame_stride;
+  const int iw = w + 1;
+  const int32_t* integ = integral + (long long)frame * iw * (h + 1);
+  const int P = pat.n_points;
+  int* val = s_val[warp];
+
+  int theta = 0;
+  float angle = kp.angle;
+  if (pat.rot_inv) {
+    if (kp.angle == -1.0f) {
+      // un-rotated samples, long-pair gradient (:697-739)
+      const float* pp = pat.points + ((long long)scale * 1024) * P * 3;
+      for (int i = lane; i < P; i += 32)
+        val[i] = smoothed_intensity(img, pitch, integ, iw, kp.x, kp.y, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2]);
+      __syncwarp();
+      int d0 = 0, d1 = 0;
+      for (int p = lane; p < pat.n_long; p += 32) {
+        const int4 lp = *reinterpret_cast<const int4*>(pat.long_pairs + 4 * p);
+        const int delta = val[lp.x] - val[lp.y];
+        d0 += delta * lp.z / 1024;
+        d1 += delta * lp.w / 1024;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
+      angle = orientation_angle(d0, d1);
+      theta = theta_from_estimated(angle);
+      __syncwarp();
+    } else {
+      theta = theta_from_given(kp.angle);
+    }
+  }
+  // samples in the rotated pattern (:755-772)
+  const float* pp = pat.points + ((long long)scale * 1024 + theta) * P * 3;
+  for (int i = lane; i < P; i += 32)
+    val[i] = smoothed_intensity(img, pitch, integ, iw, kp.x, kp.y, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2]);
+  __syncwarp();
+  // short-pair comparisons -> bits (:538-564); rows are zero-padded to desc_bytes
+  uint32_t* out = reinterpret_cast<uint32_t*>(desc + slot * pat.desc_bytes);
+  const int words = pat.desc_bytes >> 2;
+  for (int wd = 0; wd < words; ++wd) {
+    const int p = wd * 32 + lane;
+    bool bit = false;
+    if (p < pat.n_short) {
+      const ushort2 sp = *reinterpret_cast<const ushort2*>(pat.short_pairs + 2 * p);
+      bit = val[sp.x] > val[sp.y];
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+    if (lane == 0) out[wd] = word;
+  }
+  if (lane == 0) {
+    KeyPoint o = kp;
+    o.angle = angle;
+    kps_out[slot] = o;
+  }
+}
+
+cudaError_t launch_describe(const PatternDev& pat, const uint8_t* imgs, long long frame_stride, int pitch, int w, int h,
+                            int n_frames, const int32_t* integral, KeyPoint* kps, int* counts, int kp_cap,
+                            KeyPoint* kps_scratch, int* scale_scratch, uint8_t* desc, cudaStream_t stream) {
+  describe_cull_kernel<<<n_frames, 256, 0, stream>>>(pat, w, h, kps, counts, kp_cap, kps_scratch, scale_scratch);
+  dim3 grid((kp_cap + kDescWarps - 1) / kDescWarps, n_frames);
+  describe_kernel<<<grid, kDescWarps * 32, 0, stream>>>(pat, imgs, frame_stride, pitch, w, h, integral, kps_scratch,
+                                                        scale_scratch, counts, kp_cap, kps, desc);
+  return cudaGetLastError();
+}
+
+}  // namespace briskb200

@@ -1,0 +1,108 @@
+// Per-sample arithmetic of the BRISK descriptor (reference
+// brisk/src/brisk-descriptor-extractor.cc:370-530,612-778), as __host__
+// __device__ functions shared by the describe kernel and the host-side tests.
+// Float/double promotions follow the reference expression by expression
+// (SURVEY.md App. A.6); compile without FMA contraction.
+#pragma once
+#include "brisk_common.cuh"
+
+namespace briskb200 {
+
+// SmoothedIntensity<uchar,int> (brisk-descriptor-extractor.cc:370-530): box
+// filtered intensity (x ~1024) of the pattern point (px, py, sigma) placed at
+// key point (kx, ky).  `integral` is the (h+1)x(w+1) int32 integral image with
+// row stride iw = w + 1; the image has row pitch `pitch`.
+BRISK_HD int smoothed_intensity(const uint8_t* __restrict__ img, int pitch, const int32_t* __restrict__ integral, int iw,
+                                float kx, float ky, float px, float py, float sigma_half) {
+  const float xf = px + kx, yf = py + ky;
+  const float area = (float)(4.0 * (double)sigma_half * (double)sigma_half);
+  if ((double)sigma_half < 0.5) {
+    const int x = (int)xf, y = (int)yf;
+    const int r_x = (int)((xf - (float)x) * 1024.0f), r_y = (int)((yf - (float)y) * 1024.0f);
+    const int r_x_1 = 1024 - r_x, r_y_1 = 1024 - r_y;
+    const uint8_t* p = img + (long long)y * pitch + x;
+    int v = r_x_1 * r_y_1 * (int)p[0];
+    v += r_x * r_y_1 * (int)p[1];
+    v += r_x * r_y * (int)p[pitch + 1];
+    v += r_x_1 * r_y * (int)p[pitch];
+    return v / 1024;
+  }
+  const int scaling = (int)(4194304.0 / (double)area);
+  const int scaling2 = (int)((double)((float)scaling * area) / 1024.0);
+  const float x_1 = xf - sigma_half, x1 = xf + sigma_half, y_1 = yf - sigma_half, y1 = yf + sigma_half;
+  const int x_left = (int)((double)x_1 + 0.5), y_top = (int)((double)y_1 + 0.5);
+  const int x_right = (int)((double)x1 + 0.5), y_bottom = (int)((double)y1 + 0.5);
+  const float r_x_1 = (float)((double)((float)x_left - x_1) + 0.5), r_y_1 = (float)((double)((float)y_top - y_1) + 0.5);
+  const float r_x1 = (float)((double)(x1 - (float)x_right) + 0.5), r_y1 = (float)((double)(y1 - (float)y_bottom) + 0.5);
+  const int dx = x_right - x_left - 1, dy = y_bottom - y_top - 1;
+  const float fs = (float)scaling;
+  const int A = (int)((r_x_1 * r_y_1) * fs), B = (int)((r_x1 * r_y_1) * fs);
+  const int C = (int)((r_x1 * r_y1) * fs), D = (int)((r_x_1 * r_y1) * fs);
+  const int r_x_1_i = (int)(r_x_1 * fs), r_y_1_i = (int)(r_y_1 * fs), r_x1_i = (int)(r_x1 * fs), r_y1_i = (int)(r_y1 * fs);
+  const uint8_t* p = img + (long long)y_top * pitch + x_left;
+  if (dx + dy > 2) {
+    // four weighted corner pixels; the reference's pointer walk (:447-456)
+    // reads the bottom pair one row up and one column right of the geometric
+    // corners -- reproduced.
+    int v = A * (int)p[0] + B * (int)p[dx + 1];
+    const uint8_t* pc = p + (dx + 1) + (long long)dy * pitch + 1;
+    v += C * (int)pc[0] + D * (int)pc[-(dx + 1)];
+    // twelve integral-image taps (:459-484)
+    const int32_t* q = integral + (long long)y_top * iw + x_left + 1;
+    const int t1 = q[0], t2 = q[dx];
+    const int32_t* q1 = q + iw;
+    const int t3 = q1[dx], t4 = q1[dx + 1], t12 = q1[0], t11 = q1[-1];
+    const int32_t* q2 = q1 + (long long)dy * iw;
+    const int t5 = q2[dx + 1], t6 = q2[dx], t9 = q2[0], t10 = q2[-1];
+    const int32_t* q3 = q2 + iw;
+    const int t7 = q3[dx], t8 = q3[0];
+    const int upper = (t3 - t2 + t1 - t12) * r_y_1_i;
+    const int middle = (t6 - t3 + t12 - t9) * scaling;
+    const int left = (t9 - t12 + t11 - t10) * r_x_1_i;
+    const int right = (t5 - t4 + t3 - t6) * r_x1_i;
+    const int bottom = (t7 - t6 + t9 - t8) * r_y1_i;
+    return (v + upper + middle + left + right + bottom) / scaling2;
+  }
+  // small box: weighted sum over the (dx+2) x (dy+2) window, written as the
+  // reference's index walk (:497-529) so that the degenerate windows that float
+  // rounding can produce when 2*sigma ~ 1 (dx or dy == -1: the walk then reuses /
+  // drifts over neighbouring pixels) come out the same.
+  long long i = 0;
+  int v = A * (int)p[i];
+  ++i;
+  for (const long long e = i + dx; i < e; ++i) v += r_y_1_i * (int)p[i];
+  v += B * (int)p[i];
+  i += pitch - dx - 1;
+  for (const long long ej = i + (long long)dy * pitch; i < ej; i += pitch - dx - 1) {
+    v += r_x_1_i * (int)p[i];
+    ++i;
+    for (const long long e = i + dx; i < e; ++i) v += (int)p[i] * scaling;
+    v += r_x1_i * (int)p[i];
+  }
+  v += D * (int)p[i];
+  ++i;
+  for (const long long e = i + dx; i < e; ++i) v += r_y1_i * (int)p[i];
+  v += C * (int)p[i];
+  return v / scaling2;
+}
+
+// Rotation bin of a freshly estimated orientation (:732-739): angle in degrees
+// from the long-pair gradient, theta = its 1024-bin index.
+BRISK_HD float orientation_angle(int d0, int d1) {
+  return (float)(atan2((double)(float)d1, (double)(float)d0) / 3.14159265358979323846 * 180.0);
+}
+BRISK_HD int theta_from_estimated(float angle) {
+  int theta = (int)((double)(1024.0f * angle) / 360.0 + 0.5);
+  if (theta < 0) theta += 1024;
+  if (theta >= 1024) theta -= 1024;
+  return theta;
+}
+// Rotation bin of a caller-supplied angle (:746-751).
+BRISK_HD int theta_from_given(float angle) {
+  int theta = (int)(1024.0 * ((double)angle / 360.0) + 0.5);
+  if (theta < 0) theta += 1024;
+  if (theta >= 1024) theta -= 1024;
+  return theta;
+}
+
+}  // namespace briskb200

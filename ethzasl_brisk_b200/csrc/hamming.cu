@@ -1,0 +1,180 @@
+// Brute-force Hamming k-nearest-neighbour search (sm_100a).
+//
+// Replaces brisk::Hamming (reference brisk/include/brisk/internal/hamming-inl.h:
+// 85-134, SSSE3 nibble-LUT popcount of the XOR) and the k successive arg-min
+// passes of BruteForceMatcher::commonKnnMatchImpl (brisk/src/brute-force-matcher.cc:
+// 80-162).  Each thread keeps two query descriptors in registers; train rows are
+// staged in shared memory and read as warp-wide broadcasts, so a row costs one
+// LDS.128 per 16 bytes and the kernel is bound by the POPC pipe.  Candidates are
+// (distance << 32 | train index) keys: the unsigned minimum of a key is the
+// nearest neighbour with the lowest train index on ties, which is the
+// reference's tie rule (first minimum of a left-to-right scan wins).
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace briskb200 {
+
+constexpr int kKnnThreads = 256;
+constexpr int kKnnQPerThread = 2;
+constexpr int kKnnTile = 128;  // train rows per shared-memory tile
+constexpr unsigned long long kKeyNone = ~0ull;
+
+template <int K>
+__device__ __forceinline__ void topk_insert(unsigned long long (&best)[K], unsigned long long key) {
+  if (key < best[K - 1]) {
+    best[K - 1] = key;
+#pragma unroll
+    for (int i = K - 1; i > 0; --i) {
+      if (best[i] < best[i - 1]) { const unsigned long long t = best[i]; best[i] = best[i - 1]; best[i - 1] = t; }
+    }
+  }
+}
+
+template <int WORDS, int K>
+__global__ void __launch_bounds__(kKnnThreads)
+hamming_knn_kernel(const uint32_t* __restrict__ q, long long nq, const uint32_t* __restrict__ t, long long nt,
+                   long long rows_per_split, long long train_index_offset, unsigned long long* __restrict__ part) {
+  __shared__ __align__(16) uint32_t s_t[kKnnTile * WORDS];
+  const int tid = threadIdx.x;
+  const long long q0 = ((long long)blockIdx.x * kKnnThreads + tid) * kKnnQPerThread;
+  uint32_t qa[WORDS], qb[WORDS];
+#pragma unroll
+  for (int i = 0; i < WORDS; ++i) {
+    qa[i] = q0 < nq ? q[q0 * WORDS + i] : 0u;
+    qb[i] = q0 + 1 < nq ? q[(q0 + 1) * WORDS + i] : 0u;
+  }
+  unsigned long long ba[K], bb[K];
+#pragma unroll
+  for (int i = 0; i < K; ++i) { ba[i] = kKeyNone; bb[i] = kKeyNone; }
+
+  const long long t_begin = (long long)blockIdx.y * rows_per_split;
+  const long long t_end = min(nt, t_begin + rows_per_split);
+  for (long long base = t_begin; base < t_end; base += kKnnTile) {
+    const int rows = (int)min((long long)kKnnTile, t_end - base);
+    __syncthreads();
+    // stage the tile: 16-byte chunks, coalesced
+    const uint4* src = reinterpret_cast<const uint4*>(t + base * WORDS);
+    uint4* dst = reinterpret_cast<uint4*>(s_t);
+    for (int i = tid; i < rows * (WORDS / 4); i += kKnnThreads) dst[i] = src[i];
+    __syncthreads();
+    for (int r = 0; r < rows; ++r) {
+      const uint4* row = reinterpret_cast<const uint4*>(s_t + r * WORDS);
+      int da = 0, db = 0;
+#pragma unroll
+      for (int c = 0; c < WORDS / 4; ++c) {
+        const uint4 v = row[c];  // broadcast
+        da += __popc(qa[4 * c] ^ v.x) + __popc(qa[4 * c + 1] ^ v.y) + __popc(qa[4 * c + 2] ^ v.z) + __popc(qa[4 * c + 3] ^ v.w);
+        db += __popc(qb[4 * c] ^ v.x) + __popc(qb[4 * c + 1] ^ v.y) + __popc(qb[4 * c + 2] ^ v.z) + __popc(qb[4 * c + 3] ^ v.w);
+      }
+      const unsigned long long idx = (unsigned long long)(train_index_offset + base + r);
+      topk_insert<K>(ba, ((unsigned long long)(uint32_t)da << 32) | idx);
+      topk_insert<K>(bb, ((unsigned long long)(uint32_t)db << 32) | idx);
+    }
+  }
+  unsigned long long* out = part + (long long)blockIdx.y * nq * K;
+  if (q0 < nq) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) out[q0 * K + i] = ba[i];
+  }
+  if (q0 + 1 < nq) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) out[(q0 + 1) * K + i] = bb[i];
+  }
+}
+
+// k-way merge of `n_lists` sorted key lists per query ([list][query][k]) into
+// out[query][k]; also the NCCL top-k merge of per-GPU shards.
+__global__ void __launch_bounds__(256)
+knn_merge_kernel(const unsigned long long* __restrict__ lists, int n_lists, long long nq, int k, unsigned long long* __restrict__ out) {
+  const long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  unsigned long long best[8];
+  for (int i = 0; i < 8; ++i) best[i] = kKeyNone;
+  for (int l = 0; l < n_lists; ++l) {
+    const unsigned long long* src = lists + ((long long)l * nq + qi) * k;
+    for (int i = 0; i < k; ++i) {
+      const unsigned long long key = src[i];
+      if (key >= best[k - 1]) break;  // lists are sorted
+      best[k - 1] = key;
+      for (int j = k - 1; j > 0 && best[j] < best[j - 1]; --j) { const unsigned long long tmp = best[j]; best[j] = best[j - 1]; best[j - 1] = tmp; }
+    }
+  }
+  for (int i = 0; i < k; ++i) out[qi * k + i] = best[i];
+}
+
+__global__ void __launch_bounds__(256)
+knn_unpack_kernel(const unsigned long long* __restrict__ keys, long long n, int32_t* __restrict__ idx, int32_t* __restrict__ dist) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long key = keys[i];
+  if (key == kKeyNone) { idx[i] = -1; dist[i] = -1; }
+  else { idx[i] = (int32_t)(key & 0xffffffffull); dist[i] = (int32_t)(key >> 32); }
+}
+
+template <int WORDS>
+static cudaError_t launch_knn_words(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int k, long long off,
+                                    unsigned long long* keys, unsigned long long* part, int splits, long long rows_per_split,
+                                    cudaStream_t stream) {
+  dim3 grid((unsigned)((nq + kKnnThreads * kKnnQPerThread - 1) / (kKnnThreads * kKnnQPerThread)), splits);
+  unsigned long long* dst = splits == 1 ? keys : part;
+  const uint32_t* q32 = reinterpret_cast<const uint32_t*>(q);
+  const uint32_t* t32 = reinterpret_cast<const uint32_t*>(t);
+  switch (k) {
+    case 1: hamming_knn_kernel<WORDS, 1><<<grid, kKnnThreads, 0, stream>>>(q32, nq, t32, nt, rows_per_split, off, dst); break;
+    case 2: hamming_knn_kernel<WORDS, 2><<<grid, kKnnThreads, 0, stream>>>(q32, nq, t32, nt, rows_per_split, off, dst); break;
+    case 3: case 4: hamming_knn_kernel<WORDS, 4><<<grid, kKnnThreads, 0, stream>>>(q32, nq, t32, nt, rows_per_split, off, dst); break;
+    default: hamming_knn_kernel<WORDS, 8><<<grid, kKnnThreads, 0, stream>>>(q32, nq, t32, nt, rows_per_split, off, dst); break;
+  }
+  return cudaGetLastError();
+}
+
+// Number of train-set splits used so that small query sets still fill the GPU.
+int knn_num_splits(long long nq, long long nt) {
+  const long long qblocks = (nq + kKnnThreads * kKnnQPerThread - 1) / (kKnnThreads * kKnnQPerThread);
+  long long splits = (2 * 148 + qblocks - 1) / qblocks;
+  const long long max_splits = (nt + 4 * kKnnTile - 1) / (4 * kKnnTile);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 1024) splits = 1024;
+  return (int)splits;
+}
+
+int knn_round_k(int k) { return k <= 1 ? 1 : (k <= 2 ? 2 : (k <= 4 ? 4 : 8)); }
+
+// keys: [nq][kr] (kr = knn_round_k(k)); part: scratch [splits][nq][kr] (unused when splits == 1).
+cudaError_t launch_hamming_knn_ex(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes, int k,
+                                  long long train_index_offset, unsigned long long* keys, unsigned long long* part,
+                                  int splits, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  const int kr = knn_round_k(k);
+  const long long rows_per_split = ((nt + splits - 1) / splits + kKnnTile - 1) / kKnnTile * kKnnTile;
+  cudaError_t e;
+  switch (desc_bytes) {
+    case 48: e = launch_knn_words<12>(q, nq, t, nt, kr, train_index_offset, keys, part, splits, rows_per_split > 0 ? rows_per_split : kKnnTile, stream); break;
+    case 64: e = launch_knn_words<16>(q, nq, t, nt, kr, train_index_offset, keys, part, splits, rows_per_split > 0 ? rows_per_split : kKnnTile, stream); break;
+    case 128: e = launch_knn_words<32>(q, nq, t, nt, kr, train_index_offset, keys, part, splits, rows_per_split > 0 ? rows_per_split : kKnnTile, stream); break;
+    default: return cudaErrorInvalidValue;
+  }
+  if (e != cudaSuccess) return e;
+  if (splits > 1) {
+    knn_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(part, splits, nq, kr, keys);
+    e = cudaGetLastError();
+  }
+  return e;
+}
+
+cudaError_t launch_knn_merge(const unsigned long long* gathered, int n_shards, long long nq, int k, unsigned long long* out,
+                             cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  knn_merge_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, stream>>>(gathered, n_shards, nq, k, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_knn_unpack(const unsigned long long* keys, long long n, int32_t* idx, int32_t* dist, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  knn_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(keys, n, idx, dist);
+  return cudaGetLastError();
+}
+
+}  // namespace briskb200

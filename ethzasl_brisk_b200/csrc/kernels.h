@@ -1,0 +1,73 @@
+// Host-side launchers of the sm_100a kernels (internal to libbrisk_b200.so).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "brisk_common.cuh"
+
+namespace briskb200 {
+
+// Per-batch device workspace of the AGAST detector; plane blocks are laid out
+// [frame][layer] following PyramidGeom.
+struct DetectWorkspace {
+  uint8_t* pyr;         // u8 image planes
+  uint16_t* cm;         // u16 corner maps
+  uint8_t* bm;          // u8 touch maps
+  int* rowcnt;          // [frame][total_rows] corners per row -> exclusive prefix (in place)
+  int* layer_start;     // [frame][kMaxLayers + 1] first corner slot of each layer
+  uint32_t* corners;    // [frame][corner_cap] packed x | y << 13 | layer << 26, layer-major raster order
+  uint8_t* fwin;        // [frame][corner_cap][32] 5x5 FAST scores of tying corners
+  float* checks;        // [frame][corner_cap][6]  CheckResult
+  KeyPoint* kp_tmp;     // [frame][corner_cap]
+  uint8_t* kp_valid;    // [frame][corner_cap]
+  int total_rows;       // sum of layer heights
+  int row_off[kMaxLayers + 1];
+  int corner_cap;       // per frame
+};
+
+cudaError_t launch_pyramid(const CUtensorMap& src_map, const PyramidGeom& g, uint8_t* pyr, int n_frames, int write_l0,
+                           cudaStream_t stream);
+
+// Threshold map + AGAST 9-16 segment test -> corner map + per-row counts.
+cudaError_t launch_agast_detect(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int thresh, cudaStream_t stream);
+// Row prefix sums and ordered corner lists.
+cudaError_t launch_corner_lists(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int* overflow_flag,
+                                cudaStream_t stream);
+// Scale-space NMS + refinement -> ordered key points [frame][kp_cap], counts[frame].
+cudaError_t launch_agast_nms(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, const uint8_t* masks,
+                             long long mask_frame_stride, int mask_pitch, KeyPoint* out, int* counts, int kp_cap,
+                             cudaStream_t stream);
+
+cudaError_t launch_dense_scores(const LayerGeom& L, const uint8_t* img, uint8_t* out916, uint8_t* out58, cudaStream_t stream);
+
+// Descriptor extraction.
+struct PatternDev {
+  const float* points;  // [64][1024][P][3] x, y, sigma
+  const unsigned int* size_list;  // [64]
+  const unsigned short* short_pairs;  // [n_short][2] (i, j)
+  const int* long_pairs;  // [n_long][4] (i, j, wdx, wdy)
+  const float* scale_breaks;  // [64] smallest keypoint size mapping to scale index s (s >= 1)
+  int n_points, n_short, n_long, desc_bytes;
+  int rot_inv, scale_inv, basic_scale;
+};
+
+cudaError_t launch_integral(const uint8_t* imgs, long long frame_stride, int pitch, int w, int h, int n_frames,
+                            int32_t* integral, cudaStream_t stream);
+// Border cull (stable, per frame) + descriptor computation.  kps is in/out
+// [frame][kp_cap], counts in/out, desc out [frame][kp_cap][desc_bytes].
+cudaError_t launch_describe(const PatternDev& pat, const uint8_t* imgs, long long frame_stride, int pitch, int w, int h,
+                            int n_frames, const int32_t* integral, KeyPoint* kps, int* counts, int kp_cap,
+                            KeyPoint* kps_scratch, int* scale_scratch, uint8_t* desc, cudaStream_t stream);
+
+// Brute-force Hamming k-nearest neighbours (k <= 8); packed (dist << 32 | train idx) u64 keys,
+// sorted ascending per query, kr = knn_round_k(k) keys per query.
+int knn_num_splits(long long nq, long long nt);
+int knn_round_k(int k);
+cudaError_t launch_hamming_knn_ex(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes, int k,
+                                  long long train_index_offset, unsigned long long* keys, unsigned long long* part,
+                                  int splits, cudaStream_t stream);
+cudaError_t launch_knn_unpack(const unsigned long long* keys, long long n, int32_t* idx, int32_t* dist, cudaStream_t stream);
+cudaError_t launch_knn_merge(const unsigned long long* gathered, int n_shards, long long nq, int k, unsigned long long* out,
+                             cudaStream_t stream);
+
+}  // namespace briskb200

@@ -1,0 +1,221 @@
+// Scale-space NMS and refinement kernels of the AGAST path (sm_100a); the
+// per-corner logic lives in nms_logic.cuh (shared with the host-side tests).
+//
+// Replaces BriskScaleSpace::GetKeypoints and friends (reference
+// brisk/src/brisk-scale-space.cc:92-1364).  Launch sequence per batch:
+//   nms_prefix_kernel  one thread per raw corner   IsMax2D's 8 comparisons
+//   nms_checks_kernel  one thread per raw corner   above / below scale checks (pure)
+//   nms_chain_kernel   one CTA per frame           layer by layer: tying corners in
+//                                                  raster order, then the footprint
+//                                                  the accepted corners leave on the
+//                                                  layer above
+//   refine_kernel      one thread per raw corner   sub-pixel / scale refinement
+//   compact_kernel     one CTA per frame           ordered compaction (+ mask filter)
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+#include "nms_logic.cuh"
+
+namespace briskb200 {
+
+struct FrameViews {
+  LayerView v[kMaxLayers];
+};
+
+__device__ __forceinline__ void make_views(const PyramidGeom& g, const DetectWorkspace& ws, int frame, FrameViews* fv) {
+  const long long fo = (long long)frame * g.frame_elems;
+#pragma unroll 1
+  for (int l = 0; l < g.n_layers; ++l) {
+    const LayerGeom& L = g.L[l];
+    fv->v[l] = LayerView{ws.pyr + fo + L.off, ws.cm + fo + L.off, ws.bm + fo + L.off, L.w, L.h, L.pitch, L.scale, L.offset};
+  }
+}
+
+__device__ __forceinline__ void unpack_corner(uint32_t c, int* x, int* y, int* layer) {
+  *x = c & 0x1fff; *y = (c >> 13) & 0x1fff; *layer = c >> 26;
+}
+
+__global__ void __launch_bounds__(128)
+nms_prefix_kernel(PyramidGeom g, DetectWorkspace ws) {
+  const int frame = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(ws.layer_start[(long long)frame * (kMaxLayers + 1) + g.n_layers], ws.corner_cap);
+  if (k >= n) return;
+  int x, y, layer;
+  unpack_corner(ws.corners[(long long)frame * ws.corner_cap + k], &x, &y, &layer);
+  const long long fo = (long long)frame * g.frame_elems;
+  const LayerGeom& L = g.L[layer];
+  const LayerView v{ws.pyr + fo + L.off, ws.cm + fo + L.off, ws.bm + fo + L.off, L.w, L.h, L.pitch, L.scale, L.offset};
+  uint8_t fwin[25];
+  nms_prefix(v, x, y, fwin);
+  if (v.cm[(long long)y * L.pitch + x] & kCmTie) {
+    uint8_t* dst = ws.fwin + ((long long)frame * ws.corner_cap + k) * 32;
+#pragma unroll
+    for (int i = 0; i < 25; ++i) dst[i] = fwin[i];
+  }
+}
+
+__global__ void __launch_bounds__(128)
+nms_checks_kernel(PyramidGeom g, DetectWorkspace ws) {
+  const int frame = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(ws.layer_start[(long long)frame * (kMaxLayers + 1) + g.n_layers], ws.corner_cap);
+  if (k >= n) return;
+  int x, y, layer;
+  unpack_corner(ws.corners[(long long)frame * ws.corner_cap + k], &x, &y, &layer);
+  FrameViews fv;
+  make_views(g, ws, frame, &fv);
+  uint16_t* e = fv.v[layer].cm + (long long)y * fv.v[layer].pitch + x;
+  const uint16_t ev = *e;
+  if ((ev & kCmDecided) && !(ev & kCmAccept)) return;
+  CheckResult r;
+  const bool ok = nms_checks(fv.v, g.n_layers, layer, x, y, &r);
+  if (ok) {
+    *e = ev | kCmChecks;
+    float* dst = ws.checks + ((long long)frame * ws.corner_cap + k) * 6;
+    dst[0] = r.max_above; dst[1] = r.dxa; dst[2] = r.dya; dst[3] = r.max_below; dst[4] = r.dxb; dst[5] = r.dyb;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+nms_chain_kernel(PyramidGeom g, DetectWorkspace ws) {
+  __shared__ FrameViews fv;
+  const int frame = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) make_views(g, ws, frame, &fv);
+  __syncthreads();
+  const int* ls = ws.layer_start + (long long)frame * (kMaxLayers + 1);
+  const uint32_t* corners = ws.corners + (long long)frame * ws.corner_cap;
+  for (int layer = 0; layer < g.n_layers; ++layer) {
+    const int mode = g.n_layers == 1 ? kModeSingle : (layer == g.n_layers - 1 ? kModeLast : kModeMid);
+    const int begin = min(ls[layer], ws.corner_cap), end = min(ls[layer + 1], ws.corner_cap);
+    const LayerView& L = fv.v[layer];
+    // tying corners, strictly in raster order (warp 0 finds them 32 at a time, lane 0 decides)
+    if (tid < 32) {
+      for (int base = begin; base < end; base += 32) {
+        const int k = base + tid;
+        int x = 0, y = 0, l2 = 0;
+        bool tie = false;
+        if (k < end) {
+          unpack_corner(corners[k], &x, &y, &l2);
+          tie = !(L.cm[(long long)y * L.pitch + x] & kCmDecided);
+        }
+        uint32_t m = __ballot_sync(0xffffffffu, tie);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const int tx = __shfl_sync(0xffffffffu, x, src), ty = __shfl_sync(0xffffffffu, y, src);
+          if (tid == 0) {
+            const uint8_t* fw = ws.fwin + ((long long)frame * ws.corner_cap + base + src) * 32;
+            const bool ok = nms_tie_decide(L, mode, tx, ty, fw);
+            uint16_t* e = L.cm + (long long)ty * L.pitch + tx;
+            *e = *e | (uint16_t)(kCmDecided | (ok ? kCmAccept : 0));
+          }
+          __syncwarp();
+        }
+      }
+    }
+    __syncthreads();
+    // footprint of the accepted corners on the layer above
+    if (mode == kModeMid) {
+      for (int k = begin + tid; k < end; k += blockDim.x) {
+        int x, y, l2;
+        unpack_corner(corners[k], &x, &y, &l2);
+        if (L.cm[(long long)y * L.pitch + x] & kCmAccept) mark_above(fv.v, layer, x, y);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(128)
+refine_kernel(PyramidGeom g, DetectWorkspace ws) {
+  const int frame = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(ws.layer_start[(long long)frame * (kMaxLayers + 1) + g.n_layers], ws.corner_cap);
+  if (k >= n) return;
+  const long long slot = (long long)frame * ws.corner_cap + k;
+  int x, y, layer;
+  unpack_corner(ws.corners[slot], &x, &y, &layer);
+  FrameViews fv;
+  make_views(g, ws, frame, &fv);
+  const uint16_t e = fv.v[layer].cm[(long long)y * fv.v[layer].pitch + x];
+  bool valid = false;
+  if ((e & kCmAccept) && (e & kCmChecks)) {
+    const float* src = ws.checks + slot * 6;
+    CheckResult r{src[0], src[1], src[2], src[3], src[4], src[5]};
+    KeyPoint kp;
+    valid = refine_emit(fv.v, g.n_layers, layer, x, y, r, &kp);
+    if (valid) ws.kp_tmp[slot] = kp;
+  }
+  ws.kp_valid[slot] = valid ? 1 : 0;
+}
+
+// Ordered compaction of the surviving key points of a frame, with the mask
+// filter of RemoveInvalidKeyPoints (reference brisk-feature-detector.cc:49-66).
+__global__ void __launch_bounds__(256)
+compact_kernel(PyramidGeom g, DetectWorkspace ws, const uint8_t* __restrict__ masks, long long mask_frame_stride,
+               int mask_pitch, KeyPoint* __restrict__ out, int* __restrict__ counts, int kp_cap) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = min(ws.layer_start[(long long)frame * (kMaxLayers + 1) + g.n_layers], ws.corner_cap);
+  const KeyPoint* src = ws.kp_tmp + (long long)frame * ws.corner_cap;
+  const uint8_t* valid = ws.kp_valid + (long long)frame * ws.corner_cap;
+  const uint8_t* mask = masks ? masks + (long long)frame * mask_frame_stride : nullptr;
+  KeyPoint* dst = out + (long long)frame * kp_cap;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 256) {
+    const int k = base + tid;
+    bool keep = k < n && valid[k];
+    KeyPoint kp;
+    if (keep) {
+      kp = src[k];
+      if (mask && mask[(long long)(int)(kp.y + 0.5f) * mask_pitch + (int)(kp.x + 0.5f)] == 0) keep = false;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(m);
+    __syncthreads();
+    int before = s_base;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    const int pos = before + __popc(m & ((1u << lane) - 1));
+    if (keep && pos < kp_cap) dst[pos] = kp;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < 8; ++w) t += s_warp[w]; s_base += t; }
+    __syncthreads();
+  }
+  if (tid == 0) counts[frame] = s_base;  // may exceed kp_cap: caller reports truncation
+}
+
+// Debug: dense FAST 9-16 / 5-8 score planes of layer 0 (threshold 1, border rules
+// of brisk-layer.cc:118-145), for parity tests of the closed-form score.
+__global__ void __launch_bounds__(256)
+dense_scores_kernel(LayerGeom L, const uint8_t* __restrict__ img, uint8_t* __restrict__ out916, uint8_t* __restrict__ out58) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= L.w || y >= L.h) return;
+  const LayerView v{img, nullptr, nullptr, L.w, L.h, L.pitch, L.scale, L.offset};
+  out916[(long long)y * L.w + x] = in_border(v, x, y) ? 0 : (uint8_t)fastF(v, x, y);
+  out58[(long long)y * L.w + x] = (uint8_t)score58(v, x, y);
+}
+
+cudaError_t launch_dense_scores(const LayerGeom& L, const uint8_t* img, uint8_t* out916, uint8_t* out58, cudaStream_t stream) {
+  dim3 grid((L.w + 255) / 256, L.h);
+  dense_scores_kernel<<<grid, 256, 0, stream>>>(L, img, out916, out58);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_agast_nms(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, const uint8_t* masks,
+                             long long mask_frame_stride, int mask_pitch, KeyPoint* out, int* counts, int kp_cap,
+                             cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(ws.bm, 0, (size_t)n_frames * g.frame_elems, stream);
+  if (e != cudaSuccess) return e;
+  dim3 grid((ws.corner_cap + 127) / 128, n_frames);
+  nms_prefix_kernel<<<grid, 128, 0, stream>>>(g, ws);
+  nms_checks_kernel<<<grid, 128, 0, stream>>>(g, ws);
+  nms_chain_kernel<<<n_frames, 256, 0, stream>>>(g, ws);
+  refine_kernel<<<grid, 128, 0, stream>>>(g, ws);
+  compact_kernel<<<n_frames, 256, 0, stream>>>(g, ws, masks, mask_frame_stride, mask_pitch, out, counts, kp_cap);
+  return cudaGetLastError();
+}
+
+}  // namespace briskb200

@@ -1,0 +1,141 @@
+/* brisk_b200 -- C ABI of the B200-native BRISK hot path (libbrisk_b200.so).
+ *
+ * This is the drop-in boundary: the reference (ethz-asl/ethzasl_brisk) has no
+ * FFI layer, its boundary is the C++ class surface of brisk/include/brisk/*.h.
+ * The header-only C++ classes in include/brisk/ (same names, constructor
+ * arguments and semantics) and the Python mirror ethzasl_brisk_b200/api.py are
+ * thin hosts over these entry points.  Each entry point cites the reference
+ * interface it replaces.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on
+ * success or a negative brisk_status and never throws; the message of the last
+ * failure is available from brisk_last_error().  Image, key-point, descriptor
+ * and count buffers may live in host OR device memory (detected per pointer);
+ * host buffers are copied inside the call.  A context owns one CUDA stream and
+ * all workspaces: use one context per host thread / GPU.  There is no CPU
+ * fallback: without a usable CUDA device every call fails.
+ */
+#ifndef BRISK_B200_H_
+#define BRISK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct brisk_ctx brisk_ctx;
+typedef struct brisk_detector brisk_detector;
+typedef struct brisk_extractor brisk_extractor;
+
+/* Binary compatible with cv::KeyPoint (pt.x, pt.y, size, angle, response,
+ * octave, class_id): 28 bytes. */
+typedef struct {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} brisk_keypoint;
+
+typedef enum {
+  BRISK_OK = 0,
+  BRISK_ERR_INVALID = -1,     /* bad argument */
+  BRISK_ERR_CUDA = -2,        /* CUDA runtime / driver failure */
+  BRISK_ERR_UNSUPPORTED = -3, /* configuration outside the implemented range */
+  BRISK_ERR_CAPACITY = -4     /* more raw corners / key points than the configured capacity */
+} brisk_status;
+
+/* Context: device, stream, workspaces.  `stream` is a cudaStream_t to run on
+ * (e.g. the current torch stream) or NULL for a private non-blocking stream. */
+int brisk_ctx_create(int device, void* stream, brisk_ctx** out);
+void brisk_ctx_destroy(brisk_ctx* ctx);
+const char* brisk_last_error(const brisk_ctx* ctx);
+int brisk_sync(brisk_ctx* ctx);
+/* Upper bound on device workspace bytes used per call (frames are processed in
+ * chunks that fit); default 8 GiB. */
+int brisk_ctx_set_workspace_limit(brisk_ctx* ctx, size_t bytes);
+/* Device time in milliseconds of the kernels of the last detect / describe /
+ * detect_describe / knn call, per stage (see BRISK_STAGE_*), measured with CUDA
+ * events on the context stream.  Requires brisk_ctx_enable_timing(ctx, 1). */
+int brisk_ctx_enable_timing(brisk_ctx* ctx, int enable);
+enum { BRISK_STAGE_H2D = 0, BRISK_STAGE_PYRAMID, BRISK_STAGE_DETECT, BRISK_STAGE_LISTS, BRISK_STAGE_NMS,
+       BRISK_STAGE_INTEGRAL, BRISK_STAGE_DESCRIBE, BRISK_STAGE_D2H, BRISK_STAGE_KNN, BRISK_STAGE_COUNT };
+int brisk_ctx_last_timing(brisk_ctx* ctx, float* ms /* [BRISK_STAGE_COUNT] */, int64_t* launches);
+
+/* brisk::BriskFeatureDetector(int thresh, int octaves = 3, bool suppressScaleNonmaxima = true)
+ * -- reference brisk/include/brisk/brisk-feature-detector.h:51-84. */
+int brisk_agast_detector_create(brisk_ctx* ctx, int thresh, int octaves, int suppress_scale_nonmaxima,
+                                brisk_detector** out);
+void brisk_detector_destroy(brisk_detector* det);
+/* Raw-corner capacity per frame (all layers); default scales with the image area. */
+int brisk_detector_set_corner_capacity(brisk_detector* det, int corners_per_frame);
+
+/* brisk::BriskDescriptorExtractor(bool rotationInvariant, bool scaleInvariant, int version,
+ * float patternScale) and the pattern-file constructors -- reference
+ * brisk/include/brisk/brisk-descriptor-extractor.h:54-202.  version: 1 = briskV1
+ * (60 points, 64-byte descriptor), 2 = briskV2 (66 points, 48 bytes).
+ * pattern_file: NULL for the built-in pattern. */
+int brisk_extractor_create(brisk_ctx* ctx, int rotation_invariant, int scale_invariant, int version,
+                           float pattern_scale, const char* pattern_file, brisk_extractor** out);
+void brisk_extractor_destroy(brisk_extractor* ext);
+int brisk_extractor_descriptor_size(const brisk_extractor* ext); /* descriptorSize(): 48 / 64 */
+/* Pattern tables as built on the host (for inspection / parity tests); any output may be NULL.
+ * counts = {points, short pairs, long pairs, descriptor bytes}. */
+int brisk_extractor_pattern(const brisk_extractor* ext, int32_t counts[4], float* points_xys, float* scale_list,
+                            uint32_t* size_list, uint32_t* short_pairs, int32_t* long_pairs);
+
+/* detect(): BriskFeatureDetector::detectImpl -- reference brisk/src/brisk-feature-detector.cc:77-85.
+ * imgs: n frames of w x h u8, row stride `stride` bytes, frame stride `frame_pitch` bytes.
+ * masks: NULL or n masks with the same geometry (key points on zero mask pixels are removed).
+ * kps: [n][cap] out, counts: [n] out (true count; > cap means truncated and BRISK_ERR_CAPACITY). */
+int brisk_detect(brisk_ctx* ctx, brisk_detector* det, const uint8_t* imgs, int n, int w, int h, size_t stride,
+                 size_t frame_pitch, const uint8_t* masks, brisk_keypoint* kps, int32_t* counts, int cap);
+
+/* compute(): BriskDescriptorExtractor::computeImpl -- reference
+ * brisk/src/brisk-descriptor-extractor.cc:589-599,612-778.  kps/counts are in/out: key points too
+ * close to the border are removed (order kept), `angle` is written.  desc: [n][cap][descriptor_size]. */
+int brisk_describe(brisk_ctx* ctx, brisk_extractor* ext, const uint8_t* imgs, int n, int w, int h, size_t stride,
+                   size_t frame_pitch, brisk_keypoint* kps, int32_t* counts, int cap, uint8_t* desc);
+
+/* detect() followed by compute() without leaving the device. */
+int brisk_detect_describe(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const uint8_t* imgs, int n, int w,
+                          int h, size_t stride, size_t frame_pitch, const uint8_t* masks, brisk_keypoint* kps,
+                          int32_t* counts, int cap, uint8_t* desc);
+
+/* Stage dumps for parity tests: pyramid layers of ONE frame concatenated (tight rows), dims[2*i] =
+ * cols, dims[2*i+1] = rows; integral image (h+1)x(w+1) int32; raw corners (x, y, score) of all
+ * layers in detection order with layer_counts[n_layers]. */
+int brisk_debug_pyramid(brisk_ctx* ctx, int octaves, const uint8_t* img, int w, int h, size_t stride, uint8_t* out,
+                        int32_t* dims, int* n_layers);
+int brisk_debug_integral(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, int32_t* out);
+int brisk_debug_corners(brisk_ctx* ctx, brisk_detector* det, const uint8_t* img, int w, int h, size_t stride,
+                        int32_t* corners_xys, int cap, int32_t* layer_counts);
+
+/* Dense FAST 9-16 / AGAST 5-8 score planes (w*h bytes each, threshold 1) of one image. */
+int brisk_debug_scores(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, uint8_t* out916, uint8_t* out58);
+/* Corner-map (u16) and touch-map (u8) planes of all layers (tight rows, concatenated) after the
+ * full detection of one image: internal NMS state, see ethzasl_brisk_b200/csrc/brisk_common.cuh. */
+int brisk_debug_nms_state(brisk_ctx* ctx, brisk_detector* det, const uint8_t* img, int w, int h, size_t stride,
+                          uint16_t* cm_out, uint8_t* bm_out);
+
+/* brisk::Hamming::operator()(a, b, size) -- reference brisk/include/brisk/internal/hamming.h:101-113:
+ * dist[i] = popcount(a[i] xor b[i]) over n descriptor pairs of desc_bytes each. */
+int brisk_hamming_distance(brisk_ctx* ctx, const uint8_t* a, const uint8_t* b, int64_t n, int desc_bytes,
+                           int32_t* dist);
+
+/* knnMatch(): BruteForceMatcher::commonKnnMatchImpl -- reference brisk/src/brute-force-matcher.cc:80-162
+ * (one train collection, no mask).  idx/dist: [nq][k]; ties go to the lowest train index; missing
+ * neighbours (nt < k) are -1.  desc_bytes: 48, 64 or 128. */
+int brisk_hamming_knn(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt,
+                      int desc_bytes, int k, int32_t* idx, int32_t* dist);
+/* Sharded train set: local top-k as packed keys (dist << 32 | global train index), DEVICE buffer
+ * keys[nq][k]; merge n_shards gathered key sets ([shard][nq][k], device) into idx/dist.  The exchange
+ * between GPUs (NCCL all-gather of the keys) is done by the caller. */
+int brisk_hamming_knn_keys(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train_shard, int64_t nt,
+                           int desc_bytes, int k, int64_t global_train_offset, uint64_t* keys_dev);
+int brisk_knn_merge_keys(brisk_ctx* ctx, const uint64_t* gathered_keys_dev, int n_shards, int64_t nq, int k,
+                         int32_t* idx, int32_t* dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRISK_B200_H_ */

@@ -824,19 +824,27 @@ int SmoothedIntensity(const uint8_t* img, int w, const int32_t* integral, float 
     const int bottom = (t7 - t6 + t9 - t8) * r_y1_i;
     return (v + upper + middle + left + right + bottom) / scaling2;
   }
-  int v = 0;
-  for (int Y = 0; Y <= dy + 1; ++Y) {
-    const int wy = Y == 0 ? -1 : (Y == dy + 1 ? 1 : 0);
-    const uint8_t* row = img + x_left + (size_t)w * (y_top + Y);
-    for (int X = 0; X <= dx + 1; ++X) {
-      const int wx = X == 0 ? -1 : (X == dx + 1 ? 1 : 0);
-      int weight;
-      if (wy < 0) weight = wx < 0 ? A : (wx > 0 ? B : r_y_1_i);
-      else if (wy > 0) weight = wx < 0 ? D : (wx > 0 ? C : r_y1_i);
-      else weight = wx < 0 ? r_x_1_i : (wx > 0 ? r_x1_i : scaling);
-      v += weight * (int)row[X];
-    }
+  // explicit weighted sum over the window (:497-529), as an index walk: when
+  // float rounding makes the window degenerate (dx or dy == -1 for 2*sigma ~ 1)
+  // the reference's pointer arithmetic revisits / drifts over neighbouring
+  // pixels, which only the literal walk reproduces.
+  const uint8_t* p = img + x_left + (size_t)w * y_top;
+  long i = 0;
+  int v = A * (int)p[i];
+  ++i;
+  for (long e = i + dx; i < e; ++i) v += r_y_1_i * (int)p[i];
+  v += B * (int)p[i];
+  i += w - dx - 1;
+  for (long ej = i + (long)dy * w; i < ej; i += w - dx - 1) {
+    v += r_x_1_i * (int)p[i];
+    ++i;
+    for (long e = i + dx; i < e; ++i) v += (int)p[i] * scaling;
+    v += r_x1_i * (int)p[i];
   }
+  v += D * (int)p[i];
+  ++i;
+  for (long e = i + dx; i < e; ++i) v += r_y1_i * (int)p[i];
+  v += C * (int)p[i];
   return v / scaling2;
 }
 

@@ -22,7 +22,7 @@ struct HostLayer {
 };
 }  // namespace
 
-extern "C" int emul_agast_detect(const uint8_t* image, int w, int h, int thresh, int octaves, KeyPoint* out, int cap) {
+extern "C" int emul_agast_detect_ex(const uint8_t* image, int w, int h, int thresh, int octaves, KeyPoint* out, int cap, uint16_t* cm_out, uint8_t* bm_out) {
   const int n = octaves == 0 ? 1 : 2 * octaves;
   std::vector<HostLayer> H(n);
   auto alloc = [](HostLayer& l, int w_, int h_) {
@@ -112,5 +112,20 @@ extern "C" int emul_agast_detect(const uint8_t* image, int w, int h, int thresh,
       if (total < cap) out[total] = kp;
       ++total;
     }
+  if (cm_out || bm_out) {
+    size_t off = 0;
+    for (int i = 0; i < n; ++i) {
+      for (int y = 0; y < H[i].h; ++y)
+        for (int x = 0; x < H[i].w; ++x) {
+          if (cm_out) cm_out[off + (size_t)y * H[i].w + x] = H[i].cm[(size_t)y * H[i].pitch + x];
+          if (bm_out) bm_out[off + (size_t)y * H[i].w + x] = H[i].bm[(size_t)y * H[i].pitch + x];
+        }
+      off += (size_t)H[i].w * H[i].h;
+    }
+  }
   return total;
+}
+
+extern "C" int emul_agast_detect(const uint8_t* image, int w, int h, int thresh, int octaves, KeyPoint* out, int cap) {
+  return emul_agast_detect_ex(image, w, h, thresh, octaves, out, cap, nullptr, nullptr);
 }
