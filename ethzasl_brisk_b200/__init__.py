@@ -4,6 +4,7 @@ BRISK descriptors -> Hamming kNN) behind the reference's class surface.
 Importing the package does not load CUDA; constructing a Context does and
 fails loudly when libbrisk_b200.so or a GPU is missing (no CPU fallback).
 """
+from . import build
 from .api import (KP_DTYPE, STAGES, BriskDescriptorExtractor, BriskError, BriskFeatureDetector, BruteForceMatcher,
                   Context, Hamming, default_context, detect_and_compute_batch, lib_path, load_library)
 from .synthetic import random_descriptors, synthetic_batch, synthetic_frame

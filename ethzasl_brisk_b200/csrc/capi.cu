@@ -50,7 +50,7 @@ struct brisk_ctx {
   cudaEvent_t ev[BRISK_STAGE_COUNT + 1] = {};
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   DevBuf pyr, cm, bm, rowcnt, layer_start, corners, fwin, checks, kp_tmp, kp_valid, integral;
-  DevBuf kps, kps_scratch, scales, counts, desc, masks, flag, knn_q, knn_t, knn_keys, knn_part, knn_idx, knn_dist;
+  DevBuf tight, kps, kps_scratch, scales, counts, desc, masks, flag, knn_q, knn_t, knn_keys, knn_part, knn_idx, knn_dist;
 };
 
 struct brisk_detector {
@@ -303,7 +303,21 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       CU_OK(launch_integral(l0, g.frame_elems, g.L[0].pitch, w, h, c, ctx->integral.as<int32_t>(), ctx->stream));
       ctx->launches += 2;
       tm.mark(6);
-      CU_OK(launch_describe(ext->dev, l0, g.frame_elems, g.L[0].pitch, w, h, c, ctx->integral.as<int32_t>(), d_kps, d_counts, cap,
+      // The reference samples a tightly packed image (stride == cols) and a few of its reads land one
+      // column past the row end, i.e. on the first pixel of the next row; give the sampler the same
+      // layout when the pitched plane differs from it.
+      const uint8_t* simg = l0;
+      long long sstride = g.frame_elems;
+      int spitch = g.L[0].pitch;
+      if (spitch != w) {
+        const size_t fs = (size_t)w * h + 64;
+        CU_OK(ctx->tight.ensure((size_t)plan.chunk * fs));
+        for (int f = 0; f < c; ++f)
+          CU_OK(cudaMemcpy2DAsync(ctx->tight.as<uint8_t>() + (size_t)f * fs, w, l0 + (size_t)f * g.frame_elems, g.L[0].pitch, w, h,
+                                  cudaMemcpyDeviceToDevice, ctx->stream));
+        simg = ctx->tight.as<uint8_t>(); sstride = (long long)fs; spitch = w;
+      }
+      CU_OK(launch_describe(ext->dev, simg, sstride, spitch, w, h, c, ctx->integral.as<int32_t>(), d_kps, d_counts, cap,
                             ctx->kps_scratch.as<KeyPoint>(), ctx->scales.as<int>(), d_desc, ctx->stream));
       ctx->launches += 2;
     } else {
@@ -379,7 +393,7 @@ void brisk_ctx_destroy(brisk_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->pyr, &ctx->cm, &ctx->bm, &ctx->rowcnt, &ctx->layer_start, &ctx->corners, &ctx->fwin, &ctx->checks,
                     &ctx->kp_tmp, &ctx->kp_valid, &ctx->integral, &ctx->kps, &ctx->kps_scratch, &ctx->scales, &ctx->counts,
-                    &ctx->desc, &ctx->masks, &ctx->flag, &ctx->knn_q, &ctx->knn_t, &ctx->knn_keys, &ctx->knn_part,
+                    &ctx->desc, &ctx->masks, &ctx->flag, &ctx->tight, &ctx->knn_q, &ctx->knn_t, &ctx->knn_keys, &ctx->knn_part,
                     &ctx->knn_idx, &ctx->knn_dist};
   for (DevBuf* b : bufs) b->release();
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);

@@ -4,6 +4,8 @@
 // Float/double promotions follow the reference expression by expression
 // (SURVEY.md App. A.6); compile without FMA contraction.
 #pragma once
+#include <math.h>
+
 #include "brisk_common.cuh"
 
 namespace briskb200 {
@@ -97,11 +99,14 @@ BRISK_HD int theta_from_estimated(float angle) {
   if (theta >= 1024) theta -= 1024;
   return theta;
 }
-// Rotation bin of a caller-supplied angle (:746-751).
+// Rotation bin of a caller-supplied angle (:746-751).  The reference wraps once,
+// which covers angles in (-360, 720) degrees; beyond that it indexes its table
+// out of bounds (undefined).  Such angles are reduced modulo one turn here.
 BRISK_HD int theta_from_given(float angle) {
   int theta = (int)(1024.0 * ((double)angle / 360.0) + 0.5);
   if (theta < 0) theta += 1024;
   if (theta >= 1024) theta -= 1024;
+  if (theta < 0 || theta >= 1024) theta = ((theta % 1024) + 1024) % 1024;
   return theta;
 }
 

@@ -1,0 +1,279 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle, the golden
+fixtures and size-independent properties.  Needs a GPU: `pytest -m gpu`."""
+import numpy as np
+import pytest
+
+import ethzasl_brisk_b200 as bb
+from conftest import kp_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def test_native_library_is_loaded(ctx):
+    # the parity claims below are about libbrisk_b200.so, not a fallback
+    maps = open("/proc/self/maps").read()
+    assert "libbrisk_b200.so" in maps
+
+
+@pytest.mark.parametrize("w,h", [(752, 480), (800, 640), (500, 333), (1920, 1080), (193, 97), (97, 200), (250, 160)])
+def test_pyramid_bit_exact(ctx, oracle, w, h):
+    # widths cover all rounding regimes of the reference's SSE loops
+    img = bb.synthetic_frame(w, h, 100 + w)
+    for octaves in (4, 1):
+        mine = ctx.debug_pyramid(img, octaves)
+        want, _ = oracle.pyramid(img, octaves)
+        assert len(mine) == len(want)
+        for a, b in zip(mine, want):
+            assert a.shape == b.shape and np.array_equal(a, b)
+
+
+def test_pyramid_six_octaves(ctx, oracle):
+    img = bb.synthetic_frame(1600, 1200, 5)
+    mine = ctx.debug_pyramid(img, 6)
+    want, _ = oracle.pyramid(img, 6)
+    assert len(mine) == 12
+    for a, b in zip(mine, want):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("w,h", [(752, 480), (641, 479), (131, 67)])
+def test_integral_bit_exact(ctx, oracle, w, h):
+    img = bb.synthetic_frame(w, h, 7)
+    assert np.array_equal(ctx.debug_integral(img), oracle.integral8(img))
+    white = np.full((h, w), 255, np.uint8)  # int32 head-room
+    assert ctx.debug_integral(white)[-1, -1] == 255 * w * h
+
+
+def test_raw_corners_match_detector_order(ctx, oracle, golden):
+    img = golden["image0"]
+    det = bb.BriskFeatureDetector(60, 4, ctx=ctx)
+    c, lc = det.debug_corners(img)
+    pyr, _ = oracle.pyramid(img, 4)
+    off = 0
+    for li, layer in enumerate(pyr):
+        _, want = oracle.layer_dump(layer, 60)
+        assert np.array_equal(c[off:off + lc[li]], want)  # x, y, score in raster order
+        off += lc[li]
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_golden_ast_fixture(ctx, golden, i):
+    # the reference's own ValidationAST fixture (test-binary-equal.cc:315-333), bit for bit
+    img = golden[f"image{i}"]
+    det = bb.BriskFeatureDetector(70, ctx=ctx)
+    ext = bb.BriskDescriptorExtractor(ctx=ctx)
+    k, d = ext.compute(img, det.detect(img))
+    gk, gd = golden[f"ast{i}_kps"], golden[f"ast{i}_desc"]
+    assert len(k) == len(gk)
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(k[f], gk[f]), f
+    # angle: double atan2 on the device (<= 2 ulp) then rounded to float; tolerance 1e-4 degree and
+    # identical descriptors (same rotation bin) -- north_star's stated bar
+    assert np.abs(k["angle"] - gk["angle"]).max() <= 1e-4
+    assert np.array_equal(d, gd)
+
+
+@pytest.mark.parametrize("thresh,octaves", [(60, 4), (70, 3), (40, 2), (70, 0), (60, 1), (30, 4)])
+def test_detect_bit_exact(ctx, oracle, golden, thresh, octaves):
+    det = bb.BriskFeatureDetector(thresh, octaves, ctx=ctx)
+    det.set_corner_capacity(200000)
+    for img in (golden["image0"], bb.synthetic_frame(752, 480, 1000), bb.synthetic_frame(500, 333, 3)):
+        assert kp_equal(det.detect(img), oracle.agast_detect(img, thresh, octaves))
+
+
+def test_detect_tie_heavy(ctx, oracle):
+    rng = np.random.default_rng(7)
+    det = bb.BriskFeatureDetector(35, 3, ctx=ctx)
+    det.set_corner_capacity(100000)
+    for _ in range(3):
+        img = (rng.integers(0, 4, (240, 320)) * 60 + rng.integers(0, 8, (240, 320))).astype(np.uint8)
+        assert kp_equal(det.detect(img), oracle.agast_detect(img, 35, 3))
+
+
+def test_detect_mask(ctx, oracle, golden):
+    img = golden["image1"]
+    mask = np.zeros_like(img)
+    mask[50:600, 100:650] = 1
+    det = bb.BriskFeatureDetector(60, 4, ctx=ctx)
+    assert kp_equal(det.detect(img, mask), oracle.agast_detect(img, 60, 4, mask=mask))
+
+
+def test_detect_empty_and_flat(ctx):
+    det = bb.BriskFeatureDetector(60, 4, ctx=ctx)
+    assert len(det.detect(np.full((480, 752), 90, np.uint8))) == 0
+    kps, counts = det.detect_batch(np.zeros((0, 480, 752), np.uint8))
+    assert kps.shape[0] == 0 and counts.shape[0] == 0
+
+
+def test_unsupported_configurations_fail_loudly(ctx):
+    img = bb.synthetic_frame(320, 240, 1)
+    for bad in (bb.BriskFeatureDetector(20, 4, ctx=ctx), bb.BriskFeatureDetector(60, 7, ctx=ctx),
+                bb.BriskFeatureDetector(60, 4, False, ctx=ctx)):
+        with pytest.raises(bb.BriskError):
+            bad.detect(img)
+    with pytest.raises(bb.BriskError):
+        bb.BriskDescriptorExtractor(True, True, 3, ctx=ctx)
+
+
+@pytest.mark.parametrize("version,ps,rot,scale", [(2, 1.0, True, True), (1, 1.0, True, True), (2, 0.5, True, True),
+                                                   (2, 1.0, False, True), (2, 1.0, True, False), (1, 0.7, True, True)])
+def test_describe_bit_exact_given_keypoints(ctx, oracle, golden, version, ps, rot, scale):
+    ext = bb.BriskDescriptorExtractor(rot, scale, version, ps, ctx=ctx)
+    assert ext.descriptorSize() == oracle.pattern_dump(version, ps)["strings"]
+    for img in (golden["image0"], bb.synthetic_frame(500, 333, 3)):
+        kp = oracle.agast_detect(img, 45, 4)
+        k1, d1 = ext.compute(img, kp)
+        k2, d2 = oracle.describe(img, kp, rot, scale, version, ps)
+        assert len(k1) == len(k2)
+        for f in ("x", "y", "size", "response", "octave", "class_id"):
+            assert np.array_equal(k1[f], k2[f]), f
+        assert np.abs(k1["angle"] - k2["angle"]).max() <= 1e-4
+        assert np.array_equal(d1, d2)
+
+
+def test_describe_given_angles_and_edge_cases(ctx, oracle, golden):
+    img = golden["image1"]
+    kp = oracle.agast_detect(img, 60, 4)
+    kp["angle"] = np.linspace(-359, 719, len(kp)).astype(np.float32)  # caller-supplied angles, incl. wrap-around
+    kp["angle"][::7] = -1
+    kp["size"][::11] = 0.0   # log(0) path -> scale index 0
+    kp["size"][::13] = 1e9   # saturates at scale index 63 -> culled by the border test
+    ext = bb.BriskDescriptorExtractor(ctx=ctx)
+    k1, d1 = ext.compute(img, kp)
+    k2, d2 = oracle.describe(img, kp)
+    assert len(k1) == len(k2) and np.array_equal(d1, d2)
+    k0, d0 = ext.compute(img, kp[:0])
+    assert len(k0) == 0 and d0.shape == (0, 48)
+
+
+def test_pattern_tables_match_reference_construction(ctx, oracle):
+    for version, ps in ((2, 1.0), (1, 1.0), (2, 0.5)):
+        mine = bb.BriskDescriptorExtractor(True, True, version, ps, ctx=ctx).pattern()
+        want = oracle.pattern_dump(version, ps)
+        for key in ("pts", "scale_list", "size_list", "short_pairs", "long_pairs"):
+            assert np.array_equal(mine[key], want[key]), (version, ps, key)
+
+
+def test_fused_batch_matches_per_frame(ctx, oracle):
+    frames = bb.synthetic_batch(5, 752, 480, 1000)
+    det = bb.BriskFeatureDetector(60, 4, ctx=ctx)
+    ext = bb.BriskDescriptorExtractor(ctx=ctx)
+    kps, counts, desc = bb.detect_and_compute_batch(det, ext, frames, cap=8192)
+    for f in range(len(frames)):
+        k2, d2 = oracle.describe(frames[f], oracle.agast_detect(frames[f], 60, 4))
+        n = counts[f]
+        assert n == len(k2)
+        for fld in ("x", "y", "size", "response", "octave"):
+            assert np.array_equal(kps[f, :n][fld], k2[fld])
+        assert np.array_equal(desc[f, :n], d2)
+
+
+def test_chunked_batch_equals_single_pass(ctx):
+    # small workspace limit forces several chunks; results must not depend on chunking
+    frames = bb.synthetic_batch(6, 640, 480, 50)
+    det = bb.BriskFeatureDetector(60, 4, ctx=ctx)
+    ext = bb.BriskDescriptorExtractor(ctx=ctx)
+    a = bb.detect_and_compute_batch(det, ext, frames, cap=4096)
+    small = bb.Context(0, workspace_limit=96 << 20)
+    det2 = bb.BriskFeatureDetector(60, 4, ctx=small)
+    ext2 = bb.BriskDescriptorExtractor(ctx=small)
+    b = bb.detect_and_compute_batch(det2, ext2, frames, cap=4096)
+    assert np.array_equal(a[1], b[1])
+    for f in range(len(frames)):
+        n = a[1][f]
+        assert np.array_equal(a[0][f, :n], b[0][f, :n]) and np.array_equal(a[2][f, :n], b[2][f, :n])
+
+
+def test_device_resident_inputs_and_outputs(ctx):
+    import torch
+    frames = bb.synthetic_batch(3, 752, 480, 1000)
+    det = bb.BriskFeatureDetector(60, 4, ctx=ctx)
+    ext = bb.BriskDescriptorExtractor(ctx=ctx)
+    host = bb.detect_and_compute_batch(det, ext, frames, cap=4096)
+    dev_frames = torch.from_numpy(frames).cuda()
+    kps = torch.zeros((3, 4096, 7), dtype=torch.float32, device="cuda")
+    counts = torch.zeros(3, dtype=torch.int32, device="cuda")
+    desc = torch.zeros((3, 4096, 48), dtype=torch.uint8, device="cuda")
+    bb.detect_and_compute_batch(det, ext, dev_frames, cap=4096, out=(kps, counts, desc))
+    torch.cuda.synchronize()
+    assert np.array_equal(counts.cpu().numpy(), host[1])
+    for f in range(3):
+        n = host[1][f]
+        assert np.array_equal(kps[f, :n].cpu().numpy().view(np.uint8).reshape(n, 28), host[0][f, :n].view(np.uint8).reshape(n, 28))
+        assert np.array_equal(desc[f, :n].cpu().numpy(), host[2][f, :n])
+
+
+def test_capacity_overflow_is_reported(ctx):
+    img = bb.synthetic_frame(752, 480, 1000)
+    det = bb.BriskFeatureDetector(60, 4, ctx=ctx)
+    with pytest.raises(bb.BriskError) as e:
+        det.detect(img, cap=10)
+    assert e.value.code == -4
+    det.set_corner_capacity(64)
+    with pytest.raises(bb.BriskError):
+        det.detect(img)
+
+
+@pytest.mark.parametrize("nbytes", [48, 64])
+@pytest.mark.parametrize("k", [1, 2, 3, 8])
+def test_knn_bit_exact(ctx, oracle, nbytes, k):
+    q = bb.random_descriptors(700, nbytes, 5)
+    t = bb.random_descriptors(5000, nbytes, 6)
+    t[100] = q[3]
+    t[200] = q[3]  # exact ties: lowest train index first (reference brute-force-matcher.cc:138-157)
+    m = bb.BruteForceMatcher(ctx=ctx)
+    i1, d1 = m.knn(q, t, k)
+    i2, d2 = oracle.knn(q, t, k)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    assert i1[3, 0] == 100 and d1[3, 0] == 0
+
+
+def test_knn_edge_cases(ctx, oracle):
+    m = bb.BruteForceMatcher(ctx=ctx)
+    q = bb.random_descriptors(5, 64, 1)
+    t = bb.random_descriptors(1, 64, 2)
+    idx, dist = m.knn(q, t, 2)  # fewer train rows than k
+    assert np.all(idx[:, 0] == 0) and np.all(idx[:, 1] == -1) and np.all(dist[:, 1] == -1)
+    assert bb.Hamming(ctx)(q[0], t[0]) == oracle.hamming(q[0], t[0])
+    # reference test-popcount.cc: one hand-checkable 128-bit pair inside a 48-byte row
+    a = np.zeros(48, np.uint8)
+    b = np.zeros(48, np.uint8)
+    a[0], b[0], a[17], b[40] = 0xFF, 0x0F, 0x01, 0x80
+    assert bb.Hamming(ctx)(a, b) == 4 + 1 + 1
+
+
+def test_knn_large_properties(ctx):
+    # BASELINE config 5 shape at reduced size: idempotence (train == query -> distance 0 at own
+    # index), sortedness, and agreement of a split train set with the unsplit one.
+    import torch
+    t = torch.from_numpy(bb.random_descriptors(200000, 64, 6)).cuda()
+    q = t[:20000].clone()
+    m = bb.BruteForceMatcher(ctx=ctx)
+    idx, dist = m.knn(q, t, 2)
+    idx, dist = idx.cpu().numpy(), dist.cpu().numpy()
+    assert np.array_equal(idx[:, 0], np.arange(20000)) and np.all(dist[:, 0] == 0)
+    assert np.all(dist[:, 1] >= dist[:, 0])
+    # sharded: two halves -> keys -> merge == unsplit
+    keys = torch.zeros((2, 20000, 2), dtype=torch.int64, device="cuda")
+    m.knn_keys(q, t[:100000], 2, 0, keys[0])
+    m.knn_keys(q, t[100000:], 2, 100000, keys[1])
+    i2 = torch.zeros((20000, 2), dtype=torch.int32, device="cuda")
+    d2 = torch.zeros((20000, 2), dtype=torch.int32, device="cuda")
+    m.merge_keys(keys, 2, 20000, 2, i2, d2)
+    assert np.array_equal(i2.cpu().numpy(), idx) and np.array_equal(d2.cpu().numpy(), dist)
+
+
+def test_full_size_properties_1080p(ctx, oracle):
+    # BASELINE config 3 frame size: one frame against the oracle, and batch invariance
+    # (a frame's result must not depend on its neighbours in the batch).
+    frames = bb.synthetic_batch(3, 1920, 1080, 2000)
+    det = bb.BriskFeatureDetector(60, 4, ctx=ctx)
+    ext = bb.BriskDescriptorExtractor(ctx=ctx)
+    kps, counts, desc = bb.detect_and_compute_batch(det, ext, frames, cap=32768)
+    k2, d2 = oracle.describe(frames[0], oracle.agast_detect(frames[0], 60, 4))
+    n = counts[0]
+    assert n == len(k2) and np.array_equal(desc[0, :n], d2)
+    for fld in ("x", "y", "size", "response", "octave"):
+        assert np.array_equal(kps[0, :n][fld], k2[fld])
+    k1, c1, d1 = bb.detect_and_compute_batch(det, ext, frames[2:3], cap=32768)
+    assert c1[0] == counts[2] and np.array_equal(d1[0, :c1[0]], desc[2, :counts[2]])

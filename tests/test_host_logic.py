@@ -1,0 +1,84 @@
+"""CPU-side checks of the product: the device code's NMS / refinement logic
+compiled for the host (tests/host_emul) against the oracle, the C-ABI library's
+exported symbols, and the synthetic-data helpers.  No GPU needed."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, kp_equal
+from ethzasl_brisk_b200.synthetic import synthetic_frame
+from oracle.ref import KP_DTYPE
+
+
+@pytest.fixture(scope="module")
+def emul():
+    src = ROOT / "tests" / "host_emul" / "emul_agast.cc"
+    lib = ROOT / "tests" / "host_emul" / "libemul_agast.so"
+    deps = [src] + list((ROOT / "ethzasl_brisk_b200" / "csrc").glob("*.cuh"))
+    if not lib.exists() or any(d.stat().st_mtime > lib.stat().st_mtime for d in deps):
+        subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-msse2", "-ffp-contract=off", "-fPIC", "-shared",
+                        "-Wno-unknown-pragmas", "-o", str(lib), str(src)], check=True)
+    handle = C.CDLL(str(lib))
+
+    def detect(img, thresh, octaves, cap=1 << 18):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        k = np.zeros(cap, KP_DTYPE)
+        n = handle.emul_agast_detect(img.ctypes.data_as(C.c_void_p), w, h, thresh, octaves, k.ctypes.data_as(C.c_void_p), cap)
+        return k[:n].copy()
+    return detect
+
+
+@pytest.mark.parametrize("thresh,octaves", [(70, 3), (60, 4), (30, 2), (70, 0), (45, 1)])
+def test_parallel_nms_formulation_golden(emul, oracle, golden, thresh, octaves):
+    for i in (0, 1):
+        img = golden[f"image{i}"]
+        assert kp_equal(emul(img, thresh, octaves), oracle.agast_detect(img, thresh, octaves))
+
+
+@pytest.mark.parametrize("seed,w,h,thresh,octaves", [(1, 752, 480, 60, 4), (2, 640, 480, 40, 3), (3, 500, 333, 30, 4),
+                                                      (5, 321, 243, 35, 2), (6, 800, 600, 60, 0)])
+def test_parallel_nms_formulation_synthetic(emul, oracle, seed, w, h, thresh, octaves):
+    img = synthetic_frame(w, h, seed)
+    assert kp_equal(emul(img, thresh, octaves), oracle.agast_detect(img, thresh, octaves))
+
+
+def test_parallel_nms_formulation_tie_heavy(emul, oracle):
+    # quantised noise: plateaus of equal scores exercise the cache-state reconstruction
+    rng = np.random.default_rng(7)
+    for k in range(3):
+        img = (rng.integers(0, 4, (240, 320)) * 60 + rng.integers(0, 8, (240, 320))).astype(np.uint8)
+        assert kp_equal(emul(img, 30 + 5 * k, 3), oracle.agast_detect(img, 30 + 5 * k, 3))
+
+
+def test_capi_exports_every_declared_symbol():
+    from ethzasl_brisk_b200 import build, lib_path
+    build_lib = build.build()  # no-op when up to date; nvcc cross-compiles without a GPU
+    assert Path(build_lib) == lib_path()
+    header = (ROOT / "include" / "brisk_b200.h").read_text()
+    declared = set(re.findall(r"\b(brisk_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = C.CDLL(str(lib_path()))
+    missing = [name for name in sorted(declared) if not hasattr(lib, name)]
+    assert not missing, missing
+
+
+def test_missing_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ethzasl_brisk_b200 as bb
+    with pytest.raises(bb.BriskError):
+        bb.Context(0)
+
+
+def test_synthetic_frames_are_deterministic():
+    a = synthetic_frame(320, 240, 42)
+    b = synthetic_frame(320, 240, 42)
+    c = synthetic_frame(320, 240, 43)
+    assert a.dtype == np.uint8 and a.shape == (240, 320)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)

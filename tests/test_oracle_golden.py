@@ -1,0 +1,119 @@
+"""The oracle against the reference's own golden fixtures and against the
+compiled reference (oracle/_ref).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import kp_equal
+from ethzasl_brisk_b200.synthetic import random_descriptors, synthetic_frame
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_golden_ast(oracle, golden, i):
+    # reference test-binary-equal.cc:323-326: BriskFeatureDetector(70) + default extractor
+    img = golden[f"image{i}"]
+    k = oracle.agast_detect(img, 70, 3)
+    k2, d = oracle.describe(img, k)
+    assert kp_equal(k2, golden[f"ast{i}_kps"])          # all 7 fields, exact
+    assert np.array_equal(d, golden[f"ast{i}_desc"])    # Hamming 0 (the reference allows <= 5)
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_golden_harris(oracle, golden, i):
+    # reference test-binary-equal.cc:73-89,305-311: octaves 0, uniformity radius 30, abs threshold 20
+    img = golden[f"image{i}"]
+    k = oracle.harris_detect(img, 0, 30.0, 20.0)
+    k2, d = oracle.describe(img, k, True, True)
+    assert kp_equal(k2, golden[f"harris{i}_kps"])
+    assert np.array_equal(d, golden[f"harris{i}_desc"])
+
+
+def test_golden_match_homography(oracle, golden):
+    # reference test-match.cc:50-116: BriskFeatureDetector(70, 2), best match with Hamming < 50 must
+    # agree with H_1to2 within 5 px.
+    H = np.array([[8.7976964e-01, 3.1245438e-01, -3.9430589e+01], [-1.8389418e-01, 9.3847198e-01, 1.5315784e+02],
+                  [1.9641425e-04, -1.6015275e-05, 1.0000000e+00]])
+    k1, d1 = oracle.describe(golden["image0"], oracle.agast_detect(golden["image0"], 70, 2))
+    k2, d2 = oracle.describe(golden["image1"], oracle.agast_detect(golden["image1"], 70, 2))
+    idx, dist = oracle.knn(d1, d2, 1)
+    outliers = matches = 0
+    for q in range(len(k1)):
+        if dist[q, 0] < 50:
+            matches += 1
+            p = H @ np.array([k1["x"][q], k1["y"][q], 1.0])
+            p = p[:2] / p[2]
+            t = idx[q, 0]
+            if np.hypot(p[0] - k2["x"][t], p[1] - k2["y"][t]) > 5:
+                outliers += 1
+    assert matches > 50 and outliers == 0
+
+
+def test_popcount_kat(oracle):
+    # reference test-popcount.cc:72-86 style known answer: bit loop vs primitive
+    a = random_descriptors(1, 64, 1)[0]
+    b = random_descriptors(1, 64, 2)[0]
+    expect = int(np.unpackbits(a ^ b).sum())
+    assert oracle.hamming(a, b) == expect
+    assert oracle.hamming(a[:48], b[:48]) == int(np.unpackbits(a[:48] ^ b[:48]).sum())
+
+
+@pytest.mark.parametrize("w,h", [(752, 480), (500, 320), (376, 240), (250, 160), (125, 80), (801, 601), (47, 33)])
+def test_sampling_vs_ref(oracle, ref, w, h):
+    img = synthetic_frame(w, h, w + h)
+    assert np.array_equal(oracle.halfsample8(img), ref.halfsample8(img))
+    assert np.array_equal(oracle.twothirdsample8(img), ref.twothirdsample8(img))
+
+
+def test_stages_vs_ref(oracle, ref, golden):
+    for img in (golden["image0"], synthetic_frame(640, 480, 7)):
+        t1, c1 = ref.layer_dump(img, 60)
+        t2, c2 = oracle.layer_dump(img, 60)
+        assert np.array_equal(t1, t2) and np.array_equal(c1, c2)
+        a1, b1 = ref.dense_scores(img)
+        a2, b2 = oracle.dense_scores(img)
+        assert np.array_equal(a1, a2) and np.array_equal(b1, b2)
+        assert np.array_equal(ref.integral8(img), oracle.integral8(img))
+        assert np.array_equal(ref.harris_scores(img), oracle.harris_scores(img))
+        assert np.array_equal(ref.harris_maxima(img, 20), oracle.harris_maxima(img, 20))
+
+
+@pytest.mark.parametrize("thresh,octaves", [(60, 4), (70, 3), (35, 2), (70, 0), (60, 1)])
+def test_agast_detect_vs_ref(oracle, ref, golden, thresh, octaves):
+    for img in (golden["image1"], synthetic_frame(752, 480, 1000)):
+        assert kp_equal(oracle.agast_detect(img, thresh, octaves), ref.agast_detect(img, thresh, octaves))
+
+
+def test_agast_mask_vs_ref(oracle, ref, golden):
+    img = golden["image0"]
+    mask = np.zeros_like(img)
+    mask[100:500, 200:700] = 255
+    assert kp_equal(oracle.agast_detect(img, 60, 4, mask=mask), ref.agast_detect(img, 60, 4, mask=mask))
+
+
+@pytest.mark.parametrize("version,ps,rot,scale", [(2, 1.0, True, True), (1, 1.0, True, True), (2, 0.5, True, True),
+                                                   (2, 1.0, False, True), (2, 1.0, True, False), (1, 0.7, True, True)])
+def test_describe_vs_ref(oracle, ref, golden, version, ps, rot, scale):
+    img = golden["image0"]
+    k = ref.agast_detect(img, 60, 4)
+    a, da = ref.describe(img, k, rot, scale, version, ps)
+    b, db = oracle.describe(img, k, rot, scale, version, ps)
+    assert kp_equal(a, b) and np.array_equal(da, db)
+    pa, pb = ref.pattern_dump(version, ps), oracle.pattern_dump(version, ps)
+    for key in ("pts", "scale_list", "size_list", "short_pairs", "long_pairs"):
+        assert np.array_equal(pa[key], pb[key]), key
+
+
+@pytest.mark.parametrize("octaves,radius,max_kpt", [(1, 30.0, -1), (4, 30.0, -1), (2, 10.0, 300)])
+def test_harris_detect_vs_ref(oracle, ref, golden, octaves, radius, max_kpt):
+    for img in (golden["image1"], synthetic_frame(752, 480, 1001)):
+        assert kp_equal(oracle.harris_detect(img, octaves, radius, 20.0, max_kpt), ref.harris_detect(img, octaves, radius, 20.0, max_kpt))
+
+
+def test_knn_vs_ref_primitive(oracle, ref):
+    q = random_descriptors(40, 64, 5)
+    t = random_descriptors(300, 64, 6)
+    t[7] = q[3]
+    t[9] = q[3]  # exact tie -> lowest train index
+    i1, d1 = oracle.knn(q, t, 2)
+    i2, d2 = ref.knn(q, t, 2)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    assert i1[3, 0] == 7 and i1[3, 1] == 9 and d1[3, 0] == 0
