@@ -151,7 +151,7 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
   plan->integral_elems = ext ? (size_t)(w + 1) * (h + 1) : 0;
   const int desc_bytes = ext ? ext->dev.desc_bytes : 0;
   size_t per_frame = (size_t)g.frame_elems;  // image planes
-  if (det) per_frame += (size_t)g.frame_elems * 3 + (size_t)ws.total_rows * 4 + (size_t)ws.corner_cap * (4 + 32 + 24 + 28 + 1);
+  if (det) per_frame += (size_t)g.frame_elems * 3 + (size_t)ws.total_rows * 4 + (size_t)ws.corner_cap * (4 + 32 + 32 + 28 + 1);
   per_frame += plan->integral_elems * 4 + (size_t)cap * (28 * 2 + 4 + desc_bytes) + (size_t)w * h /* mask */;
   long long chunk = (long long)(ctx->ws_limit / std::max<size_t>(per_frame, 1));
   if (chunk < 1) chunk = 1;
@@ -167,7 +167,7 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
     CU_OK(ctx->layer_start.ensure(c * (kMaxLayers + 1) * 4));
     CU_OK(ctx->corners.ensure(c * ws.corner_cap * 4));
     CU_OK(ctx->fwin.ensure(c * ws.corner_cap * 32));
-    CU_OK(ctx->checks.ensure(c * ws.corner_cap * 24));
+    CU_OK(ctx->checks.ensure(c * ws.corner_cap * 32));
     CU_OK(ctx->kp_tmp.ensure(c * ws.corner_cap * 28));
     CU_OK(ctx->kp_valid.ensure(c * ws.corner_cap));
   }
@@ -292,7 +292,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       CU_OK(launch_corner_lists(g, plan.ws, c, ctx->flag.as<int>(), ctx->stream));
       ctx->launches += 1 + g.n_layers;
       tm.mark(4);
-      CU_OK(launch_agast_nms(g, plan.ws, c, d_masks, mask_fs, mask_pitch, d_kps, d_counts, cap, ctx->stream));
+      CU_OK(launch_agast_nms(g, plan.ws, c, d_masks, mask_fs, mask_pitch, d_kps, d_counts, cap, ctx->flag.as<int>(), ctx->stream));
       ctx->launches += 5;
     } else {
       tm.mark(3); tm.mark(4);
@@ -342,6 +342,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     }
     tm.mark(8);
     CU_OK(cudaStreamSynchronize(ctx->stream));
+    if (hflag == 2) return fail(ctx, BRISK_ERR_CUDA, "internal error: tie resolution did not converge");
     if (hflag) corner_overflow = true;
     if (ctx->timing) {
       static const int stage_of[8] = {BRISK_STAGE_H2D, BRISK_STAGE_PYRAMID, BRISK_STAGE_DETECT, BRISK_STAGE_LISTS, BRISK_STAGE_NMS,

@@ -17,7 +17,7 @@ struct DetectWorkspace {
   int* layer_start;     // [frame][kMaxLayers + 1] first corner slot of each layer
   uint32_t* corners;    // [frame][corner_cap] packed x | y << 13 | layer << 26, layer-major raster order
   uint8_t* fwin;        // [frame][corner_cap][32] 5x5 FAST scores of tying corners
-  float* checks;        // [frame][corner_cap][6]  CheckResult
+  float* checks;        // [frame][corner_cap][8]  CheckResult (32 bytes)
   KeyPoint* kp_tmp;     // [frame][corner_cap]
   uint8_t* kp_valid;    // [frame][corner_cap]
   int total_rows;       // sum of layer heights
@@ -36,7 +36,7 @@ cudaError_t launch_corner_lists(const PyramidGeom& g, const DetectWorkspace& ws,
 // Scale-space NMS + refinement -> ordered key points [frame][kp_cap], counts[frame].
 cudaError_t launch_agast_nms(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, const uint8_t* masks,
                              long long mask_frame_stride, int mask_pitch, KeyPoint* out, int* counts, int kp_cap,
-                             cudaStream_t stream);
+                             int* error_flag, cudaStream_t stream);
 
 cudaError_t launch_dense_scores(const LayerGeom& L, const uint8_t* img, uint8_t* out916, uint8_t* out58, cudaStream_t stream);
 

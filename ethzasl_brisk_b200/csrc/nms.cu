@@ -70,16 +70,18 @@ nms_checks_kernel(PyramidGeom g, DetectWorkspace ws) {
   if ((ev & kCmDecided) && !(ev & kCmAccept)) return;
   CheckResult r;
   const bool ok = nms_checks(fv.v, g.n_layers, layer, x, y, &r);
-  if (ok) {
-    *e = ev | kCmChecks;
-    float* dst = ws.checks + ((long long)frame * ws.corner_cap + k) * 6;
-    dst[0] = r.max_above; dst[1] = r.dxa; dst[2] = r.dya; dst[3] = r.max_below; dst[4] = r.dxb; dst[5] = r.dyb;
-  }
+  if (ok) *e = ev | kCmChecks;
+  // kept even when the checks fail: the footprint of the scan of the layer above is needed by the chain kernel
+  *reinterpret_cast<CheckResult*>(ws.checks + ((long long)frame * ws.corner_cap + k) * 8) = r;
 }
 
+// One CTA per frame, layers in order (layer i+1 needs the touch marks that layer i's accepted
+// corners leave on it).  Within a layer the tying corners are resolved in parallel rounds: a corner
+// whose raster-earlier tying neighbours are all decided is decidable, whatever the order.
 __global__ void __launch_bounds__(256)
-nms_chain_kernel(PyramidGeom g, DetectWorkspace ws) {
+nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag) {
   __shared__ FrameViews fv;
+  __shared__ int s_left;
   const int frame = blockIdx.x, tid = threadIdx.x;
   if (tid == 0) make_views(g, ws, frame, &fv);
   __syncthreads();
@@ -89,38 +91,34 @@ nms_chain_kernel(PyramidGeom g, DetectWorkspace ws) {
     const int mode = g.n_layers == 1 ? kModeSingle : (layer == g.n_layers - 1 ? kModeLast : kModeMid);
     const int begin = min(ls[layer], ws.corner_cap), end = min(ls[layer + 1], ws.corner_cap);
     const LayerView& L = fv.v[layer];
-    // tying corners, strictly in raster order (warp 0 finds them 32 at a time, lane 0 decides)
-    if (tid < 32) {
-      for (int base = begin; base < end; base += 32) {
-        const int k = base + tid;
-        int x = 0, y = 0, l2 = 0;
-        bool tie = false;
-        if (k < end) {
-          unpack_corner(corners[k], &x, &y, &l2);
-          tie = !(L.cm[(long long)y * L.pitch + x] & kCmDecided);
-        }
-        uint32_t m = __ballot_sync(0xffffffffu, tie);
-        while (m) {
-          const int src = __ffs(m) - 1;
-          m &= m - 1;
-          const int tx = __shfl_sync(0xffffffffu, x, src), ty = __shfl_sync(0xffffffffu, y, src);
-          if (tid == 0) {
-            const uint8_t* fw = ws.fwin + ((long long)frame * ws.corner_cap + base + src) * 32;
-            const bool ok = nms_tie_decide(L, mode, tx, ty, fw);
-            uint16_t* e = L.cm + (long long)ty * L.pitch + tx;
-            *e = *e | (uint16_t)(kCmDecided | (ok ? kCmAccept : 0));
-          }
-          __syncwarp();
-        }
+    for (int round = 0;; ++round) {
+      if (tid == 0) s_left = 0;
+      __syncthreads();
+      int left = 0;
+      for (int k = begin + tid; k < end; k += blockDim.x) {
+        int x, y, l2;
+        unpack_corner(corners[k], &x, &y, &l2);
+        uint16_t* e = L.cm + (long long)y * L.pitch + x;
+        const uint16_t ev = *e;
+        if (ev & kCmDecided) continue;
+        const int verdict = nms_tie_decide(L, mode, x, y, ws.fwin + ((long long)frame * ws.corner_cap + k) * 32);
+        if (verdict < 0) ++left;
+        else *e = ev | (uint16_t)(kCmDecided | (verdict ? kCmAccept : 0));
       }
+      if (left) atomicAdd(&s_left, left);
+      __syncthreads();
+      const int remaining = s_left;
+      __syncthreads();
+      if (remaining == 0) break;
+      if (round > (1 << 16)) { if (tid == 0) atomicExch(error_flag, 2); break; }  // cannot happen: dependencies are acyclic
     }
-    __syncthreads();
     // footprint of the accepted corners on the layer above
     if (mode == kModeMid) {
       for (int k = begin + tid; k < end; k += blockDim.x) {
         int x, y, l2;
         unpack_corner(corners[k], &x, &y, &l2);
-        if (L.cm[(long long)y * L.pitch + x] & kCmAccept) mark_above(fv.v, layer, x, y);
+        if (L.cm[(long long)y * L.pitch + x] & kCmAccept)
+          mark_above(fv.v, layer, x, y, *reinterpret_cast<const CheckResult*>(ws.checks + ((long long)frame * ws.corner_cap + k) * 8));
       }
     }
     __syncthreads();
@@ -141,8 +139,7 @@ refine_kernel(PyramidGeom g, DetectWorkspace ws) {
   const uint16_t e = fv.v[layer].cm[(long long)y * fv.v[layer].pitch + x];
   bool valid = false;
   if ((e & kCmAccept) && (e & kCmChecks)) {
-    const float* src = ws.checks + slot * 6;
-    CheckResult r{src[0], src[1], src[2], src[3], src[4], src[5]};
+    const CheckResult r = *reinterpret_cast<const CheckResult*>(ws.checks + slot * 8);
     KeyPoint kp;
     valid = refine_emit(fv.v, g.n_layers, layer, x, y, r, &kp);
     if (valid) ws.kp_tmp[slot] = kp;
@@ -206,13 +203,13 @@ cudaError_t launch_dense_scores(const LayerGeom& L, const uint8_t* img, uint8_t*
 
 cudaError_t launch_agast_nms(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, const uint8_t* masks,
                              long long mask_frame_stride, int mask_pitch, KeyPoint* out, int* counts, int kp_cap,
-                             cudaStream_t stream) {
+                             int* error_flag, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(ws.bm, 0, (size_t)n_frames * g.frame_elems, stream);
   if (e != cudaSuccess) return e;
   dim3 grid((ws.corner_cap + 127) / 128, n_frames);
   nms_prefix_kernel<<<grid, 128, 0, stream>>>(g, ws);
   nms_checks_kernel<<<grid, 128, 0, stream>>>(g, ws);
-  nms_chain_kernel<<<n_frames, 256, 0, stream>>>(g, ws);
+  nms_chain_kernel<<<n_frames, 256, 0, stream>>>(g, ws, error_flag);
   refine_kernel<<<grid, 128, 0, stream>>>(g, ws);
   compact_kernel<<<n_frames, 256, 0, stream>>>(g, ws, masks, mask_frame_stride, mask_pitch, out, counts, kp_cap);
   return cudaGetLastError();

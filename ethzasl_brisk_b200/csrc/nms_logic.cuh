@@ -130,27 +130,37 @@ BRISK_HD float patch3x3(const LayerView& L, int x, int y, float* dx, float* dy, 
 // neighbouring layer.  Returns false when a score above `threshold` is met (not
 // tested on the bottom row, as in the reference).  BELOW adds the tie rule of
 // :987-1010 on interior pixels.
+//
+// `steps` receives the number of patch positions that were evaluated (the scan
+// order is fixed, so this number identifies the scan's cache footprint; see
+// replay_scan_marks).
 template <bool MARK, bool BELOW>
 BRISK_HD bool scan_patch(const LayerView& nb, float x_1, float x1, float y_1, float y1, int threshold, float* max_out,
-                         int* mx, int* my) {
+                         int* mx, int* my, int* steps) {
   int max_x = (int)(x_1 + 1), max_y = (int)(y_1 + 1);
   float tmp;
+  int n = 1;
+  *steps = n;
   float max = (float)score1f<MARK>(nb, x_1, y_1);
   if (max > (float)threshold) return false;
   const int xb = (int)(x_1 + 1), xe = (int)x1, yb = (int)(y_1 + 1), ye = (int)y1;
   for (int x = xb; x <= xe; ++x) {
+    *steps = ++n;
     tmp = (float)score1f<MARK>(nb, (float)x, y_1);
     if (tmp > (float)threshold) return false;
     if (tmp > max) { max = tmp; max_x = x; }
   }
+  *steps = ++n;
   tmp = (float)score1f<MARK>(nb, x1, y_1);
   if (tmp > (float)threshold) return false;
   if (tmp > max) { max = tmp; max_x = xe; }
   for (int y = yb; y <= ye; ++y) {
+    *steps = ++n;
     tmp = (float)score1f<MARK>(nb, x_1, (float)y);
     if (tmp > (float)threshold) return false;
     if (tmp > max) { max = tmp; max_x = xb; max_y = y; }
     for (int x = xb; x <= xe; ++x) {
+      *steps = ++n;
       tmp = (float)score1<MARK>(nb, x, y);
       if (tmp > (float)threshold) return false;
       if (BELOW && tmp == max) {
@@ -162,16 +172,20 @@ BRISK_HD bool scan_patch(const LayerView& nb, float x_1, float x1, float y_1, fl
       }
       if (tmp > max) { max = tmp; max_x = x; max_y = y; }
     }
+    *steps = ++n;
     tmp = (float)score1f<MARK>(nb, x1, (float)y);
     if (tmp > (float)threshold) return false;
     if (tmp > max) { max = tmp; max_x = xe; max_y = y; }
   }
+  *steps = ++n;
   tmp = (float)score1f<MARK>(nb, x_1, y1);
   if (tmp > max) { max = tmp; max_x = xb; max_y = ye; }
   for (int x = xb; x <= xe; ++x) {
+    *steps = ++n;
     tmp = (float)score1f<MARK>(nb, (float)x, y1);
     if (tmp > max) { max = tmp; max_x = x; max_y = ye; }
   }
+  *steps = ++n;
   tmp = (float)score1f<MARK>(nb, x1, y1);
   if (tmp > max) { max = tmp; max_x = xe; max_y = ye; }
   *max_out = max; *mx = max_x; *my = max_y;
@@ -187,23 +201,40 @@ BRISK_HD bool saturate1(float* dx, float* dy) {
   return inside;
 }
 
+// Patch of the layer above that GetScoreMaxAbove scans for a corner of `layer`.
+BRISK_HD void above_patch(int layer, int x, int y, float* x_1, float* x1, float* y_1, float* y1) {
+  if ((layer & 1) == 0) {
+    *x_1 = (float)((double)(float)(4 * x - 1 - 2) / 6.0); *x1 = (float)((double)(float)(4 * x - 1 + 2) / 6.0);
+    *y_1 = (float)((double)(float)(4 * y - 1 - 2) / 6.0); *y1 = (float)((double)(float)(4 * y - 1 + 2) / 6.0);
+  } else {
+    *x_1 = (float)(6 * x - 1 - 3) / 8.0f; *x1 = (float)(6 * x - 1 + 3) / 8.0f;
+    *y_1 = (float)(6 * y - 1 - 3) / 8.0f; *y1 = (float)(6 * y - 1 + 3) / 8.0f;
+  }
+}
+
+// Cache footprint of a GetScoreMaxAbove call: how many patch positions it
+// evaluated and, when the scan ran to completion, the arg-max whose 3x3
+// neighbourhood is looked up afterwards.
+struct AboveFootprint {
+  int steps;      // evaluated patch positions (>= 1)
+  int completed;  // scan not aborted by the threshold test
+  int mx, my;     // arg-max (valid when completed)
+};
+
 // GetScoreMaxAbove (brisk-scale-space.cc:757-915).  `layer` is the index of
-// the corner's own layer, `nb` the layer above it.
-template <bool MARK>
-BRISK_HD float score_max_above(const LayerView& nb, int layer, int x, int y, int thr, bool* ismax, float* dx, float* dy) {
+// the corner's own layer, `nb` the layer above it.  Pure; the footprint is
+// returned for mark_above.
+BRISK_HD float score_max_above(const LayerView& nb, int layer, int x, int y, int thr, bool* ismax, float* dx, float* dy,
+                               AboveFootprint* fp) {
   *ismax = false;
   float x_1, x1, y_1, y1;
-  if ((layer & 1) == 0) {
-    x_1 = (float)((double)(float)(4 * x - 1 - 2) / 6.0); x1 = (float)((double)(float)(4 * x - 1 + 2) / 6.0);
-    y_1 = (float)((double)(float)(4 * y - 1 - 2) / 6.0); y1 = (float)((double)(float)(4 * y - 1 + 2) / 6.0);
-  } else {
-    x_1 = (float)(6 * x - 1 - 3) / 8.0f; x1 = (float)(6 * x - 1 + 3) / 8.0f;
-    y_1 = (float)(6 * y - 1 - 3) / 8.0f; y1 = (float)(6 * y - 1 + 3) / 8.0f;
-  }
-  float max; int mx, my;
-  if (!scan_patch<MARK, false>(nb, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my)) return 0.0f;
+  above_patch(layer, x, y, &x_1, &x1, &y_1, &y1);
+  float max; int mx = 0, my = 0;
+  fp->completed = 0; fp->mx = 0; fp->my = 0;
+  if (!scan_patch<false, false>(nb, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my, &fp->steps)) return 0.0f;
+  fp->completed = 1; fp->mx = mx; fp->my = my;
   float dx1, dy1;
-  const float refined = patch3x3<MARK>(nb, mx, my, &dx1, &dy1, nullptr);
+  const float refined = patch3x3<false>(nb, mx, my, &dx1, &dy1, nullptr);
   const float rx = (float)mx + dx1, ry = (float)my + dy1;
   if ((layer & 1) == 0) {
     *dx = (rx * 6.0f + 1.0f) / 4.0f - (float)x;
@@ -215,6 +246,39 @@ BRISK_HD float score_max_above(const LayerView& nb, int layer, int x, int y, int
   const bool inside = saturate1(dx, dy);
   *ismax = true;
   return inside ? (refined > max ? refined : max) : max;
+}
+
+// Marks, in the touch map of the layer above, the pixels that the first
+// `steps` positions of scan_patch's fixed visiting order look up (float
+// positions read the 2x2 cell they fall in), plus the 3x3 patch around the
+// arg-max when the scan completed.  No scores are evaluated.
+BRISK_HD void mark_px(const LayerView& nb, int x, int y) {
+  if (!in_border(nb, x, y)) nb.bm[(long long)y * nb.pitch + x] = 1;
+}
+BRISK_HD void mark_cell(const LayerView& nb, float xf, float yf) {
+  const int x = (int)xf, y = (int)yf;
+  mark_px(nb, x, y); mark_px(nb, x + 1, y); mark_px(nb, x, y + 1); mark_px(nb, x + 1, y + 1);
+}
+BRISK_HD void replay_scan_marks(const LayerView& nb, float x_1, float x1, float y_1, float y1, const AboveFootprint& fp) {
+  const int xb = (int)(x_1 + 1), xe = (int)x1, yb = (int)(y_1 + 1), ye = (int)y1;
+  int n = fp.steps;
+#define BRISK_STEP(stmt) { stmt; if (--n == 0) goto done; }
+  BRISK_STEP(mark_cell(nb, x_1, y_1))
+  for (int x = xb; x <= xe; ++x) BRISK_STEP(mark_cell(nb, (float)x, y_1))
+  BRISK_STEP(mark_cell(nb, x1, y_1))
+  for (int y = yb; y <= ye; ++y) {
+    BRISK_STEP(mark_cell(nb, x_1, (float)y))
+    for (int x = xb; x <= xe; ++x) BRISK_STEP(mark_px(nb, x, y))
+    BRISK_STEP(mark_cell(nb, x1, (float)y))
+  }
+  BRISK_STEP(mark_cell(nb, x_1, y1))
+  for (int x = xb; x <= xe; ++x) BRISK_STEP(mark_cell(nb, (float)x, y1))
+  BRISK_STEP(mark_cell(nb, x1, y1))
+#undef BRISK_STEP
+done:
+  if (fp.completed)
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) mark_px(nb, fp.mx + dx, fp.my + dy);
 }
 
 // GetScoreMaxBelow (brisk-scale-space.cc:917-1099); `nb` is the layer below.
@@ -231,7 +295,8 @@ BRISK_HD float score_max_below(const LayerView& nb, int layer, int x, int y, int
     y_1 = (float)((double)(float)(6 * y + 1 - 3) / 4.0); y1 = (float)((double)(float)(6 * y + 1 + 3) / 4.0);
   }
   float max; int mx, my;
-  if (!scan_patch<false, true>(nb, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my)) return 0.0f;
+  int steps;
+  if (!scan_patch<false, true>(nb, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my, &steps)) return 0.0f;
   float dx1, dy1;
   const float refined = patch3x3<false>(nb, mx, my, &dx1, &dy1, nullptr);
   const float rx = (float)mx + dx1, ry = (float)my + dy1;
@@ -298,6 +363,8 @@ BRISK_HD void nms_prefix(const LayerView& L, int x, int y, uint8_t fwin[25]) {
 struct CheckResult {
   float max_above, dxa, dya;
   float max_below, dxb, dyb;
+  int above_steps;  // AboveFootprint::steps | completed << 8 (mid layers)
+  int above_argmax; // mx | my << 16
 };
 
 // Returns true when Refine3D (mid layers) / the last-layer branch of
@@ -306,13 +373,17 @@ BRISK_HD bool nms_checks(const LayerView* layers, int n_layers, int layer, int x
   const LayerView& L = layers[layer];
   const int center = L.cm[(long long)y * L.pitch + x] & kCmT;
   r->max_above = 0; r->dxa = 0; r->dya = 0; r->max_below = 0; r->dxb = 0; r->dyb = 0;
+  r->above_steps = 0; r->above_argmax = 0;
   if (n_layers == 1) return true;
   bool ismax;
   if (layer == n_layers - 1) {
     r->max_below = score_max_below(layers[layer - 1], layer, x, y, center, &ismax, &r->dxb, &r->dyb);
     return ismax;
   }
-  r->max_above = score_max_above<false>(layers[layer + 1], layer, x, y, center, &ismax, &r->dxa, &r->dya);
+  AboveFootprint fp;
+  r->max_above = score_max_above(layers[layer + 1], layer, x, y, center, &ismax, &r->dxa, &r->dya, &fp);
+  r->above_steps = fp.steps | (fp.completed << 8);
+  r->above_argmax = fp.mx | (fp.my << 16);
   if (!ismax) return false;
   if (layer == 0) {
     // guess the virtual intra-octave below octave 0 with the 5-8 mask (:558-592)
@@ -335,7 +406,9 @@ BRISK_HD bool nms_checks(const LayerView* layers, int n_layers, int layer, int x
 
 // Raw cache byte the reference would hold at pixel (qx,qy) just before corner
 // (cx,cy) runs IsMax2D.  F is the pixel's FAST score clipped at 0.
-BRISK_HD int cache_state(const LayerView& L, int mode, int qx, int qy, int F, int cx, int cy) {
+// `*blocked` is set when a raster-earlier corner that can influence the pixel is
+// still undecided (a tying corner whose turn has not come yet).
+BRISK_HD int cache_state(const LayerView& L, int mode, int qx, int qy, int F, int cx, int cy, bool* blocked) {
   if (in_border(L, qx, qy)) return 0;
   const long long qo = (long long)qy * L.pitch + qx;
   const int tq = L.cm[qo] & kCmT;
@@ -352,6 +425,7 @@ BRISK_HD int cache_state(const LayerView& L, int mode, int qx, int qy, int F, in
       if (py == cy && px >= cx) continue;  // not earlier than (cx, cy)
       const uint16_t e = L.cm[(long long)py * L.pitch + px];
       if (!(e & kCmT)) continue;
+      if (!(e & kCmDecided)) { *blocked = true; continue; }
       const int ox = qx - px, oy = qy - py;  // in [-1,2]^2
       if (ox <= 1 && oy <= 1) {
         // IsMax2D neighbour look-up with threshold T(p), if p got that far
@@ -375,8 +449,12 @@ BRISK_HD int cache_state(const LayerView& L, int mode, int qx, int qy, int F, in
   return (last != 0 && last <= F) ? F : 0;
 }
 
-// Returns the IsMax2D verdict of the tying corner (x,y).
-BRISK_HD bool nms_tie_decide(const LayerView& L, int mode, int x, int y, const uint8_t fwin[25]) {
+// IsMax2D verdict of the tying corner (x,y): 1 accept, 0 reject, -1 not yet
+// decidable (an earlier tying corner in its neighbourhood is still undecided).
+// Corners whose dependencies are all decided can be resolved in any order, or
+// concurrently: a decision is published with one 16-bit store.
+BRISK_HD int nms_tie_decide(const LayerView& L, int mode, int x, int y, const uint8_t fwin[25]) {
+  bool blocked = false;
   const int center = L.cm[(long long)y * L.pitch + x] & kCmT;
   int s[8];
   for (int j = 0; j < 8; ++j) {
@@ -385,9 +463,10 @@ BRISK_HD bool nms_tie_decide(const LayerView& L, int mode, int x, int y, const u
     const int qx = x + dx, qy = y + dy;
     const int F = fwin[(dy + 2) * 5 + dx + 2];  // T(q) when q is a corner
     if (!in_border(L, qx, qy) && (L.cm[(long long)qy * L.pitch + qx] & kCmT)) { s[j] = F; continue; }
-    const int st = cache_state(L, mode, qx, qy, F, x, y);
+    const int st = cache_state(L, mode, qx, qy, F, x, y, &blocked);
     s[j] = st > 2 ? st : (F >= center ? F : 0);
   }
+  if (blocked) return -1;
   const int smoothed = 4 * center + 2 * (s[0] + s[1] + s[2] + s[3]) + s[7] + s[6] + s[4] + s[5];
   // ties in the reference's order: (-1,-1) (0,-1) (1,-1) (-1,0) (1,0) (-1,1) (0,1) (1,1)
   for (int k = 0; k < 8; ++k) {
@@ -401,24 +480,27 @@ BRISK_HD bool nms_tie_decide(const LayerView& L, int mode, int x, int y, const u
         int v;
         if (ox == 0 && oy == 0) v = center;
         else if (ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1) v = s[isMax2dIndex(ox, oy)];
-        else v = cache_state(L, mode, x + ox, y + oy, fwin[(oy + 2) * 5 + ox + 2], x, y);
+        else v = cache_state(L, mode, x + ox, y + oy, fwin[(oy + 2) * 5 + ox + 2], x, y, &blocked);
         const int wgt = (wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1);
         other += wgt * v;
       }
-    if (other > smoothed) return false;
+    if (blocked) return -1;
+    if (other > smoothed) return 0;
   }
-  return true;
+  return blocked ? -1 : 1;
 }
 
 // ---------------------------------------------------------------------------
 // Phase 4: cache footprint an accepted corner of `layer` leaves on the layer
 // above (its GetScoreMaxAbove look-ups), recorded in that layer's touch map.
 // ---------------------------------------------------------------------------
-BRISK_HD void mark_above(const LayerView* layers, int layer, int x, int y) {
-  const LayerView& L = layers[layer];
-  const int center = L.cm[(long long)y * L.pitch + x] & kCmT;
-  bool ismax; float dx, dy;
-  score_max_above<true>(layers[layer + 1], layer, x, y, center, &ismax, &dx, &dy);
+BRISK_HD void mark_above(const LayerView* layers, int layer, int x, int y, const CheckResult& r) {
+  float x_1, x1, y_1, y1;
+  above_patch(layer, x, y, &x_1, &x1, &y_1, &y1);
+  AboveFootprint fp;
+  fp.steps = r.above_steps & 0xff; fp.completed = (r.above_steps >> 8) & 1;
+  fp.mx = r.above_argmax & 0xffff; fp.my = r.above_argmax >> 16;
+  replay_scan_marks(layers[layer + 1], x_1, x1, y_1, y1, fp);
 }
 
 // ---------------------------------------------------------------------------

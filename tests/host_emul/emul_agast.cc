@@ -84,21 +84,28 @@ extern "C" int emul_agast_detect_ex(const uint8_t* image, int w, int h, int thre
     for (size_t k = 0; k < H[i].cx.size(); ++k) {
       uint16_t& e = H[i].cm[(size_t)H[i].cy[k] * H[i].pitch + H[i].cx[k]];
       if ((e & kCmDecided) && !(e & kCmAccept)) continue;
-      if (nms_checks(V.data(), n, i, H[i].cx[k], H[i].cy[k], &chk[i][k])) e |= kCmChecks;
+      if (nms_checks(V.data(), n, i, H[i].cx[k], H[i].cy[k], &chk[i][k])) e |= kCmChecks;  // chk kept either way: footprint
     }
-  // phase 3 + 4 (per frame: layers in order)
+  // phase 3 + 4 (per frame: layers in order).  Ties are resolved in rounds, visiting the undecided
+  // corners in REVERSE raster order to show that any order that respects the dependencies works.
   for (int i = 0; i < n; ++i) {
     const int mode = n == 1 ? kModeSingle : (i == n - 1 ? kModeLast : kModeMid);
-    for (size_t k = 0; k < H[i].cx.size(); ++k) {
-      uint16_t& e = H[i].cm[(size_t)H[i].cy[k] * H[i].pitch + H[i].cx[k]];
-      if (e & kCmDecided) continue;
-      const bool ok = nms_tie_decide(V[i], mode, H[i].cx[k], H[i].cy[k], &fwin[i][k * 25]);
-      e |= (uint16_t)(kCmDecided | (ok ? kCmAccept : 0));
+    for (bool progress = true, left = true; left;) {
+      if (!progress) return -100;  // dependency cycle: must never happen
+      progress = false; left = false;
+      for (size_t kk = H[i].cx.size(); kk-- > 0;) {
+        uint16_t& e = H[i].cm[(size_t)H[i].cy[kk] * H[i].pitch + H[i].cx[kk]];
+        if (e & kCmDecided) continue;
+        const int verdict = nms_tie_decide(V[i], mode, H[i].cx[kk], H[i].cy[kk], &fwin[i][kk * 25]);
+        if (verdict < 0) { left = true; continue; }
+        e |= (uint16_t)(kCmDecided | (verdict ? kCmAccept : 0));
+        progress = true;
+      }
     }
     if (mode == kModeMid)
       for (size_t k = 0; k < H[i].cx.size(); ++k) {
         const uint16_t e = H[i].cm[(size_t)H[i].cy[k] * H[i].pitch + H[i].cx[k]];
-        if (e & kCmAccept) mark_above(V.data(), i, H[i].cx[k], H[i].cy[k]);
+        if (e & kCmAccept) mark_above(V.data(), i, H[i].cx[k], H[i].cy[k], chk[i][k]);
       }
   }
   // phase 5 + ordered compaction
