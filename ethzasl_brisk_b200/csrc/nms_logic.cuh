@@ -84,29 +84,11 @@ BRISK_HD int fastF(const LayerView& L, int x, int y) {
 }
 
 // Value of BriskLayer::GetAgastScore(x, y, 1) (brisk-layer.cc:118-132): pure.
-template <bool MARK>
 BRISK_HD int score1(const LayerView& L, int x, int y) {
   if (in_border(L, x, y)) return 0;
-  const long long o = (long long)y * L.pitch + x;
-  if (MARK) L.bm[o] = 1;
-  const int t = L.cm[o] & kCmT;
+  const int t = L.cm[(long long)y * L.pitch + x] & kCmT;
   if (t) return t;
   return fastF(L, x, y);  // F >= 1 ? F : 0
-}
-
-// BriskLayer::GetAgastScore(float, float, 1) (brisk-layer.cc:147-161).
-template <bool MARK>
-BRISK_HD int score1f(const LayerView& L, float xf, float yf) {
-  const int x = (int)xf;
-  const float rx1 = xf - (float)x;
-  const float rx = 1.0f - rx1;
-  const int y = (int)yf;
-  const float ry1 = yf - (float)y;
-  const float ry = 1.0f - ry1;
-  const int s00 = score1<MARK>(L, x, y), s10 = score1<MARK>(L, x + 1, y);
-  const int s01 = score1<MARK>(L, x, y + 1), s11 = score1<MARK>(L, x + 1, y + 1);
-  const float v = ((((rx * ry) * (float)s00 + (rx1 * ry) * (float)s10) + (rx * ry1) * (float)s01) + (rx1 * ry1) * (float)s11);
-  return (int)(uint8_t)v;
 }
 
 // BriskLayer::GetAgastScore_5_8(x, y, 1) (brisk-layer.cc:134-145).
@@ -116,79 +98,143 @@ BRISK_HD int score58(const LayerView& L, int x, int y) {
   return f < 1 ? 0 : f;
 }
 
-template <bool MARK>
+// Scores of a small pixel rectangle (at most 4x4) of one layer, evaluated once
+// and kept in two registers.  The scans of the neighbouring layers touch the
+// same few pixels over and over (every bilinear read covers a 2x2 cell), so all
+// their look-ups go through a tile instead of re-running the FAST arithmetic.
+struct ScoreTile {
+  unsigned long long lo, hi;  // 16 bytes, row stride 4
+  int x0, y0;
+#ifdef BRISK_TILE_CHECK
+  int x1, y1;
+  mutable int violations;
+#endif
+  BRISK_HD int get(int x, int y) const {
+#ifdef BRISK_TILE_CHECK
+    if (x < x0 || y < y0 || x > x1 || y > y1) { ++violations; return 0; }
+#endif
+    const int i = ((y - y0) << 2) + (x - x0);
+    const unsigned long long w = i < 8 ? lo : hi;
+    return (int)((w >> ((i & 7) << 3)) & 0xffull);
+  }
+};
+
+// Tile over [xa, xb] x [ya, yb] (inclusive; at most 4x4).
+BRISK_HD void fill_tile(const LayerView& L, int xa, int ya, int xb, int yb, ScoreTile* t) {
+  t->lo = 0; t->hi = 0; t->x0 = xa; t->y0 = ya;
+#ifdef BRISK_TILE_CHECK
+  t->x1 = xb; t->y1 = yb; t->violations = (xb - xa > 3 || yb - ya > 3) ? 1 : 0;
+#endif
+  for (int y = ya; y <= yb; ++y)
+    for (int x = xa; x <= xb; ++x) {
+      const int i = ((y - ya) << 2) + (x - xa);
+      const unsigned long long v = (unsigned long long)score1(L, x, y);
+      if (i < 8) t->lo |= v << (i << 3); else t->hi |= v << ((i & 7) << 3);
+    }
+}
+
+// BriskLayer::GetAgastScore(float, float, 1) (brisk-layer.cc:147-161): bilinear
+// interpolation of four scores in float, truncated to a byte.
+BRISK_HD int tile_score_f(const ScoreTile& t, float xf, float yf) {
+  const int x = (int)xf;
+  const float rx1 = xf - (float)x;
+  const float rx = 1.0f - rx1;
+  const int y = (int)yf;
+  const float ry1 = yf - (float)y;
+  const float ry = 1.0f - ry1;
+  const int s00 = t.get(x, y), s10 = t.get(x + 1, y), s01 = t.get(x, y + 1), s11 = t.get(x + 1, y + 1);
+  const float v = ((((rx * ry) * (float)s00 + (rx1 * ry) * (float)s10) + (rx * ry1) * (float)s01) + (rx1 * ry1) * (float)s11);
+  return (int)(uint8_t)v;
+}
+
+BRISK_HD float tile_patch3x3(const ScoreTile& t, int x, int y, float* dx, float* dy) {
+  const int s00 = t.get(x - 1, y - 1), s10 = t.get(x, y - 1), s20 = t.get(x + 1, y - 1);
+  const int s21 = t.get(x + 1, y), s11 = t.get(x, y), s01 = t.get(x - 1, y);
+  const int s02 = t.get(x - 1, y + 1), s12 = t.get(x, y + 1), s22 = t.get(x + 1, y + 1);
+  return subpixel2d(s00, s01, s02, s10, s11, s12, s20, s21, s22, dx, dy);
+}
+
 BRISK_HD float patch3x3(const LayerView& L, int x, int y, float* dx, float* dy, int* center) {
-  const int s00 = score1<MARK>(L, x - 1, y - 1), s10 = score1<MARK>(L, x, y - 1), s20 = score1<MARK>(L, x + 1, y - 1);
-  const int s21 = score1<MARK>(L, x + 1, y), s11 = score1<MARK>(L, x, y), s01 = score1<MARK>(L, x - 1, y);
-  const int s02 = score1<MARK>(L, x - 1, y + 1), s12 = score1<MARK>(L, x, y + 1), s22 = score1<MARK>(L, x + 1, y + 1);
+  const int s00 = score1(L, x - 1, y - 1), s10 = score1(L, x, y - 1), s20 = score1(L, x + 1, y - 1);
+  const int s21 = score1(L, x + 1, y), s11 = score1(L, x, y), s01 = score1(L, x - 1, y);
+  const int s02 = score1(L, x - 1, y + 1), s12 = score1(L, x, y + 1), s22 = score1(L, x + 1, y + 1);
   if (center) *center = s11;
   return subpixel2d(s00, s01, s02, s10, s11, s12, s20, s21, s22, dx, dy);
 }
 
+// Pixel rectangle of the neighbouring layer that a scan of the patch
+// [x_1,x1]x[y_1,y1] can look up: the 2x2 cells of its float positions, and the
+// 3x3 neighbourhoods of its interior positions / its arg-max.
+BRISK_HD void fill_scan_tile(const LayerView& nb, float x_1, float x1, float y_1, float y1, ScoreTile* t) {
+  const int xb = (int)(x_1 + 1), xe = (int)x1, yb = (int)(y_1 + 1), ye = (int)y1;
+  // the arg-max can sit at xb or xe even when the interior is empty (xe < xb); its 3x3 patch is read too
+  fill_tile(nb, imin((int)x_1, imin(xb, xe) - 1), imin((int)y_1, imin(yb, ye) - 1), imax((int)x1 + 1, imax(xe, xb) + 1),
+            imax((int)y1 + 1, imax(ye, yb) + 1), t);
+}
+
 // Shared scan of GetScoreMaxAbove (brisk-scale-space.cc:757-863) and
 // GetScoreMaxBelow (:917-1047) over the patch [x_1,x1]x[y_1,y1] of the
-// neighbouring layer.  Returns false when a score above `threshold` is met (not
-// tested on the bottom row, as in the reference).  BELOW adds the tie rule of
-// :987-1010 on interior pixels.
-//
-// `steps` receives the number of patch positions that were evaluated (the scan
-// order is fixed, so this number identifies the scan's cache footprint; see
-// replay_scan_marks).
-template <bool MARK, bool BELOW>
-BRISK_HD bool scan_patch(const LayerView& nb, float x_1, float x1, float y_1, float y1, int threshold, float* max_out,
+// neighbouring layer (scores served by `nb`).  Returns false when a score above
+// `threshold` is met (not tested on the bottom row, as in the reference).  BELOW
+// adds the tie rule of :987-1010 on interior pixels.  `steps` receives the
+// number of patch positions that were evaluated: the visiting order is fixed,
+// so this number identifies the scan's cache footprint (replay_scan_marks).
+template <bool BELOW>
+BRISK_HD bool scan_patch(const ScoreTile& nb, float x_1, float x1, float y_1, float y1, int threshold, float* max_out,
                          int* mx, int* my, int* steps) {
   int max_x = (int)(x_1 + 1), max_y = (int)(y_1 + 1);
   float tmp;
   int n = 1;
-  *steps = n;
-  float max = (float)score1f<MARK>(nb, x_1, y_1);
-  if (max > (float)threshold) return false;
+  float max = (float)tile_score_f(nb, x_1, y_1);
+#define BRISK_ABORT_IF_ABOVE(v) if ((v) > (float)threshold) { *steps = n; return false; }
+  BRISK_ABORT_IF_ABOVE(max)
   const int xb = (int)(x_1 + 1), xe = (int)x1, yb = (int)(y_1 + 1), ye = (int)y1;
   for (int x = xb; x <= xe; ++x) {
-    *steps = ++n;
-    tmp = (float)score1f<MARK>(nb, (float)x, y_1);
-    if (tmp > (float)threshold) return false;
+    ++n;
+    tmp = (float)tile_score_f(nb, (float)x, y_1);
+    BRISK_ABORT_IF_ABOVE(tmp)
     if (tmp > max) { max = tmp; max_x = x; }
   }
-  *steps = ++n;
-  tmp = (float)score1f<MARK>(nb, x1, y_1);
-  if (tmp > (float)threshold) return false;
+  ++n;
+  tmp = (float)tile_score_f(nb, x1, y_1);
+  BRISK_ABORT_IF_ABOVE(tmp)
   if (tmp > max) { max = tmp; max_x = xe; }
   for (int y = yb; y <= ye; ++y) {
-    *steps = ++n;
-    tmp = (float)score1f<MARK>(nb, x_1, (float)y);
-    if (tmp > (float)threshold) return false;
+    ++n;
+    tmp = (float)tile_score_f(nb, x_1, (float)y);
+    BRISK_ABORT_IF_ABOVE(tmp)
     if (tmp > max) { max = tmp; max_x = xb; max_y = y; }
     for (int x = xb; x <= xe; ++x) {
-      *steps = ++n;
-      tmp = (float)score1<MARK>(nb, x, y);
-      if (tmp > (float)threshold) return false;
+      ++n;
+      tmp = (float)nb.get(x, y);
+      BRISK_ABORT_IF_ABOVE(tmp)
       if (BELOW && tmp == max) {
-        const int t1 = 2 * (score1<MARK>(nb, x - 1, y) + score1<MARK>(nb, x + 1, y) + score1<MARK>(nb, x, y + 1) + score1<MARK>(nb, x, y - 1)) +
-                       (score1<MARK>(nb, x + 1, y + 1) + score1<MARK>(nb, x - 1, y + 1) + score1<MARK>(nb, x + 1, y - 1) + score1<MARK>(nb, x - 1, y - 1));
-        const int t2 = 2 * (score1<MARK>(nb, max_x - 1, max_y) + score1<MARK>(nb, max_x + 1, max_y) + score1<MARK>(nb, max_x, max_y + 1) + score1<MARK>(nb, max_x, max_y - 1)) +
-                       (score1<MARK>(nb, max_x + 1, max_y + 1) + score1<MARK>(nb, max_x - 1, max_y + 1) + score1<MARK>(nb, max_x + 1, max_y - 1) + score1<MARK>(nb, max_x - 1, max_y - 1));
+        const int t1 = 2 * (nb.get(x - 1, y) + nb.get(x + 1, y) + nb.get(x, y + 1) + nb.get(x, y - 1)) +
+                       (nb.get(x + 1, y + 1) + nb.get(x - 1, y + 1) + nb.get(x + 1, y - 1) + nb.get(x - 1, y - 1));
+        const int t2 = 2 * (nb.get(max_x - 1, max_y) + nb.get(max_x + 1, max_y) + nb.get(max_x, max_y + 1) + nb.get(max_x, max_y - 1)) +
+                       (nb.get(max_x + 1, max_y + 1) + nb.get(max_x - 1, max_y + 1) + nb.get(max_x + 1, max_y - 1) + nb.get(max_x - 1, max_y - 1));
         if (t1 > t2) { max_x = x; max_y = y; }
       }
       if (tmp > max) { max = tmp; max_x = x; max_y = y; }
     }
-    *steps = ++n;
-    tmp = (float)score1f<MARK>(nb, x1, (float)y);
-    if (tmp > (float)threshold) return false;
+    ++n;
+    tmp = (float)tile_score_f(nb, x1, (float)y);
+    BRISK_ABORT_IF_ABOVE(tmp)
     if (tmp > max) { max = tmp; max_x = xe; max_y = y; }
   }
-  *steps = ++n;
-  tmp = (float)score1f<MARK>(nb, x_1, y1);
+#undef BRISK_ABORT_IF_ABOVE
+  ++n;
+  tmp = (float)tile_score_f(nb, x_1, y1);
   if (tmp > max) { max = tmp; max_x = xb; max_y = ye; }
   for (int x = xb; x <= xe; ++x) {
-    *steps = ++n;
-    tmp = (float)score1f<MARK>(nb, (float)x, y1);
+    ++n;
+    tmp = (float)tile_score_f(nb, (float)x, y1);
     if (tmp > max) { max = tmp; max_x = x; max_y = ye; }
   }
-  *steps = ++n;
-  tmp = (float)score1f<MARK>(nb, x1, y1);
+  ++n;
+  tmp = (float)tile_score_f(nb, x1, y1);
   if (tmp > max) { max = tmp; max_x = xe; max_y = ye; }
-  *max_out = max; *mx = max_x; *my = max_y;
+  *max_out = max; *mx = max_x; *my = max_y; *steps = n;
   return true;
 }
 
@@ -225,16 +271,25 @@ struct AboveFootprint {
 // the corner's own layer, `nb` the layer above it.  Pure; the footprint is
 // returned for mark_above.
 BRISK_HD float score_max_above(const LayerView& nb, int layer, int x, int y, int thr, bool* ismax, float* dx, float* dy,
-                               AboveFootprint* fp) {
+                               AboveFootprint* fp, int* tile_violations) {
   *ismax = false;
   float x_1, x1, y_1, y1;
   above_patch(layer, x, y, &x_1, &x1, &y_1, &y1);
-  float max; int mx = 0, my = 0;
+  ScoreTile tile;
+  fill_scan_tile(nb, x_1, x1, y_1, y1, &tile);
+  float max; int mx = 0, my = 0, steps = 0;
   fp->completed = 0; fp->mx = 0; fp->my = 0;
-  if (!scan_patch<false, false>(nb, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my, &fp->steps)) return 0.0f;
+  const bool ok = scan_patch<false>(tile, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my, &steps);
+  fp->steps = steps;
+  float refined = 0.0f, dx1 = 0.0f, dy1 = 0.0f;
+  if (ok) refined = tile_patch3x3(tile, mx, my, &dx1, &dy1);
+#ifdef BRISK_TILE_CHECK
+  if (tile_violations) *tile_violations += tile.violations;
+#else
+  (void)tile_violations;
+#endif
+  if (!ok) return 0.0f;
   fp->completed = 1; fp->mx = mx; fp->my = my;
-  float dx1, dy1;
-  const float refined = patch3x3<false>(nb, mx, my, &dx1, &dy1, nullptr);
   const float rx = (float)mx + dx1, ry = (float)my + dy1;
   if ((layer & 1) == 0) {
     *dx = (rx * 6.0f + 1.0f) / 4.0f - (float)x;
@@ -284,7 +339,8 @@ done:
 // GetScoreMaxBelow (brisk-scale-space.cc:917-1099); `nb` is the layer below.
 // Its look-ups land on a layer whose own NMS is already finished, so its cache
 // footprint is never observed and is not recorded.
-BRISK_HD float score_max_below(const LayerView& nb, int layer, int x, int y, int thr, bool* ismax, float* dx, float* dy) {
+BRISK_HD float score_max_below(const LayerView& nb, int layer, int x, int y, int thr, bool* ismax, float* dx, float* dy,
+                               int* tile_violations) {
   *ismax = false;
   float x_1, x1, y_1, y1;
   if ((layer & 1) == 0) {
@@ -294,11 +350,18 @@ BRISK_HD float score_max_below(const LayerView& nb, int layer, int x, int y, int
     x_1 = (float)((double)(float)(6 * x + 1 - 3) / 4.0); x1 = (float)((double)(float)(6 * x + 1 + 3) / 4.0);
     y_1 = (float)((double)(float)(6 * y + 1 - 3) / 4.0); y1 = (float)((double)(float)(6 * y + 1 + 3) / 4.0);
   }
-  float max; int mx, my;
-  int steps;
-  if (!scan_patch<false, true>(nb, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my, &steps)) return 0.0f;
-  float dx1, dy1;
-  const float refined = patch3x3<false>(nb, mx, my, &dx1, &dy1, nullptr);
+  ScoreTile tile;
+  fill_scan_tile(nb, x_1, x1, y_1, y1, &tile);
+  float max; int mx = 0, my = 0, steps = 0;
+  const bool ok = scan_patch<true>(tile, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my, &steps);
+  float refined = 0.0f, dx1 = 0.0f, dy1 = 0.0f;
+  if (ok) refined = tile_patch3x3(tile, mx, my, &dx1, &dy1);
+#ifdef BRISK_TILE_CHECK
+  if (tile_violations) *tile_violations += tile.violations;
+#else
+  (void)tile_violations;
+#endif
+  if (!ok) return 0.0f;
   const float rx = (float)mx + dx1, ry = (float)my + dy1;
   if ((layer & 1) == 0) {
     *dx = (float)(((double)rx * 6.0 + 1.0) / 8.0 - (double)(float)x);
@@ -369,7 +432,8 @@ struct CheckResult {
 
 // Returns true when Refine3D (mid layers) / the last-layer branch of
 // GetKeypoints reaches its own-layer 3x3 patch.
-BRISK_HD bool nms_checks(const LayerView* layers, int n_layers, int layer, int x, int y, CheckResult* r) {
+BRISK_HD bool nms_checks(const LayerView* layers, int n_layers, int layer, int x, int y, CheckResult* r,
+                         int* tile_violations = nullptr) {
   const LayerView& L = layers[layer];
   const int center = L.cm[(long long)y * L.pitch + x] & kCmT;
   r->max_above = 0; r->dxa = 0; r->dya = 0; r->max_below = 0; r->dxb = 0; r->dyb = 0;
@@ -377,11 +441,11 @@ BRISK_HD bool nms_checks(const LayerView* layers, int n_layers, int layer, int x
   if (n_layers == 1) return true;
   bool ismax;
   if (layer == n_layers - 1) {
-    r->max_below = score_max_below(layers[layer - 1], layer, x, y, center, &ismax, &r->dxb, &r->dyb);
+    r->max_below = score_max_below(layers[layer - 1], layer, x, y, center, &ismax, &r->dxb, &r->dyb, tile_violations);
     return ismax;
   }
   AboveFootprint fp;
-  r->max_above = score_max_above(layers[layer + 1], layer, x, y, center, &ismax, &r->dxa, &r->dya, &fp);
+  r->max_above = score_max_above(layers[layer + 1], layer, x, y, center, &ismax, &r->dxa, &r->dya, &fp, tile_violations);
   r->above_steps = fp.steps | (fp.completed << 8);
   r->above_argmax = fp.mx | (fp.my << 16);
   if (!ismax) return false;
@@ -395,7 +459,7 @@ BRISK_HD bool nms_checks(const LayerView* layers, int n_layers, int layer, int x
     r->max_below = (float)best;
     return true;
   }
-  r->max_below = score_max_below(layers[layer - 1], layer, x, y, center, &ismax, &r->dxb, &r->dyb);
+  r->max_below = score_max_below(layers[layer - 1], layer, x, y, center, &ismax, &r->dxb, &r->dyb, tile_violations);
   return ismax;
 }
 
@@ -513,7 +577,7 @@ BRISK_HD bool refine_emit(const LayerView* layers, int n_layers, int layer, int 
   const LayerView& L = layers[layer];
   float dxl, dyl;
   int s11;
-  const float max_layer = patch3x3<false>(L, x, y, &dxl, &dyl, &s11);
+  const float max_layer = patch3x3(L, x, y, &dxl, &dyl, &s11);
   kp->angle = -1.0f; kp->class_id = -1; kp->octave = layer;
   if (n_layers == 1) {
     kp->x = (float)x + dxl; kp->y = (float)y + dyl; kp->size = 12.0f; kp->response = max_layer; kp->octave = 0;

@@ -5,9 +5,12 @@
 // is a test of product device code, not a CPU fallback: nothing in the product
 // links it.
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
+#define BRISK_TILE_CHECK 1  // count score-tile accesses outside the filled rectangle (must stay 0)
 #include "../../ethzasl_brisk_b200/csrc/nms_logic.cuh"
 
 using namespace briskb200;
@@ -71,6 +74,7 @@ extern "C" int emul_agast_detect_ex(const uint8_t* image, int w, int h, int thre
         }
       }
   }
+  int violations = 0;
   // phase 1 + 2 (parallel on the GPU)
   std::vector<std::vector<uint8_t>> fwin(n);
   std::vector<std::vector<CheckResult>> chk(n);
@@ -84,8 +88,11 @@ extern "C" int emul_agast_detect_ex(const uint8_t* image, int w, int h, int thre
     for (size_t k = 0; k < H[i].cx.size(); ++k) {
       uint16_t& e = H[i].cm[(size_t)H[i].cy[k] * H[i].pitch + H[i].cx[k]];
       if ((e & kCmDecided) && !(e & kCmAccept)) continue;
-      if (nms_checks(V.data(), n, i, H[i].cx[k], H[i].cy[k], &chk[i][k])) e |= kCmChecks;  // chk kept either way: footprint
+      const int v0 = violations;
+      if (nms_checks(V.data(), n, i, H[i].cx[k], H[i].cy[k], &chk[i][k], &violations)) e |= kCmChecks;
+      if (violations != v0 && getenv("EMUL_DEBUG")) fprintf(stderr, "tile violation: layer %d corner (%d,%d) +%d\n", i, H[i].cx[k], H[i].cy[k], violations - v0);  // chk kept either way: footprint
     }
+  if (violations) return -200;  // a scan looked outside its score tile
   // phase 3 + 4 (per frame: layers in order).  Ties are resolved in rounds, visiting the undecided
   // corners in REVERSE raster order to show that any order that respects the dependencies works.
   for (int i = 0; i < n; ++i) {
