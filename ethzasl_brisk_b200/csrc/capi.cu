@@ -49,7 +49,7 @@ struct brisk_ctx {
   int64_t launches = 0;
   cudaEvent_t ev[BRISK_STAGE_COUNT + 1] = {};
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
-  DevBuf pyr, cm, bm, rowcnt, layer_start, corners, fwin, checks, kp_tmp, kp_valid, integral;
+  DevBuf pyr, cm, bm, rowcnt, layer_start, corners, fwin, checks, kp_tmp, kp_valid, integral, rounds;
   DevBuf tight, kps, kps_scratch, scales, counts, desc, masks, flag, knn_q, knn_t, knn_keys, knn_part, knn_idx, knn_dist;
 };
 
@@ -170,6 +170,7 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
     CU_OK(ctx->checks.ensure(c * ws.corner_cap * 32));
     CU_OK(ctx->kp_tmp.ensure(c * ws.corner_cap * 28));
     CU_OK(ctx->kp_valid.ensure(c * ws.corner_cap));
+    CU_OK(ctx->rounds.ensure(c * kMaxLayers * 4));
   }
   if (ext) {
     CU_OK(ctx->integral.ensure(c * plan->integral_elems * 4));
@@ -181,6 +182,7 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
   ws.rowcnt = ctx->rowcnt.as<int>(); ws.layer_start = ctx->layer_start.as<int>(); ws.corners = ctx->corners.as<uint32_t>();
   ws.fwin = ctx->fwin.as<uint8_t>(); ws.checks = ctx->checks.as<float>(); ws.kp_tmp = ctx->kp_tmp.as<KeyPoint>();
   ws.kp_valid = ctx->kp_valid.as<uint8_t>();
+  ws.rounds = ctx->rounds.as<int>();
   return BRISK_OK;
 }
 
@@ -393,7 +395,7 @@ void brisk_ctx_destroy(brisk_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->pyr, &ctx->cm, &ctx->bm, &ctx->rowcnt, &ctx->layer_start, &ctx->corners, &ctx->fwin, &ctx->checks,
-                    &ctx->kp_tmp, &ctx->kp_valid, &ctx->integral, &ctx->kps, &ctx->kps_scratch, &ctx->scales, &ctx->counts,
+                    &ctx->kp_tmp, &ctx->kp_valid, &ctx->integral, &ctx->rounds, &ctx->kps, &ctx->kps_scratch, &ctx->scales, &ctx->counts,
                     &ctx->desc, &ctx->masks, &ctx->flag, &ctx->tight, &ctx->knn_q, &ctx->knn_t, &ctx->knn_keys, &ctx->knn_part,
                     &ctx->knn_idx, &ctx->knn_dist};
   for (DevBuf* b : bufs) b->release();
@@ -632,6 +634,12 @@ int brisk_debug_nms_state(brisk_ctx* ctx, brisk_detector* det, const uint8_t* im
     off += (size_t)L.w * L.h;
   }
   return count;
+}
+
+int brisk_debug_nms_rounds(brisk_ctx* ctx, int32_t* rounds /* [12] of frame 0 of the last detect call */) {
+  if (!ctx || !rounds || !ctx->rounds.p) return BRISK_ERR_INVALID;
+  CU_OK(cudaMemcpy(rounds, ctx->rounds.p, kMaxLayers * 4, cudaMemcpyDeviceToHost));
+  return BRISK_OK;
 }
 
 // ---------------------------------------------------------------------------

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(256)
 nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag) {
   __shared__ FrameViews fv;
   __shared__ int s_left;
+  __shared__ uint16_t s_win[64 * 256];  // per-thread 8x8 corner-map windows, entry i of thread t at [i * 256 + t]
   const int frame = blockIdx.x, tid = threadIdx.x;
   if (tid == 0) make_views(g, ws, frame, &fv);
   __syncthreads();
@@ -91,25 +92,39 @@ nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag
     const int mode = g.n_layers == 1 ? kModeSingle : (layer == g.n_layers - 1 ? kModeLast : kModeMid);
     const int begin = min(ls[layer], ws.corner_cap), end = min(ls[layer + 1], ws.corner_cap);
     const LayerView& L = fv.v[layer];
-    for (int round = 0;; ++round) {
+    // collect this layer's tying (undecided) corners; the key-point scratch of the frame is free until
+    // refine_kernel runs and serves as the list
+    int* tie_list = reinterpret_cast<int*>(ws.kp_tmp + (long long)frame * ws.corner_cap);
+    if (tid == 0) s_left = 0;
+    __syncthreads();
+    for (int k = begin + tid; k < end; k += blockDim.x) {
+      int x, y, l2;
+      unpack_corner(corners[k], &x, &y, &l2);
+      if (!(L.cm[(long long)y * L.pitch + x] & kCmDecided)) tie_list[atomicAdd(&s_left, 1)] = k;
+    }
+    __syncthreads();
+    const int n_ties = s_left;
+    __syncthreads();
+    for (int round = 0; n_ties > 0; ++round) {
       if (tid == 0) s_left = 0;
       __syncthreads();
       int left = 0;
-      for (int k = begin + tid; k < end; k += blockDim.x) {
+      for (int i = tid; i < n_ties; i += blockDim.x) {
+        const int k = tie_list[i];
+        if (k < 0) continue;
         int x, y, l2;
         unpack_corner(corners[k], &x, &y, &l2);
         uint16_t* e = L.cm + (long long)y * L.pitch + x;
-        const uint16_t ev = *e;
-        if (ev & kCmDecided) continue;
-        const int verdict = nms_tie_decide(L, mode, x, y, ws.fwin + ((long long)frame * ws.corner_cap + k) * 32);
-        if (verdict < 0) ++left;
-        else *e = ev | (uint16_t)(kCmDecided | (verdict ? kCmAccept : 0));
+        const int verdict = nms_tie_decide(L, mode, x, y, ws.fwin + ((long long)frame * ws.corner_cap + k) * 32, s_win + tid, 256);
+        if (verdict < 0) { ++left; continue; }
+        *e = *e | (uint16_t)(kCmDecided | (verdict ? kCmAccept : 0));
+        tie_list[i] = -1;
       }
       if (left) atomicAdd(&s_left, left);
       __syncthreads();
       const int remaining = s_left;
       __syncthreads();
-      if (remaining == 0) break;
+      if (remaining == 0) { if (tid == 0) ws.rounds[frame * kMaxLayers + layer] = round + 1; break; }
       if (round > (1 << 16)) { if (tid == 0) atomicExch(error_flag, 2); break; }  // cannot happen: dependencies are acyclic
     }
     // footprint of the accepted corners on the layer above

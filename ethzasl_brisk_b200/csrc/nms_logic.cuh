@@ -468,28 +468,51 @@ BRISK_HD bool nms_checks(const LayerView* layers, int n_layers, int layer, int x
 // corner, given that every raster-earlier corner of the layer is decided.
 // ---------------------------------------------------------------------------
 
+// 8x8 window of corner-map entries around a tying corner (cx-4..cx+3, cy-4..cy+3):
+// every raster-earlier corner that can influence the 5x5 pixels IsMax2D's tie path
+// reads lies inside it.  Entries are staged once (64 independent loads) into
+// `w[i * stride]` -- per-thread scratch in shared memory on the GPU -- so that the
+// state reconstruction below runs on chip.
+struct TieWindow {
+  const uint16_t* w;
+  int stride, x0, y0;
+  BRISK_HD int at(int px, int py) const { return w[(((py - y0) << 3) + (px - x0)) * stride]; }
+};
+
+// Returns true when a raster-earlier corner inside the window is still
+// undecided (the tying corner cannot be resolved yet).
+BRISK_HD bool load_tie_window(const LayerView& L, int cx, int cy, uint16_t* w, int stride) {
+  bool blocked = false;
+  for (int j = 0; j < 8; ++j) {
+    const int py = cy - 4 + j;
+    for (int i = 0; i < 8; ++i) {
+      const int px = cx - 4 + i;
+      uint16_t e = 0;
+      if (py >= 3 && px >= 3 && px < L.w - 3 && py < L.h - 3) e = L.cm[(long long)py * L.pitch + px];
+      w[((j << 3) + i) * stride] = e;
+      if ((e & kCmT) && !(e & kCmDecided) && (py < cy || (py == cy && px < cx))) blocked = true;
+    }
+  }
+  return blocked;
+}
+
 // Raw cache byte the reference would hold at pixel (qx,qy) just before corner
 // (cx,cy) runs IsMax2D.  F is the pixel's FAST score clipped at 0.
-// `*blocked` is set when a raster-earlier corner that can influence the pixel is
-// still undecided (a tying corner whose turn has not come yet).
-BRISK_HD int cache_state(const LayerView& L, int mode, int qx, int qy, int F, int cx, int cy, bool* blocked) {
+BRISK_HD int cache_state(const LayerView& L, const TieWindow& W, int mode, int qx, int qy, int F, int cx, int cy) {
   if (in_border(L, qx, qy)) return 0;
-  const long long qo = (long long)qy * L.pitch + qx;
-  const int tq = L.cm[qo] & kCmT;
+  const int tq = W.at(qx, qy) & kCmT;
   if (tq) return tq;  // a detected corner holds its threshold-map value (> 2)
   if (F < 1) return 0;
   bool sticky = false;
   int last = 0;  // threshold of the most recent look-up, 0 = none
-  if (L.bm[qo]) { sticky = true; last = 1; }
+  if (L.bm[(long long)qy * L.pitch + qx]) { sticky = true; last = 1; }
   // look-ups by raster-earlier corners of this layer whose footprint holds q
   for (int py = qy - 2; py <= qy + 1; ++py) {
-    if (py < 3 || py > cy) continue;
+    if (py > cy) continue;
     for (int px = qx - 2; px <= qx + 1; ++px) {
-      if (px < 3 || px >= L.w - 3) continue;
       if (py == cy && px >= cx) continue;  // not earlier than (cx, cy)
-      const uint16_t e = L.cm[(long long)py * L.pitch + px];
+      const int e = W.at(px, py);
       if (!(e & kCmT)) continue;
-      if (!(e & kCmDecided)) { *blocked = true; continue; }
       const int ox = qx - px, oy = qy - py;  // in [-1,2]^2
       if (ox <= 1 && oy <= 1) {
         // IsMax2D neighbour look-up with threshold T(p), if p got that far
@@ -516,21 +539,22 @@ BRISK_HD int cache_state(const LayerView& L, int mode, int qx, int qy, int F, in
 // IsMax2D verdict of the tying corner (x,y): 1 accept, 0 reject, -1 not yet
 // decidable (an earlier tying corner in its neighbourhood is still undecided).
 // Corners whose dependencies are all decided can be resolved in any order, or
-// concurrently: a decision is published with one 16-bit store.
-BRISK_HD int nms_tie_decide(const LayerView& L, int mode, int x, int y, const uint8_t fwin[25]) {
-  bool blocked = false;
-  const int center = L.cm[(long long)y * L.pitch + x] & kCmT;
+// concurrently: a decision is published with one 16-bit store.  `scratch` holds
+// 64 entries at `stride`.
+BRISK_HD int nms_tie_decide(const LayerView& L, int mode, int x, int y, const uint8_t fwin[25], uint16_t* scratch, int stride) {
+  if (load_tie_window(L, x, y, scratch, stride)) return -1;
+  const TieWindow W{scratch, stride, x - 4, y - 4};
+  const int center = W.at(x, y) & kCmT;
   int s[8];
   for (int j = 0; j < 8; ++j) {
     int dx, dy;
     isMax2dOffset(j, &dx, &dy);
     const int qx = x + dx, qy = y + dy;
     const int F = fwin[(dy + 2) * 5 + dx + 2];  // T(q) when q is a corner
-    if (!in_border(L, qx, qy) && (L.cm[(long long)qy * L.pitch + qx] & kCmT)) { s[j] = F; continue; }
-    const int st = cache_state(L, mode, qx, qy, F, x, y, &blocked);
+    if (W.at(qx, qy) & kCmT) { s[j] = F; continue; }
+    const int st = cache_state(L, W, mode, qx, qy, F, x, y);
     s[j] = st > 2 ? st : (F >= center ? F : 0);
   }
-  if (blocked) return -1;
   const int smoothed = 4 * center + 2 * (s[0] + s[1] + s[2] + s[3]) + s[7] + s[6] + s[4] + s[5];
   // ties in the reference's order: (-1,-1) (0,-1) (1,-1) (-1,0) (1,0) (-1,1) (0,1) (1,1)
   for (int k = 0; k < 8; ++k) {
@@ -544,14 +568,13 @@ BRISK_HD int nms_tie_decide(const LayerView& L, int mode, int x, int y, const ui
         int v;
         if (ox == 0 && oy == 0) v = center;
         else if (ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1) v = s[isMax2dIndex(ox, oy)];
-        else v = cache_state(L, mode, x + ox, y + oy, fwin[(oy + 2) * 5 + ox + 2], x, y, &blocked);
+        else v = cache_state(L, W, mode, x + ox, y + oy, fwin[(oy + 2) * 5 + ox + 2], x, y);
         const int wgt = (wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1);
         other += wgt * v;
       }
-    if (blocked) return -1;
     if (other > smoothed) return 0;
   }
-  return blocked ? -1 : 1;
+  return 1;
 }
 
 // ---------------------------------------------------------------------------

@@ -103,7 +103,8 @@ extern "C" int emul_agast_detect_ex(const uint8_t* image, int w, int h, int thre
       for (size_t kk = H[i].cx.size(); kk-- > 0;) {
         uint16_t& e = H[i].cm[(size_t)H[i].cy[kk] * H[i].pitch + H[i].cx[kk]];
         if (e & kCmDecided) continue;
-        const int verdict = nms_tie_decide(V[i], mode, H[i].cx[kk], H[i].cy[kk], &fwin[i][kk * 25]);
+        uint16_t scratch[64];
+        const int verdict = nms_tie_decide(V[i], mode, H[i].cx[kk], H[i].cy[kk], &fwin[i][kk * 25], scratch, 1);
         if (verdict < 0) { left = true; continue; }
         e |= (uint16_t)(kCmDecided | (verdict ? kCmAccept : 0));
         progress = true;
