@@ -1,0 +1,235 @@
+// Drop-in C++ surface of ethz-asl/ethzasl_brisk over the B200 C ABI.
+//
+// Same class names, constructor arguments and call semantics as the reference
+// headers (cited per class); every method forwards to libbrisk_b200.so
+// (include/brisk_b200.h).  Header-only: link with -lbrisk_b200.  Errors that the
+// reference reports with glog CHECK / std::runtime_error are thrown as
+// std::runtime_error here.  One GPU context per thread is created on first use
+// (the reference classes are likewise not thread-safe per instance).
+#ifndef BRISK_BRISK_H_
+#define BRISK_BRISK_H_
+
+#include <bitset>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <agast/wrap-opencv.h>
+#include "../brisk_b200.h"
+
+namespace brisk {
+
+namespace detail {
+inline void check(brisk_ctx* ctx, int rc) {
+  if (rc != BRISK_OK) throw std::runtime_error(std::string("brisk_b200: ") + brisk_last_error(ctx));
+}
+// Per-thread context on device BRISK_B200_DEVICE (default 0).
+inline brisk_ctx* context() {
+  struct Holder {
+    brisk_ctx* ctx = nullptr;
+    Holder() {
+      const char* d = std::getenv("BRISK_B200_DEVICE");
+      if (brisk_ctx_create(d ? std::atoi(d) : 0, nullptr, &ctx) != BRISK_OK)
+        throw std::runtime_error("brisk_b200: no usable CUDA device (there is no CPU fallback)");
+    }
+    ~Holder() { brisk_ctx_destroy(ctx); }
+  };
+  static thread_local Holder h;
+  return h.ctx;
+}
+static_assert(sizeof(agast::KeyPoint) == sizeof(brisk_keypoint), "KeyPoint must match cv::KeyPoint's 28-byte layout");
+}  // namespace detail
+
+// brisk::BriskFeatureDetector -- reference brisk/include/brisk/brisk-feature-detector.h:51-84,
+// brisk/src/brisk-feature-detector.cc:69-92.
+class BriskFeatureDetector {
+ public:
+  BriskFeatureDetector(int thresh, int octaves = 3, bool suppressScaleNonmaxima = true)
+      : threshold(thresh), octaves(octaves), m_suppress(suppressScaleNonmaxima) {}
+  virtual ~BriskFeatureDetector() { if (det_) brisk_detector_destroy(det_); }
+  BriskFeatureDetector(const BriskFeatureDetector&) = delete;
+  BriskFeatureDetector& operator=(const BriskFeatureDetector&) = delete;
+
+  int threshold;
+  int octaves;
+
+  // cv::Feature2D::detect
+  void detect(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, const agast::Mat& mask = agast::Mat()) const {
+    detectImpl(image, keypoints, mask);
+  }
+  // raw-corner capacity per frame (B200 specific; default scales with the image area)
+  void setCornerCapacity(int n) { corner_cap_ = n; if (det_) brisk_detector_set_corner_capacity(det_, n); }
+
+ protected:
+  virtual void detectImpl(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, const agast::Mat& mask) const {
+    keypoints.clear();
+    if (image.empty()) return;
+    brisk_ctx* ctx = detail::context();
+    ensure(ctx);
+    int cap = (int)std::max<long long>(4096, (long long)image.rows * image.cols / 64);
+    for (;;) {
+      keypoints.resize(cap);
+      int32_t count = 0;
+      const int rc = brisk_detect(ctx, det_, image.data, 1, image.cols, image.rows, image.step, image.step * image.rows,
+                                  mask.empty() ? nullptr : mask.data, reinterpret_cast<brisk_keypoint*>(keypoints.data()), &count, cap);
+      if (rc == BRISK_ERR_CAPACITY && count > cap) { cap = count; continue; }  // grow and retry
+      detail::check(ctx, rc);
+      keypoints.resize(count);
+      return;
+    }
+  }
+
+ private:
+  void ensure(brisk_ctx* ctx) const {
+    if (det_ && ctx_ == ctx && cfg_thr_ == threshold && cfg_oct_ == octaves) return;
+    if (det_) brisk_detector_destroy(det_);
+    det_ = nullptr;
+    detail::check(ctx, brisk_agast_detector_create(ctx, threshold, octaves, m_suppress ? 1 : 0, &det_));
+    if (corner_cap_ > 0) brisk_detector_set_corner_capacity(det_, corner_cap_);
+    ctx_ = ctx; cfg_thr_ = threshold; cfg_oct_ = octaves;
+  }
+  bool m_suppress;
+  int corner_cap_ = 0;
+  mutable brisk_detector* det_ = nullptr;
+  mutable brisk_ctx* ctx_ = nullptr;
+  mutable int cfg_thr_ = 0, cfg_oct_ = 0;
+};
+
+// brisk::BriskDescriptorExtractor -- reference brisk/include/brisk/brisk-descriptor-extractor.h:54-202.
+class BriskDescriptorExtractor {
+ public:
+  static const unsigned int kDescriptorLength = 384;
+  enum Version { briskV1 = 1, briskV2 = 2 };
+
+  BriskDescriptorExtractor() : BriskDescriptorExtractor(true, true) {}
+  BriskDescriptorExtractor(bool rotationInvariant, bool scaleInvariant) : BriskDescriptorExtractor(rotationInvariant, scaleInvariant, briskV2, 1.0f) {}
+  BriskDescriptorExtractor(bool rotationInvariant, bool scaleInvariant, int version) : BriskDescriptorExtractor(rotationInvariant, scaleInvariant, version, 1.0f) {}
+  BriskDescriptorExtractor(bool rotationInvariant, bool scaleInvariant, int version, float patternScale)
+      : rotationInvariance(rotationInvariant), scaleInvariance(scaleInvariant), version_(version), pattern_scale_(patternScale) {
+    if (version != briskV1 && version != briskV2) throw std::runtime_error("only Version::briskV1 or Version::briskV2 supported!");
+  }
+  explicit BriskDescriptorExtractor(const std::string& fname, bool rotationInvariant = true, bool scaleInvariant = true, float patternScale = 1.0f)
+      : rotationInvariance(rotationInvariant), scaleInvariance(scaleInvariant), version_(briskV2), pattern_scale_(patternScale), fname_(fname) {}
+  virtual ~BriskDescriptorExtractor() { if (ext_) brisk_extractor_destroy(ext_); }
+  BriskDescriptorExtractor(const BriskDescriptorExtractor&) = delete;
+  BriskDescriptorExtractor& operator=(const BriskDescriptorExtractor&) = delete;
+
+  bool rotationInvariance;
+  bool scaleInvariance;
+
+  int descriptorSize() const { ensure(detail::context()); return brisk_extractor_descriptor_size(ext_); }
+  int descriptorType() const { return CV_8U; }
+
+  // compute(): removes key points too close to the border, writes their angle, fills an N x descriptorSize() matrix
+  virtual void compute(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, agast::Mat& descriptors) const {
+    brisk_ctx* ctx = detail::context();
+    ensure(ctx);
+    const int nb = brisk_extractor_descriptor_size(ext_);
+    int32_t count = (int32_t)keypoints.size();
+    const int cap = std::max<int>(count, 1);
+    std::vector<unsigned char> buf((size_t)cap * nb);
+    keypoints.resize(cap);
+    detail::check(ctx, brisk_describe(ctx, ext_, image.data, 1, image.cols, image.rows, image.step, image.step * image.rows,
+                                      reinterpret_cast<brisk_keypoint*>(keypoints.data()), &count, cap, buf.data()));
+    keypoints.resize(count);
+    descriptors = agast::Mat::zeros(count, nb, CV_8UC1);
+    if (count) std::memcpy(descriptors.data, buf.data(), (size_t)count * nb);
+  }
+  virtual void compute(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints,
+                       std::vector<std::bitset<kDescriptorLength> >& descriptors) const {
+    agast::Mat d;
+    compute(image, keypoints, d);
+    descriptors.assign(keypoints.size(), std::bitset<kDescriptorLength>());
+    for (size_t k = 0; k < keypoints.size(); ++k)
+      for (unsigned p = 0; p < kDescriptorLength && p < 8u * d.cols; ++p)
+        if (d.data[k * d.cols + p / 8] >> (p % 8) & 1) descriptors[k].set(p, true);
+  }
+
+ private:
+  void ensure(brisk_ctx* ctx) const {
+    if (ext_ && ctx_ == ctx && cfg_rot_ == rotationInvariance && cfg_scale_ == scaleInvariance) return;
+    if (ext_) brisk_extractor_destroy(ext_);
+    ext_ = nullptr;
+    detail::check(ctx, brisk_extractor_create(ctx, rotationInvariance, scaleInvariance, version_, pattern_scale_,
+                                              fname_.empty() ? nullptr : fname_.c_str(), &ext_));
+    ctx_ = ctx; cfg_rot_ = rotationInvariance; cfg_scale_ = scaleInvariance;
+  }
+  int version_;
+  float pattern_scale_;
+  std::string fname_;
+  mutable brisk_extractor* ext_ = nullptr;
+  mutable brisk_ctx* ctx_ = nullptr;
+  mutable bool cfg_rot_ = false, cfg_scale_ = false;
+};
+
+// brisk::Hamming -- reference brisk/include/brisk/internal/hamming.h:56-114.
+class Hamming {
+ public:
+  typedef unsigned char ValueType;
+  typedef int ResultType;
+  ResultType operator()(const unsigned char* a, const unsigned char* b, int size) const {
+    int32_t d = 0;
+    brisk_ctx* ctx = detail::context();
+    detail::check(ctx, brisk_hamming_distance(ctx, a, b, 1, size, &d));
+    return d;
+  }
+};
+
+struct DMatch {  // == cv::DMatch
+  int queryIdx = -1, trainIdx = -1, imgIdx = -1;
+  float distance = std::numeric_limits<float>::max();
+  bool operator<(const DMatch& m) const { return distance < m.distance; }
+};
+
+// brisk::BruteForceMatcher -- reference brisk/include/brisk/brute-force-matcher.h:54-94 and
+// brisk/src/brute-force-matcher.cc:59-162 (kNN over the concatenated train collection, no masks).
+class BruteForceMatcher {
+ public:
+  explicit BruteForceMatcher(const Hamming& = Hamming()) {}
+  bool isMaskSupported() const { return false; }
+  void add(const std::vector<agast::Mat>& descriptors) { for (const auto& d : descriptors) train_.push_back(d); }
+  void clear() { train_.clear(); }
+  const std::vector<agast::Mat>& getTrainDescriptors() const { return train_; }
+
+  void knnMatch(const agast::Mat& query, const agast::Mat& train, std::vector<std::vector<DMatch> >& matches, int k) const {
+    std::vector<agast::Mat> t(1, train);
+    knnImpl(query, t, matches, k);
+  }
+  void knnMatch(const agast::Mat& query, std::vector<std::vector<DMatch> >& matches, int k) const { knnImpl(query, train_, matches, k); }
+
+ private:
+  void knnImpl(const agast::Mat& query, const std::vector<agast::Mat>& train, std::vector<std::vector<DMatch> >& matches, int k) const {
+    matches.assign(query.rows, std::vector<DMatch>());
+    if (query.rows == 0 || train.empty()) return;
+    // concatenate the collection; global row index -> (imgIdx, trainIdx)
+    std::vector<unsigned char> all;
+    std::vector<int> start(1, 0);
+    for (const auto& t : train) {
+      if (t.cols != query.cols) throw std::runtime_error("descriptor size mismatch");
+      all.insert(all.end(), t.data, t.data + (size_t)t.rows * t.cols);
+      start.push_back(start.back() + t.rows);
+    }
+    std::vector<int32_t> idx((size_t)query.rows * k), dist((size_t)query.rows * k);
+    brisk_ctx* ctx = detail::context();
+    detail::check(ctx, brisk_hamming_knn(ctx, query.data, query.rows, all.data(), start.back(), query.cols, k, idx.data(), dist.data()));
+    for (int q = 0; q < query.rows; ++q)
+      for (int j = 0; j < k; ++j) {
+        const int g = idx[(size_t)q * k + j];
+        if (g < 0) continue;
+        int img = 0;
+        while (g >= start[img + 1]) ++img;
+        DMatch m;
+        m.queryIdx = q; m.trainIdx = g - start[img]; m.imgIdx = img; m.distance = (float)dist[(size_t)q * k + j];
+        matches[q].push_back(m);
+      }
+  }
+  std::vector<agast::Mat> train_;
+};
+
+// deprecated aliases of the reference (brisk/include/brisk/brisk.h:56-65)
+typedef BruteForceMatcher BruteForceMatcherSse;
+typedef Hamming HammingSse;
+
+}  // namespace brisk
+#endif  // BRISK_BRISK_H_

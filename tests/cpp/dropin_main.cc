@@ -1,0 +1,36 @@
+// Exercises the header-only C++ drop-in (include/brisk/brisk.h) the way an OKVIS-style caller
+// uses the reference: detector + extractor per image, then a brute-force match.
+// usage: dropin_main <in.pgm> <out.bin>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+
+#include <brisk/brisk.h>
+
+int main(int argc, char** argv) {
+  if (argc < 3) return 2;
+  std::ifstream f(argv[1], std::ios::binary);
+  std::string magic; int w, h, maxv;
+  f >> magic >> w >> h >> maxv;
+  f.get();
+  agast::Mat img(h, w, CV_8UC1);
+  f.read(reinterpret_cast<char*>(img.data), (std::streamsize)w * h);
+  brisk::BriskFeatureDetector detector(70);
+  brisk::BriskDescriptorExtractor extractor;
+  std::vector<agast::KeyPoint> kps;
+  detector.detect(img, kps);
+  agast::Mat desc;
+  extractor.compute(img, kps, desc);
+  brisk::BruteForceMatcher matcher;
+  std::vector<std::vector<brisk::DMatch> > matches;
+  matcher.knnMatch(desc, desc, matches, 2);
+  int self = 0;
+  for (size_t i = 0; i < matches.size(); ++i) self += (matches[i].size() == 2 && matches[i][0].distance == 0);
+  std::ofstream o(argv[2], std::ios::binary);
+  int n = (int)kps.size(), nb = desc.cols;
+  o.write(reinterpret_cast<char*>(&n), 4); o.write(reinterpret_cast<char*>(&nb), 4); o.write(reinterpret_cast<char*>(&self), 4);
+  o.write(reinterpret_cast<char*>(kps.data()), (std::streamsize)n * sizeof(agast::KeyPoint));
+  o.write(reinterpret_cast<char*>(desc.data), (std::streamsize)n * nb);
+  std::printf("%d key points, %d-byte descriptors, %d self matches\n", n, nb, self);
+  return 0;
+}

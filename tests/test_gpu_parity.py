@@ -277,3 +277,28 @@ def test_full_size_properties_1080p(ctx, oracle):
         assert np.array_equal(kps[0, :n][fld], k2[fld])
     k1, c1, d1 = bb.detect_and_compute_batch(det, ext, frames[2:3], cap=32768)
     assert c1[0] == counts[2] and np.array_equal(d1[0, :c1[0]], desc[2, :counts[2]])
+
+
+def test_cpp_dropin_classes(tmp_path, oracle, golden):
+    # the header-only C++ classes (include/brisk/brisk.h) used like the reference's, bit for bit
+    import subprocess
+    from conftest import ROOT
+    exe = tmp_path / "dropin_main"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", f"-I{ROOT / 'include'}", str(ROOT / "tests" / "cpp" / "dropin_main.cc"), "-o", str(exe),
+                    f"-L{ROOT / 'ethzasl_brisk_b200'}", "-lbrisk_b200", f"-Wl,-rpath,{ROOT / 'ethzasl_brisk_b200'}"], check=True)
+    img = golden["image0"]
+    pgm = tmp_path / "img.pgm"
+    with open(pgm, "wb") as f:
+        f.write(b"P5\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
+        f.write(img.tobytes())
+    out = tmp_path / "out.bin"
+    subprocess.run([str(exe), str(pgm), str(out)], check=True)
+    raw = out.read_bytes()
+    n, nb, self_matches = np.frombuffer(raw[:12], np.int32)
+    kps = np.frombuffer(raw[12:12 + n * 28], bb.KP_DTYPE)
+    desc = np.frombuffer(raw[12 + n * 28:], np.uint8).reshape(n, nb)
+    gk, gd = golden["ast0_kps"], golden["ast0_desc"]
+    assert n == len(gk) and nb == 48 and self_matches == n
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(kps[f], gk[f]), f
+    assert np.array_equal(desc, gd)
