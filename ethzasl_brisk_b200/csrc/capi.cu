@@ -38,19 +38,33 @@ struct DevBuf {
 
 }  // namespace
 
+// Per-chunk workspace + stream: two slots let the copies of one chunk overlap the kernels of the other.
+struct Slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[BRISK_STAGE_COUNT + 1] = {};
+  cudaEvent_t done = nullptr;
+  int32_t* h_counts = nullptr;  // pinned: counts of the chunk + [cap_counts] error flag
+  size_t h_counts_cap = 0;
+  DevBuf pyr, cm, bm, rowcnt, layer_start, corners, fwin, checks, kp_tmp, kp_valid, integral, rounds;
+  DevBuf tight, kps, kps_scratch, scales, counts, desc, masks, flag;
+  DevBuf* all[20] = {&pyr, &cm, &bm, &rowcnt, &layer_start, &corners, &fwin, &checks, &kp_tmp, &kp_valid, &integral, &rounds,
+                     &tight, &kps, &kps_scratch, &scales, &counts, &desc, &masks, &flag};
+};
+
 struct brisk_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;  // caller-visible stream: work of a call is ordered after it
   bool own_stream = false;
   std::string err;
   size_t ws_limit = (size_t)8 << 30;
   bool timing = false;
   float ms[BRISK_STAGE_COUNT] = {};
   int64_t launches = 0;
-  cudaEvent_t ev[BRISK_STAGE_COUNT + 1] = {};
+  cudaEvent_t ev[2] = {};
+  cudaEvent_t entry = nullptr;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
-  DevBuf pyr, cm, bm, rowcnt, layer_start, corners, fwin, checks, kp_tmp, kp_valid, integral, rounds;
-  DevBuf tight, kps, kps_scratch, scales, counts, desc, masks, flag, knn_q, knn_t, knn_keys, knn_part, knn_idx, knn_dist;
+  Slot slots[2];
+  DevBuf knn_q, knn_t, knn_keys, knn_part, knn_idx, knn_dist;
 };
 
 struct brisk_detector {
@@ -113,8 +127,9 @@ void build_geom(int w, int h, int octaves, PyramidGeom* g) {
 
 struct Timer {
   brisk_ctx* ctx;
-  explicit Timer(brisk_ctx* c) : ctx(c) {}
-  void mark(int i) { if (ctx->timing) cudaEventRecord(ctx->ev[i], ctx->stream); }
+  Slot* slot;
+  Timer(brisk_ctx* c, Slot* s) : ctx(c), slot(s) {}
+  void mark(int i) { if (ctx->timing) cudaEventRecord(slot->ev[i], slot->stream); }
 };
 
 int encode_map(brisk_ctx* ctx, const void* base, int w, int h, int n, size_t pitch, size_t frame_stride, CUtensorMap* map) {
@@ -131,8 +146,9 @@ int encode_map(brisk_ctx* ctx, const void* base, int w, int h, int n, size_t pit
 
 struct Plan {
   PyramidGeom g;
-  DetectWorkspace ws;
+  DetectWorkspace ws;  // geometry part only; pointers come from slot_ws()
   int chunk;
+  int n_slots;
   size_t integral_elems;  // per frame
 };
 
@@ -152,45 +168,65 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
   const int desc_bytes = ext ? ext->dev.desc_bytes : 0;
   size_t per_frame = (size_t)g.frame_elems;  // image planes
   if (det) per_frame += (size_t)g.frame_elems * 3 + (size_t)ws.total_rows * 4 + (size_t)ws.corner_cap * (4 + 32 + 32 + 28 + 1);
-  per_frame += plan->integral_elems * 4 + (size_t)cap * (28 * 2 + 4 + desc_bytes) + (size_t)w * h /* mask */;
-  long long chunk = (long long)(ctx->ws_limit / std::max<size_t>(per_frame, 1));
-  if (chunk < 1) chunk = 1;
-  if (chunk > n) chunk = n;
-  if (chunk > 32768) chunk = 32768;
+  per_frame += plan->integral_elems * 4 + (size_t)cap * (28 * 2 + 4 + desc_bytes) + 2 * (size_t)w * h /* mask, tight copy */;
+  // two slots share the workspace limit; at least two chunks when there is more than one frame, so
+  // that copies and the serial tail of one chunk overlap the kernels of the other
+  long long max_chunk = (long long)(ctx->ws_limit / 2 / std::max<size_t>(per_frame, 1));
+  if (max_chunk < 1) max_chunk = 1;
+  if (max_chunk > 32768) max_chunk = 32768;
+  long long n_chunks = (n + max_chunk - 1) / max_chunk;
+  if (n_chunks < 2 && n > 1) n_chunks = 2;
+  if (n_chunks < 1) n_chunks = 1;
+  const long long chunk = std::max<long long>(1, (n + n_chunks - 1) / n_chunks);  // equal-sized chunks, no tiny tail
   plan->chunk = (int)chunk;
+  plan->n_slots = n > plan->chunk ? 2 : 1;
   const size_t c = (size_t)plan->chunk;
-  CU_OK(ctx->pyr.ensure(c * g.frame_elems));
-  if (det) {
-    CU_OK(ctx->cm.ensure(c * g.frame_elems * 2));
-    CU_OK(ctx->bm.ensure(c * g.frame_elems));
-    CU_OK(ctx->rowcnt.ensure(c * ws.total_rows * 4));
-    CU_OK(ctx->layer_start.ensure(c * (kMaxLayers + 1) * 4));
-    CU_OK(ctx->corners.ensure(c * ws.corner_cap * 4));
-    CU_OK(ctx->fwin.ensure(c * ws.corner_cap * 32));
-    CU_OK(ctx->checks.ensure(c * ws.corner_cap * 32));
-    CU_OK(ctx->kp_tmp.ensure(c * ws.corner_cap * 28));
-    CU_OK(ctx->kp_valid.ensure(c * ws.corner_cap));
-    CU_OK(ctx->rounds.ensure(c * kMaxLayers * 4));
+  for (int si = 0; si < plan->n_slots; ++si) {
+    Slot& sl = ctx->slots[si];
+    CU_OK(sl.pyr.ensure(c * g.frame_elems));
+    if (det) {
+      CU_OK(sl.cm.ensure(c * g.frame_elems * 2));
+      CU_OK(sl.bm.ensure(c * g.frame_elems));
+      CU_OK(sl.rowcnt.ensure(c * ws.total_rows * 4));
+      CU_OK(sl.layer_start.ensure(c * (kMaxLayers + 1) * 4));
+      CU_OK(sl.corners.ensure(c * ws.corner_cap * 4));
+      CU_OK(sl.fwin.ensure(c * ws.corner_cap * 32));
+      CU_OK(sl.checks.ensure(c * ws.corner_cap * 32));
+      CU_OK(sl.kp_tmp.ensure(c * ws.corner_cap * 28));
+      CU_OK(sl.kp_valid.ensure(c * ws.corner_cap));
+      CU_OK(sl.rounds.ensure(c * kMaxLayers * 4));
+    }
+    if (ext) {
+      CU_OK(sl.integral.ensure(c * plan->integral_elems * 4));
+      CU_OK(sl.kps_scratch.ensure(c * cap * 28));
+      CU_OK(sl.scales.ensure(c * cap * 4));
+    }
+    CU_OK(sl.flag.ensure(16));
+    if (sl.h_counts_cap < c + 4) {
+      if (sl.h_counts) cudaFreeHost(sl.h_counts);
+      sl.h_counts = nullptr; sl.h_counts_cap = 0;
+      CU_OK(cudaMallocHost(&sl.h_counts, (c + 4) * sizeof(int32_t)));
+      sl.h_counts_cap = c + 4;
+    }
   }
-  if (ext) {
-    CU_OK(ctx->integral.ensure(c * plan->integral_elems * 4));
-    CU_OK(ctx->kps_scratch.ensure(c * cap * 28));
-    CU_OK(ctx->scales.ensure(c * cap * 4));
-  }
-  CU_OK(ctx->flag.ensure(16));
-  ws.pyr = ctx->pyr.as<uint8_t>(); ws.cm = ctx->cm.as<uint16_t>(); ws.bm = ctx->bm.as<uint8_t>();
-  ws.rowcnt = ctx->rowcnt.as<int>(); ws.layer_start = ctx->layer_start.as<int>(); ws.corners = ctx->corners.as<uint32_t>();
-  ws.fwin = ctx->fwin.as<uint8_t>(); ws.checks = ctx->checks.as<float>(); ws.kp_tmp = ctx->kp_tmp.as<KeyPoint>();
-  ws.kp_valid = ctx->kp_valid.as<uint8_t>();
-  ws.rounds = ctx->rounds.as<int>();
   return BRISK_OK;
+}
+
+// Device pointers of a slot's workspace for the kernels.
+DetectWorkspace slot_ws(const Plan& plan, const Slot& sl) {
+  DetectWorkspace ws = plan.ws;
+  ws.pyr = sl.pyr.as<uint8_t>(); ws.cm = sl.cm.as<uint16_t>(); ws.bm = sl.bm.as<uint8_t>();
+  ws.rowcnt = sl.rowcnt.as<int>(); ws.layer_start = sl.layer_start.as<int>(); ws.corners = sl.corners.as<uint32_t>();
+  ws.fwin = sl.fwin.as<uint8_t>(); ws.checks = sl.checks.as<float>(); ws.kp_tmp = sl.kp_tmp.as<KeyPoint>();
+  ws.kp_valid = sl.kp_valid.as<uint8_t>(); ws.rounds = sl.rounds.as<int>();
+  return ws;
 }
 
 // Bring `count` frames starting at `imgs` into the pyramid block (layer 0 of
 // every frame) or, when they already sit in device memory with TMA-compatible
 // alignment, describe them in place.  Returns the tensor map the pyramid
 // kernel reads and whether it has to materialise layer 0 in the block.
-int stage_input(brisk_ctx* ctx, const Plan& plan, const uint8_t* imgs, int count, int w, int h, size_t stride,
+int stage_input(brisk_ctx* ctx, Slot& sl, const Plan& plan, const uint8_t* imgs, int count, int w, int h, size_t stride,
                 size_t frame_pitch, CUtensorMap* map, int* write_l0) {
   const PyramidGeom& g = plan.g;
   const bool dev = is_device_ptr(imgs);
@@ -200,11 +236,11 @@ int stage_input(brisk_ctx* ctx, const Plan& plan, const uint8_t* imgs, int count
     return encode_map(ctx, imgs, w, h, count, stride, frame_pitch, map);
   }
   for (int f = 0; f < count; ++f)
-    CU_OK(cudaMemcpy2DAsync(ctx->pyr.as<uint8_t>() + (size_t)f * g.frame_elems + g.L[0].off, g.L[0].pitch,
+    CU_OK(cudaMemcpy2DAsync(sl.pyr.as<uint8_t>() + (size_t)f * g.frame_elems + g.L[0].off, g.L[0].pitch,
                             imgs + (size_t)f * frame_pitch, stride, w, h, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                            ctx->stream));
+                            sl.stream));
   *write_l0 = 0;
-  return encode_map(ctx, ctx->pyr.as<uint8_t>() + g.L[0].off, w, h, count, g.L[0].pitch, (size_t)g.frame_elems, map);
+  return encode_map(ctx, sl.pyr.as<uint8_t>() + g.L[0].off, w, h, count, g.L[0].pitch, (size_t)g.frame_elems, map);
 }
 
 int check_image_args(brisk_ctx* ctx, const uint8_t* imgs, int n, int w, int h, size_t stride, size_t frame_pitch) {
@@ -245,24 +281,74 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
   const int desc_bytes = ext ? ext->dev.desc_bytes : 0;
   const bool kps_dev = is_device_ptr(kps), counts_dev = is_device_ptr(counts), desc_dev = desc && is_device_ptr(desc);
   const bool masks_dev = masks && is_device_ptr(masks);
-  if (!kps_dev) CU_OK(ctx->kps.ensure((size_t)plan.chunk * cap * 28));
-  if (!counts_dev) CU_OK(ctx->counts.ensure((size_t)plan.chunk * 4));
-  if (ext && !desc_dev) CU_OK(ctx->desc.ensure((size_t)plan.chunk * cap * desc_bytes));
-  if (det && masks && !masks_dev) CU_OK(ctx->masks.ensure((size_t)plan.chunk * w * h));
-  std::vector<int32_t> hcounts(plan.chunk);
-  bool truncated = false, corner_overflow = false;
-  Timer tm(ctx);
+  for (int si = 0; si < plan.n_slots; ++si) {
+    Slot& sl = ctx->slots[si];
+    if (!kps_dev) CU_OK(sl.kps.ensure((size_t)plan.chunk * cap * 28));
+    if (!counts_dev) CU_OK(sl.counts.ensure((size_t)plan.chunk * 4));
+    if (ext && !desc_dev) CU_OK(sl.desc.ensure((size_t)plan.chunk * cap * desc_bytes));
+    if (det && masks && !masks_dev) CU_OK(sl.masks.ensure((size_t)plan.chunk * w * h));
+    if (ext && g.L[0].pitch != w) CU_OK(sl.tight.ensure((size_t)plan.chunk * ((size_t)w * h + 64)));
+  }
+  // order the slots' streams after whatever the caller queued on the context stream
+  CU_OK(cudaEventRecord(ctx->entry, ctx->stream));
+  for (int si = 0; si < plan.n_slots; ++si) CU_OK(cudaStreamWaitEvent(ctx->slots[si].stream, ctx->entry, 0));
 
-  for (int f0 = 0; f0 < n; f0 += plan.chunk) {
+  bool truncated = false, corner_overflow = false, internal_error = false;
+  struct Pending { int f0 = 0, c = 0; bool active = false; KeyPoint* d_kps = nullptr; uint8_t* d_desc = nullptr; };
+  Pending pend[2];
+
+  // second half of a chunk: wait for its kernels, then copy exactly the produced rows back
+  auto finish = [&](int si) -> int {
+    Pending& pd = pend[si];
+    if (!pd.active) return BRISK_OK;
+    Slot& sl = ctx->slots[si];
+    pd.active = false;
+    CU_OK(cudaStreamSynchronize(sl.stream));
+    const int32_t flag = sl.h_counts[plan.chunk];
+    if (flag == 2) internal_error = true; else if (flag) corner_overflow = true;
+    if (!counts_dev) memcpy(counts + pd.f0, sl.h_counts, (size_t)pd.c * 4);
+    Timer tm(ctx, &sl);
+    tm.mark(7);
+    for (int f = 0; f < pd.c; ++f) {
+      const int m = std::min(sl.h_counts[f], cap);
+      if (sl.h_counts[f] > cap) truncated = true;
+      if (m <= 0) continue;
+      if (!kps_dev) CU_OK(cudaMemcpyAsync(kps + (size_t)(pd.f0 + f) * cap, pd.d_kps + (size_t)f * cap, (size_t)m * 28, cudaMemcpyDeviceToHost, sl.stream));
+      if (ext && !desc_dev) CU_OK(cudaMemcpyAsync(desc + (size_t)(pd.f0 + f) * cap * desc_bytes, pd.d_desc + (size_t)f * cap * desc_bytes, (size_t)m * desc_bytes, cudaMemcpyDeviceToHost, sl.stream));
+    }
+    tm.mark(8);
+    return BRISK_OK;
+  };
+  auto collect_timing = [&](int si) {
+    if (!ctx->timing) return;
+    static const int stage_of[8] = {BRISK_STAGE_H2D, BRISK_STAGE_PYRAMID, BRISK_STAGE_DETECT, BRISK_STAGE_LISTS, BRISK_STAGE_NMS,
+                                    BRISK_STAGE_INTEGRAL, BRISK_STAGE_DESCRIBE, BRISK_STAGE_D2H};
+    Slot& sl = ctx->slots[si];
+    cudaStreamSynchronize(sl.stream);
+    for (int i = 0; i < 8; ++i) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, sl.ev[i], sl.ev[i + 1]) == cudaSuccess) ctx->ms[stage_of[i]] += ms; else cudaGetLastError();
+    }
+  };
+
+  int chunk_index = 0;
+  for (int f0 = 0; f0 < n; f0 += plan.chunk, ++chunk_index) {
+    const int si = chunk_index % plan.n_slots;
+    Slot& sl = ctx->slots[si];
+    // the slot's previous chunk must be fully drained (results copied) before its buffers are reused
+    if (pend[si].active) { rc = finish(si); if (rc) return rc; }
+    if (chunk_index >= plan.n_slots) collect_timing(si);
     const int c = std::min(plan.chunk, n - f0);
-    KeyPoint* d_kps = kps_dev ? reinterpret_cast<KeyPoint*>(kps) + (size_t)f0 * cap : ctx->kps.as<KeyPoint>();
-    int* d_counts = counts_dev ? counts + f0 : ctx->counts.as<int>();
-    uint8_t* d_desc = ext ? (desc_dev ? desc + (size_t)f0 * cap * desc_bytes : ctx->desc.as<uint8_t>()) : nullptr;
+    const DetectWorkspace ws = slot_ws(plan, sl);
+    KeyPoint* d_kps = kps_dev ? reinterpret_cast<KeyPoint*>(kps) + (size_t)f0 * cap : sl.kps.as<KeyPoint>();
+    int* d_counts = counts_dev ? counts + f0 : sl.counts.as<int>();
+    uint8_t* d_desc = ext ? (desc_dev ? desc + (size_t)f0 * cap * desc_bytes : sl.desc.as<uint8_t>()) : nullptr;
+    Timer tm(ctx, &sl);
 
     tm.mark(0);
     CUtensorMap map;
     int write_l0 = 0;
-    rc = stage_input(ctx, plan, imgs + (size_t)f0 * frame_pitch, c, w, h, stride, frame_pitch, &map, &write_l0);
+    rc = stage_input(ctx, sl, plan, imgs + (size_t)f0 * frame_pitch, c, w, h, stride, frame_pitch, &map, &write_l0);
     if (rc) return rc;
     const uint8_t* d_masks = nullptr;
     long long mask_fs = 0; int mask_pitch = 0;
@@ -270,39 +356,39 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       if (masks_dev) { d_masks = masks + (size_t)f0 * frame_pitch; mask_fs = (long long)frame_pitch; mask_pitch = (int)stride; }
       else {
         for (int f = 0; f < c; ++f)
-          CU_OK(cudaMemcpy2DAsync(ctx->masks.as<uint8_t>() + (size_t)f * w * h, w, masks + (size_t)(f0 + f) * frame_pitch, stride, w, h,
-                                  cudaMemcpyHostToDevice, ctx->stream));
-        d_masks = ctx->masks.as<uint8_t>(); mask_fs = (long long)w * h; mask_pitch = w;
+          CU_OK(cudaMemcpy2DAsync(sl.masks.as<uint8_t>() + (size_t)f * w * h, w, masks + (size_t)(f0 + f) * frame_pitch, stride, w, h,
+                                  cudaMemcpyHostToDevice, sl.stream));
+        d_masks = sl.masks.as<uint8_t>(); mask_fs = (long long)w * h; mask_pitch = w;
       }
     }
     if (!det) {
       // describe only: key points come from the caller
-      if (!kps_dev) CU_OK(cudaMemcpyAsync(d_kps, kps + (size_t)f0 * cap, (size_t)c * cap * 28, cudaMemcpyHostToDevice, ctx->stream));
-      if (!counts_dev) CU_OK(cudaMemcpyAsync(d_counts, counts + f0, (size_t)c * 4, cudaMemcpyHostToDevice, ctx->stream));
+      if (!kps_dev) CU_OK(cudaMemcpyAsync(d_kps, kps + (size_t)f0 * cap, (size_t)c * cap * 28, cudaMemcpyHostToDevice, sl.stream));
+      if (!counts_dev) CU_OK(cudaMemcpyAsync(d_counts, counts + f0, (size_t)c * 4, cudaMemcpyHostToDevice, sl.stream));
     }
     tm.mark(1);
     if (det || write_l0) {
-      CU_OK(launch_pyramid(map, g, plan.ws.pyr, c, write_l0, ctx->stream));
+      CU_OK(launch_pyramid(map, g, ws.pyr, c, write_l0, sl.stream));
       ctx->launches += 1;
     }
     tm.mark(2);
+    CU_OK(cudaMemsetAsync(sl.flag.p, 0, 16, sl.stream));
     if (det) {
-      CU_OK(cudaMemsetAsync(ctx->flag.p, 0, 16, ctx->stream));
-      CU_OK(launch_agast_detect(g, plan.ws, c, det->thresh, ctx->stream));
+      CU_OK(launch_agast_detect(g, ws, c, det->thresh, sl.stream));
       ctx->launches += g.n_layers;
       tm.mark(3);
-      CU_OK(launch_corner_lists(g, plan.ws, c, ctx->flag.as<int>(), ctx->stream));
+      CU_OK(launch_corner_lists(g, ws, c, sl.flag.as<int>(), sl.stream));
       ctx->launches += 1 + g.n_layers;
       tm.mark(4);
-      CU_OK(launch_agast_nms(g, plan.ws, c, d_masks, mask_fs, mask_pitch, d_kps, d_counts, cap, ctx->flag.as<int>(), ctx->stream));
+      CU_OK(launch_agast_nms(g, ws, c, d_masks, mask_fs, mask_pitch, d_kps, d_counts, cap, sl.flag.as<int>(), sl.stream));
       ctx->launches += 5;
     } else {
       tm.mark(3); tm.mark(4);
     }
     tm.mark(5);
     if (ext) {
-      const uint8_t* l0 = plan.ws.pyr + g.L[0].off;
-      CU_OK(launch_integral(l0, g.frame_elems, g.L[0].pitch, w, h, c, ctx->integral.as<int32_t>(), ctx->stream));
+      const uint8_t* l0 = ws.pyr + g.L[0].off;
+      CU_OK(launch_integral(l0, g.frame_elems, g.L[0].pitch, w, h, c, sl.integral.as<int32_t>(), sl.stream));
       ctx->launches += 2;
       tm.mark(6);
       // The reference samples a tightly packed image (stride == cols) and a few of its reads land one
@@ -313,48 +399,32 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       int spitch = g.L[0].pitch;
       if (spitch != w) {
         const size_t fs = (size_t)w * h + 64;
-        CU_OK(ctx->tight.ensure((size_t)plan.chunk * fs));
         for (int f = 0; f < c; ++f)
-          CU_OK(cudaMemcpy2DAsync(ctx->tight.as<uint8_t>() + (size_t)f * fs, w, l0 + (size_t)f * g.frame_elems, g.L[0].pitch, w, h,
-                                  cudaMemcpyDeviceToDevice, ctx->stream));
-        simg = ctx->tight.as<uint8_t>(); sstride = (long long)fs; spitch = w;
+          CU_OK(cudaMemcpy2DAsync(sl.tight.as<uint8_t>() + (size_t)f * fs, w, l0 + (size_t)f * g.frame_elems, g.L[0].pitch, w, h,
+                                  cudaMemcpyDeviceToDevice, sl.stream));
+        simg = sl.tight.as<uint8_t>(); sstride = (long long)fs; spitch = w;
       }
-      CU_OK(launch_describe(ext->dev, simg, sstride, spitch, w, h, c, ctx->integral.as<int32_t>(), d_kps, d_counts, cap,
-                            ctx->kps_scratch.as<KeyPoint>(), ctx->scales.as<int>(), d_desc, ctx->stream));
+      CU_OK(launch_describe(ext->dev, simg, sstride, spitch, w, h, c, sl.integral.as<int32_t>(), d_kps, d_counts, cap,
+                            sl.kps_scratch.as<KeyPoint>(), sl.scales.as<int>(), d_desc, sl.stream));
       ctx->launches += 2;
     } else {
       tm.mark(6);
     }
     tm.mark(7);
-    // results
-    int hflag = 0;
-    if (det) CU_OK(cudaMemcpyAsync(&hflag, ctx->flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    const bool need_host_counts = !counts_dev || !kps_dev || (ext && !desc_dev);
-    if (need_host_counts) {
-      CU_OK(cudaMemcpyAsync(hcounts.data(), d_counts, (size_t)c * 4, cudaMemcpyDeviceToHost, ctx->stream));
-      CU_OK(cudaStreamSynchronize(ctx->stream));
-      if (!counts_dev) memcpy(counts + f0, hcounts.data(), (size_t)c * 4);
-      for (int f = 0; f < c; ++f) {
-        const int m = std::min(hcounts[f], cap);
-        if (hcounts[f] > cap) truncated = true;
-        if (m <= 0) continue;
-        if (!kps_dev) CU_OK(cudaMemcpyAsync(kps + (size_t)(f0 + f) * cap, d_kps + (size_t)f * cap, (size_t)m * 28, cudaMemcpyDeviceToHost, ctx->stream));
-        if (ext && !desc_dev) CU_OK(cudaMemcpyAsync(desc + (size_t)(f0 + f) * cap * desc_bytes, d_desc + (size_t)f * cap * desc_bytes, (size_t)m * desc_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-      }
-    }
+    // counts + error flag to pinned host memory; the row copies follow in finish()
+    CU_OK(cudaMemcpyAsync(sl.h_counts, d_counts, (size_t)c * 4, cudaMemcpyDeviceToHost, sl.stream));
+    CU_OK(cudaMemcpyAsync(sl.h_counts + plan.chunk, sl.flag.p, 4, cudaMemcpyDeviceToHost, sl.stream));
     tm.mark(8);
-    CU_OK(cudaStreamSynchronize(ctx->stream));
-    if (hflag == 2) return fail(ctx, BRISK_ERR_CUDA, "internal error: tie resolution did not converge");
-    if (hflag) corner_overflow = true;
-    if (ctx->timing) {
-      static const int stage_of[8] = {BRISK_STAGE_H2D, BRISK_STAGE_PYRAMID, BRISK_STAGE_DETECT, BRISK_STAGE_LISTS, BRISK_STAGE_NMS,
-                                      BRISK_STAGE_INTEGRAL, BRISK_STAGE_DESCRIBE, BRISK_STAGE_D2H};
-      for (int i = 0; i < 8; ++i) {
-        float ms = 0;
-        if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess) ctx->ms[stage_of[i]] += ms; else cudaGetLastError();
-      }
-    }
+    pend[si].f0 = f0; pend[si].c = c; pend[si].active = true; pend[si].d_kps = d_kps; pend[si].d_desc = d_desc;
+    // drain the OTHER slot while this chunk computes
+    if (plan.n_slots == 2 && pend[si ^ 1].active) { rc = finish(si ^ 1); if (rc) return rc; }
   }
+  for (int si = 0; si < plan.n_slots; ++si) { rc = finish(si); if (rc) return rc; }
+  for (int si = 0; si < plan.n_slots; ++si) {
+    CU_OK(cudaStreamSynchronize(ctx->slots[si].stream));
+    collect_timing(si);
+  }
+  if (internal_error) return fail(ctx, BRISK_ERR_CUDA, "internal error: tie resolution did not converge");
   if (corner_overflow) return fail(ctx, BRISK_ERR_CAPACITY, "raw corner capacity exceeded; raise it with brisk_detector_set_corner_capacity");
   if (truncated) return fail(ctx, BRISK_ERR_CAPACITY, "key point capacity (cap) exceeded; counts hold the true numbers");
   return BRISK_OK;
@@ -378,6 +448,12 @@ int brisk_ctx_create(int device, void* stream, brisk_ctx** out) {
     ctx->own_stream = true;
   }
   for (auto& e : ctx->ev) cudaEventCreate(&e);
+  cudaEventCreateWithFlags(&ctx->entry, cudaEventDisableTiming);
+  for (Slot& sl : ctx->slots) {
+    if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); brisk_ctx_destroy(ctx); return BRISK_ERR_CUDA; }
+    for (auto& e : sl.ev) cudaEventCreate(&e);
+    cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
+  }
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
@@ -394,11 +470,17 @@ void brisk_ctx_destroy(brisk_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->pyr, &ctx->cm, &ctx->bm, &ctx->rowcnt, &ctx->layer_start, &ctx->corners, &ctx->fwin, &ctx->checks,
-                    &ctx->kp_tmp, &ctx->kp_valid, &ctx->integral, &ctx->rounds, &ctx->kps, &ctx->kps_scratch, &ctx->scales, &ctx->counts,
-                    &ctx->desc, &ctx->masks, &ctx->flag, &ctx->tight, &ctx->knn_q, &ctx->knn_t, &ctx->knn_keys, &ctx->knn_part,
-                    &ctx->knn_idx, &ctx->knn_dist};
+  for (Slot& sl : ctx->slots) {
+    if (sl.stream) cudaStreamSynchronize(sl.stream);
+    for (DevBuf* b : sl.all) b->release();
+    for (auto& e : sl.ev) if (e) cudaEventDestroy(e);
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.h_counts) cudaFreeHost(sl.h_counts);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+  }
+  DevBuf* bufs[] = {&ctx->knn_q, &ctx->knn_t, &ctx->knn_keys, &ctx->knn_part, &ctx->knn_idx, &ctx->knn_dist};
   for (DevBuf* b : bufs) b->release();
+  if (ctx->entry) cudaEventDestroy(ctx->entry);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -526,20 +608,23 @@ int brisk_debug_pyramid(brisk_ctx* ctx, int octaves, const uint8_t* img, int w, 
   Plan plan;
   rc = make_plan(ctx, &det, nullptr, 1, w, h, 1, &plan);
   if (rc) return rc;
+  Slot& sl = ctx->slots[0];
+  const DetectWorkspace ws = slot_ws(plan, sl);
+  (void)ws;
   CUtensorMap map; int write_l0;
-  rc = stage_input(ctx, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
+  rc = stage_input(ctx, sl, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
   if (rc) return rc;
-  CU_OK(launch_pyramid(map, plan.g, plan.ws.pyr, 1, write_l0, ctx->stream));
+  CU_OK(launch_pyramid(map, plan.g, ws.pyr, 1, write_l0, sl.stream));
   size_t off = 0;
   for (int i = 0; i < plan.g.n_layers; ++i) {
     const LayerGeom& L = plan.g.L[i];
     if (dims) { dims[2 * i] = L.w; dims[2 * i + 1] = L.h; }
     if (out && L.w > 0 && L.h > 0)
-      CU_OK(cudaMemcpy2DAsync(out + off, L.w, plan.ws.pyr + L.off, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, ctx->stream));
+      CU_OK(cudaMemcpy2DAsync(out + off, L.w, ws.pyr + L.off, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, sl.stream));
     off += (size_t)L.w * L.h;
   }
   if (n_layers) *n_layers = plan.g.n_layers;
-  CU_OK(cudaStreamSynchronize(ctx->stream));
+  CU_OK(cudaStreamSynchronize(sl.stream));
   return BRISK_OK;
 }
 
@@ -551,14 +636,17 @@ int brisk_debug_integral(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_
   Plan plan;
   rc = make_plan(ctx, nullptr, nullptr, 1, w, h, 1, &plan);
   if (rc) return rc;
-  CU_OK(ctx->integral.ensure((size_t)(w + 1) * (h + 1) * 4));
+  Slot& sl = ctx->slots[0];
+  const DetectWorkspace ws = slot_ws(plan, sl);
+  (void)ws;
+  CU_OK(sl.integral.ensure((size_t)(w + 1) * (h + 1) * 4));
   CUtensorMap map; int write_l0;
-  rc = stage_input(ctx, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
+  rc = stage_input(ctx, sl, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
   if (rc) return rc;
-  CU_OK(launch_pyramid(map, plan.g, plan.ws.pyr, 1, write_l0, ctx->stream));
-  CU_OK(launch_integral(plan.ws.pyr + plan.g.L[0].off, plan.g.frame_elems, plan.g.L[0].pitch, w, h, 1, ctx->integral.as<int32_t>(), ctx->stream));
-  CU_OK(cudaMemcpyAsync(out, ctx->integral.p, (size_t)(w + 1) * (h + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_OK(cudaStreamSynchronize(ctx->stream));
+  CU_OK(launch_pyramid(map, plan.g, ws.pyr, 1, write_l0, sl.stream));
+  CU_OK(launch_integral(ws.pyr + plan.g.L[0].off, plan.g.frame_elems, plan.g.L[0].pitch, w, h, 1, sl.integral.as<int32_t>(), sl.stream));
+  CU_OK(cudaMemcpyAsync(out, sl.integral.p, (size_t)(w + 1) * (h + 1) * 4, cudaMemcpyDeviceToHost, sl.stream));
+  CU_OK(cudaStreamSynchronize(sl.stream));
   return BRISK_OK;
 }
 
@@ -571,21 +659,24 @@ int brisk_debug_corners(brisk_ctx* ctx, brisk_detector* det, const uint8_t* img,
   Plan plan;
   rc = make_plan(ctx, det, nullptr, 1, w, h, 1, &plan);
   if (rc) return rc;
+  Slot& sl = ctx->slots[0];
+  const DetectWorkspace ws = slot_ws(plan, sl);
+  (void)ws;
   CUtensorMap map; int write_l0;
-  rc = stage_input(ctx, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
+  rc = stage_input(ctx, sl, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
   if (rc) return rc;
-  CU_OK(launch_pyramid(map, plan.g, plan.ws.pyr, 1, write_l0, ctx->stream));
-  CU_OK(cudaMemsetAsync(ctx->flag.p, 0, 16, ctx->stream));
-  CU_OK(launch_agast_detect(plan.g, plan.ws, 1, det->thresh, ctx->stream));
-  CU_OK(launch_corner_lists(plan.g, plan.ws, 1, ctx->flag.as<int>(), ctx->stream));
+  CU_OK(launch_pyramid(map, plan.g, ws.pyr, 1, write_l0, sl.stream));
+  CU_OK(cudaMemsetAsync(sl.flag.p, 0, 16, sl.stream));
+  CU_OK(launch_agast_detect(plan.g, ws, 1, det->thresh, sl.stream));
+  CU_OK(launch_corner_lists(plan.g, ws, 1, sl.flag.as<int>(), sl.stream));
   std::vector<int> ls(kMaxLayers + 1);
-  CU_OK(cudaMemcpyAsync(ls.data(), plan.ws.layer_start, ls.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_OK(cudaStreamSynchronize(ctx->stream));
-  const int total = std::min(ls[plan.g.n_layers], plan.ws.corner_cap);
+  CU_OK(cudaMemcpyAsync(ls.data(), ws.layer_start, ls.size() * 4, cudaMemcpyDeviceToHost, sl.stream));
+  CU_OK(cudaStreamSynchronize(sl.stream));
+  const int total = std::min(ls[plan.g.n_layers], ws.corner_cap);
   std::vector<uint32_t> packed(std::max(total, 1));
   std::vector<uint16_t> cm((size_t)plan.g.frame_elems);
-  CU_OK(cudaMemcpy(packed.data(), plan.ws.corners, (size_t)total * 4, cudaMemcpyDeviceToHost));
-  CU_OK(cudaMemcpy(cm.data(), plan.ws.cm, cm.size() * 2, cudaMemcpyDeviceToHost));
+  CU_OK(cudaMemcpy(packed.data(), ws.corners, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  CU_OK(cudaMemcpy(cm.data(), ws.cm, cm.size() * 2, cudaMemcpyDeviceToHost));
   for (int i = 0; i < total && i < cap; ++i) {
     const int x = packed[i] & 0x1fff, y = (packed[i] >> 13) & 0x1fff, l = packed[i] >> 26;
     corners_xys[3 * i] = x; corners_xys[3 * i + 1] = y;
@@ -603,17 +694,20 @@ int brisk_debug_scores(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_t 
   Plan plan;
   rc = make_plan(ctx, nullptr, nullptr, 1, w, h, 1, &plan);
   if (rc) return rc;
-  CU_OK(ctx->kps.ensure((size_t)w * h * 2));
+  Slot& sl = ctx->slots[0];
+  const DetectWorkspace ws = slot_ws(plan, sl);
+  (void)ws;
+  CU_OK(sl.kps.ensure((size_t)w * h * 2));
   CUtensorMap map; int write_l0;
-  rc = stage_input(ctx, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
+  rc = stage_input(ctx, sl, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
   if (rc) return rc;
-  CU_OK(launch_pyramid(map, plan.g, plan.ws.pyr, 1, write_l0, ctx->stream));
-  uint8_t* d916 = ctx->kps.as<uint8_t>();
+  CU_OK(launch_pyramid(map, plan.g, ws.pyr, 1, write_l0, sl.stream));
+  uint8_t* d916 = sl.kps.as<uint8_t>();
   uint8_t* d58 = d916 + (size_t)w * h;
-  CU_OK(launch_dense_scores(plan.g.L[0], plan.ws.pyr + plan.g.L[0].off, d916, d58, ctx->stream));
-  CU_OK(cudaMemcpyAsync(out916, d916, (size_t)w * h, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_OK(cudaMemcpyAsync(out58, d58, (size_t)w * h, cudaMemcpyDeviceToHost, ctx->stream));
-  CU_OK(cudaStreamSynchronize(ctx->stream));
+  CU_OK(launch_dense_scores(plan.g.L[0], ws.pyr + plan.g.L[0].off, d916, d58, sl.stream));
+  CU_OK(cudaMemcpyAsync(out916, d916, (size_t)w * h, cudaMemcpyDeviceToHost, sl.stream));
+  CU_OK(cudaMemcpyAsync(out58, d58, (size_t)w * h, cudaMemcpyDeviceToHost, sl.stream));
+  CU_OK(cudaStreamSynchronize(sl.stream));
   return BRISK_OK;
 }
 
@@ -629,16 +723,16 @@ int brisk_debug_nms_state(brisk_ctx* ctx, brisk_detector* det, const uint8_t* im
   size_t off = 0;
   for (int i = 0; i < g.n_layers; ++i) {
     const LayerGeom& L = g.L[i];
-    if (cm_out) CU_OK(cudaMemcpy2D(cm_out + off, (size_t)L.w * 2, ctx->cm.as<uint16_t>() + L.off, (size_t)L.pitch * 2, (size_t)L.w * 2, L.h, cudaMemcpyDeviceToHost));
-    if (bm_out) CU_OK(cudaMemcpy2D(bm_out + off, L.w, ctx->bm.as<uint8_t>() + L.off, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+    if (cm_out) CU_OK(cudaMemcpy2D(cm_out + off, (size_t)L.w * 2, ctx->slots[0].cm.as<uint16_t>() + L.off, (size_t)L.pitch * 2, (size_t)L.w * 2, L.h, cudaMemcpyDeviceToHost));
+    if (bm_out) CU_OK(cudaMemcpy2D(bm_out + off, L.w, ctx->slots[0].bm.as<uint8_t>() + L.off, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
     off += (size_t)L.w * L.h;
   }
   return count;
 }
 
 int brisk_debug_nms_rounds(brisk_ctx* ctx, int32_t* rounds /* [12] of frame 0 of the last detect call */) {
-  if (!ctx || !rounds || !ctx->rounds.p) return BRISK_ERR_INVALID;
-  CU_OK(cudaMemcpy(rounds, ctx->rounds.p, kMaxLayers * 4, cudaMemcpyDeviceToHost));
+  if (!ctx || !rounds || !ctx->slots[0].rounds.p) return BRISK_ERR_INVALID;
+  CU_OK(cudaMemcpy(rounds, ctx->slots[0].rounds.p, kMaxLayers * 4, cudaMemcpyDeviceToHost));
   return BRISK_OK;
 }
 
