@@ -5,10 +5,12 @@ Importing the package does not load CUDA; constructing a Context does and
 fails loudly when libbrisk_b200.so or a GPU is missing (no CPU fallback).
 """
 from . import build
-from .api import (KP_DTYPE, STAGES, BriskDescriptorExtractor, BriskError, BriskFeatureDetector, BruteForceMatcher,
-                  Context, Hamming, default_context, detect_and_compute_batch, lib_path, load_library)
+from .api import (KP_DTYPE, STAGES, BriskDescriptorExtractor, BriskError, BriskFeature, BriskFeatureDetector, BruteForceMatcher,
+                  Context, Hamming, HarrisScaleSpaceFeatureDetector, ScaleSpaceFeatureDetector, default_context,
+                  detect_and_compute_batch, lib_path, load_library)
 from .synthetic import random_descriptors, synthetic_batch, synthetic_frame
 
-__all__ = ["KP_DTYPE", "STAGES", "BriskDescriptorExtractor", "BriskError", "BriskFeatureDetector", "BruteForceMatcher",
+__all__ = ["KP_DTYPE", "STAGES", "BriskDescriptorExtractor", "BriskError", "BriskFeature", "BriskFeatureDetector", "BruteForceMatcher",
+           "HarrisScaleSpaceFeatureDetector", "ScaleSpaceFeatureDetector",
            "Context", "Hamming", "default_context", "detect_and_compute_batch", "lib_path", "load_library",
            "random_descriptors", "synthetic_batch", "synthetic_frame"]

@@ -212,6 +212,40 @@ class BriskFeatureDetector:
             pass
 
 
+class ScaleSpaceFeatureDetector(BriskFeatureDetector):
+    """brisk::ScaleSpaceFeatureDetector<brisk::HarrisScoreCalculator>(octaves, uniformityRadius,
+    absoluteThreshold=0, maxNumKpt=SIZE_MAX) -- reference scale-space-feature-detector.h:62-135.
+    Masks are ignored, as in the reference's detectImpl."""
+
+    def __init__(self, octaves, uniformityRadius, absoluteThreshold=0.0, maxNumKpt=None, ctx=None):
+        self.ctx = ctx or default_context()
+        self.octaves = int(octaves)
+        self._h = C.c_void_p()
+        mk = -1 if maxNumKpt is None else int(maxNumKpt)
+        self.ctx._check(self.ctx._lib.brisk_harris_detector_create(self.ctx._h, self.octaves, C.c_double(uniformityRadius),
+                                                                    C.c_double(absoluteThreshold), C.c_int64(mk), C.byref(self._h)))
+
+
+HarrisScaleSpaceFeatureDetector = ScaleSpaceFeatureDetector
+
+
+class BriskFeature:
+    """brisk::BriskFeature(octaves, uniformityRadius, absoluteThreshold=0, maxNumKpt, rotationInvariant=true,
+    scaleInvariant=true, extractorVersion=briskV2): Harris scale-space detector + extractor in one
+    object -- reference brisk/include/brisk/brisk-feature.h:54-114."""
+
+    def __init__(self, octaves, uniformityRadius, absoluteThreshold=0.0, maxNumKpt=None, rotationInvariant=True,
+                 scaleInvariant=True, extractorVersion=2, ctx=None):
+        self.ctx = ctx or default_context()
+        self.detector = ScaleSpaceFeatureDetector(octaves, uniformityRadius, absoluteThreshold, maxNumKpt, ctx=self.ctx)
+        self.extractor = BriskDescriptorExtractor(rotationInvariant, scaleInvariant, extractorVersion, ctx=self.ctx)
+
+    def detectAndCompute(self, image, mask=None, cap=65536):
+        kps, counts, desc = detect_and_compute_batch(self.detector, self.extractor, image, cap=cap)
+        n = int(counts[0])
+        return kps[0, :n].copy(), desc[0, :n].copy()
+
+
 class BriskDescriptorExtractor:
     """brisk::BriskDescriptorExtractor(rotationInvariant, scaleInvariant, version, patternScale)."""
 

@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "harris_logic.cuh"
 #include "kernels.h"
 #include "pattern.h"
 
@@ -47,8 +48,10 @@ struct Slot {
   size_t h_counts_cap = 0;
   DevBuf pyr, cm, bm, rowcnt, layer_start, corners, fwin, checks, kp_tmp, kp_valid, integral, rounds;
   DevBuf tight, kps, kps_scratch, scales, counts, desc, masks, flag;
-  DevBuf* all[20] = {&pyr, &cm, &bm, &rowcnt, &layer_start, &corners, &fwin, &checks, &kp_tmp, &kp_valid, &integral, &rounds,
-                     &tight, &kps, &kps_scratch, &scales, &counts, &desc, &masks, &flag};
+  DevBuf h_scores, h_pts, h_keep, h_sorted, h_layer_kept, h_occ, h_surv, h_layer_surv;
+  DevBuf* all[28] = {&pyr, &cm, &bm, &rowcnt, &layer_start, &corners, &fwin, &checks, &kp_tmp, &kp_valid, &integral, &rounds,
+                     &tight, &kps, &kps_scratch, &scales, &counts, &desc, &masks, &flag,
+                     &h_scores, &h_pts, &h_keep, &h_sorted, &h_layer_kept, &h_occ, &h_surv, &h_layer_surv};
 };
 
 struct brisk_ctx {
@@ -71,6 +74,9 @@ struct brisk_detector {
   brisk_ctx* ctx;
   int thresh, octaves, suppress;
   int corner_cap;  // 0 = auto
+  int harris = 0;  // 1: Harris scale-space detector
+  double radius = 0, abs_thr = 0;
+  long long max_kpt = -1;
 };
 
 struct brisk_extractor {
@@ -146,6 +152,7 @@ int encode_map(brisk_ctx* ctx, const void* base, int w, int h, int n, size_t pit
 
 struct Plan {
   PyramidGeom g;
+  HarrisWorkspace hw;  // occupancy geometry (Harris only)
   DetectWorkspace ws;  // geometry part only; pointers come from slot_ws()
   int chunk;
   int n_slots;
@@ -162,12 +169,27 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
   for (int i = 0; i < g.n_layers; ++i) { ws.row_off[i] = ws.total_rows; ws.total_rows += g.L[i].h; }
   ws.row_off[g.n_layers] = ws.total_rows;
   int ccap = det ? det->corner_cap : 0;
-  if (ccap <= 0) ccap = std::min(std::max((int)(((long long)w * h) / 24), 4096), 1 << 20);
+  const bool harris = det && det->harris;
+  if (ccap <= 0) ccap = std::min(std::max((int)(((long long)w * h) / (harris ? 10 : 24)), harris ? 8192 : 4096), 1 << 20);
+  memset(&plan->hw, 0, sizeof(plan->hw));
+  if (harris) {
+    // occupancy maps of EnforceKeyPointUniformity (uniformity-enforcement-inl.h:62-66)
+    const float scaling = (float)(15.0 / (double)(float)(det->radius == 0 ? 1.0 : det->radius));
+    long long off = 0;
+    for (int i = 0; i < g.n_layers; ++i) {
+      plan->hw.occ_h[i] = (int)(g.L[i].h * std::ceil((double)scaling) + 32);
+      plan->hw.occ_w[i] = (int)(g.L[i].w * std::ceil((double)scaling) + 32);
+      plan->hw.occ_off[i] = off;
+      off += ((long long)plan->hw.occ_h[i] * plan->hw.occ_w[i] + 64 + 255) / 256 * 256;
+    }
+    plan->hw.occ_frame_bytes = off;
+  }
   ws.corner_cap = det ? ccap : 0;
   plan->integral_elems = ext ? (size_t)(w + 1) * (h + 1) : 0;
   const int desc_bytes = ext ? ext->dev.desc_bytes : 0;
   size_t per_frame = (size_t)g.frame_elems;  // image planes
-  if (det) per_frame += (size_t)g.frame_elems * 3 + (size_t)ws.total_rows * 4 + (size_t)ws.corner_cap * (4 + 32 + 32 + 28 + 1);
+  if (det && !harris) per_frame += (size_t)g.frame_elems * 3 + (size_t)ws.total_rows * 4 + (size_t)ws.corner_cap * (4 + 32 + 32 + 28 + 1);
+  if (harris) per_frame += (size_t)g.frame_elems * 4 + (size_t)ws.total_rows * 4 + (size_t)ws.corner_cap * 25 + (size_t)plan->hw.occ_frame_bytes;
   per_frame += plan->integral_elems * 4 + (size_t)cap * (28 * 2 + 4 + desc_bytes) + 2 * (size_t)w * h /* mask, tight copy */;
   // two slots share the workspace limit; at least two chunks when there is more than one frame, so
   // that copies and the serial tail of one chunk overlap the kernels of the other
@@ -184,7 +206,18 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
   for (int si = 0; si < plan->n_slots; ++si) {
     Slot& sl = ctx->slots[si];
     CU_OK(sl.pyr.ensure(c * g.frame_elems));
-    if (det) {
+    if (harris) {
+      CU_OK(sl.rowcnt.ensure(c * ws.total_rows * 4));
+      CU_OK(sl.layer_start.ensure(c * (kMaxLayers + 1) * 4));
+      CU_OK(sl.h_scores.ensure(c * g.frame_elems * 4));
+      CU_OK(sl.h_pts.ensure(c * ws.corner_cap * 8));
+      CU_OK(sl.h_keep.ensure(c * ws.corner_cap));
+      CU_OK(sl.h_sorted.ensure(c * ws.corner_cap * 8));
+      CU_OK(sl.h_surv.ensure(c * ws.corner_cap * 8));
+      CU_OK(sl.h_layer_kept.ensure(c * kMaxLayers * 4));
+      CU_OK(sl.h_layer_surv.ensure(c * kMaxLayers * 4));
+      CU_OK(sl.h_occ.ensure(c * (size_t)plan->hw.occ_frame_bytes));
+    } else if (det) {
       CU_OK(sl.cm.ensure(c * g.frame_elems * 2));
       CU_OK(sl.bm.ensure(c * g.frame_elems));
       CU_OK(sl.rowcnt.ensure(c * ws.total_rows * 4));
@@ -262,7 +295,11 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
   memset(ctx->ms, 0, sizeof(ctx->ms));
   ctx->launches = 0;
   if (n == 0) return BRISK_OK;
-  if (det) {
+  if (det && det->harris) {
+    if (det->octaves < 0 || 2 * det->octaves > kMaxLayers) return fail(ctx, BRISK_ERR_UNSUPPORTED, "octaves must be in [0, 6]");
+    if (!(det->radius > 0.0)) return fail(ctx, BRISK_ERR_UNSUPPORTED, "uniformityRadius <= 0 (key point bucketing) is not implemented");
+    if (det->radius < 15.0 / 4.0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "uniformityRadius below 3.75 is not supported");
+  } else if (det) {
     if (det->thresh < 30 || det->thresh > 255)
       return fail(ctx, BRISK_ERR_UNSUPPORTED, "AGAST threshold must be in [30, 255] (lower values make corner scores <= 2, whose cache semantics are not implemented)");
     if (det->octaves < 0 || 2 * det->octaves > kMaxLayers) return fail(ctx, BRISK_ERR_UNSUPPORTED, "octaves must be in [0, 6]");
@@ -373,7 +410,16 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     }
     tm.mark(2);
     CU_OK(cudaMemsetAsync(sl.flag.p, 0, 16, sl.stream));
-    if (det) {
+    if (det && det->harris) {
+      HarrisWorkspace hw = plan.hw;
+      hw.det = ws;
+      hw.scores = sl.h_scores.as<int>(); hw.pts = sl.h_pts.as<HPoint>(); hw.keep = sl.h_keep.as<uint8_t>();
+      hw.sorted = sl.h_sorted.as<HPoint>(); hw.layer_kept = sl.h_layer_kept.as<int>(); hw.occ = sl.h_occ.as<uint8_t>();
+      hw.surv = sl.h_surv.as<HPoint>(); hw.layer_surv = sl.h_layer_surv.as<int>();
+      tm.mark(3); tm.mark(4);
+      CU_OK(launch_harris_detect(g, hw, c, det->radius, det->abs_thr, det->max_kpt, d_kps, d_counts, cap, sl.flag.as<int>(), sl.stream));
+      ctx->launches += 3 * g.n_layers + 5;
+    } else if (det) {
       CU_OK(launch_agast_detect(g, ws, c, det->thresh, sl.stream));
       ctx->launches += g.n_layers;
       tm.mark(3);
@@ -516,6 +562,15 @@ int brisk_ctx_last_timing(brisk_ctx* ctx, float* ms, int64_t* launches) {
 int brisk_agast_detector_create(brisk_ctx* ctx, int thresh, int octaves, int suppress, brisk_detector** out) {
   if (!ctx || !out) return BRISK_ERR_INVALID;
   *out = new brisk_detector{ctx, thresh, octaves, suppress, 0};
+  return BRISK_OK;
+}
+
+int brisk_harris_detector_create(brisk_ctx* ctx, int octaves, double uniformity_radius, double absolute_threshold,
+                                 int64_t max_kpts, brisk_detector** out) {
+  if (!ctx || !out) return BRISK_ERR_INVALID;
+  brisk_detector* d = new brisk_detector{ctx, 0, octaves, 1, 0};
+  d->harris = 1; d->radius = uniformity_radius; d->abs_thr = absolute_threshold; d->max_kpt = max_kpts < 0 ? -1 : (long long)max_kpts;
+  *out = d;
   return BRISK_OK;
 }
 

@@ -193,6 +193,11 @@ corner_fill_kernel(LayerGeom L, int layer, long long frame_elems, const uint16_t
   }
 }
 
+cudaError_t launch_row_scan(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int* overflow_flag, cudaStream_t stream) {
+  row_scan_kernel<<<n_frames, 1024, 0, stream>>>(ws.rowcnt, ws.total_rows, g, ws, overflow_flag);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_corner_lists(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int* overflow_flag, cudaStream_t stream) {
   row_scan_kernel<<<n_frames, 1024, 0, stream>>>(ws.rowcnt, ws.total_rows, g, ws, overflow_flag);
   for (int l = 0; l < g.n_layers; ++l) {

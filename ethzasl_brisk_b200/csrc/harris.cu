@@ -1,0 +1,280 @@
+// Harris scale-space detector kernels (sm_100a).
+//
+// Replaces ScaleSpaceFeatureDetector<HarrisScoreCalculator>::detectImpl and its layers
+// (reference brisk/include/brisk/scale-space-feature-detector.h:100-128,
+// internal/scale-space-layer-inl.h:60-428, brisk/src/harris-scores.cc:53-279,
+// brisk/src/harris-score-calculator.cc:57-106, internal/uniformity-enforcement-inl.h:44-194).
+//   harris_scores_kernel      tile + halo 2 in shared memory: Scharr products (pmulhw semantics),
+//                             3x3 binomial smoothing, integer response -> i32 score plane
+//   harris_maxima_*           8-neighbour maxima >= threshold, raster-ordered lists (warp per row)
+//   harris_nms3d_kernel       bilinear double-precision reads of the layers above / below
+//   harris_sort_kernel        per (frame, layer): compaction + replay of libstdc++'s introsort
+//                             (the tie order of equal scores is part of the reference's result)
+//   harris_uniformity_kernel  per (frame, layer): greedy occupancy stamping, 31x31 saturating adds
+//   harris_emit_kernel        sub-pixel refinement, key points in layer-major order
+#include <cuda_runtime.h>
+
+#include "harris_logic.cuh"
+#include "kernels.h"
+
+namespace briskb200 {
+
+constexpr int kHsTW = 64, kHsTH = 16, kHsThreads = 256;
+
+__global__ void __launch_bounds__(kHsThreads)
+harris_scores_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restrict__ pyr, int* __restrict__ scores) {
+  __shared__ uint8_t s_img[kHsTH + 4][kHsTW + 4];
+  __shared__ short s_xx[kHsTH + 2][kHsTW + 2], s_yy[kHsTH + 2][kHsTW + 2], s_xy[kHsTH + 2][kHsTW + 2];
+  const int x0 = blockIdx.x * kHsTW, y0 = blockIdx.y * kHsTH, frame = blockIdx.z, tid = threadIdx.x;
+  const uint8_t* img = pyr + (long long)frame * frame_elems + L.off;
+  int* out = scores + (long long)frame * frame_elems + L.off;
+  for (int i = tid; i < (kHsTH + 4) * (kHsTW + 4); i += kHsThreads) {
+    const int r = i / (kHsTW + 4), c = i - r * (kHsTW + 4);
+    const int y = y0 - 2 + r, x = x0 - 2 + c;
+    s_img[r][c] = (y >= 0 && y < L.h && x >= 0 && x < L.w) ? img[(long long)y * L.pitch + x] : 0;
+  }
+  __syncthreads();
+  for (int i = tid; i < (kHsTH + 2) * (kHsTW + 2); i += kHsThreads) {
+    const int r = i / (kHsTW + 2), c = i - r * (kHsTW + 2);  // product plane (r, c) <-> pixel (y0-1+r, x0-1+c) <-> s_img[r+1][c+1]
+    int p[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) p[k] = s_img[r + k / 3][c + k % 3];
+    int xx, yy, xy;
+    harris_products(p, &xx, &yy, &xy);
+    s_xx[r][c] = (short)xx; s_yy[r][c] = (short)yy; s_xy[r][c] = (short)xy;
+  }
+  __syncthreads();
+  for (int i = tid; i < kHsTH * kHsTW; i += kHsThreads) {
+    const int r = i / kHsTW, c = i - r * kHsTW;
+    const int y = y0 + r, x = x0 + c;
+    if (x >= L.w || y >= L.h) continue;
+    int v = 0;
+    if (x >= 2 && x < L.w - 2 && y >= 2 && y < L.h - 2) {
+      int qa[9], qb[9], qc[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { qa[k] = s_xx[r + k / 3][c + k % 3]; qb[k] = s_yy[r + k / 3][c + k % 3]; qc[k] = s_xy[r + k / 3][c + k % 3]; }
+      v = harris_response(harris_smooth(qa), harris_smooth(qb), harris_smooth(qc));
+    }
+    out[(long long)y * L.pitch + x] = v;
+  }
+}
+
+__device__ __forceinline__ bool harris_is_max(const int* __restrict__ p, int pitch, int thr) {
+  const int c = p[0];
+  if (c < thr) return false;
+  return !(p[1] > c || p[-1] > c || p[pitch] > c || p[-pitch] > c || p[pitch + 1] > c || p[pitch - 1] > c || p[-pitch + 1] > c || p[-pitch - 1] > c);
+}
+
+// warp per row; FILL = false: count into rowcnt, FILL = true: emit at the row's slot
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+harris_maxima_kernel(LayerGeom L, long long frame_elems, const int* __restrict__ scores, int thr, int* __restrict__ rowcnt,
+                     int total_rows, int row_off, HPoint* __restrict__ pts, int cap) {
+  const int frame = blockIdx.y, lane = threadIdx.x & 31;
+  const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (y >= L.h) return;
+  int* rc = rowcnt + (long long)frame * total_rows + row_off + y;
+  if (y < 2 || y >= L.h - 2) { if (!FILL && lane == 0) *rc = 0; return; }
+  const int* row = scores + (long long)frame * frame_elems + L.off + (long long)y * L.pitch;
+  int slot = FILL ? *rc : 0;
+  HPoint* out = pts + (long long)frame * cap;
+  for (int xb = 0; xb < L.w; xb += 32) {
+    const int x = xb + lane;
+    const bool m = x >= 2 && x < L.w - 2 && harris_is_max(row + x, L.pitch, thr);
+    const uint32_t bal = __ballot_sync(0xffffffffu, m);
+    if (FILL && m) {
+      const int s = slot + __popc(bal & ((1u << lane) - 1));
+      if (s < cap) out[s] = HPoint{row[x], (unsigned short)x, (unsigned short)y};
+    }
+    slot += __popc(bal);
+  }
+  if (!FILL && lane == 0) *rc = slot;
+}
+
+// layer of maximum k of a frame (layer_start is ascending)
+__device__ __forceinline__ int layer_of(const int* ls, int n_layers, int k) {
+  int l = 0;
+  while (l + 1 < n_layers && k >= ls[l + 1]) ++l;
+  return l;
+}
+
+struct HarrisLayerParams {
+  double scale[kMaxLayers], offset[kMaxLayers], scale_above[kMaxLayers], offset_above[kMaxLayers], scale_below[kMaxLayers], offset_below[kMaxLayers];
+};
+
+// 3-D non-maximum suppression (scale-space-layer-inl.h:218-366): reject a maximum that is smaller
+// than any of 9 bilinear reads of the layer above, or than the read of the layer below (the
+// reference's nine "below" reads collapse to one because int(1/scale_below) == 0).
+__global__ void __launch_bounds__(128)
+harris_nms3d_kernel(PyramidGeom g, HarrisLayerParams hp, const int* __restrict__ scores, const int* __restrict__ layer_start,
+                    const HPoint* __restrict__ pts, uint8_t* __restrict__ keep, int cap, int abs_thr) {
+  const int frame = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int* ls = layer_start + (long long)frame * (kMaxLayers + 1);
+  const int n = min(ls[g.n_layers], cap);
+  if (k >= n) return;
+  const int layer = layer_of(ls, g.n_layers, k);
+  const HPoint p = pts[(long long)frame * cap + k];
+  const long long fo = (long long)frame * g.frame_elems;
+  bool ok = p.score >= abs_thr;
+  if (ok && layer + 1 < g.n_layers) {
+    const LayerGeom& A = g.L[layer + 1];
+    const int* sa = scores + fo + A.off;
+    const double sc = hp.scale_above[layer], of = hp.offset_above[layer];
+    const int ox[9] = {0, 1, -1, 0, 0, 1, 1, -1, -1}, oy[9] = {0, 0, 0, 1, -1, 1, -1, 1, -1};
+#pragma unroll 1
+    for (int j = 0; j < 9 && ok; ++j) {
+      const double u = (double)((int)p.x + ox[j]), v = (double)((int)p.y + oy[j]);
+      if ((double)p.score < harris_score_bilinear(sa, A.pitch, A.w, A.h, sc * (u + of), sc * (v + of))) ok = false;
+    }
+  }
+  if (ok && layer > 0) {
+    const LayerGeom& B = g.L[layer - 1];
+    const double sc = hp.scale_below[layer], of = hp.offset_below[layer];
+    if ((double)p.score < harris_score_bilinear(scores + fo + B.off, B.pitch, B.w, B.h, sc * ((double)(int)p.x + of), sc * ((double)(int)p.y + of))) ok = false;
+  }
+  keep[(long long)frame * cap + k] = ok ? 1 : 0;
+}
+
+// One thread per (frame, layer): stable compaction of the kept maxima, then std::sort's permutation.
+__global__ void __launch_bounds__(32)
+harris_sort_kernel(int n_layers, int n_items, const int* __restrict__ layer_start, const HPoint* __restrict__ pts,
+                   const uint8_t* __restrict__ keep, HPoint* __restrict__ sorted, int* __restrict__ layer_kept, int cap) {
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_items) return;
+  const int frame = item / n_layers, layer = item - frame * n_layers;
+  const int* ls = layer_start + (long long)frame * (kMaxLayers + 1);
+  const int begin = min(ls[layer], cap), end = min(ls[layer + 1], cap);
+  const HPoint* src = pts + (long long)frame * cap;
+  const uint8_t* kf = keep + (long long)frame * cap;
+  HPoint* dst = sorted + (long long)frame * cap + begin;
+  int m = 0;
+  for (int k = begin; k < end; ++k)
+    if (kf[k]) dst[m++] = src[k];
+  layer_kept[frame * kMaxLayers + layer] = m;
+  gcc_sort(dst, m);
+}
+
+struct UniformityGeom {
+  long long occ_frame_bytes;
+  long long occ_off[kMaxLayers];
+  int occ_w[kMaxLayers], occ_h[kMaxLayers];
+  float scaling;
+};
+
+// One CTA per (frame, layer): EnforceKeyPointUniformity (uniformity-enforcement-inl.h:44-194).
+// The sorted points are visited in order; the skip test of a point must see the stamps of all its
+// predecessors, so the CTA synchronises after every stamp (about 5 % of the points).
+__global__ void __launch_bounds__(256)
+harris_uniformity_kernel(PyramidGeom g, UniformityGeom ug, const int* __restrict__ layer_start, const HPoint* __restrict__ sorted,
+                         const int* __restrict__ layer_kept, uint8_t* __restrict__ occ_all, HPoint* __restrict__ surv,
+                         int* __restrict__ layer_surv, int cap, long long max_kpt) {
+  const int frame = blockIdx.y, layer = blockIdx.x, tid = threadIdx.x;
+  const int* ls = layer_start + (long long)frame * (kMaxLayers + 1);
+  const int begin = min(ls[layer], cap);
+  const int m = layer_kept[frame * kMaxLayers + layer];
+  const HPoint* pts = sorted + (long long)frame * cap + begin;
+  HPoint* out = surv + (long long)frame * cap + begin;
+  uint8_t* occ = occ_all + (long long)frame * ug.occ_frame_bytes + ug.occ_off[layer];
+  const int ow = ug.occ_w[layer], oh = ug.occ_h[layer];
+  for (long long i = tid; i < (long long)ow * oh; i += blockDim.x) occ[i] = 0;
+  __syncthreads();
+  int kept = 0;
+  if (m > 0) {
+    const float max_score = (float)pts[0].score;
+    for (int k = 0; k < m; ++k) {
+      const HPoint p = pts[k];
+      const int cy = (int)((float)(int)p.y * ug.scaling + 16.0f), cx = (int)((float)(int)p.x * ug.scaling + 16.0f);
+      const float nsc1 = uniformity_nsc1(p.score, max_score);
+      if ((double)nsc1 < (double)occ[(long long)cy * ow + cx]) continue;  // uniform across the CTA
+      __syncthreads();  // everybody has read the cell before it is stamped
+      const float nsc = 0.99f * nsc1;
+      for (int c = tid; c < 31 * 31; c += blockDim.x) {
+        const int y = c / 31, x = c - y * 31;
+        uint8_t* o = occ + (long long)(cy + y - 15) * ow + cx + x - 15;
+        const int v = (int)*o + uniformity_stamp(x, y, nsc);
+        *o = (uint8_t)(v > 255 ? 255 : v);
+      }
+      if (tid == 0) out[kept] = p;
+      ++kept;
+      __syncthreads();
+      if ((long long)kept == max_kpt) break;
+    }
+  }
+  if (tid == 0) layer_surv[frame * kMaxLayers + layer] = kept;
+}
+
+// One CTA per frame: sub-pixel refinement and key-point emission in layer-major order
+// (scale-space-layer-inl.h:386-412).
+__global__ void __launch_bounds__(256)
+harris_emit_kernel(PyramidGeom g, HarrisLayerParams hp, const int* __restrict__ scores, const int* __restrict__ layer_start,
+                   const HPoint* __restrict__ surv, const int* __restrict__ layer_surv, int cap, KeyPoint* __restrict__ out,
+                   int* __restrict__ counts, int kp_cap) {
+  const int frame = blockIdx.x, tid = threadIdx.x;
+  const int* ls = layer_start + (long long)frame * (kMaxLayers + 1);
+  int base = 0;
+  for (int layer = 0; layer < g.n_layers; ++layer) {
+    const int m = layer_surv[frame * kMaxLayers + layer];
+    const HPoint* pts = surv + (long long)frame * cap + min(ls[layer], cap);
+    const LayerGeom& L = g.L[layer];
+    const int* sc = scores + (long long)frame * g.frame_elems + L.off;
+    for (int k = tid; k < m; k += blockDim.x) {
+      const HPoint p = pts[k];
+      const int* c = sc + (long long)p.y * L.pitch + p.x;
+      float dx, dy;
+      harris_subpixel2d((double)c[-L.pitch - 1], (double)c[-L.pitch], (double)c[-L.pitch + 1], (double)c[-1], (double)c[0], (double)c[1],
+                        (double)c[L.pitch - 1], (double)c[L.pitch], (double)c[L.pitch + 1], &dx, &dy);
+      KeyPoint kp;
+      kp.x = (float)(hp.scale[layer] * ((double)((float)(int)p.x + dx) + hp.offset[layer]));
+      kp.y = (float)(hp.scale[layer] * ((double)((float)(int)p.y + dy) + hp.offset[layer]));
+      kp.size = (float)(hp.scale[layer] * 12.0);
+      kp.angle = -1.0f; kp.response = (float)p.score; kp.octave = layer / 2; kp.class_id = -1;
+      if (base + k < kp_cap) out[(long long)frame * kp_cap + base + k] = kp;
+    }
+    base += m;
+  }
+  if (tid == 0) counts[frame] = base;
+}
+
+cudaError_t launch_harris_detect(const PyramidGeom& g, const HarrisWorkspace& hw, int n_frames, double radius, double abs_thr,
+                                 long long max_kpt, KeyPoint* out, int* counts, int kp_cap, int* overflow_flag, cudaStream_t stream) {
+  // layer transforms of ScaleSpaceLayer::Create (scale-space-layer-inl.h:60-182)
+  HarrisLayerParams hp;
+  for (int i = 0; i < g.n_layers; ++i) {
+    const bool octave = (i % 2) == 0;
+    if (octave) { hp.offset_above[i] = -0.25; hp.offset_below[i] = 1.0 / 6.0; hp.scale_above[i] = 2.0 / 3.0; hp.scale_below[i] = 4.0 / 3.0; hp.scale[i] = i == 0 ? 1.0 : pow(2.0, (double)(i / 2)); }
+    else { hp.offset_above[i] = -1.0 / 6.0; hp.offset_below[i] = 0.125; hp.scale_above[i] = 0.75; hp.scale_below[i] = 1.5; hp.scale[i] = pow(2.0, (double)(i / 2)) * 1.5; }
+    hp.offset[i] = i == 0 ? 0.0 : hp.scale[i] * 0.5 - 0.5;
+  }
+  const int thr = (int)abs_thr;
+  for (int l = 0; l < g.n_layers; ++l) {
+    const LayerGeom& L = g.L[l];
+    dim3 grid((L.w + kHsTW - 1) / kHsTW, (L.h + kHsTH - 1) / kHsTH, n_frames);
+    harris_scores_kernel<<<grid, kHsThreads, 0, stream>>>(L, g.frame_elems, hw.det.pyr, hw.scores);
+  }
+  for (int l = 0; l < g.n_layers; ++l) {
+    const LayerGeom& L = g.L[l];
+    dim3 grid((L.h + 7) / 8, n_frames);
+    harris_maxima_kernel<false><<<grid, 256, 0, stream>>>(L, g.frame_elems, hw.scores, thr, hw.det.rowcnt, hw.det.total_rows, hw.det.row_off[l], hw.pts, hw.det.corner_cap);
+  }
+  cudaError_t e = launch_row_scan(g, hw.det, n_frames, overflow_flag, stream);
+  if (e != cudaSuccess) return e;
+  for (int l = 0; l < g.n_layers; ++l) {
+    const LayerGeom& L = g.L[l];
+    dim3 grid((L.h + 7) / 8, n_frames);
+    harris_maxima_kernel<true><<<grid, 256, 0, stream>>>(L, g.frame_elems, hw.scores, thr, hw.det.rowcnt, hw.det.total_rows, hw.det.row_off[l], hw.pts, hw.det.corner_cap);
+  }
+  dim3 gp((hw.det.corner_cap + 127) / 128, n_frames);
+  harris_nms3d_kernel<<<gp, 128, 0, stream>>>(g, hp, hw.scores, hw.det.layer_start, hw.pts, hw.keep, hw.det.corner_cap, thr);
+  const int items = n_frames * g.n_layers;
+  harris_sort_kernel<<<(items + 31) / 32, 32, 0, stream>>>(g.n_layers, items, hw.det.layer_start, hw.pts, hw.keep, hw.sorted, hw.layer_kept, hw.det.corner_cap);
+  UniformityGeom ug;
+  ug.occ_frame_bytes = hw.occ_frame_bytes;
+  ug.scaling = (float)(15.0 / (double)(float)radius);
+  for (int l = 0; l < g.n_layers; ++l) { ug.occ_off[l] = hw.occ_off[l]; ug.occ_w[l] = hw.occ_w[l]; ug.occ_h[l] = hw.occ_h[l]; }
+  harris_uniformity_kernel<<<dim3(g.n_layers, n_frames), 256, 0, stream>>>(g, ug, hw.det.layer_start, hw.sorted, hw.layer_kept, hw.occ, hw.surv, hw.layer_surv, hw.det.corner_cap, max_kpt);
+  harris_emit_kernel<<<n_frames, 256, 0, stream>>>(g, hp, hw.scores, hw.det.layer_start, hw.surv, hw.layer_surv, hw.det.corner_cap, out, counts, kp_cap);
+  return cudaGetLastError();
+}
+
+}  // namespace briskb200

@@ -39,6 +39,26 @@ cudaError_t launch_agast_nms(const PyramidGeom& g, const DetectWorkspace& ws, in
                              long long mask_frame_stride, int mask_pitch, KeyPoint* out, int* counts, int kp_cap,
                              int* error_flag, cudaStream_t stream);
 
+// Harris scale-space detector (harris.cu).
+struct HPoint;
+struct HarrisWorkspace {
+  DetectWorkspace det;   // pyr, rowcnt, layer_start, total_rows, row_off, corner_cap (= maxima capacity per frame)
+  int* scores;           // i32 score planes, PyramidGeom layout
+  HPoint* pts;           // [frame][cap] 2-D maxima, layer-major raster order
+  uint8_t* keep;         // [frame][cap] 3-D NMS verdicts
+  HPoint* sorted;        // [frame][cap] kept maxima per layer, std::sort order
+  int* layer_kept;       // [frame][kMaxLayers]
+  uint8_t* occ;          // [frame][occ_frame_bytes] occupancy maps
+  HPoint* surv;          // [frame][cap] survivors of the uniformity enforcement
+  int* layer_surv;       // [frame][kMaxLayers]
+  long long occ_frame_bytes;
+  long long occ_off[kMaxLayers];
+  int occ_w[kMaxLayers], occ_h[kMaxLayers];
+};
+cudaError_t launch_row_scan(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int* overflow_flag, cudaStream_t stream);
+cudaError_t launch_harris_detect(const PyramidGeom& g, const HarrisWorkspace& hw, int n_frames, double radius, double abs_thr,
+                                 long long max_kpt, KeyPoint* out, int* counts, int kp_cap, int* overflow_flag, cudaStream_t stream);
+
 cudaError_t launch_dense_scores(const LayerGeom& L, const uint8_t* img, uint8_t* out916, uint8_t* out58, cudaStream_t stream);
 
 // Descriptor extraction.

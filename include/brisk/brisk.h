@@ -96,6 +96,61 @@ class BriskFeatureDetector {
   mutable int cfg_thr_ = 0, cfg_oct_ = 0;
 };
 
+// Tag type: the only score calculator of the reference that is usable with the scale-space
+// detector (brisk/include/brisk/harris-score-calculator.h:52-90).
+class HarrisScoreCalculator {};
+
+// brisk::ScaleSpaceFeatureDetector<SCORE_CALCULATOR_T> -- reference
+// brisk/include/brisk/scale-space-feature-detector.h:62-135.  Empty images return silently; the
+// mask is ignored (as in the reference's detectImpl); non-empty input key points ("use passed key
+// points" mode, :103-108) are not supported.
+template <class SCORE_CALCULATOR_T>
+class ScaleSpaceFeatureDetector {
+ public:
+  typedef SCORE_CALCULATOR_T ScoreCalculator_t;
+  ScaleSpaceFeatureDetector(size_t octaves, double uniformityRadius, double absoluteThreshold = 0,
+                            size_t maxNumKpt = std::numeric_limits<size_t>::max())
+      : _octaves(octaves), _uniformityRadius(uniformityRadius), _absoluteThreshold(absoluteThreshold), _maxNumKpt(maxNumKpt) {}
+  virtual ~ScaleSpaceFeatureDetector() { if (det_) brisk_detector_destroy(det_); }
+  ScaleSpaceFeatureDetector(const ScaleSpaceFeatureDetector&) = delete;
+  ScaleSpaceFeatureDetector& operator=(const ScaleSpaceFeatureDetector&) = delete;
+
+  void detect(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, const agast::Mat& /*mask*/ = agast::Mat()) const {
+    if (image.empty()) return;
+    if (!keypoints.empty()) throw std::runtime_error("brisk_b200: detection from passed key points is not supported");
+    brisk_ctx* ctx = detail::context();
+    if (!det_ || ctx_ != ctx) {
+      if (det_) brisk_detector_destroy(det_);
+      det_ = nullptr;
+      const int64_t mk = _maxNumKpt > (size_t)std::numeric_limits<int64_t>::max() ? -1 : (int64_t)_maxNumKpt;
+      detail::check(ctx, brisk_harris_detector_create(ctx, (int)_octaves, _uniformityRadius, _absoluteThreshold, mk, &det_));
+      ctx_ = ctx;
+    }
+    int cap = (int)std::max<long long>(4096, (long long)image.rows * image.cols / 64);
+    for (;;) {
+      keypoints.resize(cap);
+      int32_t count = 0;
+      const int rc = brisk_detect(ctx, det_, image.data, 1, image.cols, image.rows, image.step, image.step * image.rows, nullptr,
+                                  reinterpret_cast<brisk_keypoint*>(keypoints.data()), &count, cap);
+      if (rc == BRISK_ERR_CAPACITY && count > cap) { cap = count; continue; }
+      detail::check(ctx, rc);
+      keypoints.resize(count);
+      return;
+    }
+  }
+
+ protected:
+  size_t _octaves;
+  double _uniformityRadius;
+  double _absoluteThreshold;
+  size_t _maxNumKpt;
+
+ private:
+  mutable brisk_detector* det_ = nullptr;
+  mutable brisk_ctx* ctx_ = nullptr;
+};
+typedef ScaleSpaceFeatureDetector<HarrisScoreCalculator> HarrisScaleSpaceFeatureDetector;
+
 // brisk::BriskDescriptorExtractor -- reference brisk/include/brisk/brisk-descriptor-extractor.h:54-202.
 class BriskDescriptorExtractor {
  public:
@@ -161,6 +216,28 @@ class BriskDescriptorExtractor {
   mutable brisk_extractor* ext_ = nullptr;
   mutable brisk_ctx* ctx_ = nullptr;
   mutable bool cfg_rot_ = false, cfg_scale_ = false;
+};
+
+// brisk::BriskFeature -- reference brisk/include/brisk/brisk-feature.h:54-114: Harris scale-space
+// detector + BRISK extractor behind one detectAndCompute().
+class BriskFeature {
+ public:
+  BriskFeature(size_t octaves, double uniformityRadius, double absoluteThreshold = 0,
+               size_t maxNumKpt = std::numeric_limits<size_t>::max(), bool rotationInvariant = true, bool scaleInvariant = true,
+               int extractorVersion = BriskDescriptorExtractor::briskV2)
+      : _briskDetector(octaves, uniformityRadius, absoluteThreshold, maxNumKpt),
+        _briskExtractor(rotationInvariant, scaleInvariant, extractorVersion) {}
+  int descriptorSize() const { return _briskExtractor.descriptorSize(); }
+  int descriptorType() const { return _briskExtractor.descriptorType(); }
+  void detectAndCompute(const agast::Mat& image, const agast::Mat& mask, std::vector<agast::KeyPoint>& keypoints,
+                        agast::Mat& descriptors, bool useProvidedKeypoints = false) {
+    if (!useProvidedKeypoints) { keypoints.clear(); _briskDetector.detect(image, keypoints, mask); }
+    _briskExtractor.compute(image, keypoints, descriptors);
+  }
+
+ private:
+  ScaleSpaceFeatureDetector<HarrisScoreCalculator> _briskDetector;
+  BriskDescriptorExtractor _briskExtractor;
 };
 
 // brisk::Hamming -- reference brisk/include/brisk/internal/hamming.h:56-114.

@@ -65,6 +65,12 @@ int brisk_ctx_last_timing(brisk_ctx* ctx, float* ms /* [BRISK_STAGE_COUNT] */, i
  * -- reference brisk/include/brisk/brisk-feature-detector.h:51-84. */
 int brisk_agast_detector_create(brisk_ctx* ctx, int thresh, int octaves, int suppress_scale_nonmaxima,
                                 brisk_detector** out);
+/* brisk::ScaleSpaceFeatureDetector<brisk::HarrisScoreCalculator>(size_t octaves, double uniformityRadius,
+ * double absoluteThreshold = 0, size_t maxNumKpt = SIZE_MAX) -- reference
+ * brisk/include/brisk/scale-space-feature-detector.h:62-135.  max_kpts < 0 means unlimited.  The
+ * detector ignores masks, as the reference's detectImpl does (:100-101). */
+int brisk_harris_detector_create(brisk_ctx* ctx, int octaves, double uniformity_radius, double absolute_threshold,
+                                 int64_t max_kpts, brisk_detector** out);
 void brisk_detector_destroy(brisk_detector* det);
 /* Raw-corner capacity per frame (all layers); default scales with the image area. */
 int brisk_detector_set_corner_capacity(brisk_detector* det, int corners_per_frame);

@@ -26,11 +26,21 @@ int main(int argc, char** argv) {
   matcher.knnMatch(desc, desc, matches, 2);
   int self = 0;
   for (size_t i = 0; i < matches.size(); ++i) self += (matches[i].size() == 2 && matches[i][0].distance == 0);
+  // Harris scale-space detector + extractor in one object (reference test-binary-equal.cc:73-89)
+  brisk::BriskFeature feature(0, 30.0, 20.0);
+  std::vector<agast::KeyPoint> hk;
+  agast::Mat hd;
+  feature.detectAndCompute(img, agast::Mat(), hk, hd);
+  std::printf("harris: %d key points\n", (int)hk.size());
   std::ofstream o(argv[2], std::ios::binary);
   int n = (int)kps.size(), nb = desc.cols;
   o.write(reinterpret_cast<char*>(&n), 4); o.write(reinterpret_cast<char*>(&nb), 4); o.write(reinterpret_cast<char*>(&self), 4);
   o.write(reinterpret_cast<char*>(kps.data()), (std::streamsize)n * sizeof(agast::KeyPoint));
   o.write(reinterpret_cast<char*>(desc.data), (std::streamsize)n * nb);
+  int hn = (int)hk.size();
+  o.write(reinterpret_cast<char*>(&hn), 4);
+  o.write(reinterpret_cast<char*>(hk.data()), (std::streamsize)hn * sizeof(agast::KeyPoint));
+  o.write(reinterpret_cast<char*>(hd.data), (std::streamsize)hn * hd.cols);
   std::printf("%d key points, %d-byte descriptors, %d self matches\n", n, nb, self);
   return 0;
 }

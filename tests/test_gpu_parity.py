@@ -296,9 +296,59 @@ def test_cpp_dropin_classes(tmp_path, oracle, golden):
     raw = out.read_bytes()
     n, nb, self_matches = np.frombuffer(raw[:12], np.int32)
     kps = np.frombuffer(raw[12:12 + n * 28], bb.KP_DTYPE)
-    desc = np.frombuffer(raw[12 + n * 28:], np.uint8).reshape(n, nb)
+    desc = np.frombuffer(raw[12 + n * 28:12 + n * 28 + n * nb], np.uint8).reshape(n, nb)
+    off = 12 + n * 28 + n * nb
+    hn = int(np.frombuffer(raw[off:off + 4], np.int32)[0])
+    hk = np.frombuffer(raw[off + 4:off + 4 + hn * 28], bb.KP_DTYPE)
+    hd = np.frombuffer(raw[off + 4 + hn * 28:], np.uint8).reshape(hn, 48)
+    assert hn == len(golden["harris0_kps"]) and np.array_equal(hk["x"], golden["harris0_kps"]["x"]) and np.array_equal(hd, golden["harris0_desc"])
     gk, gd = golden["ast0_kps"], golden["ast0_desc"]
     assert n == len(gk) and nb == 48 and self_matches == n
     for f in ("x", "y", "size", "response", "octave", "class_id"):
         assert np.array_equal(kps[f], gk[f]), f
     assert np.array_equal(desc, gd)
+
+
+@pytest.mark.parametrize("i", [0, 1])
+def test_golden_harris_fixture(ctx, golden, i):
+    # the reference's own ValidationHarris fixture (test-binary-equal.cc:73-89,301-313), bit for bit
+    img = golden[f"image{i}"]
+    feat = bb.BriskFeature(0, 30.0, 20.0, ctx=ctx)
+    k, d = feat.detectAndCompute(img)
+    gk, gd = golden[f"harris{i}_kps"], golden[f"harris{i}_desc"]
+    assert len(k) == len(gk)
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(k[f], gk[f]), f
+    assert np.abs(k["angle"] - gk["angle"]).max() <= 1e-4
+    assert np.array_equal(d, gd)
+
+
+@pytest.mark.parametrize("octaves,radius,abs_thr,max_kpt", [(0, 30.0, 20.0, None), (4, 30.0, 20.0, None), (2, 10.0, 0.0, 300),
+                                                             (1, 45.0, 50.0, None), (3, 15.0, 5.0, None)])
+def test_harris_detect_bit_exact(ctx, oracle, golden, octaves, radius, abs_thr, max_kpt):
+    # multi-layer Harris incl. 3-D NMS and the introsort tie order (not covered by the golden fixture)
+    det = bb.ScaleSpaceFeatureDetector(octaves, radius, abs_thr, max_kpt, ctx=ctx)
+    det.set_corner_capacity(800 * 640)  # with abs_thr = 0 every plateau pixel is a 2-D maximum
+    for img in (golden["image1"], bb.synthetic_frame(752, 480, 1000), bb.synthetic_frame(500, 333, 3)):
+        want = oracle.harris_detect(img, octaves, radius, abs_thr, -1 if max_kpt is None else max_kpt)
+        assert kp_equal(det.detect(img), want)
+
+
+def test_harris_batch_config2(ctx, oracle):
+    # BASELINE config 2 shape: 752x480 frames, Harris (4 octaves, r = 30, abs = 20) + BRISK2
+    frames = bb.synthetic_batch(4, 752, 480, 1000)
+    det = bb.ScaleSpaceFeatureDetector(4, 30.0, 20.0, ctx=ctx)
+    ext = bb.BriskDescriptorExtractor(ctx=ctx)
+    kps, counts, desc = bb.detect_and_compute_batch(det, ext, frames, cap=8192)
+    for f in range(len(frames)):
+        k2, d2 = oracle.describe(frames[f], oracle.harris_detect(frames[f], 4, 30.0, 20.0))
+        n = counts[f]
+        assert n == len(k2)
+        for fld in ("x", "y", "size", "response", "octave"):
+            assert np.array_equal(kps[f, :n][fld], k2[fld])
+        assert np.array_equal(desc[f, :n], d2)
+
+
+def test_harris_unsupported(ctx):
+    with pytest.raises(bb.BriskError):
+        bb.ScaleSpaceFeatureDetector(4, 0.0, 20.0, ctx=ctx).detect(bb.synthetic_frame(320, 240, 1))

@@ -55,6 +55,34 @@ def test_parallel_nms_formulation_tie_heavy(emul, oracle):
         assert kp_equal(emul(img, 30 + 5 * k, 3), oracle.agast_detect(img, 30 + 5 * k, 3))
 
 
+@pytest.fixture(scope="module")
+def emul_harris():
+    src = ROOT / "tests" / "host_emul" / "emul_harris.cc"
+    lib = ROOT / "tests" / "host_emul" / "libemul_harris.so"
+    deps = [src] + list((ROOT / "ethzasl_brisk_b200" / "csrc").glob("*.cuh"))
+    if not lib.exists() or any(d.stat().st_mtime > lib.stat().st_mtime for d in deps):
+        subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-msse2", "-ffp-contract=off", "-fPIC", "-shared",
+                        "-Wno-unknown-pragmas", "-o", str(lib), str(src)], check=True)
+    handle = C.CDLL(str(lib))
+
+    def detect(img, octaves, radius, abs_thr, max_kpt=-1, cap=1 << 18):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        k = np.zeros(cap, KP_DTYPE)
+        n = handle.emul_harris_detect(img.ctypes.data_as(C.c_void_p), w, h, octaves, C.c_double(radius), C.c_double(abs_thr),
+                                      C.c_longlong(max_kpt), k.ctypes.data_as(C.c_void_p), cap)
+        return k[:n].copy()
+    return detect
+
+
+@pytest.mark.parametrize("octaves,radius,abs_thr,max_kpt", [(0, 30.0, 20.0, -1), (4, 30.0, 20.0, -1), (2, 10.0, 0.0, 300)])
+def test_harris_logic_and_introsort_replay(emul_harris, oracle, golden, octaves, radius, abs_thr, max_kpt):
+    # the device code's Harris arithmetic and its restatement of libstdc++'s std::sort, on tie-heavy
+    # score lists, against the oracle (which calls the real std::sort)
+    for img in (golden["image0"], synthetic_frame(500, 333, 3)):
+        assert kp_equal(emul_harris(img, octaves, radius, abs_thr, max_kpt), oracle.harris_detect(img, octaves, radius, abs_thr, max_kpt))
+
+
 def test_capi_exports_every_declared_symbol():
     from ethzasl_brisk_b200 import build, lib_path
     build_lib = build.build()  # no-op when up to date; nvcc cross-compiles without a GPU
