@@ -88,6 +88,9 @@ class Context:
     def enable_timing(self, on=True):
         self._check(self._lib.brisk_ctx_enable_timing(self._h, int(bool(on))))
 
+    def set_pipelining(self, on=True):
+        self._check(self._lib.brisk_ctx_set_pipelining(self._h, int(bool(on))))
+
     def last_timing(self):
         """-> (dict stage -> device ms of the last call, kernel launches of the last call)"""
         ms = (C.c_float * len(STAGES))()

@@ -61,6 +61,7 @@ struct brisk_ctx {
   std::string err;
   size_t ws_limit = (size_t)8 << 30;
   bool timing = false;
+  bool pipelining = true;
   float ms[BRISK_STAGE_COUNT] = {};
   int64_t launches = 0;
   cudaEvent_t ev[2] = {};
@@ -196,12 +197,13 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
   long long max_chunk = (long long)(ctx->ws_limit / 2 / std::max<size_t>(per_frame, 1));
   if (max_chunk < 1) max_chunk = 1;
   if (max_chunk > 32768) max_chunk = 32768;
+  if (!ctx->pipelining) max_chunk = std::min<long long>(max_chunk * 2, 32768);  // one slot gets the whole budget
   long long n_chunks = (n + max_chunk - 1) / max_chunk;
-  if (n_chunks < 2 && n > 1) n_chunks = 2;
+  if (n_chunks < 2 && n > 1 && ctx->pipelining) n_chunks = 2;
   if (n_chunks < 1) n_chunks = 1;
   const long long chunk = std::max<long long>(1, (n + n_chunks - 1) / n_chunks);  // equal-sized chunks, no tiny tail
   plan->chunk = (int)chunk;
-  plan->n_slots = n > plan->chunk ? 2 : 1;
+  plan->n_slots = (n > plan->chunk && ctx->pipelining) ? 2 : 1;
   const size_t c = (size_t)plan->chunk;
   for (int si = 0; si < plan->n_slots; ++si) {
     Slot& sl = ctx->slots[si];
@@ -543,6 +545,12 @@ int brisk_sync(brisk_ctx* ctx) {
 int brisk_ctx_set_workspace_limit(brisk_ctx* ctx, size_t bytes) {
   if (!ctx || bytes < ((size_t)64 << 20)) return BRISK_ERR_INVALID;
   ctx->ws_limit = bytes;
+  return BRISK_OK;
+}
+
+int brisk_ctx_set_pipelining(brisk_ctx* ctx, int enable) {
+  if (!ctx) return BRISK_ERR_INVALID;
+  ctx->pipelining = enable != 0;
   return BRISK_OK;
 }
 

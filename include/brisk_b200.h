@@ -53,6 +53,10 @@ int brisk_sync(brisk_ctx* ctx);
 /* Upper bound on device workspace bytes used per call (frames are processed in
  * chunks that fit); default 8 GiB. */
 int brisk_ctx_set_workspace_limit(brisk_ctx* ctx, size_t bytes);
+/* Chunks of a batch normally alternate between two streams so that copies and serial kernel tails
+ * of one chunk overlap the kernels of the other (default on).  Off: one stream, stages back to back
+ * -- used to time individual stages without overlap. */
+int brisk_ctx_set_pipelining(brisk_ctx* ctx, int enable);
 /* Device time in milliseconds of the kernels of the last detect / describe /
  * detect_describe / knn call, per stage (see BRISK_STAGE_*), measured with CUDA
  * events on the context stream.  Requires brisk_ctx_enable_timing(ctx, 1). */
