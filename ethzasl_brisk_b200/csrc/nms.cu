@@ -75,15 +75,60 @@ nms_checks_kernel(PyramidGeom g, DetectWorkspace ws) {
   *reinterpret_cast<CheckResult*>(ws.checks + ((long long)frame * ws.corner_cap + k) * 8) = r;
 }
 
+// Warp-cooperative IsMax2D tie path for one tying corner: the 64 corner-map entries of the 8x8
+// window are staged by the lanes (two each), lanes 0..24 each reconstruct the value of one pixel of
+// the 5x5 neighbourhood, and the 3x3 binomial sums around the centre and around every tying
+// neighbour are formed with shuffles.  Returns 1 accept, 0 reject, -1 blocked (an earlier tying
+// corner in the window is undecided); uniform across the warp.
+__device__ __forceinline__ int warp_tie_decide(const LayerView& L, int mode, int x, int y, const uint8_t* __restrict__ fwin,
+                                               uint16_t* s_win /* 64 entries, this warp's */) {
+  const int lane = threadIdx.x & 31;
+  bool blocked = false;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = lane + 32 * h;
+    const int px = x - 4 + (i & 7), py = y - 4 + (i >> 3);
+    uint16_t e = 0;
+    if (py >= 3 && px >= 3 && px < L.w - 3 && py < L.h - 3) e = L.cm[(long long)py * L.pitch + px];
+    s_win[i] = e;
+    if ((e & kCmT) && !(e & kCmDecided) && (py < y || (py == y && px < x))) blocked = true;
+  }
+  if (__any_sync(0xffffffffu, blocked)) return -1;
+  __syncwarp();
+  const TieWindow W{s_win, 1, x - 4, y - 4};
+  const int center = W.at(x, y) & kCmT;
+  const int ox = lane % 5 - 2, oy = lane / 5 - 2;  // lanes 0..24 <-> 5x5 offsets, row-major
+  int v = 0;
+  if (lane < 25) v = tie_pixel_value(L, W, mode, x, y, ox, oy, fwin[lane], center);
+  // binomial 3x3 sum centred on every lane's own pixel (meaningful for the inner 3x3 lanes)
+  int sum = 0;
+#pragma unroll
+  for (int wy = -1; wy <= 1; ++wy)
+#pragma unroll
+    for (int wx = -1; wx <= 1; ++wx) {
+      const int src = lane + wy * 5 + wx;
+      const int t = __shfl_sync(0xffffffffu, v, src & 31);
+      sum += ((wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1)) * t;
+    }
+  const int smoothed = __shfl_sync(0xffffffffu, sum, 12);
+  const bool inner = lane < 25 && ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1 && lane != 12;
+  const bool beaten = inner && v == center && sum > smoothed;
+  const int verdict = __any_sync(0xffffffffu, beaten) ? 0 : 1;
+  __syncwarp();
+  return verdict;
+}
+
 // One CTA per frame, layers in order (layer i+1 needs the touch marks that layer i's accepted
-// corners leave on it).  Within a layer the tying corners are resolved in parallel rounds: a corner
-// whose raster-earlier tying neighbours are all decided is decidable, whatever the order.
-__global__ void __launch_bounds__(256)
+// corners leave on it).  Within a layer the tying corners are resolved in parallel rounds, one warp
+// per corner: a corner whose raster-earlier tying neighbours are all decided is decidable, whatever
+// the order.
+constexpr int kChainThreads = 256;
+__global__ void __launch_bounds__(kChainThreads)
 nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag) {
   __shared__ FrameViews fv;
   __shared__ int s_left;
-  __shared__ uint16_t s_win[64 * 256];  // per-thread 8x8 corner-map windows, entry i of thread t at [i * 256 + t]
-  const int frame = blockIdx.x, tid = threadIdx.x;
+  __shared__ uint16_t s_win[kChainThreads / 32][64];
+  const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) make_views(g, ws, frame, &fv);
   __syncthreads();
   const int* ls = ws.layer_start + (long long)frame * (kMaxLayers + 1);
@@ -109,18 +154,21 @@ nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag
       if (tid == 0) s_left = 0;
       __syncthreads();
       int left = 0;
-      for (int i = tid; i < n_ties; i += blockDim.x) {
+      for (int i = warp; i < n_ties; i += kChainThreads / 32) {
         const int k = tie_list[i];
-        if (k < 0) continue;
+        if (k < 0) continue;  // uniform across the warp
         int x, y, l2;
         unpack_corner(corners[k], &x, &y, &l2);
-        uint16_t* e = L.cm + (long long)y * L.pitch + x;
-        const int verdict = nms_tie_decide(L, mode, x, y, ws.fwin + ((long long)frame * ws.corner_cap + k) * 32, s_win + tid, 256);
+        const int verdict = warp_tie_decide(L, mode, x, y, ws.fwin + ((long long)frame * ws.corner_cap + k) * 32, s_win[warp]);
         if (verdict < 0) { ++left; continue; }
-        *e = *e | (uint16_t)(kCmDecided | (verdict ? kCmAccept : 0));
-        tie_list[i] = -1;
+        if (lane == 0) {
+          uint16_t* e = L.cm + (long long)y * L.pitch + x;
+          *e = *e | (uint16_t)(kCmDecided | (verdict ? kCmAccept : 0));
+          tie_list[i] = -1;
+        }
+        __syncwarp();
       }
-      if (left) atomicAdd(&s_left, left);
+      if (lane == 0 && left) atomicAdd(&s_left, left);
       __syncthreads();
       const int remaining = s_left;
       __syncthreads();

@@ -536,6 +536,20 @@ BRISK_HD int cache_state(const LayerView& L, const TieWindow& W, int mode, int q
   return (last != 0 && last <= F) ? F : 0;
 }
 
+// Value IsMax2D's tie path sees at offset (ox, oy) in [-2,2]^2 from the tying corner (x, y) once the
+// corner's own eight neighbour look-ups are done: its own score at the centre, the look-up results
+// s(q) on the 8 neighbours, raw cache bytes on the outer ring.  F = fwin entry of that pixel.
+BRISK_HD int tie_pixel_value(const LayerView& L, const TieWindow& W, int mode, int x, int y, int ox, int oy, int F, int center) {
+  if (ox == 0 && oy == 0) return center;
+  const int qx = x + ox, qy = y + oy;
+  if (ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1) {
+    if (W.at(qx, qy) & kCmT) return F;  // neighbouring corner: its T (stored in fwin by nms_prefix)
+    const int st = cache_state(L, W, mode, qx, qy, F, x, y);
+    return st > 2 ? st : (F >= center ? F : 0);
+  }
+  return cache_state(L, W, mode, qx, qy, F, x, y);
+}
+
 // IsMax2D verdict of the tying corner (x,y): 1 accept, 0 reject, -1 not yet
 // decidable (an earlier tying corner in its neighbourhood is still undecided).
 // Corners whose dependencies are all decided can be resolved in any order, or
@@ -549,11 +563,7 @@ BRISK_HD int nms_tie_decide(const LayerView& L, int mode, int x, int y, const ui
   for (int j = 0; j < 8; ++j) {
     int dx, dy;
     isMax2dOffset(j, &dx, &dy);
-    const int qx = x + dx, qy = y + dy;
-    const int F = fwin[(dy + 2) * 5 + dx + 2];  // T(q) when q is a corner
-    if (W.at(qx, qy) & kCmT) { s[j] = F; continue; }
-    const int st = cache_state(L, W, mode, qx, qy, F, x, y);
-    s[j] = st > 2 ? st : (F >= center ? F : 0);
+    s[j] = tie_pixel_value(L, W, mode, x, y, dx, dy, fwin[(dy + 2) * 5 + dx + 2], center);
   }
   const int smoothed = 4 * center + 2 * (s[0] + s[1] + s[2] + s[3]) + s[7] + s[6] + s[4] + s[5];
   // ties in the reference's order: (-1,-1) (0,-1) (1,-1) (-1,0) (1,0) (-1,1) (0,1) (1,1)
@@ -568,7 +578,7 @@ BRISK_HD int nms_tie_decide(const LayerView& L, int mode, int x, int y, const ui
         int v;
         if (ox == 0 && oy == 0) v = center;
         else if (ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1) v = s[isMax2dIndex(ox, oy)];
-        else v = cache_state(L, W, mode, x + ox, y + oy, fwin[(oy + 2) * 5 + ox + 2], x, y);
+        else v = tie_pixel_value(L, W, mode, x, y, ox, oy, fwin[(oy + 2) * 5 + ox + 2], center);
         const int wgt = (wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1);
         other += wgt * v;
       }
