@@ -83,7 +83,7 @@ struct brisk_detector {
 struct brisk_extractor {
   brisk_ctx* ctx;
   PatternHost host;
-  DevBuf points, size_list, short_pairs, long_pairs, breaks;
+  DevBuf points, size_list, short_pairs, long_pairs, breaks, consts;
   PatternDev dev;
 };
 
@@ -604,7 +604,7 @@ int brisk_extractor_create(brisk_ctx* ctx, int rot, int scale, int version, floa
   struct Up { DevBuf* b; const void* src; size_t bytes; };
   const Up ups[] = {{&ext->points, ph.points.data(), ph.points.size() * 4}, {&ext->size_list, ph.size_list, sizeof(ph.size_list)},
                     {&ext->short_pairs, ph.short_pairs.data(), ph.short_pairs.size() * 2}, {&ext->long_pairs, ph.long_pairs.data(), ph.long_pairs.size() * 4},
-                    {&ext->breaks, ph.scale_breaks, sizeof(ph.scale_breaks)}};
+                    {&ext->breaks, ph.scale_breaks, sizeof(ph.scale_breaks)}, {&ext->consts, ph.sample_consts.data(), ph.sample_consts.size() * 4}};
   for (const Up& u : ups) {
     cudaError_t e = u.b->ensure(std::max<size_t>(u.bytes, 16));
     if (e == cudaSuccess && u.bytes) e = cudaMemcpy(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice);
@@ -614,6 +614,7 @@ int brisk_extractor_create(brisk_ctx* ctx, int rot, int scale, int version, floa
   d.points = ext->points.as<float>(); d.size_list = ext->size_list.as<unsigned int>();
   d.short_pairs = ext->short_pairs.as<unsigned short>(); d.long_pairs = ext->long_pairs.as<int>();
   d.scale_breaks = ext->breaks.as<float>();
+  d.sample_consts = ext->consts.as<int2>();
   d.n_points = ph.n_points; d.n_short = (int)ph.short_pairs.size() / 2; d.n_long = (int)ph.long_pairs.size() / 4;
   d.desc_bytes = ph.desc_bytes; d.rot_inv = rot != 0; d.scale_inv = scale != 0; d.basic_scale = ph.basic_scale;
   *out = ext;
@@ -623,7 +624,7 @@ int brisk_extractor_create(brisk_ctx* ctx, int rot, int scale, int version, floa
 void brisk_extractor_destroy(brisk_extractor* ext) {
   if (!ext) return;
   cudaSetDevice(ext->ctx->device);
-  ext->points.release(); ext->size_list.release(); ext->short_pairs.release(); ext->long_pairs.release(); ext->breaks.release();
+  ext->points.release(); ext->size_list.release(); ext->short_pairs.release(); ext->long_pairs.release(); ext->breaks.release(); ext->consts.release();
   delete ext;
 }
 

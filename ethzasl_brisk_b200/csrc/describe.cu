@@ -158,8 +158,10 @@ describe_kernel(PatternDev pat, const uint8_t* __restrict__ imgs, long long fram
     if (kp.angle == -1.0f) {
       // un-rotated samples, long-pair gradient (:697-739)
       const float* pp = pat.points + ((long long)scale * 1024) * P * 3;
-      for (int i = lane; i < P; i += 32)
-        val[i] = smoothed_intensity(img, pitch, integ, iw, kp.x, kp.y, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2]);
+      for (int i = lane; i < P; i += 32) {
+        const int2 sc = pat.sample_consts[scale * P + i];
+        val[i] = smoothed_intensity(img, pitch, integ, iw, kp.x, kp.y, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2], sc.x, sc.y);
+      }
       __syncwarp();
       int d0 = 0, d1 = 0;
       for (int p = lane; p < pat.n_long; p += 32) {
@@ -179,8 +181,10 @@ describe_kernel(PatternDev pat, const uint8_t* __restrict__ imgs, long long fram
   }
   // samples in the rotated pattern (:755-772)
   const float* pp = pat.points + ((long long)scale * 1024 + theta) * P * 3;
-  for (int i = lane; i < P; i += 32)
-    val[i] = smoothed_intensity(img, pitch, integ, iw, kp.x, kp.y, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2]);
+  for (int i = lane; i < P; i += 32) {
+    const int2 sc = pat.sample_consts[scale * P + i];
+    val[i] = smoothed_intensity(img, pitch, integ, iw, kp.x, kp.y, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2], sc.x, sc.y);
+  }
   __syncwarp();
   // short-pair comparisons -> bits (:538-564); rows are zero-padded to desc_bytes
   uint32_t* out = reinterpret_cast<uint32_t*>(desc + slot * pat.desc_bytes);

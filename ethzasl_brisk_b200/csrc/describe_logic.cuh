@@ -14,10 +14,18 @@ namespace briskb200 {
 // filtered intensity (x ~1024) of the pattern point (px, py, sigma) placed at
 // key point (kx, ky).  `integral` is the (h+1)x(w+1) int32 integral image with
 // row stride iw = w + 1; the image has row pitch `pitch`.
-BRISK_HD int smoothed_intensity(const uint8_t* __restrict__ img, int pitch, const int32_t* __restrict__ integral, int iw,
-                                float kx, float ky, float px, float py, float sigma_half) {
-  const float xf = px + kx, yf = py + ky;
+// The two integer normalisation constants of a pattern point depend on its sigma only (:387,
+// :412-413); they are tabulated per (scale, point) on the host with this function so that the kernel
+// does no double-precision division.
+BRISK_HD void sampling_constants(float sigma_half, int* scaling, int* scaling2) {
   const float area = (float)(4.0 * (double)sigma_half * (double)sigma_half);
+  *scaling = (int)(4194304.0 / (double)area);
+  *scaling2 = (int)((double)((float)*scaling * area) / 1024.0);
+}
+
+BRISK_HD int smoothed_intensity(const uint8_t* __restrict__ img, int pitch, const int32_t* __restrict__ integral, int iw,
+                                float kx, float ky, float px, float py, float sigma_half, int scaling, int scaling2) {
+  const float xf = px + kx, yf = py + ky;
   if ((double)sigma_half < 0.5) {
     const int x = (int)xf, y = (int)yf;
     const int r_x = (int)((xf - (float)x) * 1024.0f), r_y = (int)((yf - (float)y) * 1024.0f);
@@ -29,8 +37,6 @@ BRISK_HD int smoothed_intensity(const uint8_t* __restrict__ img, int pitch, cons
     v += r_x_1 * r_y * (int)p[pitch];
     return v / 1024;
   }
-  const int scaling = (int)(4194304.0 / (double)area);
-  const int scaling2 = (int)((double)((float)scaling * area) / 1024.0);
   const float x_1 = xf - sigma_half, x1 = xf + sigma_half, y_1 = yf - sigma_half, y1 = yf + sigma_half;
   const int x_left = (int)((double)x_1 + 0.5), y_top = (int)((double)y_1 + 0.5);
   const int x_right = (int)((double)x1 + 0.5), y_bottom = (int)((double)y1 + 0.5);

@@ -17,18 +17,27 @@
 
 namespace briskb200 {
 
-constexpr int kDetTW = 128, kDetTH = 32, kDetThreads = 256;
-constexpr int kDetSW = kDetTW + 8;   // staged row: [x0-4, x0+TW+4), 4-byte aligned
-constexpr int kDetSH = kDetTH + 6;   // staged rows: [y0-3, y0+TH+3)
-constexpr int kDetMW = kDetTW + 4;   // min/max planes: [x0-2, x0+TW+2)
-constexpr int kDetMH = kDetTH + 4;   //                 [y0-2, y0+TH+2)
+constexpr int kDetTW = 128, kDetTH = 64, kDetThreads = 256;
+constexpr int kDetStrip = 32;                 // rows per thread: 2 strips of 32 rows, 128 columns each
+constexpr int kDetSW = kDetTW + 8;            // staged row: [x0-4, x0+TW+4), 4-byte aligned
+constexpr int kDetSH = kDetTH + 6;            // staged rows: [y0-3, y0+TH+3)
 
-__global__ void __launch_bounds__(kDetThreads)
+// The reference's threshold map (brisk-layer.cc:278-598) is max - min over the centre, four diagonals
+// and four 3x3 blocks; that footprint is exactly the 37-pixel disk with row half-widths
+// 1,2,3,3,3,2,1 (it contains the 16-pixel FAST ring, which is why a corner's score equals its
+// threshold-map value).  Phase 1: each thread walks down one column; per row it forms the horizontal
+// max / min over widths 3, 5 and 7 from seven shared-memory bytes and folds them into seven rolling
+// per-output-row accumulators held in registers (no min/max planes are materialised), then runs the
+// cheap 4-point compass pre-test and queues the survivors.  Phase 2: the queue is processed densely,
+// one candidate per thread, with the full 9-of-16 run test -- so the expensive test only costs the
+// lanes that need it.
+__global__ void __launch_bounds__(kDetThreads, 3)
 agast_detect_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restrict__ pyr, uint16_t* __restrict__ cm,
                     int* __restrict__ rowcnt, int total_rows, int row_off, int thresh) {
   __shared__ __align__(16) uint8_t s_img[kDetSH][kDetSW];
-  __shared__ uint8_t s_hmx[kDetSH][kDetMW], s_hmn[kDetSH][kDetMW];
-  __shared__ uint8_t s_mx[kDetMH][kDetMW], s_mn[kDetMH][kDetMW];
+  __shared__ uint32_t s_queue[kDetTW * kDetTH];  // cx | ry << 8 | T << 16
+  __shared__ int s_count;
+  __shared__ int s_rows[kDetTH];
 
   const int x0 = blockIdx.x * kDetTW, y0 = blockIdx.y * kDetTH, frame = blockIdx.z;
   const uint8_t* img = pyr + (long long)frame * frame_elems + L.off;
@@ -43,43 +52,43 @@ agast_detect_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restric
     if (y >= 0 && y < L.h && x >= 0 && x < L.pitch) v = *reinterpret_cast<const uint32_t*>(img + (long long)y * L.pitch + x);
     *reinterpret_cast<uint32_t*>(&s_img[r][4 * c]) = v;
   }
-  __syncthreads();
-  // horizontal 3-tap min / max: plane column m <-> x = x0-2+m <-> staged column m+2
-  for (int i = tid; i < kDetSH * kDetMW; i += kDetThreads) {
-    const int r = i / kDetMW, m = i - r * kDetMW;
-    const int a = s_img[r][m + 1], b = s_img[r][m + 2], c = s_img[r][m + 3];
-    s_hmx[r][m] = (uint8_t)imax(imax(a, b), c);
-    s_hmn[r][m] = (uint8_t)imin(imin(a, b), c);
-  }
-  __syncthreads();
-  // vertical 3-tap: plane row n <-> y = y0-2+n <-> staged row n+1
-  for (int i = tid; i < kDetMH * kDetMW; i += kDetThreads) {
-    const int n = i / kDetMW, m = i - n * kDetMW;
-    s_mx[n][m] = (uint8_t)imax(imax(s_hmx[n][m], s_hmx[n + 1][m]), s_hmx[n + 2][m]);
-    s_mn[n][m] = (uint8_t)imin(imin(s_hmn[n][m], s_hmn[n + 1][m]), s_hmn[n + 2][m]);
-  }
+  if (tid == 0) s_count = 0;
+  if (tid < kDetTH) s_rows[tid] = 0;
   __syncthreads();
 
   const int cmp = (thresh * kLowerThreshold) / 100;  // ast-detector.h:62-68
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int ry = warp; ry < kDetTH; ry += kDetThreads / 32) {
-    const int y = y0 + ry;
-    if (y >= L.h) break;
-    int row_corners = 0;
-    for (int rx = lane; rx < kDetTW; rx += 32) {
-      const int x = x0 + rx;
-      int T = 0;
-      bool corner = false;
-      if (x >= 3 && x < L.w - 3 && y >= 3 && y < L.h - 3) {
-        // threshold map (brisk-layer.cc:380-598): staged (ry+3, rx+4), planes (ry+2, rx+2)
-        const int sr = ry + 3, sc = rx + 4, pn = ry + 2, pm = rx + 2;
-        int hi = s_img[sr][sc], lo = hi;
-        hi = imax(hi, imax(imax(s_img[sr - 2][sc - 2], s_img[sr - 2][sc + 2]), imax(s_img[sr + 2][sc - 2], s_img[sr + 2][sc + 2])));
-        lo = imin(lo, imin(imin(s_img[sr - 2][sc - 2], s_img[sr - 2][sc + 2]), imin(s_img[sr + 2][sc - 2], s_img[sr + 2][sc + 2])));
-        hi = imax(hi, imax(imax(s_mx[pn - 2][pm], s_mx[pn + 2][pm]), imax(s_mx[pn][pm - 2], s_mx[pn][pm + 2])));
-        lo = imin(lo, imin(imin(s_mn[pn - 2][pm], s_mn[pn + 2][pm]), imin(s_mn[pn][pm - 2], s_mn[pn][pm + 2])));
-        T = hi - lo;
-        if (T >= cmp) {
+  {
+    const int cx = tid & (kDetTW - 1), strip = tid >> 7;
+    const int x = x0 + cx;
+    const int ys = y0 + strip * kDetStrip;  // first output row of this thread
+    const int sc = cx + 4;                  // staged column of x
+    int hi[7], lo[7];                       // rolling accumulators, slot = (output row - (ys - 6)) % 7
+#pragma unroll
+    for (int k = 0; k < 7; ++k) { hi[k] = 0; lo[k] = 255; }
+    if (ys < L.h) {
+#pragma unroll 7
+      for (int i = 0; i < 42; ++i) {  // 42 = 6 groups of 7 >= kDetStrip + 6; slots are static after unrolling by 7
+        if (i >= kDetStrip + 6) break;
+        // source row r = ys - 3 + i  <->  staged row (ys - y0) + i
+        const uint8_t* row = &s_img[strip * kDetStrip + i][sc - 3];
+        const int a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3], a4 = row[4], a5 = row[5], a6 = row[6];
+        const int M3 = imax(imax(a2, a3), a4), M5 = imax(imax(M3, a1), a5), M7 = imax(imax(M5, a0), a6);
+        const int m3 = imin(imin(a2, a3), a4), m5 = imin(imin(m3, a1), a5), m7 = imin(imin(m5, a0), a6);
+        hi[(i + 6) % 7] = M3;                       lo[(i + 6) % 7] = m3;   // output row r+3 starts here
+        hi[(i + 5) % 7] = imax(hi[(i + 5) % 7], M5); lo[(i + 5) % 7] = imin(lo[(i + 5) % 7], m5);
+        hi[(i + 4) % 7] = imax(hi[(i + 4) % 7], M7); lo[(i + 4) % 7] = imin(lo[(i + 4) % 7], m7);
+        hi[(i + 3) % 7] = imax(hi[(i + 3) % 7], M7); lo[(i + 3) % 7] = imin(lo[(i + 3) % 7], m7);
+        hi[(i + 2) % 7] = imax(hi[(i + 2) % 7], M7); lo[(i + 2) % 7] = imin(lo[(i + 2) % 7], m7);
+        hi[(i + 1) % 7] = imax(hi[(i + 1) % 7], M5); lo[(i + 1) % 7] = imin(lo[(i + 1) % 7], m5);
+        hi[i % 7] = imax(hi[i % 7], M3);             lo[i % 7] = imin(lo[i % 7], m3);   // output row r-3 complete
+        if (i < 6) continue;
+        const int ry = strip * kDetStrip + i - 6;  // row inside the tile
+        const int y = y0 + ry;
+        if (y >= L.h) break;
+        const int T = hi[i % 7] - lo[i % 7];
+        if (x < L.w) cmap[(long long)y * L.pitch + x] = 0;  // corners are written in phase 2
+        if (T >= cmp && x >= 3 && x < L.w - 3 && y >= 3 && y < L.h - 3) {
+          const int sr = ry + 3;  // staged row of y
           const int t = T < kLowerThreshold ? kLowerThreshold : (T > kUpperThreshold ? kUpperThreshold : T);
           const int b2 = (t * thresh) / 100;
           const int c = s_img[sr][sc], cb = c + b2, c_b = c - b2;
@@ -87,29 +96,41 @@ agast_detect_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restric
           const int p0 = s_img[sr][sc - 3], p4 = s_img[sr - 3][sc], p8 = s_img[sr][sc + 3], p12 = s_img[sr + 3][sc];
           const int nb = (p0 > cb) + (p4 > cb) + (p8 > cb) + (p12 > cb);
           const int nd = (p0 < c_b) + (p4 < c_b) + (p8 < c_b) + (p12 < c_b);
-          if (nb >= 2 || nd >= 2) {
-            // ring of agast/include/agast/oast9-16.h:99-116
-            int r[16];
-            r[0] = p0;                      r[1] = s_img[sr - 1][sc - 3]; r[2] = s_img[sr - 2][sc - 2]; r[3] = s_img[sr - 3][sc - 1];
-            r[4] = p4;                      r[5] = s_img[sr - 3][sc + 1]; r[6] = s_img[sr - 2][sc + 2]; r[7] = s_img[sr - 1][sc + 3];
-            r[8] = p8;                      r[9] = s_img[sr + 1][sc + 3]; r[10] = s_img[sr + 2][sc + 2]; r[11] = s_img[sr + 3][sc + 1];
-            r[12] = p12;                    r[13] = s_img[sr + 3][sc - 1]; r[14] = s_img[sr + 2][sc - 2]; r[15] = s_img[sr + 1][sc - 3];
-            uint32_t mb = 0, md = 0;
-#pragma unroll
-            for (int k = 0; k < 16; ++k) { mb |= (uint32_t)(r[k] > cb) << k; md |= (uint32_t)(r[k] < c_b) << k; }
-            // 9 contiguous set bits on the circular 16-bit mask
-            mb |= mb << 16; md |= md << 16;
-            uint32_t xb = mb & (mb >> 1); xb &= xb >> 2; xb &= xb >> 4; xb &= mb >> 8;
-            uint32_t xd = md & (md >> 1); xd &= xd >> 2; xd &= xd >> 4; xd &= md >> 8;
-            corner = ((xb | xd) & 0xffffu) != 0;
-          }
+          if (nb >= 2 || nd >= 2) s_queue[atomicAdd(&s_count, 1)] = (uint32_t)cx | ((uint32_t)ry << 8) | ((uint32_t)T << 16);
         }
       }
-      if (x < L.w) cmap[(long long)y * L.pitch + x] = corner ? (uint16_t)T : (uint16_t)0;
-      row_corners += __popc(__ballot_sync(0xffffffffu, corner));
     }
-    if (lane == 0 && row_corners) atomicAdd(&rowcnt[(long long)frame * total_rows + row_off + y], row_corners);
   }
+  __syncthreads();
+  // phase 2: full segment test on the queued candidates
+  const int n_cand = s_count;
+  for (int q = tid; q < n_cand; q += kDetThreads) {
+    const uint32_t e = s_queue[q];
+    const int cx = e & 0xff, ry = (e >> 8) & 0xff, T = e >> 16;
+    const int sr = ry + 3, sc = cx + 4;
+    const int t = T < kLowerThreshold ? kLowerThreshold : (T > kUpperThreshold ? kUpperThreshold : T);
+    const int b2 = (t * thresh) / 100;
+    const int c = s_img[sr][sc], cb = c + b2, c_b = c - b2;
+    // ring of agast/include/agast/oast9-16.h:99-116
+    int r[16];
+    r[0] = s_img[sr][sc - 3];      r[1] = s_img[sr - 1][sc - 3]; r[2] = s_img[sr - 2][sc - 2]; r[3] = s_img[sr - 3][sc - 1];
+    r[4] = s_img[sr - 3][sc];      r[5] = s_img[sr - 3][sc + 1]; r[6] = s_img[sr - 2][sc + 2]; r[7] = s_img[sr - 1][sc + 3];
+    r[8] = s_img[sr][sc + 3];      r[9] = s_img[sr + 1][sc + 3]; r[10] = s_img[sr + 2][sc + 2]; r[11] = s_img[sr + 3][sc + 1];
+    r[12] = s_img[sr + 3][sc];     r[13] = s_img[sr + 3][sc - 1]; r[14] = s_img[sr + 2][sc - 2]; r[15] = s_img[sr + 1][sc - 3];
+    uint32_t mb = 0, md = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { mb |= (uint32_t)(r[k] > cb) << k; md |= (uint32_t)(r[k] < c_b) << k; }
+    // 9 contiguous set bits on the circular 16-bit mask
+    mb |= mb << 16; md |= md << 16;
+    uint32_t xb = mb & (mb >> 1); xb &= xb >> 2; xb &= xb >> 4; xb &= mb >> 8;
+    uint32_t xd = md & (md >> 1); xd &= xd >> 2; xd &= xd >> 4; xd &= md >> 8;
+    if (((xb | xd) & 0xffffu) != 0) {
+      cmap[(long long)(y0 + ry) * L.pitch + x0 + cx] = (uint16_t)T;
+      atomicAdd(&s_rows[ry], 1);
+    }
+  }
+  __syncthreads();
+  if (tid < kDetTH && s_rows[tid] && y0 + tid < L.h) atomicAdd(&rowcnt[(long long)frame * total_rows + row_off + y0 + tid], s_rows[tid]);
 }
 
 cudaError_t launch_agast_detect(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int thresh, cudaStream_t stream) {

@@ -68,6 +68,7 @@ struct PatternDev {
   const unsigned short* short_pairs;  // [n_short][2] (i, j)
   const int* long_pairs;  // [n_long][4] (i, j, wdx, wdy)
   const float* scale_breaks;  // [64] smallest keypoint size mapping to scale index s (s >= 1)
+  const int2* sample_consts;  // [64][P] (scaling, scaling2) of every pattern point
   int n_points, n_short, n_long, desc_bytes;
   int rot_inv, scale_inv, basic_scale;
 };

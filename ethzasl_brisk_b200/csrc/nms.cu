@@ -122,7 +122,7 @@ __device__ __forceinline__ int warp_tie_decide(const LayerView& L, int mode, int
 // corners leave on it).  Within a layer the tying corners are resolved in parallel rounds, one warp
 // per corner: a corner whose raster-earlier tying neighbours are all decided is decidable, whatever
 // the order.
-constexpr int kChainThreads = 256;
+constexpr int kChainThreads = 1024;
 __global__ void __launch_bounds__(kChainThreads)
 nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag) {
   __shared__ FrameViews fv;
@@ -272,7 +272,7 @@ cudaError_t launch_agast_nms(const PyramidGeom& g, const DetectWorkspace& ws, in
   dim3 grid((ws.corner_cap + 127) / 128, n_frames);
   nms_prefix_kernel<<<grid, 128, 0, stream>>>(g, ws);
   nms_checks_kernel<<<grid, 128, 0, stream>>>(g, ws);
-  nms_chain_kernel<<<n_frames, 256, 0, stream>>>(g, ws, error_flag);
+  nms_chain_kernel<<<n_frames, kChainThreads, 0, stream>>>(g, ws, error_flag);
   refine_kernel<<<grid, 128, 0, stream>>>(g, ws);
   compact_kernel<<<n_frames, 256, 0, stream>>>(g, ws, masks, mask_frame_stride, mask_pitch, out, counts, kp_cap);
   return cudaGetLastError();

@@ -15,6 +15,7 @@
 #include <sstream>
 
 #include "brisk_pattern_data.inc"
+#include "describe_logic.cuh"
 
 namespace briskb200 {
 namespace {
@@ -44,6 +45,12 @@ int scale_index(float size) {
 
 void finish(PatternHost* p) {
   const int ns = (int)p->short_pairs.size() / 2;
+  p->sample_consts.resize((size_t)kScales * p->n_points * 2);
+  for (unsigned s = 0; s < kScales; ++s)
+    for (int i = 0; i < p->n_points; ++i) {
+      const float sigma = p->points[(((size_t)s * kRot) * p->n_points + i) * 3 + 2];  // same for every rotation
+      sampling_constants(sigma, &p->sample_consts[((size_t)s * p->n_points + i) * 2], &p->sample_consts[((size_t)s * p->n_points + i) * 2 + 1]);
+    }
   p->desc_bytes = (int)std::ceil((float)ns / 128.0) * 16;
   // smallest float size that reaches each scale index (monotone in size)
   p->scale_breaks[0] = 0.0f;

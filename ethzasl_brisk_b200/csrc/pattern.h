@@ -15,6 +15,7 @@ struct PatternHost {
   unsigned int size_list[64];
   std::vector<unsigned short> short_pairs;  // [n][2] i, j
   std::vector<int> long_pairs;              // [n][4] i, j, weighted_dx, weighted_dy
+  std::vector<int> sample_consts;       // [64][n_points][2] scaling, scaling2 (describe_logic.cuh)
   float scale_breaks[64];               // smallest key-point size mapping to scale index s
   int basic_scale = 0;                  // scale index used when scale invariance is off
   int desc_bytes = 0;

@@ -22,7 +22,8 @@ extern "C" int emul_samples(const uint8_t* img, int w, int h, const KeyPoint* kp
   for (int k = 0; k < n; ++k) {
     const float* pp = ph.points.data() + ((size_t)scales[k] * 1024 + theta) * P * 3;
     for (int i = 0; i < P; ++i)
-      samples[(size_t)k * P + i] = smoothed_intensity(img, w, integ.data(), w + 1, kps[k].x, kps[k].y, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2]);
+      samples[(size_t)k * P + i] = smoothed_intensity(img, w, integ.data(), w + 1, kps[k].x, kps[k].y, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2],
+                                                      ph.sample_consts[((size_t)scales[k] * P + i) * 2], ph.sample_consts[((size_t)scales[k] * P + i) * 2 + 1]);
   }
   return P;
 }
