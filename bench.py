@@ -296,7 +296,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
     ap.add_argument("--cap", type=int, default=12288, help="key-point capacity per frame")
-    ap.add_argument("--workspace-gb", type=int, default=24)
+    ap.add_argument("--workspace-gb", type=int, default=32)
     ap.add_argument("--knn-q", type=int, default=100000)
     ap.add_argument("--knn-t", type=int, default=1000000)
     args = ap.parse_args()

@@ -135,6 +135,30 @@ describe_cull_kernel(PatternDev pat, int w, int h, const KeyPoint* __restrict__ 
 constexpr int kDescWarps = 8;
 constexpr int kMaxPoints = 96;
 
+// All pattern points of one key point, spread over the warp.  The sampler is latency bound (16
+// scattered loads per point), so every lane works on its first two points at once: the two
+// independent gather chains overlap.
+__device__ __forceinline__ void sample_pattern(const PatternDev& pat, const uint8_t* __restrict__ img, int pitch,
+                                               const int32_t* __restrict__ integ, int iw, float kx, float ky,
+                                               const float* __restrict__ pp, int scale, int P, int lane, int* val) {
+  const int i0 = lane, i1 = lane + 32;
+  if (i1 < P) {
+    const int2 c0 = pat.sample_consts[scale * P + i0], c1 = pat.sample_consts[scale * P + i1];
+    const float x0 = pp[3 * i0], y0 = pp[3 * i0 + 1], s0 = pp[3 * i0 + 2];
+    const float x1 = pp[3 * i1], y1 = pp[3 * i1 + 1], s1 = pp[3 * i1 + 2];
+    const int v0 = smoothed_intensity(img, pitch, integ, iw, kx, ky, x0, y0, s0, c0.x, c0.y);
+    const int v1 = smoothed_intensity(img, pitch, integ, iw, kx, ky, x1, y1, s1, c1.x, c1.y);
+    val[i0] = v0; val[i1] = v1;
+  } else if (i0 < P) {
+    const int2 c0 = pat.sample_consts[scale * P + i0];
+    val[i0] = smoothed_intensity(img, pitch, integ, iw, kx, ky, pp[3 * i0], pp[3 * i0 + 1], pp[3 * i0 + 2], c0.x, c0.y);
+  }
+  for (int i = lane + 64; i < P; i += 32) {
+    const int2 sc = pat.sample_consts[scale * P + i];
+    val[i] = smoothed_intensity(img, pitch, integ, iw, kx, ky, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2], sc.x, sc.y);
+  }
+}
+
 __global__ void __launch_bounds__(kDescWarps * 32)
 describe_kernel(PatternDev pat, const uint8_t* __restrict__ imgs, long long frame_stride, int pitch, int w, int h,
                 const int32_t* __restrict__ integral, const KeyPoint* __restrict__ kps_in, const int* __restrict__ scales,
@@ -158,10 +182,7 @@ describe_kernel(PatternDev pat, const uint8_t* __restrict__ imgs, long long fram
     if (kp.angle == -1.0f) {
       // un-rotated samples, long-pair gradient (:697-739)
       const float* pp = pat.points + ((long long)scale * 1024) * P * 3;
-      for (int i = lane; i < P; i += 32) {
-        const int2 sc = pat.sample_consts[scale * P + i];
-        val[i] = smoothed_intensity(img, pitch, integ, iw, kp.x, kp.y, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2], sc.x, sc.y);
-      }
+      sample_pattern(pat, img, pitch, integ, iw, kp.x, kp.y, pp, scale, P, lane, val);
       __syncwarp();
       int d0 = 0, d1 = 0;
       for (int p = lane; p < pat.n_long; p += 32) {
@@ -181,10 +202,7 @@ describe_kernel(PatternDev pat, const uint8_t* __restrict__ imgs, long long fram
   }
   // samples in the rotated pattern (:755-772)
   const float* pp = pat.points + ((long long)scale * 1024 + theta) * P * 3;
-  for (int i = lane; i < P; i += 32) {
-    const int2 sc = pat.sample_consts[scale * P + i];
-    val[i] = smoothed_intensity(img, pitch, integ, iw, kp.x, kp.y, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2], sc.x, sc.y);
-  }
+  sample_pattern(pat, img, pitch, integ, iw, kp.x, kp.y, pp, scale, P, lane, val);
   __syncwarp();
   // short-pair comparisons -> bits (:538-564); rows are zero-padded to desc_bytes
   uint32_t* out = reinterpret_cast<uint32_t*>(desc + slot * pat.desc_bytes);
