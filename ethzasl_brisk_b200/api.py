@@ -88,6 +88,10 @@ class Context:
     def enable_timing(self, on=True):
         self._check(self._lib.brisk_ctx_enable_timing(self._h, int(bool(on))))
 
+    def set_knn_variant(self, variant):
+        """0: POPC kernel; 1: tensor-core kernel (k == 2, 48/64-byte rows)."""
+        self._check(self._lib.brisk_ctx_set_knn_variant(self._h, int(variant)))
+
     def set_pipelining(self, on=True):
         self._check(self._lib.brisk_ctx_set_pipelining(self._h, int(bool(on))))
 

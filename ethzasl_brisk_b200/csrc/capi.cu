@@ -62,6 +62,7 @@ struct brisk_ctx {
   size_t ws_limit = (size_t)8 << 30;
   bool timing = false;
   bool pipelining = true;
+  int knn_variant = 0;  // 0: POPC kernel, 1: tensor-core kernel where applicable (k == 2, 48/64-byte rows)
   float ms[BRISK_STAGE_COUNT] = {};
   int64_t launches = 0;
   cudaEvent_t ev[2] = {};
@@ -548,6 +549,12 @@ int brisk_ctx_set_workspace_limit(brisk_ctx* ctx, size_t bytes) {
   return BRISK_OK;
 }
 
+int brisk_ctx_set_knn_variant(brisk_ctx* ctx, int variant) {
+  if (!ctx || variant < 0 || variant > 1) return BRISK_ERR_INVALID;
+  ctx->knn_variant = variant;
+  return BRISK_OK;
+}
+
 int brisk_ctx_set_pipelining(brisk_ctx* ctx, int enable) {
   if (!ctx) return BRISK_ERR_INVALID;
   ctx->pipelining = enable != 0;
@@ -823,12 +830,17 @@ static int knn_keys_impl(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const
     dt = ctx->knn_t.as<uint8_t>();
   }
   const int kr = knn_round_k(k);
-  const int splits = knn_num_splits(nq, nt);
+  const bool mma = ctx->knn_variant == 1 && k == 2 && (desc_bytes == 48 || desc_bytes == 64);
+  const int splits = mma ? knn_mma_num_splits(nq, nt) : knn_num_splits(nq, nt);
   CU_OK(ctx->knn_keys.ensure(std::max<size_t>((size_t)nq * kr * 8, 16)));
   if (splits > 1) CU_OK(ctx->knn_part.ensure((size_t)splits * nq * kr * 8));
   if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
-  CU_OK(launch_hamming_knn_ex(dq, nq, dt, nt, desc_bytes, k, offset, ctx->knn_keys.as<unsigned long long>(),
-                              ctx->knn_part.as<unsigned long long>(), splits, ctx->stream));
+  if (mma)
+    CU_OK(launch_hamming_knn2_mma(dq, nq, dt, nt, desc_bytes, offset, ctx->knn_keys.as<unsigned long long>(),
+                                  ctx->knn_part.as<unsigned long long>(), splits, ctx->stream));
+  else
+    CU_OK(launch_hamming_knn_ex(dq, nq, dt, nt, desc_bytes, k, offset, ctx->knn_keys.as<unsigned long long>(),
+                                ctx->knn_part.as<unsigned long long>(), splits, ctx->stream));
   if (ctx->timing) cudaEventRecord(ctx->ev[1], ctx->stream);
   ctx->launches = splits > 1 ? 2 : 1;
   *keys_out = ctx->knn_keys.as<unsigned long long>();

@@ -88,6 +88,11 @@ int knn_round_k(int k);
 cudaError_t launch_hamming_knn_ex(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes, int k,
                                   long long train_index_offset, unsigned long long* keys, unsigned long long* part,
                                   int splits, cudaStream_t stream);
+// Tensor-core (u8 IMMA on 0/1-expanded bits) variant, k == 2, 48/64-byte rows (hamming_mma.cu).
+int knn_mma_num_splits(long long nq, long long nt);
+cudaError_t launch_hamming_knn2_mma(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes,
+                                    long long train_index_offset, unsigned long long* keys, unsigned long long* part,
+                                    int splits, cudaStream_t stream);
 cudaError_t launch_knn_unpack(const unsigned long long* keys, long long n, int32_t* idx, int32_t* dist, cudaStream_t stream);
 cudaError_t launch_knn_merge(const unsigned long long* gathered, int n_shards, long long nq, int k, unsigned long long* out,
                              cudaStream_t stream);

@@ -352,3 +352,23 @@ def test_harris_batch_config2(ctx, oracle):
 def test_harris_unsupported(ctx):
     with pytest.raises(bb.BriskError):
         bb.ScaleSpaceFeatureDetector(4, 0.0, 20.0, ctx=ctx).detect(bb.synthetic_frame(320, 240, 1))
+
+
+@pytest.mark.parametrize("nbytes", [48, 64])
+def test_knn_tensor_core_variant_matches_popc(oracle, nbytes):
+    # the u8-IMMA variant must return exactly what the POPC kernel returns (ties, missing rows, ragged tiles)
+    ctx2 = bb.Context(0)
+    m = bb.BruteForceMatcher(ctx=ctx2)
+    for nq, nt in ((700, 5000), (129, 257), (5, 1), (300, 50000), (1000, 127)):
+        q = bb.random_descriptors(nq, nbytes, 5)
+        t = bb.random_descriptors(nt, nbytes, 6)
+        if nt > 200:
+            t[100] = q[3]
+            t[200] = q[3]
+        ctx2.set_knn_variant(0)
+        i0, d0 = m.knn(q, t, 2)
+        ctx2.set_knn_variant(1)
+        i1, d1 = m.knn(q, t, 2)
+        assert np.array_equal(i0, i1) and np.array_equal(d0, d1), (nq, nt)
+    i2, d2 = oracle.knn(q, t, 2)
+    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
