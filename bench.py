@@ -227,9 +227,14 @@ def run_gpu(args):
     q = torch.from_numpy(bb.random_descriptors(args.knn_q, 64, 5)).to(dev)
     t = torch.from_numpy(bb.random_descriptors(args.knn_t, 64, 6 + rank)).to(dev)
     m = bb.BruteForceMatcher(ctx=ctx)
-    m.knn(q, t, 2)
-    knn_ms, _, _ = timed(lambda: m.knn(q, t, 2), 3)
-    gcmp = world * args.knn_q * args.knn_t * 3 / (knn_ms * 1e-3) / 1e9
+    knn_variants = {}
+    for name, variant in (("popc", 0), ("tensor_core", 1)):
+        ctx.set_knn_variant(variant)
+        m.knn(q, t, 2)
+        v_ms, _, _ = timed(lambda: m.knn(q, t, 2), 3)
+        knn_variants[name] = {"Gcmp/s": world * args.knn_q * args.knn_t * 3 / (v_ms * 1e-3) / 1e9, "ms": v_ms / 3}
+    knn_ms = 3 * knn_variants["tensor_core"]["ms"]   # the default path
+    gcmp = knn_variants["tensor_core"]["Gcmp/s"]
 
     if rank != 0:
         if world > 1:
@@ -281,7 +286,10 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roof, "stages": stage_report, "cpu_baseline": cpu, "clocks": clocks,
             "secondary": {"metric": "hamming_knn_k2_512bit", "value": gcmp, "unit": "Gcmp/s", "queries": args.knn_q, "train": args.knn_t,
-                          "ms": knn_ms / 3}}
+                          "ms": knn_ms / 3, "variants": knn_variants,
+                          "int8_TOPS": gcmp * 1024 / 1e3,
+                          "note": "default = s8 x u8 IMMA (mma.sync m16n8k32) on byte-expanded bits, 512 MACs per comparison; "
+                                  "tensor-pipe activity from ncu is in profiles/"}}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -62,7 +62,7 @@ struct brisk_ctx {
   size_t ws_limit = (size_t)8 << 30;
   bool timing = false;
   bool pipelining = true;
-  int knn_variant = 0;  // 0: POPC kernel, 1: tensor-core kernel where applicable (k == 2, 48/64-byte rows)
+  int knn_variant = 1;  // 0: POPC kernel always, 1 (default): tensor-core kernel where it applies (k == 2, 48/64-byte rows)
   float ms[BRISK_STAGE_COUNT] = {};
   int64_t launches = 0;
   cudaEvent_t ev[2] = {};

@@ -3,13 +3,14 @@
 // int8 tensor-core GEMM variant kept only if ncu shows it wins").
 //
 // Blackwell has no binary MMA (`mma.sync ... b1 ... and.popc` is expanded by ptxas into eight
-// IMMA.16832.U8), so the descriptors' bits are expanded to 0/1 bytes while they are staged in shared
-// memory and the kernel runs a u8 x u8 -> s32 GEMM with `mma.sync.m16n8k32`:
-//   dot(q, t) = popcount(q AND t),  hamming(q, t) = popcount(q) + popcount(t) - 2 dot(q, t).
-// A CTA owns 128 queries (expanded once) and streams 128-row train tiles; every warp computes a
-// 64 x 32 block of dot products, converts them to distances and keeps the two smallest
-// (distance << 32 | train index) keys per query.  Keys order exactly like the reference's
-// selection rule (first minimum wins => lowest train index on ties).
+// IMMA.16832.U8), so the descriptors' bits are expanded to bytes while they are staged in shared
+// memory and the kernel runs an s8 x u8 -> s32 GEMM with `mma.sync.m16n8k32`: query bits become
+// +1/-1, train bits 0/1, so that
+//   v(q, t) = sum_k t_k (2 q_k - 1) = 2 popcount(q AND t) - popcount(t),  hamming(q, t) = popcount(q) - v(q, t).
+// A CTA owns 128 queries (expanded once) and streams 128-row train tiles through a double buffer
+// filled by four producer warps; each of the eight consumer warps computes a 64 x 32 block of v,
+// and keeps the two smallest (distance, train index) pairs per query and thread in registers.  Keys
+// order exactly like the reference's selection rule (first minimum wins => lowest train index on ties).
 #include <cuda_runtime.h>
 
 #include "kernels.h"
@@ -23,23 +24,27 @@ constexpr int kMmaThreads = kMmaConsumers + kMmaProducers;
 constexpr int kMmaPad = 16;          // row padding (bytes) -> conflict-free ldmatrix rows and 128-bit stores
 constexpr unsigned long long kMmaKeyNone = ~0ull;
 constexpr unsigned kMmaDistNone = 0x7fff0000u;   // list sentinel; every real distance is <= 8 * DB
-constexpr int kMmaPopInvalid = 0x7ffffbff;       // popcount of a padding train row: its "distance" never beats the sentinel
 constexpr int kBarFull = 1, kBarEmpty = 3;       // named barriers: kBarFull + buf, kBarEmpty + buf
 
 __device__ __forceinline__ void bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kMmaThreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kMmaThreads) : "memory"); }
 
 // 4 descriptor bits -> 4 bytes of 0/1 (byte i = bit i of the low nibble of b).
+// The multiply parks bit i in the top bit of byte i; PRMT's sign-replicate mode turns that into 0x00 / 0xff.
+template <bool SIGNED>
 __device__ __forceinline__ unsigned expand_nibble(unsigned b) {
-  const unsigned spread = ((b & 0xfu) * 0x01010101u) & 0x08040201u;
-  return ((spread + 0x7f7f7f7fu) >> 7) & 0x01010101u;
+  unsigned mask;   // (__byte_perm drops the selector's replicate-sign bits, hence the PTX)
+  asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(mask) : "r"((b & 0xfu) * 0x10204080u));
+  return SIGNED ? (mask & 0x01010101u) | ~mask   // bit set -> 0x01, clear -> 0xff (-1)
+                : mask & 0x01010101u;
 }
 
-// 32 descriptor bits -> 32 bytes of 0/1, stored as two 128-bit words.
+// 32 descriptor bits -> 32 bytes (0/1, or +1/-1 when SIGNED), stored as two 128-bit words.
+template <bool SIGNED>
 __device__ __forceinline__ void store_expanded_word(uint8_t* dst, unsigned v) {
   uint4 lo, hi;
-  lo.x = expand_nibble(v); lo.y = expand_nibble(v >> 4); lo.z = expand_nibble(v >> 8); lo.w = expand_nibble(v >> 12);
-  hi.x = expand_nibble(v >> 16); hi.y = expand_nibble(v >> 20); hi.z = expand_nibble(v >> 24); hi.w = expand_nibble(v >> 28);
+  lo.x = expand_nibble<SIGNED>(v); lo.y = expand_nibble<SIGNED>(v >> 4); lo.z = expand_nibble<SIGNED>(v >> 8); lo.w = expand_nibble<SIGNED>(v >> 12);
+  hi.x = expand_nibble<SIGNED>(v >> 16); hi.y = expand_nibble<SIGNED>(v >> 20); hi.z = expand_nibble<SIGNED>(v >> 24); hi.w = expand_nibble<SIGNED>(v >> 28);
   *reinterpret_cast<uint4*>(dst) = lo;
   *reinterpret_cast<uint4*>(dst + 16) = hi;
 }
@@ -55,8 +60,8 @@ __device__ __forceinline__ RowRegs<DB> load_row(const uint8_t* __restrict__ src,
   return r;
 }
 
-// Expand one descriptor row into dst (DB * 8 bytes of 0/1); returns its popcount.
-template <int DB>
+// Expand one descriptor row into dst (DB * 8 bytes); returns its popcount.
+template <int DB, bool SIGNED>
 __device__ __forceinline__ int store_row(uint8_t* dst, const RowRegs<DB>& r) {
   int pc = 0;
 #pragma unroll
@@ -64,7 +69,7 @@ __device__ __forceinline__ int store_row(uint8_t* dst, const RowRegs<DB>& r) {
     const unsigned w[4] = {r.v[i].x, r.v[i].y, r.v[i].z, r.v[i].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      store_expanded_word(dst + (i * 4 + j) * 32, w[j]);
+      store_expanded_word<SIGNED>(dst + (i * 4 + j) * 32, w[j]);
       pc += __popc(w[j]);
     }
   }
@@ -76,7 +81,7 @@ __device__ __forceinline__ void ldmatrix_x4(unsigned addr, unsigned& r0, unsigne
 }
 
 // Shared memory: sA [128][LD] expanded queries | sB [2][128][LD] expanded train tiles (double buffered; the
-// first 32 KB are reused for the final list merge) | pq [128] | pt [2][128].
+// first 32 KB are reused for the final list merge) | pq [128].
 template <int DB>
 __global__ void __launch_bounds__(kMmaThreads, 1)
 hamming_knn2_mma_kernel(const uint8_t* __restrict__ q, long long nq, const uint8_t* __restrict__ t, long long nt,
@@ -86,7 +91,6 @@ hamming_knn2_mma_kernel(const uint8_t* __restrict__ q, long long nq, const uint8
   uint8_t* sA = smem;
   uint8_t* sB = sA + kMmaTile * LD;
   int* pq = reinterpret_cast<int*>(sB + 2 * kMmaTile * LD);
-  int* pt = pq + kMmaTile;
 
   const int tid = threadIdx.x;
   const long long q0 = (long long)blockIdx.x * kMmaTile;
@@ -97,7 +101,7 @@ hamming_knn2_mma_kernel(const uint8_t* __restrict__ q, long long nq, const uint8
   if (tid < kMmaTile) {
     const bool valid = q0 + tid < nq;
     const RowRegs<DB> r = load_row<DB>(q + (q0 + tid) * DB, valid);
-    pq[tid] = store_row<DB>(sA + tid * LD, r);
+    pq[tid] = store_row<DB, true>(sA + tid * LD, r);
   }
   __syncthreads();
 
@@ -114,9 +118,7 @@ hamming_knn2_mma_kernel(const uint8_t* __restrict__ q, long long nq, const uint8
       const long long next_row = t_begin + (long long)(i + 1) * kMmaTile + p;
       const RowRegs<DB> nxt = load_row<DB>(t + next_row * DB, next_row < t_end);
       if (i >= 2) bar_sync(kBarEmpty + buf);
-      const bool valid = t_begin + (long long)i * kMmaTile + p < t_end;
-      const int pc = store_row<DB>(sB + (buf * kMmaTile + p) * LD, cur);
-      pt[buf * kMmaTile + p] = valid ? pc : kMmaPopInvalid;
+      store_row<DB, false>(sB + (buf * kMmaTile + p) * LD, cur);
       bar_arrive(kBarFull + buf);
       cur = nxt;
     }
@@ -132,9 +134,11 @@ hamming_knn2_mma_kernel(const uint8_t* __restrict__ q, long long nq, const uint8
     // B fragments of two 8-column blocks: (cols 0-7,k 0-15) (cols 0-7,k 16-31) (cols 8-15,k 0-15) (cols 8-15,k 16-31)
     const unsigned b_off = (unsigned)((wn * 32 + (lane & 7) + 8 * (lane >> 4)) * LD + 16 * ((lane >> 3) & 1));
     const int g = lane >> 2;
-    int pqr[8];
+    int pqr[8], vthr[8];   // popcount of the row's query; v must exceed vthr = pq - (2nd best distance) to matter
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) { pqr[mt * 2] = pq[wm * 64 + mt * 16 + g]; pqr[mt * 2 + 1] = pq[wm * 64 + mt * 16 + g + 8]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) vthr[i] = pqr[i] - (int)kMmaDistNone;
 
     for (int i = 0; i < ntiles; ++i) {
       const int buf = i & 1;
@@ -156,36 +160,41 @@ hamming_knn2_mma_kernel(const uint8_t* __restrict__ q, long long nq, const uint8
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
           for (int n = 0; n < 4; ++n)
-            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                          : "+r"(acc[mt][n][0]), "+r"(acc[mt][n][1]), "+r"(acc[mt][n][2]), "+r"(acc[mt][n][3])
                          : "r"(a[mt][0]), "r"(a[mt][1]), "r"(a[mt][2]), "r"(a[mt][3]), "r"(b[n][0]), "r"(b[n][1]));
       }
-      int ptc[4][2];
-#pragma unroll
-      for (int n = 0; n < 4; ++n) {
-        const int2 v = *reinterpret_cast<const int2*>(pt + buf * kMmaTile + wn * 32 + n * 8 + 2 * tq);
-        ptc[n][0] = v.x; ptc[n][1] = v.y;
-      }
       if (i + 2 < ntiles) bar_arrive(kBarEmpty + buf);
-      // epilogue: distances and the per-thread two best per row.  A thread meets the train rows of one
-      // query in increasing index order, so an equal distance never displaces an earlier entry.
-      const unsigned col_base = (unsigned)(train_index_offset + t_begin + (long long)i * kMmaTile) + wn * 32 + 2 * tq;
+      // epilogue: one max + compare per row decides whether any of its 8 columns can enter the list.
+      // A thread meets the train rows of one query in increasing index order, so an equal distance
+      // never displaces an earlier entry.
+      const long long tile_base = t_begin + (long long)i * kMmaTile;
+      const int valid_cols = (int)min((long long)kMmaTile, t_end - tile_base);
+      const unsigned col_base = (unsigned)(train_index_offset + tile_base);
+      const int col_thread = wn * 32 + 2 * tq;
 #pragma unroll
       for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const int ri = mt * 2 + half;
+          const int h = half * 2;
+          const int m = max(max(max(acc[mt][0][h], acc[mt][0][h + 1]), max(acc[mt][1][h], acc[mt][1][h + 1])),
+                            max(max(acc[mt][2][h], acc[mt][2][h + 1]), max(acc[mt][3][h], acc[mt][3][h + 1])));
+          if (m > vthr[ri]) {
 #pragma unroll
-          for (int n = 0; n < 4; ++n)
+            for (int n = 0; n < 4; ++n)
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              const unsigned ham = (unsigned)(pqr[ri] + ptc[n][j] - 2 * acc[mt][n][half * 2 + j]);
-              if (ham < d1[ri]) {
-                const unsigned idx = col_base + n * 8 + j;
-                if (ham < d0[ri]) { d1[ri] = d0[ri]; i1[ri] = i0[ri]; d0[ri] = ham; i0[ri] = idx; }
-                else { d1[ri] = ham; i1[ri] = idx; }
+              for (int j = 0; j < 2; ++j) {
+                const int col = col_thread + n * 8 + j;
+                const unsigned ham = (unsigned)(pqr[ri] - acc[mt][n][h + j]);
+                if (ham < d1[ri] && col < valid_cols) {
+                  const unsigned idx = col_base + col;
+                  if (ham < d0[ri]) { d1[ri] = d0[ri]; i1[ri] = i0[ri]; d0[ri] = ham; i0[ri] = idx; }
+                  else { d1[ri] = ham; i1[ri] = idx; }
+                }
               }
-            }
+            vthr[ri] = pqr[ri] - (int)d1[ri];
+          }
         }
     }
   }
@@ -220,7 +229,7 @@ template <int DB>
 static cudaError_t launch_mma(const uint8_t* q, long long nq, const uint8_t* t, long long nt, long long off,
                               unsigned long long* dst, int splits, long long rows_per_split, cudaStream_t stream) {
   constexpr int LD = DB * 8 + kMmaPad;
-  const size_t smem = (size_t)3 * kMmaTile * LD + 3 * kMmaTile * sizeof(int);
+  const size_t smem = (size_t)3 * kMmaTile * LD + kMmaTile * sizeof(int);
   cudaError_t e = cudaFuncSetAttribute(hamming_knn2_mma_kernel<DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)((nq + kMmaTile - 1) / kMmaTile), splits);

@@ -53,8 +53,9 @@ int brisk_sync(brisk_ctx* ctx);
 /* Upper bound on device workspace bytes used per call (frames are processed in
  * chunks that fit); default 8 GiB. */
 int brisk_ctx_set_workspace_limit(brisk_ctx* ctx, size_t bytes);
-/* Matcher kernel: 0 = XOR + POPC tiles (default, any k <= 8), 1 = tensor-core variant (u8 IMMA on
- * 0/1-expanded descriptor bits) where it applies (k == 2, 48- or 64-byte rows); results are identical. */
+/* Matcher kernel: 0 = XOR + POPC tiles for every request, 1 (default) = tensor-core variant (s8 x u8 IMMA
+ * on byte-expanded descriptor bits) where it applies (k == 2, 48- or 64-byte rows) and XOR + POPC
+ * otherwise; results are identical. */
 int brisk_ctx_set_knn_variant(brisk_ctx* ctx, int variant);
 /* Chunks of a batch normally alternate between two streams so that copies and serial kernel tails
  * of one chunk overlap the kernels of the other (default on).  Off: one stream, stages back to back
