@@ -161,7 +161,8 @@ struct Plan {
   size_t integral_elems;  // per frame
 };
 
-int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* ext, int n, int w, int h, int cap, Plan* plan) {
+int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* ext, int n, int w, int h, int cap, Plan* plan,
+              bool host_io = false) {
   const int octaves = det ? det->octaves : 0;
   build_geom(w, h, octaves, &plan->g);
   const PyramidGeom& g = plan->g;
@@ -201,6 +202,12 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
   if (!ctx->pipelining) max_chunk = std::min<long long>(max_chunk * 2, 32768);  // one slot gets the whole budget
   long long n_chunks = (n + max_chunk - 1) / max_chunk;
   if (n_chunks < 2 && n > 1 && ctx->pipelining) n_chunks = 2;
+  // host buffers: the first chunk's upload and the last chunk's download are not hidden behind any
+  // kernel, so cut the batch finer (down to about 150 MB of pixels per chunk, at most 8 chunks)
+  if (host_io && ctx->pipelining) {
+    const long long by_size = std::max<long long>(1, (long long)n * w * h / (150ll << 20));
+    n_chunks = std::max(n_chunks, std::min<long long>(8, by_size));
+  }
   if (n_chunks < 1) n_chunks = 1;
   const long long chunk = std::max<long long>(1, (n + n_chunks - 1) / n_chunks);  // equal-sized chunks, no tiny tail
   plan->chunk = (int)chunk;
@@ -263,13 +270,22 @@ DetectWorkspace slot_ws(const Plan& plan, const Slot& sl) {
 // alignment, describe them in place.  Returns the tensor map the pyramid
 // kernel reads and whether it has to materialise layer 0 in the block.
 int stage_input(brisk_ctx* ctx, Slot& sl, const Plan& plan, const uint8_t* imgs, int count, int w, int h, size_t stride,
-                size_t frame_pitch, CUtensorMap* map, int* write_l0) {
+                size_t frame_pitch, CUtensorMap* map, int* write_l0, bool* staged_tight = nullptr) {
   const PyramidGeom& g = plan.g;
   const bool dev = is_device_ptr(imgs);
   const bool aligned = dev && ((uintptr_t)imgs % 16 == 0) && (stride % 16 == 0) && (frame_pitch % 16 == 0);
+  if (staged_tight) *staged_tight = false;
   if (aligned) {
     *write_l0 = 1;
     return encode_map(ctx, imgs, w, h, count, stride, frame_pitch, map);
+  }
+  // Host frames that are tightly packed and contiguous travel in ONE copy into the staging buffer, which
+  // the pyramid kernel then reads like a caller's device batch (and the sampler reuses as its packed image).
+  if (staged_tight && !dev && w % 16 == 0 && stride == (size_t)w && (count == 1 || frame_pitch == (size_t)w * h)) {
+    CU_OK(cudaMemcpyAsync(sl.tight.p, imgs, (size_t)count * w * h, cudaMemcpyHostToDevice, sl.stream));
+    *write_l0 = 1;
+    *staged_tight = true;
+    return encode_map(ctx, sl.tight.as<uint8_t>(), w, h, count, (size_t)w, (size_t)w * h, map);
   }
   for (int f = 0; f < count; ++f)
     CU_OK(cudaMemcpy2DAsync(sl.pyr.as<uint8_t>() + (size_t)f * g.frame_elems + g.L[0].off, g.L[0].pitch,
@@ -315,7 +331,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       if (probe.L[i].w < 8 || probe.L[i].h < 8) return fail(ctx, BRISK_ERR_INVALID, "image too small: every pyramid layer must be at least 8x8");
   }
   Plan plan;
-  rc = make_plan(ctx, det, ext, n, w, h, cap, &plan);
+  rc = make_plan(ctx, det, ext, n, w, h, cap, &plan, !is_device_ptr(imgs));
   if (rc) return rc;
   const PyramidGeom& g = plan.g;
   const int desc_bytes = ext ? ext->dev.desc_bytes : 0;
@@ -327,7 +343,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     if (!counts_dev) CU_OK(sl.counts.ensure((size_t)plan.chunk * 4));
     if (ext && !desc_dev) CU_OK(sl.desc.ensure((size_t)plan.chunk * cap * desc_bytes));
     if (det && masks && !masks_dev) CU_OK(sl.masks.ensure((size_t)plan.chunk * w * h));
-    if (ext && g.L[0].pitch != w) CU_OK(sl.tight.ensure((size_t)plan.chunk * ((size_t)w * h + 64)));
+    if ((ext && g.L[0].pitch != w) || !is_device_ptr(imgs)) CU_OK(sl.tight.ensure((size_t)plan.chunk * ((size_t)w * h + 64)));
   }
   // order the slots' streams after whatever the caller queued on the context stream
   CU_OK(cudaEventRecord(ctx->entry, ctx->stream));
@@ -388,7 +404,8 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     tm.mark(0);
     CUtensorMap map;
     int write_l0 = 0;
-    rc = stage_input(ctx, sl, plan, imgs + (size_t)f0 * frame_pitch, c, w, h, stride, frame_pitch, &map, &write_l0);
+    bool staged_tight = false;
+    rc = stage_input(ctx, sl, plan, imgs + (size_t)f0 * frame_pitch, c, w, h, stride, frame_pitch, &map, &write_l0, &staged_tight);
     if (rc) return rc;
     const uint8_t* d_masks = nullptr;
     long long mask_fs = 0; int mask_pitch = 0;
@@ -446,11 +463,12 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       const uint8_t* simg = l0;
       long long sstride = g.frame_elems;
       int spitch = g.L[0].pitch;
-      if (spitch != w) {
+      if (spitch != w && staged_tight) {
+        simg = sl.tight.as<uint8_t>(); sstride = (long long)w * h; spitch = w;
+      } else if (spitch != w) {
         const size_t fs = (size_t)w * h + 64;
-        for (int f = 0; f < c; ++f)
-          CU_OK(cudaMemcpy2DAsync(sl.tight.as<uint8_t>() + (size_t)f * fs, w, l0 + (size_t)f * g.frame_elems, g.L[0].pitch, w, h,
-                                  cudaMemcpyDeviceToDevice, sl.stream));
+        CU_OK(launch_copy_tight(l0, g.frame_elems, g.L[0].pitch, w, h, c, sl.tight.as<uint8_t>(), (long long)fs, sl.stream));
+        ctx->launches += 1;
         simg = sl.tight.as<uint8_t>(); sstride = (long long)fs; spitch = w;
       }
       CU_OK(launch_describe(ext->dev, simg, sstride, spitch, w, h, c, sl.integral.as<int32_t>(), d_kps, d_counts, cap,

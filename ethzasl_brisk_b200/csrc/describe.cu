@@ -10,6 +10,8 @@
 // order, reference :538-564).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "describe_logic.cuh"
 #include "kernels.h"
 
@@ -73,6 +75,33 @@ cudaError_t launch_integral(const uint8_t* imgs, long long frame_stride, int pit
   integral_rows_kernel<<<g1, 256, 0, stream>>>(imgs, frame_stride, pitch, w, h, integral);
   dim3 g2((w + 255) / 256, n_frames);
   integral_cols_kernel<<<g2, 256, 0, stream>>>(w, h, integral);
+  return cudaGetLastError();
+}
+
+// --- pitched planes -> tightly packed frames (row stride == width), one launch for a whole chunk ---
+
+__global__ void __launch_bounds__(256)
+copy_tight_kernel(const uint8_t* __restrict__ src, long long src_frame_stride, int src_pitch, int w, int h,
+                  uint8_t* __restrict__ dst, long long dst_frame_stride) {
+  const int frame = blockIdx.y;
+  const uint8_t* s = src + (long long)frame * src_frame_stride;
+  uint8_t* d = dst + (long long)frame * dst_frame_stride;
+  const int words_per_row = (w + 3) / 4;   // source rows are 4-byte aligned (pitch is a multiple of 16)
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)words_per_row * h; i += (long long)gridDim.x * blockDim.x) {
+    const int y = (int)(i / words_per_row), x = 4 * (int)(i - (long long)y * words_per_row);
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(s + (long long)y * src_pitch + x);
+    uint8_t* o = d + (long long)y * w + x;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (x + b < w) o[b] = (uint8_t)(v >> (8 * b));
+  }
+}
+
+cudaError_t launch_copy_tight(const uint8_t* src, long long src_frame_stride, int src_pitch, int w, int h, int n_frames,
+                              uint8_t* dst, long long dst_frame_stride, cudaStream_t stream) {
+  const long long words = (long long)((w + 3) / 4) * h;
+  dim3 grid((unsigned)std::min<long long>((words + 255) / 256, 256), n_frames);
+  copy_tight_kernel<<<grid, 256, 0, stream>>>(src, src_frame_stride, src_pitch, w, h, dst, dst_frame_stride);
   return cudaGetLastError();
 }
 

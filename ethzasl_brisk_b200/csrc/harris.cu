@@ -136,23 +136,72 @@ harris_nms3d_kernel(PyramidGeom g, HarrisLayerParams hp, const int* __restrict__
   keep[(long long)frame * cap + k] = ok ? 1 : 0;
 }
 
-// One thread per (frame, layer): stable compaction of the kept maxima, then std::sort's permutation.
-__global__ void __launch_bounds__(32)
-harris_sort_kernel(int n_layers, int n_items, const int* __restrict__ layer_start, const HPoint* __restrict__ pts,
+// One CTA per (frame, layer): stable compaction of the kept maxima, then the order std::sort gives them
+// (descending score; the arrangement of equal scores is part of the reference's result, so the CTA
+// replays libstdc++'s introsort).  The two sides of a partition are independent, so the replay runs
+// level by level with one thread per open range; ranges of at most 16 elements get their share of
+// the final insertion sort from the thread that produced them.
+constexpr int kSortThreads = 256;
+constexpr int kSortRanges = 2048;   // open ranges per level held in shared memory; overflow is sorted by its producer
+
+__global__ void __launch_bounds__(kSortThreads)
+harris_sort_kernel(int n_layers, const int* __restrict__ layer_start, const HPoint* __restrict__ pts,
                    const uint8_t* __restrict__ keep, HPoint* __restrict__ sorted, int* __restrict__ layer_kept, int cap) {
-  const int item = blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= n_items) return;
-  const int frame = item / n_layers, layer = item - frame * n_layers;
+  __shared__ int2 s_ranges[2][kSortRanges];
+  __shared__ int s_count[2];
+  __shared__ int s_warp[kSortThreads / 32];
+  __shared__ int s_base;
+  const int layer = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int* ls = layer_start + (long long)frame * (kMaxLayers + 1);
   const int begin = min(ls[layer], cap), end = min(ls[layer + 1], cap);
   const HPoint* src = pts + (long long)frame * cap;
   const uint8_t* kf = keep + (long long)frame * cap;
   HPoint* dst = sorted + (long long)frame * cap + begin;
-  int m = 0;
-  for (int k = begin; k < end; ++k)
-    if (kf[k]) dst[m++] = src[k];
-  layer_kept[frame * kMaxLayers + layer] = m;
-  gcc_sort(dst, m);
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  // stable compaction, kSortThreads candidates per round
+  for (int k0 = begin; k0 < end; k0 += kSortThreads) {
+    const int k = k0 + tid;
+    const bool on = k < end && kf[k];
+    const unsigned bal = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (on) dst[off + __popc(bal & ((1u << lane) - 1u))] = src[k];
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < kSortThreads / 32; ++w) t += s_warp[w]; s_base += t; }
+    __syncthreads();
+  }
+  const int m = s_base;
+  if (tid == 0) {
+    layer_kept[frame * kMaxLayers + layer] = m;
+    s_ranges[0][0] = make_int2(0, m);
+    s_count[0] = m > 16 ? 1 : 0;
+    s_count[1] = 0;
+    if (m > 1 && m <= 16) hp_insertion_sort(dst, dst + m);
+  }
+  __syncthreads();
+  int cur = 0;
+  for (int depth = gcc_depth_limit(max(m, 1)); s_count[cur] > 0; --depth, cur ^= 1) {
+    const int count = s_count[cur];
+    for (int r = tid; r < count; r += kSortThreads) {
+      const int2 rg = s_ranges[cur][r];
+      if (depth == 0) { hp_heapsort(dst + rg.x, rg.y - rg.x); continue; }
+      const int cut = gcc_partition(dst, rg.x, rg.y);
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const int f = side ? cut : rg.x, l = side ? rg.y : cut;
+        if (l - f <= 16) { hp_insertion_sort(dst + f, dst + l); continue; }
+        const int slot = atomicAdd(&s_count[cur ^ 1], 1);
+        if (slot < kSortRanges) s_ranges[cur ^ 1][slot] = make_int2(f, l);
+        else gcc_sort_range(dst, f, l, depth - 1);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) { s_count[cur] = 0; s_count[cur ^ 1] = min(s_count[cur ^ 1], kSortRanges); }
+    __syncthreads();
+  }
 }
 
 struct UniformityGeom {
@@ -163,8 +212,6 @@ struct UniformityGeom {
 };
 
 // One CTA per (frame, layer): EnforceKeyPointUniformity (uniformity-enforcement-inl.h:44-194).
-// The sorted points are visited in order; the skip test of a point must see the stamps of all its
-// predecessors, so the CTA synchronises after every stamp (about 5 % of the points).
 __global__ void __launch_bounds__(256)
 harris_uniformity_kernel(PyramidGeom g, UniformityGeom ug, const int* __restrict__ layer_start, const HPoint* __restrict__ sorted,
                          const int* __restrict__ layer_kept, uint8_t* __restrict__ occ_all, HPoint* __restrict__ surv,
@@ -177,28 +224,56 @@ harris_uniformity_kernel(PyramidGeom g, UniformityGeom ug, const int* __restrict
   HPoint* out = surv + (long long)frame * cap + begin;
   uint8_t* occ = occ_all + (long long)frame * ug.occ_frame_bytes + ug.occ_off[layer];
   const int ow = ug.occ_w[layer], oh = ug.occ_h[layer];
-  for (long long i = tid; i < (long long)ow * oh; i += blockDim.x) occ[i] = 0;
+  {  // every layer's region starts 256-byte aligned and is padded to a multiple of 256 bytes
+    uint4* o4 = reinterpret_cast<uint4*>(occ);
+    for (long long i = tid; i < ((long long)ow * oh + 15) / 16; i += blockDim.x) o4[i] = make_uint4(0, 0, 0, 0);
+  }
   __syncthreads();
+  __shared__ int s_first[8];
+  __shared__ HPoint s_pt;
+  __shared__ float s_nsc1;
   int kept = 0;
-  if (m > 0) {
-    const float max_score = (float)pts[0].score;
-    for (int k = 0; k < m; ++k) {
-      const HPoint p = pts[k];
+  bool full = false;
+  const float max_score = m > 0 ? (float)pts[0].score : 1.0f;
+  // The skip test of a point must see the stamps of all its predecessors.  Occupancy only grows, so a
+  // "skip" verdict is final; the points are judged 256 at a time, the first survivor of the batch
+  // stamps, and only the points after it are judged again.
+  for (int base = 0; base < m && !full; base += 256) {
+    const int k = base + tid;
+    HPoint p = {0, 0, 0};
+    int cell = 0;
+    float nsc1 = 0.0f;
+    bool undecided = k < m;
+    if (undecided) {
+      p = pts[k];
       const int cy = (int)((float)(int)p.y * ug.scaling + 16.0f), cx = (int)((float)(int)p.x * ug.scaling + 16.0f);
-      const float nsc1 = uniformity_nsc1(p.score, max_score);
-      if ((double)nsc1 < (double)occ[(long long)cy * ow + cx]) continue;  // uniform across the CTA
-      __syncthreads();  // everybody has read the cell before it is stamped
-      const float nsc = 0.99f * nsc1;
+      cell = cy * ow + cx;
+      nsc1 = uniformity_nsc1(p.score, max_score);
+    }
+    for (;;) {
+      if (undecided && (double)nsc1 < (double)*(volatile uint8_t*)(occ + cell)) undecided = false;
+      const unsigned bal = __ballot_sync(0xffffffffu, undecided);
+      if ((tid & 31) == 0) s_first[tid >> 5] = bal ? (tid | (__ffs(bal) - 1)) : 0x7fffffff;
+      __syncthreads();
+      int first = s_first[0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) first = min(first, s_first[w]);
+      if (first == 0x7fffffff) { __syncthreads(); break; }
+      if (tid == first) { s_pt = p; s_nsc1 = nsc1; undecided = false; }
+      __syncthreads();
+      const HPoint sp = s_pt;
+      const float nsc = 0.99f * s_nsc1;
+      const int cy = (int)((float)(int)sp.y * ug.scaling + 16.0f), cx = (int)((float)(int)sp.x * ug.scaling + 16.0f);
       for (int c = tid; c < 31 * 31; c += blockDim.x) {
         const int y = c / 31, x = c - y * 31;
         uint8_t* o = occ + (long long)(cy + y - 15) * ow + cx + x - 15;
         const int v = (int)*o + uniformity_stamp(x, y, nsc);
         *o = (uint8_t)(v > 255 ? 255 : v);
       }
-      if (tid == 0) out[kept] = p;
+      if (tid == 0) out[kept] = sp;
       ++kept;
       __syncthreads();
-      if ((long long)kept == max_kpt) break;
+      if ((long long)kept == max_kpt) { full = true; break; }
     }
   }
   if (tid == 0) layer_surv[frame * kMaxLayers + layer] = kept;
@@ -266,8 +341,7 @@ cudaError_t launch_harris_detect(const PyramidGeom& g, const HarrisWorkspace& hw
   }
   dim3 gp((hw.det.corner_cap + 127) / 128, n_frames);
   harris_nms3d_kernel<<<gp, 128, 0, stream>>>(g, hp, hw.scores, hw.det.layer_start, hw.pts, hw.keep, hw.det.corner_cap, thr);
-  const int items = n_frames * g.n_layers;
-  harris_sort_kernel<<<(items + 31) / 32, 32, 0, stream>>>(g.n_layers, items, hw.det.layer_start, hw.pts, hw.keep, hw.sorted, hw.layer_kept, hw.det.corner_cap);
+  harris_sort_kernel<<<dim3(g.n_layers, n_frames), kSortThreads, 0, stream>>>(g.n_layers, hw.det.layer_start, hw.pts, hw.keep, hw.sorted, hw.layer_kept, hw.det.corner_cap);
   UniformityGeom ug;
   ug.occ_frame_bytes = hw.occ_frame_bytes;
   ug.scaling = (float)(15.0 / (double)(float)radius);

@@ -187,52 +187,63 @@ BRISK_HD void hp_insertion_sort(HPoint* first, HPoint* last) {
   }
 }
 
-BRISK_HD void gcc_sort(HPoint* a, int n) {
-  if (n <= 0) return;
-  int lg = 0;
-  for (unsigned v = (unsigned)n; v > 1; v >>= 1) ++lg;  // std::__lg
-  // explicit stack of (first, last, depth_limit)
+// One pass of std::__introsort_loop's body on [first, last): __unguarded_partition_pivot (median of
+// first+1, mid, last-1 moved to first, then the unguarded Hoare scan).  Returns the cut.
+BRISK_HD int gcc_partition(HPoint* a, int first, int last) {
+  const int mid = first + (last - first) / 2;
+  HPoint& ra = a[first + 1]; HPoint& rb = a[mid]; HPoint& rc = a[last - 1];
+  if (hp_less(ra, rb)) {
+    if (hp_less(rb, rc)) hp_swap(a[first], rb);
+    else if (hp_less(ra, rc)) hp_swap(a[first], rc);
+    else hp_swap(a[first], ra);
+  } else if (hp_less(ra, rc)) hp_swap(a[first], ra);
+  else if (hp_less(rb, rc)) hp_swap(a[first], rc);
+  else hp_swap(a[first], rb);
+  int lo = first + 1, hi = last;
+  for (;;) {
+    while (hp_less(a[lo], a[first])) ++lo;
+    --hi;
+    while (hp_less(a[first], a[hi])) --hi;
+    if (!(lo < hi)) break;
+    hp_swap(a[lo], a[hi]);
+    ++lo;
+  }
+  return lo;
+}
+
+// std::__introsort_loop on [first, last) with the given depth limit, followed by the part of
+// __final_insertion_sort that concerns this range.  The final insertion sort never moves an element
+// across a partition cut (everything left of a cut compares >= everything right of it), so it is
+// the same as a stable insertion sort of every leaf range of at most 16 elements.
+BRISK_HD void gcc_sort_range(HPoint* a, int first0, int last0, int depth0) {
   int st_first[64], st_last[64], st_depth[64];
   int sp = 0;
-  st_first[0] = 0; st_last[0] = n; st_depth[0] = 2 * lg; sp = 1;
+  st_first[0] = first0; st_last[0] = last0; st_depth[0] = depth0; sp = 1;
   while (sp > 0) {
     --sp;
     int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
+    bool heap = false;
     while (last - first > 16) {
-      if (depth == 0) { hp_heapsort(a + first, last - first); break; }
+      if (depth == 0) { hp_heapsort(a + first, last - first); heap = true; break; }
       --depth;
-      // __unguarded_partition_pivot: median of (first+1, mid, last-1) moved to first
-      const int mid = first + (last - first) / 2;
-      HPoint& ra = a[first + 1]; HPoint& rb = a[mid]; HPoint& rc = a[last - 1];
-      if (hp_less(ra, rb)) {
-        if (hp_less(rb, rc)) hp_swap(a[first], rb);
-        else if (hp_less(ra, rc)) hp_swap(a[first], rc);
-        else hp_swap(a[first], ra);
-      } else if (hp_less(ra, rc)) hp_swap(a[first], ra);
-      else if (hp_less(rb, rc)) hp_swap(a[first], rc);
-      else hp_swap(a[first], rb);
-      // __unguarded_partition(first + 1, last, pivot = first)
-      int lo = first + 1, hi = last;
-      for (;;) {
-        while (hp_less(a[lo], a[first])) ++lo;
-        --hi;
-        while (hp_less(a[first], a[hi])) --hi;
-        if (!(lo < hi)) break;
-        hp_swap(a[lo], a[hi]);
-        ++lo;
-      }
-      // recurse on [cut, last), continue with [first, cut)
-      st_first[sp] = lo; st_last[sp] = last; st_depth[sp] = depth; ++sp;
-      last = lo;
+      const int cut = gcc_partition(a, first, last);
+      st_first[sp] = cut; st_last[sp] = last; st_depth[sp] = depth; ++sp;   // recurse on [cut, last), go on with [first, cut)
+      last = cut;
     }
+    if (!heap) hp_insertion_sort(a + first, a + last);
   }
-  // __final_insertion_sort
-  if (n > 16) {
-    hp_insertion_sort(a, a + 16);
-    for (HPoint* i = a + 16; i != a + n; ++i) hp_unguarded_linear_insert(i);
-  } else {
-    hp_insertion_sort(a, a + n);
-  }
+}
+
+BRISK_HD int gcc_depth_limit(int n) {
+  int lg = 0;
+  for (unsigned v = (unsigned)n; v > 1; v >>= 1) ++lg;  // std::__lg
+  return 2 * lg;
+}
+
+// std::sort(a, a + n) with hp_less, element for element (libstdc++ of GCC 13).
+BRISK_HD void gcc_sort(HPoint* a, int n) {
+  if (n <= 0) return;
+  gcc_sort_range(a, 0, n, gcc_depth_limit(n));
 }
 
 // Uniformity enforcement constants (uniformity-enforcement-inl.h:59-80).

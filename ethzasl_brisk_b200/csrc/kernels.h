@@ -77,6 +77,8 @@ cudaError_t launch_integral(const uint8_t* imgs, long long frame_stride, int pit
                             int32_t* integral, cudaStream_t stream);
 // Border cull (stable, per frame) + descriptor computation.  kps is in/out
 // [frame][kp_cap], counts in/out, desc out [frame][kp_cap][desc_bytes].
+cudaError_t launch_copy_tight(const uint8_t* src, long long src_frame_stride, int src_pitch, int w, int h, int n_frames,
+                              uint8_t* dst, long long dst_frame_stride, cudaStream_t stream);
 cudaError_t launch_describe(const PatternDev& pat, const uint8_t* imgs, long long frame_stride, int pitch, int w, int h,
                             int n_frames, const int32_t* integral, KeyPoint* kps, int* counts, int kp_cap,
                             KeyPoint* kps_scratch, int* scale_scratch, uint8_t* desc, cudaStream_t stream);
