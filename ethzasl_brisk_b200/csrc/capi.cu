@@ -261,7 +261,7 @@ DetectWorkspace slot_ws(const Plan& plan, const Slot& sl) {
   ws.pyr = sl.pyr.as<uint8_t>(); ws.cm = sl.cm.as<uint16_t>(); ws.bm = sl.bm.as<uint8_t>();
   ws.rowcnt = sl.rowcnt.as<int>(); ws.layer_start = sl.layer_start.as<int>(); ws.corners = sl.corners.as<uint32_t>();
   ws.fwin = sl.fwin.as<uint8_t>(); ws.checks = sl.checks.as<float>(); ws.kp_tmp = sl.kp_tmp.as<KeyPoint>();
-  ws.kp_valid = sl.kp_valid.as<uint8_t>(); ws.rounds = sl.rounds.as<int>();
+  ws.kp_valid = sl.kp_valid.as<uint8_t>(); ws.n_ties = sl.rounds.as<int>();
   return ws;
 }
 
@@ -819,9 +819,9 @@ int brisk_debug_nms_state(brisk_ctx* ctx, brisk_detector* det, const uint8_t* im
   return count;
 }
 
-int brisk_debug_nms_rounds(brisk_ctx* ctx, int32_t* rounds /* [12] of frame 0 of the last detect call */) {
-  if (!ctx || !rounds || !ctx->slots[0].rounds.p) return BRISK_ERR_INVALID;
-  CU_OK(cudaMemcpy(rounds, ctx->slots[0].rounds.p, kMaxLayers * 4, cudaMemcpyDeviceToHost));
+int brisk_debug_nms_ties(brisk_ctx* ctx, int32_t* ties /* [12] of frame 0 of the last detect call */) {
+  if (!ctx || !ties || !ctx->slots[0].rounds.p) return BRISK_ERR_INVALID;
+  CU_OK(cudaMemcpy(ties, ctx->slots[0].rounds.p, kMaxLayers * 4, cudaMemcpyDeviceToHost));
   return BRISK_OK;
 }
 

@@ -20,7 +20,7 @@ struct DetectWorkspace {
   float* checks;        // [frame][corner_cap][8]  CheckResult (32 bytes)
   KeyPoint* kp_tmp;     // [frame][corner_cap]
   uint8_t* kp_valid;    // [frame][corner_cap]
-  int* rounds;          // [frame][kMaxLayers] tie-resolution rounds per layer (diagnostic)
+  int* n_ties;          // [frame][kMaxLayers] tying corners per layer (diagnostic)
   int total_rows;       // sum of layer heights
   int row_off[kMaxLayers + 1];
   int corner_cap;       // per frame

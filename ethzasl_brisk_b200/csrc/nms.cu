@@ -3,15 +3,18 @@
 //
 // Replaces BriskScaleSpace::GetKeypoints and friends (reference
 // brisk/src/brisk-scale-space.cc:92-1364).  Launch sequence per batch:
-//   nms_prefix_kernel  one thread per raw corner   IsMax2D's 8 comparisons
-//   nms_checks_kernel  one thread per raw corner   above / below scale checks (pure)
-//   nms_chain_kernel   one CTA per frame           layer by layer: tying corners in
-//                                                  raster order, then the footprint
-//                                                  the accepted corners leave on the
-//                                                  layer above
+//   nms_prefix_kernel  one thread per raw corner   IsMax2D's 8 comparisons; flags tying corners
+//   nms_checks_kernel  one thread per raw corner   above / below scale checks (pure) and, for
+//                                                  corners accepted without a tie, the footprint
+//                                                  they leave on the layer above
+//   nms_chain_kernel   one CTA per frame           layer by layer: the tying corners only, one
+//                                                  warp per corner in raster order, each waiting
+//                                                  for its raster-earlier tying neighbours
 //   refine_kernel      one thread per raw corner   sub-pixel / scale refinement
 //   compact_kernel     one CTA per frame           ordered compaction (+ mask filter)
 #include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 #include "nms_logic.cuh"
@@ -31,6 +34,12 @@ __device__ __forceinline__ void make_views(const PyramidGeom& g, const DetectWor
   }
 }
 
+__device__ __forceinline__ LayerView make_view(const PyramidGeom& g, const DetectWorkspace& ws, int frame, int layer) {
+  const long long fo = (long long)frame * g.frame_elems;
+  const LayerGeom& L = g.L[layer];
+  return LayerView{ws.pyr + fo + L.off, ws.cm + fo + L.off, ws.bm + fo + L.off, L.w, L.h, L.pitch, L.scale, L.offset};
+}
+
 __device__ __forceinline__ void unpack_corner(uint32_t c, int* x, int* y, int* layer) {
   *x = c & 0x1fff; *y = (c >> 13) & 0x1fff; *layer = c >> 26;
 }
@@ -48,7 +57,13 @@ nms_prefix_kernel(PyramidGeom g, DetectWorkspace ws) {
   const LayerView v{ws.pyr + fo + L.off, ws.cm + fo + L.off, ws.bm + fo + L.off, L.w, L.h, L.pitch, L.scale, L.offset};
   uint8_t fwin[25];
   nms_prefix(v, x, y, fwin);
-  if (v.cm[(long long)y * L.pitch + x] & kCmTie) {
+  const bool tie = v.cm[(long long)y * L.pitch + x] & kCmTie;
+  if (tie) {
+    // per-layer list of the tying corners (any order) for the chain kernel, in the frame's key-point
+    // scratch, which is free until refine_kernel runs; layer l's list starts at its first corner slot
+    const int pos = atomicAdd(&ws.n_ties[frame * kMaxLayers + layer], 1);
+    reinterpret_cast<int2*>(ws.kp_tmp + (long long)frame * ws.corner_cap)[ws.layer_start[(long long)frame * (kMaxLayers + 1) + layer] + pos] =
+        make_int2(k, x | (y << 16));
     uint8_t* dst = ws.fwin + ((long long)frame * ws.corner_cap + k) * 32;
 #pragma unroll
     for (int i = 0; i < 25; ++i) dst[i] = fwin[i];
@@ -63,43 +78,109 @@ nms_checks_kernel(PyramidGeom g, DetectWorkspace ws) {
   if (k >= n) return;
   int x, y, layer;
   unpack_corner(ws.corners[(long long)frame * ws.corner_cap + k], &x, &y, &layer);
-  FrameViews fv;
-  make_views(g, ws, frame, &fv);
-  uint16_t* e = fv.v[layer].cm + (long long)y * fv.v[layer].pitch + x;
+  const LayerView own = make_view(g, ws, frame, layer);
+  uint16_t* e = own.cm + (long long)y * own.pitch + x;
   const uint16_t ev = *e;
   if ((ev & kCmDecided) && !(ev & kCmAccept)) return;
+  // only the corner's own layer and its two neighbours are looked at
+  const LayerView below = make_view(g, ws, frame, layer > 0 ? layer - 1 : 0);
+  const LayerView above = make_view(g, ws, frame, layer + 1 < g.n_layers ? layer + 1 : layer);
   CheckResult r;
-  const bool ok = nms_checks(fv.v, g.n_layers, layer, x, y, &r);
+  const bool ok = nms_checks3(below, own, above, g.n_layers, layer, x, y, &r);
   if (ok) *e = ev | kCmChecks;
   // kept even when the checks fail: the footprint of the scan of the layer above is needed by the chain kernel
   *reinterpret_cast<CheckResult*>(ws.checks + ((long long)frame * ws.corner_cap + k) * 8) = r;
+  // A corner accepted without a tie leaves its footprint on the layer above right away (the touch map is
+  // only read by the chain kernel); tying corners do so once they are resolved.
+  if ((ev & kCmAccept) && g.n_layers > 1 && layer < g.n_layers - 1) mark_above1(above, layer, x, y, r);
 }
 
-// Warp-cooperative IsMax2D tie path for one tying corner: the 64 corner-map entries of the 8x8
-// window are staged by the lanes (two each), lanes 0..24 each reconstruct the value of one pixel of
-// the 5x5 neighbourhood, and the 3x3 binomial sums around the centre and around every tying
-// neighbour are formed with shuffles.  Returns 1 accept, 0 reject, -1 blocked (an earlier tying
-// corner in the window is undecided); uniform across the warp.
-__device__ __forceinline__ int warp_tie_decide(const LayerView& L, int mode, int x, int y, const uint8_t* __restrict__ fwin,
-                                               uint16_t* s_win /* 64 entries, this warp's */) {
+// Warp-cooperative IsMax2D tie path for one tying corner (same result as nms_tie_decide, which
+// states the rule pixel by pixel).  The 64 corner-map entries of the 8x8 window are staged by the
+// lanes (two each); lanes 0..24 own one pixel of the 5x5 neighbourhood each and reconstruct its
+// cache state together, stepping through the raster-earlier corners of the window (a handful,
+// found with two ballots) -- under both assumptions about the pending verdicts.  The 3x3 binomial
+// sums around the centre and around every tying neighbour are formed with shuffles.  Returns 1
+// accept, 0 reject, -1 not decidable yet; uniform across the warp.
+// Everything warp_tie_decide reads from global memory for one corner, per lane: two entries of the
+// 8x8 corner-map window, the FAST score and the touch mark of the lane's pixel of the 5x5
+// neighbourhood, and the scan footprint for warp_mark_above.  Loaded one corner ahead of its use.
+struct TieLoads {
+  uint16_t we[2];
+  int F, bmv;
+  int2 fp;  // CheckResult::above_steps, above_argmax
+};
+
+__device__ __forceinline__ void tie_issue_loads(const LayerView& L, int mode, int x, int y, const uint8_t* __restrict__ fwin,
+                                                const float* __restrict__ checks, TieLoads* t) {
   const int lane = threadIdx.x & 31;
-  bool blocked = false;
+  const int ox = lane % 5 - 2, oy = lane / 5 - 2;  // lanes 0..24 <-> 5x5 offsets, row-major
+  t->we[0] = 0; t->we[1] = 0; t->F = 0; t->bmv = 0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int i = lane + 32 * h;
     const int px = x - 4 + (i & 7), py = y - 4 + (i >> 3);
-    uint16_t e = 0;
-    if (py >= 3 && px >= 3 && px < L.w - 3 && py < L.h - 3) e = L.cm[(long long)py * L.pitch + px];
-    s_win[i] = e;
-    if ((e & kCmT) && !(e & kCmDecided) && (py < y || (py == y && px < x))) blocked = true;
+    if (py >= 3 && px >= 3 && px < L.w - 3 && py < L.h - 3) t->we[h] = L.cm[(long long)py * L.pitch + px];
   }
-  if (__any_sync(0xffffffffu, blocked)) return -1;
-  __syncwarp();
-  const TieWindow W{s_win, 1, x - 4, y - 4};
-  const int center = W.at(x, y) & kCmT;
+  if (lane < 25) {
+    t->F = fwin[lane];
+    if (!in_border(L, x + ox, y + oy)) t->bmv = L.bm[(long long)(y + oy) * L.pitch + x + ox];
+  }
+  t->fp = mode == kModeMid ? *reinterpret_cast<const int2*>(checks + 6) : make_int2(0, 0);
+}
+
+__device__ __forceinline__ int warp_tie_decide(const LayerView& L, int mode, int x, int y, const TieLoads& ld,
+                                               uint16_t* s_win /* 64 entries, this warp's */) {
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
   const int ox = lane % 5 - 2, oy = lane / 5 - 2;  // lanes 0..24 <-> 5x5 offsets, row-major
-  int v = 0;
-  if (lane < 25) v = tie_pixel_value(L, W, mode, x, y, ox, oy, fwin[lane], center);
+  const int F = ld.F;
+  s_win[lane] = ld.we[0];
+  s_win[lane + 32] = ld.we[1];
+  // raster-earlier corners of the window (entry 36 is the corner itself): the only entries cache_state looks at
+  const bool c0 = ld.we[0] & kCmT, c1 = (ld.we[1] & kCmT) && lane < 4;
+  unsigned long long earlier = (unsigned long long)__ballot_sync(kFull, c0) | ((unsigned long long)__ballot_sync(kFull, c1) << 32);
+  const bool pending = __any_sync(kFull, (c0 && !(ld.we[0] & kCmDecided)) || (c1 && !(ld.we[1] & kCmDecided)));
+  __syncwarp();
+  const int center = s_win[4 * 8 + 4] & kCmT;
+  const bool ring1 = ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1;
+  const int tq = lane < 25 ? (s_win[(oy + 4) * 8 + ox + 4] & kCmT) : 0;  // 0 on border pixels
+  // cache_state of the lane's pixel q, for all lanes at once: one step per raster-earlier corner p of the
+  // window (uniform), in raster order; pending verdicts taken as reject (0) / accept (1)
+  bool sticky0 = ld.bmv != 0, sticky1 = sticky0;
+  int last0 = sticky0 ? 1 : 0, last1 = last0;
+  while (earlier) {
+    const int i = __ffsll((long long)earlier) - 1;
+    earlier &= earlier - 1;
+    const int e = s_win[i];
+    const int t = e & kCmT, calls = (e & kCmCalls) >> kCmCallsShift;
+    const bool acc0 = e & kCmAccept, acc1 = acc0 || !(e & kCmDecided), chk = e & kCmChecks;
+    const int pox = ox + 4 - (i & 7), poy = oy + 4 - (i >> 3);  // q - p; p can touch q when both are in [-1,2]
+    const bool inblk = (unsigned)(pox + 1) <= 3u && (unsigned)(poy + 1) <= 3u;
+    const bool near = inblk && pox <= 1 && poy <= 1;
+    // IsMax2D neighbour look-up of p with threshold T(p), if p got that far (isMax2dIndex as a nibble table)
+    const int j = (int)((0x534150627ull >> (4 * (((poy + 1) * 3 + pox + 1) & 15))) & 0xfull);
+    const bool look = near && j < calls;
+    bool patch;  // q inside the patch an accepted p looks up with threshold 1
+    if (mode == kModeSingle) patch = inblk;
+    else if (mode == kModeLast) patch = inblk && ((pox >= 0 && poy >= 0 && near) || chk);
+    else patch = near && chk;
+    if (look) { last0 = t; last1 = t; if (t <= F) { sticky0 = true; sticky1 = true; } }
+    if (patch && acc0) { sticky0 = true; last0 = 1; }
+    if (patch && acc1) { sticky1 = true; last1 = 1; }
+  }
+  int st0 = 0, st1 = 0;
+  if (lane < 25 && !tq && F >= 1 && !in_border(L, x + ox, y + oy)) {
+    st0 = F > 2 ? (sticky0 ? F : 0) : ((last0 != 0 && last0 <= F) ? F : 0);
+    st1 = F > 2 ? (sticky1 ? F : 0) : ((last1 != 0 && last1 <= F) ? F : 0);
+  }
+  // what the tie path sees (tie_pixel_value): own score, look-up results on the 8 neighbours, raw cache bytes outside
+  int v, v1;
+  if (lane == 12) v = v1 = center;
+  else if (tq) v = v1 = ring1 ? F : tq;  // a neighbouring corner: its T (stored in fwin by nms_prefix)
+  else if (ring1) { v = st0 > 2 ? st0 : (F >= center ? F : 0); v1 = st1 > 2 ? st1 : (F >= center ? F : 0); }
+  else { v = st0; v1 = st1; }
+  if (__any_sync(kFull, pending && v != v1)) { __syncwarp(); return -1; }
   // binomial 3x3 sum centred on every lane's own pixel (meaningful for the inner 3x3 lanes)
   int sum = 0;
 #pragma unroll
@@ -107,82 +188,103 @@ __device__ __forceinline__ int warp_tie_decide(const LayerView& L, int mode, int
 #pragma unroll
     for (int wx = -1; wx <= 1; ++wx) {
       const int src = lane + wy * 5 + wx;
-      const int t = __shfl_sync(0xffffffffu, v, src & 31);
+      const int t = __shfl_sync(kFull, v, src & 31);
       sum += ((wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1)) * t;
     }
-  const int smoothed = __shfl_sync(0xffffffffu, sum, 12);
-  const bool inner = lane < 25 && ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1 && lane != 12;
+  const int smoothed = __shfl_sync(kFull, sum, 12);
+  const bool inner = lane < 25 && ring1 && lane != 12;
   const bool beaten = inner && v == center && sum > smoothed;
-  const int verdict = __any_sync(0xffffffffu, beaten) ? 0 : 1;
+  const int verdict = __any_sync(kFull, beaten) ? 0 : 1;
   __syncwarp();
   return verdict;
 }
 
+// mark_above1 spread over the lanes of a warp: the scan visits a (columns x rows) grid of positions
+// in row-major order -- columns x_1, the integers in (x_1, x1], x1; rows alike -- and `steps` of them
+// were evaluated; lane n replays position n.  (The footprint is uniform across the warp.)
+__device__ __forceinline__ void warp_mark_above(const LayerView& nb, int layer, int x, int y, int above_steps, int above_argmax) {
+  const int lane = threadIdx.x & 31;
+  float x_1, x1, y_1, y1;
+  above_patch(layer, x, y, &x_1, &x1, &y_1, &y1);
+  const int xb = (int)(x_1 + 1), xe = (int)x1, yb = (int)(y_1 + 1), ye = (int)y1;
+  const int ncols = imax(xe - xb + 1, 0) + 2, nrows = imax(ye - yb + 1, 0) + 2;
+  const int steps = above_steps & 0xff;
+  for (int n = lane; n < steps; n += 32) {
+    const int c = n % ncols, rr = n / ncols;
+    const bool xi = c > 0 && c < ncols - 1, yi = rr > 0 && rr < nrows - 1;
+    const float xf = c == 0 ? x_1 : (xi ? (float)(xb + c - 1) : x1);
+    const float yf = rr == 0 ? y_1 : (yi ? (float)(yb + rr - 1) : y1);
+    if (xi && yi) mark_px(nb, xb + c - 1, yb + rr - 1);
+    else mark_cell(nb, xf, yf);
+  }
+  if (((above_steps >> 8) & 1) && lane < 9) mark_px(nb, (above_argmax & 0xffff) + lane % 3 - 1, (above_argmax >> 16) + lane / 3 - 1);
+}
+
 // One CTA per frame, layers in order (layer i+1 needs the touch marks that layer i's accepted
-// corners leave on it).  Within a layer the tying corners are resolved in parallel rounds, one warp
-// per corner: a corner whose raster-earlier tying neighbours are all decided is decidable, whatever
-// the order.
+// corners leave on it).  Only the tying corners are handled here (nms_prefix_kernel listed them per
+// layer).  A layer is resolved in passes, one warp per corner: a corner whose verdict does not depend on
+// a pending one is decided and published (one 16-bit store; a concurrent reader may or may not see it,
+// both are fine), the others form the list of the next pass.  The raster-earliest pending corner is
+// always decidable, so every pass makes progress.
 constexpr int kChainThreads = 1024;
-__global__ void __launch_bounds__(kChainThreads)
+constexpr int kChainWarps = kChainThreads / 32;
+__global__ void __launch_bounds__(kChainThreads, 1)
 nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag) {
   __shared__ FrameViews fv;
-  __shared__ int s_left;
-  __shared__ uint16_t s_win[kChainThreads / 32][64];
+  __shared__ int s_next[2];
+  __shared__ uint16_t s_win[kChainWarps][64];
   const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) make_views(g, ws, frame, &fv);
-  __syncthreads();
   const int* ls = ws.layer_start + (long long)frame * (kMaxLayers + 1);
-  const uint32_t* corners = ws.corners + (long long)frame * ws.corner_cap;
+  if (ls[g.n_layers] > ws.corner_cap) return;  // corner list truncated: the call fails with BRISK_ERR_CAPACITY anyway
+  if (tid == 0) { make_views(g, ws, frame, &fv); s_next[0] = 0; s_next[1] = 0; }
+  __syncthreads();
+  // the key-point scratch of the frame is free until refine_kernel runs: it holds the tie lists (corner
+  // slot, x | y << 16; layer l's list starts at its first corner slot) and the lists of the next passes
+  int2* lists = reinterpret_cast<int2*>(ws.kp_tmp + (long long)frame * ws.corner_cap);
+  const long long fslot = (long long)frame * ws.corner_cap;
   for (int layer = 0; layer < g.n_layers; ++layer) {
     const int mode = g.n_layers == 1 ? kModeSingle : (layer == g.n_layers - 1 ? kModeLast : kModeMid);
-    const int begin = min(ls[layer], ws.corner_cap), end = min(ls[layer + 1], ws.corner_cap);
     const LayerView& L = fv.v[layer];
-    // collect this layer's tying (undecided) corners; the key-point scratch of the frame is free until
-    // refine_kernel runs and serves as the list
-    int* tie_list = reinterpret_cast<int*>(ws.kp_tmp + (long long)frame * ws.corner_cap);
-    if (tid == 0) s_left = 0;
-    __syncthreads();
-    for (int k = begin + tid; k < end; k += blockDim.x) {
-      int x, y, l2;
-      unpack_corner(corners[k], &x, &y, &l2);
-      if (!(L.cm[(long long)y * L.pitch + x] & kCmDecided)) tie_list[atomicAdd(&s_left, 1)] = k;
-    }
-    __syncthreads();
-    const int n_ties = s_left;
-    __syncthreads();
-    for (int round = 0; n_ties > 0; ++round) {
-      if (tid == 0) s_left = 0;
-      __syncthreads();
-      int left = 0;
-      for (int i = warp; i < n_ties; i += kChainThreads / 32) {
-        const int k = tie_list[i];
-        if (k < 0) continue;  // uniform across the warp
-        int x, y, l2;
-        unpack_corner(corners[k], &x, &y, &l2);
-        const int verdict = warp_tie_decide(L, mode, x, y, ws.fwin + ((long long)frame * ws.corner_cap + k) * 32, s_win[warp]);
-        if (verdict < 0) { ++left; continue; }
+    int n = ws.n_ties[frame * kMaxLayers + layer];
+    const int2* cur = lists + ls[layer];
+    for (int pass = 0; n > 0; ++pass) {
+      int2* nxt = lists + (1 + (pass & 1)) * (long long)ws.corner_cap;  // never the list being read
+      // software pipeline: the list entry is fetched two corners ahead, the corner's data one ahead
+      // (a window read early may miss a verdict of this pass: that can only defer the corner, never
+      // change its verdict, and everything decided in earlier passes is seen)
+      int2 ent = warp < n ? cur[warp] : make_int2(0, 0);
+      int2 ent1 = warp + kChainWarps < n ? cur[warp + kChainWarps] : make_int2(0, 0);
+      TieLoads ld;
+      if (warp < n) tie_issue_loads(L, mode, ent.y & 0xffff, ent.y >> 16, ws.fwin + (fslot + ent.x) * 32, ws.checks + (fslot + ent.x) * 8, &ld);
+      for (int i = warp; i < n; i += kChainWarps) {
+        TieLoads ld1;
+        int2 ent2 = make_int2(0, 0);
+        if (i + kChainWarps < n) tie_issue_loads(L, mode, ent1.y & 0xffff, ent1.y >> 16, ws.fwin + (fslot + ent1.x) * 32, ws.checks + (fslot + ent1.x) * 8, &ld1);
+        if (i + 2 * kChainWarps < n) ent2 = cur[i + 2 * kChainWarps];
+        const int x = ent.y & 0xffff, y = ent.y >> 16;
+        const int verdict = warp_tie_decide(L, mode, x, y, ld, s_win[warp]);
         if (lane == 0) {
-          uint16_t* e = L.cm + (long long)y * L.pitch + x;
-          *e = *e | (uint16_t)(kCmDecided | (verdict ? kCmAccept : 0));
-          tie_list[i] = -1;
+          if (verdict < 0) nxt[atomicAdd(&s_next[pass & 1], 1)] = ent;
+          else {
+            uint16_t* e = L.cm + (long long)y * L.pitch + x;
+            *e = s_win[warp][4 * 8 + 4] | (uint16_t)(kCmDecided | (verdict ? kCmAccept : 0));  // the window's centre is the corner's own entry
+          }
         }
+        // footprint of the accepted corner on the layer above
+        if (verdict > 0 && mode == kModeMid) warp_mark_above(fv.v[layer + 1], layer, x, y, ld.fp.x, ld.fp.y);
         __syncwarp();
+        ent = ent1; ent1 = ent2; ld = ld1;
       }
-      if (lane == 0 && left) atomicAdd(&s_left, left);
       __syncthreads();
-      const int remaining = s_left;
+      const int left = s_next[pass & 1];
+      if (tid == 0) s_next[(pass + 1) & 1] = 0;
       __syncthreads();
-      if (remaining == 0) { if (tid == 0) ws.rounds[frame * kMaxLayers + layer] = round + 1; break; }
-      if (round > (1 << 16)) { if (tid == 0) atomicExch(error_flag, 2); break; }  // cannot happen: dependencies are acyclic
-    }
-    // footprint of the accepted corners on the layer above
-    if (mode == kModeMid) {
-      for (int k = begin + tid; k < end; k += blockDim.x) {
-        int x, y, l2;
-        unpack_corner(corners[k], &x, &y, &l2);
-        if (L.cm[(long long)y * L.pitch + x] & kCmAccept)
-          mark_above(fv.v, layer, x, y, *reinterpret_cast<const CheckResult*>(ws.checks + ((long long)frame * ws.corner_cap + k) * 8));
+      if (left >= n) {  // no progress: cannot happen
+        if (tid == 0) { atomicExch(error_flag, 2); s_next[pass & 1] = 0; }
+        break;
       }
+      n = left;
+      cur = nxt;
     }
     __syncthreads();
   }
@@ -197,14 +299,13 @@ refine_kernel(PyramidGeom g, DetectWorkspace ws) {
   const long long slot = (long long)frame * ws.corner_cap + k;
   int x, y, layer;
   unpack_corner(ws.corners[slot], &x, &y, &layer);
-  FrameViews fv;
-  make_views(g, ws, frame, &fv);
-  const uint16_t e = fv.v[layer].cm[(long long)y * fv.v[layer].pitch + x];
+  const LayerView own = make_view(g, ws, frame, layer);
+  const uint16_t e = own.cm[(long long)y * own.pitch + x];
   bool valid = false;
   if ((e & kCmAccept) && (e & kCmChecks)) {
     const CheckResult r = *reinterpret_cast<const CheckResult*>(ws.checks + slot * 8);
     KeyPoint kp;
-    valid = refine_emit(fv.v, g.n_layers, layer, x, y, r, &kp);
+    valid = refine_emit1(own, g.n_layers, layer, x, y, r, &kp);
     if (valid) ws.kp_tmp[slot] = kp;
   }
   ws.kp_valid[slot] = valid ? 1 : 0;
@@ -269,12 +370,30 @@ cudaError_t launch_agast_nms(const PyramidGeom& g, const DetectWorkspace& ws, in
                              int* error_flag, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(ws.bm, 0, (size_t)n_frames * g.frame_elems, stream);
   if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(ws.n_ties, 0, (size_t)n_frames * kMaxLayers * sizeof(int), stream);
+  if (e != cudaSuccess) return e;
   dim3 grid((ws.corner_cap + 127) / 128, n_frames);
+  // BRISK_B200_NMS_TIMING=1: per-kernel CUDA-event times of this launch sequence on stderr (debug aid; synchronises)
+  static const bool timing = getenv("BRISK_B200_NMS_TIMING") != nullptr;
+  cudaEvent_t ev[6];
+  if (timing) { for (auto& v : ev) cudaEventCreate(&v); cudaEventRecord(ev[0], stream); }
   nms_prefix_kernel<<<grid, 128, 0, stream>>>(g, ws);
+  if (timing) cudaEventRecord(ev[1], stream);
   nms_checks_kernel<<<grid, 128, 0, stream>>>(g, ws);
+  if (timing) cudaEventRecord(ev[2], stream);
   nms_chain_kernel<<<n_frames, kChainThreads, 0, stream>>>(g, ws, error_flag);
+  if (timing) cudaEventRecord(ev[3], stream);
   refine_kernel<<<grid, 128, 0, stream>>>(g, ws);
+  if (timing) cudaEventRecord(ev[4], stream);
   compact_kernel<<<n_frames, 256, 0, stream>>>(g, ws, masks, mask_frame_stride, mask_pitch, out, counts, kp_cap);
+  if (timing) {
+    cudaEventRecord(ev[5], stream);
+    cudaStreamSynchronize(stream);
+    float ms[5];
+    for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    fprintf(stderr, "[nms %d frames] prefix %.3f checks %.3f chain %.3f refine %.3f compact %.3f ms\n", n_frames, ms[0], ms[1], ms[2], ms[3], ms[4]);
+    for (auto& v : ev) cudaEventDestroy(v);
+  }
   return cudaGetLastError();
 }
 

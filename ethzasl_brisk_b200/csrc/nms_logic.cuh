@@ -432,20 +432,20 @@ struct CheckResult {
 
 // Returns true when Refine3D (mid layers) / the last-layer branch of
 // GetKeypoints reaches its own-layer 3x3 patch.
-BRISK_HD bool nms_checks(const LayerView* layers, int n_layers, int layer, int x, int y, CheckResult* r,
-                         int* tile_violations = nullptr) {
-  const LayerView& L = layers[layer];
+// `below` / `above` are the neighbouring layers (ignored where the corner's layer has none).
+BRISK_HD bool nms_checks3(const LayerView& below, const LayerView& L, const LayerView& above, int n_layers, int layer, int x,
+                          int y, CheckResult* r, int* tile_violations = nullptr) {
   const int center = L.cm[(long long)y * L.pitch + x] & kCmT;
   r->max_above = 0; r->dxa = 0; r->dya = 0; r->max_below = 0; r->dxb = 0; r->dyb = 0;
   r->above_steps = 0; r->above_argmax = 0;
   if (n_layers == 1) return true;
   bool ismax;
   if (layer == n_layers - 1) {
-    r->max_below = score_max_below(layers[layer - 1], layer, x, y, center, &ismax, &r->dxb, &r->dyb, tile_violations);
+    r->max_below = score_max_below(below, layer, x, y, center, &ismax, &r->dxb, &r->dyb, tile_violations);
     return ismax;
   }
   AboveFootprint fp;
-  r->max_above = score_max_above(layers[layer + 1], layer, x, y, center, &ismax, &r->dxa, &r->dya, &fp, tile_violations);
+  r->max_above = score_max_above(above, layer, x, y, center, &ismax, &r->dxa, &r->dya, &fp, tile_violations);
   r->above_steps = fp.steps | (fp.completed << 8);
   r->above_argmax = fp.mx | (fp.my << 16);
   if (!ismax) return false;
@@ -459,8 +459,14 @@ BRISK_HD bool nms_checks(const LayerView* layers, int n_layers, int layer, int x
     r->max_below = (float)best;
     return true;
   }
-  r->max_below = score_max_below(layers[layer - 1], layer, x, y, center, &ismax, &r->dxb, &r->dyb, tile_violations);
+  r->max_below = score_max_below(below, layer, x, y, center, &ismax, &r->dxb, &r->dyb, tile_violations);
   return ismax;
+}
+
+BRISK_HD bool nms_checks(const LayerView* layers, int n_layers, int layer, int x, int y, CheckResult* r,
+                         int* tile_violations = nullptr) {
+  return nms_checks3(layers[layer > 0 ? layer - 1 : 0], layers[layer], layers[layer + 1 < n_layers ? layer + 1 : layer], n_layers,
+                     layer, x, y, r, tile_violations);
 }
 
 // ---------------------------------------------------------------------------
@@ -497,8 +503,13 @@ BRISK_HD bool load_tie_window(const LayerView& L, int cx, int cy, uint16_t* w, i
 }
 
 // Raw cache byte the reference would hold at pixel (qx,qy) just before corner
-// (cx,cy) runs IsMax2D.  F is the pixel's FAST score clipped at 0.
-BRISK_HD int cache_state(const LayerView& L, const TieWindow& W, int mode, int qx, int qy, int F, int cx, int cy) {
+// (cx,cy) runs IsMax2D.  F is the pixel's FAST score clipped at 0.  Raster-earlier
+// tying corners that are not decided yet count as rejected, or as accepted when
+// `assume_accept` is set; the result is monotone in those bits (an accepted corner
+// can only make a pixel sticky), so a value that is the same under both assumptions
+// does not depend on the pending decisions at all.
+BRISK_HD int cache_state(const LayerView& L, const TieWindow& W, int mode, int qx, int qy, int F, int cx, int cy,
+                         bool assume_accept = false) {
   if (in_border(L, qx, qy)) return 0;
   const int tq = W.at(qx, qy) & kCmT;
   if (tq) return tq;  // a detected corner holds its threshold-map value (> 2)
@@ -523,7 +534,7 @@ BRISK_HD int cache_state(const LayerView& L, const TieWindow& W, int mode, int q
           last = t;
         }
       }
-      if (e & kCmAccept) {
+      if ((e & kCmAccept) || (assume_accept && !(e & kCmDecided))) {
         bool touched;
         if (mode == kModeSingle) touched = true;                                       // 4x4 float-accessor patch
         else if (mode == kModeLast) touched = (ox >= 0 && oy >= 0 && ox <= 1 && oy <= 1) || (e & kCmChecks);  // 2x2 centre read, then 4x4 patch
@@ -539,51 +550,47 @@ BRISK_HD int cache_state(const LayerView& L, const TieWindow& W, int mode, int q
 // Value IsMax2D's tie path sees at offset (ox, oy) in [-2,2]^2 from the tying corner (x, y) once the
 // corner's own eight neighbour look-ups are done: its own score at the centre, the look-up results
 // s(q) on the 8 neighbours, raw cache bytes on the outer ring.  F = fwin entry of that pixel.
-BRISK_HD int tie_pixel_value(const LayerView& L, const TieWindow& W, int mode, int x, int y, int ox, int oy, int F, int center) {
+BRISK_HD int tie_pixel_value(const LayerView& L, const TieWindow& W, int mode, int x, int y, int ox, int oy, int F, int center,
+                             bool assume_accept = false) {
   if (ox == 0 && oy == 0) return center;
   const int qx = x + ox, qy = y + oy;
   if (ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1) {
     if (W.at(qx, qy) & kCmT) return F;  // neighbouring corner: its T (stored in fwin by nms_prefix)
-    const int st = cache_state(L, W, mode, qx, qy, F, x, y);
+    const int st = cache_state(L, W, mode, qx, qy, F, x, y, assume_accept);
     return st > 2 ? st : (F >= center ? F : 0);
   }
-  return cache_state(L, W, mode, qx, qy, F, x, y);
+  return cache_state(L, W, mode, qx, qy, F, x, y, assume_accept);
 }
 
 // IsMax2D verdict of the tying corner (x,y): 1 accept, 0 reject, -1 not yet
-// decidable (an earlier tying corner in its neighbourhood is still undecided).
-// Corners whose dependencies are all decided can be resolved in any order, or
-// concurrently: a decision is published with one 16-bit store.  `scratch` holds
-// 64 entries at `stride`.
+// decidable: one of the 25 values the tie path reads depends on whether a
+// raster-earlier tying corner of its neighbourhood, still undecided, will be
+// accepted.  (Most pending neighbours do not matter: their patch misses the
+// pixels read here, or those pixels are sticky / zero anyway.)  Decidable corners
+// can be resolved in any order, or concurrently: a decision is published with one
+// 16-bit store.  `scratch` holds 64 entries at `stride`.
 BRISK_HD int nms_tie_decide(const LayerView& L, int mode, int x, int y, const uint8_t fwin[25], uint16_t* scratch, int stride) {
-  if (load_tie_window(L, x, y, scratch, stride)) return -1;
+  const bool pending = load_tie_window(L, x, y, scratch, stride);
   const TieWindow W{scratch, stride, x - 4, y - 4};
   const int center = W.at(x, y) & kCmT;
-  int s[8];
-  for (int j = 0; j < 8; ++j) {
-    int dx, dy;
-    isMax2dOffset(j, &dx, &dy);
-    s[j] = tie_pixel_value(L, W, mode, x, y, dx, dy, fwin[(dy + 2) * 5 + dx + 2], center);
+  int v[25];
+  for (int i = 0; i < 25; ++i) {
+    const int ox = i % 5 - 2, oy = i / 5 - 2;
+    v[i] = tie_pixel_value(L, W, mode, x, y, ox, oy, fwin[i], center);
+    if (pending && tie_pixel_value(L, W, mode, x, y, ox, oy, fwin[i], center, true) != v[i]) return -1;
   }
-  const int smoothed = 4 * center + 2 * (s[0] + s[1] + s[2] + s[3]) + s[7] + s[6] + s[4] + s[5];
-  // ties in the reference's order: (-1,-1) (0,-1) (1,-1) (-1,0) (1,0) (-1,1) (0,1) (1,1)
-  for (int k = 0; k < 8; ++k) {
-    const int ty = (k < 3) ? -1 : (k < 5 ? 0 : 1);
-    const int tx = (k < 3) ? k - 1 : (k < 5 ? (k == 3 ? -1 : 1) : k - 6);
-    if (s[isMax2dIndex(tx, ty)] != center) continue;
-    int other = 0;
-    for (int wy = -1; wy <= 1; ++wy)
-      for (int wx = -1; wx <= 1; ++wx) {
-        const int ox = tx + wx, oy = ty + wy;  // offset from the corner, in [-2,2]^2
-        int v;
-        if (ox == 0 && oy == 0) v = center;
-        else if (ox >= -1 && ox <= 1 && oy >= -1 && oy <= 1) v = s[isMax2dIndex(ox, oy)];
-        else v = tie_pixel_value(L, W, mode, x, y, ox, oy, fwin[(oy + 2) * 5 + ox + 2], center);
-        const int wgt = (wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1);
-        other += wgt * v;
-      }
-    if (other > smoothed) return 0;
-  }
+  // 3x3 binomial sums (weights 4 / 2 / 1) around the centre and around every tying neighbour
+  int smoothed = 0;
+  for (int wy = -1; wy <= 1; ++wy)
+    for (int wx = -1; wx <= 1; ++wx) smoothed += ((wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1)) * v[(2 + wy) * 5 + 2 + wx];
+  for (int ty = -1; ty <= 1; ++ty)
+    for (int tx = -1; tx <= 1; ++tx) {
+      if ((tx == 0 && ty == 0) || v[(2 + ty) * 5 + 2 + tx] != center) continue;
+      int other = 0;
+      for (int wy = -1; wy <= 1; ++wy)
+        for (int wx = -1; wx <= 1; ++wx) other += ((wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1)) * v[(2 + ty + wy) * 5 + 2 + tx + wx];
+      if (other > smoothed) return 0;
+    }
   return 1;
 }
 
@@ -591,13 +598,16 @@ BRISK_HD int nms_tie_decide(const LayerView& L, int mode, int x, int y, const ui
 // Phase 4: cache footprint an accepted corner of `layer` leaves on the layer
 // above (its GetScoreMaxAbove look-ups), recorded in that layer's touch map.
 // ---------------------------------------------------------------------------
-BRISK_HD void mark_above(const LayerView* layers, int layer, int x, int y, const CheckResult& r) {
+BRISK_HD void mark_above1(const LayerView& above, int layer, int x, int y, const CheckResult& r) {
   float x_1, x1, y_1, y1;
   above_patch(layer, x, y, &x_1, &x1, &y_1, &y1);
   AboveFootprint fp;
   fp.steps = r.above_steps & 0xff; fp.completed = (r.above_steps >> 8) & 1;
   fp.mx = r.above_argmax & 0xffff; fp.my = r.above_argmax >> 16;
-  replay_scan_marks(layers[layer + 1], x_1, x1, y_1, y1, fp);
+  replay_scan_marks(above, x_1, x1, y_1, y1, fp);
+}
+BRISK_HD void mark_above(const LayerView* layers, int layer, int x, int y, const CheckResult& r) {
+  mark_above1(layers[layer + 1], layer, x, y, r);
 }
 
 // ---------------------------------------------------------------------------
@@ -605,9 +615,7 @@ BRISK_HD void mark_above(const LayerView* layers, int layer, int x, int y, const
 // checks, and the single / last-layer branches of GetKeypoints :172-256).
 // Returns false when the corner is discarded on the scale axis.
 // ---------------------------------------------------------------------------
-BRISK_HD bool refine_emit(const LayerView* layers, int n_layers, int layer, int x, int y, const CheckResult& r,
-                          KeyPoint* kp) {
-  const LayerView& L = layers[layer];
+BRISK_HD bool refine_emit1(const LayerView& L, int n_layers, int layer, int x, int y, const CheckResult& r, KeyPoint* kp) {
   float dxl, dyl;
   int s11;
   const float max_layer = patch3x3(L, x, y, &dxl, &dyl, &s11);
@@ -656,6 +664,10 @@ BRISK_HD bool refine_emit(const LayerView* layers, int n_layers, int layer, int 
   kp->size = 12.0f * (scale * L.scale);
   kp->response = max;
   return true;
+}
+BRISK_HD bool refine_emit(const LayerView* layers, int n_layers, int layer, int x, int y, const CheckResult& r,
+                          KeyPoint* kp) {
+  return refine_emit1(layers[layer], n_layers, layer, x, y, r, kp);
 }
 
 }  // namespace briskb200

@@ -131,8 +131,8 @@ int brisk_debug_scores(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_t 
 int brisk_debug_nms_state(brisk_ctx* ctx, brisk_detector* det, const uint8_t* img, int w, int h, size_t stride,
                           uint16_t* cm_out, uint8_t* bm_out);
 
-/* Diagnostic: parallel tie-resolution rounds per layer, frame 0 of the last detect call. */
-int brisk_debug_nms_rounds(brisk_ctx* ctx, int32_t* rounds);
+/* Diagnostic: corners per layer (up to 12) that went through IsMax2D's tie path, frame 0 of the last detect call. */
+int brisk_debug_nms_ties(brisk_ctx* ctx, int32_t* ties);
 
 /* brisk::Hamming::operator()(a, b, size) -- reference brisk/include/brisk/internal/hamming.h:101-113:
  * dist[i] = popcount(a[i] xor b[i]) over n descriptor pairs of desc_bytes each. */

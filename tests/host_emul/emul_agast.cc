@@ -93,22 +93,26 @@ extern "C" int emul_agast_detect_ex(const uint8_t* image, int w, int h, int thre
       if (violations != v0 && getenv("EMUL_DEBUG")) fprintf(stderr, "tile violation: layer %d corner (%d,%d) +%d\n", i, H[i].cx[k], H[i].cy[k], violations - v0);  // chk kept either way: footprint
     }
   if (violations) return -200;  // a scan looked outside its score tile
-  // phase 3 + 4 (per frame: layers in order).  Ties are resolved in rounds, visiting the undecided
-  // corners in REVERSE raster order to show that any order that respects the dependencies works.
+  // phase 3 + 4 (per frame: layers in order).
   for (int i = 0; i < n; ++i) {
     const int mode = n == 1 ? kModeSingle : (i == n - 1 ? kModeLast : kModeMid);
-    for (bool progress = true, left = true; left;) {
-      if (!progress) return -100;  // dependency cycle: must never happen
-      progress = false; left = false;
+    // Passes as the GPU runs them: every undecided corner is evaluated against the SAME snapshot of the
+    // corner map (a parallel pass), then the verdicts are published.
+    for (int pass = 0;; ++pass) {
+      std::vector<std::pair<size_t, int>> verdicts;
+      size_t left = 0;
       for (size_t kk = H[i].cx.size(); kk-- > 0;) {
-        uint16_t& e = H[i].cm[(size_t)H[i].cy[kk] * H[i].pitch + H[i].cx[kk]];
+        const uint16_t e = H[i].cm[(size_t)H[i].cy[kk] * H[i].pitch + H[i].cx[kk]];
         if (e & kCmDecided) continue;
         uint16_t scratch[64];
         const int verdict = nms_tie_decide(V[i], mode, H[i].cx[kk], H[i].cy[kk], &fwin[i][kk * 25], scratch, 1);
-        if (verdict < 0) { left = true; continue; }
-        e |= (uint16_t)(kCmDecided | (verdict ? kCmAccept : 0));
-        progress = true;
+        if (verdict < 0) { ++left; continue; }
+        verdicts.emplace_back(kk, verdict);
       }
+      for (auto& kv : verdicts) H[i].cm[(size_t)H[i].cy[kv.first] * H[i].pitch + H[i].cx[kv.first]] |= (uint16_t)(kCmDecided | (kv.second ? kCmAccept : 0));
+      if (getenv("EMUL_DEBUG")) fprintf(stderr, "layer %d pass %d: decided %zu, left %zu\n", i, pass, verdicts.size(), left);
+      if (!left) break;
+      if (verdicts.empty()) return -100;  // no progress: must never happen
     }
     if (mode == kModeMid)
       for (size_t k = 0; k < H[i].cx.size(); ++k) {

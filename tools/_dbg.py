@@ -7,6 +7,6 @@ img = bb.synthetic_frame(1920,1080,2000)
 det = bb.BriskFeatureDetector(60,4,ctx=ctx)
 for i in range(3):
     k = det.detect(img)
-    r = np.zeros(12,np.int32); ctx._lib.brisk_debug_nms_rounds(ctx._h,_ptr(r))
-    print(len(k), 'rounds per layer', r[:8], {a:round(b,3) for a,b in ctx.last_timing()[0].items() if b>0})
+    r = np.zeros(12,np.int32); ctx._lib.brisk_debug_nms_ties(ctx._h,_ptr(r))
+    print(len(k), 'ties per layer', r[:8], {a:round(b,3) for a,b in ctx.last_timing()[0].items() if b>0})
 c,lc = det.debug_corners(img); print('corners per layer', lc[:8])
