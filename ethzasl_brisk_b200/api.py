@@ -353,23 +353,43 @@ class Hamming:
 
 
 class BruteForceMatcher:
-    """brisk::BruteForceMatcher: brute-force Hamming kNN (one train collection, no masks)."""
+    """brisk::BruteForceMatcher (reference brisk/include/brisk/brute-force-matcher.h:54-94): brute-force Hamming
+    kNN / radius matching against a train collection, with the cv::DescriptorMatcher conventions the
+    reference implements in brisk/src/brute-force-matcher.cc:80-214 (masks, several train images,
+    compactResult, result order)."""
 
     def __init__(self, distance=None, ctx=None):
         self.ctx = ctx or (distance.ctx if distance is not None else default_context())
         self._train = []
 
     def isMaskSupported(self):
-        return False  # masks: SURVEY.md 8(f), not in this round
+        return True  # brute-force-matcher.h:60-62
 
     def add(self, descriptors):
-        self._train.append(np.ascontiguousarray(descriptors, np.uint8))
+        """cv::DescriptorMatcher::add: one descriptor matrix, or a list of them (one per train image)."""
+        if isinstance(descriptors, (list, tuple)):
+            self._train.extend(np.ascontiguousarray(d, np.uint8) for d in descriptors)
+        else:
+            self._train.append(np.ascontiguousarray(descriptors, np.uint8))
 
     def clear(self):
         self._train = []
 
-    def knn(self, query, train, k):
-        """-> (idx [nq,k] int32, dist [nq,k] int32); query/train: numpy u8 [n, bytes] or torch CUDA tensors."""
+    def getTrainDescriptors(self):
+        return self._train
+
+    def empty(self):
+        return not self._train
+
+    def clone(self, emptyTrainData=False):
+        m = BruteForceMatcher(ctx=self.ctx)
+        if not emptyTrainData:
+            m._train = [t.copy() for t in self._train]
+        return m
+
+    def knn(self, query, train, k, mask=None):
+        """-> (idx [nq,k] int32, dist [nq,k] int32); query/train: numpy u8 [n, bytes] or torch CUDA tensors;
+        mask: optional [nq, nt] u8, 0 = pair excluded.  Missing neighbours are -1."""
         nq, nb = query.shape
         nt = train.shape[0]
         if _is_torch(query):
@@ -381,15 +401,123 @@ class BruteForceMatcher:
             train = np.ascontiguousarray(train, np.uint8)
             idx = np.zeros((nq, k), np.int32)
             dist = np.zeros((nq, k), np.int32)
-        self.ctx._check(self.ctx._lib.brisk_hamming_knn(self.ctx._h, _ptr(query), C.c_int64(nq), _ptr(train), C.c_int64(nt), int(nb), int(k),
-                                                        _ptr(idx), _ptr(dist)))
+        if mask is None:
+            rc = self.ctx._lib.brisk_hamming_knn(self.ctx._h, _ptr(query), C.c_int64(nq), _ptr(train), C.c_int64(nt), int(nb), int(k),
+                                                 _ptr(idx), _ptr(dist))
+        else:
+            if not _is_torch(mask):
+                mask = np.ascontiguousarray(mask, np.uint8)
+            assert tuple(mask.shape) == (nq, nt)
+            rc = self.ctx._lib.brisk_hamming_knn_masked(self.ctx._h, _ptr(query), C.c_int64(nq), _ptr(train), C.c_int64(nt), int(nb), int(k),
+                                                        _ptr(mask), _ptr(idx), _ptr(dist))
+        self.ctx._check(rc)
         return idx, dist
 
-    def knnMatch(self, queryDescriptors, trainDescriptors=None, k=1):
-        """cv::DescriptorMatcher::knnMatch -> list (per query) of (queryIdx, trainIdx, imgIdx, distance) tuples."""
-        train = trainDescriptors if trainDescriptors is not None else np.concatenate(self._train)
-        idx, dist = self.knn(np.ascontiguousarray(queryDescriptors, np.uint8), train, k)
-        return [[(qi, int(i), 0, float(d)) for i, d in zip(idx[qi], dist[qi]) if i >= 0] for qi in range(len(idx))]
+    def radius(self, query, train, maxDistance, mask=None, sort=True):
+        """-> (offsets [nq+1] int64, idx, dist): the matches of query i are idx/dist[offsets[i]:offsets[i+1]], in the
+        reference's order (sort=True) or in train order.  numpy in / numpy out."""
+        query = np.ascontiguousarray(query, np.uint8)
+        train = np.ascontiguousarray(train, np.uint8).reshape(-1, query.shape[1])
+        nq, nb = query.shape
+        nt = train.shape[0]
+        if mask is not None:
+            mask = np.ascontiguousarray(mask, np.uint8)
+            assert mask.shape == (nq, nt)
+        offsets = np.zeros(nq + 1, np.int64)
+        cap = max(1024, 4 * nq)
+        while True:
+            idx = np.zeros(cap, np.int32)
+            dist = np.zeros(cap, np.int32)
+            rc = self.ctx._lib.brisk_hamming_radius(self.ctx._h, _ptr(query), C.c_int64(nq), _ptr(train), C.c_int64(nt), int(nb),
+                                                    C.c_float(maxDistance), _ptr(mask) if mask is not None else None, int(bool(sort)),
+                                                    _ptr(offsets), _ptr(idx), _ptr(dist), C.c_int64(cap))
+            if rc == -4 and offsets[nq] > cap:  # BRISK_ERR_CAPACITY: offsets[nq] is the size needed
+                cap = int(offsets[nq])
+                continue
+            self.ctx._check(rc)
+            n = int(offsets[nq])
+            return offsets, idx[:n], dist[:n]
+
+    # --- cv::DescriptorMatcher surface ---
+    def _collection(self, query, trainDescriptors, masks):
+        query = np.ascontiguousarray(query, np.uint8)
+        trains = [np.ascontiguousarray(trainDescriptors, np.uint8)] if trainDescriptors is not None else self._train
+        trains = [t.reshape(-1, query.shape[1]) for t in trains]
+        start = np.concatenate([[0], np.cumsum([len(t) for t in trains])]).astype(np.int64)
+        train = np.concatenate(trains) if trains else np.zeros((0, query.shape[1]), np.uint8)
+        mask = None
+        masked_out = np.zeros(len(query), bool)
+        if masks is not None and not isinstance(masks, (list, tuple)):
+            masks = [masks]
+        if masks:
+            assert len(masks) == len(trains)
+            cols = []
+            every_mask_given = True
+            for m, t in zip(masks, trains):
+                if m is None or np.size(m) == 0:
+                    cols.append(np.ones((len(query), len(t)), np.uint8))
+                    every_mask_given = False
+                else:
+                    cols.append((np.asarray(m).reshape(len(query), len(t)) != 0).astype(np.uint8))
+            mask = np.ascontiguousarray(np.concatenate(cols, axis=1))
+            if every_mask_given:  # cv::DescriptorMatcher::isMaskedOut
+                masked_out = np.array([all(not c[q].any() for c in cols) for q in range(len(query))], bool)
+        return query, trains, train, start, mask, masked_out
+
+    def knnMatch(self, queryDescriptors, trainDescriptors=None, k=1, masks=None, compactResult=False):
+        """cv::DescriptorMatcher::knnMatch -> list (per query) of (queryIdx, trainIdx, imgIdx, distance) tuples,
+        as BruteForceMatcher::commonKnnMatchImpl returns them (brute-force-matcher.cc:80-162)."""
+        query, trains, train, start, mask, masked_out = self._collection(queryDescriptors, trainDescriptors, masks)
+        out = []
+        if len(query) == 0:
+            return out
+        nonempty = [i for i, t in enumerate(trains) if len(t)]
+        if not nonempty:
+            return [[] for q in range(len(query)) if not (compactResult and masked_out[q])]
+        idx, dist = self.knn(query, train, k, mask)  # k <= 8: the kernels keep up to 8 candidates per query
+        for q in range(len(query)):
+            if masked_out[q]:
+                if not compactResult:
+                    out.append([])
+                continue
+            cur = []
+            for g, d in zip(idx[q], dist[q]):
+                if g >= 0:
+                    img = int(np.searchsorted(start, g, side="right") - 1)
+                    cur.append((q, int(g - start[img]), img, float(d)))
+                else:
+                    # the reference keeps selecting once the real candidates have run out: every entry holds INT_MAX,
+                    # minMaxLoc returns location 0 and INT_MAX (as double) is below the float it was just rounded to,
+                    # so the last non-empty image wins (brute-force-matcher.cc:138-157)
+                    cur.append((q, 0, nonempty[-1], 2147483648.0))
+            out.append(cur)
+        return out
+
+    def radiusMatch(self, queryDescriptors, trainDescriptors=None, maxDistance=0.0, masks=None, compactResult=False):
+        """cv::DescriptorMatcher::radiusMatch -> as knnMatch; BruteForceMatcher::commonRadiusMatchImpl
+        (brute-force-matcher.cc:164-214): distance < maxDistance, sorted by distance the way std::sort leaves them."""
+        query, trains, train, start, mask, masked_out = self._collection(queryDescriptors, trainDescriptors, masks)
+        if len(query) == 0:
+            return []
+        if len(train) == 0:
+            return [[] for q in range(len(query)) if not (compactResult and masked_out[q])]
+        offsets, idx, dist = self.radius(query, train, maxDistance, mask, sort=True)
+        out = []
+        for q in range(len(query)):
+            if masked_out[q]:
+                if not compactResult:
+                    out.append([])
+                continue
+            cur = []
+            for g, d in zip(idx[offsets[q]:offsets[q + 1]], dist[offsets[q]:offsets[q + 1]]):
+                img = int(np.searchsorted(start, g, side="right") - 1)
+                cur.append((q, int(g - start[img]), img, float(d)))
+            out.append(cur)
+        return out
+
+    def match(self, queryDescriptors, trainDescriptors=None, masks=None):
+        """cv::DescriptorMatcher::match: knnMatch(k=1, compactResult=true), flattened."""
+        return [m for ms in self.knnMatch(queryDescriptors, trainDescriptors, 1, masks, True) for m in ms]
 
     # --- train set sharded across GPUs: local keys, caller exchanges them (NCCL all-gather), merge ---
     def knn_keys(self, query, train_shard, k, global_offset, keys_out):

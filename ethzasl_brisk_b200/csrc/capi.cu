@@ -69,7 +69,7 @@ struct brisk_ctx {
   cudaEvent_t entry = nullptr;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   Slot slots[2];
-  DevBuf knn_q, knn_t, knn_keys, knn_part, knn_idx, knn_dist;
+  DevBuf knn_q, knn_t, knn_keys, knn_part, knn_idx, knn_dist, knn_mask, rad_counts, rad_offsets, rad_matches;
 };
 
 struct brisk_detector {
@@ -545,7 +545,8 @@ void brisk_ctx_destroy(brisk_ctx* ctx) {
     if (sl.h_counts) cudaFreeHost(sl.h_counts);
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
-  DevBuf* bufs[] = {&ctx->knn_q, &ctx->knn_t, &ctx->knn_keys, &ctx->knn_part, &ctx->knn_idx, &ctx->knn_dist};
+  DevBuf* bufs[] = {&ctx->knn_q, &ctx->knn_t, &ctx->knn_keys, &ctx->knn_part, &ctx->knn_idx, &ctx->knn_dist,
+                    &ctx->knn_mask, &ctx->rad_counts, &ctx->rad_offsets, &ctx->rad_matches};
   for (DevBuf* b : bufs) b->release();
   if (ctx->entry) cudaEventDestroy(ctx->entry);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -891,6 +892,91 @@ int brisk_hamming_knn(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const ui
   int rc = knn_keys_impl(ctx, query, nq, train, nt, desc_bytes, k, 0, &keys, &kr);
   if (rc) return rc;
   return knn_emit(ctx, keys, nq, kr, k, idx, dist);
+}
+
+// query / train / mask staged on the device (16-byte aligned rows) for the masked and radius paths
+static int stage_match_inputs(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int desc_bytes,
+                              const uint8_t* mask, const uint8_t** dq, const uint8_t** dt, const uint8_t** dm) {
+  if (!query || !train || nq < 0 || nt < 0) return fail(ctx, BRISK_ERR_INVALID, "bad matcher arguments");
+  if (desc_bytes != 48 && desc_bytes != 64 && desc_bytes != 128) return fail(ctx, BRISK_ERR_UNSUPPORTED, "descriptor size must be 48, 64 or 128 bytes");
+  if (nt > 0x7fffffffll) return fail(ctx, BRISK_ERR_UNSUPPORTED, "train index does not fit 31 bits");
+  CU_OK(cudaSetDevice(ctx->device));
+  *dq = query; *dt = train; *dm = mask;
+  if (!is_device_ptr(query) || (uintptr_t)query % 16) {
+    CU_OK(ctx->knn_q.ensure(std::max<size_t>((size_t)nq * desc_bytes, 16)));
+    CU_OK(cudaMemcpyAsync(ctx->knn_q.p, query, (size_t)nq * desc_bytes, cudaMemcpyDefault, ctx->stream));
+    *dq = ctx->knn_q.as<uint8_t>();
+  }
+  if (!is_device_ptr(train) || (uintptr_t)train % 16) {
+    CU_OK(ctx->knn_t.ensure(std::max<size_t>((size_t)nt * desc_bytes, 16)));
+    CU_OK(cudaMemcpyAsync(ctx->knn_t.p, train, (size_t)nt * desc_bytes, cudaMemcpyDefault, ctx->stream));
+    *dt = ctx->knn_t.as<uint8_t>();
+  }
+  if (mask && !is_device_ptr(mask)) {
+    CU_OK(ctx->knn_mask.ensure(std::max<size_t>((size_t)nq * nt, 16)));
+    CU_OK(cudaMemcpyAsync(ctx->knn_mask.p, mask, (size_t)nq * nt, cudaMemcpyDefault, ctx->stream));
+    *dm = ctx->knn_mask.as<uint8_t>();
+  }
+  return BRISK_OK;
+}
+
+int brisk_hamming_knn_masked(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int desc_bytes,
+                             int k, const uint8_t* mask, int32_t* idx, int32_t* dist) {
+  if (!ctx) return BRISK_ERR_INVALID;
+  if (!mask) return brisk_hamming_knn(ctx, query, nq, train, nt, desc_bytes, k, idx, dist);
+  if (k < 1 || k > 8) return fail(ctx, BRISK_ERR_INVALID, "bad kNN arguments (1 <= k <= 8)");
+  const uint8_t *dq, *dt, *dm;
+  int rc = stage_match_inputs(ctx, query, nq, train, nt, desc_bytes, mask, &dq, &dt, &dm);
+  if (rc) return rc;
+  const int kr = knn_round_k(k);
+  CU_OK(ctx->knn_keys.ensure(std::max<size_t>((size_t)nq * kr * 8, 16)));
+  if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
+  CU_OK(launch_hamming_knn_masked(dq, nq, dt, nt, desc_bytes, k, dm, ctx->knn_keys.as<unsigned long long>(), ctx->stream));
+  if (ctx->timing) cudaEventRecord(ctx->ev[1], ctx->stream);
+  ctx->launches = 1;
+  return knn_emit(ctx, ctx->knn_keys.as<unsigned long long>(), nq, kr, k, idx, dist);
+}
+
+int brisk_hamming_radius(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int desc_bytes,
+                         float max_distance, const uint8_t* mask, int sort, int64_t* offsets, int32_t* idx, int32_t* dist,
+                         int64_t capacity) {
+  if (!ctx) return BRISK_ERR_INVALID;
+  if (!offsets || capacity < 0 || (capacity > 0 && (!idx || !dist))) return fail(ctx, BRISK_ERR_INVALID, "bad radius-match arguments");
+  const uint8_t *dq, *dt, *dm;
+  int rc = stage_match_inputs(ctx, query, nq, train, nt, desc_bytes, mask, &dq, &dt, &dm);
+  if (rc) return rc;
+  CU_OK(ctx->rad_counts.ensure(std::max<size_t>((size_t)nq * 8, 16)));
+  CU_OK(ctx->rad_offsets.ensure((size_t)(nq + 1) * 8));
+  long long* d_off = ctx->rad_offsets.as<long long>();
+  if (nq == 0) CU_OK(cudaMemsetAsync(d_off, 0, 8, ctx->stream));
+  if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
+  CU_OK(launch_hamming_radius(0, dq, nq, dt, nt, desc_bytes, max_distance, dm, ctx->rad_counts.as<long long>(), d_off, nullptr, 0, 0, ctx->stream));
+  long long total = 0;
+  CU_OK(cudaMemcpyAsync(&total, d_off + nq, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_OK(cudaStreamSynchronize(ctx->stream));
+  ctx->launches = 2;
+  const long long emit = std::min<long long>(total, capacity);
+  if (emit > 0) {
+    CU_OK(ctx->rad_matches.ensure((size_t)emit * 8));
+    CU_OK(launch_hamming_radius(1, dq, nq, dt, nt, desc_bytes, max_distance, dm, nullptr, d_off, ctx->rad_matches.p, emit,
+                                total <= capacity ? sort : 0, ctx->stream));
+    CU_OK(ctx->knn_idx.ensure((size_t)emit * 4));
+    CU_OK(ctx->knn_dist.ensure((size_t)emit * 4));
+    CU_OK(launch_radius_unpack(ctx->rad_matches.p, emit, ctx->knn_idx.as<int32_t>(), ctx->knn_dist.as<int32_t>(), ctx->stream));
+    ctx->launches += sort ? 3 : 2;
+    CU_OK(cudaMemcpyAsync(idx, ctx->knn_idx.p, (size_t)emit * 4, cudaMemcpyDefault, ctx->stream));
+    CU_OK(cudaMemcpyAsync(dist, ctx->knn_dist.p, (size_t)emit * 4, cudaMemcpyDefault, ctx->stream));
+  }
+  if (ctx->timing) cudaEventRecord(ctx->ev[1], ctx->stream);
+  CU_OK(cudaMemcpyAsync(offsets, d_off, (size_t)(nq + 1) * 8, cudaMemcpyDefault, ctx->stream));
+  CU_OK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->timing) {
+    float ms = 0;
+    memset(ctx->ms, 0, sizeof(ctx->ms));
+    if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->ms[BRISK_STAGE_KNN] = ms; else cudaGetLastError();
+  }
+  if (total > capacity) return fail(ctx, BRISK_ERR_CAPACITY, "more radius matches than the output capacity; offsets[nq] holds the number needed");
+  return BRISK_OK;
 }
 
 int brisk_hamming_knn_keys(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train_shard, int64_t nt,

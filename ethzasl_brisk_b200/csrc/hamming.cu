@@ -11,6 +11,7 @@
 // reference's tie rule (first minimum of a left-to-right scan wins).
 #include <cuda_runtime.h>
 
+#include "gcc_sort.cuh"
 #include "kernels.h"
 
 namespace briskb200 {
@@ -31,10 +32,13 @@ __device__ __forceinline__ void topk_insert(unsigned long long (&best)[K], unsig
   }
 }
 
-template <int WORDS, int K>
+// MASKED: `mask` is the [nq][nt] byte matrix of DescriptorMatcher's masks (0 = pair not allowed,
+// brute-force-matcher.cc:118-119); excluded pairs never become candidates.
+template <int WORDS, int K, bool MASKED = false>
 __global__ void __launch_bounds__(kKnnThreads)
 hamming_knn_kernel(const uint32_t* __restrict__ q, long long nq, const uint32_t* __restrict__ t, long long nt,
-                   long long rows_per_split, long long train_index_offset, unsigned long long* __restrict__ part) {
+                   long long rows_per_split, long long train_index_offset, unsigned long long* __restrict__ part,
+                   const uint8_t* __restrict__ mask = nullptr) {
   __shared__ __align__(16) uint32_t s_t[kKnnTile * WORDS];
   const int tid = threadIdx.x;
   const long long q0 = ((long long)blockIdx.x * kKnnThreads + tid) * kKnnQPerThread;
@@ -68,8 +72,8 @@ hamming_knn_kernel(const uint32_t* __restrict__ q, long long nq, const uint32_t*
         db += __popc(qb[4 * c] ^ v.x) + __popc(qb[4 * c + 1] ^ v.y) + __popc(qb[4 * c + 2] ^ v.z) + __popc(qb[4 * c + 3] ^ v.w);
       }
       const unsigned long long idx = (unsigned long long)(train_index_offset + base + r);
-      topk_insert<K>(ba, ((unsigned long long)(uint32_t)da << 32) | idx);
-      topk_insert<K>(bb, ((unsigned long long)(uint32_t)db << 32) | idx);
+      if (!MASKED || (q0 < nq && mask[q0 * nt + base + r])) topk_insert<K>(ba, ((unsigned long long)(uint32_t)da << 32) | idx);
+      if (!MASKED || (q0 + 1 < nq && mask[(q0 + 1) * nt + base + r])) topk_insert<K>(bb, ((unsigned long long)(uint32_t)db << 32) | idx);
     }
   }
   unsigned long long* out = part + (long long)blockIdx.y * nq * K;
@@ -126,6 +130,165 @@ static cudaError_t launch_knn_words(const uint8_t* q, long long nq, const uint8_
     case 3: case 4: hamming_knn_kernel<WORDS, 4><<<grid, kKnnThreads, 0, stream>>>(q32, nq, t32, nt, rows_per_split, off, dst); break;
     default: hamming_knn_kernel<WORDS, 8><<<grid, kKnnThreads, 0, stream>>>(q32, nq, t32, nt, rows_per_split, off, dst); break;
   }
+  return cudaGetLastError();
+}
+
+template <int WORDS>
+static cudaError_t launch_knn_masked_words(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int k, const uint8_t* mask,
+                                           unsigned long long* keys, cudaStream_t stream) {
+  dim3 grid((unsigned)((nq + kKnnThreads * kKnnQPerThread - 1) / (kKnnThreads * kKnnQPerThread)), 1);
+  const uint32_t* q32 = reinterpret_cast<const uint32_t*>(q);
+  const uint32_t* t32 = reinterpret_cast<const uint32_t*>(t);
+  const long long rows = (nt + kKnnTile - 1) / kKnnTile * kKnnTile;
+  switch (k) {
+    case 1: hamming_knn_kernel<WORDS, 1, true><<<grid, kKnnThreads, 0, stream>>>(q32, nq, t32, nt, rows, 0, keys, mask); break;
+    case 2: hamming_knn_kernel<WORDS, 2, true><<<grid, kKnnThreads, 0, stream>>>(q32, nq, t32, nt, rows, 0, keys, mask); break;
+    case 3: case 4: hamming_knn_kernel<WORDS, 4, true><<<grid, kKnnThreads, 0, stream>>>(q32, nq, t32, nt, rows, 0, keys, mask); break;
+    default: hamming_knn_kernel<WORDS, 8, true><<<grid, kKnnThreads, 0, stream>>>(q32, nq, t32, nt, rows, 0, keys, mask); break;
+  }
+  return cudaGetLastError();
+}
+
+// kNN with a [nq][nt] byte mask; keys [nq][knn_round_k(k)].
+cudaError_t launch_hamming_knn_masked(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes, int k,
+                                      const uint8_t* mask, unsigned long long* keys, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  const int kr = knn_round_k(k);
+  switch (desc_bytes) {
+    case 48: return launch_knn_masked_words<12>(q, nq, t, nt, kr, mask, keys, stream);
+    case 64: return launch_knn_masked_words<16>(q, nq, t, nt, kr, mask, keys, stream);
+    case 128: return launch_knn_masked_words<32>(q, nq, t, nt, kr, mask, keys, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// radiusMatch: BruteForceMatcher::commonRadiusMatchImpl (reference
+// brisk/src/brute-force-matcher.cc:164-214).  Two sweeps with the same tiling
+// as the kNN kernel, one thread per query: count the train rows with
+// (float)d < maxDistance (and an allowing mask byte), prefix-sum the counts, then
+// emit (train index, distance) pairs in train order -- the order in which the
+// reference pushes them -- and finally std::sort each query's list by distance the
+// way libstdc++ does (gcc_sort.cuh: equal distances keep the reference's order).
+// ---------------------------------------------------------------------------
+struct RadiusMatch { int idx, dist; };
+struct RadiusLess { BRISK_HD bool operator()(const RadiusMatch& a, const RadiusMatch& b) const { return a.dist < b.dist; } };
+
+template <int WORDS, bool EMIT>
+__global__ void __launch_bounds__(kKnnThreads)
+hamming_radius_kernel(const uint32_t* __restrict__ q, long long nq, const uint32_t* __restrict__ t, long long nt, float max_distance,
+                      const uint8_t* __restrict__ mask, long long* __restrict__ counts, const long long* __restrict__ offsets,
+                      RadiusMatch* __restrict__ out, long long capacity) {
+  __shared__ __align__(16) uint32_t s_t[kKnnTile * WORDS];
+  const int tid = threadIdx.x;
+  const long long qi = (long long)blockIdx.x * kKnnThreads + tid;
+  uint32_t qa[WORDS];
+#pragma unroll
+  for (int i = 0; i < WORDS; ++i) qa[i] = qi < nq ? q[qi * WORDS + i] : 0u;
+  long long n = 0;
+  const long long o = EMIT && qi < nq ? offsets[qi] : 0;
+  for (long long base = 0; base < nt; base += kKnnTile) {
+    const int rows = (int)min((long long)kKnnTile, nt - base);
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(t + base * WORDS);
+    uint4* dst = reinterpret_cast<uint4*>(s_t);
+    for (int i = tid; i < rows * (WORDS / 4); i += kKnnThreads) dst[i] = src[i];
+    __syncthreads();
+    if (qi >= nq) continue;
+    for (int r = 0; r < rows; ++r) {
+      const uint4* row = reinterpret_cast<const uint4*>(s_t + r * WORDS);
+      int d = 0;
+#pragma unroll
+      for (int c = 0; c < WORDS / 4; ++c) {
+        const uint4 v = row[c];
+        d += __popc(qa[4 * c] ^ v.x) + __popc(qa[4 * c + 1] ^ v.y) + __popc(qa[4 * c + 2] ^ v.z) + __popc(qa[4 * c + 3] ^ v.w);
+      }
+      if ((float)d < max_distance && (!mask || mask[qi * nt + base + r])) {
+        if (EMIT && o + n < capacity) out[o + n] = RadiusMatch{(int)(base + r), d};
+        ++n;
+      }
+    }
+  }
+  if (!EMIT && qi < nq) counts[qi] = n;
+}
+
+// exclusive prefix sum of counts[n] into offsets[n + 1] (one CTA; n is a query count)
+__global__ void __launch_bounds__(1024)
+radius_scan_kernel(const long long* __restrict__ counts, long long n, long long* __restrict__ offsets) {
+  __shared__ long long s_warp[32];
+  __shared__ long long s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (long long base = 0; base < n; base += 1024) {
+    const long long i = base + tid;
+    const long long v = i < n ? counts[i] : 0;
+    long long x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const long long y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    long long before = s_carry;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (i < n) offsets[i] = before + x - v;
+    __syncthreads();
+    if (tid == 1023) s_carry = before + x;
+    __syncthreads();
+  }
+  if (tid == 0) offsets[n] = s_carry;
+}
+
+__global__ void __launch_bounds__(128)
+radius_sort_kernel(RadiusMatch* __restrict__ m, const long long* __restrict__ offsets, long long nq, long long capacity) {
+  const long long qi = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  const long long b = offsets[qi], e = offsets[qi + 1];
+  if (e > capacity || e - b < 2) return;
+  gs_sort(RadiusLess(), m + b, (int)(e - b));
+}
+
+__global__ void __launch_bounds__(256)
+radius_unpack_kernel(const RadiusMatch* __restrict__ m, long long n, int32_t* __restrict__ idx, int32_t* __restrict__ dist) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  idx[i] = m[i].idx; dist[i] = m[i].dist;
+}
+
+template <int WORDS>
+static cudaError_t radius_words(int phase, const uint8_t* q, long long nq, const uint8_t* t, long long nt, float max_distance,
+                                const uint8_t* mask, long long* counts, long long* offsets, RadiusMatch* out, long long capacity,
+                                cudaStream_t stream) {
+  const unsigned grid = (unsigned)((nq + kKnnThreads - 1) / kKnnThreads);
+  const uint32_t* q32 = reinterpret_cast<const uint32_t*>(q);
+  const uint32_t* t32 = reinterpret_cast<const uint32_t*>(t);
+  if (phase == 0) hamming_radius_kernel<WORDS, false><<<grid, kKnnThreads, 0, stream>>>(q32, nq, t32, nt, max_distance, mask, counts, offsets, out, capacity);
+  else hamming_radius_kernel<WORDS, true><<<grid, kKnnThreads, 0, stream>>>(q32, nq, t32, nt, max_distance, mask, counts, offsets, out, capacity);
+  return cudaGetLastError();
+}
+
+// phase 0: counts[nq] and offsets[nq + 1]; phase 1: matches (8 bytes each: train index, distance) at
+// offsets, up to `capacity` in all, optionally sorted per query the way std::sort does.
+cudaError_t launch_hamming_radius(int phase, const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes,
+                                  float max_distance, const uint8_t* mask, long long* counts, long long* offsets, void* matches,
+                                  long long capacity, int sort, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  RadiusMatch* out = static_cast<RadiusMatch*>(matches);
+  cudaError_t e;
+  switch (desc_bytes) {
+    case 48: e = radius_words<12>(phase, q, nq, t, nt, max_distance, mask, counts, offsets, out, capacity, stream); break;
+    case 64: e = radius_words<16>(phase, q, nq, t, nt, max_distance, mask, counts, offsets, out, capacity, stream); break;
+    case 128: e = radius_words<32>(phase, q, nq, t, nt, max_distance, mask, counts, offsets, out, capacity, stream); break;
+    default: return cudaErrorInvalidValue;
+  }
+  if (e != cudaSuccess) return e;
+  if (phase == 0) radius_scan_kernel<<<1, 1024, 0, stream>>>(counts, nq, offsets);
+  else if (sort) radius_sort_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, stream>>>(out, offsets, nq, capacity);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_radius_unpack(const void* matches, long long n, int32_t* idx, int32_t* dist, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  radius_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(static_cast<const RadiusMatch*>(matches), n, idx, dist);
   return cudaGetLastError();
 }
 

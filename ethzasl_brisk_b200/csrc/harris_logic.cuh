@@ -7,6 +7,7 @@
 #include <math.h>
 
 #include "brisk_common.cuh"
+#include "gcc_sort.cuh"
 
 namespace briskb200 {
 
@@ -107,144 +108,17 @@ BRISK_HD void harris_subpixel2d(double s00, double s01, double s02, double s10, 
 }
 
 // ---------------------------------------------------------------------------
-// std::sort of libstdc++ (GCC 13, bits/stl_algo.h:1848-1950, bits/stl_heap.h) on
-// HPoint with the reference's comparator `a.score > b.score`
-// (score-calculator.h:82-84).  Introsort is not stable and equal Harris scores
-// are the norm, so the exact permutation matters: it fixes both
-// the greedy uniformity outcome and the output order.  The recursion on
-// disjoint sub-ranges is replaced by an explicit stack (order independent).
+// std::sort on HPoint with the reference's comparator `a.score > b.score`
+// (score-calculator.h:82-84): see gcc_sort.cuh.  Equal Harris scores are the norm, so
+// the exact permutation matters: it fixes both the greedy uniformity outcome and the output order.
 // ---------------------------------------------------------------------------
-BRISK_HD bool hp_less(const HPoint& a, const HPoint& b) { return a.score > b.score; }
-BRISK_HD void hp_swap(HPoint& a, HPoint& b) { const HPoint t = a; a = b; b = t; }
-
-BRISK_HD void hp_push_heap(HPoint* first, long hole, long top, HPoint value) {
-  long parent = (hole - 1) / 2;
-  while (hole > top && hp_less(first[parent], value)) {
-    first[hole] = first[parent];
-    hole = parent;
-    parent = (hole - 1) / 2;
-  }
-  first[hole] = value;
-}
-
-BRISK_HD void hp_adjust_heap(HPoint* first, long hole, long len, HPoint value) {
-  const long top = hole;
-  long child = hole;
-  while (child < (len - 1) / 2) {
-    child = 2 * (child + 1);
-    if (hp_less(first[child], first[child - 1])) child--;
-    first[hole] = first[child];
-    hole = child;
-  }
-  if ((len & 1) == 0 && child == (len - 2) / 2) {
-    child = 2 * (child + 1);
-    first[hole] = first[child - 1];
-    hole = child - 1;
-  }
-  hp_push_heap(first, hole, top, value);
-}
-
-BRISK_HD void hp_heapsort(HPoint* first, long len) {  // __partial_sort(first, last, last)
-  if (len >= 2) {
-    long parent = (len - 2) / 2;
-    for (;;) {
-      const HPoint v = first[parent];
-      hp_adjust_heap(first, parent, len, v);
-      if (parent == 0) break;
-      parent--;
-    }
-  }
-  long last = len;
-  while (last > 1) {
-    --last;
-    const HPoint v = first[last];
-    first[last] = first[0];
-    hp_adjust_heap(first, 0, last, v);
-  }
-}
-
-BRISK_HD void hp_unguarded_linear_insert(HPoint* last) {
-  const HPoint val = *last;
-  HPoint* next = last - 1;
-  while (hp_less(val, *next)) {
-    *last = *next;
-    last = next;
-    --next;
-  }
-  *last = val;
-}
-
-BRISK_HD void hp_insertion_sort(HPoint* first, HPoint* last) {
-  if (first == last) return;
-  for (HPoint* i = first + 1; i != last; ++i) {
-    if (hp_less(*i, *first)) {
-      const HPoint val = *i;
-      for (HPoint* j = i; j != first; --j) *j = *(j - 1);
-      *first = val;
-    } else {
-      hp_unguarded_linear_insert(i);
-    }
-  }
-}
-
-// One pass of std::__introsort_loop's body on [first, last): __unguarded_partition_pivot (median of
-// first+1, mid, last-1 moved to first, then the unguarded Hoare scan).  Returns the cut.
-BRISK_HD int gcc_partition(HPoint* a, int first, int last) {
-  const int mid = first + (last - first) / 2;
-  HPoint& ra = a[first + 1]; HPoint& rb = a[mid]; HPoint& rc = a[last - 1];
-  if (hp_less(ra, rb)) {
-    if (hp_less(rb, rc)) hp_swap(a[first], rb);
-    else if (hp_less(ra, rc)) hp_swap(a[first], rc);
-    else hp_swap(a[first], ra);
-  } else if (hp_less(ra, rc)) hp_swap(a[first], ra);
-  else if (hp_less(rb, rc)) hp_swap(a[first], rc);
-  else hp_swap(a[first], rb);
-  int lo = first + 1, hi = last;
-  for (;;) {
-    while (hp_less(a[lo], a[first])) ++lo;
-    --hi;
-    while (hp_less(a[first], a[hi])) --hi;
-    if (!(lo < hi)) break;
-    hp_swap(a[lo], a[hi]);
-    ++lo;
-  }
-  return lo;
-}
-
-// std::__introsort_loop on [first, last) with the given depth limit, followed by the part of
-// __final_insertion_sort that concerns this range.  The final insertion sort never moves an element
-// across a partition cut (everything left of a cut compares >= everything right of it), so it is
-// the same as a stable insertion sort of every leaf range of at most 16 elements.
-BRISK_HD void gcc_sort_range(HPoint* a, int first0, int last0, int depth0) {
-  int st_first[64], st_last[64], st_depth[64];
-  int sp = 0;
-  st_first[0] = first0; st_last[0] = last0; st_depth[0] = depth0; sp = 1;
-  while (sp > 0) {
-    --sp;
-    int first = st_first[sp], last = st_last[sp], depth = st_depth[sp];
-    bool heap = false;
-    while (last - first > 16) {
-      if (depth == 0) { hp_heapsort(a + first, last - first); heap = true; break; }
-      --depth;
-      const int cut = gcc_partition(a, first, last);
-      st_first[sp] = cut; st_last[sp] = last; st_depth[sp] = depth; ++sp;   // recurse on [cut, last), go on with [first, cut)
-      last = cut;
-    }
-    if (!heap) hp_insertion_sort(a + first, a + last);
-  }
-}
-
-BRISK_HD int gcc_depth_limit(int n) {
-  int lg = 0;
-  for (unsigned v = (unsigned)n; v > 1; v >>= 1) ++lg;  // std::__lg
-  return 2 * lg;
-}
-
-// std::sort(a, a + n) with hp_less, element for element (libstdc++ of GCC 13).
-BRISK_HD void gcc_sort(HPoint* a, int n) {
-  if (n <= 0) return;
-  gcc_sort_range(a, 0, n, gcc_depth_limit(n));
-}
+struct HpLess { BRISK_HD bool operator()(const HPoint& a, const HPoint& b) const { return a.score > b.score; } };
+BRISK_HD void hp_heapsort(HPoint* first, long len) { gs_heapsort(HpLess(), first, len); }
+BRISK_HD void hp_insertion_sort(HPoint* first, HPoint* last) { gs_insertion_sort(HpLess(), first, last); }
+BRISK_HD int gcc_partition(HPoint* a, int first, int last) { return gs_partition(HpLess(), a, first, last); }
+BRISK_HD void gcc_sort_range(HPoint* a, int first0, int last0, int depth0) { gs_sort_range(HpLess(), a, first0, last0, depth0); }
+BRISK_HD int gcc_depth_limit(int n) { return gs_depth_limit(n); }
+BRISK_HD void gcc_sort(HPoint* a, int n) { gs_sort(HpLess(), a, n); }
 
 // Uniformity enforcement constants (uniformity-enforcement-inl.h:59-80).
 // LUT(y,x) = max(1 - ((15-x)^2 + (15-y)^2) / 225, 0) as float (scale-space-layer-inl.h:89-97).

@@ -90,6 +90,15 @@ int knn_round_k(int k);
 cudaError_t launch_hamming_knn_ex(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes, int k,
                                   long long train_index_offset, unsigned long long* keys, unsigned long long* part,
                                   int splits, cudaStream_t stream);
+// kNN with a [nq][nt] byte mask (0 = pair excluded); keys [nq][knn_round_k(k)].
+cudaError_t launch_hamming_knn_masked(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes, int k,
+                                      const uint8_t* mask, unsigned long long* keys, cudaStream_t stream);
+// Radius match: phase 0 -> counts[nq], offsets[nq + 1]; phase 1 -> (train index, distance) int pairs at offsets
+// (train order, or the reference's std::sort order when `sort`), at most `capacity` pairs in all.
+cudaError_t launch_hamming_radius(int phase, const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes,
+                                  float max_distance, const uint8_t* mask, long long* counts, long long* offsets, void* matches,
+                                  long long capacity, int sort, cudaStream_t stream);
+cudaError_t launch_radius_unpack(const void* matches, long long n, int32_t* idx, int32_t* dist, cudaStream_t stream);
 // Tensor-core (u8 IMMA on 0/1-expanded bits) variant, k == 2, 48/64-byte rows (hamming_mma.cu).
 int knn_mma_num_splits(long long nq, long long nt);
 cudaError_t launch_hamming_knn2_mma(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes,

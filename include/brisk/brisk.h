@@ -9,7 +9,10 @@
 #ifndef BRISK_BRISK_H_
 #define BRISK_BRISK_H_
 
+#include <algorithm>
 #include <bitset>
+#include <cstdlib>
+#include <cstring>
 #include <limits>
 #include <stdexcept>
 #include <string>
@@ -260,46 +263,153 @@ struct DMatch {  // == cv::DMatch
 };
 
 // brisk::BruteForceMatcher -- reference brisk/include/brisk/brute-force-matcher.h:54-94 and
-// brisk/src/brute-force-matcher.cc:59-162 (kNN over the concatenated train collection, no masks).
+// brisk/src/brute-force-matcher.cc:59-214, with the cv::DescriptorMatcher conventions it relies on: a train
+// collection (add / clear), per-image masks (query rows x train rows, 0 = pair excluded; an empty mask allows
+// everything), compactResult, knnMatch / radiusMatch / match.  Distances and candidate selection run on the GPU;
+// this class only reshapes the results into the reference's DMatch lists.
 class BruteForceMatcher {
  public:
   explicit BruteForceMatcher(const Hamming& = Hamming()) {}
-  bool isMaskSupported() const { return false; }
+  bool isMaskSupported() const { return true; }
   void add(const std::vector<agast::Mat>& descriptors) { for (const auto& d : descriptors) train_.push_back(d); }
   void clear() { train_.clear(); }
+  bool empty() const { return train_.empty(); }
   const std::vector<agast::Mat>& getTrainDescriptors() const { return train_; }
+  BruteForceMatcher clone(bool emptyTrainData = false) const { BruteForceMatcher m; if (!emptyTrainData) m.train_ = train_; return m; }
 
-  void knnMatch(const agast::Mat& query, const agast::Mat& train, std::vector<std::vector<DMatch> >& matches, int k) const {
-    std::vector<agast::Mat> t(1, train);
-    knnImpl(query, t, matches, k);
+  void knnMatch(const agast::Mat& query, const agast::Mat& train, std::vector<std::vector<DMatch> >& matches, int k,
+                const agast::Mat& mask = agast::Mat(), bool compactResult = false) const {
+    knnImpl(query, std::vector<agast::Mat>(1, train), matches, k, mask.empty() ? std::vector<agast::Mat>() : std::vector<agast::Mat>(1, mask), compactResult);
   }
-  void knnMatch(const agast::Mat& query, std::vector<std::vector<DMatch> >& matches, int k) const { knnImpl(query, train_, matches, k); }
+  void knnMatch(const agast::Mat& query, std::vector<std::vector<DMatch> >& matches, int k,
+                const std::vector<agast::Mat>& masks = std::vector<agast::Mat>(), bool compactResult = false) const {
+    knnImpl(query, train_, matches, k, masks, compactResult);
+  }
+  void radiusMatch(const agast::Mat& query, const agast::Mat& train, std::vector<std::vector<DMatch> >& matches, float maxDistance,
+                   const agast::Mat& mask = agast::Mat(), bool compactResult = false) const {
+    radiusImpl(query, std::vector<agast::Mat>(1, train), matches, maxDistance, mask.empty() ? std::vector<agast::Mat>() : std::vector<agast::Mat>(1, mask), compactResult);
+  }
+  void radiusMatch(const agast::Mat& query, std::vector<std::vector<DMatch> >& matches, float maxDistance,
+                   const std::vector<agast::Mat>& masks = std::vector<agast::Mat>(), bool compactResult = false) const {
+    radiusImpl(query, train_, matches, maxDistance, masks, compactResult);
+  }
+  // cv::DescriptorMatcher::match: knnMatch(k = 1, compactResult = true), flattened
+  void match(const agast::Mat& query, const agast::Mat& train, std::vector<DMatch>& matches, const agast::Mat& mask = agast::Mat()) const {
+    std::vector<std::vector<DMatch> > knn;
+    knnMatch(query, train, knn, 1, mask, true);
+    matches.clear();
+    for (const auto& v : knn) matches.insert(matches.end(), v.begin(), v.end());
+  }
 
  private:
-  void knnImpl(const agast::Mat& query, const std::vector<agast::Mat>& train, std::vector<std::vector<DMatch> >& matches, int k) const {
-    matches.assign(query.rows, std::vector<DMatch>());
-    if (query.rows == 0 || train.empty()) return;
-    // concatenate the collection; global row index -> (imgIdx, trainIdx)
-    std::vector<unsigned char> all;
-    std::vector<int> start(1, 0);
-    for (const auto& t : train) {
-      if (t.cols != query.cols) throw std::runtime_error("descriptor size mismatch");
-      all.insert(all.end(), t.data, t.data + (size_t)t.rows * t.cols);
-      start.push_back(start.back() + t.rows);
+  struct Collection {
+    std::vector<unsigned char> all, mask;
+    std::vector<int> start;
+    std::vector<char> masked_out;
+    int last_nonempty = -1;
+  };
+  // concatenated train rows (global row -> (imgIdx, trainIdx) through `start`), masks side by side, and
+  // cv::DescriptorMatcher::isMaskedOut per query
+  static void gather(const agast::Mat& query, const std::vector<agast::Mat>& train, const std::vector<agast::Mat>& masks, Collection* c) {
+    c->start.assign(1, 0);
+    for (size_t i = 0; i < train.size(); ++i) {
+      const agast::Mat& t = train[i];
+      if (!t.empty() && t.cols != query.cols) throw std::runtime_error("descriptor size mismatch");
+      for (int r = 0; r < t.rows; ++r) c->all.insert(c->all.end(), t.data + (size_t)r * t.step, t.data + (size_t)r * t.step + t.cols);
+      c->start.push_back(c->start.back() + t.rows);
+      if (t.rows > 0) c->last_nonempty = (int)i;
     }
-    std::vector<int32_t> idx((size_t)query.rows * k), dist((size_t)query.rows * k);
-    brisk_ctx* ctx = detail::context();
-    detail::check(ctx, brisk_hamming_knn(ctx, query.data, query.rows, all.data(), start.back(), query.cols, k, idx.data(), dist.data()));
-    for (int q = 0; q < query.rows; ++q)
+    c->masked_out.assign(query.rows, 0);
+    if (masks.empty()) return;
+    if (masks.size() != train.size()) throw std::runtime_error("one mask per train image expected");
+    const int nt = c->start.back();
+    c->mask.assign((size_t)query.rows * nt, 1);
+    bool every_mask_given = true;
+    for (size_t i = 0; i < masks.size(); ++i) {
+      const agast::Mat& m = masks[i];
+      if (m.empty()) { every_mask_given = false; continue; }
+      if (m.rows != query.rows || m.cols != train[i].rows) throw std::runtime_error("mask size mismatch");
+      for (int q = 0; q < query.rows; ++q)
+        for (int t = 0; t < m.cols; ++t) c->mask[(size_t)q * nt + c->start[i] + t] = m.data[(size_t)q * m.step + t] != 0;
+    }
+    if (every_mask_given)
+      for (int q = 0; q < query.rows; ++q) {
+        bool any = false;
+        for (int t = 0; t < nt && !any; ++t) any = c->mask[(size_t)q * nt + t] != 0;
+        c->masked_out[q] = !any;
+      }
+  }
+  static std::vector<unsigned char> tight(const agast::Mat& m) {
+    std::vector<unsigned char> v((size_t)m.rows * m.cols);
+    for (int r = 0; r < m.rows; ++r) std::memcpy(v.data() + (size_t)r * m.cols, m.data + (size_t)r * m.step, m.cols);
+    return v;
+  }
+  static DMatch make(int q, int g, const std::vector<int>& start, float d) {
+    int img = 0;
+    while (g >= start[img + 1]) ++img;
+    DMatch m;
+    m.queryIdx = q; m.trainIdx = g - start[img]; m.imgIdx = img; m.distance = d;
+    return m;
+  }
+  void knnImpl(const agast::Mat& query, const std::vector<agast::Mat>& train, std::vector<std::vector<DMatch> >& matches, int k,
+               const std::vector<agast::Mat>& masks, bool compactResult) const {
+    matches.clear();
+    if (query.rows == 0) return;
+    Collection c;
+    gather(query, train, masks, &c);
+    const int nt = c.start.back();
+    std::vector<int32_t> idx((size_t)query.rows * k, -1), dist((size_t)query.rows * k, -1);
+    if (nt > 0) {
+      const std::vector<unsigned char> q = tight(query);
+      brisk_ctx* ctx = detail::context();
+      detail::check(ctx, brisk_hamming_knn_masked(ctx, q.data(), query.rows, c.all.data(), nt, query.cols, k,
+                                                  c.mask.empty() ? nullptr : c.mask.data(), idx.data(), dist.data()));
+    }
+    for (int q = 0; q < query.rows; ++q) {
+      if (c.masked_out[q]) { if (!compactResult) matches.push_back(std::vector<DMatch>()); continue; }
+      matches.push_back(std::vector<DMatch>());
+      if (nt == 0) continue;
       for (int j = 0; j < k; ++j) {
         const int g = idx[(size_t)q * k + j];
-        if (g < 0) continue;
-        int img = 0;
-        while (g >= start[img + 1]) ++img;
-        DMatch m;
-        m.queryIdx = q; m.trainIdx = g - start[img]; m.imgIdx = img; m.distance = (float)dist[(size_t)q * k + j];
-        matches[q].push_back(m);
+        if (g >= 0) matches.back().push_back(make(q, g, c.start, (float)dist[(size_t)q * k + j]));
+        else {
+          // The reference keeps selecting once the real candidates have run out (brute-force-matcher.cc:138-157):
+          // every entry then holds INT_MAX, minMaxLoc returns location 0, and INT_MAX as a double is below the
+          // float it was just rounded to, so the last non-empty image wins.
+          DMatch m;
+          m.queryIdx = q; m.trainIdx = 0; m.imgIdx = c.last_nonempty; m.distance = 2147483648.0f;
+          matches.back().push_back(m);
+        }
       }
+    }
+  }
+  void radiusImpl(const agast::Mat& query, const std::vector<agast::Mat>& train, std::vector<std::vector<DMatch> >& matches,
+                  float maxDistance, const std::vector<agast::Mat>& masks, bool compactResult) const {
+    matches.clear();
+    if (query.rows == 0) return;
+    Collection c;
+    gather(query, train, masks, &c);
+    const int nt = c.start.back();
+    std::vector<int64_t> offsets((size_t)query.rows + 1, 0);
+    std::vector<int32_t> idx, dist;
+    if (nt > 0) {
+      const std::vector<unsigned char> q = tight(query);
+      brisk_ctx* ctx = detail::context();
+      int64_t cap = std::max<int64_t>(1024, 4 * (int64_t)query.rows);
+      for (;;) {
+        idx.resize((size_t)cap); dist.resize((size_t)cap);
+        const int rc = brisk_hamming_radius(ctx, q.data(), query.rows, c.all.data(), nt, query.cols, maxDistance,
+                                            c.mask.empty() ? nullptr : c.mask.data(), 1, offsets.data(), idx.data(), dist.data(), cap);
+        if (rc == BRISK_ERR_CAPACITY && offsets.back() > cap) { cap = offsets.back(); continue; }
+        detail::check(ctx, rc);
+        break;
+      }
+    }
+    for (int q = 0; q < query.rows; ++q) {
+      if (c.masked_out[q]) { if (!compactResult) matches.push_back(std::vector<DMatch>()); continue; }
+      matches.push_back(std::vector<DMatch>());
+      for (int64_t j = offsets[q]; j < offsets[q + 1]; ++j) matches.back().push_back(make(q, idx[(size_t)j], c.start, (float)dist[(size_t)j]));
+    }
   }
   std::vector<agast::Mat> train_;
 };

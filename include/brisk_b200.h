@@ -144,6 +144,22 @@ int brisk_hamming_distance(brisk_ctx* ctx, const uint8_t* a, const uint8_t* b, i
  * neighbours (nt < k) are -1.  desc_bytes: 48, 64 or 128. */
 int brisk_hamming_knn(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt,
                       int desc_bytes, int k, int32_t* idx, int32_t* dist);
+/* knnMatch() with masks: commonKnnMatchImpl's `isPossibleMatch` test -- reference brisk/src/brute-force-matcher.cc:
+ * 118-119.  mask: [nq][nt] bytes, 0 = pair excluded (the per-image masks of a train collection side by side, as the
+ * train rows are); NULL = no mask.  Queries with fewer than k allowed rows get -1 entries (the host classes turn
+ * those into what the reference returns, see include/brisk/brisk.h). */
+int brisk_hamming_knn_masked(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt,
+                             int desc_bytes, int k, const uint8_t* mask, int32_t* idx, int32_t* dist);
+/* radiusMatch(): BruteForceMatcher::commonRadiusMatchImpl -- reference brisk/src/brute-force-matcher.cc:164-214.
+ * Every train row with (float)distance < max_distance (and a non-zero mask byte, if a mask is given).  The
+ * matches of query i are idx/dist[offsets[i] .. offsets[i+1]); offsets has nq + 1 entries.  sort = 0: train
+ * order; sort = 1: the reference's order, i.e. std::sort by distance as libstdc++ performs it on the
+ * train-ordered list (equal distances included).  If more than `capacity` matches exist the call
+ * returns BRISK_ERR_CAPACITY with offsets filled in (offsets[nq] = capacity needed) and the first
+ * `capacity` matches in train order. */
+int brisk_hamming_radius(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int desc_bytes,
+                         float max_distance, const uint8_t* mask, int sort, int64_t* offsets, int32_t* idx, int32_t* dist,
+                         int64_t capacity);
 /* Sharded train set: local top-k as packed keys (dist << 32 | global train index), DEVICE buffer
  * keys[nq][k]; merge n_shards gathered key sets ([shard][nq][k], device) into idx/dist.  The exchange
  * between GPUs (NCCL all-gather of the keys) is done by the caller. */

@@ -1283,4 +1283,23 @@ int orc_knn(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, int nbyt
   return 0;
 }
 
+// std::sort(curMatches->begin(), curMatches->end()) of brute-force-matcher.cc:160,210 on cv::DMatch
+// records (operator< compares `distance` only): libstdc++'s introsort, not stable, so the permutation of
+// equal distances is part of the reference's result.  In/out: parallel arrays of n matches.
+int orc_sort_matches(int32_t* train_idx, int32_t* img_idx, float* distance, int n) {
+  struct M { int t, i; float d; bool operator<(const M& m) const { return d < m.d; } };
+  std::vector<M> v(n);
+  for (int j = 0; j < n; ++j) v[j] = M{train_idx[j], img_idx[j], distance[j]};
+  std::sort(v.begin(), v.end());
+  for (int j = 0; j < n; ++j) { train_idx[j] = v[j].t; img_idx[j] = v[j].i; distance[j] = v[j].d; }
+  return 0;
+}
+
+// All pairwise distances (hamming-inl.h:85-134) of two descriptor sets: out[nq][nt].
+int orc_hamming_matrix(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, int nbytes, int32_t* out) {
+  for (int64_t i = 0; i < nq; ++i)
+    for (int64_t j = 0; j < nt; ++j) out[i * nt + j] = orc_hamming(q + i * nbytes, t + j * nbytes, nbytes);
+  return 0;
+}
+
 }  // extern "C"

@@ -58,6 +58,11 @@ int orc_hamming(const uint8_t* a, const uint8_t* b, int nbytes);
 int orc_knn(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, int nbytes, int k, int32_t* idx,
             int32_t* dist);
 
+/* brute-force-matcher.cc:160,210: std::sort of the DMatch list of one query (by distance, libstdc++ order) */
+int orc_sort_matches(int32_t* train_idx, int32_t* img_idx, float* distance, int n);
+/* all pairwise Hamming distances, out[nq][nt] */
+int orc_hamming_matrix(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, int nbytes, int32_t* out);
+
 #ifdef __cplusplus
 }
 #endif

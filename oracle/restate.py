@@ -168,3 +168,101 @@ def knn(q, t, k):
     dist = np.zeros((len(q), k), np.int32)
     lib().orc_knn(_p(q), C.c_int64(len(q)), _p(t), C.c_int64(len(t)), q.shape[1], int(k), _p(idx), _p(dist))
     return idx, dist
+
+
+def _is_masked_out(masks, q):
+    """cv::DescriptorMatcher::isMaskedOut: every mask is non-empty and has an all-zero row q."""
+    if not masks:
+        return False
+    out = sum(1 for m in masks if m is not None and m.size and not np.any(m[q]))
+    return out == len(masks)
+
+
+def _possible(masks, img, q, t):
+    """masks.empty() || isPossibleMatch(masks[img], q, t) (an empty mask allows everything)."""
+    if not masks:
+        return True
+    m = masks[img]
+    return m is None or m.size == 0 or m[q, t] != 0
+
+
+def _sorted_matches(ms):
+    """std::sort of one query's DMatch list (brute-force-matcher.cc:160,210)."""
+    if len(ms) < 2:
+        return ms
+    t = np.array([m[1] for m in ms], np.int32)
+    i = np.array([m[2] for m in ms], np.int32)
+    d = np.array([m[3] for m in ms], np.float32)
+    lib().orc_sort_matches(_p(t), _p(i), _p(d), len(ms))
+    return [(ms[0][0], int(a), int(b), float(c)) for a, b, c in zip(t, i, d)]
+
+
+def _distance_matrices(q, trains):
+    out = []
+    for t in trains:
+        t = np.ascontiguousarray(t, np.uint8).reshape(-1, q.shape[1])
+        d = np.zeros((len(q), len(t)), np.int32)
+        if len(t):
+            lib().orc_hamming_matrix(_p(q), C.c_int64(len(q)), _p(t), C.c_int64(len(t)), q.shape[1], _p(d))
+        out.append(d)
+    return out
+
+
+def knn_match(q, trains, k, masks=None, compact=False):
+    """BruteForceMatcher::commonKnnMatchImpl (brute-force-matcher.cc:80-162) over a train collection with
+    optional per-image masks [nq][nt_i]: list (per query) of (queryIdx, trainIdx, imgIdx, distance).
+    Line by line, including what the code does once the real candidates of a query run out: masked /
+    taken entries hold INT_MAX, minMaxLoc still returns a location and INT_MAX < FLT_MAX, so the list is
+    padded with (trainIdx of the first INT_MAX entry, first image whose minimum it is, 2147483648.0f)."""
+    q = np.ascontiguousarray(q, np.uint8)
+    INT_MAX = np.iinfo(np.int32).max
+    dist = _distance_matrices(q, trains)
+    matches = []
+    for qi in range(len(q)):
+        if _is_masked_out(masks, qi):
+            if not compact:
+                matches.append([])
+            continue
+        all_d = []
+        for img, d in enumerate(dist):
+            row = np.full(d.shape[1], INT_MAX, np.int64)
+            for t in range(d.shape[1]):
+                if _possible(masks, img, qi, t):
+                    row[t] = d[qi, t]
+            all_d.append(row)
+        cur = []
+        for _ in range(k):
+            best = None
+            best_d = float(np.finfo(np.float32).max)
+            for img, row in enumerate(all_d):
+                if row.size:
+                    loc = int(np.argmin(row))  # minMaxLoc: first minimum
+                    if float(row[loc]) < best_d:
+                        best = (qi, loc, img, float(np.float32(float(row[loc]))))
+                        best_d = best[3]
+            if best is None:
+                break
+            all_d[best[2]][best[1]] = INT_MAX
+            cur.append(best)
+        matches.append(_sorted_matches(cur))
+    return matches
+
+
+def radius_match(q, trains, max_distance, masks=None, compact=False):
+    """BruteForceMatcher::commonRadiusMatchImpl (brute-force-matcher.cc:164-214)."""
+    q = np.ascontiguousarray(q, np.uint8)
+    dist = _distance_matrices(q, trains)
+    md = np.float32(max_distance)
+    matches = []
+    for qi in range(len(q)):
+        if _is_masked_out(masks, qi):
+            if not compact:
+                matches.append([])
+            continue
+        cur = []
+        for img, d in enumerate(dist):
+            for t in range(d.shape[1]):
+                if _possible(masks, img, qi, t) and np.float32(d[qi, t]) < md:
+                    cur.append((qi, t, img, float(d[qi, t])))
+        matches.append(_sorted_matches(cur))
+    return matches

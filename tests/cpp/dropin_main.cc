@@ -1,6 +1,6 @@
 // Exercises the header-only C++ drop-in (include/brisk/brisk.h) the way an OKVIS-style caller
 // uses the reference: detector + extractor per image, then a brute-force match.
-// usage: dropin_main <in.pgm> <out.bin>
+// usage: dropin_main <in.pgm> <out.bin> [<matches.bin>]
 #include <cstdio>
 #include <fstream>
 #include <iostream>
@@ -42,5 +42,37 @@ int main(int argc, char** argv) {
   o.write(reinterpret_cast<char*>(hk.data()), (std::streamsize)hn * sizeof(agast::KeyPoint));
   o.write(reinterpret_cast<char*>(hd.data), (std::streamsize)hn * hd.cols);
   std::printf("%d key points, %d-byte descriptors, %d self matches\n", n, nb, self);
+  if (argc > 3) {
+    // matcher surface: a two-image train collection with masks, knnMatch(k = 3) and radiusMatch(45)
+    const int nq = std::min(n, 150), n0 = n / 3;
+    agast::Mat q(nq, nb, CV_8UC1, desc.data, desc.step);
+    std::vector<agast::Mat> train;
+    train.push_back(agast::Mat(n0, nb, CV_8UC1, desc.data, desc.step));
+    train.push_back(agast::Mat(n - n0, nb, CV_8UC1, desc.data + (size_t)n0 * desc.step, desc.step));
+    std::vector<agast::Mat> masks;
+    masks.push_back(agast::Mat::zeros(nq, n0, CV_8UC1));
+    masks.push_back(agast::Mat::zeros(nq, n - n0, CV_8UC1));
+    for (int i = 0; i < nq; ++i) {
+      for (int t = 0; t < n0; ++t) masks[0].data[(size_t)i * n0 + t] = (i % 7 != 3) && ((i + t) % 3 != 0);
+      for (int t = 0; t < n - n0; ++t) masks[1].data[(size_t)i * (n - n0) + t] = (i % 7 != 3) && ((i + 2 * t) % 5 != 0);
+    }
+    brisk::BruteForceMatcher coll;
+    coll.add(train);
+    std::ofstream mo(argv[3], std::ios::binary);
+    auto dump = [&](const std::vector<std::vector<brisk::DMatch> >& mm) {
+      int lists = (int)mm.size();
+      mo.write(reinterpret_cast<char*>(&lists), 4);
+      for (const auto& v : mm) {
+        int c = (int)v.size();
+        mo.write(reinterpret_cast<char*>(&c), 4);
+        for (const auto& m : v) mo.write(reinterpret_cast<const char*>(&m), sizeof(brisk::DMatch));
+      }
+    };
+    std::vector<std::vector<brisk::DMatch> > mm;
+    coll.knnMatch(q, mm, 3, masks, false);
+    dump(mm);
+    coll.radiusMatch(q, mm, 45.0f, masks, true);
+    dump(mm);
+  }
   return 0;
 }

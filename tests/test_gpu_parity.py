@@ -292,7 +292,8 @@ def test_cpp_dropin_classes(tmp_path, oracle, golden):
         f.write(b"P5\n%d %d\n255\n" % (img.shape[1], img.shape[0]))
         f.write(img.tobytes())
     out = tmp_path / "out.bin"
-    subprocess.run([str(exe), str(pgm), str(out)], check=True)
+    mout = tmp_path / "matches.bin"
+    subprocess.run([str(exe), str(pgm), str(out), str(mout)], check=True)
     raw = out.read_bytes()
     n, nb, self_matches = np.frombuffer(raw[:12], np.int32)
     kps = np.frombuffer(raw[12:12 + n * 28], bb.KP_DTYPE)
@@ -307,6 +308,95 @@ def test_cpp_dropin_classes(tmp_path, oracle, golden):
     for f in ("x", "y", "size", "response", "octave", "class_id"):
         assert np.array_equal(kps[f], gk[f]), f
     assert np.array_equal(desc, gd)
+    # matcher surface: masked knnMatch over a two-image collection, radiusMatch with compactResult
+    nq, n0 = min(n, 150), n // 3
+    trains = [desc[:n0], desc[n0:]]
+    qi = np.arange(nq)[:, None]
+    masks = [((qi % 7 != 3) & ((qi + np.arange(n0)[None, :]) % 3 != 0)).astype(np.uint8),
+             ((qi % 7 != 3) & ((qi + 2 * np.arange(n - n0)[None, :]) % 5 != 0)).astype(np.uint8)]
+    mraw = np.frombuffer(mout.read_bytes(), np.int32)
+
+    def read_lists(pos):
+        lists = int(mraw[pos]); pos += 1
+        res = []
+        for _ in range(lists):
+            c = int(mraw[pos]); pos += 1
+            rec = mraw[pos:pos + 4 * c].reshape(c, 4)
+            res.append([(int(r[0]), int(r[1]), int(r[2]), float(r[3:4].view(np.float32)[0])) for r in rec])
+            pos += 4 * c
+        return res, pos
+    knn_lists, pos = read_lists(0)
+    rad_lists, pos = read_lists(pos)
+    assert knn_lists == oracle.knn_match(desc[:nq], trains, 3, masks, False)
+    assert rad_lists == oracle.radius_match(desc[:nq], trains, 45.0, masks, True)
+
+
+def _tie_rich_descriptors(n, nbytes, seed):
+    # few distinct byte values in few positions: distances fall in a narrow range, equal distances are the norm
+    rng = np.random.default_rng(seed)
+    d = np.zeros((n, nbytes), np.uint8)
+    d[:, :6] = rng.integers(0, 4, (n, 6), dtype=np.uint8) * 17
+    return d
+
+
+@pytest.mark.parametrize("nbytes", [48, 64])
+def test_knn_match_collection_masks(ctx, oracle, nbytes):
+    # knnMatch over a train collection (one image empty, one mask empty), ties across images, masked-out
+    # queries, fewer allowed rows than k: reference brute-force-matcher.cc:80-162 line by line
+    rng = np.random.default_rng(11)
+    q = bb.random_descriptors(90, nbytes, 5)
+    trains = [bb.random_descriptors(300, nbytes, 6), np.zeros((0, nbytes), np.uint8), bb.random_descriptors(170, nbytes, 7)]
+    trains[0][10] = q[3]; trains[2][5] = q[3]; trains[0][200] = q[3]
+    masks = [(rng.random((90, 300)) < 0.7).astype(np.uint8), None, (rng.random((90, 170)) < 0.5).astype(np.uint8)]
+    masks[0][7] = 0; masks[2][7] = 0                    # no allowed row at all
+    masks[0][9] = 0; masks[2][9] = 0; masks[2][9, 4] = 1  # a single allowed row
+    m = bb.BruteForceMatcher(ctx=ctx)
+    m.add(trains)
+    for k in (1, 2, 5):
+        for compact in (False, True):
+            assert m.knnMatch(q, None, k, masks, compact) == oracle.knn_match(q, trains, k, masks, compact), (k, compact)
+        assert m.knnMatch(q, None, k) == oracle.knn_match(q, trains, k)
+    # with the empty image (whose mask is empty too) query 7 is not "masked out": it gets k padding entries
+    assert m.knnMatch(q, None, 2, masks)[7] == [(7, 0, 2, 2147483648.0)] * 2
+    # every image has a mask: query 7 is masked out (dropped when compactResult), query 9 is padded the reference's way
+    m2 = bb.BruteForceMatcher(ctx=ctx)
+    m2.add([trains[0], trains[2]])
+    full = [masks[0], masks[2]]
+    got = m2.knnMatch(q, None, 3, full, True)
+    assert got == oracle.knn_match(q, [trains[0], trains[2]], 3, full, True) and len(got) == 89
+    assert got[8][1:] == [(9, 0, 1, 2147483648.0)] * 2
+    assert m2.match(q, None, full) == [ms[0] for ms in oracle.knn_match(q, [trains[0], trains[2]], 1, full, True)]
+    # fewer train rows than k
+    assert m.knnMatch(q[:4], trains[0][:2], 3) == oracle.knn_match(q[:4], [trains[0][:2]], 3)
+
+
+@pytest.mark.parametrize("nbytes", [48, 64])
+def test_radius_match(ctx, oracle, nbytes):
+    # radiusMatch: long lists of equal distances (std::sort's permutation is part of the result), masks, two
+    # images, compactResult, the capacity retry: reference brute-force-matcher.cc:164-214
+    rng = np.random.default_rng(12)
+    q = _tie_rich_descriptors(60, nbytes, 1)
+    trains = [_tie_rich_descriptors(400, nbytes, 2), _tie_rich_descriptors(250, nbytes, 3)]
+    m = bb.BruteForceMatcher(ctx=ctx)
+    m.add(trains)
+    for md in (0.0, 1.0, 7.5, 12.0, 1000.0):
+        got = m.radiusMatch(q, None, md)
+        assert got == oracle.radius_match(q, trains, md), md
+    assert max(len(v) for v in m.radiusMatch(q, None, 12.0)) > 64
+    masks = [(rng.random((60, 400)) < 0.6).astype(np.uint8), (rng.random((60, 250)) < 0.6).astype(np.uint8)]
+    masks[0][5] = 0; masks[1][5] = 0
+    for compact in (False, True):
+        assert m.radiusMatch(q, None, 9.0, masks, compact) == oracle.radius_match(q, trains, 9.0, masks, compact)
+    # random descriptors, one train image given per call
+    q2, t2 = bb.random_descriptors(300, nbytes, 5), bb.random_descriptors(4000, nbytes, 6)
+    md = float(nbytes * 8 * 0.44)
+    assert m.radiusMatch(q2, t2, md) == oracle.radius_match(q2, [t2], md)
+    # train-order output of the C ABI and its offsets
+    off, idx, dist = m.radius(q2, t2, md, sort=False)
+    ref = oracle.radius_match(q2, [t2], md)
+    assert off[-1] == sum(len(v) for v in ref)
+    for i in (0, 17, 299):
+        assert sorted(idx[off[i]:off[i + 1]].tolist()) == idx[off[i]:off[i + 1]].tolist() == sorted(t for _, t, _, _ in ref[i])
 
 
 @pytest.mark.parametrize("i", [0, 1])

@@ -117,3 +117,23 @@ def test_knn_vs_ref_primitive(oracle, ref):
     i2, d2 = ref.knn(q, t, 2)
     assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
     assert i1[3, 0] == 7 and i1[3, 1] == 9 and d1[3, 0] == 0
+
+
+def test_matcher_restatement_consistency(oracle):
+    # knn_match / radius_match (brute-force-matcher.cc:80-214 line by line) against the plain single-image kNN
+    # restatement and a numpy brute force; std::sort replay keeps lists sorted by distance
+    rng = np.random.default_rng(3)
+    q = rng.integers(0, 256, (40, 48), dtype=np.uint8)
+    t = rng.integers(0, 256, (500, 48), dtype=np.uint8)
+    t[7] = q[2]; t[9] = q[2]
+    idx, dist = oracle.knn(q, t, 3)
+    lists = oracle.knn_match(q, [t], 3)
+    assert [[m[1] for m in v] for v in lists] == idx.tolist() and [[int(m[3]) for m in v] for v in lists] == dist.tolist()
+    d = np.unpackbits(q[:, None, :] ^ t[None, :, :], axis=2).sum(axis=2)
+    rad = oracle.radius_match(q, [t[:250], t[250:]], 180.0)
+    for qi, v in enumerate(rad):
+        assert sorted((m[2] * 250 + m[1]) for m in v) == np.nonzero(d[qi] < 180)[0].tolist()
+        assert all(a[3] <= b[3] for a, b in zip(v, v[1:]))
+    # fewer candidates than k: the reference pads with (0, last non-empty image, 2147483648.0f)
+    short = oracle.knn_match(q[:2], [t[:1], t[:0]], 3)
+    assert short[0][1:] == [(0, 0, 0, 2147483648.0)] * 2
