@@ -175,8 +175,8 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
   const bool harris = det && det->harris;
   if (ccap <= 0) ccap = std::min(std::max((int)(((long long)w * h) / (harris ? 10 : 24)), harris ? 8192 : 4096), 1 << 20);
   memset(&plan->hw, 0, sizeof(plan->hw));
-  if (harris) {
-    // occupancy maps of EnforceKeyPointUniformity (uniformity-enforcement-inl.h:62-66)
+  if (harris && det->radius > 0.0) {
+    // occupancy maps of EnforceKeyPointUniformity (uniformity-enforcement-inl.h:62-66); none for key-point bucketing
     const float scaling = (float)(15.0 / (double)(float)(det->radius == 0 ? 1.0 : det->radius));
     long long off = 0;
     for (int i = 0; i < g.n_layers; ++i) {
@@ -316,13 +316,21 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
   if (n == 0) return BRISK_OK;
   if (det && det->harris) {
     if (det->octaves < 0 || 2 * det->octaves > kMaxLayers) return fail(ctx, BRISK_ERR_UNSUPPORTED, "octaves must be in [0, 6]");
-    if (!(det->radius > 0.0)) return fail(ctx, BRISK_ERR_UNSUPPORTED, "uniformityRadius <= 0 (key point bucketing) is not implemented");
-    if (det->radius < 15.0 / 4.0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "uniformityRadius below 3.75 is not supported");
+    if (!(det->radius > 0.0)) {
+      // KeyPointBucketing (key-point-bucketing-inl.h:74-112): the reference reserves maxNumKpt entries up front, so the default
+      // maxNumKpt = SIZE_MAX throws std::length_error there; a finite limit is required, and 4 buckets per axis need > 4 pixels
+      if (det->max_kpt <= 0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "key point bucketing (uniformityRadius <= 0) needs a finite maxNumKpt > 0");
+    } else if (det->radius < 15.0 / 4.0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "uniformityRadius below 3.75 is not supported");
   } else if (det) {
     if (det->thresh < 30 || det->thresh > 255)
       return fail(ctx, BRISK_ERR_UNSUPPORTED, "AGAST threshold must be in [30, 255] (lower values make corner scores <= 2, whose cache semantics are not implemented)");
     if (det->octaves < 0 || 2 * det->octaves > kMaxLayers) return fail(ctx, BRISK_ERR_UNSUPPORTED, "octaves must be in [0, 6]");
-    if (!det->suppress) return fail(ctx, BRISK_ERR_UNSUPPORTED, "suppressScaleNonmaxima=false is not implemented");
+    // suppressScaleNonmaxima = false (brisk-scale-space.cc:131-170): with one layer it is the single-layer branch
+    // (:172-209) word for word; with more layers the reference indexes layer 0's corner list with the counts of
+    // layer i (`agastPoints.at(0)[n]`, :137), which reads past its end whenever a coarser layer has more corners
+    // -- undefined behaviour, nothing to be bit-exact with.
+    if (!det->suppress && det->octaves != 0)
+      return fail(ctx, BRISK_ERR_UNSUPPORTED, "suppressScaleNonmaxima=false is only defined for octaves == 0 (the reference reads out of bounds otherwise)");
   }
   {
     PyramidGeom probe;

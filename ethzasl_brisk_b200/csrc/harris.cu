@@ -279,6 +279,46 @@ harris_uniformity_kernel(PyramidGeom g, UniformityGeom ug, const int* __restrict
   if (tid == 0) layer_surv[frame * kMaxLayers + layer] = kept;
 }
 
+// One warp per (frame, layer): KeyPointBucketing (key-point-bucketing-inl.h:44-112, key-point-bucketing.h:45-93) with the
+// 4 x 4 buckets of ScaleSpaceLayer (scale-space-layer.h:73-74).  The sorted points are taken 32 at a time; a point is kept
+// while fewer than maxNumKpt / 16 earlier points of its bucket were kept, i.e. while (bucket count so far + its rank among
+// the lanes of the same bucket) is below the quota.  Output keeps the sorted order.
+__global__ void __launch_bounds__(32)
+harris_bucketing_kernel(PyramidGeom g, const int* __restrict__ layer_start, const HPoint* __restrict__ sorted,
+                        const int* __restrict__ layer_kept, HPoint* __restrict__ surv, int* __restrict__ layer_surv, int cap,
+                        long long max_kpt) {
+  __shared__ unsigned s_cnt[16];
+  const int frame = blockIdx.y, layer = blockIdx.x, lane = threadIdx.x;
+  const int* ls = layer_start + (long long)frame * (kMaxLayers + 1);
+  const int begin = min(ls[layer], cap);
+  const int m = layer_kept[frame * kMaxLayers + layer];
+  const HPoint* pts = sorted + (long long)frame * cap + begin;
+  HPoint* out = surv + (long long)frame * cap + begin;
+  const unsigned step_u = 1u + (unsigned)(g.L[layer].w - 1) / 4u, step_v = 1u + (unsigned)(g.L[layer].h - 1) / 4u;
+  const unsigned quota = (unsigned)((unsigned long long)max_kpt / 16ull);  // unsigned int _maxNumKeyPointsPerBucket
+  if (lane < 16) s_cnt[lane] = 0;
+  __syncwarp();
+  int kept = 0;
+  for (int base = 0; base < m; base += 32) {
+    const int k = base + lane;
+    const bool valid = k < m;
+    HPoint p = {0, 0, 0};
+    if (valid) p = pts[k];
+    const unsigned b = valid ? (p.x / step_u) * 4u + p.y / step_v : 16u + lane;
+    const unsigned same = __match_any_sync(0xffffffffu, b);
+    const unsigned rank = __popc(same & ((1u << lane) - 1u));
+    const unsigned before = valid ? s_cnt[b] : 0u;
+    const bool keep = valid && before + rank < quota;
+    __syncwarp();
+    if (valid && rank == 0) s_cnt[b] = before + __popc(same);  // counts past the quota change nothing
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    if (keep) out[kept + __popc(bal & ((1u << lane) - 1u))] = p;
+    kept += __popc(bal);
+    __syncwarp();
+  }
+  if (lane == 0) layer_surv[frame * kMaxLayers + layer] = kept;
+}
+
 // One CTA per frame: sub-pixel refinement and key-point emission in layer-major order
 // (scale-space-layer-inl.h:386-412).
 __global__ void __launch_bounds__(256)
@@ -342,6 +382,11 @@ cudaError_t launch_harris_detect(const PyramidGeom& g, const HarrisWorkspace& hw
   dim3 gp((hw.det.corner_cap + 127) / 128, n_frames);
   harris_nms3d_kernel<<<gp, 128, 0, stream>>>(g, hp, hw.scores, hw.det.layer_start, hw.pts, hw.keep, hw.det.corner_cap, thr);
   harris_sort_kernel<<<dim3(g.n_layers, n_frames), kSortThreads, 0, stream>>>(g.n_layers, hw.det.layer_start, hw.pts, hw.keep, hw.sorted, hw.layer_kept, hw.det.corner_cap);
+  if (!(radius > 0.0)) {
+    harris_bucketing_kernel<<<dim3(g.n_layers, n_frames), 32, 0, stream>>>(g, hw.det.layer_start, hw.sorted, hw.layer_kept, hw.surv, hw.layer_surv, hw.det.corner_cap, max_kpt);
+    harris_emit_kernel<<<n_frames, 256, 0, stream>>>(g, hp, hw.scores, hw.det.layer_start, hw.surv, hw.layer_surv, hw.det.corner_cap, out, counts, kp_cap);
+    return cudaGetLastError();
+  }
   UniformityGeom ug;
   ug.occ_frame_bytes = hw.occ_frame_bytes;
   ug.scaling = (float)(15.0 / (double)(float)radius);

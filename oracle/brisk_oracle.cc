@@ -1127,9 +1127,21 @@ void HarrisDetect(const uint8_t* image, int w, int h, int octaves, double radius
     if (pts.empty()) continue;
     if (uniformity && r > 0.0) EnforceUniformity(r, l.h, l.w, max_kpt, &pts);
     else {
-      // KeyPointBucketing (key-point-bucketing-inl.h:44-112) is reached only with
-      // uniformityRadius <= 0 and is not restated yet.
+      // KeyPointBucketing (key-point-bucketing-inl.h:74-112) with the 4 x 4 buckets of ScaleSpaceLayer
+      // (scale-space-layer.h:73-74): KeyPointBuckets::filterKeyPoints (:44-72) sorts, then keeps a point while its
+      // bucket holds fewer than maxNumKpt / 16 points (key-point-bucketing.h:64-66, an unsigned int).  (The
+      // single-bucket partial_sort branch needs numBuckets == 1, which ScaleSpaceLayer never sets.  The
+      // reference reserves maxNumKpt entries first, so it throws for the default SIZE_MAX; callers pass a limit.)
+      const unsigned step_u = 1u + (unsigned)((l.w - 1u) / 4u), step_v = 1u + (unsigned)((l.h - 1u) / 4u);
+      const unsigned quota = (unsigned)(max_kpt / 16u);
+      unsigned count[4][4] = {};
       std::sort(pts.begin(), pts.end());
+      std::vector<ScoredPoint> kept;
+      for (const ScoredPoint& p : pts) {
+        unsigned* c = &count[p.x / step_u][p.y / step_v];
+        if (*c < quota) { ++*c; kept.push_back(p); }
+      }
+      pts.swap(kept);
     }
     for (const ScoredPoint& p : pts) {
       const int u = p.x, v = p.y;

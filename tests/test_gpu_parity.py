@@ -81,6 +81,16 @@ def test_detect_bit_exact(ctx, oracle, golden, thresh, octaves):
         assert kp_equal(det.detect(img), oracle.agast_detect(img, thresh, octaves))
 
 
+def test_detect_without_scale_suppression_single_layer(ctx, oracle, ref, golden):
+    # suppressScaleNonmaxima = false is defined for one layer only (the reference indexes layer 0's corner list
+    # with the other layers' counts, brisk-scale-space.cc:137); there it equals the compiled reference
+    for img in (golden["image0"], bb.synthetic_frame(500, 333, 3)):
+        got = bb.BriskFeatureDetector(55, 0, False, ctx=ctx).detect(img)
+        assert kp_equal(got, oracle.agast_detect(img, 55, 0, False)) and len(got) > 50
+        if ref is not None:
+            assert kp_equal(got, ref.agast_detect(img, 55, 0, False))
+
+
 def test_detect_tie_heavy(ctx, oracle):
     rng = np.random.default_rng(7)
     det = bb.BriskFeatureDetector(35, 3, ctx=ctx)
@@ -439,7 +449,20 @@ def test_harris_batch_config2(ctx, oracle):
         assert np.array_equal(desc[f, :n], d2)
 
 
+@pytest.mark.parametrize("octaves,radius,abs_thr,max_kpt", [(4, 0.0, 20.0, 400), (2, -1.0, 0.0, 64), (0, 0.0, 50.0, 100000), (3, 0.0, 5.0, 15)])
+def test_harris_key_point_bucketing_bit_exact(ctx, oracle, golden, octaves, radius, abs_thr, max_kpt):
+    # uniformityRadius <= 0: KeyPointBucketing, 4 x 4 buckets with maxNumKpt / 16 points each, per layer
+    det = bb.ScaleSpaceFeatureDetector(octaves, radius, abs_thr, max_kpt, ctx=ctx)
+    det.set_corner_capacity(800 * 640)
+    for img in (golden["image0"], bb.synthetic_frame(752, 480, 1000), bb.synthetic_frame(322, 241, 4)):
+        want = oracle.harris_detect(img, octaves, radius, abs_thr, max_kpt)
+        got = det.detect(img)
+        assert kp_equal(got, want)
+    assert max_kpt < 16 or len(got) > 0
+
+
 def test_harris_unsupported(ctx):
+    # bucketing with the default maxNumKpt = SIZE_MAX: the reference throws std::length_error (reserve)
     with pytest.raises(bb.BriskError):
         bb.ScaleSpaceFeatureDetector(4, 0.0, 20.0, ctx=ctx).detect(bb.synthetic_frame(320, 240, 1))
 

@@ -102,7 +102,7 @@ def test_describe_vs_ref(oracle, ref, golden, version, ps, rot, scale):
         assert np.array_equal(pa[key], pb[key]), key
 
 
-@pytest.mark.parametrize("octaves,radius,max_kpt", [(1, 30.0, -1), (4, 30.0, -1), (2, 10.0, 300)])
+@pytest.mark.parametrize("octaves,radius,max_kpt", [(1, 30.0, -1), (4, 30.0, -1), (2, 10.0, 300), (4, 0.0, 400), (2, -1.0, 64), (0, 0.0, 100000)])
 def test_harris_detect_vs_ref(oracle, ref, golden, octaves, radius, max_kpt):
     for img in (golden["image1"], synthetic_frame(752, 480, 1001)):
         assert kp_equal(oracle.harris_detect(img, octaves, radius, 20.0, max_kpt), ref.harris_detect(img, octaves, radius, 20.0, max_kpt))
