@@ -70,31 +70,6 @@ nms_prefix_kernel(PyramidGeom g, DetectWorkspace ws) {
   }
 }
 
-__global__ void __launch_bounds__(128)
-nms_checks_kernel(PyramidGeom g, DetectWorkspace ws) {
-  const int frame = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = min(ws.layer_start[(long long)frame * (kMaxLayers + 1) + g.n_layers], ws.corner_cap);
-  if (k >= n) return;
-  int x, y, layer;
-  unpack_corner(ws.corners[(long long)frame * ws.corner_cap + k], &x, &y, &layer);
-  const LayerView own = make_view(g, ws, frame, layer);
-  uint16_t* e = own.cm + (long long)y * own.pitch + x;
-  const uint16_t ev = *e;
-  if ((ev & kCmDecided) && !(ev & kCmAccept)) return;
-  // only the corner's own layer and its two neighbours are looked at
-  const LayerView below = make_view(g, ws, frame, layer > 0 ? layer - 1 : 0);
-  const LayerView above = make_view(g, ws, frame, layer + 1 < g.n_layers ? layer + 1 : layer);
-  CheckResult r;
-  const bool ok = nms_checks3(below, own, above, g.n_layers, layer, x, y, &r);
-  if (ok) *e = ev | kCmChecks;
-  // kept even when the checks fail: the footprint of the scan of the layer above is needed by the chain kernel
-  *reinterpret_cast<CheckResult*>(ws.checks + ((long long)frame * ws.corner_cap + k) * 8) = r;
-  // A corner accepted without a tie leaves its footprint on the layer above right away (the touch map is
-  // only read by the chain kernel); tying corners do so once they are resolved.
-  if ((ev & kCmAccept) && g.n_layers > 1 && layer < g.n_layers - 1) mark_above1(above, layer, x, y, r);
-}
-
 // Warp-cooperative IsMax2D tie path for one tying corner (same result as nms_tie_decide, which
 // states the rule pixel by pixel).  The 64 corner-map entries of the 8x8 window are staged by the
 // lanes (two each); lanes 0..24 own one pixel of the 5x5 neighbourhood each and reconstruct its
@@ -218,6 +193,44 @@ __device__ __forceinline__ void warp_mark_above(const LayerView& nb, int layer, 
     else mark_cell(nb, xf, yf);
   }
   if (((above_steps >> 8) & 1) && lane < 9) mark_px(nb, (above_argmax & 0xffff) + lane % 3 - 1, (above_argmax >> 16) + lane / 3 - 1);
+}
+
+__global__ void __launch_bounds__(128, 5)
+nms_checks_kernel(PyramidGeom g, DetectWorkspace ws) {
+  const int frame = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(ws.layer_start[(long long)frame * (kMaxLayers + 1) + g.n_layers], ws.corner_cap);
+  if (blockIdx.x * blockDim.x >= n) return;
+  int x = 0, y = 0, layer = 0;
+  CheckResult r;
+  bool mark = false;
+  if (k < n) {
+    unpack_corner(ws.corners[(long long)frame * ws.corner_cap + k], &x, &y, &layer);
+    const LayerView own = make_view(g, ws, frame, layer);
+    uint16_t* e = own.cm + (long long)y * own.pitch + x;
+    const uint16_t ev = *e;
+    if (!(ev & kCmDecided) || (ev & kCmAccept)) {
+      // only the corner's own layer and its two neighbours are looked at
+      const LayerView below = make_view(g, ws, frame, layer > 0 ? layer - 1 : 0);
+      const LayerView above = make_view(g, ws, frame, layer + 1 < g.n_layers ? layer + 1 : layer);
+      const bool ok = nms_checks3(below, own, above, g.n_layers, layer, x, y, &r);
+      if (ok) *e = ev | kCmChecks;
+      // kept even when the checks fail: the footprint of the scan of the layer above is needed by the chain kernel
+      *reinterpret_cast<CheckResult*>(ws.checks + ((long long)frame * ws.corner_cap + k) * 8) = r;
+      // A corner accepted without a tie leaves its footprint on the layer above right away (the touch map is
+      // only read by the chain kernel); tying corners do so once they are resolved.
+      mark = (ev & kCmAccept) && g.n_layers > 1 && layer < g.n_layers - 1;
+    }
+  }
+  // the marks of the warp's corners, one corner at a time with one lane per scan position
+  unsigned todo = __ballot_sync(0xffffffffu, mark);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int mx = __shfl_sync(0xffffffffu, x, src), my = __shfl_sync(0xffffffffu, y, src), ml = __shfl_sync(0xffffffffu, layer, src);
+    const int ms = __shfl_sync(0xffffffffu, r.above_steps, src), ma = __shfl_sync(0xffffffffu, r.above_argmax, src);
+    warp_mark_above(make_view(g, ws, frame, ml + 1), ml, mx, my, ms, ma);
+  }
 }
 
 // One CTA per frame, layers in order (layer i+1 needs the touch marks that layer i's accepted

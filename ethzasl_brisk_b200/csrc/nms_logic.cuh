@@ -155,11 +155,13 @@ BRISK_HD float tile_patch3x3(const ScoreTile& t, int x, int y, float* dx, float*
 }
 
 BRISK_HD float patch3x3(const LayerView& L, int x, int y, float* dx, float* dy, int* center) {
-  const int s00 = score1(L, x - 1, y - 1), s10 = score1(L, x, y - 1), s20 = score1(L, x + 1, y - 1);
-  const int s21 = score1(L, x + 1, y), s11 = score1(L, x, y), s01 = score1(L, x - 1, y);
-  const int s02 = score1(L, x - 1, y + 1), s12 = score1(L, x, y + 1), s22 = score1(L, x + 1, y + 1);
-  if (center) *center = s11;
-  return subpixel2d(s00, s01, s02, s10, s11, s12, s20, s21, s22, dx, dy);
+  int s[9];  // s[3 * column + row], the reference's s_<column>_<row>; one copy of the score code
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int k = 0; k < 9; ++k) s[k] = score1(L, x + k / 3 - 1, y + k % 3 - 1);
+  if (center) *center = s[4];
+  return subpixel2d(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], dx, dy);
 }
 
 // Pixel rectangle of the neighbouring layer that a scan of the patch
@@ -179,61 +181,49 @@ BRISK_HD void fill_scan_tile(const LayerView& nb, float x_1, float x1, float y_1
 // adds the tie rule of :987-1010 on interior pixels.  `steps` receives the
 // number of patch positions that were evaluated: the visiting order is fixed,
 // so this number identifies the scan's cache footprint (replay_scan_marks).
-template <bool BELOW>
-BRISK_HD bool scan_patch(const ScoreTile& nb, float x_1, float x1, float y_1, float y1, int threshold, float* max_out,
+BRISK_HD bool scan_patch(bool BELOW, const ScoreTile& nb, float x_1, float x1, float y_1, float y1, int threshold, float* max_out,
                          int* mx, int* my, int* steps) {
-  int max_x = (int)(x_1 + 1), max_y = (int)(y_1 + 1);
-  float tmp;
-  int n = 1;
-  float max = (float)tile_score_f(nb, x_1, y_1);
-#define BRISK_ABORT_IF_ABOVE(v) if ((v) > (float)threshold) { *steps = n; return false; }
-  BRISK_ABORT_IF_ABOVE(max)
+  // The reference walks a grid of positions in row-major order: columns x_1, the integers xb..xe, x1 and
+  // rows y_1, yb..ye, y1 (float positions are bilinear reads, interior ones plain look-ups).  One loop
+  // body serves all of them (a single copy of the score code matters: these kernels are bound by
+  // instruction fetch).  An arg-max on a border column / row is recorded as xb / xe (yb / ye).
   const int xb = (int)(x_1 + 1), xe = (int)x1, yb = (int)(y_1 + 1), ye = (int)y1;
-  for (int x = xb; x <= xe; ++x) {
-    ++n;
-    tmp = (float)tile_score_f(nb, (float)x, y_1);
-    BRISK_ABORT_IF_ABOVE(tmp)
-    if (tmp > max) { max = tmp; max_x = x; }
-  }
-  ++n;
-  tmp = (float)tile_score_f(nb, x1, y_1);
-  BRISK_ABORT_IF_ABOVE(tmp)
-  if (tmp > max) { max = tmp; max_x = xe; }
-  for (int y = yb; y <= ye; ++y) {
-    ++n;
-    tmp = (float)tile_score_f(nb, x_1, (float)y);
-    BRISK_ABORT_IF_ABOVE(tmp)
-    if (tmp > max) { max = tmp; max_x = xb; max_y = y; }
-    for (int x = xb; x <= xe; ++x) {
+  const int ncols = (xe >= xb ? xe - xb + 1 : 0) + 2, nrows = (ye >= yb ? ye - yb + 1 : 0) + 2;
+  int max_x = xb, max_y = yb, n = 0;
+  float max = 0.0f;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int r = 0; r < nrows; ++r) {
+    const bool yi = r > 0 && r < nrows - 1;
+    const float yf = r == 0 ? y_1 : (yi ? (float)(yb + r - 1) : y1);
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (int c = 0; c < ncols; ++c) {
+      const bool xi = c > 0 && c < ncols - 1;
+      const float xf = c == 0 ? x_1 : (xi ? (float)(xb + c - 1) : x1);
+      const int px = xb + c - 1, py = yb + r - 1;  // the pixel itself on interior positions
+      const float tmp = (xi && yi) ? (float)nb.get(px, py) : (float)tile_score_f(nb, xf, yf);
       ++n;
-      tmp = (float)nb.get(x, y);
-      BRISK_ABORT_IF_ABOVE(tmp)
-      if (BELOW && tmp == max) {
-        const int t1 = 2 * (nb.get(x - 1, y) + nb.get(x + 1, y) + nb.get(x, y + 1) + nb.get(x, y - 1)) +
-                       (nb.get(x + 1, y + 1) + nb.get(x - 1, y + 1) + nb.get(x + 1, y - 1) + nb.get(x - 1, y - 1));
+      if (r < nrows - 1 && tmp > (float)threshold) { *steps = n; return false; }  // not tested on the bottom row
+      if (BELOW && xi && yi && tmp == max) {
+        // tie rule of GetScoreMaxBelow (:987-1010): the larger 3x3 binomial sum (centre excluded) wins
+        const int t1 = 2 * (nb.get(px - 1, py) + nb.get(px + 1, py) + nb.get(px, py + 1) + nb.get(px, py - 1)) +
+                       (nb.get(px + 1, py + 1) + nb.get(px - 1, py + 1) + nb.get(px + 1, py - 1) + nb.get(px - 1, py - 1));
         const int t2 = 2 * (nb.get(max_x - 1, max_y) + nb.get(max_x + 1, max_y) + nb.get(max_x, max_y + 1) + nb.get(max_x, max_y - 1)) +
                        (nb.get(max_x + 1, max_y + 1) + nb.get(max_x - 1, max_y + 1) + nb.get(max_x + 1, max_y - 1) + nb.get(max_x - 1, max_y - 1));
-        if (t1 > t2) { max_x = x; max_y = y; }
+        if (t1 > t2) { max_x = px; max_y = py; }
       }
-      if (tmp > max) { max = tmp; max_x = x; max_y = y; }
+      if (n == 1 || tmp > max) {
+        max = tmp;
+        if (n > 1) {
+          max_x = c == 0 ? xb : (xi ? px : xe);
+          if (r > 0) max_y = yi ? py : ye;
+        }
+      }
     }
-    ++n;
-    tmp = (float)tile_score_f(nb, x1, (float)y);
-    BRISK_ABORT_IF_ABOVE(tmp)
-    if (tmp > max) { max = tmp; max_x = xe; max_y = y; }
   }
-#undef BRISK_ABORT_IF_ABOVE
-  ++n;
-  tmp = (float)tile_score_f(nb, x_1, y1);
-  if (tmp > max) { max = tmp; max_x = xb; max_y = ye; }
-  for (int x = xb; x <= xe; ++x) {
-    ++n;
-    tmp = (float)tile_score_f(nb, (float)x, y1);
-    if (tmp > max) { max = tmp; max_x = x; max_y = ye; }
-  }
-  ++n;
-  tmp = (float)tile_score_f(nb, x1, y1);
-  if (tmp > max) { max = tmp; max_x = xe; max_y = ye; }
   *max_out = max; *mx = max_x; *my = max_y; *steps = n;
   return true;
 }
@@ -267,19 +257,33 @@ struct AboveFootprint {
   int mx, my;     // arg-max (valid when completed)
 };
 
-// GetScoreMaxAbove (brisk-scale-space.cc:757-915).  `layer` is the index of
-// the corner's own layer, `nb` the layer above it.  Pure; the footprint is
-// returned for mark_above.
-BRISK_HD float score_max_above(const LayerView& nb, int layer, int x, int y, int thr, bool* ismax, float* dx, float* dy,
-                               AboveFootprint* fp, int* tile_violations) {
+// Patch of the layer below that GetScoreMaxBelow scans for a corner of `layer` (:917-933).
+BRISK_HD void below_patch(int layer, int x, int y, float* x_1, float* x1, float* y_1, float* y1) {
+  if ((layer & 1) == 0) {
+    *x_1 = (float)((double)(float)(8 * x + 1 - 4) / 6.0); *x1 = (float)((double)(float)(8 * x + 1 + 4) / 6.0);
+    *y_1 = (float)((double)(float)(8 * y + 1 - 4) / 6.0); *y1 = (float)((double)(float)(8 * y + 1 + 4) / 6.0);
+  } else {
+    *x_1 = (float)((double)(float)(6 * x + 1 - 3) / 4.0); *x1 = (float)((double)(float)(6 * x + 1 + 3) / 4.0);
+    *y_1 = (float)((double)(float)(6 * y + 1 - 3) / 4.0); *y1 = (float)((double)(float)(6 * y + 1 + 3) / 4.0);
+  }
+}
+
+// GetScoreMaxAbove (brisk-scale-space.cc:757-915) / GetScoreMaxBelow (:917-1099) in one body (the two
+// differ in the patch, the tie rule of the scan and the mapping back; one body keeps the kernels' code
+// small enough for the instruction cache).  `layer` is the index of the corner's own layer, `nb` the
+// neighbouring layer.  Pure; the cache footprint of the scan is returned (it matters for the layer above
+// only: look-ups on the layer below land on a layer whose own NMS is already finished).
+BRISK_HD float score_max_side(bool below, const LayerView& nb, int layer, int x, int y, int thr, bool* ismax, float* dx,
+                              float* dy, AboveFootprint* fp, int* tile_violations) {
   *ismax = false;
   float x_1, x1, y_1, y1;
-  above_patch(layer, x, y, &x_1, &x1, &y_1, &y1);
+  if (below) below_patch(layer, x, y, &x_1, &x1, &y_1, &y1);
+  else above_patch(layer, x, y, &x_1, &x1, &y_1, &y1);
   ScoreTile tile;
   fill_scan_tile(nb, x_1, x1, y_1, y1, &tile);
   float max; int mx = 0, my = 0, steps = 0;
   fp->completed = 0; fp->mx = 0; fp->my = 0;
-  const bool ok = scan_patch<false>(tile, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my, &steps);
+  const bool ok = scan_patch(below, tile, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my, &steps);
   fp->steps = steps;
   float refined = 0.0f, dx1 = 0.0f, dy1 = 0.0f;
   if (ok) refined = tile_patch3x3(tile, mx, my, &dx1, &dy1);
@@ -291,12 +295,21 @@ BRISK_HD float score_max_above(const LayerView& nb, int layer, int x, int y, int
   if (!ok) return 0.0f;
   fp->completed = 1; fp->mx = mx; fp->my = my;
   const float rx = (float)mx + dx1, ry = (float)my + dy1;
-  if ((layer & 1) == 0) {
-    *dx = (rx * 6.0f + 1.0f) / 4.0f - (float)x;
-    *dy = (ry * 6.0f + 1.0f) / 4.0f - (float)y;
+  const bool octave = (layer & 1) == 0;
+  if (!below) {
+    if (octave) {
+      *dx = (rx * 6.0f + 1.0f) / 4.0f - (float)x;
+      *dy = (ry * 6.0f + 1.0f) / 4.0f - (float)y;
+    } else {
+      *dx = (float)(((double)rx * 8.0 + 1.0) / 6.0 - (double)(float)x);
+      *dy = (float)(((double)ry * 8.0 + 1.0) / 6.0 - (double)(float)y);
+    }
+  } else if (octave) {
+    *dx = (float)(((double)rx * 6.0 + 1.0) / 8.0 - (double)(float)x);
+    *dy = (float)(((double)ry * 6.0 + 1.0) / 8.0 - (double)(float)y);
   } else {
-    *dx = (float)(((double)rx * 8.0 + 1.0) / 6.0 - (double)(float)x);
-    *dy = (float)(((double)ry * 8.0 + 1.0) / 6.0 - (double)(float)y);
+    *dx = (float)(((double)rx * 4.0 - 1.0) / 6.0 - (double)(float)x);
+    *dy = (float)(((double)ry * 4.0 - 1.0) / 6.0 - (double)(float)y);
   }
   const bool inside = saturate1(dx, dy);
   *ismax = true;
@@ -336,45 +349,6 @@ done:
       for (int dx = -1; dx <= 1; ++dx) mark_px(nb, fp.mx + dx, fp.my + dy);
 }
 
-// GetScoreMaxBelow (brisk-scale-space.cc:917-1099); `nb` is the layer below.
-// Its look-ups land on a layer whose own NMS is already finished, so its cache
-// footprint is never observed and is not recorded.
-BRISK_HD float score_max_below(const LayerView& nb, int layer, int x, int y, int thr, bool* ismax, float* dx, float* dy,
-                               int* tile_violations) {
-  *ismax = false;
-  float x_1, x1, y_1, y1;
-  if ((layer & 1) == 0) {
-    x_1 = (float)((double)(float)(8 * x + 1 - 4) / 6.0); x1 = (float)((double)(float)(8 * x + 1 + 4) / 6.0);
-    y_1 = (float)((double)(float)(8 * y + 1 - 4) / 6.0); y1 = (float)((double)(float)(8 * y + 1 + 4) / 6.0);
-  } else {
-    x_1 = (float)((double)(float)(6 * x + 1 - 3) / 4.0); x1 = (float)((double)(float)(6 * x + 1 + 3) / 4.0);
-    y_1 = (float)((double)(float)(6 * y + 1 - 3) / 4.0); y1 = (float)((double)(float)(6 * y + 1 + 3) / 4.0);
-  }
-  ScoreTile tile;
-  fill_scan_tile(nb, x_1, x1, y_1, y1, &tile);
-  float max; int mx = 0, my = 0, steps = 0;
-  const bool ok = scan_patch<true>(tile, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my, &steps);
-  float refined = 0.0f, dx1 = 0.0f, dy1 = 0.0f;
-  if (ok) refined = tile_patch3x3(tile, mx, my, &dx1, &dy1);
-#ifdef BRISK_TILE_CHECK
-  if (tile_violations) *tile_violations += tile.violations;
-#else
-  (void)tile_violations;
-#endif
-  if (!ok) return 0.0f;
-  const float rx = (float)mx + dx1, ry = (float)my + dy1;
-  if ((layer & 1) == 0) {
-    *dx = (float)(((double)rx * 6.0 + 1.0) / 8.0 - (double)(float)x);
-    *dy = (float)(((double)ry * 6.0 + 1.0) / 8.0 - (double)(float)y);
-  } else {
-    *dx = (float)(((double)rx * 4.0 - 1.0) / 6.0 - (double)(float)x);
-    *dy = (float)(((double)ry * 4.0 - 1.0) / 6.0 - (double)(float)y);
-  }
-  const bool inside = saturate1(dx, dy);
-  *ismax = true;
-  return inside ? (refined > max ? refined : max) : max;
-}
-
 // ---------------------------------------------------------------------------
 // Phase 1: the eight comparisons of IsMax2D (brisk-scale-space.cc:437-462).
 // Order independent.  Updates the corner's map entry; for tying corners also
@@ -387,6 +361,9 @@ BRISK_HD void nms_prefix(const LayerView& L, int x, int y, uint8_t fwin[25]) {
   int calls = 8;
   bool tie = false, rejected = false;
   int f8[8];
+#ifdef __CUDA_ARCH__
+#pragma unroll 1  // one copy of the score code: the kernels are bound by instruction fetch otherwise
+#endif
   for (int j = 0; j < 8; ++j) {
     int dx, dy;
     isMax2dOffset(j, &dx, &dy);
@@ -407,15 +384,18 @@ BRISK_HD void nms_prefix(const LayerView& L, int x, int y, uint8_t fwin[25]) {
   else e |= kCmTie;
   L.cm[o] = e;
   if (!rejected && tie) {
-    for (int wy = -2; wy <= 2; ++wy)
-      for (int wx = -2; wx <= 2; ++wx) {
-        const int qx = x + wx, qy = y + wy;
-        int v;
-        if (wx >= -1 && wx <= 1 && wy >= -1 && wy <= 1 && (wx || wy)) v = f8[isMax2dIndex(wx, wy)];
-        else if ((wx == 0 && wy == 0) || in_border(L, qx, qy)) v = 0;
-        else v = (L.cm[(long long)qy * L.pitch + qx] & kCmT) ? 0 : fastF(L, qx, qy);
-        fwin[(wy + 2) * 5 + wx + 2] = (uint8_t)v;
-      }
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (int i = 0; i < 25; ++i) {
+      const int wx = i % 5 - 2, wy = i / 5 - 2;
+      const int qx = x + wx, qy = y + wy;
+      int v;
+      if (wx >= -1 && wx <= 1 && wy >= -1 && wy <= 1 && (wx || wy)) v = f8[isMax2dIndex(wx, wy)];
+      else if ((wx == 0 && wy == 0) || in_border(L, qx, qy)) v = 0;
+      else v = (L.cm[(long long)qy * L.pitch + qx] & kCmT) ? 0 : fastF(L, qx, qy);
+      fwin[i] = (uint8_t)v;
+    }
   }
 }
 
@@ -439,28 +419,39 @@ BRISK_HD bool nms_checks3(const LayerView& below, const LayerView& L, const Laye
   r->max_above = 0; r->dxa = 0; r->dya = 0; r->max_below = 0; r->dxb = 0; r->dyb = 0;
   r->above_steps = 0; r->above_argmax = 0;
   if (n_layers == 1) return true;
-  bool ismax;
-  if (layer == n_layers - 1) {
-    r->max_below = score_max_below(below, layer, x, y, center, &ismax, &r->dxb, &r->dyb, tile_violations);
-    return ismax;
+  // the layer above first (Refine3D :540-556; none for the last layer :213-222), then the layer below; both run
+  // through one copy of the scan code
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int side = layer == n_layers - 1 ? 1 : 0; side < 2; ++side) {
+    if (side == 1 && layer == 0) break;
+    bool ismax;
+    float dx = 0.0f, dy = 0.0f;
+    AboveFootprint fp;
+    const float m = score_max_side(side == 1, side == 1 ? below : above, layer, x, y, center, &ismax, &dx, &dy, &fp, tile_violations);
+    if (side == 0) {
+      r->max_above = m; r->dxa = dx; r->dya = dy;
+      r->above_steps = fp.steps | (fp.completed << 8);
+      r->above_argmax = fp.mx | (fp.my << 16);
+      if (!ismax) return false;
+    } else {
+      r->max_below = m; r->dxb = dx; r->dyb = dy;
+      return ismax;
+    }
   }
-  AboveFootprint fp;
-  r->max_above = score_max_above(above, layer, x, y, center, &ismax, &r->dxa, &r->dya, &fp, tile_violations);
-  r->above_steps = fp.steps | (fp.completed << 8);
-  r->above_argmax = fp.mx | (fp.my << 16);
-  if (!ismax) return false;
-  if (layer == 0) {
-    // guess the virtual intra-octave below octave 0 with the 5-8 mask (:558-592)
-    const int s00 = score58(L, x - 1, y - 1), s10 = score58(L, x, y - 1), s20 = score58(L, x + 1, y - 1);
-    const int s21 = score58(L, x + 1, y), s11 = score58(L, x, y), s01 = score58(L, x - 1, y);
-    const int s02 = score58(L, x - 1, y + 1), s12 = score58(L, x, y + 1), s22 = score58(L, x + 1, y + 1);
-    int best = imax(imax(imax(s00, s10), imax(s20, s21)), imax(imax(s11, s01), imax(imax(s02, s12), s22)));
-    subpixel2d(s00, s01, s02, s10, s11, s12, s20, s21, s22, &r->dxb, &r->dyb);
-    r->max_below = (float)best;
-    return true;
+  // layer 0: guess the virtual intra-octave below octave 0 with the 5-8 mask (:558-592)
+  int s[9], best = 0;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int k = 0; k < 9; ++k) {  // s[3 * column + row], the reference's s_<column>_<row>
+    s[k] = score58(L, x + k / 3 - 1, y + k % 3 - 1);
+    best = imax(best, s[k]);
   }
-  r->max_below = score_max_below(below, layer, x, y, center, &ismax, &r->dxb, &r->dyb, tile_violations);
-  return ismax;
+  subpixel2d(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], &r->dxb, &r->dyb);
+  r->max_below = (float)best;
+  return true;
 }
 
 BRISK_HD bool nms_checks(const LayerView* layers, int n_layers, int layer, int x, int y, CheckResult* r,
