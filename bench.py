@@ -145,7 +145,12 @@ def run_gpu(args):
 
     import ethzasl_brisk_b200 as bb
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    # keep stdout to the one JSON line: NCCL prints its version banner to stdout from level WARN upwards
+    if "BENCH_NCCL_DEBUG" in os.environ:
+        os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
+    else:
+        os.environ.pop("NCCL_DEBUG", None)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

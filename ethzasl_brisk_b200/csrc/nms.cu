@@ -75,8 +75,8 @@ nms_prefix_kernel(PyramidGeom g, DetectWorkspace ws) {
 // lanes (two each); lanes 0..24 own one pixel of the 5x5 neighbourhood each and reconstruct its
 // cache state together, stepping through the raster-earlier corners of the window (a handful,
 // found with two ballots) -- under both assumptions about the pending verdicts.  The 3x3 binomial
-// sums around the centre and around every tying neighbour are formed with shuffles.  Returns 1
-// accept, 0 reject, -1 not decidable yet; uniform across the warp.
+// sums around the centre and around every tying neighbour are formed with shuffles, as intervals.
+// Returns 1 accept, 0 reject, -1 not decidable yet; uniform across the warp.
 // Everything warp_tie_decide reads from global memory for one corner, per lane: two entries of the
 // 8x8 corner-map window, the FAST score and the touch mark of the lane's pixel of the 5x5
 // neighbourhood, and the scan footprint for warp_mark_above.  Loaded one corner ahead of its use.
@@ -155,21 +155,34 @@ __device__ __forceinline__ int warp_tie_decide(const LayerView& L, int mode, int
   else if (tq) v = v1 = ring1 ? F : tq;  // a neighbouring corner: its T (stored in fwin by nms_prefix)
   else if (ring1) { v = st0 > 2 ? st0 : (F >= center ? F : 0); v1 = st1 > 2 ? st1 : (F >= center ? F : 0); }
   else { v = st0; v1 = st1; }
-  if (__any_sync(kFull, pending && v != v1)) { __syncwarp(); return -1; }
-  // binomial 3x3 sum centred on every lane's own pixel (meaningful for the inner 3x3 lanes)
-  int sum = 0;
+  // binomial 3x3 sums centred on every lane's own pixel (meaningful for the inner 3x3 lanes), as intervals:
+  // `sum` with the pending verdicts taken as reject, `sum1` as accept (nms_tie_decide)
+  int sum = 0, sum1 = 0;
 #pragma unroll
   for (int wy = -1; wy <= 1; ++wy)
 #pragma unroll
     for (int wx = -1; wx <= 1; ++wx) {
       const int src = lane + wy * 5 + wx;
-      const int t = __shfl_sync(kFull, v, src & 31);
-      sum += ((wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1)) * t;
+      sum += ((wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1)) * __shfl_sync(kFull, v, src & 31);
     }
-  const int smoothed = __shfl_sync(kFull, sum, 12);
+  if (pending) {
+#pragma unroll
+    for (int wy = -1; wy <= 1; ++wy)
+#pragma unroll
+      for (int wx = -1; wx <= 1; ++wx) {
+        const int src = lane + wy * 5 + wx;
+        sum1 += ((wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1)) * __shfl_sync(kFull, v1, src & 31);
+      }
+  } else {
+    sum1 = sum;
+  }
+  const int s_lo = __shfl_sync(kFull, sum, 12), s_hi = __shfl_sync(kFull, sum1, 12);
   const bool inner = lane < 25 && ring1 && lane != 12;
-  const bool beaten = inner && v == center && sum > smoothed;
-  const int verdict = __any_sync(kFull, beaten) ? 0 : 1;
+  // a certainly tying neighbour that certainly beats the centre rejects; a possibly tying one that possibly
+  // does leaves the verdict open
+  const bool lost = inner && v == center && v1 == center && sum > s_hi;
+  const bool may_lose = inner && (v == center || v1 == center) && sum1 > s_lo;
+  const int verdict = __any_sync(kFull, lost) ? 0 : (__any_sync(kFull, may_lose) ? -1 : 1);
   __syncwarp();
   return verdict;
 }

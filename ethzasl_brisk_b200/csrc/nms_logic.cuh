@@ -564,25 +564,38 @@ BRISK_HD int nms_tie_decide(const LayerView& L, int mode, int x, int y, const ui
   const bool pending = load_tie_window(L, x, y, scratch, stride);
   const TieWindow W{scratch, stride, x - 4, y - 4};
   const int center = W.at(x, y) & kCmT;
-  int v[25];
+  // every value is known up to the pending verdicts: v0 with all of them taken as reject, v1 as accept
+  // (v0 <= v1, and the true value is one of the two)
+  int v0[25], v1[25];
   for (int i = 0; i < 25; ++i) {
     const int ox = i % 5 - 2, oy = i / 5 - 2;
-    v[i] = tie_pixel_value(L, W, mode, x, y, ox, oy, fwin[i], center);
-    if (pending && tie_pixel_value(L, W, mode, x, y, ox, oy, fwin[i], center, true) != v[i]) return -1;
+    v0[i] = tie_pixel_value(L, W, mode, x, y, ox, oy, fwin[i], center);
+    v1[i] = pending ? tie_pixel_value(L, W, mode, x, y, ox, oy, fwin[i], center, true) : v0[i];
   }
-  // 3x3 binomial sums (weights 4 / 2 / 1) around the centre and around every tying neighbour
-  int smoothed = 0;
+  // 3x3 binomial sums (weights 4 / 2 / 1) around the centre and around every tying neighbour, as intervals.
+  // Reject if a certainly tying neighbour certainly beats the centre, accept if no possibly tying one possibly
+  // does; otherwise the verdict depends on a pending one.
+  int s_lo = 0, s_hi = 0;
   for (int wy = -1; wy <= 1; ++wy)
-    for (int wx = -1; wx <= 1; ++wx) smoothed += ((wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1)) * v[(2 + wy) * 5 + 2 + wx];
+    for (int wx = -1; wx <= 1; ++wx) {
+      const int wgt = (wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1), i = (2 + wy) * 5 + 2 + wx;
+      s_lo += wgt * v0[i]; s_hi += wgt * v1[i];
+    }
+  bool may_lose = false;
   for (int ty = -1; ty <= 1; ++ty)
     for (int tx = -1; tx <= 1; ++tx) {
-      if ((tx == 0 && ty == 0) || v[(2 + ty) * 5 + 2 + tx] != center) continue;
-      int other = 0;
+      const int t = (2 + ty) * 5 + 2 + tx;
+      if ((tx == 0 && ty == 0) || (v0[t] != center && v1[t] != center)) continue;
+      int o_lo = 0, o_hi = 0;
       for (int wy = -1; wy <= 1; ++wy)
-        for (int wx = -1; wx <= 1; ++wx) other += ((wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1)) * v[(2 + ty + wy) * 5 + 2 + tx + wx];
-      if (other > smoothed) return 0;
+        for (int wx = -1; wx <= 1; ++wx) {
+          const int wgt = (wx == 0 ? 2 : 1) * (wy == 0 ? 2 : 1), i = (2 + ty + wy) * 5 + 2 + tx + wx;
+          o_lo += wgt * v0[i]; o_hi += wgt * v1[i];
+        }
+      if (v0[t] == center && v1[t] == center && o_lo > s_hi) return 0;
+      if (o_hi > s_lo) may_lose = true;
     }
-  return 1;
+  return may_lose ? -1 : 1;
 }
 
 // ---------------------------------------------------------------------------
