@@ -17,25 +17,56 @@
 
 namespace briskb200 {
 
-constexpr int kDetTW = 128, kDetTH = 64, kDetThreads = 256;
-constexpr int kDetStrip = 32;                 // rows per thread: 2 strips of 32 rows, 128 columns each
+constexpr int kDetTW = 256, kDetTH = 60, kDetThreads = 128;
+constexpr int kDetStrip = 30;                 // rows per thread: 2 strips of 30 rows; a thread owns 4 adjacent columns
+constexpr int kDetRows = kDetStrip + 6;       // source rows a thread walks (36 = 3 * 12, the unroll period)
 constexpr int kDetSW = kDetTW + 8;            // staged row: [x0-4, x0+TW+4), 4-byte aligned
 constexpr int kDetSH = kDetTH + 6;            // staged rows: [y0-3, y0+TH+3)
+constexpr int kDetQueue = 6144;               // candidate queue (cx | ry << 8); beyond it candidates are tested in place
+constexpr uint32_t kB2None = 0x3fffu;         // contrast no pixel reaches: "threshold map below the lower bound"
+
+// 9-of-16 segment test of OastDetector9_16::detect on the staged tile (ring of agast/include/agast/oast9-16.h:99-116).
+__device__ __forceinline__ bool segment_test(const uint8_t (*s_img)[kDetSW], int sr, int sc, int b2) {
+  const int c = s_img[sr][sc], cb = c + b2, c_b = c - b2;
+  int r[16];
+  r[0] = s_img[sr][sc - 3];      r[1] = s_img[sr - 1][sc - 3]; r[2] = s_img[sr - 2][sc - 2]; r[3] = s_img[sr - 3][sc - 1];
+  r[4] = s_img[sr - 3][sc];      r[5] = s_img[sr - 3][sc + 1]; r[6] = s_img[sr - 2][sc + 2]; r[7] = s_img[sr - 1][sc + 3];
+  r[8] = s_img[sr][sc + 3];      r[9] = s_img[sr + 1][sc + 3]; r[10] = s_img[sr + 2][sc + 2]; r[11] = s_img[sr + 3][sc + 1];
+  r[12] = s_img[sr + 3][sc];     r[13] = s_img[sr + 3][sc - 1]; r[14] = s_img[sr + 2][sc - 2]; r[15] = s_img[sr + 1][sc - 3];
+  uint32_t mb = 0, md = 0;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { mb |= (uint32_t)(r[k] > cb) << k; md |= (uint32_t)(r[k] < c_b) << k; }
+  // 9 contiguous set bits on the circular 16-bit mask
+  mb |= mb << 16; md |= md << 16;
+  uint32_t xb = mb & (mb >> 1); xb &= xb >> 2; xb &= xb >> 4; xb &= mb >> 8;
+  uint32_t xd = md & (md >> 1); xd &= xd >> 2; xd &= xd >> 4; xd &= md >> 8;
+  return ((xb | xd) & 0xffffu) != 0;
+}
 
 // The reference's threshold map (brisk-layer.cc:278-598) is max - min over the centre, four diagonals
 // and four 3x3 blocks; that footprint is exactly the 37-pixel disk with row half-widths
 // 1,2,3,3,3,2,1 (it contains the 16-pixel FAST ring, which is why a corner's score equals its
-// threshold-map value).  Phase 1: each thread walks down one column; per row it forms the horizontal
-// max / min over widths 3, 5 and 7 from seven shared-memory bytes and folds them into seven rolling
-// per-output-row accumulators held in registers (no min/max planes are materialised), then runs the
-// cheap 4-point compass pre-test and queues the survivors.  Phase 2: the queue is processed densely,
-// one candidate per thread, with the full 9-of-16 run test -- so the expensive test only costs the
-// lanes that need it.
-__global__ void __launch_bounds__(kDetThreads, 3)
+// threshold-map value).
+//
+// Phase 1 works on packed pairs of pixels (two 16-bit lanes per register, VIMNMX3.U16x2): a thread owns
+// four adjacent columns x..x+3 as the pairs E = (x, x+2) and O = (x+1, x+3) and walks down 30 rows.  Per
+// source row it loads 12 staged bytes, spreads them into the pairs P_j = (b_j, b_j+2), forms the
+// horizontal max / min over widths 3, 5 and 7 with three 3-input operations each, and combines seven
+// rows with three more:  out(y) = max3(G(y-1), M7(y), H(y+3)),  G(r) = max3(M3(r-2), M5(r-1), M7(r)),
+// H(r) = max3(M7(r-2), M5(r-1), M3(r)); the short histories live in registers (the loop is unrolled by
+// 12, a multiple of every history depth, so all slots are static).  The 4-point compass pre-test (a
+// 9-arc holds at least two compass points) is done on the pairs as well: at least two compass pixels
+// brighter than c + b  <=>  the second largest exceeds it.  The verdicts are shifted into two 64-bit
+// registers (two bits per row) and the threshold-map values go to a byte plane in shared memory; the
+// survivors (a few per cent) are queued once the walk is over, so that the row loop has no divergent path.
+// Phase 2: the queue is processed densely, one candidate per thread, with the full 9-of-16 run test.
+__global__ void __launch_bounds__(kDetThreads)
 agast_detect_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restrict__ pyr, uint16_t* __restrict__ cm,
                     int* __restrict__ rowcnt, int total_rows, int row_off, int thresh) {
   __shared__ __align__(16) uint8_t s_img[kDetSH][kDetSW];
-  __shared__ uint32_t s_queue[kDetTW * kDetTH];  // cx | ry << 8 | T << 16
+  __shared__ __align__(4) uint8_t s_T[kDetTH][kDetTW];  // threshold-map values of the tile
+  __shared__ uint16_t s_queue[kDetQueue];  // cx | ry << 8
+  __shared__ uint16_t s_b2[256];           // threshold-map value -> contrast b of the segment test
   __shared__ int s_count;
   __shared__ int s_rows[kDetTH];
 
@@ -52,79 +83,141 @@ agast_detect_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restric
     if (y >= 0 && y < L.h && x >= 0 && x < L.pitch) v = *reinterpret_cast<const uint32_t*>(img + (long long)y * L.pitch + x);
     *reinterpret_cast<uint32_t*>(&s_img[r][4 * c]) = v;
   }
+  {
+    // ast-detector.h:62-68 and oast9-16.cc:86-100: no corner where T < (thresh * lower) / 100, else
+    // b = (clamp(T, lower, upper) * thresh) / 100
+    const int cmp = (thresh * kLowerThreshold) / 100;
+    for (int T = tid; T < 256; T += kDetThreads) {
+      const int t = T < kLowerThreshold ? kLowerThreshold : (T > kUpperThreshold ? kUpperThreshold : T);
+      s_b2[T] = (uint16_t)(T >= cmp ? (t * thresh) / 100 : kB2None);
+    }
+  }
+  for (int i = tid; i < kDetQueue / 2; i += kDetThreads) reinterpret_cast<uint32_t*>(s_queue)[i] = 0xffffffffu;
   if (tid == 0) s_count = 0;
   if (tid < kDetTH) s_rows[tid] = 0;
   __syncthreads();
 
-  const int cmp = (thresh * kLowerThreshold) / 100;  // ast-detector.h:62-68
   {
-    const int cx = tid & (kDetTW - 1), strip = tid >> 7;
-    const int x = x0 + cx;
+    const int g = tid & 63, strip = tid >> 6;
+    const int cx = 4 * g, x = x0 + cx;
     const int ys = y0 + strip * kDetStrip;  // first output row of this thread
     const int sc = cx + 4;                  // staged column of x
-    int hi[7], lo[7];                       // rolling accumulators, slot = (output row - (ys - 6)) % 7
+    if (ys < L.h && x < L.pitch) {
+      constexpr uint32_t kHi = 0x80008000u;
+      // histories, indexed by source row modulo their depth; [0] = max / pair E, see below
+      uint32_t m3[4][2], m5[4], m7[4][3], gg[4][4];  // [pair E max, pair E min, pair O max, pair O min]
+      uint32_t ce[6], co[6], le[3], lo[3], re[3], ro[3];  // centre / left (x-3) / right (x+3) pixels of the pairs
+      unsigned long long acc_lo = 0, acc_hi = 0;          // compass verdicts, two bits per row
+      int last_ry = 0;
 #pragma unroll
-    for (int k = 0; k < 7; ++k) { hi[k] = 0; lo[k] = 255; }
-    if (ys < L.h) {
-#pragma unroll 7
-      for (int i = 0; i < 42; ++i) {  // 42 = 6 groups of 7 >= kDetStrip + 6; slots are static after unrolling by 7
-        if (i >= kDetStrip + 6) break;
-        // source row r = ys - 3 + i  <->  staged row (ys - y0) + i
-        const uint8_t* row = &s_img[strip * kDetStrip + i][sc - 3];
-        const int a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3], a4 = row[4], a5 = row[5], a6 = row[6];
-        const int M3 = imax(imax(a2, a3), a4), M5 = imax(imax(M3, a1), a5), M7 = imax(imax(M5, a0), a6);
-        const int m3 = imin(imin(a2, a3), a4), m5 = imin(imin(m3, a1), a5), m7 = imin(imin(m5, a0), a6);
-        hi[(i + 6) % 7] = M3;                       lo[(i + 6) % 7] = m3;   // output row r+3 starts here
-        hi[(i + 5) % 7] = imax(hi[(i + 5) % 7], M5); lo[(i + 5) % 7] = imin(lo[(i + 5) % 7], m5);
-        hi[(i + 4) % 7] = imax(hi[(i + 4) % 7], M7); lo[(i + 4) % 7] = imin(lo[(i + 4) % 7], m7);
-        hi[(i + 3) % 7] = imax(hi[(i + 3) % 7], M7); lo[(i + 3) % 7] = imin(lo[(i + 3) % 7], m7);
-        hi[(i + 2) % 7] = imax(hi[(i + 2) % 7], M7); lo[(i + 2) % 7] = imin(lo[(i + 2) % 7], m7);
-        hi[(i + 1) % 7] = imax(hi[(i + 1) % 7], M5); lo[(i + 1) % 7] = imin(lo[(i + 1) % 7], m5);
-        hi[i % 7] = imax(hi[i % 7], M3);             lo[i % 7] = imin(lo[i % 7], m3);   // output row r-3 complete
+      for (int k = 0; k < 4; ++k) {
+        m3[k][0] = m3[k][1] = m5[k] = m7[k][0] = m7[k][1] = m7[k][2] = 0;
+        gg[k][0] = gg[k][1] = gg[k][2] = gg[k][3] = 0;
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) ce[k] = co[k] = 0;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) le[k] = lo[k] = re[k] = ro[k] = 0;
+#pragma unroll 12
+      for (int i = 0; i < kDetRows; ++i) {
+        // source row r = ys - 3 + i  <->  staged row (ys - y0) + i; bytes b0..b11 = staged columns sc-4 .. sc+7
+        const uint32_t* row = reinterpret_cast<const uint32_t*>(&s_img[strip * kDetStrip + i][sc - 4]);
+        const uint32_t w0 = row[0], w1 = row[1], w2 = row[2];
+        const uint32_t f0 = __funnelshift_r(w0, w1, 16), f1 = __funnelshift_r(w1, w2, 16);  // b2..b5, b6..b9
+        // P_j = (b_j, b_j+2) as two 16-bit lanes
+        const uint32_t P1 = __byte_perm(w0, 0, 0x4341), P2 = __byte_perm(f0, 0, 0x4240), P3 = __byte_perm(f0, 0, 0x4341);
+        const uint32_t P4 = __byte_perm(w1, 0, 0x4240), P5 = __byte_perm(w1, 0, 0x4341), P6 = __byte_perm(f1, 0, 0x4240);
+        const uint32_t P7 = __byte_perm(f1, 0, 0x4341), P8 = __byte_perm(w2, 0, 0x4240);
+        // horizontal extrema over widths 3 / 5 / 7: pair E is centred on P4, pair O on P5
+        uint32_t M3[4], M5[4], M7[4];
+        M3[0] = __vimax3_u16x2(P3, P4, P5); M5[0] = __vimax3_u16x2(M3[0], P2, P6); M7[0] = __vimax3_u16x2(M5[0], P1, P7);
+        M3[1] = __vimin3_u16x2(P3, P4, P5); M5[1] = __vimin3_u16x2(M3[1], P2, P6); M7[1] = __vimin3_u16x2(M5[1], P1, P7);
+        M3[2] = __vimax3_u16x2(P4, P5, P6); M5[2] = __vimax3_u16x2(M3[2], P3, P7); M7[2] = __vimax3_u16x2(M5[2], P2, P8);
+        M3[3] = __vimin3_u16x2(P4, P5, P6); M5[3] = __vimin3_u16x2(M3[3], P3, P7); M7[3] = __vimin3_u16x2(M5[3], P2, P8);
+        uint32_t out[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          uint32_t G, H;
+          if (k & 1) {
+            G = __vimin3_u16x2(m3[k][i % 2], m5[k], M7[k]);
+            H = __vimin3_u16x2(m7[k][(i + 1) % 3], m5[k], M3[k]);
+            out[k] = __vimin3_u16x2(gg[k][i % 4], m7[k][i % 3], H);
+          } else {
+            G = __vimax3_u16x2(m3[k][i % 2], m5[k], M7[k]);
+            H = __vimax3_u16x2(m7[k][(i + 1) % 3], m5[k], M3[k]);
+            out[k] = __vimax3_u16x2(gg[k][i % 4], m7[k][i % 3], H);
+          }
+          m3[k][i % 2] = M3[k]; m5[k] = M5[k]; m7[k][i % 3] = M7[k]; gg[k][i % 4] = G;
+        }
+        // pixels of output row y = r - 3: centre and x -+ 3 from three rows ago, (x, y - 3) from six rows ago
+        const uint32_t cE = ce[(i + 3) % 6], cO = co[(i + 3) % 6], nE = ce[i % 6], nO = co[i % 6];
+        const uint32_t lE = le[i % 3], lO = lo[i % 3], rE = re[i % 3], rO = ro[i % 3];
+        ce[i % 6] = P4; co[i % 6] = P5; le[i % 3] = P1; lo[i % 3] = P2; re[i % 3] = P7; ro[i % 3] = P8;
         if (i < 6) continue;
         const int ry = strip * kDetStrip + i - 6;  // row inside the tile
         const int y = y0 + ry;
         if (y >= L.h) break;
-        const int T = hi[i % 7] - lo[i % 7];
-        if (x < L.w) cmap[(long long)y * L.pitch + x] = 0;  // corners are written in phase 2
-        if (T >= cmp && x >= 3 && x < L.w - 3 && y >= 3 && y < L.h - 3) {
-          const int sr = ry + 3;  // staged row of y
-          const int t = T < kLowerThreshold ? kLowerThreshold : (T > kUpperThreshold ? kUpperThreshold : T);
-          const int b2 = (t * thresh) / 100;
-          const int c = s_img[sr][sc], cb = c + b2, c_b = c - b2;
-          // compass points first: a 9-arc holds at least two of them
-          const int p0 = s_img[sr][sc - 3], p4 = s_img[sr - 3][sc], p8 = s_img[sr][sc + 3], p12 = s_img[sr + 3][sc];
-          const int nb = (p0 > cb) + (p4 > cb) + (p8 > cb) + (p12 > cb);
-          const int nd = (p0 < c_b) + (p4 < c_b) + (p8 < c_b) + (p12 < c_b);
-          if (nb >= 2 || nd >= 2) s_queue[atomicAdd(&s_count, 1)] = (uint32_t)cx | ((uint32_t)ry << 8) | ((uint32_t)T << 16);
+        *reinterpret_cast<uint2*>(cmap + (long long)y * L.pitch + x) = make_uint2(0, 0);  // corners are written in phase 2
+        const uint32_t TE = out[0] - out[1], TO = out[2] - out[3];  // per lane max >= min: no borrow
+        // T of x, x+1, x+2, x+3 = TE.lo, TO.lo, TE.hi, TO.hi as four bytes
+        *reinterpret_cast<uint32_t*>(&s_T[ry][cx]) = __byte_perm(TE, TO, 0x6240);
+        const uint32_t bE = (uint32_t)s_b2[TE & 0xffffu] | ((uint32_t)s_b2[TE >> 16] << 16);
+        const uint32_t bO = (uint32_t)s_b2[TO & 0xffffu] | ((uint32_t)s_b2[TO >> 16] << 16);
+        uint32_t cand[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t c = h ? cO : cE, b = h ? bO : bE;
+          const uint32_t p0 = h ? lO : lE, p4 = h ? nO : nE, p8 = h ? rO : rE, p12 = h ? P5 : P4;
+          // second largest / second smallest of the four compass pixels
+          const uint32_t h1 = __vmaxu2(p0, p4), l1 = __vminu2(p0, p4), h2 = __vmaxu2(p8, p12), l2 = __vminu2(p8, p12);
+          const uint32_t S2 = __vimax3_u16x2(__vminu2(h1, h2), l1, l2), s2 = __vimin3_u16x2(__vmaxu2(l1, l2), h1, h2);
+          // lane test A > B as ((B | 0x8000) - A) losing bit 15 (all values stay below 0x8000)
+          const uint32_t bright = ((c + b) | kHi) - S2;   // bit 15 clear <=> S2 > c + b
+          const uint32_t dark = ((s2 + b) | kHi) - c;     // bit 15 clear <=> c > s2 + b
+          cand[h] = ~(bright & dark) & kHi;
+        }
+        // flags of x (bit 0), x+1 (bit 1) -> acc_lo; of x+2, x+3 -> acc_hi; the latest row in the lowest bits
+        const uint32_t c4 = (cand[0] >> 15) | (cand[1] >> 14);
+        acc_lo = (acc_lo << 2) | (c4 & 3u);
+        acc_hi = (acc_hi << 2) | (c4 >> 16);
+        last_ry = ry;
+      }
+      // queue the candidates of the thread's four columns (rows last_ry, last_ry - 1, ... from bit 0 upwards)
+      const int n_mine = __popcll(acc_lo) + __popcll(acc_hi);
+      if (n_mine) {
+        int slot = atomicAdd(&s_count, n_mine);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          unsigned long long a = half ? acc_hi : acc_lo;
+          while (a) {
+            const int bit = __ffsll((long long)a) - 1;
+            a &= a - 1;
+            const int ry = last_ry - (bit >> 1), j = 2 * half + (bit & 1);
+            const int xx = x + j, y = y0 + ry;
+            if (xx < 3 || xx >= L.w - 3 || y < 3 || y >= L.h - 3) continue;  // (its slot stays unused)
+            if (slot < kDetQueue) s_queue[slot] = (uint16_t)((cx + j) | (ry << 8));
+            else {  // queue full: test in place
+              const int T = s_T[ry][cx + j];
+              if (segment_test(s_img, ry + 3, sc + j, s_b2[T])) {
+                cmap[(long long)y * L.pitch + xx] = (uint16_t)T;
+                atomicAdd(&s_rows[ry], 1);
+              }
+            }
+            ++slot;
+          }
         }
       }
     }
   }
   __syncthreads();
-  // phase 2: full segment test on the queued candidates
-  const int n_cand = s_count;
+  // phase 2: full segment test on the queued candidates (slots of border pixels were left unused: 0xffff)
+  const int n_cand = min(s_count, kDetQueue);
   for (int q = tid; q < n_cand; q += kDetThreads) {
     const uint32_t e = s_queue[q];
-    const int cx = e & 0xff, ry = (e >> 8) & 0xff, T = e >> 16;
-    const int sr = ry + 3, sc = cx + 4;
-    const int t = T < kLowerThreshold ? kLowerThreshold : (T > kUpperThreshold ? kUpperThreshold : T);
-    const int b2 = (t * thresh) / 100;
-    const int c = s_img[sr][sc], cb = c + b2, c_b = c - b2;
-    // ring of agast/include/agast/oast9-16.h:99-116
-    int r[16];
-    r[0] = s_img[sr][sc - 3];      r[1] = s_img[sr - 1][sc - 3]; r[2] = s_img[sr - 2][sc - 2]; r[3] = s_img[sr - 3][sc - 1];
-    r[4] = s_img[sr - 3][sc];      r[5] = s_img[sr - 3][sc + 1]; r[6] = s_img[sr - 2][sc + 2]; r[7] = s_img[sr - 1][sc + 3];
-    r[8] = s_img[sr][sc + 3];      r[9] = s_img[sr + 1][sc + 3]; r[10] = s_img[sr + 2][sc + 2]; r[11] = s_img[sr + 3][sc + 1];
-    r[12] = s_img[sr + 3][sc];     r[13] = s_img[sr + 3][sc - 1]; r[14] = s_img[sr + 2][sc - 2]; r[15] = s_img[sr + 1][sc - 3];
-    uint32_t mb = 0, md = 0;
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { mb |= (uint32_t)(r[k] > cb) << k; md |= (uint32_t)(r[k] < c_b) << k; }
-    // 9 contiguous set bits on the circular 16-bit mask
-    mb |= mb << 16; md |= md << 16;
-    uint32_t xb = mb & (mb >> 1); xb &= xb >> 2; xb &= xb >> 4; xb &= mb >> 8;
-    uint32_t xd = md & (md >> 1); xd &= xd >> 2; xd &= xd >> 4; xd &= md >> 8;
-    if (((xb | xd) & 0xffffu) != 0) {
+    if (e == 0xffffu) continue;
+    const int cx = e & 0xff, ry = e >> 8;
+    const int T = s_T[ry][cx];
+    if (segment_test(s_img, ry + 3, cx + 4, s_b2[T])) {
       cmap[(long long)(y0 + ry) * L.pitch + x0 + cx] = (uint16_t)T;
       atomicAdd(&s_rows[ry], 1);
     }
