@@ -64,21 +64,23 @@ BRISK_HD int imax(int a, int b) { return a > b ? a : b; }
 // rewrite it as max(min(d), -max(d)) on differences: ptxas 12.9 for sm_100a
 // folds that negation into VIMNMX3 and drops it (observed on hardware: wrong
 // scores), while plain subtractions are compiled correctly.
+BRISK_HD int imin3(int a, int b, int c) { return imin(imin(a, b), c); }  // one VIMNMX3 on sm_100a
+BRISK_HD int imax3(int a, int b, int c) { return imax(imax(a, b), c); }
+
 BRISK_HD int arc_contrast16(const int p[16], int c) {
-  // sliding minimum / maximum over windows of 9 on the circular sequence
-  int lo2[16], hi2[16], lo4[16], hi4[16];
+  // sliding minimum / maximum over windows of 9 on the circular sequence, as 3-input operations:
+  // windows of 3, then three of those 3 apart; max_i(min9_i) - c and c - min_i(max9_i) are then
+  // the best bright / dark arc contrasts
+  int lo3[16], hi3[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { lo2[i] = imin(p[i], p[(i + 1) & 15]); hi2[i] = imax(p[i], p[(i + 1) & 15]); }
+  for (int i = 0; i < 16; ++i) { lo3[i] = imin3(p[i], p[(i + 1) & 15], p[(i + 2) & 15]); hi3[i] = imax3(p[i], p[(i + 1) & 15], p[(i + 2) & 15]); }
+  int lo9[16], hi9[16];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { lo4[i] = imin(lo2[i], lo2[(i + 2) & 15]); hi4[i] = imax(hi2[i], hi2[(i + 2) & 15]); }
-  int best = -1000;
+  for (int i = 0; i < 16; ++i) { lo9[i] = imin3(lo3[i], lo3[(i + 3) & 15], lo3[(i + 6) & 15]); hi9[i] = imax3(hi3[i], hi3[(i + 3) & 15], hi3[(i + 6) & 15]); }
+  int bright = lo9[15], dark = hi9[15];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int lo9 = imin(imin(lo4[i], lo4[(i + 4) & 15]), p[(i + 8) & 15]);
-    const int hi9 = imax(imax(hi4[i], hi4[(i + 4) & 15]), p[(i + 8) & 15]);
-    best = imax(best, imax(lo9 - c, c - hi9));
-  }
-  return best;
+  for (int i = 0; i < 15; i += 3) { bright = imax(bright, imax3(lo9[i], lo9[i + 1], lo9[i + 2])); dark = imin(dark, imin3(hi9[i], hi9[i + 1], hi9[i + 2])); }
+  return imax(bright - c, c - dark);
 }
 
 BRISK_HD int arc_contrast8(const int p[8], int c) {

@@ -46,10 +46,10 @@ struct Slot {
   cudaEvent_t done = nullptr;
   int32_t* h_counts = nullptr;  // pinned: counts of the chunk + [cap_counts] error flag
   size_t h_counts_cap = 0;
-  DevBuf pyr, cm, bm, rowcnt, layer_start, corners, fwin, checks, kp_tmp, kp_valid, integral, rounds;
+  DevBuf pyr, cm, bm, rowcnt, layer_start, corners, fwin, checks, kp_tmp, kp_valid, integral, rounds, surv;
   DevBuf tight, kps, kps_scratch, scales, counts, desc, masks, flag;
   DevBuf h_scores, h_pts, h_keep, h_sorted, h_layer_kept, h_occ, h_surv, h_layer_surv;
-  DevBuf* all[28] = {&pyr, &cm, &bm, &rowcnt, &layer_start, &corners, &fwin, &checks, &kp_tmp, &kp_valid, &integral, &rounds,
+  DevBuf* all[29] = {&pyr, &cm, &bm, &rowcnt, &layer_start, &corners, &fwin, &checks, &kp_tmp, &kp_valid, &integral, &rounds, &surv,
                      &tight, &kps, &kps_scratch, &scales, &counts, &desc, &masks, &flag,
                      &h_scores, &h_pts, &h_keep, &h_sorted, &h_layer_kept, &h_occ, &h_surv, &h_layer_surv};
 };
@@ -191,7 +191,7 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
   plan->integral_elems = ext ? (size_t)(w + 1) * (h + 1) : 0;
   const int desc_bytes = ext ? ext->dev.desc_bytes : 0;
   size_t per_frame = (size_t)g.frame_elems;  // image planes
-  if (det && !harris) per_frame += (size_t)g.frame_elems * 3 + (size_t)ws.total_rows * 4 + (size_t)ws.corner_cap * (4 + 32 + 32 + 28 + 1);
+  if (det && !harris) per_frame += (size_t)g.frame_elems * 3 + (size_t)ws.total_rows * 4 + (size_t)ws.corner_cap * (4 + 32 + 32 + 28 + 1 + 4);
   if (harris) per_frame += (size_t)g.frame_elems * 4 + (size_t)ws.total_rows * 4 + (size_t)ws.corner_cap * 25 + (size_t)plan->hw.occ_frame_bytes;
   per_frame += plan->integral_elems * 4 + (size_t)cap * (28 * 2 + 4 + desc_bytes) + 2 * (size_t)w * h /* mask, tight copy */;
   // two slots share the workspace limit; at least two chunks when there is more than one frame, so
@@ -237,7 +237,8 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
       CU_OK(sl.checks.ensure(c * ws.corner_cap * 32));
       CU_OK(sl.kp_tmp.ensure(c * ws.corner_cap * 28));
       CU_OK(sl.kp_valid.ensure(c * ws.corner_cap));
-      CU_OK(sl.rounds.ensure(c * kMaxLayers * 4));
+      CU_OK(sl.rounds.ensure(c * kTieStride * 4));
+      CU_OK(sl.surv.ensure(c * (size_t)ws.corner_cap * 4));
     }
     if (ext) {
       CU_OK(sl.integral.ensure(c * plan->integral_elems * 4));
@@ -261,7 +262,7 @@ DetectWorkspace slot_ws(const Plan& plan, const Slot& sl) {
   ws.pyr = sl.pyr.as<uint8_t>(); ws.cm = sl.cm.as<uint16_t>(); ws.bm = sl.bm.as<uint8_t>();
   ws.rowcnt = sl.rowcnt.as<int>(); ws.layer_start = sl.layer_start.as<int>(); ws.corners = sl.corners.as<uint32_t>();
   ws.fwin = sl.fwin.as<uint8_t>(); ws.checks = sl.checks.as<float>(); ws.kp_tmp = sl.kp_tmp.as<KeyPoint>();
-  ws.kp_valid = sl.kp_valid.as<uint8_t>(); ws.n_ties = sl.rounds.as<int>();
+  ws.kp_valid = sl.kp_valid.as<uint8_t>(); ws.n_ties = sl.rounds.as<int>(); ws.surv = sl.surv.as<int>();
   return ws;
 }
 

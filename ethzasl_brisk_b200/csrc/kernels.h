@@ -9,6 +9,7 @@ namespace briskb200 {
 
 // Per-batch device workspace of the AGAST detector; plane blocks are laid out
 // [frame][layer] following PyramidGeom.
+constexpr int kTieStride = 16;
 struct DetectWorkspace {
   uint8_t* pyr;         // u8 image planes
   uint16_t* cm;         // u16 corner maps
@@ -20,7 +21,8 @@ struct DetectWorkspace {
   float* checks;        // [frame][corner_cap][8]  CheckResult (32 bytes)
   KeyPoint* kp_tmp;     // [frame][corner_cap]
   uint8_t* kp_valid;    // [frame][corner_cap]
-  int* n_ties;          // [frame][kMaxLayers] tying corners per layer (diagnostic)
+  int* n_ties;          // [frame][kTieStride]: tying corners per layer, then [kMaxLayers] = corners that need the scale checks
+  int* surv;            // [frame][corner_cap] slots of the corners that passed IsMax2D's comparisons (any order)
   int total_rows;       // sum of layer heights
   int row_off[kMaxLayers + 1];
   int corner_cap;       // per frame

@@ -46,27 +46,39 @@ __device__ __forceinline__ void unpack_corner(uint32_t c, int* x, int* y, int* l
 
 __global__ void __launch_bounds__(128)
 nms_prefix_kernel(PyramidGeom g, DetectWorkspace ws) {
-  const int frame = blockIdx.y;
+  const int frame = blockIdx.y, lane = threadIdx.x & 31;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = min(ws.layer_start[(long long)frame * (kMaxLayers + 1) + g.n_layers], ws.corner_cap);
-  if (k >= n) return;
-  int x, y, layer;
-  unpack_corner(ws.corners[(long long)frame * ws.corner_cap + k], &x, &y, &layer);
-  const long long fo = (long long)frame * g.frame_elems;
-  const LayerGeom& L = g.L[layer];
-  const LayerView v{ws.pyr + fo + L.off, ws.cm + fo + L.off, ws.bm + fo + L.off, L.w, L.h, L.pitch, L.scale, L.offset};
-  uint8_t fwin[25];
-  nms_prefix(v, x, y, fwin);
-  const bool tie = v.cm[(long long)y * L.pitch + x] & kCmTie;
-  if (tie) {
-    // per-layer list of the tying corners (any order) for the chain kernel, in the frame's key-point
-    // scratch, which is free until refine_kernel runs; layer l's list starts at its first corner slot
-    const int pos = atomicAdd(&ws.n_ties[frame * kMaxLayers + layer], 1);
-    reinterpret_cast<int2*>(ws.kp_tmp + (long long)frame * ws.corner_cap)[ws.layer_start[(long long)frame * (kMaxLayers + 1) + layer] + pos] =
-        make_int2(k, x | (y << 16));
-    uint8_t* dst = ws.fwin + ((long long)frame * ws.corner_cap + k) * 32;
+  if (blockIdx.x * blockDim.x >= n) return;
+  bool on = false;
+  if (k < n) {
+    int x, y, layer;
+    unpack_corner(ws.corners[(long long)frame * ws.corner_cap + k], &x, &y, &layer);
+    const LayerView v = make_view(g, ws, frame, layer);
+    uint8_t fwin[25];
+    nms_prefix(v, x, y, fwin);
+    const uint16_t ev = v.cm[(long long)y * v.pitch + x];
+    on = ev & (kCmAccept | kCmTie);
+    if (ev & kCmTie) {
+      // per-layer list of the tying corners (any order) for the chain kernel, in the frame's key-point
+      // scratch, which is free until refine_kernel runs; layer l's list starts at its first corner slot
+      const int pos = atomicAdd(&ws.n_ties[frame * kTieStride + layer], 1);
+      reinterpret_cast<int2*>(ws.kp_tmp + (long long)frame * ws.corner_cap)[ws.layer_start[(long long)frame * (kMaxLayers + 1) + layer] + pos] =
+          make_int2(k, x | (y << 16));
+      uint8_t* dst = ws.fwin + ((long long)frame * ws.corner_cap + k) * 32;
 #pragma unroll
-    for (int i = 0; i < 25; ++i) dst[i] = fwin[i];
+      for (int i = 0; i < 25; ++i) dst[i] = fwin[i];
+    }
+  }
+  // corners that survive (accepted or tying) go on to the scale checks: compacted (order within a warp
+  // kept, warps in any order), so that nms_checks_kernel runs full warps
+  const unsigned bal = __ballot_sync(0xffffffffu, on);
+  if (bal) {
+    const int leader = __ffs(bal) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&ws.n_ties[frame * kTieStride + kMaxLayers], __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (on) ws.surv[(long long)frame * ws.corner_cap + base + __popc(bal & ((1u << lane) - 1u))] = k;
   }
 }
 
@@ -211,29 +223,28 @@ __device__ __forceinline__ void warp_mark_above(const LayerView& nb, int layer, 
 __global__ void __launch_bounds__(128, 5)
 nms_checks_kernel(PyramidGeom g, DetectWorkspace ws) {
   const int frame = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = min(ws.layer_start[(long long)frame * (kMaxLayers + 1) + g.n_layers], ws.corner_cap);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = ws.n_ties[frame * kTieStride + kMaxLayers];  // corners that passed IsMax2D's comparisons
   if (blockIdx.x * blockDim.x >= n) return;
   int x = 0, y = 0, layer = 0;
   CheckResult r;
   bool mark = false;
-  if (k < n) {
+  if (i < n) {
+    const int k = ws.surv[(long long)frame * ws.corner_cap + i];
     unpack_corner(ws.corners[(long long)frame * ws.corner_cap + k], &x, &y, &layer);
     const LayerView own = make_view(g, ws, frame, layer);
     uint16_t* e = own.cm + (long long)y * own.pitch + x;
     const uint16_t ev = *e;
-    if (!(ev & kCmDecided) || (ev & kCmAccept)) {
-      // only the corner's own layer and its two neighbours are looked at
-      const LayerView below = make_view(g, ws, frame, layer > 0 ? layer - 1 : 0);
-      const LayerView above = make_view(g, ws, frame, layer + 1 < g.n_layers ? layer + 1 : layer);
-      const bool ok = nms_checks3(below, own, above, g.n_layers, layer, x, y, &r);
-      if (ok) *e = ev | kCmChecks;
-      // kept even when the checks fail: the footprint of the scan of the layer above is needed by the chain kernel
-      *reinterpret_cast<CheckResult*>(ws.checks + ((long long)frame * ws.corner_cap + k) * 8) = r;
-      // A corner accepted without a tie leaves its footprint on the layer above right away (the touch map is
-      // only read by the chain kernel); tying corners do so once they are resolved.
-      mark = (ev & kCmAccept) && g.n_layers > 1 && layer < g.n_layers - 1;
-    }
+    // only the corner's own layer and its two neighbours are looked at
+    const LayerView below = make_view(g, ws, frame, layer > 0 ? layer - 1 : 0);
+    const LayerView above = make_view(g, ws, frame, layer + 1 < g.n_layers ? layer + 1 : layer);
+    const bool ok = nms_checks3(below, own, above, g.n_layers, layer, x, y, &r);
+    if (ok) *e = ev | kCmChecks;
+    // kept even when the checks fail: the footprint of the scan of the layer above is needed by the chain kernel
+    *reinterpret_cast<CheckResult*>(ws.checks + ((long long)frame * ws.corner_cap + k) * 8) = r;
+    // A corner accepted without a tie leaves its footprint on the layer above right away (the touch map is
+    // only read by the chain kernel); tying corners do so once they are resolved.
+    mark = (ev & kCmAccept) && g.n_layers > 1 && layer < g.n_layers - 1;
   }
   // the marks of the warp's corners, one corner at a time with one lane per scan position
   unsigned todo = __ballot_sync(0xffffffffu, mark);
@@ -271,7 +282,7 @@ nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag
   for (int layer = 0; layer < g.n_layers; ++layer) {
     const int mode = g.n_layers == 1 ? kModeSingle : (layer == g.n_layers - 1 ? kModeLast : kModeMid);
     const LayerView& L = fv.v[layer];
-    int n = ws.n_ties[frame * kMaxLayers + layer];
+    int n = ws.n_ties[frame * kTieStride + layer];
     const int2* cur = lists + ls[layer];
     for (int pass = 0; n > 0; ++pass) {
       int2* nxt = lists + (1 + (pass & 1)) * (long long)ws.corner_cap;  // never the list being read
@@ -396,7 +407,7 @@ cudaError_t launch_agast_nms(const PyramidGeom& g, const DetectWorkspace& ws, in
                              int* error_flag, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(ws.bm, 0, (size_t)n_frames * g.frame_elems, stream);
   if (e != cudaSuccess) return e;
-  e = cudaMemsetAsync(ws.n_ties, 0, (size_t)n_frames * kMaxLayers * sizeof(int), stream);
+  e = cudaMemsetAsync(ws.n_ties, 0, (size_t)n_frames * kTieStride * sizeof(int), stream);
   if (e != cudaSuccess) return e;
   dim3 grid((ws.corner_cap + 127) / 128, n_frames);
   // BRISK_B200_NMS_TIMING=1: per-kernel CUDA-event times of this launch sequence on stderr (debug aid; synchronises)
