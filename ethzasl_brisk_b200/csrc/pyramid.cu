@@ -61,25 +61,65 @@ __device__ void half_tile(const uint8_t* __restrict__ s, int sw, int src_w, uint
   }
 }
 
+// Horizontal step of Twothirdsample8's SSE body on four triples at once: w0..w2 hold twelve vertically
+// combined bytes b0..b11; per triple (b0,b1,b2) the two outputs are avg(avg(b0,b1),b0) and avg(avg(b2,b1),b2)
+// (pavgb).  Returns the eight output bytes in order.
+__device__ __forceinline__ uint2 twothird_row4(uint32_t w0, uint32_t w1, uint32_t w2) {
+  const uint32_t A = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);  // b0 b3 b6 b9
+  const uint32_t B = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);  // b1 b4 b7 b10
+  const uint32_t C = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);  // b2 b5 b8 b11
+  const uint32_t o0 = __vavgu4(__vavgu4(A, B), A), o1 = __vavgu4(__vavgu4(C, B), C);
+  return make_uint2(__byte_perm(o0, o1, 0x5140), __byte_perm(o0, o1, 0x7362));
+}
+
 // dst tile = Twothirdsample8 of the 192x96 layer-0 tile; tx0 = absolute index
-// of the tile's first source triple.
+// of the tile's first source triple.  Four triples (12 source columns, 8 outputs per row) per step on packed
+// bytes where all four lie in the reference's 15-column SSE blocks; the scalar tail columns go one 3x3
+// block at a time.
 __device__ void twothird_tile(const uint8_t* __restrict__ s, int src_w, uint8_t* __restrict__ d, int tx0) {
-  constexpr int bw = kTileW / 3, bh = kTileH / 3, dw = 2 * bw;
-  for (int i = threadIdx.x; i < bw * bh; i += kPyrThreads) {
-    const int by = i / bw, bx = i - by * bw;
-    int p[9], o[4];
+  constexpr int bw = kTileW / 3, bh = kTileH / 3, dw = 2 * bw, groups = bw / 4;
+  const int sse_triples = 5 * (src_w / 15);
+  for (int i = threadIdx.x; i < groups * bh; i += kPyrThreads) {
+    const int by = i / groups, gx = i - by * groups;
+    if (tx0 + 4 * gx + 3 < sse_triples) {
+      const uint32_t* r0 = reinterpret_cast<const uint32_t*>(s + (3 * by) * kTileW + 12 * gx);
+      const uint32_t* r1 = r0 + kTileW / 4;
+      const uint32_t* r2 = r1 + kTileW / 4;
+      uint32_t u[3], l[3];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) p[k] = s[(3 * by + k / 3) * kTileW + 3 * bx + (k % 3)];
-    twothird_block(p, tx0 + bx, src_w, o);
-    *reinterpret_cast<uchar2*>(d + (2 * by) * dw + 2 * bx) = make_uchar2((uint8_t)o[0], (uint8_t)o[1]);
-    *reinterpret_cast<uchar2*>(d + (2 * by + 1) * dw + 2 * bx) = make_uchar2((uint8_t)o[2], (uint8_t)o[3]);
+      for (int k = 0; k < 3; ++k) {
+        const uint32_t a = r0[k], b = r1[k], c = r2[k];
+        u[k] = __vavgu4(__vavgu4(a, b), a);  // upper output row: rows 0 and 1
+        l[k] = __vavgu4(__vavgu4(c, b), c);  // lower output row: rows 2 and 1
+      }
+      *reinterpret_cast<uint2*>(d + (2 * by) * dw + 8 * gx) = twothird_row4(u[0], u[1], u[2]);
+      *reinterpret_cast<uint2*>(d + (2 * by + 1) * dw + 8 * gx) = twothird_row4(l[0], l[1], l[2]);
+    } else {
+      for (int bx = 4 * gx; bx < 4 * gx + 4; ++bx) {
+        int p[9], o[4];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) p[k] = s[(3 * by + k / 3) * kTileW + 3 * bx + (k % 3)];
+        twothird_block(p, tx0 + bx, src_w, o);
+        *reinterpret_cast<uchar2*>(d + (2 * by) * dw + 2 * bx) = make_uchar2((uint8_t)o[0], (uint8_t)o[1]);
+        *reinterpret_cast<uchar2*>(d + (2 * by + 1) * dw + 2 * bx) = make_uchar2((uint8_t)o[2], (uint8_t)o[3]);
+      }
+    }
   }
 }
 
 // Stream a finished tile from shared memory to its layer in HBM.
 __device__ void flush_tile(const uint8_t* __restrict__ s, int tw, int th, uint8_t* __restrict__ layer, const LayerGeom& L,
                            int x0, int y0) {
-  if ((tw & 3) == 0) {
+  if ((tw & 15) == 0) {
+    // 16-byte stores: tile origins and row pitches are multiples of 16, and writing the padding columns
+    // [w, pitch) of a row is harmless
+    const int groups = tw >> 4;
+    for (int i = threadIdx.x; i < groups * th; i += kPyrThreads) {
+      const int r = i / groups, g = i - r * groups;
+      const int x = x0 + 16 * g, y = y0 + r;
+      if (x < L.pitch && x < L.w && y < L.h) *reinterpret_cast<uint4*>(layer + (long long)y * L.pitch + x) = *reinterpret_cast<const uint4*>(s + r * tw + 16 * g);
+    }
+  } else if ((tw & 3) == 0) {
     const int groups = tw >> 2;
     for (int i = threadIdx.x; i < groups * th; i += kPyrThreads) {
       const int r = i / groups, g = i - r * groups;
