@@ -290,20 +290,30 @@ corner_fill_kernel(LayerGeom L, int layer, long long frame_elems, const uint16_t
   const uint16_t* row = cm + (long long)frame * frame_elems + L.off + (long long)y * L.pitch;
   int slot = rowcnt[(long long)frame * total_rows + row_off + y];
   uint32_t* out = corners + (long long)frame * corner_cap;
-  for (int xb = 0; xb < L.w; xb += 64) {
-    // two pixels per lane
-    const int x = xb + 2 * lane;
-    uint32_t v = 0;
-    if (x < L.pitch) v = *reinterpret_cast<const uint32_t*>(row + x);
-    const bool c0 = (v & 0xffffu) != 0 && x < L.w, c1 = (v >> 16) != 0 && x + 1 < L.w;
-    const uint32_t m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
-    if (m0 | m1) {
-      const uint32_t below = (1u << lane) - 1;
-      const int rank0 = __popc(m0 & below) + __popc(m1 & below);
-      if (c0) { const int s = slot + rank0; if (s < corner_cap) out[s] = (uint32_t)x | ((uint32_t)y << 13) | ((uint32_t)layer << 26); }
-      if (c1) { const int s = slot + rank0 + (c0 ? 1 : 0); if (s < corner_cap) out[s] = (uint32_t)(x + 1) | ((uint32_t)y << 13) | ((uint32_t)layer << 26); }
-      slot += __popc(m0) + __popc(m1);
+  for (int xb = 0; xb < L.w; xb += 256) {
+    // eight map entries (16 bytes) per lane; rows are sparse, so most steps end at the first ballot
+    const int x = xb + 8 * lane;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (x < L.pitch) v = *reinterpret_cast<const uint4*>(row + x);
+    const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    uint32_t m8 = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if ((wv[j] & 0xffffu) && x + 2 * j < L.w) m8 |= 1u << (2 * j);
+      if ((wv[j] >> 16) && x + 2 * j + 1 < L.w) m8 |= 2u << (2 * j);
     }
+    if (!__ballot_sync(0xffffffffu, m8 != 0)) continue;
+    const int cnt = __popc(m8);
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+    int s = slot + inc - cnt;
+    for (uint32_t m = m8; m; m &= m - 1) {
+      const int j = __ffs(m) - 1;
+      if (s < corner_cap) out[s] = (uint32_t)(x + j) | ((uint32_t)y << 13) | ((uint32_t)layer << 26);
+      ++s;
+    }
+    slot += __shfl_sync(0xffffffffu, inc, 31);
   }
 }
 
