@@ -98,7 +98,7 @@ def stage_bytes(n_layers_dims, n_corners, n_kps, desc_bytes=48):
         "detect": sum(px) + 2 * sum(px),            # read u8 layers, write u16 corner maps
         "lists": 2 * sum(px) + 4 * n_corners,       # read corner maps, write packed corners
         "nms": 3 * sum(px) + 100 * n_corners,       # touch-map clear + corner-map traffic + per-corner records
-        "integral": px[0] + 3 * 4 * (W + 1) * (H + 1),  # rows: read u8 write i32; columns: read + write i32
+        "integral": px[0] + 4 * (W + 1) * (H + 1),  # u8 in, i32 out (the kernels read the image twice: +px[0] of real traffic)
         "describe": n_kps * (28 * 2 + desc_bytes),  # compulsory HBM only; the gathers hit L2
     }
 

@@ -194,11 +194,12 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
   }
   ws.corner_cap = det ? ccap : 0;
   plan->integral_elems = ext ? (size_t)(w + 1) * (h + 1) : 0;
+  const size_t integral_aux = ext ? (size_t)integral_aux_elems(w, h) : 0;
   const int desc_bytes = ext ? ext->dev.desc_bytes : 0;
   size_t per_frame = (size_t)g.frame_elems;  // image planes
   if (det && !harris) per_frame += (size_t)g.frame_elems * 3 + (size_t)ws.total_rows * 4 + (size_t)ws.corner_cap * (4 + 32 + 32 + 28 + 1 + 4);
   if (harris) per_frame += (size_t)g.frame_elems * 4 + (size_t)ws.total_rows * 4 + (size_t)ws.corner_cap * 25 + (size_t)plan->hw.occ_frame_bytes;
-  per_frame += plan->integral_elems * 4 + (size_t)cap * (28 * 2 + 4 + desc_bytes) + 2 * (size_t)w * h /* mask, tight copy */;
+  per_frame += (plan->integral_elems + integral_aux) * 4 + (size_t)cap * (28 * 2 + 4 + desc_bytes) + 2 * (size_t)w * h /* mask, tight copy */;
   // two slots share the workspace limit; at least two chunks when there is more than one frame, so
   // that copies and the serial tail of one chunk overlap the kernels of the other
   long long max_chunk = (long long)(ctx->ws_limit / 2 / std::max<size_t>(per_frame, 1));
@@ -246,7 +247,7 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
       CU_OK(sl.surv.ensure(c * (size_t)ws.corner_cap * 4));
     }
     if (ext) {
-      CU_OK(sl.integral.ensure(c * plan->integral_elems * 4));
+      CU_OK(sl.integral.ensure(c * (plan->integral_elems + integral_aux) * 4));
       CU_OK(sl.kps_scratch.ensure(c * cap * 28));
       CU_OK(sl.scales.ensure(c * cap * 4));
     }
@@ -752,7 +753,7 @@ int brisk_debug_integral(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_
   Slot& sl = ctx->slots[0];
   const DetectWorkspace ws = slot_ws(plan, sl);
   (void)ws;
-  CU_OK(sl.integral.ensure((size_t)(w + 1) * (h + 1) * 4));
+  CU_OK(sl.integral.ensure(((size_t)(w + 1) * (h + 1) + (size_t)integral_aux_elems(w, h)) * 4));
   CUtensorMap map; int write_l0;
   rc = stage_input(ctx, sl, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
   if (rc) return rc;

@@ -17,64 +17,133 @@
 
 namespace briskb200 {
 
-// --- integral image: row scans (one warp per row), then column accumulation ---
+// --- integral image in one pass over the output ---
+//
+// S(y+1, x+1) = sum of I over rows <= y and columns <= x.  The frame is cut into vertical strips of 256
+// columns.  Kernel 1 (one warp per row) writes, for every row and strip, the sum of the row's pixels LEFT of
+// the strip.  Kernel 2 (one CTA per strip, one thread per column) walks down the rows, eight at a time,
+// keeping the running column sums in registers; the eight rows of column sums go through shared memory to
+// the eight warps, each of which turns one row into its prefix sums (eight consecutive columns per lane,
+// then one warp scan) and adds what lies left of the strip; the threads then store the rows coalesced.
+// Traffic: the image twice (1 byte per pixel each) and the integral once (4 bytes per pixel); nothing is
+// read back (the two-pass form moved 27 MB per 1080p frame, this one 12.4 MB).
+constexpr int kIntStrip = 256, kIntRows = 8;
+
+__host__ __device__ inline int integral_strips(int w) { return (w + kIntStrip - 1) / kIntStrip; }
+long long integral_aux_elems(int w, int h) { return (long long)h * integral_strips(w); }
 
 __global__ void __launch_bounds__(256)
-integral_rows_kernel(const uint8_t* __restrict__ imgs, long long frame_stride, int pitch, int w, int h,
-                     int32_t* __restrict__ integral) {
+integral_left_sums_kernel(const uint8_t* __restrict__ imgs, long long frame_stride, int pitch, int w, int h, int32_t* __restrict__ aux) {
   const int frame = blockIdx.y, lane = threadIdx.x & 31;
-  const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // output row y in [0, h]
-  if (y > h) return;
-  const int iw = w + 1;
-  int32_t* out = integral + (long long)frame * iw * (h + 1) + (long long)y * iw;
-  if (y == 0) {
-    for (int x = lane; x < iw; x += 32) out[x] = 0;
-    return;
-  }
-  const uint8_t* row = imgs + (long long)frame * frame_stride + (long long)(y - 1) * pitch;
-  if (lane == 0) out[0] = 0;
-  int carry = 0;
-  for (int xb = 0; xb < w; xb += 128) {
-    const int x = xb + 4 * lane;
-    uint32_t v = 0;
-    if (x < pitch) v = *reinterpret_cast<const uint32_t*>(row + x);
-    const int b0 = v & 0xff, b1 = b0 + ((v >> 8) & 0xff), b2 = b1 + ((v >> 16) & 0xff), b3 = b2 + (v >> 24);
-    int inc = b3;
+  const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (y >= h) return;
+  const int ns = integral_strips(w);
+  const uint8_t* row = imgs + (long long)frame * frame_stride + (long long)y * pitch;
+  int32_t* out = aux + ((long long)frame * h + y) * ns;
+  int left = 0;
+  for (int s = 0; s < ns; ++s) {
+    if (lane == 0) out[s] = left;
+    // 256 bytes of the strip: two words per lane, bytes past the row end masked off (the pitch is a multiple of 16)
+    int sum = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
-    const int base = carry + inc - b3;
-    if (x < w) out[x + 1] = base + b0;
-    if (x + 1 < w) out[x + 2] = base + b1;
-    if (x + 2 < w) out[x + 3] = base + b2;
-    if (x + 3 < w) out[x + 4] = base + b3;
-    carry += __shfl_sync(0xffffffffu, inc, 31);
+    for (int k = 0; k < 2; ++k) {
+      const int x = s * kIntStrip + 4 * (lane + 32 * k);
+      uint32_t v = 0;
+      if (x < pitch) v = *reinterpret_cast<const uint32_t*>(row + x);
+      if (x + 4 > w) v = x < w ? (v & (0xffffffffu >> (8 * (x + 4 - w)))) : 0u;
+      sum += __vsadu4(v, 0u);
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    left += sum;
   }
 }
 
-__global__ void __launch_bounds__(256)
-integral_cols_kernel(int w, int h, int32_t* __restrict__ integral) {
-  const int frame = blockIdx.y;
-  const int x = blockIdx.x * blockDim.x + threadIdx.x + 1;
-  if (x > w) return;
-  const int iw = w + 1;
-  int32_t* p = integral + (long long)frame * iw * (h + 1) + x;
-  int acc = 0;
-  int y = 1;
-  for (; y + 3 <= h; y += 4) {  // 4 independent loads in flight
-    const int a = p[(long long)y * iw], b = p[(long long)(y + 1) * iw], c = p[(long long)(y + 2) * iw], d = p[(long long)(y + 3) * iw];
-    const int s0 = acc + a, s1 = s0 + b, s2 = s1 + c, s3 = s2 + d;
-    p[(long long)y * iw] = s0; p[(long long)(y + 1) * iw] = s1; p[(long long)(y + 2) * iw] = s2; p[(long long)(y + 3) * iw] = s3;
-    acc = s3;
+__global__ void __launch_bounds__(kIntStrip)
+integral_strip_kernel(const uint8_t* __restrict__ imgs, long long frame_stride, int pitch, int w, int h,
+                      const int32_t* __restrict__ aux, int32_t* __restrict__ integral) {
+  __shared__ __align__(16) int s_t[2][kIntRows][kIntStrip];
+  const int strip = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ns = integral_strips(w), iw = w + 1;
+  const int x = strip * kIntStrip + tid;
+  const bool in = x < w;
+  const uint8_t* col = imgs + (long long)frame * frame_stride + x;
+  const int32_t* lft = aux + (long long)frame * h * ns + strip;
+  int32_t* out = integral + (long long)frame * iw * (h + 1);
+  // row 0 and column 0 are zero
+  if (in) out[x + 1] = 0;
+  if (x == 0) out[0] = 0;
+  int acc = 0, left_run = 0;
+  int v[kIntRows], l[kIntRows];
+  const uint8_t* cp = col;          // first row of the NEXT step's loads
+  const int32_t* lp = lft;
+  int32_t* op = out + iw + x + 1;   // S(y0 + 1, x + 1)
+#pragma unroll
+  for (int r = 0; r < kIntRows; ++r) { v[r] = (in && r < h) ? cp[r * pitch] : 0; l[r] = r < h ? lp[r * ns] : 0; }
+  for (int y0 = 0, it = 0; y0 < h; y0 += kIntRows, ++it) {
+    int (*t)[kIntStrip] = s_t[it & 1];
+    int left_mine = left_run;  // left of the strip, rows <= y0 + warp (the row this thread's warp will finish)
+#pragma unroll
+    for (int r = 0; r < kIntRows; ++r) {
+      acc += v[r];             // column sum over rows <= y0 + r
+      t[r][tid] = acc;
+      left_run += l[r];
+      if (r <= warp) left_mine += l[r];
+    }
+    // next step's loads, in flight during the scans
+    cp += kIntRows * pitch; lp += kIntRows * ns;
+    if (y0 + 2 * kIntRows <= h) {
+#pragma unroll
+      for (int r = 0; r < kIntRows; ++r) { v[r] = in ? cp[r * pitch] : 0; l[r] = lp[r * ns]; }
+    } else {
+#pragma unroll
+      for (int r = 0; r < kIntRows; ++r) {
+        const bool row_in = y0 + kIntRows + r < h;
+        v[r] = (in && row_in) ? cp[r * pitch] : 0;
+        l[r] = row_in ? lp[r * ns] : 0;
+      }
+    }
+    __syncthreads();
+    {
+      // warp `warp` finishes row y0 + warp: eight consecutive columns per lane, serial prefix, warp scan of the totals
+      int4* p = reinterpret_cast<int4*>(&t[warp][8 * lane]);
+      int4 a = p[0], b = p[1];
+      a.y += a.x; a.z += a.y; a.w += a.z; b.x += a.w; b.y += b.x; b.z += b.y; b.w += b.z;
+      int inc = b.w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += u; }
+      const int base = left_mine + inc - b.w;
+      a.x += base; a.y += base; a.z += base; a.w += base; b.x += base; b.y += base; b.z += base; b.w += base;
+      p[0] = a; p[1] = b;
+    }
+    __syncthreads();
+    if (y0 + kIntRows <= h) {
+      if (in) {
+#pragma unroll
+        for (int r = 0; r < kIntRows; ++r) op[r * iw] = t[r][tid];
+      }
+      if (x == 0) {
+#pragma unroll
+        for (int r = 0; r < kIntRows; ++r) op[r * iw - 1] = 0;
+      }
+    } else {
+      for (int r = 0; y0 + r < h; ++r) {
+        if (in) op[r * iw] = t[r][tid];
+        if (x == 0) op[r * iw - 1] = 0;
+      }
+    }
+    op += kIntRows * iw;
   }
-  for (; y <= h; ++y) { acc += p[(long long)y * iw]; p[(long long)y * iw] = acc; }
 }
 
 cudaError_t launch_integral(const uint8_t* imgs, long long frame_stride, int pitch, int w, int h, int n_frames,
                             int32_t* integral, cudaStream_t stream) {
-  dim3 g1((h + 1 + 7) / 8, n_frames);
-  integral_rows_kernel<<<g1, 256, 0, stream>>>(imgs, frame_stride, pitch, w, h, integral);
-  dim3 g2((w + 255) / 256, n_frames);
-  integral_cols_kernel<<<g2, 256, 0, stream>>>(w, h, integral);
+  // the per-row "left of the strip" sums live behind the integral images (integral_aux_elems per frame)
+  int32_t* aux = integral + (long long)n_frames * (w + 1) * (h + 1);
+  dim3 g1((h + 7) / 8, n_frames);
+  integral_left_sums_kernel<<<g1, 256, 0, stream>>>(imgs, frame_stride, pitch, w, h, aux);
+  dim3 g2(integral_strips(w), n_frames);
+  integral_strip_kernel<<<g2, kIntStrip, 0, stream>>>(imgs, frame_stride, pitch, w, h, aux, integral);
   return cudaGetLastError();
 }
 
