@@ -405,13 +405,15 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
   };
 
   int chunk_index = 0;
-  for (int f0 = 0; f0 < n; f0 += plan.chunk, ++chunk_index) {
+  // With host frames the upload of the first chunk is not hidden behind any kernel: start with a quarter chunk.
+  const int first_chunk = (plan.n_slots == 2 && !is_device_ptr(imgs) && n >= 4 * plan.chunk) ? std::max(1, plan.chunk / 4) : plan.chunk;
+  for (int f0 = 0, step = first_chunk; f0 < n; f0 += step, step = plan.chunk, ++chunk_index) {
     const int si = chunk_index % plan.n_slots;
     Slot& sl = ctx->slots[si];
     // the slot's previous chunk must be fully drained (results copied) before its buffers are reused
     if (pend[si].active) { rc = finish(si); if (rc) return rc; }
     if (chunk_index >= plan.n_slots) collect_timing(si);
-    const int c = std::min(plan.chunk, n - f0);
+    const int c = std::min(step, n - f0);
     const DetectWorkspace ws = slot_ws(plan, sl);
     KeyPoint* d_kps = kps_dev ? reinterpret_cast<KeyPoint*>(kps) + (size_t)f0 * cap : sl.kps.as<KeyPoint>();
     int* d_counts = counts_dev ? counts + f0 : sl.counts.as<int>();

@@ -327,25 +327,26 @@ nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag
   }
 }
 
+// One thread per corner that passed IsMax2D's comparisons (the compacted list of nms_prefix_kernel); the
+// validity bytes of all other slots were cleared by launch_agast_nms.
 __global__ void __launch_bounds__(128)
 refine_kernel(PyramidGeom g, DetectWorkspace ws) {
   const int frame = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = min(ws.layer_start[(long long)frame * (kMaxLayers + 1) + g.n_layers], ws.corner_cap);
-  if (k >= n) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ws.n_ties[frame * kTieStride + kMaxLayers]) return;
+  const int k = ws.surv[(long long)frame * ws.corner_cap + i];
   const long long slot = (long long)frame * ws.corner_cap + k;
   int x, y, layer;
   unpack_corner(ws.corners[slot], &x, &y, &layer);
   const LayerView own = make_view(g, ws, frame, layer);
   const uint16_t e = own.cm[(long long)y * own.pitch + x];
-  bool valid = false;
-  if ((e & kCmAccept) && (e & kCmChecks)) {
-    const CheckResult r = *reinterpret_cast<const CheckResult*>(ws.checks + slot * 8);
-    KeyPoint kp;
-    valid = refine_emit1(own, g.n_layers, layer, x, y, r, &kp);
-    if (valid) ws.kp_tmp[slot] = kp;
+  if (!(e & kCmAccept) || !(e & kCmChecks)) return;
+  const CheckResult r = *reinterpret_cast<const CheckResult*>(ws.checks + slot * 8);
+  KeyPoint kp;
+  if (refine_emit1(own, g.n_layers, layer, x, y, r, &kp)) {
+    ws.kp_tmp[slot] = kp;
+    ws.kp_valid[slot] = 1;
   }
-  ws.kp_valid[slot] = valid ? 1 : 0;
 }
 
 // Ordered compaction of the surviving key points of a frame, with the mask
@@ -408,6 +409,8 @@ cudaError_t launch_agast_nms(const PyramidGeom& g, const DetectWorkspace& ws, in
   cudaError_t e = cudaMemsetAsync(ws.bm, 0, (size_t)n_frames * g.frame_elems, stream);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(ws.n_ties, 0, (size_t)n_frames * kTieStride * sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  e = cudaMemsetAsync(ws.kp_valid, 0, (size_t)n_frames * ws.corner_cap, stream);
   if (e != cudaSuccess) return e;
   dim3 grid((ws.corner_cap + 127) / 128, n_frames);
   // BRISK_B200_NMS_TIMING=1: per-kernel CUDA-event times of this launch sequence on stderr (debug aid; synchronises)
