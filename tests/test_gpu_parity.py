@@ -192,6 +192,15 @@ def test_chunked_batch_equals_single_pass(ctx):
     for f in range(len(frames)):
         n = a[1][f]
         assert np.array_equal(a[0][f, :n], b[0][f, :n]) and np.array_equal(a[2][f, :n], b[2][f, :n])
+    # many small chunks of host frames: the two-slot pipeline with its short first chunk
+    frames = bb.synthetic_batch(13, 640, 480, 70)
+    a = bb.detect_and_compute_batch(det, ext, frames, cap=4096)
+    tiny = bb.Context(0, workspace_limit=64 << 20)
+    b = bb.detect_and_compute_batch(bb.BriskFeatureDetector(60, 4, ctx=tiny), bb.BriskDescriptorExtractor(ctx=tiny), frames, cap=4096)
+    assert np.array_equal(a[1], b[1]) and a[1].min() > 0
+    for f in range(len(frames)):
+        n = a[1][f]
+        assert np.array_equal(a[0][f, :n], b[0][f, :n]) and np.array_equal(a[2][f, :n], b[2][f, :n])
 
 
 def test_device_resident_inputs_and_outputs(ctx):
