@@ -89,8 +89,9 @@ BRISK_HD void gs_insertion_sort(const Less& less, T* first, T* last) {
 
 // One pass of std::__introsort_loop's body on [first, last): __unguarded_partition_pivot (median of
 // first+1, mid, last-1 moved to first, then the unguarded Hoare scan).  Returns the cut.
+// __move_median_to_first(first, first + 1, mid, last - 1) of __unguarded_partition_pivot.
 template <class T, class Less>
-BRISK_HD int gs_partition(const Less& less, T* a, int first, int last) {
+BRISK_HD void gs_median_to_first(const Less& less, T* a, int first, int last) {
   const int mid = first + (last - first) / 2;
   T& ra = a[first + 1]; T& rb = a[mid]; T& rc = a[last - 1];
   if (less(ra, rb)) {
@@ -100,6 +101,11 @@ BRISK_HD int gs_partition(const Less& less, T* a, int first, int last) {
   } else if (less(ra, rc)) gs_swap(a[first], ra);
   else if (less(rb, rc)) gs_swap(a[first], rc);
   else gs_swap(a[first], rb);
+}
+
+template <class T, class Less>
+BRISK_HD int gs_partition(const Less& less, T* a, int first, int last) {
+  gs_median_to_first(less, a, first, last);
   int lo = first + 1, hi = last;
   for (;;) {
     while (less(a[lo], a[first])) ++lo;

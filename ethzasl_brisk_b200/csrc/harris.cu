@@ -138,25 +138,88 @@ harris_nms3d_kernel(PyramidGeom g, HarrisLayerParams hp, const int* __restrict__
 
 // One CTA per (frame, layer): stable compaction of the kept maxima, then the order std::sort gives them
 // (descending score; the arrangement of equal scores is part of the reference's result, so the CTA
-// replays libstdc++'s introsort).  The two sides of a partition are independent, so the replay runs
-// level by level with one thread per open range; ranges of at most 16 elements get their share of
-// the final insertion sort from the thread that produced them.
+// replays libstdc++'s introsort).  Large ranges are partitioned by the whole CTA (cta_partition), the rest
+// level by level with one thread per open range; ranges of at most 16 elements get their share of the
+// final insertion sort from the thread that produced them.
 constexpr int kSortThreads = 256;
-constexpr int kSortRanges = 2048;   // open ranges per level held in shared memory; overflow is sorted by its producer
+constexpr int kSortRanges = 1792;   // open ranges per level held in shared memory; overflow is sorted by its producer
+constexpr int kCoopMin = 768;       // ranges above this size are partitioned by the whole CTA
+constexpr int kCoopStack = 96;      // > 2 x depth limit of a 2^20-element sort
+
+struct SortRange { int first, last, depth; };
+
+// std::__unguarded_partition_pivot on dst[first, last), by the whole CTA, with the same result as the serial
+// scan (gs_partition).  The serial loop alternates "advance lo to the next element that is not before the
+// pivot" and "retreat hi to the next element that is not after it", swapping the two until they cross.  Those
+// stops are properties of the ORIGINAL array as long as the scans have not met: the k-th swap exchanges the
+// k-th such element from the left with the k-th from the right.  So: list both kinds of stops (two CTA-wide
+// compactions into `scratch`, 2 x (last - first) ints), count the K leading pairs with l_k < r_k, swap them
+// in parallel, and the cut is min(l_(K+1), r_K) -- once hi has passed, everything from r_K on stops lo.
+__device__ int cta_partition(HPoint* __restrict__ dst, int first, int last, int* __restrict__ scratch, int* s_warp, int* s_misc) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = last - first;
+  if (tid == 0) gs_median_to_first(HpLess(), dst, first, last);
+  __syncthreads();
+  const HPoint pivot = dst[first];
+  int* Ls = scratch;        // ascending positions j in [first + 1, last) with !(dst[j] before pivot)
+  int* Rs = scratch + n;    // ascending positions j in [first, last - 1] with !(pivot before dst[j])
+  if (tid == 0) { s_misc[0] = 0; s_misc[1] = 0; s_misc[2] = 0; }
+  __syncthreads();
+  for (int base = first; base < last; base += kSortThreads) {
+    const int j = base + tid;
+    bool isL = false, isR = false;
+    if (j < last) {
+      const HPoint e = dst[j];
+      isL = j > first && !hp_before(e, pivot);
+      isR = !hp_before(pivot, e);
+    }
+    const unsigned bl = __ballot_sync(0xffffffffu, isL), br = __ballot_sync(0xffffffffu, isR);
+    if (lane == 0) { s_warp[warp] = __popc(bl); s_warp[8 + warp] = __popc(br); }
+    __syncthreads();
+    int offL = s_misc[0], offR = s_misc[1];
+    for (int w = 0; w < warp; ++w) { offL += s_warp[w]; offR += s_warp[8 + w]; }
+    if (isL) Ls[offL + __popc(bl & ((1u << lane) - 1u))] = j;
+    if (isR) Rs[offR + __popc(br & ((1u << lane) - 1u))] = j;
+    __syncthreads();
+    if (tid == 0) { int a = 0, b = 0; for (int w = 0; w < kSortThreads / 32; ++w) { a += s_warp[w]; b += s_warp[8 + w]; } s_misc[0] += a; s_misc[1] += b; }
+    __syncthreads();
+  }
+  const int nL = s_misc[0], nR = s_misc[1];
+  // K = number of leading pairs (k-th stop from the left, k-th from the right) that have not crossed
+  int mine = 0;
+  for (int k = tid; k < min(nL, nR); k += kSortThreads) mine += Ls[k] < Rs[nR - 1 - k] ? 1 : 0;
+  if (mine) atomicAdd(&s_misc[2], mine);
+  __syncthreads();
+  const int K = s_misc[2];
+  for (int k = tid; k < K; k += kSortThreads) {
+    const int l = Ls[k], r = Rs[nR - 1 - k];
+    const HPoint t = dst[l]; dst[l] = dst[r]; dst[r] = t;
+  }
+  int cut;
+  if (K == 0) cut = Ls[0];
+  else { const int rK = Rs[nR - K]; cut = K < nL ? min(Ls[K], rK) : rK; }
+  __syncthreads();
+  return cut;
+}
 
 __global__ void __launch_bounds__(kSortThreads)
 harris_sort_kernel(int n_layers, const int* __restrict__ layer_start, const HPoint* __restrict__ pts,
-                   const uint8_t* __restrict__ keep, HPoint* __restrict__ sorted, int* __restrict__ layer_kept, int cap) {
-  __shared__ int2 s_ranges[2][kSortRanges];
+                   const uint8_t* __restrict__ keep, HPoint* __restrict__ sorted, int* __restrict__ layer_kept,
+                   HPoint* __restrict__ scratch_all, int cap) {
+  __shared__ SortRange s_ranges[2][kSortRanges];
+  __shared__ SortRange s_stack[kCoopStack];
   __shared__ int s_count[2];
-  __shared__ int s_warp[kSortThreads / 32];
-  __shared__ int s_base;
+  __shared__ int s_warp[16];
+  __shared__ int s_misc[4];
+  __shared__ int s_base, s_sp;
   const int layer = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int* ls = layer_start + (long long)frame * (kMaxLayers + 1);
   const int begin = min(ls[layer], cap), end = min(ls[layer + 1], cap);
   const HPoint* src = pts + (long long)frame * cap;
   const uint8_t* kf = keep + (long long)frame * cap;
   HPoint* dst = sorted + (long long)frame * cap + begin;
+  // 8 bytes per element of the layer's segment of the survivor buffer, which is written only later
+  int* scratch = reinterpret_cast<int*>(scratch_all + (long long)frame * cap + begin);
   if (tid == 0) s_base = 0;
   __syncthreads();
   // stable compaction, kSortThreads candidates per round
@@ -176,31 +239,57 @@ harris_sort_kernel(int n_layers, const int* __restrict__ layer_start, const HPoi
   const int m = s_base;
   if (tid == 0) {
     layer_kept[frame * kMaxLayers + layer] = m;
-    s_ranges[0][0] = make_int2(0, m);
-    s_count[0] = m > 16 ? 1 : 0;
-    s_count[1] = 0;
-    if (m > 1 && m <= 16) hp_insertion_sort(dst, dst + m);
+    s_count[0] = 0; s_count[1] = 0; s_sp = 0;
+    if (m > 16) { s_stack[0] = SortRange{0, m, gcc_depth_limit(m)}; s_sp = 1; }
+    else if (m > 1) hp_insertion_sort(dst, dst + m);
   }
   __syncthreads();
-  int cur = 0;
-  for (int depth = gcc_depth_limit(max(m, 1)); s_count[cur] > 0; --depth, cur ^= 1) {
-    const int count = s_count[cur];
-    for (int r = tid; r < count; r += kSortThreads) {
-      const int2 rg = s_ranges[cur][r];
-      if (depth == 0) { hp_heapsort(dst + rg.x, rg.y - rg.x); continue; }
-      const int cut = gcc_partition(dst, rg.x, rg.y);
+  // phase A: ranges above kCoopMin, one at a time, by the whole CTA
+  while (s_sp > 0) {
+    const SortRange rg = s_stack[s_sp - 1];
+    __syncthreads();
+    if (tid == 0) --s_sp;
+    if (rg.last - rg.first <= kCoopMin || rg.depth == 0) {
+      // small enough for one thread (or out of depth: heapsort): hand it to phase B
+      if (tid == 0) { const int slot = s_count[0]++; if (slot < kSortRanges) s_ranges[0][slot] = rg; else gcc_sort_range(dst, rg.first, rg.last, rg.depth); }
+      __syncthreads();
+      continue;
+    }
+    __syncthreads();
+    const int cut = cta_partition(dst, rg.first, rg.last, scratch, s_warp, s_misc);
+    if (tid == 0) {
 #pragma unroll
       for (int side = 0; side < 2; ++side) {
-        const int f = side ? cut : rg.x, l = side ? rg.y : cut;
+        const int f = side ? cut : rg.first, l = side ? rg.last : cut;
+        if (l - f <= 16) { hp_insertion_sort(dst + f, dst + l); continue; }
+        s_stack[s_sp++] = SortRange{f, l, rg.depth - 1};
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) s_count[0] = min(s_count[0], kSortRanges);
+  __syncthreads();
+  // phase B: level by level, one thread per open range
+  int cur = 0;
+  while (s_count[cur] > 0) {
+    const int count = s_count[cur];
+    for (int r = tid; r < count; r += kSortThreads) {
+      const SortRange rg = s_ranges[cur][r];
+      if (rg.depth == 0) { hp_heapsort(dst + rg.first, rg.last - rg.first); continue; }
+      const int cut = gcc_partition(dst, rg.first, rg.last);
+#pragma unroll
+      for (int side = 0; side < 2; ++side) {
+        const int f = side ? cut : rg.first, l = side ? rg.last : cut;
         if (l - f <= 16) { hp_insertion_sort(dst + f, dst + l); continue; }
         const int slot = atomicAdd(&s_count[cur ^ 1], 1);
-        if (slot < kSortRanges) s_ranges[cur ^ 1][slot] = make_int2(f, l);
-        else gcc_sort_range(dst, f, l, depth - 1);
+        if (slot < kSortRanges) s_ranges[cur ^ 1][slot] = SortRange{f, l, rg.depth - 1};
+        else gcc_sort_range(dst, f, l, rg.depth - 1);
       }
     }
     __syncthreads();
     if (tid == 0) { s_count[cur] = 0; s_count[cur ^ 1] = min(s_count[cur ^ 1], kSortRanges); }
     __syncthreads();
+    cur ^= 1;
   }
 }
 
@@ -381,7 +470,7 @@ cudaError_t launch_harris_detect(const PyramidGeom& g, const HarrisWorkspace& hw
   }
   dim3 gp((hw.det.corner_cap + 127) / 128, n_frames);
   harris_nms3d_kernel<<<gp, 128, 0, stream>>>(g, hp, hw.scores, hw.det.layer_start, hw.pts, hw.keep, hw.det.corner_cap, thr);
-  harris_sort_kernel<<<dim3(g.n_layers, n_frames), kSortThreads, 0, stream>>>(g.n_layers, hw.det.layer_start, hw.pts, hw.keep, hw.sorted, hw.layer_kept, hw.det.corner_cap);
+  harris_sort_kernel<<<dim3(g.n_layers, n_frames), kSortThreads, 0, stream>>>(g.n_layers, hw.det.layer_start, hw.pts, hw.keep, hw.sorted, hw.layer_kept, hw.surv, hw.det.corner_cap);
   if (!(radius > 0.0)) {
     harris_bucketing_kernel<<<dim3(g.n_layers, n_frames), 32, 0, stream>>>(g, hw.det.layer_start, hw.sorted, hw.layer_kept, hw.surv, hw.layer_surv, hw.det.corner_cap, max_kpt);
     harris_emit_kernel<<<n_frames, 256, 0, stream>>>(g, hp, hw.scores, hw.det.layer_start, hw.surv, hw.layer_surv, hw.det.corner_cap, out, counts, kp_cap);

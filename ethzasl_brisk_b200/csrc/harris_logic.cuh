@@ -113,6 +113,7 @@ BRISK_HD void harris_subpixel2d(double s00, double s01, double s02, double s10, 
 // the exact permutation matters: it fixes both the greedy uniformity outcome and the output order.
 // ---------------------------------------------------------------------------
 struct HpLess { BRISK_HD bool operator()(const HPoint& a, const HPoint& b) const { return a.score > b.score; } };
+BRISK_HD bool hp_before(const HPoint& a, const HPoint& b) { return HpLess()(a, b); }
 BRISK_HD void hp_heapsort(HPoint* first, long len) { gs_heapsort(HpLess(), first, len); }
 BRISK_HD void hp_insertion_sort(HPoint* first, HPoint* last) { gs_insertion_sort(HpLess(), first, last); }
 BRISK_HD int gcc_partition(HPoint* a, int first, int last) { return gs_partition(HpLess(), a, first, last); }
