@@ -50,6 +50,14 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.keep, self.on = [], False
+
+    def mark(self):
+        """Start of a timed region: lines read from now on count."""
+        self.on = True
+
+    def pause(self):
+        self.on = False
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -63,7 +71,10 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            row = [c.strip() for c in line.split(",")]
+            self.rows.append(row)
+            if self.on:
+                self.keep.append(row)
 
     def stop(self):
         if not self.proc:
@@ -71,7 +82,7 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in (self.keep or self.rows[-1:]):
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -207,13 +218,18 @@ def run_gpu(args):
     resident = lambda: bb.detect_and_compute_batch(det, ext, d_frames, cap=cap, out=d_out)
     e2e = lambda: bb.detect_and_compute_batch(det, ext, h_frames, cap=cap, out=h_out)
 
-    for _ in range(args.warmup):
-        resident()
+    # nvidia-smi takes a few hundred ms to deliver its first line: start it before the warm-up, count only the
+    # lines of the two timed regions (resident and host end-to-end)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        resident()
+    if rank == 0:
+        sampler.mark()
     ms_res, stages, launches = timed(resident, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        sampler.pause()
     counts = d_out[1].cpu().numpy()
     # per-stage device times without cross-stream overlap (same kernels, one stream, stages back to
     # back): these feed the per-kernel roofline numbers; the headline numbers above keep pipelining on
@@ -223,7 +239,10 @@ def run_gpu(args):
     ctx.set_pipelining(True)
     for _ in range(max(1, args.warmup // 2)):
         e2e()
+    if rank == 0:
+        sampler.mark()
     ms_e2e, _, _ = timed(e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
     hc = h_out[1].numpy()
     assert np.array_equal(hc, counts), "host and device paths disagree"
     kp_total = int(np.minimum(counts, cap).sum())
@@ -304,7 +323,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
