@@ -327,7 +327,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       // KeyPointBucketing (key-point-bucketing-inl.h:74-112): the reference reserves maxNumKpt entries up front, so the default
       // maxNumKpt = SIZE_MAX throws std::length_error there; a finite limit is required, and 4 buckets per axis need > 4 pixels
       if (det->max_kpt <= 0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "key point bucketing (uniformityRadius <= 0) needs a finite maxNumKpt > 0");
-    } else if (det->radius < 15.0 / 4.0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "uniformityRadius below 3.75 is not supported");
+    } else if (det->radius < 1.0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "uniformityRadius in (0, 1) is not supported (the occupancy map would take more than 225 bytes per pixel)");
   } else if (det) {
     if (det->thresh < 30 || det->thresh > 255)
       return fail(ctx, BRISK_ERR_UNSUPPORTED, "AGAST threshold must be in [30, 255] (lower values make corner scores <= 2, whose cache semantics are not implemented)");

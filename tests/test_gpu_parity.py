@@ -433,7 +433,8 @@ def test_golden_harris_fixture(ctx, golden, i):
 
 
 @pytest.mark.parametrize("octaves,radius,abs_thr,max_kpt", [(0, 30.0, 20.0, None), (4, 30.0, 20.0, None), (2, 10.0, 0.0, 300),
-                                                             (1, 45.0, 50.0, None), (3, 15.0, 5.0, None)])
+                                                             (1, 45.0, 50.0, None), (3, 15.0, 5.0, None), (2, 2.5, 20.0, None),
+                                                             (1, 1.0, 40.0, 500)])
 def test_harris_detect_bit_exact(ctx, oracle, golden, octaves, radius, abs_thr, max_kpt):
     # multi-layer Harris incl. 3-D NMS and the introsort tie order (not covered by the golden fixture)
     det = bb.ScaleSpaceFeatureDetector(octaves, radius, abs_thr, max_kpt, ctx=ctx)
