@@ -329,8 +329,12 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       if (det->max_kpt <= 0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "key point bucketing (uniformityRadius <= 0) needs a finite maxNumKpt > 0");
     } else if (det->radius < 1.0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "uniformityRadius in (0, 1) is not supported (the occupancy map would take more than 225 bytes per pixel)");
   } else if (det) {
-    if (det->thresh < 30 || det->thresh > 255)
-      return fail(ctx, BRISK_ERR_UNSUPPORTED, "AGAST threshold must be in [30, 255] (lower values make corner scores <= 2, whose cache semantics are not implemented)");
+    // The closed form of the lazy score cache (nms_logic.cuh) relies on every detected corner holding a score > 2 (such
+    // cache entries are returned whatever threshold is asked, brisk-layer.cc:124-126).  A corner's score is its
+    // threshold-map value T, and a corner needs 9 ring pixels more than b = (max(T, 10) * thresh) / 100 away from the
+    // centre inside a disk whose range is T, i.e. T >= thresh / 10 + 1: that is > 2 for every thresh >= 20.
+    if (det->thresh < 20 || det->thresh > 255)
+      return fail(ctx, BRISK_ERR_UNSUPPORTED, "AGAST threshold must be in [20, 255] (below 20 corners can score 2, which the reference's score cache does not keep)");
     if (det->octaves < 0 || 2 * det->octaves > kMaxLayers) return fail(ctx, BRISK_ERR_UNSUPPORTED, "octaves must be in [0, 6]");
     // suppressScaleNonmaxima = false (brisk-scale-space.cc:131-170): with one layer it is the single-layer branch
     // (:172-209) word for word; with more layers the reference indexes layer 0's corner list with the counts of

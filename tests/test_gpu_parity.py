@@ -73,7 +73,7 @@ def test_golden_ast_fixture(ctx, golden, i):
     assert np.array_equal(d, gd)
 
 
-@pytest.mark.parametrize("thresh,octaves", [(60, 4), (70, 3), (40, 2), (70, 0), (60, 1), (30, 4)])
+@pytest.mark.parametrize("thresh,octaves", [(60, 4), (70, 3), (40, 2), (70, 0), (60, 1), (30, 4), (20, 3), (24, 4)])
 def test_detect_bit_exact(ctx, oracle, golden, thresh, octaves):
     det = bb.BriskFeatureDetector(thresh, octaves, ctx=ctx)
     det.set_corner_capacity(200000)
@@ -117,7 +117,7 @@ def test_detect_empty_and_flat(ctx):
 
 def test_unsupported_configurations_fail_loudly(ctx):
     img = bb.synthetic_frame(320, 240, 1)
-    for bad in (bb.BriskFeatureDetector(20, 4, ctx=ctx), bb.BriskFeatureDetector(60, 7, ctx=ctx),
+    for bad in (bb.BriskFeatureDetector(19, 4, ctx=ctx), bb.BriskFeatureDetector(60, 7, ctx=ctx),
                 bb.BriskFeatureDetector(60, 4, False, ctx=ctx)):
         with pytest.raises(bb.BriskError):
             bad.detect(img)

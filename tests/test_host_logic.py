@@ -33,7 +33,7 @@ def emul():
     return detect
 
 
-@pytest.mark.parametrize("thresh,octaves", [(70, 3), (60, 4), (30, 2), (70, 0), (45, 1)])
+@pytest.mark.parametrize("thresh,octaves", [(70, 3), (60, 4), (30, 2), (70, 0), (45, 1), (20, 3)])
 def test_parallel_nms_formulation_golden(emul, oracle, golden, thresh, octaves):
     for i in (0, 1):
         img = golden[f"image{i}"]
