@@ -110,3 +110,23 @@ def test_synthetic_frames_are_deterministic():
     c = synthetic_frame(320, 240, 43)
     assert a.dtype == np.uint8 and a.shape == (240, 320)
     assert np.array_equal(a, b) and not np.array_equal(a, c)
+
+
+def test_matcher_collection_host_logic():
+    # the host part of BruteForceMatcher (no GPU): train collection -> one matrix, masks side by side, and
+    # cv::DescriptorMatcher::isMaskedOut (only when every image has a non-empty mask)
+    import ethzasl_brisk_b200 as bb
+    m = object.__new__(bb.BruteForceMatcher)
+    m.ctx = None
+    m._train = [np.full((3, 48), 1, np.uint8), np.zeros((0, 48), np.uint8), np.full((2, 48), 2, np.uint8)]
+    q = np.zeros((4, 48), np.uint8)
+    query, trains, train, start, mask, masked_out = m._collection(q, None, None)
+    assert train.shape == (5, 48) and start.tolist() == [0, 3, 3, 5] and mask is None and not masked_out.any()
+    masks = [np.array([[1, 0, 0], [0, 0, 0], [0, 0, 0], [1, 1, 1]], np.uint8), None, np.array([[0, 0], [0, 0], [0, 5], [0, 0]], np.uint8)]
+    _, _, _, _, mask, masked_out = m._collection(q, None, masks)
+    assert mask.tolist() == [[1, 0, 0, 0, 0], [0, 0, 0, 0, 0], [0, 0, 0, 0, 1], [1, 1, 1, 0, 0]]
+    assert not masked_out.any()  # one image has no mask: no query is "masked out"
+    m._train = [m._train[0], m._train[2]]
+    _, _, _, _, mask, masked_out = m._collection(q, None, [masks[0], masks[2]])
+    assert masked_out.tolist() == [False, True, False, False]
+    assert m.isMaskSupported()
