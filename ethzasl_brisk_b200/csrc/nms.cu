@@ -116,7 +116,8 @@ __device__ __forceinline__ void tie_issue_loads(const LayerView& L, int mode, in
   t->fp = mode == kModeMid ? *reinterpret_cast<const int2*>(checks + 6) : make_int2(0, 0);
 }
 
-__device__ __forceinline__ int warp_tie_decide(const LayerView& L, int mode, int x, int y, const TieLoads& ld,
+template <int mode>
+__device__ __forceinline__ int warp_tie_decide(const LayerView& L, int x, int y, const TieLoads& ld,
                                                uint16_t* s_win /* 64 entries, this warp's */) {
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
@@ -134,8 +135,8 @@ __device__ __forceinline__ int warp_tie_decide(const LayerView& L, int mode, int
   const int tq = lane < 25 ? (s_win[(oy + 4) * 8 + ox + 4] & kCmT) : 0;  // 0 on border pixels
   // cache_state of the lane's pixel q, for all lanes at once: one step per raster-earlier corner p of the
   // window (uniform), in raster order; pending verdicts taken as reject (0) / accept (1)
-  bool sticky0 = ld.bmv != 0, sticky1 = sticky0;
-  int last0 = sticky0 ? 1 : 0, last1 = last0;
+  int sticky0 = ld.bmv != 0 ? 1 : 0, sticky1 = sticky0;  // (ints: bools get packed into bytes of one register)
+  int last0 = sticky0, last1 = last0;
   while (earlier) {
     const int i = __ffsll((long long)earlier) - 1;
     earlier &= earlier - 1;
@@ -152,9 +153,9 @@ __device__ __forceinline__ int warp_tie_decide(const LayerView& L, int mode, int
     if (mode == kModeSingle) patch = inblk;
     else if (mode == kModeLast) patch = inblk && ((pox >= 0 && poy >= 0 && near) || chk);
     else patch = near && chk;
-    if (look) { last0 = t; last1 = t; if (t <= F) { sticky0 = true; sticky1 = true; } }
-    if (patch && acc0) { sticky0 = true; last0 = 1; }
-    if (patch && acc1) { sticky1 = true; last1 = 1; }
+    if (look) { last0 = t; last1 = t; if (t <= F) { sticky0 = 1; sticky1 = 1; } }
+    if (patch && acc0) { sticky0 = 1; last0 = 1; }
+    if (patch && acc1) { sticky1 = 1; last1 = 1; }
   }
   int st0 = 0, st1 = 0;
   if (lane < 25 && !tq && F >= 1 && !in_border(L, x + ox, y + oy)) {
@@ -299,7 +300,9 @@ nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag
         if (i + kChainWarps < n) tie_issue_loads(L, mode, ent1.y & 0xffff, ent1.y >> 16, ws.fwin + (fslot + ent1.x) * 32, ws.checks + (fslot + ent1.x) * 8, &ld1);
         if (i + 2 * kChainWarps < n) ent2 = cur[i + 2 * kChainWarps];
         const int x = ent.y & 0xffff, y = ent.y >> 16;
-        const int verdict = warp_tie_decide(L, mode, x, y, ld, s_win[warp]);
+        const int verdict = mode == kModeMid ? warp_tie_decide<kModeMid>(L, x, y, ld, s_win[warp])
+                          : mode == kModeLast ? warp_tie_decide<kModeLast>(L, x, y, ld, s_win[warp])
+                                              : warp_tie_decide<kModeSingle>(L, x, y, ld, s_win[warp]);
         if (lane == 0) {
           if (verdict < 0) nxt[atomicAdd(&s_next[pass & 1], 1)] = ent;
           else {
