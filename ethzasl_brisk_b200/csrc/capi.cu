@@ -45,6 +45,8 @@ struct Slot {
   cudaEvent_t ev[BRISK_STAGE_COUNT + 1] = {};
   cudaEvent_t done = nullptr;
   cudaEvent_t computed = nullptr;  // recorded after the last kernel of a chunk
+  cudaStream_t side = nullptr;     // the integral image of a chunk is built here while the detector's kernels run
+  cudaEvent_t fork = nullptr, join = nullptr;
   int32_t* h_counts = nullptr;  // pinned: counts of the chunk + [cap_counts] error flag
   size_t h_counts_cap = 0;
   DevBuf pyr, cm, bm, rowcnt, layer_start, corners, fwin, checks, kp_tmp, kp_valid, integral, rounds, surv;
@@ -456,6 +458,17 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       ctx->launches += 1;
     }
     tm.mark(2);
+    // The integral image only needs layer 0: with a detector in front of the extractor it is built on a side
+    // stream while the detector's kernels run (the tie chain and the per-corner kernels are ALU bound, the integral
+    // image is bandwidth bound).  Not when stage times are being collected.
+    const bool integral_aside = det && ext && !ctx->timing;
+    if (integral_aside) {
+      CU_OK(cudaEventRecord(sl.fork, sl.stream));
+      CU_OK(cudaStreamWaitEvent(sl.side, sl.fork, 0));
+      CU_OK(launch_integral(ws.pyr + g.L[0].off, g.frame_elems, g.L[0].pitch, w, h, c, sl.integral.as<int32_t>(), sl.side));
+      CU_OK(cudaEventRecord(sl.join, sl.side));
+      ctx->launches += 2;
+    }
     CU_OK(cudaMemsetAsync(sl.flag.p, 0, 16, sl.stream));
     if (det && det->harris) {
       HarrisWorkspace hw = plan.hw;
@@ -481,8 +494,11 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     tm.mark(5);
     if (ext) {
       const uint8_t* l0 = ws.pyr + g.L[0].off;
-      CU_OK(launch_integral(l0, g.frame_elems, g.L[0].pitch, w, h, c, sl.integral.as<int32_t>(), sl.stream));
-      ctx->launches += 2;
+      if (integral_aside) CU_OK(cudaStreamWaitEvent(sl.stream, sl.join, 0));
+      else {
+        CU_OK(launch_integral(l0, g.frame_elems, g.L[0].pitch, w, h, c, sl.integral.as<int32_t>(), sl.stream));
+        ctx->launches += 2;
+      }
       tm.mark(6);
       // The reference samples a tightly packed image (stride == cols) and a few of its reads land one
       // column past the row end, i.e. on the first pixel of the next row; give the sampler the same
@@ -546,6 +562,9 @@ int brisk_ctx_create(int device, void* stream, brisk_ctx** out) {
   cudaEventCreateWithFlags(&ctx->entry, cudaEventDisableTiming);
   for (Slot& sl : ctx->slots) {
     if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); brisk_ctx_destroy(ctx); return BRISK_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&sl.side, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); brisk_ctx_destroy(ctx); return BRISK_ERR_CUDA; }
+    cudaEventCreateWithFlags(&sl.fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&sl.join, cudaEventDisableTiming);
     for (auto& e : sl.ev) cudaEventCreate(&e);
     cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&sl.computed, cudaEventDisableTiming);
@@ -574,6 +593,9 @@ void brisk_ctx_destroy(brisk_ctx* ctx) {
     if (sl.computed) cudaEventDestroy(sl.computed);
     if (sl.h_counts) cudaFreeHost(sl.h_counts);
     if (sl.stream) cudaStreamDestroy(sl.stream);
+    if (sl.side) cudaStreamDestroy(sl.side);
+    if (sl.fork) cudaEventDestroy(sl.fork);
+    if (sl.join) cudaEventDestroy(sl.join);
   }
   DevBuf* bufs[] = {&ctx->knn_q, &ctx->knn_t, &ctx->knn_keys, &ctx->knn_part, &ctx->knn_idx, &ctx->knn_dist,
                     &ctx->knn_mask, &ctx->rad_counts, &ctx->rad_offsets, &ctx->rad_matches};
