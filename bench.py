@@ -94,6 +94,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def pin_to_gpu_numa_node(index):
+    """One process per GPU: run on the CPUs NVML reports as local to the GPU, so that the pinned host buffers
+    of the end-to-end path are allocated on the GPU's NUMA node (first touch).  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
+        full = os.sched_getaffinity(0)
+        cpus &= full
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            pin_to_gpu_numa_node.full = full
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -168,6 +188,7 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
+    numa = pin_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -243,6 +264,8 @@ def run_gpu(args):
         sampler.mark()
     ms_e2e, _, _ = timed(e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    if getattr(pin_to_gpu_numa_node, "full", None):
+        os.sched_setaffinity(0, pin_to_gpu_numa_node.full)  # the CPU baseline below uses every host core
     hc = h_out[1].numpy()
     assert np.array_equal(hc, counts), "host and device paths disagree"
     kp_total = int(np.minimum(counts, cap).sum())
@@ -305,7 +328,7 @@ def run_gpu(args):
             "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
             "config": {"workload": "C3: AGAST(60,4) detect + BRISK2 describe, 1920x1080 synthetic frames", "frames_per_gpu_per_step": n,
-                       "global_frames_per_step": world * n, "keypoints_per_frame": kps_per_frame, "parallelism": f"frame-sharded x{world}, no collective",
+                       "global_frames_per_step": world * n, "keypoints_per_frame": kps_per_frame, "parallelism": f"frame-sharded x{world}, no collective", "cpus_per_rank": numa,
                        "l2": f"inputs ({n * H * W / 1e6:.0f} MB per step) exceed the 126 MB L2; no explicit flush", "kp_capacity": cap},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roof, "stages": stage_report, "cpu_baseline": cpu, "clocks": clocks,
