@@ -309,6 +309,22 @@ def run_gpu(args):
     roof = {"bound": "hbm", "kernel": top, "achieved": stage_report[top]["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
             "frac": stage_report[top]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
             "note": "dominant stage by CUDA-event time of a non-pipelined step (stages back to back on one stream); see stages"}
+    # DRAM bytes per frame of the stages' kernels from the committed `ncu --set full` captures (dram__bytes_read.sum +
+    # dram__bytes_write.sum of one launch / frames of that launch); reported for one frame of the dominant stage,
+    # like `achieved`, which is per frame too (algorithmic bytes of n frames / time of n frames)
+    NCU_DRAM_BYTES_PER_FRAME = {"describe": (2.195719e9 + 87.774e6) / 256,        # profiles/r01_ncu_full_top_kernels_v14.txt
+                                "pyramid": (0.354613e9 + 0.626522e9) / 256}       # (inputs partly L2 resident in that capture)
+    LIMITER = {"describe": "L1/L2 sector rate of scattered 4-byte gathers (ncu: l1tex 77 %, lts 55 % of peak, DRAM 30 %); the "
+                           "integral images of a chunk do not fit L2, so ~8.9 MB per frame come from DRAM although only "
+                           "104 B per key point are compulsory",
+               "nms": "ALU pipe / instruction issue of the per-corner kernels and the tie chain (ncu: ALU 73-79 %)",
+               "detect": "ALU pipe (packed min/max at half rate; ncu: ALU 73 %, DRAM 10 %)"}
+    roof["algorithmic_bytes"] = bytes_per_frame[top] * n
+    if top in NCU_DRAM_BYTES_PER_FRAME:
+        roof["traffic"] = NCU_DRAM_BYTES_PER_FRAME[top] * n
+        roof["traffic_note"] = "ncu dram bytes per frame x frames of the step (capture: profiles/r01_ncu_full_top_kernels_v14.txt)"
+    if top in LIMITER:
+        roof["limiter"] = LIMITER[top]
 
     # CPU baseline beside it: the unmodified reference on a bounded sample of the same frames
     cpu = None
