@@ -195,7 +195,7 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
     plan->hw.occ_frame_bytes = off;
   }
   ws.corner_cap = det ? ccap : 0;
-  plan->integral_elems = ext ? (size_t)(w + 1) * (h + 1) : 0;
+  plan->integral_elems = ext ? (size_t)w * h * 4 : 0;  // one 2x2 block of the integral image per pixel
   const size_t integral_aux = ext ? (size_t)integral_aux_elems(w, h) : 0;
   const int desc_bytes = ext ? ext->dev.desc_bytes : 0;
   size_t per_frame = (size_t)g.frame_elems;  // image planes
@@ -781,14 +781,27 @@ int brisk_debug_integral(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_
   Slot& sl = ctx->slots[0];
   const DetectWorkspace ws = slot_ws(plan, sl);
   (void)ws;
-  CU_OK(sl.integral.ensure(((size_t)(w + 1) * (h + 1) + (size_t)integral_aux_elems(w, h)) * 4));
+  CU_OK(sl.integral.ensure(((size_t)w * h * 4 + (size_t)integral_aux_elems(w, h)) * 4));
   CUtensorMap map; int write_l0;
   rc = stage_input(ctx, sl, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0);
   if (rc) return rc;
   CU_OK(launch_pyramid(map, plan.g, ws.pyr, 1, write_l0, sl.stream));
   CU_OK(launch_integral(ws.pyr + plan.g.L[0].off, plan.g.frame_elems, plan.g.L[0].pitch, w, h, 1, sl.integral.as<int32_t>(), sl.stream));
-  CU_OK(cudaMemcpyAsync(out, sl.integral.p, (size_t)(w + 1) * (h + 1) * 4, cudaMemcpyDeviceToHost, sl.stream));
+  // the device holds one 2x2 block {S(Y,X), S(Y,X+1), S(Y+1,X), S(Y+1,X+1)} per pixel: rebuild S from the last
+  // components and check that the other three say the same
+  std::vector<int32_t> blk((size_t)w * h * 4);
+  CU_OK(cudaMemcpyAsync(blk.data(), sl.integral.p, blk.size() * 4, cudaMemcpyDeviceToHost, sl.stream));
   CU_OK(cudaStreamSynchronize(sl.stream));
+  const size_t iw = (size_t)w + 1;
+  for (size_t i = 0; i < iw * ((size_t)h + 1); ++i) out[i] = 0;
+  for (int Y = 0; Y < h; ++Y)
+    for (int X = 0; X < w; ++X) out[(size_t)(Y + 1) * iw + X + 1] = blk[((size_t)Y * w + X) * 4 + 3];
+  for (int Y = 0; Y < h; ++Y)
+    for (int X = 0; X < w; ++X) {
+      const int32_t* b = &blk[((size_t)Y * w + X) * 4];
+      if (b[0] != out[(size_t)Y * iw + X] || b[1] != out[(size_t)Y * iw + X + 1] || b[2] != out[(size_t)(Y + 1) * iw + X])
+        return fail(ctx, BRISK_ERR_CUDA, "internal error: inconsistent integral-image blocks");
+    }
   return BRISK_OK;
 }
 

@@ -24,9 +24,12 @@ namespace briskb200 {
 // the strip.  Kernel 2 (one CTA per strip, one thread per column) walks down the rows, eight at a time,
 // keeping the running column sums in registers; the eight rows of column sums go through shared memory to
 // the eight warps, each of which turns one row into its prefix sums (eight consecutive columns per lane,
-// then one warp scan) and adds what lies left of the strip; the threads then store the rows coalesced.
-// Traffic: the image twice (1 byte per pixel each) and the integral once (4 bytes per pixel); nothing is
-// read back (the two-pass form moved 27 MB per 1080p frame, this one 12.4 MB).
+// then one warp scan) and adds what lies left of the strip.  The result is stored as one 2x2 BLOCK per pixel,
+// block(Y, X) = {S(Y,X), S(Y,X+1), S(Y+1,X), S(Y+1,X+1)} (16 bytes, Y < h, X < w): the descriptor sampler then
+// gets the twelve taps and the two top corner pixels of a box from four 16-byte loads instead of fourteen
+// scattered 4- and 1-byte loads (describe is bound by the L1 sector rate of exactly those gathers).  A thread
+// builds its blocks from its own column, its left neighbour's (the sum left of the strip for the first thread)
+// and the row before.  Traffic: the image twice (1 byte per pixel each) and 16 bytes per pixel out.
 constexpr int kIntStrip = 256, kIntRows = 8;
 
 __host__ __device__ inline int integral_strips(int w) { return (w + kIntStrip - 1) / kIntStrip; }
@@ -61,33 +64,32 @@ integral_left_sums_kernel(const uint8_t* __restrict__ imgs, long long frame_stri
 
 __global__ void __launch_bounds__(kIntStrip)
 integral_strip_kernel(const uint8_t* __restrict__ imgs, long long frame_stride, int pitch, int w, int h,
-                      const int32_t* __restrict__ aux, int32_t* __restrict__ integral) {
+                      const int32_t* __restrict__ aux, int4* __restrict__ blocks) {
   __shared__ __align__(16) int s_t[2][kIntRows][kIntStrip];
   const int strip = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ns = integral_strips(w), iw = w + 1;
+  const int ns = integral_strips(w);
   const int x = strip * kIntStrip + tid;
   const bool in = x < w;
   const uint8_t* col = imgs + (long long)frame * frame_stride + x;
   const int32_t* lft = aux + (long long)frame * h * ns + strip;
-  int32_t* out = integral + (long long)frame * iw * (h + 1);
-  // row 0 and column 0 are zero
-  if (in) out[x + 1] = 0;
-  if (x == 0) out[0] = 0;
   int acc = 0, left_run = 0;
   int v[kIntRows], l[kIntRows];
   const uint8_t* cp = col;          // first row of the NEXT step's loads
   const int32_t* lp = lft;
-  int32_t* op = out + iw + x + 1;   // S(y0 + 1, x + 1)
+  int4* op = blocks + (long long)frame * w * h + x;   // block(y0, x)
+  int up_own = 0, up_left = 0;      // S(y0, x + 1) and S(y0, x): the row above the step (row 0 of S is zero)
 #pragma unroll
   for (int r = 0; r < kIntRows; ++r) { v[r] = (in && r < h) ? cp[r * pitch] : 0; l[r] = r < h ? lp[r * ns] : 0; }
   for (int y0 = 0, it = 0; y0 < h; y0 += kIntRows, ++it) {
     int (*t)[kIntStrip] = s_t[it & 1];
     int left_mine = left_run;  // left of the strip, rows <= y0 + warp (the row this thread's warp will finish)
+    int lf[kIntRows];          // left of the strip, rows <= y0 + r: S(y0 + r + 1, strip start)
 #pragma unroll
     for (int r = 0; r < kIntRows; ++r) {
       acc += v[r];             // column sum over rows <= y0 + r
       t[r][tid] = acc;
       left_run += l[r];
+      lf[r] = left_run;
       if (r <= warp) left_mine += l[r];
     }
     // next step's loads, in flight during the scans
@@ -117,33 +119,27 @@ integral_strip_kernel(const uint8_t* __restrict__ imgs, long long frame_stride, 
       p[0] = a; p[1] = b;
     }
     __syncthreads();
-    if (y0 + kIntRows <= h) {
-      if (in) {
+    // t[r][tid] = S(y0 + r + 1, x + 1); block(y0 + r, x) = {S(y0+r, x), S(y0+r, x+1), S(y0+r+1, x), S(y0+r+1, x+1)}
 #pragma unroll
-        for (int r = 0; r < kIntRows; ++r) op[r * iw] = t[r][tid];
-      }
-      if (x == 0) {
-#pragma unroll
-        for (int r = 0; r < kIntRows; ++r) op[r * iw - 1] = 0;
-      }
-    } else {
-      for (int r = 0; y0 + r < h; ++r) {
-        if (in) op[r * iw] = t[r][tid];
-        if (x == 0) op[r * iw - 1] = 0;
-      }
+    for (int r = 0; r < kIntRows; ++r) {
+      if (y0 + r >= h) break;
+      const int own = t[r][tid];
+      const int left = tid ? t[r][tid - 1] : lf[r];
+      if (in) op[(long long)r * w] = make_int4(up_left, up_own, left, own);
+      up_own = own; up_left = left;
     }
-    op += kIntRows * iw;
+    op += (long long)kIntRows * w;
   }
 }
 
 cudaError_t launch_integral(const uint8_t* imgs, long long frame_stride, int pitch, int w, int h, int n_frames,
                             int32_t* integral, cudaStream_t stream) {
-  // the per-row "left of the strip" sums live behind the integral images (integral_aux_elems per frame)
-  int32_t* aux = integral + (long long)n_frames * (w + 1) * (h + 1);
+  // the per-row "left of the strip" sums live behind the block images (integral_aux_elems per frame)
+  int32_t* aux = integral + (long long)n_frames * w * h * 4;
   dim3 g1((h + 7) / 8, n_frames);
   integral_left_sums_kernel<<<g1, 256, 0, stream>>>(imgs, frame_stride, pitch, w, h, aux);
   dim3 g2(integral_strips(w), n_frames);
-  integral_strip_kernel<<<g2, kIntStrip, 0, stream>>>(imgs, frame_stride, pitch, w, h, aux, integral);
+  integral_strip_kernel<<<g2, kIntStrip, 0, stream>>>(imgs, frame_stride, pitch, w, h, aux, reinterpret_cast<int4*>(integral));
   return cudaGetLastError();
 }
 
@@ -237,23 +233,23 @@ constexpr int kMaxPoints = 96;
 // scattered loads per point), so every lane works on its first two points at once: the two
 // independent gather chains overlap.
 __device__ __forceinline__ void sample_pattern(const PatternDev& pat, const uint8_t* __restrict__ img, int pitch,
-                                               const int32_t* __restrict__ integ, int iw, float kx, float ky,
+                                               const BlockIntegral integ, float kx, float ky,
                                                const float* __restrict__ pp, int scale, int P, int lane, int* val) {
   const int i0 = lane, i1 = lane + 32;
   if (i1 < P) {
     const int2 c0 = pat.sample_consts[scale * P + i0], c1 = pat.sample_consts[scale * P + i1];
     const float x0 = pp[3 * i0], y0 = pp[3 * i0 + 1], s0 = pp[3 * i0 + 2];
     const float x1 = pp[3 * i1], y1 = pp[3 * i1 + 1], s1 = pp[3 * i1 + 2];
-    const int v0 = smoothed_intensity(img, pitch, integ, iw, kx, ky, x0, y0, s0, c0.x, c0.y);
-    const int v1 = smoothed_intensity(img, pitch, integ, iw, kx, ky, x1, y1, s1, c1.x, c1.y);
+    const int v0 = smoothed_intensity_t(img, pitch, integ, kx, ky, x0, y0, s0, c0.x, c0.y);
+    const int v1 = smoothed_intensity_t(img, pitch, integ, kx, ky, x1, y1, s1, c1.x, c1.y);
     val[i0] = v0; val[i1] = v1;
   } else if (i0 < P) {
     const int2 c0 = pat.sample_consts[scale * P + i0];
-    val[i0] = smoothed_intensity(img, pitch, integ, iw, kx, ky, pp[3 * i0], pp[3 * i0 + 1], pp[3 * i0 + 2], c0.x, c0.y);
+    val[i0] = smoothed_intensity_t(img, pitch, integ, kx, ky, pp[3 * i0], pp[3 * i0 + 1], pp[3 * i0 + 2], c0.x, c0.y);
   }
   for (int i = lane + 64; i < P; i += 32) {
     const int2 sc = pat.sample_consts[scale * P + i];
-    val[i] = smoothed_intensity(img, pitch, integ, iw, kx, ky, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2], sc.x, sc.y);
+    val[i] = smoothed_intensity_t(img, pitch, integ, kx, ky, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2], sc.x, sc.y);
   }
 }
 
@@ -269,8 +265,7 @@ describe_kernel(PatternDev pat, const uint8_t* __restrict__ imgs, long long fram
   const KeyPoint kp = kps_in[slot];
   const int scale = scales[slot];
   const uint8_t* img = imgs + (long long)frame * frame_stride;
-  const int iw = w + 1;
-  const int32_t* integ = integral + (long long)frame * iw * (h + 1);
+  const BlockIntegral integ{reinterpret_cast<const Block4*>(integral) + (long long)frame * w * h, w};
   const int P = pat.n_points;
   int* val = s_val[warp];
 
@@ -280,7 +275,7 @@ describe_kernel(PatternDev pat, const uint8_t* __restrict__ imgs, long long fram
     if (kp.angle == -1.0f) {
       // un-rotated samples, long-pair gradient (:697-739)
       const float* pp = pat.points + ((long long)scale * 1024) * P * 3;
-      sample_pattern(pat, img, pitch, integ, iw, kp.x, kp.y, pp, scale, P, lane, val);
+      sample_pattern(pat, img, pitch, integ, kp.x, kp.y, pp, scale, P, lane, val);
       __syncwarp();
       int d0 = 0, d1 = 0;
       for (int p = lane; p < pat.n_long; p += 32) {
@@ -300,7 +295,7 @@ describe_kernel(PatternDev pat, const uint8_t* __restrict__ imgs, long long fram
   }
   // samples in the rotated pattern (:755-772)
   const float* pp = pat.points + ((long long)scale * 1024 + theta) * P * 3;
-  sample_pattern(pat, img, pitch, integ, iw, kp.x, kp.y, pp, scale, P, lane, val);
+  sample_pattern(pat, img, pitch, integ, kp.x, kp.y, pp, scale, P, lane, val);
   __syncwarp();
   // short-pair comparisons -> bits (:538-564); rows are zero-padded to desc_bytes
   uint32_t* out = reinterpret_cast<uint32_t*>(desc + slot * pat.desc_bytes);

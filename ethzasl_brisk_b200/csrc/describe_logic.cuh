@@ -23,8 +23,62 @@ BRISK_HD void sampling_constants(float sigma_half, int* scaling, int* scaling2) 
   *scaling2 = (int)((double)((float)*scaling * area) / 1024.0);
 }
 
-BRISK_HD int smoothed_intensity(const uint8_t* __restrict__ img, int pitch, const int32_t* __restrict__ integral, int iw,
-                                float kx, float ky, float px, float py, float sigma_half, int scaling, int scaling2) {
+// The twelve integral-image taps of the large-box case (:459-484) and the two weighted corner pixels of the
+// box's top row, by name (t1..t12 as in the reference).
+struct BoxTaps {
+  int t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12;
+  int p_tl, p_tr;  // I(y_top, x_left), I(y_top, x_left + dx + 1)
+};
+
+// Plain (h+1) x (w+1) int32 integral image, row stride iw = w + 1: one load per tap.
+struct PlainIntegral {
+  const int32_t* s;
+  int iw;
+  BRISK_HD void taps(const uint8_t* p /* &img(y_top, x_left) */, int y_top, int x_left, int dx, int dy, BoxTaps* o) const {
+    const int32_t* q = s + (long long)y_top * iw + x_left + 1;
+    o->t1 = q[0]; o->t2 = q[dx];
+    const int32_t* q1 = q + iw;
+    o->t3 = q1[dx]; o->t4 = q1[dx + 1]; o->t12 = q1[0]; o->t11 = q1[-1];
+    const int32_t* q2 = q1 + (long long)dy * iw;
+    o->t5 = q2[dx + 1]; o->t6 = q2[dx]; o->t9 = q2[0]; o->t10 = q2[-1];
+    const int32_t* q3 = q2 + iw;
+    o->t7 = q3[dx]; o->t8 = q3[0];
+    o->p_tl = p[0]; o->p_tr = p[dx + 1];
+  }
+};
+
+// The same integral image stored as one 2x2 block per pixel: block(Y, X) = {S(Y,X), S(Y,X+1), S(Y+1,X), S(Y+1,X+1)}
+// for Y < h, X < w (16 bytes, row stride w blocks).  The twelve taps are three corners each of the four blocks at
+// rows {y_top, y_top+dy+1} x columns {x_left, x_left+dx+1}, and a block also holds the pixel it sits on
+// (I = d - b - c + a): four 16-byte loads replace twelve 4-byte loads and two byte loads.
+struct Block4 { int a, b, c, d; };
+struct BlockIntegral {
+  const Block4* s;
+  int bw;  // blocks per row (= image width)
+  BRISK_HD static Block4 load(const Block4* p) {
+#ifdef __CUDA_ARCH__
+    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    return Block4{v.x, v.y, v.z, v.w};
+#else
+    return *p;
+#endif
+  }
+  BRISK_HD void taps(const uint8_t*, int y_top, int x_left, int dx, int dy, BoxTaps* o) const {
+    const Block4* r0 = s + (long long)y_top * bw + x_left;
+    const Block4* r1 = r0 + (long long)(dy + 1) * bw;
+    const Block4 tl = load(r0), tr = load(r0 + dx + 1), bl = load(r1), br = load(r1 + dx + 1);
+    o->t1 = tl.b; o->t11 = tl.c; o->t12 = tl.d;
+    o->t2 = tr.a; o->t3 = tr.c; o->t4 = tr.d;
+    o->t10 = bl.a; o->t9 = bl.b; o->t8 = bl.d;
+    o->t6 = br.a; o->t5 = br.b; o->t7 = br.c;
+    o->p_tl = tl.d - tl.b - tl.c + tl.a;
+    o->p_tr = tr.d - tr.b - tr.c + tr.a;
+  }
+};
+
+template <class Integral>
+BRISK_HD int smoothed_intensity_t(const uint8_t* __restrict__ img, int pitch, const Integral& integral,
+                                  float kx, float ky, float px, float py, float sigma_half, int scaling, int scaling2) {
   const float xf = px + kx, yf = py + ky;
   if ((double)sigma_half < 0.5) {
     const int x = (int)xf, y = (int)yf;
@@ -49,26 +103,20 @@ BRISK_HD int smoothed_intensity(const uint8_t* __restrict__ img, int pitch, cons
   const int r_x_1_i = (int)(r_x_1 * fs), r_y_1_i = (int)(r_y_1 * fs), r_x1_i = (int)(r_x1 * fs), r_y1_i = (int)(r_y1 * fs);
   const uint8_t* p = img + (long long)y_top * pitch + x_left;
   if (dx + dy > 2) {
+    BoxTaps t;
+    integral.taps(p, y_top, x_left, dx, dy, &t);
     // four weighted corner pixels; the reference's pointer walk (:447-456)
     // reads the bottom pair one row up and one column right of the geometric
     // corners -- reproduced.
-    int v = A * (int)p[0] + B * (int)p[dx + 1];
+    int v = A * t.p_tl + B * t.p_tr;
     const uint8_t* pc = p + (dx + 1) + (long long)dy * pitch + 1;
     v += C * (int)pc[0] + D * (int)pc[-(dx + 1)];
     // twelve integral-image taps (:459-484)
-    const int32_t* q = integral + (long long)y_top * iw + x_left + 1;
-    const int t1 = q[0], t2 = q[dx];
-    const int32_t* q1 = q + iw;
-    const int t3 = q1[dx], t4 = q1[dx + 1], t12 = q1[0], t11 = q1[-1];
-    const int32_t* q2 = q1 + (long long)dy * iw;
-    const int t5 = q2[dx + 1], t6 = q2[dx], t9 = q2[0], t10 = q2[-1];
-    const int32_t* q3 = q2 + iw;
-    const int t7 = q3[dx], t8 = q3[0];
-    const int upper = (t3 - t2 + t1 - t12) * r_y_1_i;
-    const int middle = (t6 - t3 + t12 - t9) * scaling;
-    const int left = (t9 - t12 + t11 - t10) * r_x_1_i;
-    const int right = (t5 - t4 + t3 - t6) * r_x1_i;
-    const int bottom = (t7 - t6 + t9 - t8) * r_y1_i;
+    const int upper = (t.t3 - t.t2 + t.t1 - t.t12) * r_y_1_i;
+    const int middle = (t.t6 - t.t3 + t.t12 - t.t9) * scaling;
+    const int left = (t.t9 - t.t12 + t.t11 - t.t10) * r_x_1_i;
+    const int right = (t.t5 - t.t4 + t.t3 - t.t6) * r_x1_i;
+    const int bottom = (t.t7 - t.t6 + t.t9 - t.t8) * r_y1_i;
     return (v + upper + middle + left + right + bottom) / scaling2;
   }
   // small box: weighted sum over the (dx+2) x (dy+2) window, written as the
@@ -92,6 +140,11 @@ BRISK_HD int smoothed_intensity(const uint8_t* __restrict__ img, int pitch, cons
   for (const long long e = i + dx; i < e; ++i) v += r_y1_i * (int)p[i];
   v += C * (int)p[i];
   return v / scaling2;
+}
+
+BRISK_HD int smoothed_intensity(const uint8_t* __restrict__ img, int pitch, const int32_t* __restrict__ integral, int iw,
+                                float kx, float ky, float px, float py, float sigma_half, int scaling, int scaling2) {
+  return smoothed_intensity_t(img, pitch, PlainIntegral{integral, iw}, kx, ky, px, py, sigma_half, scaling, scaling2);
 }
 
 // Rotation bin of a freshly estimated orientation (:732-739): angle in degrees

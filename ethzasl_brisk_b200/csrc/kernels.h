@@ -75,7 +75,8 @@ struct PatternDev {
   int rot_inv, scale_inv, basic_scale;
 };
 
-// `integral` holds n_frames images of (h+1) x (w+1) int32 followed by n_frames * integral_aux_elems(w, h) scratch ints.
+// `integral` holds n_frames block images (w x h blocks of four int32: {S(Y,X), S(Y,X+1), S(Y+1,X), S(Y+1,X+1)}, S = the
+// (h+1) x (w+1) integral image of the reference) followed by n_frames * integral_aux_elems(w, h) scratch ints.
 long long integral_aux_elems(int w, int h);
 cudaError_t launch_integral(const uint8_t* imgs, long long frame_stride, int pitch, int w, int h, int n_frames,
                             int32_t* integral, cudaStream_t stream);
