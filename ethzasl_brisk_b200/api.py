@@ -201,6 +201,29 @@ class BriskFeatureDetector:
         kps, counts = self.detect_batch(image, None if mask is None else mask, cap)
         return kps[0, :counts[0]].copy()
 
+    def compute_scale_batch(self, images, kps, counts, cap=65536, _allow_capacity=False):
+        """BriskFeatureDetector::ComputeScale for a batch (reference brisk-feature-detector.cc:87-92):
+        images [n,h,w] u8, kps [n,cap_in] structured, counts [n] -> (kps [n,cap], counts [n])."""
+        a, n, h, w, stride, fp = _frames(images)
+        k = np.ascontiguousarray(kps, KP_DTYPE).reshape(n, -1)
+        c = np.ascontiguousarray(counts, np.int32).reshape(n)
+        out = np.zeros((n, cap), KP_DTYPE)
+        oc = np.zeros(n, np.int32)
+        self._last_rc = self.ctx._check(self.ctx._lib.brisk_compute_scale(self.ctx._h, self._h, _ptr(a), n, w, h, C.c_size_t(stride),
+                                                          C.c_size_t(fp), _ptr(k), _ptr(c), k.shape[1], _ptr(out), _ptr(oc),
+                                                          int(cap)), allow_capacity=_allow_capacity)
+        return out, oc
+
+    def compute_scale(self, image, keypoints, cap=None):
+        """ComputeScale(image, keypoints) for one image: the provided key points (x, y, class_id are read)
+        are tested in every pyramid layer -> the key points the reference leaves in `keypoints`."""
+        k = np.ascontiguousarray(keypoints, KP_DTYPE).reshape(1, -1)
+        n_layers = max(1, 2 * self.octaves)
+        out, oc = self.compute_scale_batch(image, k, [k.shape[1]], cap or max(1, n_layers * k.shape[1]), _allow_capacity=cap is None)
+        if self._last_rc != 0:  # layers without points contributed their corners: retry with room for them
+            out, oc = self.compute_scale_batch(image, k, [k.shape[1]], max(int(oc[0]), out.shape[1]))
+        return out[0, :oc[0]].copy()
+
     def debug_corners(self, image, cap=1 << 20):
         img = np.ascontiguousarray(image, np.uint8)
         h, w = img.shape

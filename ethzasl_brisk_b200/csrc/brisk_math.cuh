@@ -119,9 +119,9 @@ BRISK_HD int fast58(const uint8_t* img, int pitch, int x, int y) {
 // Segment test of OastDetector9_16::detect with the per-pixel adaptive threshold
 // (agast/src/oast9-16.cc:86-100, ast-detector.h:62-68): T = threshold-map value,
 // b = user threshold.  Returns true when (x, y) is a corner.
-BRISK_HD bool agast_is_corner(const uint8_t* img, int pitch, int x, int y, int T, int b) {
-  if (T < (b * kLowerThreshold) / 100) return false;
-  const int t = T < kLowerThreshold ? kLowerThreshold : (T > kUpperThreshold ? kUpperThreshold : T);
+BRISK_HD bool agast_is_corner(const uint8_t* img, int pitch, int x, int y, int T, int b, int lower = kLowerThreshold) {
+  if (T < (b * lower) / 100) return false;
+  const int t = T < lower ? lower : (T > kUpperThreshold ? kUpperThreshold : T);
   const int b2 = (t * b) / 100;
   return fast916(img, pitch, x, y) >= b2;
 }

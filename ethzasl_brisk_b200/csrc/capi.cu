@@ -52,9 +52,10 @@ struct Slot {
   DevBuf pyr, cm, bm, rowcnt, layer_start, corners, fwin, checks, kp_tmp, kp_valid, integral, rounds, surv;
   DevBuf tight, kps, kps_scratch, scales, counts, desc, masks, flag;
   DevBuf h_scores, h_pts, h_keep, h_sorted, h_layer_kept, h_occ, h_surv, h_layer_surv;
-  DevBuf* all[29] = {&pyr, &cm, &bm, &rowcnt, &layer_start, &corners, &fwin, &checks, &kp_tmp, &kp_valid, &integral, &rounds, &surv,
+  DevBuf prov_base;  // ComputeScale: first key-point slot of every layer, [frame][kMaxLayers + 1]
+  DevBuf* all[30] = {&pyr, &cm, &bm, &rowcnt, &layer_start, &corners, &fwin, &checks, &kp_tmp, &kp_valid, &integral, &rounds, &surv,
                      &tight, &kps, &kps_scratch, &scales, &counts, &desc, &masks, &flag,
-                     &h_scores, &h_pts, &h_keep, &h_sorted, &h_layer_kept, &h_occ, &h_surv, &h_layer_surv};
+                     &h_scores, &h_pts, &h_keep, &h_sorted, &h_layer_kept, &h_occ, &h_surv, &h_layer_surv, &prov_base};
 };
 
 struct brisk_ctx {
@@ -738,6 +739,124 @@ int brisk_detect_describe(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* 
                           int32_t* counts, int cap, uint8_t* desc) {
   if (!ctx || !det || !ext || det->ctx != ctx || ext->ctx != ctx) return fail(ctx, BRISK_ERR_INVALID, "detector / extractor do not belong to this context");
   return run_batch(ctx, det, ext, imgs, n, w, h, stride, frame_pitch, masks, kps, counts, cap, desc);
+}
+
+int brisk_compute_scale(brisk_ctx* ctx, brisk_detector* det, const uint8_t* imgs, int n, int w, int h, size_t stride,
+                        size_t frame_pitch, const brisk_keypoint* kps_in, const int32_t* counts_in, int cap_in,
+                        brisk_keypoint* kps_out, int32_t* counts_out, int cap_out) {
+  int rc = check_image_args(ctx, imgs, n, w, h, stride, frame_pitch);
+  if (rc) return rc;
+  if (!det || det->harris) return fail(ctx, BRISK_ERR_INVALID, "ComputeScale needs a BriskFeatureDetector (AGAST) handle");
+  if (!kps_in || !counts_in || cap_in <= 0 || !kps_out || !counts_out || cap_out <= 0) return fail(ctx, BRISK_ERR_INVALID, "bad key point arguments");
+  if (det->octaves < 0 || 2 * det->octaves > kMaxLayers) return fail(ctx, BRISK_ERR_UNSUPPORTED, "octaves must be in [0, 6]");
+  if (!det->suppress && det->octaves != 0)
+    return fail(ctx, BRISK_ERR_UNSUPPORTED, "suppressScaleNonmaxima=false is only defined for octaves == 0 (the reference reads out of bounds otherwise)");
+  CU_OK(cudaSetDevice(ctx->device));
+  memset(ctx->ms, 0, sizeof(ctx->ms));
+  ctx->launches = 0;
+  if (n == 0) return BRISK_OK;
+  {
+    PyramidGeom probe;
+    build_geom(w, h, det->octaves, &probe);
+    for (int i = 0; i < probe.n_layers; ++i)
+      if (probe.L[i].w < 8 || probe.L[i].h < 8) return fail(ctx, BRISK_ERR_INVALID, "image too small: every pyramid layer must be at least 8x8");
+  }
+  const bool in_dev = is_device_ptr(kps_in), cin_dev = is_device_ptr(counts_in);
+  const bool out_dev = is_device_ptr(kps_out), cout_dev = is_device_ptr(counts_out);
+  // the largest input list sizes the per-frame scratch (one slot per layer and provided point)
+  std::vector<int32_t> h_cin(n);
+  if (cin_dev) {
+    CU_OK(cudaStreamSynchronize(ctx->stream));
+    CU_OK(cudaMemcpy(h_cin.data(), counts_in, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  } else memcpy(h_cin.data(), counts_in, (size_t)n * 4);
+  int in_max = 0;
+  for (int f = 0; f < n; ++f) {
+    if (h_cin[f] < 0 || h_cin[f] > cap_in) return fail(ctx, BRISK_ERR_INVALID, "counts_in must be in [0, cap_in]");
+    // an empty vector makes the reference detect instead (with the lower threshold of the map set to 0)
+    if (h_cin[f] == 0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "ComputeScale without key points runs the detector in the reference; use detect()");
+    in_max = std::max(in_max, h_cin[f]);
+  }
+  brisk_detector sized = *det;
+  const int n_layers = det->octaves == 0 ? 1 : 2 * det->octaves;
+  if ((long long)n_layers * in_max > (1ll << 26)) return fail(ctx, BRISK_ERR_UNSUPPORTED, "too many provided key points");
+  // one slot per layer and provided point, plus room for the corners of layers that keep no point (there the
+  // reference runs its detector): the detector's own corner capacity
+  int detect_cap = det->corner_cap;
+  if (detect_cap <= 0) detect_cap = std::min(std::max((int)(((long long)w * h) / 24), 4096), 1 << 20);
+  sized.corner_cap = n_layers * in_max + detect_cap;
+  Plan plan;
+  rc = make_plan(ctx, &sized, nullptr, n, w, h, cap_out, &plan, false, false);
+  if (rc) return rc;
+  const PyramidGeom& g = plan.g;
+  Slot& sl = ctx->slots[0];
+  const size_t c_max = (size_t)plan.chunk;
+  if (!in_dev) CU_OK(sl.kps_scratch.ensure(c_max * cap_in * 28));
+  if (!cin_dev) CU_OK(sl.scales.ensure(c_max * 4));
+  if (!out_dev) CU_OK(sl.kps.ensure(c_max * cap_out * 28));
+  if (!cout_dev) CU_OK(sl.counts.ensure(c_max * 4));
+  if (!is_device_ptr(imgs)) CU_OK(sl.tight.ensure(c_max * ((size_t)w * h + 64)));
+  CU_OK(sl.prov_base.ensure(c_max * (kMaxLayers + 1) * 4));
+  std::vector<int> h_kept(c_max * kTieStride);
+  CU_OK(cudaEventRecord(ctx->entry, ctx->stream));
+  CU_OK(cudaStreamWaitEvent(sl.stream, ctx->entry, 0));
+  bool truncated = false, empty_layer = false, corner_overflow = false;
+  const DetectWorkspace ws = slot_ws(plan, sl);
+  for (int f0 = 0; f0 < n; f0 += plan.chunk) {
+    const int c = std::min(plan.chunk, n - f0);
+    const KeyPoint* d_in = reinterpret_cast<const KeyPoint*>(kps_in) + (size_t)f0 * cap_in;
+    const int* d_cin = counts_in + f0;
+    if (!in_dev) {
+      for (int f = 0; f < c; ++f)
+        CU_OK(cudaMemcpyAsync(sl.kps_scratch.as<KeyPoint>() + (size_t)f * cap_in, kps_in + (size_t)(f0 + f) * cap_in,
+                              (size_t)h_cin[f0 + f] * 28, cudaMemcpyHostToDevice, sl.stream));
+      d_in = sl.kps_scratch.as<KeyPoint>();
+    }
+    if (!cin_dev) {
+      CU_OK(cudaMemcpyAsync(sl.scales.p, h_cin.data() + f0, (size_t)c * 4, cudaMemcpyHostToDevice, sl.stream));
+      d_cin = sl.scales.as<int>();
+    }
+    KeyPoint* d_out = out_dev ? reinterpret_cast<KeyPoint*>(kps_out) + (size_t)f0 * cap_out : sl.kps.as<KeyPoint>();
+    int* d_cout = cout_dev ? counts_out + f0 : sl.counts.as<int>();
+    CUtensorMap map;
+    int write_l0 = 0;
+    bool staged_tight = false;
+    rc = stage_input(ctx, sl, plan, imgs + (size_t)f0 * frame_pitch, c, w, h, stride, frame_pitch, &map, &write_l0, &staged_tight);
+    if (rc) return rc;
+    CU_OK(launch_pyramid(map, g, ws.pyr, c, write_l0, sl.stream));
+    CU_OK(cudaMemsetAsync(sl.flag.p, 0, 16, sl.stream));
+    // which layers keep none of their frame's points?  Those run the detector (threshold map without lower bound).
+    CU_OK(launch_provided_count(g, ws, c, d_in, d_cin, cap_in, in_max, sl.stream));
+    CU_OK(cudaMemcpyAsync(h_kept.data(), ws.n_ties, (size_t)c * kTieStride * 4, cudaMemcpyDeviceToHost, sl.stream));
+    CU_OK(cudaStreamSynchronize(sl.stream));
+    int with_fallback = 0;
+    for (int f = 0; f < c; ++f)
+      for (int l = 0; l < g.n_layers; ++l) with_fallback |= h_kept[(size_t)f * kTieStride + l] == 0;
+    if (with_fallback) {
+      CU_OK(launch_agast_detect(g, ws, c, det->thresh, sl.stream, 0));
+      CU_OK(launch_corner_lists(g, ws, c, sl.flag.as<int>(), sl.stream));
+      ctx->launches += 2 * g.n_layers + 3;
+    }
+    CU_OK(launch_provided_scale(g, ws, c, d_in, d_cin, cap_in, in_max, with_fallback, sl.prov_base.as<int>(), d_out, d_cout, cap_out,
+                                sl.flag.as<int>(), sl.stream));
+    ctx->launches += 7;
+    CU_OK(cudaMemcpyAsync(sl.h_counts, d_cout, (size_t)c * 4, cudaMemcpyDeviceToHost, sl.stream));
+    CU_OK(cudaMemcpyAsync(sl.h_counts + plan.chunk, sl.flag.p, 4, cudaMemcpyDeviceToHost, sl.stream));
+    CU_OK(cudaStreamSynchronize(sl.stream));
+    if (sl.h_counts[plan.chunk] == 3) empty_layer = true;
+    else if (sl.h_counts[plan.chunk]) corner_overflow = true;
+    if (!cout_dev) memcpy(counts_out + f0, sl.h_counts, (size_t)c * 4);
+    for (int f = 0; f < c; ++f) {
+      const int m = std::min(sl.h_counts[f], cap_out);
+      if (sl.h_counts[f] > cap_out) truncated = true;
+      if (m > 0 && !out_dev)
+        CU_OK(cudaMemcpyAsync(kps_out + (size_t)(f0 + f) * cap_out, d_out + (size_t)f * cap_out, (size_t)m * 28, cudaMemcpyDeviceToHost, sl.stream));
+    }
+    CU_OK(cudaStreamSynchronize(sl.stream));
+  }
+  if (empty_layer) return fail(ctx, BRISK_ERR_CUDA, "internal error: a layer without provided key points was not detected on");
+  if (corner_overflow) return fail(ctx, BRISK_ERR_CAPACITY, "raw corner capacity exceeded on a layer without provided key points; raise it with brisk_detector_set_corner_capacity");
+  if (truncated) return fail(ctx, BRISK_ERR_CAPACITY, "key point capacity (cap_out) exceeded; counts hold the true numbers");
+  return BRISK_OK;
 }
 
 int brisk_debug_pyramid(brisk_ctx* ctx, int octaves, const uint8_t* img, int w, int h, size_t stride, uint8_t* out,

@@ -60,6 +60,9 @@ __device__ __forceinline__ bool segment_test(const uint8_t (*s_img)[kDetSW], int
 // registers (two bits per row) and the threshold-map values go to a byte plane in shared memory; the
 // survivors (a few per cent) are queued once the walk is over, so that the row loop has no divergent path.
 // Phase 2: the queue is processed densely, one candidate per thread, with the full 9-of-16 run test.
+// LOWER: lower bound of the threshold map (BriskScaleSpace::kDefaultLowerThreshold = 10 for detection;
+// 0 for the pyramid that BriskFeatureDetector::ComputeScale builds, brisk-feature-detector.cc:90).
+template <int LOWER>
 __global__ void __launch_bounds__(kDetThreads)
 agast_detect_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restrict__ pyr, uint16_t* __restrict__ cm,
                     int* __restrict__ rowcnt, int total_rows, int row_off, int thresh) {
@@ -86,9 +89,9 @@ agast_detect_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restric
   {
     // ast-detector.h:62-68 and oast9-16.cc:86-100: no corner where T < (thresh * lower) / 100, else
     // b = (clamp(T, lower, upper) * thresh) / 100
-    const int cmp = (thresh * kLowerThreshold) / 100;
+    const int cmp = (thresh * LOWER) / 100;
     for (int T = tid; T < 256; T += kDetThreads) {
-      const int t = T < kLowerThreshold ? kLowerThreshold : (T > kUpperThreshold ? kUpperThreshold : T);
+      const int t = T < LOWER ? LOWER : (T > kUpperThreshold ? kUpperThreshold : T);
       s_b2[T] = (uint16_t)(T >= cmp ? (t * thresh) / 100 : kB2None);
     }
   }
@@ -226,13 +229,18 @@ agast_detect_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restric
   if (tid < kDetTH && s_rows[tid] && y0 + tid < L.h) atomicAdd(&rowcnt[(long long)frame * total_rows + row_off + y0 + tid], s_rows[tid]);
 }
 
-cudaError_t launch_agast_detect(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int thresh, cudaStream_t stream) {
+cudaError_t launch_agast_detect(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int thresh, cudaStream_t stream,
+                                int lower) {
+  if (lower != kLowerThreshold && lower != 0) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(ws.rowcnt, 0, sizeof(int) * (size_t)n_frames * ws.total_rows, stream);
   if (e != cudaSuccess) return e;
   for (int l = 0; l < g.n_layers; ++l) {
     const LayerGeom& L = g.L[l];
     dim3 grid((L.w + kDetTW - 1) / kDetTW, (L.h + kDetTH - 1) / kDetTH, n_frames);
-    agast_detect_kernel<<<grid, kDetThreads, 0, stream>>>(L, g.frame_elems, ws.pyr, ws.cm, ws.rowcnt, ws.total_rows, ws.row_off[l], thresh);
+    if (lower == kLowerThreshold)
+      agast_detect_kernel<kLowerThreshold><<<grid, kDetThreads, 0, stream>>>(L, g.frame_elems, ws.pyr, ws.cm, ws.rowcnt, ws.total_rows, ws.row_off[l], thresh);
+    else
+      agast_detect_kernel<0><<<grid, kDetThreads, 0, stream>>>(L, g.frame_elems, ws.pyr, ws.cm, ws.rowcnt, ws.total_rows, ws.row_off[l], thresh);
   }
   return cudaGetLastError();
 }

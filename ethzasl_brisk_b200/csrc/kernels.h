@@ -32,7 +32,9 @@ cudaError_t launch_pyramid(const CUtensorMap& src_map, const PyramidGeom& g, uin
                            cudaStream_t stream);
 
 // Threshold map + AGAST 9-16 segment test -> corner map + per-row counts.
-cudaError_t launch_agast_detect(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int thresh, cudaStream_t stream);
+// `lower`: lower bound of the threshold map, kLowerThreshold (detection) or 0 (ComputeScale's pyramid).
+cudaError_t launch_agast_detect(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int thresh, cudaStream_t stream,
+                                int lower = kLowerThreshold);
 // Row prefix sums and ordered corner lists.
 cudaError_t launch_corner_lists(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int* overflow_flag,
                                 cudaStream_t stream);
@@ -40,6 +42,18 @@ cudaError_t launch_corner_lists(const PyramidGeom& g, const DetectWorkspace& ws,
 cudaError_t launch_agast_nms(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, const uint8_t* masks,
                              long long mask_frame_stride, int mask_pitch, KeyPoint* out, int* counts, int kp_cap,
                              int* error_flag, cudaStream_t stream);
+
+// BriskFeatureDetector::ComputeScale: scale-space checks + refinement of caller-provided key points
+// (in: [frame][in_cap], in_counts[frame] <= in_max).  launch_provided_count leaves in ws.n_ties[frame][layer]
+// how many points each layer keeps; a layer that keeps none is a fallback layer (the reference detects there):
+// if any exists the caller runs launch_agast_detect(lower = 0) + launch_corner_lists and passes with_fallback = 1
+// (otherwise *error_flag is set to 3).  base: [frame][kMaxLayers + 1] scratch.  Needs ws.corner_cap >=
+// n_layers * in_max (+ the corners of the fallback layers); *error_flag = 1 when that does not hold.
+cudaError_t launch_provided_count(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, const KeyPoint* in,
+                                  const int* in_counts, int in_cap, int in_max, cudaStream_t stream);
+cudaError_t launch_provided_scale(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, const KeyPoint* in,
+                                  const int* in_counts, int in_cap, int in_max, int with_fallback, int* base, KeyPoint* out,
+                                  int* counts, int kp_cap, int* error_flag, cudaStream_t stream);
 
 // Harris scale-space detector (harris.cu).
 struct HPoint;

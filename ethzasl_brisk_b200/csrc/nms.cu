@@ -389,6 +389,151 @@ compact_kernel(PyramidGeom g, DetectWorkspace ws, const uint8_t* __restrict__ ma
   if (tid == 0) counts[frame] = s_base;  // may exceed kp_cap: caller reports truncation
 }
 
+// ---------------------------------------------------------------------------
+// BriskFeatureDetector::ComputeScale (reference brisk-feature-detector.cc:87-92): GetKeypoints with
+// caller-provided key points (brisk-scale-space.cc:104-124).  One thread per (frame, layer, provided
+// point); passes (nms_logic.cuh, "Provided key points"):
+//   0  count the points every layer keeps (n_ties[frame][layer]); a layer that keeps none is a FALLBACK
+//      layer: the reference runs its detector there (brisk-layer.cc:103-105; lower threshold 0) and
+//      treats the corners like provided points -- the caller then runs the detect kernel with lower = 0
+//      and the corner lists before going on
+//   1  the threshold-0 look-ups        2  the score write of GetAgastPoints
+//   3  scale checks + refinement into the frame's key-point scratch; layer l's slots start at
+//      base[frame][l] (in_max slots for a layer with provided points, one per corner for a fallback
+//      layer), so that compact_kernel packs them in the reference's order (layers, then input order).
+// ---------------------------------------------------------------------------
+template <int PASS>
+__global__ void __launch_bounds__(128)
+provided_kernel(PyramidGeom g, DetectWorkspace ws, const KeyPoint* __restrict__ in, const int* __restrict__ in_counts, int in_cap,
+                const int* __restrict__ base) {
+  const int frame = blockIdx.z, layer = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_in = min(in_counts[frame], in_cap);
+  int* kept = ws.n_ties + frame * kTieStride + layer;
+  const LayerView L = make_view(g, ws, frame, layer);
+  float px = 0.0f, py = 0.0f;
+  KeyPoint kin;
+  bool inside = false;
+  if (j < n_in) {
+    kin = in[(long long)frame * in_cap + j];
+    inside = provided_to_layer(L, kin.x, kin.y, &px, &py);
+  }
+  if (PASS == 0) {
+    const unsigned m = __ballot_sync(0xffffffffu, inside);
+    if (m && (threadIdx.x & 31) == 0) atomicAdd(kept, __popc(m));
+    return;
+  }
+  if (!inside) return;
+  if (PASS == 1) provided_touch(L, px, py);
+  else if (PASS == 2) provided_stamp(L, px, py);
+  else {
+    const LayerView below = make_view(g, ws, frame, layer > 0 ? layer - 1 : 0);
+    const LayerView above = make_view(g, ws, frame, layer + 1 < g.n_layers ? layer + 1 : layer);
+    KeyPoint kp;
+    kp.class_id = kin.class_id;
+    if (provided_refine(below, L, above, g.n_layers, layer, px, py, &kp)) {
+      const long long slot = (long long)frame * ws.corner_cap + base[frame * (kMaxLayers + 1) + layer] + j;
+      ws.kp_tmp[slot] = kp;
+      ws.kp_valid[slot] = 1;
+    }
+  }
+}
+
+// One thread per frame: first slot of every layer (and the total, which compact_kernel reads).
+__global__ void provided_layout_kernel(PyramidGeom g, DetectWorkspace ws, int n_frames, int in_max, int with_fallback,
+                                       int* __restrict__ base, int* __restrict__ error_flag) {
+  const int frame = blockIdx.x * blockDim.x + threadIdx.x;
+  if (frame >= n_frames) return;
+  const int* ls = ws.layer_start + (long long)frame * (kMaxLayers + 1);
+  int total = 0;
+  for (int l = 0; l < g.n_layers; ++l) {
+    base[frame * (kMaxLayers + 1) + l] = total;
+    if (ws.n_ties[frame * kTieStride + l] > 0) total += in_max;
+    else if (with_fallback) total += ls[l + 1] - ls[l];
+    else atomicExch(error_flag, 3);
+  }
+  base[frame * (kMaxLayers + 1) + g.n_layers] = total;
+  if (total > ws.corner_cap || (with_fallback && ls[g.n_layers] > ws.corner_cap)) atomicExch(error_flag, 1);
+}
+
+// After the detect kernel ran on every layer: layers with provided points start from an empty score cache;
+// on fallback layers a corner whose score is <= 2 does not stay cached (brisk-layer.cc:124-126) -- its entry
+// goes, its place in the corner list stays.
+__global__ void __launch_bounds__(256)
+provided_clear_kernel(PyramidGeom g, DetectWorkspace ws) {
+  const int frame = blockIdx.z, layer = blockIdx.y;
+  const LayerGeom& G = g.L[layer];
+  uint16_t* cm = ws.cm + (long long)frame * g.frame_elems + G.off;
+  const bool fallback = ws.n_ties[frame * kTieStride + layer] == 0;
+  const long long n = (long long)G.pitch * G.h;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const uint16_t v = cm[i];
+    if (v && (!fallback || (v & kCmT) <= 2)) cm[i] = 0;
+  }
+}
+
+// Fallback layers: one thread per detected corner.
+__global__ void __launch_bounds__(128)
+provided_corner_kernel(PyramidGeom g, DetectWorkspace ws, const int* __restrict__ base) {
+  const int frame = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int* ls = ws.layer_start + (long long)frame * (kMaxLayers + 1);
+  if (k >= min(ls[g.n_layers], ws.corner_cap)) return;
+  int x, y, layer;
+  unpack_corner(ws.corners[(long long)frame * ws.corner_cap + k], &x, &y, &layer);
+  if (ws.n_ties[frame * kTieStride + layer] > 0) return;
+  const LayerView L = make_view(g, ws, frame, layer);
+  const LayerView below = make_view(g, ws, frame, layer > 0 ? layer - 1 : 0);
+  const LayerView above = make_view(g, ws, frame, layer + 1 < g.n_layers ? layer + 1 : layer);
+  KeyPoint kp;
+  kp.class_id = -1;
+  if (provided_refine(below, L, above, g.n_layers, layer, (float)x, (float)y, &kp)) {
+    const long long slot = (long long)frame * ws.corner_cap + base[frame * (kMaxLayers + 1) + layer] + (k - ls[layer]);
+    if (slot < (long long)(frame + 1) * ws.corner_cap) {
+      ws.kp_tmp[slot] = kp;
+      ws.kp_valid[slot] = 1;
+    }
+  }
+}
+
+cudaError_t launch_provided_count(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, const KeyPoint* in,
+                                  const int* in_counts, int in_cap, int in_max, cudaStream_t stream) {
+  if (in_max <= 0) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(ws.n_ties, 0, (size_t)n_frames * kTieStride * sizeof(int), stream);
+  if (e != cudaSuccess) return e;
+  dim3 grid((in_max + 127) / 128, g.n_layers, n_frames);
+  provided_kernel<0><<<grid, 128, 0, stream>>>(g, ws, in, in_counts, in_cap, nullptr);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_provided_scale(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, const KeyPoint* in,
+                                  const int* in_counts, int in_cap, int in_max, int with_fallback, int* base, KeyPoint* out,
+                                  int* counts, int kp_cap, int* error_flag, cudaStream_t stream) {
+  if (in_max <= 0) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(ws.kp_valid, 0, (size_t)n_frames * ws.corner_cap, stream);
+  if (e != cudaSuccess) return e;
+  if (with_fallback) {
+    dim3 cgrid(64, g.n_layers, n_frames);
+    provided_clear_kernel<<<cgrid, 256, 0, stream>>>(g, ws);
+  } else {
+    e = cudaMemsetAsync(ws.cm, 0, (size_t)n_frames * g.frame_elems * sizeof(uint16_t), stream);
+    if (e != cudaSuccess) return e;
+  }
+  provided_layout_kernel<<<(n_frames + 127) / 128, 128, 0, stream>>>(g, ws, n_frames, in_max, with_fallback, base, error_flag);
+  dim3 grid((in_max + 127) / 128, g.n_layers, n_frames);
+  provided_kernel<1><<<grid, 128, 0, stream>>>(g, ws, in, in_counts, in_cap, base);
+  provided_kernel<2><<<grid, 128, 0, stream>>>(g, ws, in, in_counts, in_cap, base);
+  provided_kernel<3><<<grid, 128, 0, stream>>>(g, ws, in, in_counts, in_cap, base);
+  if (with_fallback) {
+    dim3 kgrid((ws.corner_cap + 127) / 128, n_frames);
+    provided_corner_kernel<<<kgrid, 128, 0, stream>>>(g, ws, base);
+  }
+  DetectWorkspace cw = ws;
+  cw.layer_start = base;  // compact_kernel packs the first base[frame][n_layers] slots
+  compact_kernel<<<n_frames, 256, 0, stream>>>(g, cw, nullptr, 0, 0, out, counts, kp_cap);
+  return cudaGetLastError();
+}
+
 // Debug: dense FAST 9-16 / 5-8 score planes of layer 0 (threshold 1, border rules
 // of brisk-layer.cc:118-145), for parity tests of the closed-form score.
 __global__ void __launch_bounds__(256)

@@ -413,9 +413,11 @@ struct CheckResult {
 // Returns true when Refine3D (mid layers) / the last-layer branch of
 // GetKeypoints reaches its own-layer 3x3 patch.
 // `below` / `above` are the neighbouring layers (ignored where the corner's layer has none).
+// `center_in` < 0: the corner's own score is its corner-map entry (detection mode); otherwise the caller
+// passes GetAgastScore(x, y, 1) of a point that need not be a corner (provided-key-point mode).
 BRISK_HD bool nms_checks3(const LayerView& below, const LayerView& L, const LayerView& above, int n_layers, int layer, int x,
-                          int y, CheckResult* r, int* tile_violations = nullptr) {
-  const int center = L.cm[(long long)y * L.pitch + x] & kCmT;
+                          int y, CheckResult* r, int* tile_violations = nullptr, int center_in = -1) {
+  const int center = center_in >= 0 ? center_in : (L.cm[(long long)y * L.pitch + x] & kCmT);
   r->max_above = 0; r->dxa = 0; r->dya = 0; r->max_below = 0; r->dxb = 0; r->dyb = 0;
   r->above_steps = 0; r->above_argmax = 0;
   if (n_layers == 1) return true;
@@ -672,6 +674,104 @@ BRISK_HD bool refine_emit1(const LayerView& L, int n_layers, int layer, int x, i
 BRISK_HD bool refine_emit(const LayerView* layers, int n_layers, int layer, int x, int y, const CheckResult& r,
                           KeyPoint* kp) {
   return refine_emit1(layers[layer], n_layers, layer, x, y, r, kp);
+}
+
+// ---------------------------------------------------------------------------
+// "Provided key points" mode: BriskFeatureDetector::ComputeScale (reference
+// brisk-feature-detector.cc:87-92), i.e. BriskScaleSpace::GetKeypoints with a
+// non-empty key-point vector (brisk-scale-space.cc:104-124) on a pyramid whose
+// lower threshold is 0.  No detector runs and IsMax2D is skipped; what is left
+// of the lazy score cache is again a pure function once three things are known
+// per pixel q of a layer (all of it happens before the first refinement):
+//   * q is one of the four bilinear neighbours of a provided point: it was
+//     scored with threshold 0, and a pixel that is no corner at b = 0 then holds
+//     cornerScore = -1 stored as the byte 255 -- sticky (brisk-layer.cc:124-130);
+//   * q is the flat offset int(x + y * cols) of a provided point (float
+//     arithmetic, brisk-layer.cc:110-116): it holds the threshold-map value T,
+//     sticky when T > 2 (and T >= F, so otherwise nothing sticks there);
+//   * else the usual F >= 1 ? F : 0.
+// The corner map carries these as its T byte (255 / T / 0), so score1() serves
+// every look-up unchanged.
+// ---------------------------------------------------------------------------
+
+// Layer coordinates of a provided key point and the border test of :110-121.
+BRISK_HD bool provided_to_layer(const LayerView& L, float kx, float ky, float* px, float* py) {
+  const float x = kx / L.scale - L.offset, y = ky / L.scale - L.offset;
+  *px = x; *py = y;
+  return !(x < 3 || y < 3 || x > (float)(L.w - 3) || y > (float)(L.h - 3));
+}
+
+// Pass 1 (any order, idempotent): the threshold-0 look-ups of GetAgastScore(x, y, 0) (:119).
+BRISK_HD void provided_touch(const LayerView& L, float px, float py) {
+  const int x = (int)px, y = (int)py;
+  for (int k = 0; k < 4; ++k) {
+    const int qx = x + (k & 1), qy = y + (k >> 1);
+    if (in_border(L, qx, qy)) continue;
+    if (fast916(L.img, L.pitch, qx, qy) < 0) L.cm[(long long)qy * L.pitch + qx] = 255;
+  }
+}
+
+// Pass 2 (after pass 1 of every point of the layer; idempotent): the score write of GetAgastPoints.
+BRISK_HD void provided_stamp(const LayerView& L, float px, float py) {
+  const int offs = (int)(px + py * (float)L.w);
+  const int qx = offs % L.w, qy = offs / L.w;
+  if (in_border(L, qx, qy)) return;  // never read back (GetAgastScore's border test comes first)
+  const int T = thrmap_px(L.img, L.pitch, qx, qy);
+  L.cm[(long long)qy * L.pitch + qx] = (uint16_t)(T > 2 ? T : 0);
+}
+
+// BriskLayer::GetAgastScore(float, float, 1) without a tile.
+BRISK_HD int score1_f(const LayerView& L, float xf, float yf) {
+  const int x = (int)xf;
+  const float rx1 = xf - (float)x;
+  const float rx = 1.0f - rx1;
+  const int y = (int)yf;
+  const float ry1 = yf - (float)y;
+  const float ry = 1.0f - ry1;
+  const int s00 = score1(L, x, y), s10 = score1(L, x + 1, y), s01 = score1(L, x, y + 1), s11 = score1(L, x + 1, y + 1);
+  const float v = ((((rx * ry) * (float)s00 + (rx1 * ry) * (float)s10) + (rx * ry1) * (float)s01) + (rx1 * ry1) * (float)s11);
+  return (int)(uint8_t)v;
+}
+
+// The 3x3 patch of :184-195 / :232-243 read at float positions.
+BRISK_HD float patch3x3_f(const LayerView& L, float x, float y, float* dx, float* dy) {
+  int s[9];  // s[3 * column + row]
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int k = 0; k < 9; ++k) s[k] = score1_f(L, x + (float)(k / 3 - 1), y + (float)(k % 3 - 1));
+  return subpixel2d(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], dx, dy);
+}
+
+// Pass 3 (pure): one provided point of one layer -> at most one key point (:172-285 with
+// perform_2d_nonMax = false).  class_id is the caller's (the reference copies the input key point).
+BRISK_HD bool provided_refine(const LayerView& below, const LayerView& L, const LayerView& above, int n_layers, int layer,
+                              float px, float py, KeyPoint* kp, int* tile_violations = nullptr) {
+  kp->angle = -1.0f; kp->octave = layer;
+  if (n_layers == 1) {
+    float dx, dy;
+    const float m = patch3x3_f(L, px, py, &dx, &dy);
+    kp->x = px + dx; kp->y = py + dy; kp->size = 12.0f; kp->response = m; kp->octave = 0;
+    return true;
+  }
+  const int x = (int)px, y = (int)py;
+  if (layer == n_layers - 1) {
+    bool ismax;
+    float dx = 0.0f, dy = 0.0f;
+    AboveFootprint fp;
+    score_max_side(true, below, layer, x, y, score1_f(L, px, py), &ismax, &dx, &dy, &fp, tile_violations);
+    if (!ismax) return false;
+    const float m = patch3x3_f(L, px, py, &dx, &dy);
+    kp->x = (px + dx) * L.scale + L.offset; kp->y = (py + dy) * L.scale + L.offset;
+    kp->size = 12.0f * L.scale; kp->response = m;
+    return true;
+  }
+  CheckResult r;
+  if (!nms_checks3(below, L, above, n_layers, layer, x, y, &r, tile_violations, score1(L, x, y))) return false;
+  const int class_id = kp->class_id;
+  const bool ok = refine_emit1(L, n_layers, layer, x, y, r, kp);
+  kp->class_id = class_id;
+  return ok;
 }
 
 }  // namespace briskb200

@@ -61,6 +61,30 @@ class BriskFeatureDetector {
   void detect(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, const agast::Mat& mask = agast::Mat()) const {
     detectImpl(image, keypoints, mask);
   }
+  // brisk-feature-detector.cc:87-92: re-examines the passed key points in every pyramid layer and replaces
+  // them by the key points the scale-space checks accept (one per accepting layer; octave = layer index).
+  // A layer that keeps none of the points is detected on instead, as in the reference (brisk-layer.cc:103-105).
+  // With an empty vector the reference detects on every layer (threshold map without lower bound): that case
+  // is reported as std::runtime_error here -- call detect().
+  void ComputeScale(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints) const {
+    brisk_ctx* ctx = detail::context();
+    ensure(ctx);
+    const int32_t n_in = (int32_t)keypoints.size();
+    const int n_layers = octaves == 0 ? 1 : 2 * octaves;
+    std::vector<agast::KeyPoint> out((size_t)std::max(1, n_layers * n_in));
+    for (;;) {
+      int32_t count = 0;
+      const int rc = brisk_compute_scale(ctx, det_, image.data, 1, image.cols, image.rows, image.step, image.step * image.rows,
+                                         reinterpret_cast<const brisk_keypoint*>(keypoints.data()), &n_in, std::max(1, n_in),
+                                         reinterpret_cast<brisk_keypoint*>(out.data()), &count, (int)out.size());
+      // layers without points contribute their corners: grow and retry
+      if (rc == BRISK_ERR_CAPACITY && count > (int)out.size()) { out.resize(count); continue; }
+      detail::check(ctx, rc);
+      out.resize(count);
+      keypoints.swap(out);
+      return;
+    }
+  }
   // raw-corner capacity per frame (B200 specific; default scales with the image area)
   void setCornerCapacity(int n) { corner_cap_ = n; if (det_) brisk_detector_set_corner_capacity(det_, n); }
 

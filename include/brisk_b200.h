@@ -104,6 +104,19 @@ int brisk_extractor_pattern(const brisk_extractor* ext, int32_t counts[4], float
 int brisk_detect(brisk_ctx* ctx, brisk_detector* det, const uint8_t* imgs, int n, int w, int h, size_t stride,
                  size_t frame_pitch, const uint8_t* masks, brisk_keypoint* kps, int32_t* counts, int cap);
 
+/* ComputeScale(): BriskFeatureDetector::ComputeScale -- reference brisk/src/brisk-feature-detector.cc:87-92, i.e.
+ * BriskScaleSpace::GetKeypoints with caller-provided key points (brisk/src/brisk-scale-space.cc:104-124): every
+ * provided point is mapped into every pyramid layer, goes through the scale-space checks there (no 2-D
+ * non-maximum test) and yields one key point per layer that accepts it (x, y, size, response refined; octave =
+ * layer; class_id copied).  A layer that keeps none of a frame's points (they must fall inside its 3-pixel
+ * border after x / scale - offset) is detected on instead, with the threshold map's lower bound at 0, and its
+ * corners go through the same checks (brisk/src/brisk-layer.cc:103-105).  kps_in: [n][cap_in], counts_in: [n]
+ * (>= 1 each; with an empty vector the reference detects on all layers -- use brisk_detect); kps_out:
+ * [n][cap_out], counts_out: [n] (true count; > cap_out means truncated and BRISK_ERR_CAPACITY). */
+int brisk_compute_scale(brisk_ctx* ctx, brisk_detector* det, const uint8_t* imgs, int n, int w, int h, size_t stride,
+                        size_t frame_pitch, const brisk_keypoint* kps_in, const int32_t* counts_in, int cap_in,
+                        brisk_keypoint* kps_out, int32_t* counts_out, int cap_out);
+
 /* compute(): BriskDescriptorExtractor::computeImpl -- reference
  * brisk/src/brisk-descriptor-extractor.cc:589-599,612-778.  kps/counts are in/out: key points too
  * close to the border are removed (order kept), `angle` is written.  desc: [n][cap][descriptor_size]. */

@@ -211,8 +211,12 @@ struct Layer {
     if (x < 3 || y < 3 || x >= w - 3 || y >= h - 3) return 0;
     uint8_t& s = scores[(size_t)y * w + x];
     if (s > 2) return s;
+    // the byte is assigned first and compared afterwards (:128-130): with threshold 0 (only asked by the
+    // "provided key points" mode, brisk-scale-space.cc:119) a pixel that is no corner at b = 0 scores
+    // cornerScore = -1, is stored as 255 and stays cached
     const int v = std::max(threshold - 1, Fast916(img.data(), w, x, y));
-    s = (uint8_t)(v < threshold ? 0 : v);
+    s = (uint8_t)v;
+    if (s < threshold) s = 0;
     return s;
   }
   // reference brisk-layer.cc:134-145: uncached 5-8 score, border 2.
@@ -572,8 +576,71 @@ struct ScaleSpace {
     return max;
   }
 
-  // reference brisk-scale-space.cc:92-287 (GetKeypoints; detection mode only:
-  // the "provided keypoints" mode is out of scope).
+  // reference brisk-scale-space.cc:92-287 with a non-empty key-point vector ("provided key points",
+  // :104-124; reached through BriskFeatureDetector::ComputeScale, brisk-feature-detector.cc:87-92, which
+  // builds the pyramid with lower threshold 0).  Per layer the points are mapped into layer coordinates and
+  // kept when inside the 3-pixel border; their four bilinear neighbours are scored with threshold 0; the
+  // layer's detector only runs when no point was kept (brisk-layer.cc:103-105); every point then gets the
+  // score cornerScore(b = thrmap) written at the flat offset int(x + y * cols) -- evaluated in float, so a
+  // fractional y lands on some other column (brisk-layer.cc:110-116).  No 2-D non-maximum test afterwards.
+  void GetKeypointsProvided(const orc_keypoint* in, int n_in, std::vector<orc_keypoint>* out) {
+    const int n = (int)L.size();
+    struct P { float x, y; int class_id; };
+    std::vector<std::vector<P>> pts(n);
+    for (int i = 0; i < n; ++i) {
+      Layer& l = L[i];
+      for (int k = 0; k < n_in; ++k) {
+        const float x = in[k].x / l.scale - l.offset, y = in[k].y / l.scale - l.offset;
+        if (x < 3 || y < 3 || x > l.w - 3 || y > l.h - 3) continue;
+        l.ScoreF(x, y, 0);
+        pts[i].push_back(P{x, y, in[k].class_id});
+      }
+      if (pts[i].empty()) {
+        std::vector<Corner> c;
+        DetectCorners(l.img.data(), l.thr.data(), l.w, l.h, threshold, 0, 230, &c);
+        for (const Corner& q : c) pts[i].push_back(P{(float)q.x, (float)q.y, -1});
+      }
+      for (const P& p : pts[i]) {
+        const int offs = (int)(p.x + p.y * (float)l.w);
+        const int qx = offs % l.w, qy = offs / l.w;
+        // cornerScore(b = thrmap) = max(thrmap, F) = thrmap wherever the ring is inside the image; border
+        // pixels (where the reference reads its ring across row ends) are never read back (Score())
+        if (qx >= 3 && qy >= 3 && qx < l.w - 3 && qy < l.h - 3) l.scores[(size_t)offs] = l.thr[(size_t)offs];
+      }
+    }
+    out->clear();
+    auto emit = [&](float x, float y, float size, float response, int octave, int class_id) {
+      out->push_back(orc_keypoint{x, y, size, -1.0f, response, octave, class_id});
+    };
+    if (n == 1) {  // :172-209, and :131-170 when scale non-maxima are kept (same arithmetic for one layer)
+      for (const P& p : pts[0]) {
+        float dx, dy;
+        const float max = Patch3x3F(L[0], p.x, p.y, &dx, &dy);
+        emit(p.x + dx, p.y + dy, 12.0f, max, 0, p.class_id);
+      }
+      return;
+    }
+    for (int i = 0; i < n; ++i) {
+      Layer& l = L[i];
+      for (const P& p : pts[i]) {
+        if (i == n - 1) {  // :215-256
+          bool ismax; float dx, dy;
+          ScoreMaxBelow(i, (int)p.x, (int)p.y, l.ScoreF(p.x, p.y, 1), &ismax, &dx, &dy);
+          if (!ismax) continue;
+          float ddx, ddy;
+          const float max = Patch3x3F(l, p.x, p.y, &ddx, &ddy);
+          emit((p.x + ddx) * l.scale + l.offset, (p.y + ddy) * l.scale + l.offset, 12.0f * l.scale, max, i, p.class_id);
+        } else {  // :257-285
+          bool ismax; float x, y, scale;
+          const float score = Refine3D(i, (int)p.x, (int)p.y, &x, &y, &scale, &ismax);
+          if (!ismax) continue;
+          emit(x, y, 12.0f * scale, score, i, p.class_id);
+        }
+      }
+    }
+  }
+
+  // reference brisk-scale-space.cc:92-287 (GetKeypoints, detection mode).
   void GetKeypoints(std::vector<orc_keypoint>* out) {
     const int n = (int)L.size();
     std::vector<std::vector<Corner>> pts(n);
@@ -1213,6 +1280,21 @@ int orc_agast_detect(const uint8_t* img, int w, int h, int thresh, int octaves, 
     ++total;
   }
   return total;
+}
+
+// reference brisk-feature-detector.cc:87-92 (BriskFeatureDetector::ComputeScale) with a non-empty key-point
+// vector.  suppress = 0 is only defined for one layer (as in orc_agast_detect).
+int orc_compute_scale(const uint8_t* img, int w, int h, int thresh, int octaves, int suppress, const orc_keypoint* in,
+                      int n_in, orc_keypoint* out, int cap) {
+  if (n_in <= 0) return -1;
+  if (!suppress && octaves != 0) return -1;
+  ScaleSpace ss;
+  ss.suppress = suppress != 0;
+  ss.Construct(img, w, h, octaves, thresh);
+  std::vector<orc_keypoint> kps;
+  ss.GetKeypointsProvided(in, n_in, &kps);
+  for (size_t i = 0; i < kps.size() && (int)i < cap; ++i) out[i] = kps[i];
+  return (int)kps.size();
 }
 
 // debug aid: final lazy-cache state of all layers, concatenated.

@@ -35,6 +35,9 @@ int orc_pyramid(const uint8_t* img, int w, int h, int octaves, uint8_t* out, int
 /* brisk-feature-detector.cc:77-85 (BriskFeatureDetector::detectImpl) */
 int orc_agast_detect(const uint8_t* img, int w, int h, int thresh, int octaves, int suppress,
                      const uint8_t* mask, orc_keypoint* out, int cap);
+/* brisk-feature-detector.cc:87-92 (ComputeScale) = brisk-scale-space.cc:92-287 with provided key points */
+int orc_compute_scale(const uint8_t* img, int w, int h, int thresh, int octaves, int suppress, const orc_keypoint* in,
+                      int n_in, orc_keypoint* out, int cap);
 /* debug aid: final lazy score cache of every layer (brisk-layer.cc:118-132) */
 int orc_agast_cache_dump(const uint8_t* img, int w, int h, int thresh, int octaves, uint8_t* out);
 /* integral-image.h:56-161 */

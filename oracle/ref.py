@@ -98,6 +98,16 @@ def agast_detect(img, thresh, octaves=3, suppress=True, mask=None, cap=1 << 18):
     return kps[:n].copy()
 
 
+def compute_scale(img, kps, thresh, octaves=3, suppress=True, cap=1 << 18):
+    """BriskFeatureDetector(thresh, octaves, suppress).ComputeScale(img, kps) -> key points"""
+    img, w, h = _img(img)
+    k = np.ascontiguousarray(kps, KP_DTYPE)
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().ref_compute_scale(_p(img), w, h, int(thresh), int(octaves), int(bool(suppress)), _p(k), len(k), _p(out), cap)
+    assert n <= cap
+    return out[:n].copy()
+
+
 def harris_detect(img, octaves, radius, abs_thr=0.0, max_kpt=-1, cap=1 << 18):
     img, w, h = _img(img)
     kps = np.zeros(cap, KP_DTYPE)

@@ -226,6 +226,18 @@ int ref_agast_detect(const uint8_t* img, int w, int h, int thresh, int octaves, 
   return FromVec(kps, out, cap);
 }
 
+// brisk::BriskFeatureDetector(thresh, octaves, suppress).ComputeScale(image, keypoints): the
+// "provided key points" mode of BriskScaleSpace::GetKeypoints (brisk-scale-space.cc:104-124).
+int ref_compute_scale(const uint8_t* img, int w, int h, int thresh, int octaves, int suppress,
+                      const RefKeyPoint* in, int n_in, RefKeyPoint* out, int cap) {
+  cv::Mat m = WrapCopy(img, w, h);
+  brisk::BriskFeatureDetector det(thresh, octaves, suppress != 0);
+  std::vector<cv::KeyPoint> kps;
+  ToVec(in, n_in, &kps);
+  det.ComputeScale(m, kps);
+  return FromVec(kps, out, cap);
+}
+
 // ScaleSpaceFeatureDetector<HarrisScoreCalculator>(octaves, radius, absThr, maxKpt)
 int ref_harris_detect(const uint8_t* img, int w, int h, int octaves, double radius, double abs_thr,
                       int64_t max_kpt, RefKeyPoint* out, int cap) {

@@ -41,7 +41,13 @@ int main(int argc, char** argv) {
   o.write(reinterpret_cast<char*>(&hn), 4);
   o.write(reinterpret_cast<char*>(hk.data()), (std::streamsize)hn * sizeof(agast::KeyPoint));
   o.write(reinterpret_cast<char*>(hd.data), (std::streamsize)hn * hd.cols);
-  std::printf("%d key points, %d-byte descriptors, %d self matches\n", n, nb, self);
+  // ComputeScale: the detected key points re-examined in every layer (reference brisk-feature-detector.cc:87-92)
+  std::vector<agast::KeyPoint> cs(kps);
+  detector.ComputeScale(img, cs);
+  int cn = (int)cs.size();
+  o.write(reinterpret_cast<char*>(&cn), 4);
+  o.write(reinterpret_cast<char*>(cs.data()), (std::streamsize)cn * sizeof(agast::KeyPoint));
+  std::printf("%d key points, %d-byte descriptors, %d self matches, %d from ComputeScale\n", n, nb, self, cn);
   if (argc > 3) {
     // matcher surface: a two-image train collection with masks, knnMatch(k = 3) and radiusMatch(45)
     const int nq = std::min(n, 150), n0 = n / 3;

@@ -25,7 +25,9 @@ struct HostLayer {
 };
 }  // namespace
 
-extern "C" int emul_agast_detect_ex(const uint8_t* image, int w, int h, int thresh, int octaves, KeyPoint* out, int cap, uint16_t* cm_out, uint8_t* bm_out) {
+namespace {
+// pyramid as the pyramid kernel builds it (brisk_math.cuh sampling formulas)
+std::vector<HostLayer> build_layers(const uint8_t* image, int w, int h, int octaves) {
   const int n = octaves == 0 ? 1 : 2 * octaves;
   std::vector<HostLayer> H(n);
   auto alloc = [](HostLayer& l, int w_, int h_) {
@@ -60,6 +62,13 @@ extern "C" int emul_agast_detect_ex(const uint8_t* image, int w, int h, int thre
     }
     d.offset = (float)(0.5 * d.scale - 0.5);
   }
+  return H;
+}
+}  // namespace
+
+extern "C" int emul_agast_detect_ex(const uint8_t* image, int w, int h, int thresh, int octaves, KeyPoint* out, int cap, uint16_t* cm_out, uint8_t* bm_out) {
+  const int n = octaves == 0 ? 1 : 2 * octaves;
+  std::vector<HostLayer> H = build_layers(image, w, h, octaves);
   std::vector<LayerView> V(n);
   for (int i = 0; i < n; ++i) {
     HostLayer& l = H[i];
@@ -147,4 +156,71 @@ extern "C" int emul_agast_detect_ex(const uint8_t* image, int w, int h, int thre
 
 extern "C" int emul_agast_detect(const uint8_t* image, int w, int h, int thresh, int octaves, KeyPoint* out, int cap) {
   return emul_agast_detect_ex(image, w, h, thresh, octaves, out, cap, nullptr, nullptr);
+}
+
+// BriskFeatureDetector::ComputeScale (provided key points): the passes of the GPU path (nms.cu, provided_*)
+// run serially.  A layer that keeps no point is detected on with the threshold map's lower bound at 0.
+extern "C" int emul_compute_scale(const uint8_t* image, int w, int h, int thresh, int octaves, const KeyPoint* in, int n_in, KeyPoint* out, int cap) {
+  const int n = octaves == 0 ? 1 : 2 * octaves;
+  std::vector<HostLayer> H = build_layers(image, w, h, octaves);
+  std::vector<LayerView> V(n);
+  for (int i = 0; i < n; ++i) V[i] = LayerView{H[i].img.data(), H[i].cm.data(), H[i].bm.data(), H[i].w, H[i].h, H[i].pitch, H[i].scale, H[i].offset};
+  // pass 0: points kept per layer
+  std::vector<int> kept(n, 0);
+  bool fallback = false;
+  for (int i = 0; i < n; ++i) {
+    for (int k = 0; k < n_in; ++k) {
+      float px, py;
+      kept[i] += provided_to_layer(V[i], in[k].x, in[k].y, &px, &py);
+    }
+    fallback |= kept[i] == 0;
+  }
+  if (fallback) {
+    // detect kernel (lower = 0) on every layer, then provided_clear_kernel
+    for (int i = 0; i < n; ++i) {
+      HostLayer& l = H[i];
+      for (int y = 3; y < l.h - 3; ++y)
+        for (int x = 3; x < l.w - 3; ++x) {
+          const int T = thrmap_px(l.img.data(), l.pitch, x, y);
+          if (agast_is_corner(l.img.data(), l.pitch, x, y, T, thresh, 0)) {
+            l.cm[(size_t)y * l.pitch + x] = (uint16_t)T;
+            l.cx.push_back(x); l.cy.push_back(y);
+          }
+        }
+      for (auto& v : l.cm)
+        if (v && (kept[i] > 0 || (v & kCmT) <= 2)) v = 0;
+    }
+  }
+  for (int pass = 1; pass <= 2; ++pass)
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < n_in; ++k) {
+        float px, py;
+        if (!provided_to_layer(V[i], in[k].x, in[k].y, &px, &py)) continue;
+        if (pass == 1) provided_touch(V[i], px, py); else provided_stamp(V[i], px, py);
+      }
+  int total = 0, violations = 0;
+  for (int i = 0; i < n; ++i) {
+    const LayerView &below = V[i > 0 ? i - 1 : 0], &above = V[i + 1 < n ? i + 1 : i];
+    if (kept[i] > 0) {
+      for (int k = 0; k < n_in; ++k) {
+        float px, py;
+        if (!provided_to_layer(V[i], in[k].x, in[k].y, &px, &py)) continue;
+        KeyPoint kp;
+        kp.class_id = in[k].class_id;
+        if (!provided_refine(below, V[i], above, n, i, px, py, &kp, &violations)) continue;
+        if (total < cap) out[total] = kp;
+        ++total;
+      }
+    } else {
+      for (size_t k = 0; k < H[i].cx.size(); ++k) {
+        KeyPoint kp;
+        kp.class_id = -1;
+        if (!provided_refine(below, V[i], above, n, i, (float)H[i].cx[k], (float)H[i].cy[k], &kp, &violations)) continue;
+        if (total < cap) out[total] = kp;
+        ++total;
+      }
+    }
+  }
+  if (violations) return -200;  // a scan looked outside its score tile
+  return total;
 }

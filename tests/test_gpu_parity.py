@@ -91,6 +91,69 @@ def test_detect_without_scale_suppression_single_layer(ctx, oracle, ref, golden)
             assert kp_equal(got, ref.agast_detect(img, 55, 0, False))
 
 
+@pytest.mark.parametrize("thresh,octaves", [(60, 4), (70, 3), (40, 2), (70, 0), (60, 1), (30, 5)])
+def test_compute_scale_bit_exact(ctx, oracle, golden, thresh, octaves):
+    # BriskFeatureDetector::ComputeScale (provided key points, brisk-scale-space.cc:104-124)
+    from test_oracle_golden import _provided_points
+    det = bb.BriskFeatureDetector(thresh, octaves, ctx=ctx)
+    for img in (golden["image0"], bb.synthetic_frame(752, 480, 1000), bb.synthetic_frame(500, 333, 3)):
+        for k in (oracle.agast_detect(img, max(thresh, 40), min(octaves, 4)), _provided_points(img, 2000, 21),
+                  _provided_points(img, 500, 22, True)):
+            got = det.compute_scale(img, k)
+            assert len(got) > 5 and kp_equal(got, oracle.compute_scale(img, k, thresh, octaves))
+
+
+@pytest.mark.parametrize("thresh,octaves", [(60, 3), (30, 5), (12, 3), (70, 0)])
+def test_compute_scale_layers_without_points(ctx, oracle, golden, thresh, octaves):
+    # a layer that keeps none of the points is detected on (threshold map without lower bound, brisk-layer.cc:103-105)
+    # and its corners go through the scale checks like provided points; mixed with provided layers in one frame
+    from test_oracle_golden import _provided_points
+    det = bb.BriskFeatureDetector(thresh, octaves, ctx=ctx)
+    det.set_corner_capacity(300000)
+    few = _provided_points(golden["image0"], 3, 1)
+    few["x"], few["y"] = [5, 6.5, 30], [5, 7.25, 9]
+    for img in (golden["image0"], bb.synthetic_frame(500, 333, 3)):
+        for k in (few, _provided_points(img, 40, 5)):
+            assert kp_equal(det.compute_scale(img, k, cap=400000), oracle.compute_scale(img, k, thresh, octaves))
+    # a batch in which only some frames have such layers
+    imgs = np.stack([bb.synthetic_frame(500, 333, 60 + i) for i in range(3)])
+    lists = [few, _provided_points(imgs[1], 600, 6), few[:1]]
+    kin = np.zeros((3, 600), bb.KP_DTYPE)
+    for i, k in enumerate(lists):
+        kin[i, :len(k)] = k
+    out, oc = det.compute_scale_batch(imgs, kin, [len(k) for k in lists], cap=400000)
+    for i in range(3):
+        assert kp_equal(out[i, :oc[i]], oracle.compute_scale(imgs[i], lists[i], thresh, octaves))
+
+
+def test_compute_scale_batch_and_errors(ctx, oracle):
+    from test_oracle_golden import _provided_points
+    det = bb.BriskFeatureDetector(60, 3, ctx=ctx)
+    imgs = np.stack([bb.synthetic_frame(640, 360, 40 + i) for i in range(5)])
+    lists = [_provided_points(imgs[i], 300 + 50 * i, 30 + i) for i in range(5)]
+    cap_in = max(len(k) for k in lists)
+    kin = np.zeros((5, cap_in), bb.KP_DTYPE)
+    for i, k in enumerate(lists):
+        kin[i, :len(k)] = k
+    counts = np.array([len(k) for k in lists], np.int32)
+    out, oc = det.compute_scale_batch(imgs, kin, counts, cap=6 * cap_in)
+    for i in range(5):
+        assert kp_equal(out[i, :oc[i]], oracle.compute_scale(imgs[i], lists[i], 60, 3))
+    # the same batch in chunks (small workspace limit) and with device-resident frames
+    import torch
+    small = bb.Context(0, workspace_limit=8 << 20)
+    out2, oc2 = bb.BriskFeatureDetector(60, 3, ctx=small).compute_scale_batch(torch.from_numpy(imgs).cuda(), kin, counts, cap=6 * cap_in)
+    assert np.array_equal(oc, oc2) and all(kp_equal(out[i, :oc[i]], out2[i, :oc[i]]) for i in range(5))
+    # truncation is reported with the true counts
+    with pytest.raises(bb.BriskError):
+        det.compute_scale_batch(imgs, kin, counts, cap=10)
+    # an empty list / the Harris detector: refused, not guessed
+    with pytest.raises(bb.BriskError):
+        det.compute_scale_batch(imgs[:1], kin[:1], [0])
+    with pytest.raises(bb.BriskError):
+        bb.ScaleSpaceFeatureDetector(2, 30.0, 20.0, ctx=ctx).compute_scale(imgs[0], lists[0])
+
+
 def test_detect_tie_heavy(ctx, oracle):
     rng = np.random.default_rng(7)
     det = bb.BriskFeatureDetector(35, 3, ctx=ctx)
@@ -320,13 +383,18 @@ def test_cpp_dropin_classes(tmp_path, oracle, golden):
     off = 12 + n * 28 + n * nb
     hn = int(np.frombuffer(raw[off:off + 4], np.int32)[0])
     hk = np.frombuffer(raw[off + 4:off + 4 + hn * 28], bb.KP_DTYPE)
-    hd = np.frombuffer(raw[off + 4 + hn * 28:], np.uint8).reshape(hn, 48)
+    hd = np.frombuffer(raw[off + 4 + hn * 28:off + 4 + hn * 76], np.uint8).reshape(hn, 48)
+    off += 4 + hn * 76
+    cn = int(np.frombuffer(raw[off:off + 4], np.int32)[0])
+    cs = np.frombuffer(raw[off + 4:off + 4 + cn * 28], bb.KP_DTYPE)
     assert hn == len(golden["harris0_kps"]) and np.array_equal(hk["x"], golden["harris0_kps"]["x"]) and np.array_equal(hd, golden["harris0_desc"])
     gk, gd = golden["ast0_kps"], golden["ast0_desc"]
     assert n == len(gk) and nb == 48 and self_matches == n
     for f in ("x", "y", "size", "response", "octave", "class_id"):
         assert np.array_equal(kps[f], gk[f]), f
     assert np.array_equal(desc, gd)
+    # ComputeScale on the detected key points (their `angle` was written by compute(); it is not read)
+    assert kp_equal(cs, oracle.compute_scale(img, kps, 70, 3))
     # matcher surface: masked knnMatch over a two-image collection, radiusMatch with compactResult
     nq, n0 = min(n, 150), n // 3
     trains = [desc[:n0], desc[n0:]]

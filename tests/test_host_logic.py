@@ -30,6 +30,16 @@ def emul():
         k = np.zeros(cap, KP_DTYPE)
         n = handle.emul_agast_detect(img.ctypes.data_as(C.c_void_p), w, h, thresh, octaves, k.ctypes.data_as(C.c_void_p), cap)
         return k[:n].copy()
+
+    def compute_scale(img, kps, thresh, octaves, cap=1 << 18):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        kin = np.ascontiguousarray(kps, KP_DTYPE)
+        k = np.zeros(cap, KP_DTYPE)
+        n = handle.emul_compute_scale(img.ctypes.data_as(C.c_void_p), w, h, thresh, octaves, kin.ctypes.data_as(C.c_void_p), len(kin),
+                                      k.ctypes.data_as(C.c_void_p), cap)
+        return n if n < 0 else k[:n].copy()
+    detect.compute_scale = compute_scale
     return detect
 
 
@@ -53,6 +63,26 @@ def test_parallel_nms_formulation_tie_heavy(emul, oracle):
     for k in range(3):
         img = (rng.integers(0, 4, (240, 320)) * 60 + rng.integers(0, 8, (240, 320))).astype(np.uint8)
         assert kp_equal(emul(img, 30 + 5 * k, 3), oracle.agast_detect(img, 30 + 5 * k, 3))
+
+
+@pytest.mark.parametrize("thresh,octaves", [(60, 4), (70, 3), (35, 2), (70, 0), (60, 1), (30, 5), (12, 3)])
+def test_provided_keypoints_closed_form(emul, oracle, golden, thresh, octaves):
+    # ComputeScale: the three data-parallel passes of the GPU path (touch / stamp / refine, nms_logic.cuh) run on
+    # the CPU against the oracle's sequential replay of the lazy score cache
+    from test_oracle_golden import _provided_points
+    for img in (golden["image0"], synthetic_frame(500, 333, 3), synthetic_frame(1000, 700, 5)):
+        for k in (oracle.agast_detect(img, max(thresh, 40), min(octaves, 4)), _provided_points(img, 2000, 21),
+                  _provided_points(img, 500, 22, True)):
+            got = emul.compute_scale(img, k, thresh, octaves)
+            assert not isinstance(got, int), got
+            assert len(got) > 5 and kp_equal(got, oracle.compute_scale(img, k, thresh, octaves))
+    # layers that keep no point are detected on (threshold map without lower bound): deep pyramids, few points
+    few = _provided_points(golden["image0"], 3, 1)
+    few["x"], few["y"] = [5, 6.5, 30], [5, 7.25, 9]
+    for img in (golden["image0"], synthetic_frame(500, 333, 3)):
+        got = emul.compute_scale(img, few, thresh, octaves)
+        assert not isinstance(got, int), got
+        assert kp_equal(got, oracle.compute_scale(img, few, thresh, octaves))
 
 
 @pytest.fixture(scope="module")

@@ -82,6 +82,35 @@ def test_agast_detect_vs_ref(oracle, ref, golden, thresh, octaves):
         assert kp_equal(oracle.agast_detect(img, thresh, octaves), ref.agast_detect(img, thresh, octaves))
 
 
+def _provided_points(img, n, seed, integer=False):
+    """n key points anywhere on the image (also on its border), with class ids to be copied through."""
+    from oracle.ref import KP_DTYPE
+    rng = np.random.default_rng(seed)
+    h, w = img.shape
+    k = np.zeros(n, KP_DTYPE)
+    k["x"], k["y"] = rng.uniform(0, w, n), rng.uniform(0, h, n)
+    if integer:
+        k["x"], k["y"] = np.floor(k["x"]), np.floor(k["y"])
+    k["size"], k["angle"], k["class_id"] = 9.0, -1.0, np.arange(n)
+    return k
+
+
+@pytest.mark.parametrize("thresh,octaves", [(60, 4), (70, 3), (35, 2), (70, 0), (60, 1)])
+def test_compute_scale_vs_ref(oracle, ref, golden, thresh, octaves):
+    # BriskFeatureDetector::ComputeScale = GetKeypoints with provided key points (brisk-scale-space.cc:104-124):
+    # detected key points fed back, arbitrary fractional points, integer points
+    for img in (golden["image1"], synthetic_frame(500, 333, 3)):
+        lists = [ref.agast_detect(img, thresh, octaves), _provided_points(img, 400, 11), _provided_points(img, 400, 12, True)]
+        for k in lists:
+            want = ref.compute_scale(img, k, thresh, octaves)
+            assert len(want) > 5 and kp_equal(oracle.compute_scale(img, k, thresh, octaves), want)
+    # a layer that keeps no point runs the detector (threshold map without lower bound) on that layer only
+    few = _provided_points(golden["image0"], 3, 1)
+    few["x"], few["y"] = [5, 6.5, 30], [5, 7.25, 9]
+    want = ref.compute_scale(golden["image0"], few, thresh, octaves)
+    assert kp_equal(oracle.compute_scale(golden["image0"], few, thresh, octaves), want)
+
+
 def test_agast_mask_vs_ref(oracle, ref, golden):
     img = golden["image0"]
     mask = np.zeros_like(img)
