@@ -256,6 +256,33 @@ class ScaleSpaceFeatureDetector(BriskFeatureDetector):
                                                                     C.c_double(absoluteThreshold), C.c_int64(mk), C.byref(self._h)))
 
 
+    def detect(self, image, mask=None, cap=65536, keypoints=None):
+        """detect(image, keypoints): a non-empty `keypoints` switches to the reference's "use passed key points" mode
+        (scale-space-feature-detector.h:103-108)."""
+        if keypoints is not None and len(keypoints):
+            a = image if _is_torch(image) else np.asarray(image)
+            return self.detect_passed(tuple(a.shape[-2:]), keypoints)
+        return super().detect(image, mask, cap)
+
+    def detect_passed_batch(self, shape, kps, counts, cap=None):
+        """shape = (h, w); kps [n,cap_in] structured, counts [n] -> (kps [n,cap], counts [n])."""
+        h, w = (int(v) for v in shape)
+        c = np.ascontiguousarray(counts, np.int32).reshape(-1)
+        n = len(c)
+        k = np.ascontiguousarray(kps, KP_DTYPE).reshape(n, -1)
+        cap = int(cap or k.shape[1])
+        out = np.zeros((n, cap), KP_DTYPE)
+        oc = np.zeros(n, np.int32)
+        self.ctx._check(self.ctx._lib.brisk_harris_detect_passed(self.ctx._h, self._h, n, w, h, _ptr(k), _ptr(c), k.shape[1],
+                                                                 _ptr(out), _ptr(oc), cap))
+        return out, oc
+
+    def detect_passed(self, shape, keypoints):
+        k = np.ascontiguousarray(keypoints, KP_DTYPE).reshape(1, -1)
+        out, oc = self.detect_passed_batch(shape, k, [k.shape[1]])
+        return out[0, :oc[0]].copy()
+
+
 HarrisScaleSpaceFeatureDetector = ScaleSpaceFeatureDetector
 
 

@@ -782,7 +782,7 @@ int brisk_compute_scale(brisk_ctx* ctx, brisk_detector* det, const uint8_t* imgs
   // one slot per layer and provided point, plus room for the corners of layers that keep no point (there the
   // reference runs its detector): the detector's own corner capacity
   int detect_cap = det->corner_cap;
-  if (detect_cap <= 0) detect_cap = std::min(std::max((int)(((long long)w * h) / 24), 4096), 1 << 20);
+  if (detect_cap <= 0) detect_cap = std::min(std::max((int)(((long long)w * h) / 8), 4096), 1 << 20);  // no lower bound: more corners
   sized.corner_cap = n_layers * in_max + detect_cap;
   Plan plan;
   rc = make_plan(ctx, &sized, nullptr, n, w, h, cap_out, &plan, false, false);
@@ -855,6 +855,93 @@ int brisk_compute_scale(brisk_ctx* ctx, brisk_detector* det, const uint8_t* imgs
   }
   if (empty_layer) return fail(ctx, BRISK_ERR_CUDA, "internal error: a layer without provided key points was not detected on");
   if (corner_overflow) return fail(ctx, BRISK_ERR_CAPACITY, "raw corner capacity exceeded on a layer without provided key points; raise it with brisk_detector_set_corner_capacity");
+  if (truncated) return fail(ctx, BRISK_ERR_CAPACITY, "key point capacity (cap_out) exceeded; counts hold the true numbers");
+  return BRISK_OK;
+}
+
+int brisk_harris_detect_passed(brisk_ctx* ctx, brisk_detector* det, int n, int w, int h, const brisk_keypoint* kps_in,
+                               const int32_t* counts_in, int cap_in, brisk_keypoint* kps_out, int32_t* counts_out, int cap_out) {
+  if (!ctx) return BRISK_ERR_INVALID;
+  if (!det || !det->harris) return fail(ctx, BRISK_ERR_INVALID, "passed key points are a mode of the Harris scale-space detector");
+  if (n < 0 || w <= 0 || h <= 0 || w > 8191 || h > 8191) return fail(ctx, BRISK_ERR_INVALID, "bad image size");
+  if (!kps_in || !counts_in || cap_in <= 0 || !kps_out || !counts_out || cap_out <= 0) return fail(ctx, BRISK_ERR_INVALID, "bad key point arguments");
+  // a second layer would index its (smaller) occupancy map with layer 0's image coordinates: out of bounds in the reference
+  if (det->octaves != 0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "passed key points are only defined for octaves == 0 (the reference writes out of bounds otherwise)");
+  if (!(det->radius > 0.0)) {
+    if (det->max_kpt <= 0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "key point bucketing (uniformityRadius <= 0) needs a finite maxNumKpt > 0");
+  } else if (det->radius < 1.0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "uniformityRadius in (0, 1) is not supported (the occupancy map would take more than 225 bytes per pixel)");
+  if (w < 8 || h < 8) return fail(ctx, BRISK_ERR_INVALID, "image too small");
+  CU_OK(cudaSetDevice(ctx->device));
+  memset(ctx->ms, 0, sizeof(ctx->ms));
+  ctx->launches = 0;
+  if (n == 0) return BRISK_OK;
+  const bool in_dev = is_device_ptr(kps_in), cin_dev = is_device_ptr(counts_in);
+  const bool out_dev = is_device_ptr(kps_out), cout_dev = is_device_ptr(counts_out);
+  std::vector<int32_t> h_cin(n);
+  if (cin_dev) {
+    CU_OK(cudaStreamSynchronize(ctx->stream));
+    CU_OK(cudaMemcpy(h_cin.data(), counts_in, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  } else memcpy(h_cin.data(), counts_in, (size_t)n * 4);
+  int in_max = 0;
+  for (int f = 0; f < n; ++f) {
+    if (h_cin[f] < 0 || h_cin[f] > cap_in) return fail(ctx, BRISK_ERR_INVALID, "counts_in must be in [0, cap_in]");
+    if (h_cin[f] == 0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "an empty key point vector means detection; use detect()");
+    in_max = std::max(in_max, h_cin[f]);
+  }
+  brisk_detector sized = *det;
+  sized.corner_cap = in_max;
+  Plan plan;
+  int rc = make_plan(ctx, &sized, nullptr, n, w, h, cap_out, &plan, false, false);
+  if (rc) return rc;
+  const PyramidGeom& g = plan.g;
+  Slot& sl = ctx->slots[0];
+  const size_t c_max = (size_t)plan.chunk;
+  if (!in_dev) CU_OK(sl.kps_scratch.ensure(c_max * cap_in * 28));
+  if (!cin_dev) CU_OK(sl.scales.ensure(c_max * 4));
+  if (!out_dev) CU_OK(sl.kps.ensure(c_max * cap_out * 28));
+  if (!cout_dev) CU_OK(sl.counts.ensure(c_max * 4));
+  CU_OK(cudaEventRecord(ctx->entry, ctx->stream));
+  CU_OK(cudaStreamWaitEvent(sl.stream, ctx->entry, 0));
+  HarrisWorkspace hw = plan.hw;
+  hw.det = slot_ws(plan, sl);
+  hw.scores = sl.h_scores.as<int>(); hw.pts = sl.h_pts.as<HPoint>(); hw.keep = sl.h_keep.as<uint8_t>();
+  hw.sorted = sl.h_sorted.as<HPoint>(); hw.layer_kept = sl.h_layer_kept.as<int>(); hw.occ = sl.h_occ.as<uint8_t>();
+  hw.surv = sl.h_surv.as<HPoint>(); hw.layer_surv = sl.h_layer_surv.as<int>();
+  bool truncated = false, bad_point = false;
+  for (int f0 = 0; f0 < n; f0 += plan.chunk) {
+    const int c = std::min(plan.chunk, n - f0);
+    const KeyPoint* d_in = reinterpret_cast<const KeyPoint*>(kps_in) + (size_t)f0 * cap_in;
+    const int* d_cin = counts_in + f0;
+    if (!in_dev) {
+      for (int f = 0; f < c; ++f)
+        CU_OK(cudaMemcpyAsync(sl.kps_scratch.as<KeyPoint>() + (size_t)f * cap_in, kps_in + (size_t)(f0 + f) * cap_in,
+                              (size_t)h_cin[f0 + f] * 28, cudaMemcpyHostToDevice, sl.stream));
+      d_in = sl.kps_scratch.as<KeyPoint>();
+    }
+    if (!cin_dev) {
+      CU_OK(cudaMemcpyAsync(sl.scales.p, h_cin.data() + f0, (size_t)c * 4, cudaMemcpyHostToDevice, sl.stream));
+      d_cin = sl.scales.as<int>();
+    }
+    KeyPoint* d_out = out_dev ? reinterpret_cast<KeyPoint*>(kps_out) + (size_t)f0 * cap_out : sl.kps.as<KeyPoint>();
+    int* d_cout = cout_dev ? counts_out + f0 : sl.counts.as<int>();
+    CU_OK(cudaMemsetAsync(sl.flag.p, 0, 16, sl.stream));
+    CU_OK(launch_harris_passed(g, hw, c, det->radius, det->max_kpt, d_in, d_cin, cap_in, in_max, d_out, d_cout, cap_out,
+                               sl.flag.as<int>(), sl.stream));
+    ctx->launches += 4;
+    CU_OK(cudaMemcpyAsync(sl.h_counts, d_cout, (size_t)c * 4, cudaMemcpyDeviceToHost, sl.stream));
+    CU_OK(cudaMemcpyAsync(sl.h_counts + plan.chunk, sl.flag.p, 4, cudaMemcpyDeviceToHost, sl.stream));
+    CU_OK(cudaStreamSynchronize(sl.stream));
+    if (sl.h_counts[plan.chunk] == 4) bad_point = true;
+    if (!cout_dev) memcpy(counts_out + f0, sl.h_counts, (size_t)c * 4);
+    for (int f = 0; f < c; ++f) {
+      const int m = std::min(sl.h_counts[f], cap_out);
+      if (sl.h_counts[f] > cap_out) truncated = true;
+      if (m > 0 && !out_dev)
+        CU_OK(cudaMemcpyAsync(kps_out + (size_t)(f0 + f) * cap_out, d_out + (size_t)f * cap_out, (size_t)m * 28, cudaMemcpyDeviceToHost, sl.stream));
+    }
+    CU_OK(cudaStreamSynchronize(sl.stream));
+  }
+  if (bad_point) return fail(ctx, BRISK_ERR_INVALID, "a passed key point with response > 1e6 lies outside the image (or its response does not fit an int)");
   if (truncated) return fail(ctx, BRISK_ERR_CAPACITY, "key point capacity (cap_out) exceeded; counts hold the true numbers");
   return BRISK_OK;
 }

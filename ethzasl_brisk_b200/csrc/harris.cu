@@ -485,4 +485,80 @@ cudaError_t launch_harris_detect(const PyramidGeom& g, const HarrisWorkspace& hw
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// "Use passed key points" (scale-space-feature-detector.h:103-108, scale-space-layer-inl.h:198-208,370-428):
+// detect() on a non-empty vector computes no scores; the points with response > 1e6 are re-filtered by the
+// uniformity enforcement (or the bucketing) and come back unrefined.  One layer only (octaves == 0).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+harris_import_kernel(const KeyPoint* __restrict__ in, const int* __restrict__ in_counts, int in_cap, int w, int h,
+                     HPoint* __restrict__ pts, uint8_t* __restrict__ keep, int* __restrict__ layer_start, int cap,
+                     int* __restrict__ error_flag) {
+  const int frame = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n_in = min(min(in_counts[frame], in_cap), cap);
+  if (j == 0) {
+    int* ls = layer_start + (long long)frame * (kMaxLayers + 1);
+    ls[0] = 0; ls[1] = n_in;
+  }
+  if (j >= n_in) return;
+  const KeyPoint kp = in[(long long)frame * in_cap + j];
+  bool on = (double)kp.response > 1e6;
+  HPoint p = {0, 0, 0};
+  if (on) {
+    // PointWithScore(int score, uint16_t x, uint16_t y) from float fields: defined for values in range only
+    if (!(kp.response < 2147483648.0f) || !(kp.x >= 0.0f && kp.x < (float)w && kp.y >= 0.0f && kp.y < (float)h)) {
+      atomicExch(error_flag, 4);
+      on = false;
+    } else {
+      p.score = (int)kp.response; p.x = (unsigned short)(int)kp.x; p.y = (unsigned short)(int)kp.y;
+    }
+  }
+  pts[(long long)frame * cap + j] = p;
+  keep[(long long)frame * cap + j] = on ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(256)
+harris_emit_passed_kernel(const KeyPoint* __restrict__ in, const int* __restrict__ in_counts, int in_cap, const HPoint* __restrict__ surv,
+                          const int* __restrict__ layer_kept, const int* __restrict__ layer_surv, int cap, KeyPoint* __restrict__ out,
+                          int* __restrict__ counts, int kp_cap) {
+  const int frame = blockIdx.x, tid = threadIdx.x;
+  if (layer_kept[frame * kMaxLayers] == 0) {
+    // no point passed the response test: the reference returns before it clears the vector (:370-371)
+    const int n_in = min(in_counts[frame], in_cap);
+    for (int k = tid; k < n_in && k < kp_cap; k += blockDim.x) out[(long long)frame * kp_cap + k] = in[(long long)frame * in_cap + k];
+    if (tid == 0) counts[frame] = n_in;
+    return;
+  }
+  const int m = layer_surv[frame * kMaxLayers];
+  for (int k = tid; k < m && k < kp_cap; k += blockDim.x) {
+    const HPoint p = surv[(long long)frame * cap + k];
+    KeyPoint kp;
+    kp.x = (float)(1.0 * ((double)(int)p.x + 0.0)); kp.y = (float)(1.0 * ((double)(int)p.y + 0.0));
+    kp.size = (float)(1.0 * 12.0); kp.angle = -1.0f; kp.response = (float)p.score; kp.octave = 0; kp.class_id = -1;
+    out[(long long)frame * kp_cap + k] = kp;
+  }
+  if (tid == 0) counts[frame] = m;
+}
+
+cudaError_t launch_harris_passed(const PyramidGeom& g, const HarrisWorkspace& hw, int n_frames, double radius, long long max_kpt,
+                                 const KeyPoint* in, const int* in_counts, int in_cap, int in_max, KeyPoint* out, int* counts,
+                                 int kp_cap, int* error_flag, cudaStream_t stream) {
+  if (g.n_layers != 1 || in_max <= 0 || in_max > hw.det.corner_cap) return cudaErrorInvalidValue;
+  const int cap = hw.det.corner_cap;
+  harris_import_kernel<<<dim3((in_max + 255) / 256, n_frames), 256, 0, stream>>>(in, in_counts, in_cap, g.L[0].w, g.L[0].h, hw.pts, hw.keep,
+                                                                                 hw.det.layer_start, cap, error_flag);
+  harris_sort_kernel<<<dim3(1, n_frames), kSortThreads, 0, stream>>>(1, hw.det.layer_start, hw.pts, hw.keep, hw.sorted, hw.layer_kept, hw.surv, cap);
+  if (!(radius > 0.0)) {
+    harris_bucketing_kernel<<<dim3(1, n_frames), 32, 0, stream>>>(g, hw.det.layer_start, hw.sorted, hw.layer_kept, hw.surv, hw.layer_surv, cap, max_kpt);
+  } else {
+    UniformityGeom ug;
+    ug.occ_frame_bytes = hw.occ_frame_bytes;
+    ug.scaling = (float)(15.0 / (double)(float)radius);
+    for (int l = 0; l < g.n_layers; ++l) { ug.occ_off[l] = hw.occ_off[l]; ug.occ_w[l] = hw.occ_w[l]; ug.occ_h[l] = hw.occ_h[l]; }
+    harris_uniformity_kernel<<<dim3(1, n_frames), 256, 0, stream>>>(g, ug, hw.det.layer_start, hw.sorted, hw.layer_kept, hw.occ, hw.surv, hw.layer_surv, cap, max_kpt);
+  }
+  harris_emit_passed_kernel<<<n_frames, 256, 0, stream>>>(in, in_counts, in_cap, hw.surv, hw.layer_kept, hw.layer_surv, cap, out, counts, kp_cap);
+  return cudaGetLastError();
+}
+
 }  // namespace briskb200

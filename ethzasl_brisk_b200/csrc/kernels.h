@@ -75,6 +75,13 @@ cudaError_t launch_row_scan(const PyramidGeom& g, const DetectWorkspace& ws, int
 cudaError_t launch_harris_detect(const PyramidGeom& g, const HarrisWorkspace& hw, int n_frames, double radius, double abs_thr,
                                  long long max_kpt, KeyPoint* out, int* counts, int kp_cap, int* overflow_flag, cudaStream_t stream);
 
+// detect() of the Harris scale-space detector on a non-empty key-point vector ("use passed key points"), one layer:
+// response > 1e6 filter, std::sort replay, uniformity enforcement / bucketing, unrefined output.  *error_flag = 4 when a
+// passed point lies outside the image (or its response does not fit an int).
+cudaError_t launch_harris_passed(const PyramidGeom& g, const HarrisWorkspace& hw, int n_frames, double radius, long long max_kpt,
+                                 const KeyPoint* in, const int* in_counts, int in_cap, int in_max, KeyPoint* out, int* counts,
+                                 int kp_cap, int* error_flag, cudaStream_t stream);
+
 cudaError_t launch_dense_scores(const LayerGeom& L, const uint8_t* img, uint8_t* out916, uint8_t* out58, cudaStream_t stream);
 
 // Descriptor extraction.

@@ -129,8 +129,9 @@ class HarrisScoreCalculator {};
 
 // brisk::ScaleSpaceFeatureDetector<SCORE_CALCULATOR_T> -- reference
 // brisk/include/brisk/scale-space-feature-detector.h:62-135.  Empty images return silently; the
-// mask is ignored (as in the reference's detectImpl); non-empty input key points ("use passed key
-// points" mode, :103-108) are not supported.
+// mask is ignored (as in the reference's detectImpl); a non-empty input vector switches to the "use passed
+// key points" mode (:103-108): no detection, the passed points with response > 1e6 are re-filtered by the
+// uniformity enforcement / bucketing and returned unrefined (defined for octaves == 0 only).
 template <class SCORE_CALCULATOR_T>
 class ScaleSpaceFeatureDetector {
  public:
@@ -144,7 +145,6 @@ class ScaleSpaceFeatureDetector {
 
   void detect(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, const agast::Mat& /*mask*/ = agast::Mat()) const {
     if (image.empty()) return;
-    if (!keypoints.empty()) throw std::runtime_error("brisk_b200: detection from passed key points is not supported");
     brisk_ctx* ctx = detail::context();
     if (!det_ || ctx_ != ctx) {
       if (det_) brisk_detector_destroy(det_);
@@ -152,6 +152,16 @@ class ScaleSpaceFeatureDetector {
       const int64_t mk = _maxNumKpt > (size_t)std::numeric_limits<int64_t>::max() ? -1 : (int64_t)_maxNumKpt;
       detail::check(ctx, brisk_harris_detector_create(ctx, (int)_octaves, _uniformityRadius, _absoluteThreshold, mk, &det_));
       ctx_ = ctx;
+    }
+    if (!keypoints.empty()) {  // use the passed key points
+      const int32_t n_in = (int32_t)keypoints.size();
+      std::vector<agast::KeyPoint> out(keypoints.size());
+      int32_t count = 0;
+      detail::check(ctx, brisk_harris_detect_passed(ctx, det_, 1, image.cols, image.rows, reinterpret_cast<const brisk_keypoint*>(keypoints.data()),
+                                                    &n_in, n_in, reinterpret_cast<brisk_keypoint*>(out.data()), &count, n_in));
+      out.resize(count);
+      keypoints.swap(out);
+      return;
     }
     int cap = (int)std::max<long long>(4096, (long long)image.rows * image.cols / 64);
     for (;;) {

@@ -117,6 +117,16 @@ int brisk_compute_scale(brisk_ctx* ctx, brisk_detector* det, const uint8_t* imgs
                         size_t frame_pitch, const brisk_keypoint* kps_in, const int32_t* counts_in, int cap_in,
                         brisk_keypoint* kps_out, int32_t* counts_out, int cap_out);
 
+/* ScaleSpaceFeatureDetector::detect() on a NON-EMPTY key-point vector ("use passed key points") -- reference
+ * brisk/include/brisk/scale-space-feature-detector.h:103-108, brisk/include/brisk/internal/scale-space-layer-inl.h:
+ * 198-208,370-428.  No image is read (the reference computes no scores in this mode; w, h size the occupancy map /
+ * the buckets): the points with response > 1e6 are taken as (int score, uint16 x, uint16 y), sorted, filtered by the
+ * uniformity enforcement (uniformityRadius > 0) or the bucketing, and returned unrefined (x, y truncated, size 12,
+ * octave 0, class_id -1).  If no point of a frame passes the response test its vector is returned unchanged.
+ * Only for octaves == 0 (a second layer indexes its occupancy map out of bounds in the reference). */
+int brisk_harris_detect_passed(brisk_ctx* ctx, brisk_detector* det, int n, int w, int h, const brisk_keypoint* kps_in,
+                               const int32_t* counts_in, int cap_in, brisk_keypoint* kps_out, int32_t* counts_out, int cap_out);
+
 /* compute(): BriskDescriptorExtractor::computeImpl -- reference
  * brisk/src/brisk-descriptor-extractor.cc:589-599,612-778.  kps/counts are in/out: key points too
  * close to the border are removed (order kept), `angle` is written.  desc: [n][cap][descriptor_size]. */

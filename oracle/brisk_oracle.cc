@@ -1226,6 +1226,41 @@ void HarrisDetect(const uint8_t* image, int w, int h, int octaves, double radius
   }
 }
 
+// reference scale-space-feature-detector.h:100-128 with a NON-EMPTY key-point vector ("use passed key points",
+// :103-108) and scale-space-layer-inl.h:193-208,370-428: no scores are computed; the points with response > 1e6
+// become (int score, uint16 x, uint16 y), go through the uniformity enforcement (or the bucketing) and come back
+// unrefined.  Only one layer (octaves == 0): a second layer would index its smaller occupancy map with layer 0's
+// image coordinates (out of bounds in the reference).  If no point passes the response test the vector is
+// returned untouched (:370-371 returns before the clear).
+void HarrisFilterPassed(int w, int h, double radius, size_t max_kpt, const orc_keypoint* in, int n_in,
+                        std::vector<orc_keypoint>* out) {
+  std::vector<ScoredPoint> pts;
+  for (int k = 0; k < n_in; ++k)
+    if (in[k].response > 1e6) { ScoredPoint p; p.score = (int)in[k].response; p.x = (uint16_t)in[k].x; p.y = (uint16_t)in[k].y; pts.push_back(p); }
+  out->clear();
+  if (pts.empty()) { out->assign(in, in + n_in); return; }
+  const double r = radius == 0 ? 1.0 : radius;  // SetUniformityRadius (scale-space-layer-inl.h:185-189)
+  if (radius > 0.0 && r > 0.0) EnforceUniformity(r, h, w, max_kpt, &pts);
+  else {
+    const unsigned step_u = 1u + (unsigned)((w - 1u) / 4u), step_v = 1u + (unsigned)((h - 1u) / 4u);
+    const unsigned quota = (unsigned)(max_kpt / 16u);
+    unsigned count[4][4] = {};
+    std::sort(pts.begin(), pts.end());
+    std::vector<ScoredPoint> kept;
+    for (const ScoredPoint& p : pts) {
+      unsigned* c = &count[p.x / step_u][p.y / step_v];
+      if (*c < quota) { ++*c; kept.push_back(p); }
+    }
+    pts.swap(kept);
+  }
+  for (const ScoredPoint& p : pts) {
+    orc_keypoint k;
+    k.x = (float)(1.0 * ((p.x) + 0.0)); k.y = (float)(1.0 * ((p.y) + 0.0));
+    k.size = (float)(1.0 * 12.0); k.angle = -1; k.response = (float)p.score; k.octave = 0; k.class_id = -1;
+    out->push_back(k);
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -1348,6 +1383,15 @@ int orc_harris_detect(const uint8_t* img, int w, int h, int octaves, double radi
                       orc_keypoint* out, int cap) {
   std::vector<orc_keypoint> kps;
   HarrisDetect(img, w, h, octaves, radius, abs_thr, max_kpt < 0 ? (size_t)-1 : (size_t)max_kpt, &kps);
+  for (size_t i = 0; i < kps.size() && (int)i < cap; ++i) out[i] = kps[i];
+  return (int)kps.size();
+}
+
+int orc_harris_detect_passed(int w, int h, double radius, int64_t max_kpt, const orc_keypoint* in, int n_in,
+                             orc_keypoint* out, int cap) {
+  if (n_in <= 0 || w <= 0 || h <= 0) return -1;
+  std::vector<orc_keypoint> kps;
+  HarrisFilterPassed(w, h, radius, max_kpt < 0 ? SIZE_MAX : (size_t)max_kpt, in, n_in, &kps);
   for (size_t i = 0; i < kps.size() && (int)i < cap; ++i) out[i] = kps[i];
   return (int)kps.size();
 }

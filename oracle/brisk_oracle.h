@@ -55,6 +55,9 @@ int orc_harris_maxima(const uint8_t* img, int w, int h, int abs_thr, int32_t* ou
 /* scale-space-feature-detector.h:100-128 */
 int orc_harris_detect(const uint8_t* img, int w, int h, int octaves, double radius, double abs_thr, int64_t max_kpt,
                       orc_keypoint* out, int cap);
+/* scale-space-feature-detector.h:100-128 with passed key points (one layer, octaves == 0) */
+int orc_harris_detect_passed(int w, int h, double radius, int64_t max_kpt, const orc_keypoint* in, int n_in,
+                             orc_keypoint* out, int cap);
 /* hamming-inl.h:85-134 */
 int orc_hamming(const uint8_t* a, const uint8_t* b, int nbytes);
 /* brute-force-matcher.cc:80-162 (single train image, no mask) */

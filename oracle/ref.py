@@ -117,6 +117,17 @@ def harris_detect(img, octaves, radius, abs_thr=0.0, max_kpt=-1, cap=1 << 18):
     return kps[:n].copy()
 
 
+def harris_detect_passed(img, kps, radius, max_kpt=-1, cap=1 << 18):
+    """ScaleSpaceFeatureDetector<HarrisScoreCalculator>(0, radius, 0, max_kpt).detect(img, kps) with kps non-empty"""
+    img, w, h = _img(img)
+    k = np.ascontiguousarray(kps, KP_DTYPE)
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().ref_harris_detect_passed(_p(img), w, h, 0, C.c_double(radius), C.c_double(0.0), C.c_int64(max_kpt), _p(k), len(k),
+                                       _p(out), cap)
+    assert n <= cap
+    return out[:n].copy()
+
+
 def harris_scores(img):
     img, w, h = _img(img)
     out = np.zeros((h, w), np.int32)

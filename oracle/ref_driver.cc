@@ -249,6 +249,17 @@ int ref_harris_detect(const uint8_t* img, int w, int h, int octaves, double radi
   return FromVec(kps, out, cap);
 }
 
+// ScaleSpaceFeatureDetector<HarrisScoreCalculator>::detect with a non-empty key-point vector ("use passed key points")
+int ref_harris_detect_passed(const uint8_t* img, int w, int h, int octaves, double radius, double abs_thr, int64_t max_kpt,
+                             const RefKeyPoint* in, int n_in, RefKeyPoint* out, int cap) {
+  cv::Mat m = WrapCopy(img, w, h);
+  HarrisDetector det((size_t)octaves, radius, abs_thr, max_kpt < 0 ? std::numeric_limits<size_t>::max() : (size_t)max_kpt);
+  std::vector<cv::KeyPoint> kps;
+  ToVec(in, n_in, &kps);
+  det.detect(m, kps);
+  return FromVec(kps, out, cap);
+}
+
 int ref_harris_scores(const uint8_t* img, int w, int h, int32_t* out) {
   cv::Mat m = WrapCopy(img, w, h);
   cv::Mat scores;

@@ -118,6 +118,16 @@ def harris_detect(img, octaves, radius, abs_thr=0.0, max_kpt=-1, cap=1 << 18):
     return kps[:n].copy()
 
 
+def harris_detect_passed(shape, kps, radius, max_kpt=-1, cap=1 << 18):
+    """The "use passed key points" mode of the Harris scale-space detector on one layer; shape = (h, w)."""
+    h, w = shape
+    k = np.ascontiguousarray(kps, KP_DTYPE)
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().orc_harris_detect_passed(int(w), int(h), C.c_double(radius), C.c_int64(max_kpt), _p(k), len(k), _p(out), cap)
+    assert 0 <= n <= cap
+    return out[:n].copy()
+
+
 def harris_scores(img):
     img, w, h = _img(img)
     out = np.zeros((h, w), np.int32)

@@ -47,7 +47,14 @@ int main(int argc, char** argv) {
   int cn = (int)cs.size();
   o.write(reinterpret_cast<char*>(&cn), 4);
   o.write(reinterpret_cast<char*>(cs.data()), (std::streamsize)cn * sizeof(agast::KeyPoint));
-  std::printf("%d key points, %d-byte descriptors, %d self matches, %d from ComputeScale\n", n, nb, self, cn);
+  // Harris detector on a non-empty vector: "use passed key points" (reference scale-space-feature-detector.h:103-108)
+  brisk::HarrisScaleSpaceFeatureDetector hdet(0, 30.0, 20.0);
+  std::vector<agast::KeyPoint> pk(hk);
+  hdet.detect(img, pk);
+  int pn = (int)pk.size();
+  o.write(reinterpret_cast<char*>(&pn), 4);
+  o.write(reinterpret_cast<char*>(pk.data()), (std::streamsize)pn * sizeof(agast::KeyPoint));
+  std::printf("%d key points, %d-byte descriptors, %d self matches, %d from ComputeScale, %d of the passed Harris points\n", n, nb, self, cn, pn);
   if (argc > 3) {
     // matcher surface: a two-image train collection with masks, knnMatch(k = 3) and radiusMatch(45)
     const int nq = std::min(n, 150), n0 = n / 3;

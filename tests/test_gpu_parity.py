@@ -96,6 +96,7 @@ def test_compute_scale_bit_exact(ctx, oracle, golden, thresh, octaves):
     # BriskFeatureDetector::ComputeScale (provided key points, brisk-scale-space.cc:104-124)
     from test_oracle_golden import _provided_points
     det = bb.BriskFeatureDetector(thresh, octaves, ctx=ctx)
+    det.set_corner_capacity(300000)  # the top layers of a 5-octave pyramid keep no point and are detected on
     for img in (golden["image0"], bb.synthetic_frame(752, 480, 1000), bb.synthetic_frame(500, 333, 3)):
         for k in (oracle.agast_detect(img, max(thresh, 40), min(octaves, 4)), _provided_points(img, 2000, 21),
                   _provided_points(img, 500, 22, True)):
@@ -141,8 +142,10 @@ def test_compute_scale_batch_and_errors(ctx, oracle):
         assert kp_equal(out[i, :oc[i]], oracle.compute_scale(imgs[i], lists[i], 60, 3))
     # the same batch in chunks (small workspace limit) and with device-resident frames
     import torch
-    small = bb.Context(0, workspace_limit=8 << 20)
-    out2, oc2 = bb.BriskFeatureDetector(60, 3, ctx=small).compute_scale_batch(torch.from_numpy(imgs).cuda(), kin, counts, cap=6 * cap_in)
+    small = bb.Context(0, workspace_limit=64 << 20)
+    det2 = bb.BriskFeatureDetector(60, 3, ctx=small)
+    det2.set_corner_capacity(200000)  # 20 MB of per-frame scratch: two frames per chunk
+    out2, oc2 = det2.compute_scale_batch(torch.from_numpy(imgs).cuda(), kin, counts, cap=6 * cap_in)
     assert np.array_equal(oc, oc2) and all(kp_equal(out[i, :oc[i]], out2[i, :oc[i]]) for i in range(5))
     # truncation is reported with the true counts
     with pytest.raises(bb.BriskError):
@@ -387,6 +390,9 @@ def test_cpp_dropin_classes(tmp_path, oracle, golden):
     off += 4 + hn * 76
     cn = int(np.frombuffer(raw[off:off + 4], np.int32)[0])
     cs = np.frombuffer(raw[off + 4:off + 4 + cn * 28], bb.KP_DTYPE)
+    off += 4 + cn * 28
+    pn = int(np.frombuffer(raw[off:off + 4], np.int32)[0])
+    pk = np.frombuffer(raw[off + 4:off + 4 + pn * 28], bb.KP_DTYPE)
     assert hn == len(golden["harris0_kps"]) and np.array_equal(hk["x"], golden["harris0_kps"]["x"]) and np.array_equal(hd, golden["harris0_desc"])
     gk, gd = golden["ast0_kps"], golden["ast0_desc"]
     assert n == len(gk) and nb == 48 and self_matches == n
@@ -395,6 +401,8 @@ def test_cpp_dropin_classes(tmp_path, oracle, golden):
     assert np.array_equal(desc, gd)
     # ComputeScale on the detected key points (their `angle` was written by compute(); it is not read)
     assert kp_equal(cs, oracle.compute_scale(img, kps, 70, 3))
+    # the Harris detector handed its own key points back (non-empty vector: re-filtering instead of detection)
+    assert pn > 10 and kp_equal(pk, oracle.harris_detect_passed(img.shape, hk, 30.0, -1))
     # matcher surface: masked knnMatch over a two-image collection, radiusMatch with compactResult
     nq, n0 = min(n, 150), n // 3
     trains = [desc[:n0], desc[n0:]]
@@ -537,6 +545,39 @@ def test_harris_key_point_bucketing_bit_exact(ctx, oracle, golden, octaves, radi
         got = det.detect(img)
         assert kp_equal(got, want)
     assert max_kpt < 16 or len(got) > 0
+
+
+@pytest.mark.parametrize("radius,max_kpt", [(30.0, None), (8.0, None), (3.0, 150), (0.0, 400), (-1.0, 90), (15.0, 40)])
+def test_harris_passed_keypoints(ctx, oracle, golden, radius, max_kpt):
+    # detect() on a non-empty vector: the "use passed key points" mode (scale-space-feature-detector.h:103-108)
+    from test_oracle_golden import _passed_points
+    img = golden["image0"]
+    det = bb.ScaleSpaceFeatureDetector(0, radius, 0.0, max_kpt, ctx=ctx)
+    mk = -1 if max_kpt is None else max_kpt
+    lists = [_passed_points(img.shape, 3000, 1), _passed_points(img.shape, 700, 2, True), _passed_points(img.shape, 20, 3),
+             _passed_points(img.shape, 40000, 4)]
+    if radius > 0:
+        lists.append(bb.ScaleSpaceFeatureDetector(0, 1.0, 0.0, ctx=ctx).detect(img))
+    for k in lists:
+        assert kp_equal(det.detect(img, keypoints=k), oracle.harris_detect_passed(img.shape, k, radius, mk))
+    low = lists[0].copy()
+    low["response"] = 999999.0
+    assert kp_equal(det.detect(img, keypoints=low), low)
+    # a batch with lists of different lengths
+    kin = np.zeros((3, 3000), bb.KP_DTYPE)
+    for i in range(3):
+        kin[i, :len(lists[i])] = lists[i]
+    out, oc = det.detect_passed_batch(img.shape, kin, [len(lists[i]) for i in range(3)])
+    for i in range(3):
+        assert kp_equal(out[i, :oc[i]], oracle.harris_detect_passed(img.shape, lists[i], radius, mk))
+    # refused: more than one layer, a point outside the image
+    with pytest.raises(bb.BriskError):
+        bb.ScaleSpaceFeatureDetector(1, 30.0, 0.0, ctx=ctx).detect(img, keypoints=lists[0])
+    bad = lists[2].copy()
+    bad["x"][0] = img.shape[1] + 5.0
+    bad["response"][0] = 5.0e6
+    with pytest.raises(bb.BriskError):
+        det.detect(img, keypoints=bad)
 
 
 def test_harris_unsupported(ctx):

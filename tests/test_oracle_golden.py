@@ -111,6 +111,35 @@ def test_compute_scale_vs_ref(oracle, ref, golden, thresh, octaves):
     assert kp_equal(oracle.compute_scale(golden["image0"], few, thresh, octaves), want)
 
 
+def _passed_points(shape, n, seed, ties=False):
+    """n key points inside the image with Harris-like responses on both sides of the 1e6 gate."""
+    from oracle.ref import KP_DTYPE
+    rng = np.random.default_rng(seed)
+    h, w = shape
+    k = np.zeros(n, KP_DTYPE)
+    k["x"], k["y"] = rng.uniform(0, w - 0.01, n), rng.uniform(0, h - 0.01, n)
+    r = 10.0 ** rng.uniform(5.0, 9.2, n)
+    if ties:  # many equal scores: the order libstdc++'s introsort leaves them in is part of the result
+        r = rng.choice(np.array([2.0e6, 3.0e6, 5.0e5, 7.5e6, 1.0e9]), n)
+    k["response"], k["size"], k["angle"], k["class_id"] = r, 12.0, -1.0, np.arange(n)
+    return k
+
+
+@pytest.mark.parametrize("radius,max_kpt", [(30.0, -1), (8.0, -1), (3.0, 150), (0.0, 400), (-1.0, 90), (15.0, 40)])
+def test_harris_passed_keypoints_vs_ref(oracle, ref, golden, radius, max_kpt):
+    # detect() on a non-empty vector (scale-space-feature-detector.h:103-108): re-filtering, no detection
+    img = golden["image0"]
+    lists = [ref.harris_detect(img, 0, 1.0, 0.0), _passed_points(img.shape, 3000, 1), _passed_points(img.shape, 700, 2, True),
+             _passed_points(img.shape, 20, 3)]
+    for k in lists:
+        want = ref.harris_detect_passed(img, k, radius, max_kpt)
+        assert kp_equal(oracle.harris_detect_passed(img.shape, k, radius, max_kpt), want)
+    low = lists[1].copy()
+    low["response"] = 999999.0  # nothing passes the gate: the vector comes back untouched
+    assert kp_equal(oracle.harris_detect_passed(img.shape, low, radius, max_kpt), ref.harris_detect_passed(img, low, radius, max_kpt))
+    assert kp_equal(oracle.harris_detect_passed(img.shape, low, radius, max_kpt), low)
+
+
 def test_agast_mask_vs_ref(oracle, ref, golden):
     img = golden["image0"]
     mask = np.zeros_like(img)
