@@ -314,7 +314,10 @@ def run_gpu(args):
     # dram__bytes_write.sum of one launch / frames of that launch); reported for one frame of the dominant stage,
     # like `achieved`, which is per frame too (algorithmic bytes of n frames / time of n frames)
     NCU_DRAM_BYTES_PER_FRAME = {"describe": (2.195719e9 + 87.774e6) / 256,        # profiles/r01_ncu_full_top_kernels_v14.txt
-                                "pyramid": (0.354613e9 + 0.626522e9) / 256}       # (inputs partly L2 resident in that capture)
+                                "pyramid": (0.354613e9 + 0.626522e9) / 256,       # (inputs partly L2 resident in that capture)
+                                # nms_prefix + nms_checks (v14 capture, 256 frames per launch) + nms_chain (v15 capture, 171 frames
+                                # per launch); refine / compact (a few per cent of the stage's time) were not captured
+                                "nms": (1.080348e9 + 0.191219e9 + 1.312184e9 + 0.260362e9) / 256 + (961.691392e6 + 79.735040e6) / 171}
     LIMITER = {"describe": "L1/L2 sector rate of scattered 4-byte gathers (ncu: l1tex 77 %, lts 55 % of peak, DRAM 30 %); the "
                            "integral images of a chunk do not fit L2, so ~8.9 MB per frame come from DRAM although only "
                            "104 B per key point are compulsory",
@@ -327,7 +330,8 @@ def run_gpu(args):
         stage_report["integral"]["hbm_traffic_frac_of_peak"] = stage_report["integral"]["hbm_traffic_GBps"] / peak
     if top in NCU_DRAM_BYTES_PER_FRAME:
         roof["traffic"] = NCU_DRAM_BYTES_PER_FRAME[top] * n
-        roof["traffic_note"] = "ncu dram bytes per frame x frames of the step (capture: profiles/r01_ncu_full_top_kernels_v14.txt)"
+        roof["traffic_note"] = ("ncu dram bytes per frame x frames of the step (captures: profiles/r01_ncu_full_top_kernels_v14.txt, "
+                                "profiles/r01_ncu_full_top_kernels_v15.txt)")
     if top in LIMITER:
         roof["limiter"] = LIMITER[top]
 

@@ -305,6 +305,15 @@ int stage_input(brisk_ctx* ctx, Slot& sl, const Plan& plan, const uint8_t* imgs,
   return encode_map(ctx, sl.pyr.as<uint8_t>() + g.L[0].off, w, h, count, g.L[0].pitch, (size_t)g.frame_elems, map);
 }
 
+// The occupancy map of EnforceKeyPointUniformity (uniformity-enforcement-inl.h:62-66) takes ceil(15 / radius)^2 bytes
+// per pixel; the kernel indexes one layer's map with an int.
+const char* const kOccupancyTooLarge = "uniformityRadius is too small for this image size: the occupancy map of layer 0 would exceed 2 GiB";
+bool occupancy_fits(double radius, int w, int h) {
+  const float scaling = (float)(15.0 / (double)(float)(radius == 0 ? 1.0 : radius));
+  const double c = std::ceil((double)scaling);
+  return ((double)h * c + 32.0) * ((double)w * c + 32.0) + 64.0 < 2147483648.0;
+}
+
 int check_image_args(brisk_ctx* ctx, const uint8_t* imgs, int n, int w, int h, size_t stride, size_t frame_pitch) {
   if (!ctx) return BRISK_ERR_INVALID;
   if (!imgs || n < 0 || w <= 0 || h <= 0) return fail(ctx, BRISK_ERR_INVALID, "bad image arguments");
@@ -330,7 +339,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       // KeyPointBucketing (key-point-bucketing-inl.h:74-112): the reference reserves maxNumKpt entries up front, so the default
       // maxNumKpt = SIZE_MAX throws std::length_error there; a finite limit is required, and 4 buckets per axis need > 4 pixels
       if (det->max_kpt <= 0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "key point bucketing (uniformityRadius <= 0) needs a finite maxNumKpt > 0");
-    } else if (det->radius < 1.0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "uniformityRadius in (0, 1) is not supported (the occupancy map would take more than 225 bytes per pixel)");
+    } else if (!occupancy_fits(det->radius, w, h)) return fail(ctx, BRISK_ERR_UNSUPPORTED, kOccupancyTooLarge);
   } else if (det) {
     // The closed form of the lazy score cache (nms_logic.cuh) relies on every detected corner holding a score > 2 (such
     // cache entries are returned whatever threshold is asked, brisk-layer.cc:124-126).  A corner's score is its
@@ -869,7 +878,7 @@ int brisk_harris_detect_passed(brisk_ctx* ctx, brisk_detector* det, int n, int w
   if (det->octaves != 0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "passed key points are only defined for octaves == 0 (the reference writes out of bounds otherwise)");
   if (!(det->radius > 0.0)) {
     if (det->max_kpt <= 0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "key point bucketing (uniformityRadius <= 0) needs a finite maxNumKpt > 0");
-  } else if (det->radius < 1.0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "uniformityRadius in (0, 1) is not supported (the occupancy map would take more than 225 bytes per pixel)");
+  } else if (!occupancy_fits(det->radius, w, h)) return fail(ctx, BRISK_ERR_UNSUPPORTED, kOccupancyTooLarge);
   if (w < 8 || h < 8) return fail(ctx, BRISK_ERR_INVALID, "image too small");
   CU_OK(cudaSetDevice(ctx->device));
   memset(ctx->ms, 0, sizeof(ctx->ms));

@@ -580,10 +580,21 @@ def test_harris_passed_keypoints(ctx, oracle, golden, radius, max_kpt):
         det.detect(img, keypoints=bad)
 
 
+@pytest.mark.parametrize("octaves,radius,abs_thr,max_kpt", [(0, 0.5, 0.0, None), (2, 0.7, 20.0, None), (1, 0.25, 0.0, 500)])
+def test_harris_small_uniformity_radius(ctx, oracle, octaves, radius, abs_thr, max_kpt):
+    # radii below 1: occupancy maps of ceil(15 / radius)^2 bytes per pixel (here up to 3600)
+    img = bb.synthetic_frame(320, 240, 8)
+    want = oracle.harris_detect(img, octaves, radius, abs_thr, -1 if max_kpt is None else max_kpt)
+    assert len(want) > 100 and kp_equal(bb.ScaleSpaceFeatureDetector(octaves, radius, abs_thr, max_kpt, ctx=ctx).detect(img), want)
+
+
 def test_harris_unsupported(ctx):
     # bucketing with the default maxNumKpt = SIZE_MAX: the reference throws std::length_error (reserve)
     with pytest.raises(bb.BriskError):
         bb.ScaleSpaceFeatureDetector(4, 0.0, 20.0, ctx=ctx).detect(bb.synthetic_frame(320, 240, 1))
+    # an occupancy map beyond 2 GiB per layer is refused
+    with pytest.raises(bb.BriskError):
+        bb.ScaleSpaceFeatureDetector(0, 0.2, 20.0, ctx=ctx).detect(bb.synthetic_frame(1920, 1080, 1))
 
 
 @pytest.mark.parametrize("nbytes", [48, 64])

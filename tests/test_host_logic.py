@@ -113,6 +113,15 @@ def test_harris_logic_and_introsort_replay(emul_harris, oracle, golden, octaves,
         assert kp_equal(emul_harris(img, octaves, radius, abs_thr, max_kpt), oracle.harris_detect(img, octaves, radius, abs_thr, max_kpt))
 
 
+@pytest.mark.parametrize("octaves,radius,abs_thr,max_kpt", [(0, 0.5, 0.0, -1), (2, 0.7, 20.0, -1), (1, 0.25, 0.0, 500)])
+def test_harris_logic_small_uniformity_radius(emul_harris, oracle, ref, octaves, radius, abs_thr, max_kpt):
+    # radii below 1: occupancy maps of ceil(15 / radius)^2 bytes per pixel (small images only)
+    img = synthetic_frame(320, 240, 8)
+    want = ref.harris_detect(img, octaves, radius, abs_thr, max_kpt)
+    assert len(want) > 100 and kp_equal(oracle.harris_detect(img, octaves, radius, abs_thr, max_kpt), want)
+    assert kp_equal(emul_harris(img, octaves, radius, abs_thr, max_kpt), want)
+
+
 def test_capi_exports_every_declared_symbol():
     from ethzasl_brisk_b200 import build, lib_path
     build_lib = build.build()  # no-op when up to date; nvcc cross-compiles without a GPU
