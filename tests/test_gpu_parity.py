@@ -588,6 +588,28 @@ def test_harris_small_uniformity_radius(ctx, oracle, octaves, radius, abs_thr, m
     assert len(want) > 100 and kp_equal(bb.ScaleSpaceFeatureDetector(octaves, radius, abs_thr, max_kpt, ctx=ctx).detect(img), want)
 
 
+@pytest.mark.parametrize("kind", ["ast", "harris"])
+def test_make_set_tool_reproduces_reference_fixtures(tmp_path, golden, kind):
+    # tools/make_set.py writes what the reference's test-binary-equal.cc serialises; against the reference's own
+    # fixtures (rebuilt from the committed goldens in the same format) everything but `angle` must be identical
+    import subprocess
+    import sys
+    from conftest import ROOT
+    pgms = []
+    for i in (0, 1):
+        pgms.append(str(tmp_path / f"img{i + 1}.pgm"))
+        bb.write_pgm(pgms[-1], golden[f"image{i}"])
+    bb.write_set(tmp_path / "golden.set", [dict(path=pgms[i], image=golden[f"image{i}"], keypoints=golden[f"{kind}{i}_kps"],
+                                                descriptors=golden[f"{kind}{i}_desc"], blobs={"testImage": golden[f"image{i}"].tobytes()})
+                                           for i in (0, 1)])
+    tool = str(ROOT / "tools" / "make_set.py")
+    subprocess.run([sys.executable, tool, "--detector", kind, "-o", str(tmp_path / "ours.set"), *pgms], check=True)
+    r = subprocess.run([sys.executable, tool, "--compare", str(tmp_path / "ours.set"), str(tmp_path / "golden.set")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    ours = bb.read_set(tmp_path / "ours.set")
+    assert all(np.abs(ours[i]["keypoints"]["angle"] - golden[f"{kind}{i}_kps"]["angle"]).max() <= 1e-4 for i in (0, 1))
+
+
 def test_harris_unsupported(ctx):
     # bucketing with the default maxNumKpt = SIZE_MAX: the reference throws std::length_error (reserve)
     with pytest.raises(bb.BriskError):

@@ -122,6 +122,39 @@ def test_harris_logic_small_uniformity_radius(emul_harris, oracle, ref, octaves,
     assert kp_equal(emul_harris(img, octaves, radius, abs_thr, max_kpt), want)
 
 
+def test_set_and_pgm_io_round_trip(tmp_path, golden):
+    # the reference's serialized datasets (brisk/src/test/serialization.cc, bench-ds.cc:57-94) and its PGM images
+    import ethzasl_brisk_b200 as bb
+    entries = [dict(path=f"img{i}.pgm", image=golden[f"image{i}"], keypoints=golden[f"ast{i}_kps"], descriptors=golden[f"ast{i}_desc"],
+                    blobs={"testImage": golden[f"image{i}"].tobytes()}) for i in (0, 1)]
+    entries.append(dict(path="empty", image=np.zeros((8, 8), np.uint8), keypoints=np.zeros(0, KP_DTYPE),
+                        descriptors=np.zeros((0, 48), np.uint8), blobs={}))
+    bb.write_set(tmp_path / "a.set", entries)
+    back = bb.read_set(tmp_path / "a.set")
+    assert len(back) == 3
+    for e, b in zip(entries, back):
+        assert b["path"] == e["path"] and np.array_equal(b["image"], e["image"]) and kp_equal(b["keypoints"], e["keypoints"])
+        assert b["descriptors"].shape[0] == len(e["keypoints"]) and np.array_equal(b["descriptors"].ravel(), e["descriptors"].ravel())
+        assert b["blobs"] == e["blobs"]
+    bb.write_pgm(tmp_path / "a.pgm", golden["image0"])
+    assert np.array_equal(bb.read_pgm(tmp_path / "a.pgm"), golden["image0"])
+    with pytest.raises(ValueError):
+        (tmp_path / "cut.set").write_bytes((tmp_path / "a.set").read_bytes()[:-7])
+        bb.read_set(tmp_path / "cut.set")
+    # the reference's own fixtures: parse -> serialize is the identity on their bytes, and they hold the committed goldens
+    ref_dir = Path("/root/reference/brisk/src/test/test_data")
+    if ref_dir.exists():
+        for kind in ("ast", "harris"):
+            src = ref_dir / f"brisk_verification_{kind}.set"
+            parsed = bb.read_set(src)
+            bb.write_set(tmp_path / "b.set", parsed)
+            assert (tmp_path / "b.set").read_bytes() == src.read_bytes()
+            for i, e in enumerate(parsed):
+                assert kp_equal(e["keypoints"], golden[f"{kind}{i}_kps"]) and np.array_equal(e["descriptors"], golden[f"{kind}{i}_desc"])
+        img = bb.read_pgm(ref_dir / "img1.pgm")
+        assert img.shape == (640, 800)
+
+
 def test_capi_exports_every_declared_symbol():
     from ethzasl_brisk_b200 import build, lib_path
     build_lib = build.build()  # no-op when up to date; nvcc cross-compiles without a GPU

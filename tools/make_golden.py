@@ -10,9 +10,10 @@ per entry, the 800x640 input image, the keypoints (x, y, size, angle, response,
 octave, class_id) and the 48-byte descriptors.  The GPU box has no
 /root/reference, so tests read only the npz.
 """
-import struct
 import sys
 from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 import numpy as np
 
@@ -20,51 +21,9 @@ REF = Path("/root/reference/brisk/src/test/test_data")
 OUT = Path(__file__).resolve().parent.parent / "tests" / "golden" / "brisk_verification.npz"
 
 
-class Reader:
-    def __init__(self, buf):
-        self.b, self.o = buf, 0
-
-    def take(self, fmt):
-        v = struct.unpack_from("<" + fmt, self.b, self.o)
-        self.o += struct.calcsize("<" + fmt)
-        return v if len(v) > 1 else v[0]
-
-    def raw(self, n):
-        v = self.b[self.o:self.o + n]
-        self.o += n
-        return v
-
-    def string(self):
-        return self.raw(self.take("I")).decode()
-
-    def mat(self):
-        rows, cols, typ, esz = self.take("iiii")
-        data = self.raw(rows * cols * esz)
-        return rows, cols, typ, esz, data
-
-
 def parse_set(path):
-    r = Reader(path.read_bytes())
-    entries = []
-    for _ in range(r.take("I")):
-        name = r.string()
-        rows, cols, typ, esz, data = r.mat()
-        assert typ == 0 and esz == 1
-        img = np.frombuffer(data, np.uint8).reshape(rows, cols).copy()
-        nk = r.take("I")
-        kps = np.zeros(nk, dtype=[("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"),
-                                  ("response", "f4"), ("octave", "i4"), ("class_id", "i4")])
-        for i in range(nk):
-            angle, class_id, octave, x, y, response, size = r.take("fiiffff")
-            kps[i] = (x, y, size, angle, response, octave, class_id)
-        drows, dcols, dtyp, desz, ddata = r.mat()
-        desc = np.frombuffer(ddata, np.uint8).reshape(drows, dcols).copy()
-        for _ in range(r.take("I")):
-            r.string()
-            r.raw(r.take("I"))
-        entries.append((name, img, kps, desc))
-    assert r.o == len(r.b), (r.o, len(r.b))
-    return entries
+    from ethzasl_brisk_b200.setio import read_set
+    return [(e["path"], e["image"], e["keypoints"], e["descriptors"]) for e in read_set(path)]
 
 
 def main():

@@ -1,3 +1,4 @@
+"""Debug aid: tying corners per layer and per-stage times of one 1080p frame (needs a GPU)."""
 import sys, numpy as np, ctypes as C, time
 sys.path.insert(0,'.')
 import ethzasl_brisk_b200 as bb
