@@ -322,6 +322,75 @@ int check_image_args(brisk_ctx* ctx, const uint8_t* imgs, int n, int w, int h, s
   return BRISK_OK;
 }
 
+// Key-point lists in, key-point lists out (ComputeScale, passed key points): validation and staging of the caller's
+// host or device buffers, chunk by chunk on one slot.
+struct KpLists {
+  const brisk_keypoint* kps_in; const int32_t* counts_in; int cap_in;
+  brisk_keypoint* kps_out; int32_t* counts_out; int cap_out;
+  bool in_dev = false, cin_dev = false, out_dev = false, cout_dev = false, truncated = false;
+  std::vector<int32_t> h_cin;  // counts_in on the host
+  int in_max = 0;              // longest input list
+  const KeyPoint* d_in = nullptr; const int* d_cin = nullptr; KeyPoint* d_out = nullptr; int* d_cout = nullptr;  // current chunk
+
+  int init(brisk_ctx* ctx, int n, const char* empty_msg) {
+    if (!kps_in || !counts_in || cap_in <= 0 || !kps_out || !counts_out || cap_out <= 0) return fail(ctx, BRISK_ERR_INVALID, "bad key point arguments");
+    in_dev = is_device_ptr(kps_in); cin_dev = is_device_ptr(counts_in);
+    out_dev = is_device_ptr(kps_out); cout_dev = is_device_ptr(counts_out);
+    h_cin.resize(n);
+    if (cin_dev) {
+      CU_OK(cudaStreamSynchronize(ctx->stream));
+      CU_OK(cudaMemcpy(h_cin.data(), counts_in, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    } else if (n) memcpy(h_cin.data(), counts_in, (size_t)n * 4);
+    for (int f = 0; f < n; ++f) {
+      if (h_cin[f] < 0 || h_cin[f] > cap_in) return fail(ctx, BRISK_ERR_INVALID, "counts_in must be in [0, cap_in]");
+      if (h_cin[f] == 0) return fail(ctx, BRISK_ERR_UNSUPPORTED, empty_msg);
+      in_max = std::max(in_max, h_cin[f]);
+    }
+    return BRISK_OK;
+  }
+  int reserve(brisk_ctx* ctx, Slot& sl, size_t c_max) {
+    if (!in_dev) CU_OK(sl.kps_scratch.ensure(c_max * cap_in * 28));
+    if (!cin_dev) CU_OK(sl.scales.ensure(c_max * 4));
+    if (!out_dev) CU_OK(sl.kps.ensure(c_max * cap_out * 28));
+    if (!cout_dev) CU_OK(sl.counts.ensure(c_max * 4));
+    return BRISK_OK;
+  }
+  // device views of frames [f0, f0 + c); host lists are uploaded (only their used part)
+  int upload(brisk_ctx* ctx, Slot& sl, int f0, int c) {
+    d_in = reinterpret_cast<const KeyPoint*>(kps_in) + (size_t)f0 * cap_in;
+    d_cin = counts_in + f0;
+    if (!in_dev) {
+      for (int f = 0; f < c; ++f)
+        CU_OK(cudaMemcpyAsync(sl.kps_scratch.as<KeyPoint>() + (size_t)f * cap_in, kps_in + (size_t)(f0 + f) * cap_in,
+                              (size_t)h_cin[f0 + f] * 28, cudaMemcpyHostToDevice, sl.stream));
+      d_in = sl.kps_scratch.as<KeyPoint>();
+    }
+    if (!cin_dev) {
+      CU_OK(cudaMemcpyAsync(sl.scales.p, h_cin.data() + f0, (size_t)c * 4, cudaMemcpyHostToDevice, sl.stream));
+      d_cin = sl.scales.as<int>();
+    }
+    d_out = out_dev ? reinterpret_cast<KeyPoint*>(kps_out) + (size_t)f0 * cap_out : sl.kps.as<KeyPoint>();
+    d_cout = cout_dev ? counts_out + f0 : sl.counts.as<int>();
+    return BRISK_OK;
+  }
+  // waits for the chunk, returns its error flag, copies counts and the produced rows back
+  int download(brisk_ctx* ctx, Slot& sl, int chunk, int f0, int c, int* flag) {
+    CU_OK(cudaMemcpyAsync(sl.h_counts, d_cout, (size_t)c * 4, cudaMemcpyDeviceToHost, sl.stream));
+    CU_OK(cudaMemcpyAsync(sl.h_counts + chunk, sl.flag.p, 4, cudaMemcpyDeviceToHost, sl.stream));
+    CU_OK(cudaStreamSynchronize(sl.stream));
+    *flag = sl.h_counts[chunk];
+    if (!cout_dev) memcpy(counts_out + f0, sl.h_counts, (size_t)c * 4);
+    for (int f = 0; f < c; ++f) {
+      const int m = std::min(sl.h_counts[f], cap_out);
+      if (sl.h_counts[f] > cap_out) truncated = true;
+      if (m > 0 && !out_dev)
+        CU_OK(cudaMemcpyAsync(kps_out + (size_t)(f0 + f) * cap_out, d_out + (size_t)f * cap_out, (size_t)m * 28, cudaMemcpyDeviceToHost, sl.stream));
+    }
+    CU_OK(cudaStreamSynchronize(sl.stream));
+    return BRISK_OK;
+  }
+};
+
 // Core batch driver: detect and/or describe, chunk by chunk.
 int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const uint8_t* imgs, int n, int w, int h,
               size_t stride, size_t frame_pitch, const uint8_t* masks, brisk_keypoint* kps, int32_t* counts, int cap,
@@ -770,21 +839,12 @@ int brisk_compute_scale(brisk_ctx* ctx, brisk_detector* det, const uint8_t* imgs
     for (int i = 0; i < probe.n_layers; ++i)
       if (probe.L[i].w < 8 || probe.L[i].h < 8) return fail(ctx, BRISK_ERR_INVALID, "image too small: every pyramid layer must be at least 8x8");
   }
-  const bool in_dev = is_device_ptr(kps_in), cin_dev = is_device_ptr(counts_in);
-  const bool out_dev = is_device_ptr(kps_out), cout_dev = is_device_ptr(counts_out);
-  // the largest input list sizes the per-frame scratch (one slot per layer and provided point)
-  std::vector<int32_t> h_cin(n);
-  if (cin_dev) {
-    CU_OK(cudaStreamSynchronize(ctx->stream));
-    CU_OK(cudaMemcpy(h_cin.data(), counts_in, (size_t)n * 4, cudaMemcpyDeviceToHost));
-  } else memcpy(h_cin.data(), counts_in, (size_t)n * 4);
-  int in_max = 0;
-  for (int f = 0; f < n; ++f) {
-    if (h_cin[f] < 0 || h_cin[f] > cap_in) return fail(ctx, BRISK_ERR_INVALID, "counts_in must be in [0, cap_in]");
-    // an empty vector makes the reference detect instead (with the lower threshold of the map set to 0)
-    if (h_cin[f] == 0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "ComputeScale without key points runs the detector in the reference; use detect()");
-    in_max = std::max(in_max, h_cin[f]);
-  }
+  // the largest input list sizes the per-frame scratch (one slot per layer and provided point); an empty vector makes
+  // the reference detect instead (with the lower threshold of the map set to 0)
+  KpLists io{kps_in, counts_in, cap_in, kps_out, counts_out, cap_out};
+  rc = io.init(ctx, n, "ComputeScale without key points runs the detector in the reference; use detect()");
+  if (rc) return rc;
+  const int in_max = io.in_max;
   brisk_detector sized = *det;
   const int n_layers = det->octaves == 0 ? 1 : 2 * det->octaves;
   if ((long long)n_layers * in_max > (1ll << 26)) return fail(ctx, BRISK_ERR_UNSUPPORTED, "too many provided key points");
@@ -799,33 +859,19 @@ int brisk_compute_scale(brisk_ctx* ctx, brisk_detector* det, const uint8_t* imgs
   const PyramidGeom& g = plan.g;
   Slot& sl = ctx->slots[0];
   const size_t c_max = (size_t)plan.chunk;
-  if (!in_dev) CU_OK(sl.kps_scratch.ensure(c_max * cap_in * 28));
-  if (!cin_dev) CU_OK(sl.scales.ensure(c_max * 4));
-  if (!out_dev) CU_OK(sl.kps.ensure(c_max * cap_out * 28));
-  if (!cout_dev) CU_OK(sl.counts.ensure(c_max * 4));
+  rc = io.reserve(ctx, sl, c_max);
+  if (rc) return rc;
   if (!is_device_ptr(imgs)) CU_OK(sl.tight.ensure(c_max * ((size_t)w * h + 64)));
   CU_OK(sl.prov_base.ensure(c_max * (kMaxLayers + 1) * 4));
   std::vector<int> h_kept(c_max * kTieStride);
   CU_OK(cudaEventRecord(ctx->entry, ctx->stream));
   CU_OK(cudaStreamWaitEvent(sl.stream, ctx->entry, 0));
-  bool truncated = false, empty_layer = false, corner_overflow = false;
+  bool empty_layer = false, corner_overflow = false;
   const DetectWorkspace ws = slot_ws(plan, sl);
   for (int f0 = 0; f0 < n; f0 += plan.chunk) {
     const int c = std::min(plan.chunk, n - f0);
-    const KeyPoint* d_in = reinterpret_cast<const KeyPoint*>(kps_in) + (size_t)f0 * cap_in;
-    const int* d_cin = counts_in + f0;
-    if (!in_dev) {
-      for (int f = 0; f < c; ++f)
-        CU_OK(cudaMemcpyAsync(sl.kps_scratch.as<KeyPoint>() + (size_t)f * cap_in, kps_in + (size_t)(f0 + f) * cap_in,
-                              (size_t)h_cin[f0 + f] * 28, cudaMemcpyHostToDevice, sl.stream));
-      d_in = sl.kps_scratch.as<KeyPoint>();
-    }
-    if (!cin_dev) {
-      CU_OK(cudaMemcpyAsync(sl.scales.p, h_cin.data() + f0, (size_t)c * 4, cudaMemcpyHostToDevice, sl.stream));
-      d_cin = sl.scales.as<int>();
-    }
-    KeyPoint* d_out = out_dev ? reinterpret_cast<KeyPoint*>(kps_out) + (size_t)f0 * cap_out : sl.kps.as<KeyPoint>();
-    int* d_cout = cout_dev ? counts_out + f0 : sl.counts.as<int>();
+    rc = io.upload(ctx, sl, f0, c);
+    if (rc) return rc;
     CUtensorMap map;
     int write_l0 = 0;
     bool staged_tight = false;
@@ -834,7 +880,7 @@ int brisk_compute_scale(brisk_ctx* ctx, brisk_detector* det, const uint8_t* imgs
     CU_OK(launch_pyramid(map, g, ws.pyr, c, write_l0, sl.stream));
     CU_OK(cudaMemsetAsync(sl.flag.p, 0, 16, sl.stream));
     // which layers keep none of their frame's points?  Those run the detector (threshold map without lower bound).
-    CU_OK(launch_provided_count(g, ws, c, d_in, d_cin, cap_in, in_max, sl.stream));
+    CU_OK(launch_provided_count(g, ws, c, io.d_in, io.d_cin, cap_in, in_max, sl.stream));
     CU_OK(cudaMemcpyAsync(h_kept.data(), ws.n_ties, (size_t)c * kTieStride * 4, cudaMemcpyDeviceToHost, sl.stream));
     CU_OK(cudaStreamSynchronize(sl.stream));
     int with_fallback = 0;
@@ -845,26 +891,18 @@ int brisk_compute_scale(brisk_ctx* ctx, brisk_detector* det, const uint8_t* imgs
       CU_OK(launch_corner_lists(g, ws, c, sl.flag.as<int>(), sl.stream));
       ctx->launches += 2 * g.n_layers + 3;
     }
-    CU_OK(launch_provided_scale(g, ws, c, d_in, d_cin, cap_in, in_max, with_fallback, sl.prov_base.as<int>(), d_out, d_cout, cap_out,
-                                sl.flag.as<int>(), sl.stream));
+    CU_OK(launch_provided_scale(g, ws, c, io.d_in, io.d_cin, cap_in, in_max, with_fallback, sl.prov_base.as<int>(), io.d_out, io.d_cout,
+                                cap_out, sl.flag.as<int>(), sl.stream));
     ctx->launches += 7;
-    CU_OK(cudaMemcpyAsync(sl.h_counts, d_cout, (size_t)c * 4, cudaMemcpyDeviceToHost, sl.stream));
-    CU_OK(cudaMemcpyAsync(sl.h_counts + plan.chunk, sl.flag.p, 4, cudaMemcpyDeviceToHost, sl.stream));
-    CU_OK(cudaStreamSynchronize(sl.stream));
-    if (sl.h_counts[plan.chunk] == 3) empty_layer = true;
-    else if (sl.h_counts[plan.chunk]) corner_overflow = true;
-    if (!cout_dev) memcpy(counts_out + f0, sl.h_counts, (size_t)c * 4);
-    for (int f = 0; f < c; ++f) {
-      const int m = std::min(sl.h_counts[f], cap_out);
-      if (sl.h_counts[f] > cap_out) truncated = true;
-      if (m > 0 && !out_dev)
-        CU_OK(cudaMemcpyAsync(kps_out + (size_t)(f0 + f) * cap_out, d_out + (size_t)f * cap_out, (size_t)m * 28, cudaMemcpyDeviceToHost, sl.stream));
-    }
-    CU_OK(cudaStreamSynchronize(sl.stream));
+    int flag = 0;
+    rc = io.download(ctx, sl, plan.chunk, f0, c, &flag);
+    if (rc) return rc;
+    if (flag == 3) empty_layer = true;
+    else if (flag) corner_overflow = true;
   }
   if (empty_layer) return fail(ctx, BRISK_ERR_CUDA, "internal error: a layer without provided key points was not detected on");
   if (corner_overflow) return fail(ctx, BRISK_ERR_CAPACITY, "raw corner capacity exceeded on a layer without provided key points; raise it with brisk_detector_set_corner_capacity");
-  if (truncated) return fail(ctx, BRISK_ERR_CAPACITY, "key point capacity (cap_out) exceeded; counts hold the true numbers");
+  if (io.truncated) return fail(ctx, BRISK_ERR_CAPACITY, "key point capacity (cap_out) exceeded; counts hold the true numbers");
   return BRISK_OK;
 }
 
@@ -884,31 +922,19 @@ int brisk_harris_detect_passed(brisk_ctx* ctx, brisk_detector* det, int n, int w
   memset(ctx->ms, 0, sizeof(ctx->ms));
   ctx->launches = 0;
   if (n == 0) return BRISK_OK;
-  const bool in_dev = is_device_ptr(kps_in), cin_dev = is_device_ptr(counts_in);
-  const bool out_dev = is_device_ptr(kps_out), cout_dev = is_device_ptr(counts_out);
-  std::vector<int32_t> h_cin(n);
-  if (cin_dev) {
-    CU_OK(cudaStreamSynchronize(ctx->stream));
-    CU_OK(cudaMemcpy(h_cin.data(), counts_in, (size_t)n * 4, cudaMemcpyDeviceToHost));
-  } else memcpy(h_cin.data(), counts_in, (size_t)n * 4);
-  int in_max = 0;
-  for (int f = 0; f < n; ++f) {
-    if (h_cin[f] < 0 || h_cin[f] > cap_in) return fail(ctx, BRISK_ERR_INVALID, "counts_in must be in [0, cap_in]");
-    if (h_cin[f] == 0) return fail(ctx, BRISK_ERR_UNSUPPORTED, "an empty key point vector means detection; use detect()");
-    in_max = std::max(in_max, h_cin[f]);
-  }
+  KpLists io{kps_in, counts_in, cap_in, kps_out, counts_out, cap_out};
+  int rc = io.init(ctx, n, "an empty key point vector means detection; use detect()");
+  if (rc) return rc;
+  const int in_max = io.in_max;
   brisk_detector sized = *det;
   sized.corner_cap = in_max;
   Plan plan;
-  int rc = make_plan(ctx, &sized, nullptr, n, w, h, cap_out, &plan, false, false);
+  rc = make_plan(ctx, &sized, nullptr, n, w, h, cap_out, &plan, false, false);
   if (rc) return rc;
   const PyramidGeom& g = plan.g;
   Slot& sl = ctx->slots[0];
-  const size_t c_max = (size_t)plan.chunk;
-  if (!in_dev) CU_OK(sl.kps_scratch.ensure(c_max * cap_in * 28));
-  if (!cin_dev) CU_OK(sl.scales.ensure(c_max * 4));
-  if (!out_dev) CU_OK(sl.kps.ensure(c_max * cap_out * 28));
-  if (!cout_dev) CU_OK(sl.counts.ensure(c_max * 4));
+  rc = io.reserve(ctx, sl, (size_t)plan.chunk);
+  if (rc) return rc;
   CU_OK(cudaEventRecord(ctx->entry, ctx->stream));
   CU_OK(cudaStreamWaitEvent(sl.stream, ctx->entry, 0));
   HarrisWorkspace hw = plan.hw;
@@ -916,42 +942,22 @@ int brisk_harris_detect_passed(brisk_ctx* ctx, brisk_detector* det, int n, int w
   hw.scores = sl.h_scores.as<int>(); hw.pts = sl.h_pts.as<HPoint>(); hw.keep = sl.h_keep.as<uint8_t>();
   hw.sorted = sl.h_sorted.as<HPoint>(); hw.layer_kept = sl.h_layer_kept.as<int>(); hw.occ = sl.h_occ.as<uint8_t>();
   hw.surv = sl.h_surv.as<HPoint>(); hw.layer_surv = sl.h_layer_surv.as<int>();
-  bool truncated = false, bad_point = false;
+  bool bad_point = false;
   for (int f0 = 0; f0 < n; f0 += plan.chunk) {
     const int c = std::min(plan.chunk, n - f0);
-    const KeyPoint* d_in = reinterpret_cast<const KeyPoint*>(kps_in) + (size_t)f0 * cap_in;
-    const int* d_cin = counts_in + f0;
-    if (!in_dev) {
-      for (int f = 0; f < c; ++f)
-        CU_OK(cudaMemcpyAsync(sl.kps_scratch.as<KeyPoint>() + (size_t)f * cap_in, kps_in + (size_t)(f0 + f) * cap_in,
-                              (size_t)h_cin[f0 + f] * 28, cudaMemcpyHostToDevice, sl.stream));
-      d_in = sl.kps_scratch.as<KeyPoint>();
-    }
-    if (!cin_dev) {
-      CU_OK(cudaMemcpyAsync(sl.scales.p, h_cin.data() + f0, (size_t)c * 4, cudaMemcpyHostToDevice, sl.stream));
-      d_cin = sl.scales.as<int>();
-    }
-    KeyPoint* d_out = out_dev ? reinterpret_cast<KeyPoint*>(kps_out) + (size_t)f0 * cap_out : sl.kps.as<KeyPoint>();
-    int* d_cout = cout_dev ? counts_out + f0 : sl.counts.as<int>();
+    rc = io.upload(ctx, sl, f0, c);
+    if (rc) return rc;
     CU_OK(cudaMemsetAsync(sl.flag.p, 0, 16, sl.stream));
-    CU_OK(launch_harris_passed(g, hw, c, det->radius, det->max_kpt, d_in, d_cin, cap_in, in_max, d_out, d_cout, cap_out,
+    CU_OK(launch_harris_passed(g, hw, c, det->radius, det->max_kpt, io.d_in, io.d_cin, cap_in, in_max, io.d_out, io.d_cout, cap_out,
                                sl.flag.as<int>(), sl.stream));
     ctx->launches += 4;
-    CU_OK(cudaMemcpyAsync(sl.h_counts, d_cout, (size_t)c * 4, cudaMemcpyDeviceToHost, sl.stream));
-    CU_OK(cudaMemcpyAsync(sl.h_counts + plan.chunk, sl.flag.p, 4, cudaMemcpyDeviceToHost, sl.stream));
-    CU_OK(cudaStreamSynchronize(sl.stream));
-    if (sl.h_counts[plan.chunk] == 4) bad_point = true;
-    if (!cout_dev) memcpy(counts_out + f0, sl.h_counts, (size_t)c * 4);
-    for (int f = 0; f < c; ++f) {
-      const int m = std::min(sl.h_counts[f], cap_out);
-      if (sl.h_counts[f] > cap_out) truncated = true;
-      if (m > 0 && !out_dev)
-        CU_OK(cudaMemcpyAsync(kps_out + (size_t)(f0 + f) * cap_out, d_out + (size_t)f * cap_out, (size_t)m * 28, cudaMemcpyDeviceToHost, sl.stream));
-    }
-    CU_OK(cudaStreamSynchronize(sl.stream));
+    int flag = 0;
+    rc = io.download(ctx, sl, plan.chunk, f0, c, &flag);
+    if (rc) return rc;
+    if (flag == 4) bad_point = true;
   }
   if (bad_point) return fail(ctx, BRISK_ERR_INVALID, "a passed key point with response > 1e6 lies outside the image (or its response does not fit an int)");
-  if (truncated) return fail(ctx, BRISK_ERR_CAPACITY, "key point capacity (cap_out) exceeded; counts hold the true numbers");
+  if (io.truncated) return fail(ctx, BRISK_ERR_CAPACITY, "key point capacity (cap_out) exceeded; counts hold the true numbers");
   return BRISK_OK;
 }
 

@@ -127,6 +127,19 @@ def test_compute_scale_layers_without_points(ctx, oracle, golden, thresh, octave
         assert kp_equal(out[i, :oc[i]], oracle.compute_scale(imgs[i], lists[i], thresh, octaves))
 
 
+def test_compute_scale_full_size_1080p(ctx, oracle):
+    # BASELINE config 3's frame size: the key points the detector found, fed back through ComputeScale
+    img = bb.synthetic_frame(1920, 1080, 2000)
+    det = bb.BriskFeatureDetector(60, 4, ctx=ctx)
+    kps = det.detect(img)
+    got = det.compute_scale(img, kps)
+    assert len(kps) > 3000 and len(got) > len(kps)
+    assert kp_equal(got, oracle.compute_scale(img, kps, 60, 4))
+    # properties that hold at any size: octave is the layer that accepted the point, sizes follow the layer scale
+    assert got["octave"].min() >= 0 and got["octave"].max() <= 7 and np.all(np.diff(got["octave"]) >= 0)
+    assert np.all(got["size"] >= 12.0 * 0.5) and np.all(got["angle"] == -1.0)
+
+
 def test_compute_scale_batch_and_errors(ctx, oracle):
     from test_oracle_golden import _provided_points
     det = bb.BriskFeatureDetector(60, 3, ctx=ctx)
