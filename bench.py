@@ -348,6 +348,20 @@ def run_gpu(args):
                    "sample": f"{len(sample_frames)} frames drawn from the same {UNIQUE} distinct 1080p frames, unmodified reference (oracle/_ref), {cores} threads"}
     except Exception as e:  # the baseline is informative; never fail the bench on it
         cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    # ... and of the matcher: the reference's brisk::Hamming primitive in its k-successive-arg-min loop (brute-force-matcher.cc:
+    # 80-162), one std::thread per core over the queries, on a bounded slice of the same descriptors
+    knn_cpu = None
+    try:
+        from oracle import ref
+        if ref.available() and world == 1:
+            cores = host_cores()
+            cq, ct = q[:min(4096, args.knn_q)].cpu().numpy(), t[:min(1000000, args.knn_t)].cpu().numpy()
+            t0 = time.perf_counter()
+            ref.knn(cq, ct, 2, nthreads=cores)
+            knn_cpu = {"value": len(cq) * len(ct) / (time.perf_counter() - t0) / 1e9, "unit": "Gcmp/s", "cores": cores, "kind": "reference",
+                       "sample": f"{len(cq)} queries x {len(ct)} train rows of the same descriptors, k = 2, {cores} threads"}
+    except Exception as e:
+        knn_cpu = {"value": None, "unit": "Gcmp/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
@@ -358,7 +372,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roof, "stages": stage_report, "cpu_baseline": cpu, "clocks": clocks,
             "secondary": {"metric": "hamming_knn_k2_512bit", "value": gcmp, "unit": "Gcmp/s", "queries": args.knn_q, "train": args.knn_t,
-                          "ms": knn_ms / 3, "variants": knn_variants,
+                          "ms": knn_ms / 3, "variants": knn_variants, "cpu_baseline": knn_cpu,
                           "int8_TOPS": gcmp * 1024 / 1e3,
                           "note": "default = s8 x u8 IMMA (mma.sync m16n8k32) on byte-expanded bits, 512 MACs per comparison; "
                                   "tensor-pipe activity from ncu is in profiles/"}}
