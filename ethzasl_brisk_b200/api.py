@@ -297,7 +297,11 @@ class BriskFeature:
         self.detector = ScaleSpaceFeatureDetector(octaves, uniformityRadius, absoluteThreshold, maxNumKpt, ctx=self.ctx)
         self.extractor = BriskDescriptorExtractor(rotationInvariant, scaleInvariant, extractorVersion, ctx=self.ctx)
 
-    def detectAndCompute(self, image, mask=None, cap=65536):
+    def detectAndCompute(self, image, mask=None, cap=65536, keypoints=None):
+        """keypoints (useProvidedKeypoints = true): the detector re-filters them instead of detecting
+        (brisk-feature.h:80-93), then the extractor runs."""
+        if keypoints is not None and len(keypoints):
+            return self.extractor.compute(image, self.detector.detect(image, keypoints=keypoints))
         kps, counts, desc = detect_and_compute_batch(self.detector, self.extractor, image, cap=cap)
         n = int(counts[0])
         return kps[0, :n].copy(), desc[0, :n].copy()

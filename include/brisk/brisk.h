@@ -268,7 +268,10 @@ class BriskFeature {
   int descriptorType() const { return _briskExtractor.descriptorType(); }
   void detectAndCompute(const agast::Mat& image, const agast::Mat& mask, std::vector<agast::KeyPoint>& keypoints,
                         agast::Mat& descriptors, bool useProvidedKeypoints = false) {
-    if (!useProvidedKeypoints) { keypoints.clear(); _briskDetector.detect(image, keypoints, mask); }
+    // brisk-feature.h:80-93: the detector runs either way -- on provided key points it re-filters them
+    // ("use passed key points") instead of detecting
+    if (!useProvidedKeypoints) keypoints.clear();
+    _briskDetector.detect(image, keypoints, mask);
     _briskExtractor.compute(image, keypoints, descriptors);
   }
 

@@ -583,6 +583,10 @@ def test_harris_passed_keypoints(ctx, oracle, golden, radius, max_kpt):
     out, oc = det.detect_passed_batch(img.shape, kin, [len(lists[i]) for i in range(3)])
     for i in range(3):
         assert kp_equal(out[i, :oc[i]], oracle.harris_detect_passed(img.shape, lists[i], radius, mk))
+    # BriskFeature::detectAndCompute(useProvidedKeypoints = true): re-filter, then describe (brisk-feature.h:80-93)
+    k1, d1 = bb.BriskFeature(0, radius, 0.0, max_kpt, ctx=ctx).detectAndCompute(img, keypoints=lists[0])
+    k2, d2 = oracle.describe(img, oracle.harris_detect_passed(img.shape, lists[0], radius, mk))
+    assert len(k1) == len(k2) > 0 and np.array_equal(k1["x"], k2["x"]) and np.array_equal(k1["y"], k2["y"]) and np.array_equal(d1, d2)
     # refused: more than one layer, a point outside the image
     with pytest.raises(bb.BriskError):
         bb.ScaleSpaceFeatureDetector(1, 30.0, 0.0, ctx=ctx).detect(img, keypoints=lists[0])
