@@ -405,6 +405,20 @@ class Hamming:
         self.ctx._check(self.ctx._lib.brisk_hamming_distance(self.ctx._h, _ptr(a), _ptr(b), C.c_int64(1), nb, _ptr(d)))
         return int(d[0])
 
+    def pairs(self, a, b):
+        """Row-wise distances of two [n, bytes] arrays (counted over bytes // 16 whole 128-bit words, as the reference does)."""
+        a = np.ascontiguousarray(a, np.uint8)
+        b = np.ascontiguousarray(b, np.uint8)
+        assert a.ndim == 2 and a.shape == b.shape
+        d = np.zeros(len(a), np.int32)
+        self.ctx._check(self.ctx._lib.brisk_hamming_distance(self.ctx._h, _ptr(a), _ptr(b), C.c_int64(len(a)), a.shape[1], _ptr(d)))
+        return d
+
+    @staticmethod
+    def PopcntofXORed(signature1, signature2, numberOf128BitWords, ctx=None):
+        """Static form of the reference (hamming.h:79-91)."""
+        return Hamming(ctx)(signature1, signature2, 16 * int(numberOf128BitWords))
+
 
 class BruteForceMatcher:
     """brisk::BruteForceMatcher (reference brisk/include/brisk/brute-force-matcher.h:54-94): brute-force Hamming

@@ -1290,15 +1290,30 @@ int brisk_knn_merge_keys(brisk_ctx* ctx, const uint64_t* gathered_keys_dev, int 
 }
 
 int brisk_hamming_distance(brisk_ctx* ctx, const uint8_t* a, const uint8_t* b, int64_t n, int desc_bytes, int32_t* dist) {
-  // pairwise distance = 1-NN of a one-row train set, row by row; used by the
-  // parity tests of the distance primitive only (small n).
-  if (!ctx || !a || !b || !dist || n < 0) return fail(ctx, BRISK_ERR_INVALID, "bad arguments");
-  for (int64_t i = 0; i < n; ++i) {
-    int32_t idx = 0, d = 0;
-    int rc = brisk_hamming_knn(ctx, a + i * desc_bytes, 1, b + i * desc_bytes, 1, desc_bytes, 1, &idx, &d);
-    if (rc) return rc;
-    dist[i] = d;
+  if (!ctx || !a || !b || !dist || n < 0 || desc_bytes <= 0) return fail(ctx, BRISK_ERR_INVALID, "bad arguments");
+  CU_OK(cudaSetDevice(ctx->device));
+  if (n == 0) return BRISK_OK;
+  const size_t bytes = (size_t)n * desc_bytes;
+  const uint8_t *da = a, *db = b;
+  if (!is_device_ptr(a)) {
+    CU_OK(ctx->knn_q.ensure(std::max<size_t>(bytes, 16)));
+    CU_OK(cudaMemcpyAsync(ctx->knn_q.p, a, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    da = ctx->knn_q.as<uint8_t>();
   }
+  if (!is_device_ptr(b)) {
+    CU_OK(ctx->knn_t.ensure(std::max<size_t>(bytes, 16)));
+    CU_OK(cudaMemcpyAsync(ctx->knn_t.p, b, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    db = ctx->knn_t.as<uint8_t>();
+  }
+  const bool out_dev = is_device_ptr(dist);
+  int32_t* dd = dist;
+  if (!out_dev) {
+    CU_OK(ctx->knn_dist.ensure((size_t)n * 4));
+    dd = ctx->knn_dist.as<int32_t>();
+  }
+  CU_OK(launch_hamming_pairs(da, db, n, desc_bytes, dd, ctx->stream));
+  if (!out_dev) CU_OK(cudaMemcpyAsync(dist, dd, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_OK(cudaStreamSynchronize(ctx->stream));
   return BRISK_OK;
 }
 

@@ -340,4 +340,37 @@ cudaError_t launch_knn_unpack(const unsigned long long* keys, long long n, int32
   return cudaGetLastError();
 }
 
+// brisk::Hamming::operator()(a, b, size) on n descriptor pairs (reference hamming.h:101-113, hamming-inl.h:85-134):
+// popcount of the XOR over size / 16 whole 128-bit words -- bytes beyond the last whole word are not read.
+// One warp per pair, one 32-bit word per lane and step.
+__global__ void __launch_bounds__(256)
+hamming_pairs_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, long long n, int desc_bytes, int32_t* __restrict__ dist) {
+  const long long pair = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pair >= n) return;
+  const int words = (desc_bytes / 16) * 4;  // 32-bit words inside whole 128-bit words
+  const uint8_t* pa = a + pair * desc_bytes;
+  const uint8_t* pb = b + pair * desc_bytes;
+  const bool aligned = (((uintptr_t)pa | (uintptr_t)pb) & 3) == 0;
+  int d = 0;
+  for (int w = lane; w < words; w += 32) {
+    uint32_t x, y;
+    if (aligned) { x = reinterpret_cast<const uint32_t*>(pa)[w]; y = reinterpret_cast<const uint32_t*>(pb)[w]; }
+    else {
+      x = pa[4 * w] | (pa[4 * w + 1] << 8) | (pa[4 * w + 2] << 16) | ((uint32_t)pa[4 * w + 3] << 24);
+      y = pb[4 * w] | (pb[4 * w + 1] << 8) | (pb[4 * w + 2] << 16) | ((uint32_t)pb[4 * w + 3] << 24);
+    }
+    d += __popc(x ^ y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  if (lane == 0) dist[pair] = d;
+}
+
+cudaError_t launch_hamming_pairs(const uint8_t* a, const uint8_t* b, long long n, int desc_bytes, int32_t* dist, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  hamming_pairs_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(a, b, n, desc_bytes, dist);
+  return cudaGetLastError();
+}
+
 }  // namespace briskb200

@@ -130,6 +130,8 @@ int knn_mma_num_splits(long long nq, long long nt);
 cudaError_t launch_hamming_knn2_mma(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes,
                                     long long train_index_offset, unsigned long long* keys, unsigned long long* part,
                                     int splits, cudaStream_t stream);
+// brisk::Hamming::operator() on n pairs of desc_bytes-byte rows: popcount of the XOR over desc_bytes / 16 whole 128-bit words.
+cudaError_t launch_hamming_pairs(const uint8_t* a, const uint8_t* b, long long n, int desc_bytes, int32_t* dist, cudaStream_t stream);
 cudaError_t launch_knn_unpack(const unsigned long long* keys, long long n, int32_t* idx, int32_t* dist, cudaStream_t stream);
 cudaError_t launch_knn_merge(const unsigned long long* gathered, int n_shards, long long nq, int k, unsigned long long* out,
                              cudaStream_t stream);

@@ -291,6 +291,13 @@ class Hamming {
     detail::check(ctx, brisk_hamming_distance(ctx, a, b, 1, size, &d));
     return d;
   }
+  // hamming.h:79-91: the distance over `numberOf128BitWords` 16-byte words
+  static uint32_t PopcntofXORed(const unsigned char* signature1, const unsigned char* signature2, const int numberOf128BitWords) {
+    int32_t d = 0;
+    brisk_ctx* ctx = detail::context();
+    detail::check(ctx, brisk_hamming_distance(ctx, signature1, signature2, 1, 16 * numberOf128BitWords, &d));
+    return (uint32_t)d;
+  }
 };
 
 struct DMatch {  // == cv::DMatch

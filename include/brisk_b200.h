@@ -157,8 +157,9 @@ int brisk_debug_nms_state(brisk_ctx* ctx, brisk_detector* det, const uint8_t* im
 /* Diagnostic: corners per layer (up to 12) that went through IsMax2D's tie path, frame 0 of the last detect call. */
 int brisk_debug_nms_ties(brisk_ctx* ctx, int32_t* ties);
 
-/* brisk::Hamming::operator()(a, b, size) -- reference brisk/include/brisk/internal/hamming.h:101-113:
- * dist[i] = popcount(a[i] xor b[i]) over n descriptor pairs of desc_bytes each. */
+/* brisk::Hamming::operator()(a, b, size) -- reference brisk/include/brisk/internal/hamming.h:101-113,
+ * hamming-inl.h:85-134: dist[i] = popcount(a[i] xor b[i]) over n descriptor pairs of desc_bytes each (rows desc_bytes
+ * apart), counted over desc_bytes / 16 whole 128-bit words as the reference does (any size; trailing bytes are ignored). */
 int brisk_hamming_distance(brisk_ctx* ctx, const uint8_t* a, const uint8_t* b, int64_t n, int desc_bytes,
                            int32_t* dist);
 

@@ -340,6 +340,34 @@ def test_knn_edge_cases(ctx, oracle):
     assert bb.Hamming(ctx)(a, b) == 4 + 1 + 1
 
 
+def test_hamming_primitive(ctx):
+    # the reference's own known-answer test (test-popcount.cc:60-113): one 128-bit pair, bit loop vs primitive
+    d1 = np.zeros(16, np.uint8)
+    d2 = np.zeros(16, np.uint8)
+    for i, v in {0: 0x5, 3: 0x2, 6: 0x34, 8: 0x7, 10: 0x23, 13: 0x45, 15: 0x78}.items():
+        d1[i] = v
+    for i, v in {0: 0x22, 3: 0x78, 6: 0x12, 8: 0x32, 10: 0x1, 13: 0x23, 15: 0x75}.items():
+        d2[i] = v
+    want = int(np.unpackbits(d1 ^ d2).sum())
+    ham = bb.Hamming(ctx)
+    assert ham(d1, d2) == want and bb.Hamming.PopcntofXORed(d1, d2, 1, ctx=ctx) == want
+    # any size: size // 16 whole 128-bit words are counted (hamming.h:101-113), trailing bytes ignored; batches; unaligned rows
+    rng = np.random.default_rng(3)
+    for nbytes in (16, 32, 48, 64, 100, 128, 15, 1000):
+        a = rng.integers(0, 256, (257, nbytes), dtype=np.uint8)
+        b = rng.integers(0, 256, (257, nbytes), dtype=np.uint8)
+        used = (nbytes // 16) * 16
+        expect = np.unpackbits(a[:, :used] ^ b[:, :used], axis=1).sum(axis=1).astype(np.int32) if used else np.zeros(257, np.int32)
+        assert np.array_equal(ham.pairs(a, b), expect)
+        assert ham(a[5], b[5]) == expect[5]
+    import ctypes as C
+    import torch
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    out = torch.zeros(257, dtype=torch.int32, device="cuda")
+    ctx._check(ctx._lib.brisk_hamming_distance(ctx._h, bb.api._ptr(ta), bb.api._ptr(tb), C.c_int64(257), 1000, bb.api._ptr(out)))
+    assert np.array_equal(out.cpu().numpy(), expect)
+
+
 def test_knn_large_properties(ctx):
     # BASELINE config 5 shape at reduced size: idempotence (train == query -> distance 0 at own
     # index), sortedness, and agreement of a split train set with the unsplit one.
