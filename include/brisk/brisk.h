@@ -61,6 +61,11 @@ class BriskFeatureDetector {
   void detect(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, const agast::Mat& mask = agast::Mat()) const {
     detectImpl(image, keypoints, mask);
   }
+  // cv::Feature2D::detectAndCompute as the reference overrides it (brisk-feature-detector.h:69-74): detection only
+  virtual void detectAndCompute(const agast::Mat& image, const agast::Mat& mask, std::vector<agast::KeyPoint>& keypoints,
+                                agast::Mat& /*descriptors*/, bool /*useProvidedKeypoints*/ = false) {
+    detectImpl(image, keypoints, mask);
+  }
   // brisk-feature-detector.cc:87-92: re-examines the passed key points in every pyramid layer and replaces
   // them by the key points the scale-space checks accept (one per accepting layer; octave = layer index).
   // A layer that keeps none of the points is detected on instead, as in the reference (brisk-layer.cc:103-105).
@@ -176,6 +181,12 @@ class ScaleSpaceFeatureDetector {
     }
   }
 
+  // scale-space-feature-detector.h:92-97: detection only
+  virtual void detectAndCompute(const agast::Mat& image, const agast::Mat& mask, std::vector<agast::KeyPoint>& keypoints,
+                                agast::Mat& /*descriptors*/, bool /*useProvidedKeypoints*/ = false) {
+    detect(image, keypoints, mask);
+  }
+
  protected:
   size_t _octaves;
   double _uniformityRadius;
@@ -227,6 +238,11 @@ class BriskDescriptorExtractor {
     keypoints.resize(count);
     descriptors = agast::Mat::zeros(count, nb, CV_8UC1);
     if (count) std::memcpy(descriptors.data, buf.data(), (size_t)count * nb);
+  }
+  // cv::Feature2D::detectAndCompute as the reference overrides it (brisk-descriptor-extractor.h:120-125): extraction only
+  virtual void detectAndCompute(const agast::Mat& image, const agast::Mat& /*mask*/, std::vector<agast::KeyPoint>& keypoints,
+                                agast::Mat& descriptors, bool /*useProvidedKeypoints*/ = false) {
+    compute(image, keypoints, descriptors);
   }
   virtual void compute(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints,
                        std::vector<std::bitset<kDescriptorLength> >& descriptors) const {

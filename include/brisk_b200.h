@@ -1,7 +1,7 @@
 /* brisk_b200 -- C ABI of the B200-native BRISK hot path (libbrisk_b200.so).
  *
  * This is the drop-in boundary: the reference (ethz-asl/ethzasl_brisk) has no
- * FFI layer, its boundary is the C++ class surface of brisk/include/brisk/*.h.
+ * FFI layer, its boundary is the C++ class surface of the headers in brisk/include/brisk/.
  * The header-only C++ classes in include/brisk/ (same names, constructor
  * arguments and semantics) and the Python mirror ethzasl_brisk_b200/api.py are
  * thin hosts over these entry points.  Each entry point cites the reference

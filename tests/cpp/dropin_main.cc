@@ -2,6 +2,7 @@
 // uses the reference: detector + extractor per image, then a brute-force match.
 // usage: dropin_main <in.pgm> <out.bin> [<matches.bin>]
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 
@@ -54,6 +55,15 @@ int main(int argc, char** argv) {
   int pn = (int)pk.size();
   o.write(reinterpret_cast<char*>(&pn), 4);
   o.write(reinterpret_cast<char*>(pk.data()), (std::streamsize)pn * sizeof(agast::KeyPoint));
+  // the distance primitive's static form (hamming.h:79-91) and the detectAndCompute overrides
+  int ham = n > 1 ? (int)brisk::Hamming::PopcntofXORed(desc.data, desc.data + desc.step, nb / 16) : -1;
+  o.write(reinterpret_cast<char*>(&ham), 4);
+  std::vector<agast::KeyPoint> k2;
+  agast::Mat none, d2;
+  detector.detectAndCompute(img, agast::Mat(), k2, none);
+  extractor.detectAndCompute(img, agast::Mat(), k2, d2);
+  int same = k2.size() == kps.size() && d2.rows == desc.rows && std::memcmp(d2.data, desc.data, (size_t)desc.rows * nb) == 0;
+  o.write(reinterpret_cast<char*>(&same), 4);
   std::printf("%d key points, %d-byte descriptors, %d self matches, %d from ComputeScale, %d of the passed Harris points\n", n, nb, self, cn, pn);
   if (argc > 3) {
     // matcher surface: a two-image train collection with masks, knnMatch(k = 3) and radiusMatch(45)

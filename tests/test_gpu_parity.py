@@ -434,6 +434,8 @@ def test_cpp_dropin_classes(tmp_path, oracle, golden):
     off += 4 + cn * 28
     pn = int(np.frombuffer(raw[off:off + 4], np.int32)[0])
     pk = np.frombuffer(raw[off + 4:off + 4 + pn * 28], bb.KP_DTYPE)
+    off += 4 + pn * 28
+    ham, same_again = (int(v) for v in np.frombuffer(raw[off:off + 8], np.int32))
     assert hn == len(golden["harris0_kps"]) and np.array_equal(hk["x"], golden["harris0_kps"]["x"]) and np.array_equal(hd, golden["harris0_desc"])
     gk, gd = golden["ast0_kps"], golden["ast0_desc"]
     assert n == len(gk) and nb == 48 and self_matches == n
@@ -442,6 +444,8 @@ def test_cpp_dropin_classes(tmp_path, oracle, golden):
     assert np.array_equal(desc, gd)
     # ComputeScale on the detected key points (their `angle` was written by compute(); it is not read)
     assert kp_equal(cs, oracle.compute_scale(img, kps, 70, 3))
+    # Hamming::PopcntofXORed on the first two descriptors; detectAndCompute overrides reproduce detect() + compute()
+    assert ham == int(np.unpackbits(desc[0] ^ desc[1]).sum()) and same_again == 1
     # the Harris detector handed its own key points back (non-empty vector: re-filtering instead of detection)
     assert pn > 10 and kp_equal(pk, oracle.harris_detect_passed(img.shape, hk, 30.0, -1))
     # matcher surface: masked knnMatch over a two-image collection, radiusMatch with compactResult
