@@ -414,8 +414,9 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     // cache entries are returned whatever threshold is asked, brisk-layer.cc:124-126).  A corner's score is its
     // threshold-map value T, and a corner needs 9 ring pixels more than b = (max(T, 10) * thresh) / 100 away from the
     // centre inside a disk whose range is T, i.e. T >= thresh / 10 + 1: that is > 2 for every thresh >= 20.
-    if (det->thresh < 20 || det->thresh > 255)
-      return fail(ctx, BRISK_ERR_UNSUPPORTED, "AGAST threshold must be in [20, 255] (below 20 corners can score 2, which the reference's score cache does not keep)");
+    // Below 20 the same holds unless some corner actually scores <= 2 (rare down to thresh 10, common below): checked on the
+    // detected corners of every batch (launch_corner_score_check).
+    if (det->thresh < 1 || det->thresh > 255) return fail(ctx, BRISK_ERR_INVALID, "AGAST threshold must be in [1, 255]");
     if (det->octaves < 0 || 2 * det->octaves > kMaxLayers) return fail(ctx, BRISK_ERR_UNSUPPORTED, "octaves must be in [0, 6]");
     // suppressScaleNonmaxima = false (brisk-scale-space.cc:131-170): with one layer it is the single-layer branch
     // (:172-209) word for word; with more layers the reference indexes layer 0's corner list with the counts of
@@ -451,7 +452,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
   CU_OK(cudaEventRecord(ctx->entry, ctx->stream));
   for (int si = 0; si < plan.n_slots; ++si) CU_OK(cudaStreamWaitEvent(ctx->slots[si].stream, ctx->entry, 0));
 
-  bool truncated = false, corner_overflow = false, internal_error = false;
+  bool truncated = false, corner_overflow = false, internal_error = false, low_score = false;
   struct Pending { int f0 = 0, c = 0; bool active = false; KeyPoint* d_kps = nullptr; uint8_t* d_desc = nullptr; };
   Pending pend[2];
 
@@ -463,7 +464,9 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     pd.active = false;
     CU_OK(cudaStreamSynchronize(sl.stream));
     const int32_t flag = sl.h_counts[plan.chunk];
-    if (flag == 2) internal_error = true; else if (flag) corner_overflow = true;
+    if (sl.h_counts[plan.chunk + 1] == 5) low_score = true;
+    else if (flag == 2) internal_error = true;
+    else if (flag) corner_overflow = true;
     if (!counts_dev) memcpy(counts + pd.f0, sl.h_counts, (size_t)pd.c * 4);
     Timer tm(ctx, &sl);
     tm.mark(7);
@@ -564,6 +567,10 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       tm.mark(3);
       CU_OK(launch_corner_lists(g, ws, c, sl.flag.as<int>(), sl.stream));
       ctx->launches += 1 + g.n_layers;
+      if (det->thresh < 20) {
+        CU_OK(launch_corner_score_check(g, ws, c, sl.flag.as<int>() + 1, sl.stream));  // its own flag word
+        ctx->launches += 1;
+      }
       tm.mark(4);
       CU_OK(launch_agast_nms(g, ws, c, d_masks, mask_fs, mask_pitch, d_kps, d_counts, cap, sl.flag.as<int>(), sl.stream));
       ctx->launches += 5;
@@ -603,7 +610,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     if (plan.n_slots == 2) CU_OK(cudaEventRecord(sl.computed, sl.stream));
     // counts + error flag to pinned host memory; the row copies follow in finish()
     CU_OK(cudaMemcpyAsync(sl.h_counts, d_counts, (size_t)c * 4, cudaMemcpyDeviceToHost, sl.stream));
-    CU_OK(cudaMemcpyAsync(sl.h_counts + plan.chunk, sl.flag.p, 4, cudaMemcpyDeviceToHost, sl.stream));
+    CU_OK(cudaMemcpyAsync(sl.h_counts + plan.chunk, sl.flag.p, 8, cudaMemcpyDeviceToHost, sl.stream));
     tm.mark(8);
     pend[si].f0 = f0; pend[si].c = c; pend[si].active = true; pend[si].d_kps = d_kps; pend[si].d_desc = d_desc;
     // drain the OTHER slot while this chunk computes
@@ -614,6 +621,9 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     CU_OK(cudaStreamSynchronize(ctx->slots[si].stream));
     collect_timing(si);
   }
+  if (low_score)
+    return fail(ctx, BRISK_ERR_UNSUPPORTED, "a detected corner scores <= 2 (possible for thresh < 20 only): the reference's score cache does not keep such scores "
+                                            "and its result becomes order dependent; not supported");
   if (internal_error) return fail(ctx, BRISK_ERR_CUDA, "internal error: tie resolution did not converge");
   if (corner_overflow) return fail(ctx, BRISK_ERR_CAPACITY, "raw corner capacity exceeded; raise it with brisk_detector_set_corner_capacity");
   if (truncated) return fail(ctx, BRISK_ERR_CAPACITY, "key point capacity (cap) exceeded; counts hold the true numbers");

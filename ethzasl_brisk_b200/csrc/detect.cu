@@ -325,6 +325,28 @@ corner_fill_kernel(LayerGeom L, int layer, long long frame_elems, const uint16_t
   }
 }
 
+// Guard for AGAST thresholds below 20: the closed form of the lazy score cache (nms_logic.cuh) needs every detected
+// corner to hold a score > 2 (only such cache entries are sticky, brisk-layer.cc:124-126).  For thresh >= 20 that is
+// guaranteed; below, it is checked on the actual corners: *flag = 5 when one of them scores <= 2.
+__global__ void __launch_bounds__(256)
+corner_score_check_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ flag) {
+  const int frame = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = min(ws.layer_start[(long long)frame * (kMaxLayers + 1) + g.n_layers], ws.corner_cap);
+  if (k >= n) return;
+  const uint32_t c = ws.corners[(long long)frame * ws.corner_cap + k];
+  const int x = c & 0x1fff, y = (c >> 13) & 0x1fff, layer = c >> 26;
+  const LayerGeom& L = g.L[layer];
+  const int T = ws.cm[(long long)frame * g.frame_elems + L.off + (long long)y * L.pitch + x] & kCmT;
+  if (T <= 2) atomicExch(flag, 5);
+}
+
+cudaError_t launch_corner_score_check(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int* flag, cudaStream_t stream) {
+  dim3 grid((ws.corner_cap + 255) / 256, n_frames);
+  corner_score_check_kernel<<<grid, 256, 0, stream>>>(g, ws, flag);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_row_scan(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int* overflow_flag, cudaStream_t stream) {
   row_scan_kernel<<<n_frames, 1024, 0, stream>>>(ws.rowcnt, ws.total_rows, g, ws, overflow_flag);
   return cudaGetLastError();

@@ -38,6 +38,9 @@ cudaError_t launch_agast_detect(const PyramidGeom& g, const DetectWorkspace& ws,
 // Row prefix sums and ordered corner lists.
 cudaError_t launch_corner_lists(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int* overflow_flag,
                                 cudaStream_t stream);
+// After the corner lists: *flag = 5 when a detected corner scores <= 2 (possible only for thresh < 20; such a corner's
+// cache entry would not be sticky and the NMS closed form would not apply).
+cudaError_t launch_corner_score_check(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int* flag, cudaStream_t stream);
 // Scale-space NMS + refinement -> ordered key points [frame][kp_cap], counts[frame].
 cudaError_t launch_agast_nms(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, const uint8_t* masks,
                              long long mask_frame_stride, int mask_pitch, KeyPoint* out, int* counts, int kp_cap,

@@ -78,6 +78,7 @@ extern "C" int emul_agast_detect_ex(const uint8_t* image, int w, int h, int thre
       for (int x = 3; x < l.w - 3; ++x) {
         const int T = thrmap_px(l.img.data(), l.pitch, x, y);
         if (agast_is_corner(l.img.data(), l.pitch, x, y, T, thresh)) {
+          if (T <= 2) return -400;  // corner_score_check_kernel: the closed form needs sticky corner scores (thresh < 20 only)
           l.cm[(size_t)y * l.pitch + x] = (uint16_t)T;
           l.cx.push_back(x); l.cy.push_back(y);
         }

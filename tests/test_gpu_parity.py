@@ -73,12 +73,13 @@ def test_golden_ast_fixture(ctx, golden, i):
     assert np.array_equal(d, gd)
 
 
-@pytest.mark.parametrize("thresh,octaves", [(60, 4), (70, 3), (40, 2), (70, 0), (60, 1), (30, 4), (20, 3), (24, 4)])
+@pytest.mark.parametrize("thresh,octaves", [(60, 4), (70, 3), (40, 2), (70, 0), (60, 1), (30, 4), (20, 3), (24, 4), (15, 3), (10, 4)])
 def test_detect_bit_exact(ctx, oracle, golden, thresh, octaves):
+    # thresholds below 20 are served while no detected corner scores <= 2 (none does on these images down to 10)
     det = bb.BriskFeatureDetector(thresh, octaves, ctx=ctx)
-    det.set_corner_capacity(200000)
+    det.set_corner_capacity(400000)
     for img in (golden["image0"], bb.synthetic_frame(752, 480, 1000), bb.synthetic_frame(500, 333, 3)):
-        assert kp_equal(det.detect(img), oracle.agast_detect(img, thresh, octaves))
+        assert kp_equal(det.detect(img, cap=400000), oracle.agast_detect(img, thresh, octaves, cap=1 << 20))
 
 
 def test_detect_without_scale_suppression_single_layer(ctx, oracle, ref, golden):
@@ -194,12 +195,17 @@ def test_detect_empty_and_flat(ctx):
     assert kps.shape[0] == 0 and counts.shape[0] == 0
 
 
-def test_unsupported_configurations_fail_loudly(ctx):
+def test_unsupported_configurations_fail_loudly(ctx, golden):
     img = bb.synthetic_frame(320, 240, 1)
-    for bad in (bb.BriskFeatureDetector(19, 4, ctx=ctx), bb.BriskFeatureDetector(60, 7, ctx=ctx),
+    for bad in (bb.BriskFeatureDetector(0, 4, ctx=ctx), bb.BriskFeatureDetector(256, 4, ctx=ctx), bb.BriskFeatureDetector(60, 7, ctx=ctx),
                 bb.BriskFeatureDetector(60, 4, False, ctx=ctx)):
         with pytest.raises(bb.BriskError):
             bad.detect(img)
+    # thresh < 20: refused only when a detected corner really scores <= 2 (the reference's cache does not keep such scores)
+    low = bb.BriskFeatureDetector(5, 3, ctx=ctx)
+    low.set_corner_capacity(400000)
+    with pytest.raises(bb.BriskError, match="scores <= 2"):
+        low.detect(golden["image0"], cap=400000)
     with pytest.raises(bb.BriskError):
         bb.BriskDescriptorExtractor(True, True, 3, ctx=ctx)
 

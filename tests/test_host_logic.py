@@ -29,7 +29,7 @@ def emul():
         h, w = img.shape
         k = np.zeros(cap, KP_DTYPE)
         n = handle.emul_agast_detect(img.ctypes.data_as(C.c_void_p), w, h, thresh, octaves, k.ctypes.data_as(C.c_void_p), cap)
-        return k[:n].copy()
+        return n if n < 0 else k[:n].copy()
 
     def compute_scale(img, kps, thresh, octaves, cap=1 << 18):
         img = np.ascontiguousarray(img, np.uint8)
@@ -55,6 +55,16 @@ def test_parallel_nms_formulation_golden(emul, oracle, golden, thresh, octaves):
 def test_parallel_nms_formulation_synthetic(emul, oracle, seed, w, h, thresh, octaves):
     img = synthetic_frame(w, h, seed)
     assert kp_equal(emul(img, thresh, octaves), oracle.agast_detect(img, thresh, octaves))
+
+
+@pytest.mark.parametrize("thresh,octaves", [(19, 3), (15, 4), (10, 2)])
+def test_parallel_nms_formulation_low_thresholds(emul, oracle, golden, thresh, octaves):
+    # below 20 the closed form still holds as long as no detected corner scores <= 2 (checked on the data by
+    # corner_score_check_kernel); on these images none does down to thresh 10
+    for img in (golden["image0"], synthetic_frame(500, 333, 3)):
+        assert kp_equal(emul(img, thresh, octaves, cap=1 << 20), oracle.agast_detect(img, thresh, octaves, cap=1 << 20))
+    # ... and below 10 such corners exist: refused, not guessed
+    assert emul(golden["image0"], 5, 3) == -400
 
 
 def test_parallel_nms_formulation_tie_heavy(emul, oracle):
