@@ -1,5 +1,7 @@
 """Debug aid: tying corners per layer and per-stage times of one 1080p frame (needs a GPU)."""
-import sys, numpy as np, ctypes as C, time
+import sys
+
+import numpy as np
 sys.path.insert(0,'.')
 import ethzasl_brisk_b200 as bb
 from ethzasl_brisk_b200.api import _ptr
