@@ -165,6 +165,129 @@ def test_set_and_pgm_io_round_trip(tmp_path, golden):
         assert img.shape == (640, 800)
 
 
+@pytest.fixture(scope="module")
+def emul_describe():
+    src = ROOT / "tests" / "host_emul" / "emul_describe.cc"
+    lib = ROOT / "tests" / "host_emul" / "libemul_describe.so"
+    csrc = ROOT / "ethzasl_brisk_b200" / "csrc"
+    deps = [src, csrc / "pattern.cc", csrc / "pattern.h", csrc / "brisk_pattern_data.inc"] + list(csrc.glob("*.cuh"))
+    if not lib.exists() or any(d.stat().st_mtime > lib.stat().st_mtime for d in deps):
+        subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-msse2", "-ffp-contract=off", "-fPIC", "-shared",
+                        "-Wno-unknown-pragmas", "-o", str(lib), str(src), str(csrc / "pattern.cc")], check=True)
+    handle = C.CDLL(str(lib))
+
+    def describe(img, kps, rot=True, scale=True, version=2, pattern_scale=1.0):
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        k = np.ascontiguousarray(kps, KP_DTYPE).copy()
+        nb = C.c_int(0)
+        flat = np.zeros(max(len(k), 1) * 256, np.uint8)
+        n = handle.emul_describe(img.ctypes.data_as(C.c_void_p), w, h, k.ctypes.data_as(C.c_void_p), len(k), int(rot), int(scale),
+                                 int(version), C.c_float(pattern_scale), flat.ctypes.data_as(C.c_void_p), C.byref(nb))
+        assert n >= 0
+        return k[:n].copy(), flat[:n * nb.value].reshape(n, nb.value).copy()
+    return describe
+
+
+@pytest.mark.parametrize("version,ps,rot,scale", [(2, 1.0, True, True), (1, 1.0, True, True), (2, 0.5, True, True), (2, 1.0, False, True),
+                                                   (2, 1.0, True, False), (1, 0.7, True, True), (2, 1.3, True, True)])
+def test_descriptor_logic(emul_describe, oracle, golden, version, ps, rot, scale):
+    # describe_cull_kernel + describe_kernel run serially on the CPU with the kernels' own sampler (2x2-block integral
+    # layout, tabulated constants), host-built pattern tables and size breaks: key points, angles and descriptor bytes
+    # must equal the oracle's -- including the angle, which is the same double atan2 here
+    rng = np.random.default_rng(5)
+    for img in (golden["image0"], synthetic_frame(500, 333, 3)):
+        kp = oracle.agast_detect(img, 45, 4)
+        given = kp.copy()
+        given["angle"] = rng.uniform(-359, 719, len(kp)).astype(np.float32)  # the range in which the reference is defined
+        for k in (kp, given, kp[:0]):
+            k1, d1 = emul_describe(img, k, rot, scale, version, ps)
+            k2, d2 = oracle.describe(img, k, rot, scale, version, ps)
+            assert kp_equal(k1, k2) and np.array_equal(d1.ravel(), d2.ravel())
+
+
+def test_randomized_sweep_describe(emul_describe, oracle, ref):
+    rng = np.random.default_rng(20261020)
+    for _ in range(40):
+        w, h = int(rng.integers(120, 420)), int(rng.integers(120, 330))
+        img = _sweep_image(rng, w, h)
+        m = 300
+        k = np.zeros(m, KP_DTYPE)
+        k["x"], k["y"] = rng.uniform(0, w, m), rng.uniform(0, h, m)
+        k["size"] = 10.0 ** rng.uniform(0.3, 2.2, m)  # all 64 scale indices, most large ones culled at the border
+        k["angle"] = np.where(rng.integers(0, 2, m) == 1, -1.0, rng.uniform(-359, 719, m))
+        k["class_id"] = np.arange(m)
+        version, ps = (int(rng.choice([1, 2])), float(rng.choice([1.0, 0.6, 1.4])))
+        rot, scale = bool(rng.integers(0, 2)), bool(rng.integers(0, 2))
+        want_k, want_d = ref.describe(img, k, rot, scale, version, ps)
+        k2, d2 = oracle.describe(img, k, rot, scale, version, ps)
+        assert kp_equal(k2, want_k) and np.array_equal(d2.ravel(), want_d.ravel()), (w, h, version, ps, rot, scale)
+        k1, d1 = emul_describe(img, k, rot, scale, version, ps)
+        assert kp_equal(k1, want_k) and np.array_equal(d1.ravel(), want_d.ravel()), (w, h, version, ps, rot, scale)
+
+
+def _sweep_image(rng, w, h):
+    kind = int(rng.integers(0, 3))
+    if kind == 0:
+        return synthetic_frame(w, h, int(rng.integers(0, 10000)))
+    if kind == 1:  # quantised noise: plateaus of equal scores
+        return (rng.integers(0, 4, (h, w)) * 60 + rng.integers(0, 8, (h, w))).astype(np.uint8)
+    return rng.integers(0, 256, (h, w)).astype(np.uint8)
+
+
+def test_randomized_sweep_agast(emul, oracle, ref):
+    # odd sizes (all column regimes of the samplers, tiny top layers), thresholds and depths drawn at random: the compiled
+    # reference, the oracle and the device logic compiled for the host must agree on every case
+    rng = np.random.default_rng(20261017)
+    for _ in range(120):
+        octaves = int(rng.integers(0, 5))
+        lo = max(40, 12 * 2 ** max(octaves - 1, 0) + 16)
+        w, h = int(rng.integers(lo, 420)), int(rng.integers(lo, 330))
+        thresh = int(rng.integers(20, 95))
+        img = _sweep_image(rng, w, h)
+        want = ref.agast_detect(img, thresh, octaves, cap=1 << 20)
+        assert kp_equal(oracle.agast_detect(img, thresh, octaves, cap=1 << 20), want), (w, h, thresh, octaves)
+        got = emul(img, thresh, octaves, cap=1 << 20)
+        assert not isinstance(got, int) and kp_equal(got, want), (w, h, thresh, octaves)
+
+
+def test_randomized_sweep_compute_scale(emul, oracle, ref):
+    # ComputeScale on random images / depths / thresholds (also below 20: the threshold only matters on layers that fall
+    # back to detection) with 1 to 400 provided points, fractional or integral
+    rng = np.random.default_rng(20261019)
+    for _ in range(150):
+        octaves = int(rng.integers(0, 5))
+        lo = max(40, 12 * 2 ** max(octaves - 1, 0) + 16)
+        w, h = int(rng.integers(lo, 420)), int(rng.integers(lo, 330))
+        thresh = int(rng.integers(5, 95))
+        img = _sweep_image(rng, w, h)
+        m = int(rng.choice([1, 3, 40, 400]))
+        k = np.zeros(m, KP_DTYPE)
+        # a few rows away from the bottom: there the compiled reference reads its ring pixels past the image buffer
+        k["x"], k["y"], k["class_id"] = rng.uniform(0, w, m), rng.uniform(0, h - 4, m), np.arange(m)
+        if rng.integers(0, 2):
+            k["x"], k["y"] = np.floor(k["x"]), np.floor(k["y"])
+        want = ref.compute_scale(img, k, thresh, octaves, cap=1 << 20)
+        assert kp_equal(oracle.compute_scale(img, k, thresh, octaves, cap=1 << 20), want), (w, h, thresh, octaves, m)
+        got = emul.compute_scale(img, k, thresh, octaves, cap=1 << 20)
+        assert not isinstance(got, int) and kp_equal(got, want), (w, h, thresh, octaves, m)
+
+
+def test_randomized_sweep_harris(emul_harris, oracle, ref):
+    rng = np.random.default_rng(20261018)
+    for _ in range(120):
+        octaves = int(rng.integers(0, 5))
+        lo = max(40, 12 * 2 ** max(octaves - 1, 0) + 16)
+        w, h = int(rng.integers(lo, 420)), int(rng.integers(lo, 330))
+        radius = float(rng.choice([30.0, 10.0, 5.0, 2.5, 1.0, 17.3]))
+        abs_thr = float(rng.choice([0.0, 20.0, 1000.0, 1e6]))
+        max_kpt = int(rng.choice([-1, 50, 300, 2000]))
+        img = _sweep_image(rng, w, h)
+        want = ref.harris_detect(img, octaves, radius, abs_thr, max_kpt)
+        assert kp_equal(oracle.harris_detect(img, octaves, radius, abs_thr, max_kpt), want), (w, h, octaves, radius, abs_thr, max_kpt)
+        assert kp_equal(emul_harris(img, octaves, radius, abs_thr, max_kpt), want), (w, h, octaves, radius, abs_thr, max_kpt)
+
+
 def test_capi_exports_every_declared_symbol():
     from ethzasl_brisk_b200 import build, lib_path
     build_lib = build.build()  # no-op when up to date; nvcc cross-compiles without a GPU
