@@ -332,6 +332,24 @@ def test_knn_bit_exact(ctx, oracle, nbytes, k):
     assert i1[3, 0] == 100 and d1[3, 0] == 0
 
 
+def test_reference_match_test_homography(ctx, golden):
+    # the reference's own matching test (test-match.cc:50-116) end to end on the GPU: BriskFeatureDetector(70, 2) + BRISK2 on
+    # both images, best match per query; every match with Hamming distance < 50 must agree with H_1to2 within 5 px
+    H = np.array([[8.7976964e-01, 3.1245438e-01, -3.9430589e+01], [-1.8389418e-01, 9.3847198e-01, 1.5315784e+02],
+                  [1.9641425e-04, -1.6015275e-05, 1.0000000e+00]])
+    det = bb.BriskFeatureDetector(70, 2, ctx=ctx)
+    ext = bb.BriskDescriptorExtractor(ctx=ctx)
+    k1, d1 = ext.compute(golden["image0"], det.detect(golden["image0"]))
+    k2, d2 = ext.compute(golden["image1"], det.detect(golden["image1"]))
+    idx, dist = bb.BruteForceMatcher(ctx=ctx).knn(d1, d2, 1)
+    good = np.flatnonzero(dist[:, 0] < 50)
+    p = (H @ np.stack([k1["x"][good], k1["y"][good], np.ones(len(good))]).astype(np.float64))
+    p = p[:2] / p[2]
+    t = idx[good, 0]
+    err = np.hypot(p[0] - k2["x"][t], p[1] - k2["y"][t])
+    assert len(good) > 50 and np.all(err <= 5)
+
+
 def test_knn_edge_cases(ctx, oracle):
     m = bb.BruteForceMatcher(ctx=ctx)
     q = bb.random_descriptors(5, 64, 1)
