@@ -19,6 +19,46 @@ struct HL {
 };
 }  // namespace
 
+namespace {
+// harris_sort_kernel (gcc_sort.cuh: libstdc++'s std::sort replayed) followed by harris_uniformity_kernel (radius > 0) or
+// harris_bucketing_kernel (radius <= 0; run here point by point, the kernel takes the sorted points 32 at a time with the
+// same per-bucket quota): the thinning step of one layer.
+std::vector<HPoint> thin_points(std::vector<HPoint> pts, double radius, int w, int h, long long max_kpt) {
+  std::vector<HPoint> keep;
+  if (pts.empty()) return keep;
+  gcc_sort(pts.data(), (int)pts.size());
+  if (!(radius > 0.0)) {
+    const unsigned step_u = 1u + (unsigned)(w - 1) / 4u, step_v = 1u + (unsigned)(h - 1) / 4u;
+    const unsigned quota = (unsigned)((unsigned long long)max_kpt / 16ull);
+    unsigned cnt[16] = {};
+    for (const HPoint& p : pts) {
+      const unsigned b = (p.x / step_u) * 4u + p.y / step_v;
+      if (cnt[b] < quota) { ++cnt[b]; keep.push_back(p); }
+    }
+    return keep;
+  }
+  const float max_score = (float)pts[0].score;
+  const float scaling = (float)(15.0 / (double)(float)radius);
+  const int orows = (int)(h * ceil((double)scaling) + 32), ocols = (int)(w * ceil((double)scaling) + 32);
+  std::vector<uint8_t> occ((size_t)orows * ocols + 64, 0);
+  for (const HPoint& p : pts) {
+    const int cy = (int)((float)(int)p.y * scaling + 16.0f), cx = (int)((float)(int)p.x * scaling + 16.0f);
+    const float nsc1 = uniformity_nsc1(p.score, max_score);
+    if ((double)nsc1 < (double)occ[(size_t)cy * ocols + cx]) continue;
+    const float nsc = 0.99f * nsc1;
+    for (int y = 0; y < 31; ++y)
+      for (int x = 0; x < 31; ++x) {
+        uint8_t& o = occ[(size_t)(cy + y - 15) * ocols + cx + x - 15];
+        const int v = (int)o + uniformity_stamp(x, y, nsc);
+        o = (uint8_t)(v > 255 ? 255 : v);
+      }
+    keep.push_back(p);
+    if ((long long)keep.size() == max_kpt) break;
+  }
+  return keep;
+}
+}  // namespace
+
 extern "C" int emul_harris_detect(const uint8_t* image, int w, int h, int octaves, double radius, double abs_thr,
                                   long long max_kpt, KeyPoint* out, int cap) {
   const int n = octaves * 2 > 1 ? octaves * 2 : 1;
@@ -68,8 +108,6 @@ extern "C" int emul_harris_detect(const uint8_t* image, int w, int h, int octave
         l.sc[(size_t)y * l.w + x] = harris_response(harris_smooth(qa), harris_smooth(qb), harris_smooth(qc));
       }
   }
-  const double r = radius == 0 ? 1 : radius;
-  if (!(radius > 0.0)) return -1;  // bucketing not implemented
   int total = 0;
   for (int i = 0; i < n; ++i) {
     HL& l = L[i];
@@ -104,26 +142,7 @@ extern "C" int emul_harris_detect(const uint8_t* image, int w, int h, int octave
       pts.swap(kept);
     }
     if (pts.empty()) continue;
-    gcc_sort(pts.data(), (int)pts.size());
-    const float max_score = (float)pts[0].score;
-    const float scaling = (float)(15.0 / (double)(float)r);
-    const int orows = (int)(l.h * ceil((double)scaling) + 32), ocols = (int)(l.w * ceil((double)scaling) + 32);
-    std::vector<uint8_t> occ((size_t)orows * ocols + 64, 0);
-    std::vector<HPoint> keep;
-    for (const HPoint& p : pts) {
-      const int cy = (int)((float)(int)p.y * scaling + 16.0f), cx = (int)((float)(int)p.x * scaling + 16.0f);
-      const float nsc1 = uniformity_nsc1(p.score, max_score);
-      if ((double)nsc1 < (double)occ[(size_t)cy * ocols + cx]) continue;
-      const float nsc = 0.99f * nsc1;
-      for (int y = 0; y < 31; ++y)
-        for (int x = 0; x < 31; ++x) {
-          uint8_t& o = occ[(size_t)(cy + y - 15) * ocols + cx + x - 15];
-          const int v = (int)o + uniformity_stamp(x, y, nsc);
-          o = (uint8_t)(v > 255 ? 255 : v);
-        }
-      keep.push_back(p);
-      if ((long long)keep.size() == max_kpt) break;
-    }
+    std::vector<HPoint> keep = thin_points(pts, radius, l.w, l.h, max_kpt);
     for (const HPoint& p : keep) {
       auto S = [&](int u, int v) { return (double)l.sc[(size_t)v * l.w + u]; };
       const int u = p.x, v = p.y;
@@ -139,3 +158,29 @@ extern "C" int emul_harris_detect(const uint8_t* image, int w, int h, int octave
   }
   return total;
 }
+
+// detect() on a non-empty key-point vector, one layer (harris_import_kernel, sort, thinning, harris_emit_passed_kernel).
+// Returns -4 for a passed point outside the image (the C ABI reports BRISK_ERR_INVALID).
+extern "C" int emul_harris_passed(int w, int h, double radius, long long max_kpt, const KeyPoint* in, int n_in, KeyPoint* out, int cap) {
+  std::vector<HPoint> pts;
+  for (int j = 0; j < n_in; ++j) {
+    const KeyPoint& kp = in[j];
+    if (!((double)kp.response > 1e6)) continue;
+    if (!(kp.response < 2147483648.0f) || !(kp.x >= 0.0f && kp.x < (float)w && kp.y >= 0.0f && kp.y < (float)h)) return -4;
+    pts.push_back(HPoint{(int)kp.response, (unsigned short)(int)kp.x, (unsigned short)(int)kp.y});
+  }
+  if (pts.empty()) {
+    for (int j = 0; j < n_in && j < cap; ++j) out[j] = in[j];
+    return n_in;
+  }
+  const std::vector<HPoint> keep = thin_points(pts, radius, w, h, max_kpt);
+  int total = 0;
+  for (const HPoint& p : keep) {
+    KeyPoint k;
+    k.x = (float)(int)p.x; k.y = (float)(int)p.y; k.size = 12.0f; k.angle = -1.0f; k.response = (float)p.score; k.octave = 0; k.class_id = -1;
+    if (total < cap) out[total] = k;
+    ++total;
+  }
+  return total;
+}
+

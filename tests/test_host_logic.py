@@ -112,6 +112,14 @@ def emul_harris():
         n = handle.emul_harris_detect(img.ctypes.data_as(C.c_void_p), w, h, octaves, C.c_double(radius), C.c_double(abs_thr),
                                       C.c_longlong(max_kpt), k.ctypes.data_as(C.c_void_p), cap)
         return k[:n].copy()
+
+    def passed(shape, kps, radius, max_kpt=-1, cap=1 << 18):
+        kin = np.ascontiguousarray(kps, KP_DTYPE)
+        k = np.zeros(cap, KP_DTYPE)
+        n = handle.emul_harris_passed(int(shape[1]), int(shape[0]), C.c_double(radius), C.c_longlong(max_kpt), kin.ctypes.data_as(C.c_void_p),
+                                      len(kin), k.ctypes.data_as(C.c_void_p), cap)
+        return n if n < 0 else k[:n].copy()
+    detect.passed = passed
     return detect
 
 
@@ -279,13 +287,29 @@ def test_randomized_sweep_harris(emul_harris, oracle, ref):
         octaves = int(rng.integers(0, 5))
         lo = max(40, 12 * 2 ** max(octaves - 1, 0) + 16)
         w, h = int(rng.integers(lo, 420)), int(rng.integers(lo, 330))
-        radius = float(rng.choice([30.0, 10.0, 5.0, 2.5, 1.0, 17.3]))
+        radius = float(rng.choice([30.0, 10.0, 5.0, 2.5, 1.0, 17.3, 0.0, -1.0]))
         abs_thr = float(rng.choice([0.0, 20.0, 1000.0, 1e6]))
-        max_kpt = int(rng.choice([-1, 50, 300, 2000]))
+        max_kpt = int(rng.choice([-1, 50, 300, 2000])) if radius > 0 else int(rng.choice([16, 100, 400, 3000]))  # bucketing needs a limit
         img = _sweep_image(rng, w, h)
         want = ref.harris_detect(img, octaves, radius, abs_thr, max_kpt)
         assert kp_equal(oracle.harris_detect(img, octaves, radius, abs_thr, max_kpt), want), (w, h, octaves, radius, abs_thr, max_kpt)
         assert kp_equal(emul_harris(img, octaves, radius, abs_thr, max_kpt), want), (w, h, octaves, radius, abs_thr, max_kpt)
+
+
+@pytest.mark.parametrize("radius,max_kpt", [(30.0, -1), (8.0, -1), (3.0, 150), (0.0, 400), (-1.0, 90), (15.0, 40)])
+def test_harris_passed_keypoints_logic(emul_harris, oracle, golden, radius, max_kpt):
+    # "use passed key points": import gate / truncation, std::sort replay, thinning, unrefined emit -- as the GPU path does it
+    from test_oracle_golden import _passed_points
+    shape = golden["image0"].shape
+    for k in (_passed_points(shape, 3000, 1), _passed_points(shape, 700, 2, True), _passed_points(shape, 20, 3), _passed_points(shape, 40000, 4)):
+        got = emul_harris.passed(shape, k, radius, max_kpt)
+        assert not isinstance(got, int) and kp_equal(got, oracle.harris_detect_passed(shape, k, radius, max_kpt))
+    low = _passed_points(shape, 50, 5)
+    low["response"] = 999999.0
+    assert kp_equal(emul_harris.passed(shape, low, radius, max_kpt), low)
+    bad = _passed_points(shape, 5, 6)
+    bad["x"][0], bad["response"][0] = shape[1] + 5.0, 5.0e6
+    assert emul_harris.passed(shape, bad, radius, max_kpt) == -4
 
 
 def test_capi_exports_every_declared_symbol():
