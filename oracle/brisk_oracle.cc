@@ -9,8 +9,8 @@
 //
 // Pinning: tests/test_oracle_golden.py checks this file against the reference's
 // own golden fixtures (brisk_verification_{ast,harris}.set, committed as
-// tests/golden/brisk_verification.npz) and tests/test_oracle_vs_ref.py checks it
-// stage by stage against the unmodified reference compiled into oracle/_ref.
+// tests/golden/brisk_verification.npz) and, in the same file (`*_vs_ref` tests) and in the seeded random sweeps of
+// tests/test_host_logic.py, stage by stage against the unmodified reference compiled into oracle/_ref.
 //
 // NB: this file includes <math.h>, which in C++ also exposes the float
 // overloads of log/sqrt/atan2 in the global namespace; the reference's

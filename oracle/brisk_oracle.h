@@ -5,7 +5,7 @@
  * Pinned against (a) the reference's golden fixtures
  * (tests/golden/brisk_verification.npz, extracted from
  * brisk/src/test/test_data/brisk_verification_{ast,harris}.set) and (b) the
- * unmodified reference compiled into oracle/_ref (tests/test_oracle_*.py).
+ * unmodified reference compiled into oracle/_ref (tests/test_oracle_golden.py, tests/test_host_logic.py).
  */
 #ifndef BRISK_ORACLE_H_
 #define BRISK_ORACLE_H_
