@@ -328,6 +328,10 @@ def run_gpu(args):
         real = 2 * W * H + 16 * W * H
         stage_report["integral"]["hbm_traffic_GBps"] = real * n / (compute_stages["integral"] * 1e-3) / 1e9
         stage_report["integral"]["hbm_traffic_frac_of_peak"] = stage_report["integral"]["hbm_traffic_GBps"] / peak
+    if stage_report.get("describe", {}).get("ms_per_step", 0) > 0:
+        # describe is gather bound, not HBM bound -- its meaningful rate is key points per second (132 box-filter
+        # samples each); ncu of the round: L1 71 %, L2 51 % of peak, 46 % of the stall samples on dependent global loads
+        stage_report["describe"]["keypoints_per_s"] = kp_total / (stage_report["describe"]["ms_per_step"] * 1e-3)
     if top in NCU_DRAM_BYTES_PER_FRAME:
         roof["traffic"] = NCU_DRAM_BYTES_PER_FRAME[top] * n
         roof["traffic_note"] = ("ncu dram bytes per frame x frames of the step (captures: profiles/r01_ncu_full_top_kernels_v14.txt, "
