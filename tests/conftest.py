@@ -37,6 +37,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_provided():
+    """Outputs of the compiled reference for ComputeScale / passed key points, see tools/make_golden_provided.py."""
+    return np.load(ROOT / "tests" / "golden" / "provided_keypoints.npz")
+
+
+@pytest.fixture(scope="session")
 def oracle():
     """CPU restatement of the reference (oracle/brisk_oracle.cc), built on demand."""
     from oracle import restate

@@ -141,6 +141,19 @@ def test_compute_scale_full_size_1080p(ctx, oracle):
     assert np.all(got["size"] >= 12.0 * 0.5) and np.all(got["angle"] == -1.0)
 
 
+def test_provided_keypoints_golden_fixture(ctx, golden, golden_provided):
+    # outputs of the compiled reference, committed as tests/golden/provided_keypoints.npz (tools/make_golden_provided.py)
+    from test_oracle_golden import COMPUTE_SCALE_GOLDEN, PASSED_GOLDEN
+    img = golden["image0"]
+    for i, (thresh, octaves) in enumerate(COMPUTE_SCALE_GOLDEN):
+        det = bb.BriskFeatureDetector(thresh, octaves, ctx=ctx)
+        det.set_corner_capacity(300000)
+        assert kp_equal(det.compute_scale(img, golden_provided[f"cs{i}_in"], cap=400000), golden_provided[f"cs{i}_out"])
+    for i, (radius, max_kpt) in enumerate(PASSED_GOLDEN):
+        det = bb.ScaleSpaceFeatureDetector(0, radius, 0.0, None if max_kpt < 0 else max_kpt, ctx=ctx)
+        assert kp_equal(det.detect(img, keypoints=golden_provided[f"hp{i}_in"]), golden_provided[f"hp{i}_out"])
+
+
 def test_compute_scale_batch_and_errors(ctx, oracle):
     from test_oracle_golden import _provided_points
     det = bb.BriskFeatureDetector(60, 3, ctx=ctx)

@@ -140,6 +140,20 @@ def test_harris_passed_keypoints_vs_ref(oracle, ref, golden, radius, max_kpt):
     assert kp_equal(oracle.harris_detect_passed(img.shape, low, radius, max_kpt), low)
 
 
+# (thresh, octaves) / (radius, maxNumKpt) of the cases in tests/golden/provided_keypoints.npz (tools/make_golden_provided.py)
+COMPUTE_SCALE_GOLDEN = [(60, 4), (70, 3), (30, 5), (70, 0)]
+PASSED_GOLDEN = [(30.0, -1), (3.0, 150), (0.0, 400)]
+
+
+def test_provided_keypoints_golden(oracle, golden, golden_provided):
+    # the committed reference outputs (no compiled reference needed): ComputeScale and "use passed key points"
+    img = golden["image0"]
+    for i, (thresh, octaves) in enumerate(COMPUTE_SCALE_GOLDEN):
+        assert kp_equal(oracle.compute_scale(img, golden_provided[f"cs{i}_in"], thresh, octaves), golden_provided[f"cs{i}_out"])
+    for i, (radius, max_kpt) in enumerate(PASSED_GOLDEN):
+        assert kp_equal(oracle.harris_detect_passed(img.shape, golden_provided[f"hp{i}_in"], radius, max_kpt), golden_provided[f"hp{i}_out"])
+
+
 def test_agast_mask_vs_ref(oracle, ref, golden):
     img = golden["image0"]
     mask = np.zeros_like(img)
