@@ -312,6 +312,18 @@ def test_harris_passed_keypoints_logic(emul_harris, oracle, golden, radius, max_
     assert emul_harris.passed(shape, bad, radius, max_kpt) == -4
 
 
+def test_provided_keypoints_golden_logic(emul, emul_harris, golden, golden_provided):
+    # the device logic against the committed outputs of the compiled reference (tests/golden/provided_keypoints.npz)
+    from test_oracle_golden import COMPUTE_SCALE_GOLDEN, PASSED_GOLDEN
+    img = golden["image0"]
+    for i, (thresh, octaves) in enumerate(COMPUTE_SCALE_GOLDEN):
+        got = emul.compute_scale(img, golden_provided[f"cs{i}_in"], thresh, octaves)
+        assert not isinstance(got, int) and kp_equal(got, golden_provided[f"cs{i}_out"])
+    for i, (radius, max_kpt) in enumerate(PASSED_GOLDEN):
+        got = emul_harris.passed(img.shape, golden_provided[f"hp{i}_in"], radius, max_kpt)
+        assert not isinstance(got, int) and kp_equal(got, golden_provided[f"hp{i}_out"])
+
+
 def test_capi_exports_every_declared_symbol():
     from ethzasl_brisk_b200 import build, lib_path
     build_lib = build.build()  # no-op when up to date; nvcc cross-compiles without a GPU
