@@ -38,7 +38,7 @@ def golden():
 
 @pytest.fixture(scope="session")
 def golden_provided():
-    """Outputs of the compiled reference for ComputeScale / passed key points, see tools/make_golden_provided.py."""
+    """Outputs of the compiled reference for ComputeScale / passed key points, see tests/golden/make_provided_keypoints.py."""
     return np.load(ROOT / "tests" / "golden" / "provided_keypoints.npz")
 
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Verbose stage-by-stage parity check of the CUDA path against the oracle
-(run on a GPU box: `python tools/gpu_check.py`).  Prints diffs instead of
+(run on a GPU box: `python tests/gpu_check.py`; test infrastructure, not collected by pytest).  Prints diffs instead of
 asserting, for debugging; the asserting versions live in tests/."""
 import sys
 import time

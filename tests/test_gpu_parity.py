@@ -142,7 +142,7 @@ def test_compute_scale_full_size_1080p(ctx, oracle):
 
 
 def test_provided_keypoints_golden_fixture(ctx, golden, golden_provided):
-    # outputs of the compiled reference, committed as tests/golden/provided_keypoints.npz (tools/make_golden_provided.py)
+    # outputs of the compiled reference, committed as tests/golden/provided_keypoints.npz (tests/golden/make_provided_keypoints.py)
     from test_oracle_golden import COMPUTE_SCALE_GOLDEN, PASSED_GOLDEN
     img = golden["image0"]
     for i, (thresh, octaves) in enumerate(COMPUTE_SCALE_GOLDEN):

@@ -140,7 +140,7 @@ def test_harris_passed_keypoints_vs_ref(oracle, ref, golden, radius, max_kpt):
     assert kp_equal(oracle.harris_detect_passed(img.shape, low, radius, max_kpt), low)
 
 
-# (thresh, octaves) / (radius, maxNumKpt) of the cases in tests/golden/provided_keypoints.npz (tools/make_golden_provided.py)
+# (thresh, octaves) / (radius, maxNumKpt) of the cases in tests/golden/provided_keypoints.npz (tests/golden/make_provided_keypoints.py)
 COMPUTE_SCALE_GOLDEN = [(60, 4), (70, 3), (30, 5), (70, 0)]
 PASSED_GOLDEN = [(30.0, -1), (3.0, 150), (0.0, 400)]
 
