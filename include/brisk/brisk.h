@@ -48,8 +48,8 @@ static_assert(sizeof(agast::KeyPoint) == sizeof(brisk_keypoint), "KeyPoint must 
 // brisk/src/brisk-feature-detector.cc:69-92.
 class BriskFeatureDetector {
  public:
-  BriskFeatureDetector(int thresh, int octaves = 3, bool suppressScaleNonmaxima = true)
-      : threshold(thresh), octaves(octaves), m_suppress(suppressScaleNonmaxima) {}
+  BriskFeatureDetector(int thresh, int octaves_ = 3, bool suppressScaleNonmaxima = true)
+      : threshold(thresh), octaves(octaves_), m_suppress(suppressScaleNonmaxima) {}
   virtual ~BriskFeatureDetector() { if (det_) brisk_detector_destroy(det_); }
   BriskFeatureDetector(const BriskFeatureDetector&) = delete;
   BriskFeatureDetector& operator=(const BriskFeatureDetector&) = delete;
