@@ -70,7 +70,10 @@ class Context:
     def __init__(self, device=0, stream=None, workspace_limit=None, timing=False):
         self._lib = load_library()
         self._h = C.c_void_p()
-        sp = C.c_void_p(int(stream)) if stream else None
+        # stream=None: the context creates a private non-blocking stream.  Any other value is the caller's stream handle
+        # (e.g. torch.cuda.current_stream().cuda_stream); handle 0, the default stream, is passed as cudaStreamLegacy (0x1),
+        # because a NULL handle means "create one" in brisk_ctx_create.  Inputs must be complete on that stream.
+        sp = None if stream is None else C.c_void_p(int(stream) or 1)
         rc = self._lib.brisk_ctx_create(int(device), sp, C.byref(self._h))
         if rc != 0:
             raise BriskError(rc, "brisk_ctx_create failed (no usable CUDA device?)")
@@ -168,6 +171,19 @@ def _frames(images):
     return a, n, h, w, w, w * h
 
 
+def _mask_frames(masks, frames):
+    """Masks share the images' geometry in the C ABI (same n, h, w, row stride and frame pitch): validated here."""
+    if masks is None:
+        return None
+    m, n, h, w, stride, fp = _frames(masks)
+    _, n2, h2, w2, stride2, fp2 = frames
+    if (n, h, w) != (n2, h2, w2):
+        raise ValueError(f"mask shape {(n, h, w)} differs from the image shape {(n2, h2, w2)}")
+    if (stride, fp) != (stride2, fp2):
+        raise ValueError("mask strides differ from the image strides: pass a contiguous mask (or one laid out like the images)")
+    return m
+
+
 class BriskFeatureDetector:
     """brisk::BriskFeatureDetector(thresh, octaves=3, suppressScaleNonmaxima=true)."""
 
@@ -184,9 +200,7 @@ class BriskFeatureDetector:
     def detect_batch(self, images, masks=None, cap=16384, out=None):
         """images [n,h,w] u8 -> (kps [n,cap] structured, counts [n])."""
         a, n, h, w, stride, fp = _frames(images)
-        m = None
-        if masks is not None:
-            m = _frames(masks)[0]
+        m = _mask_frames(masks, (a, n, h, w, stride, fp))
         if out is None:
             kps = np.zeros((n, cap), KP_DTYPE)
             counts = np.zeros(n, np.int32)
@@ -378,7 +392,7 @@ def detect_and_compute_batch(detector, extractor, images, masks=None, cap=16384,
     ctx = detector.ctx
     assert extractor.ctx is ctx
     a, n, h, w, stride, fp = _frames(images)
-    m = None if masks is None else _frames(masks)[0]
+    m = _mask_frames(masks, (a, n, h, w, stride, fp))
     if out is None:
         kps = np.zeros((n, cap), KP_DTYPE)
         counts = np.zeros(n, np.int32)

@@ -179,7 +179,10 @@ describe_cull_kernel(PatternDev pat, int w, int h, const KeyPoint* __restrict__ 
   __shared__ int s_warp[8];
   __shared__ int s_base;
   const int frame = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = min(counts[frame], kp_cap);
+  // A list that did not fit into kp_cap slots is truncated, i.e. not the reference's key-point set: the frame keeps
+  // its true count (> kp_cap), nothing of it is described and the call reports BRISK_ERR_CAPACITY.
+  if (counts[frame] > kp_cap) return;
+  const int n = counts[frame];
   const KeyPoint* src = kps + (long long)frame * kp_cap;
   KeyPoint* dst = kps_out + (long long)frame * kp_cap;
   int* sdst = scales_out + (long long)frame * kp_cap;
@@ -260,7 +263,7 @@ describe_kernel(PatternDev pat, const uint8_t* __restrict__ imgs, long long fram
   __shared__ int s_val[kDescWarps][kMaxPoints];
   const int frame = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int k = blockIdx.x * kDescWarps + warp;
-  if (k >= counts[frame]) return;
+  if (k >= counts[frame] || counts[frame] > kp_cap) return;
   const long long slot = (long long)frame * kp_cap + k;
   const KeyPoint kp = kps_in[slot];
   const int scale = scales[slot];

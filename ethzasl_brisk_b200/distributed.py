@@ -66,8 +66,11 @@ def sharded_knn(matcher, query, train_shard, k, global_offset, group=None):
     import torch.distributed as dist
     nq = query.shape[0]
     keys = torch.empty((nq, k), dtype=torch.int64, device=query.device)
-    matcher.knn_keys(query, train_shard, k, global_offset, keys)
+    matcher.knn_keys(query, train_shard, k, global_offset, keys)  # returns with the keys complete (it synchronises)
     gathered = all_gather_keys(keys, group)
+    if gathered.is_cuda:
+        # the collective is ordered on torch's stream only; the merge kernel runs on the context's stream
+        torch.cuda.current_stream(gathered.device).synchronize()
     idx = torch.empty((nq, k), dtype=torch.int32, device=query.device)
     dst = torch.empty((nq, k), dtype=torch.int32, device=query.device)
     matcher.merge_keys(gathered, dist.get_world_size(group), nq, k, idx, dst)

@@ -45,7 +45,9 @@ typedef enum {
 } brisk_status;
 
 /* Context: device, stream, workspaces.  `stream` is a cudaStream_t to run on
- * (e.g. the current torch stream) or NULL for a private non-blocking stream. */
+ * (e.g. the current torch stream) or NULL for a private non-blocking stream.  The default stream has handle 0 == NULL:
+ * pass cudaStreamLegacy ((void*)0x1) or cudaStreamPerThread ((void*)0x2) to name it.  Work of a call is ordered after
+ * what the caller queued on that stream; device inputs produced on OTHER streams must be complete before the call. */
 int brisk_ctx_create(int device, void* stream, brisk_ctx** out);
 void brisk_ctx_destroy(brisk_ctx* ctx);
 const char* brisk_last_error(const brisk_ctx* ctx);

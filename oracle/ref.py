@@ -196,6 +196,47 @@ def knn(q, t, k, nthreads=1):
     return idx, dist
 
 
+def _matcher(q, trains, masks, k, radius, compact):
+    q = np.ascontiguousarray(q, np.uint8)
+    nb = q.shape[1]
+    tr = [np.ascontiguousarray(t, np.uint8).reshape(-1, nb) for t in trains]
+    n = len(tr)
+    tp = (C.c_void_p * n)(*[t.ctypes.data if len(t) else None for t in tr])
+    nts = np.array([len(t) for t in tr], np.int32)
+    mp, keep = None, []
+    if masks:
+        for m, t in zip(masks, tr):
+            keep.append(None if m is None or m.size == 0 else np.ascontiguousarray(m, np.uint8).reshape(len(q), len(t)))
+        mp = (C.c_void_p * n)(*[m.ctypes.data if m is not None else None for m in keep])
+    f = lib().ref_matcher
+    f.restype = C.c_int64
+    cap = 1 << 16
+    while True:
+        out = np.zeros(cap, np.int32)
+        need = f(_p(q), len(q), nb, n, tp, _p(nts), mp, int(k), C.c_float(radius), int(bool(compact)), _p(out), C.c_int64(cap))
+        if need <= cap:
+            break
+        cap = int(need)
+    pos, res = 1, []
+    for _ in range(int(out[0])):
+        c = int(out[pos]); pos += 1
+        rec = out[pos:pos + 4 * c].reshape(c, 4)
+        res.append([(int(r[0]), int(r[1]), int(r[2]), float(r[3:4].view(np.float32)[0])) for r in rec])
+        pos += 4 * c
+    return res
+
+
+def knn_match(q, trains, k, masks=None, compact=False):
+    """brisk::BruteForceMatcher::knnMatch (the reference class itself, brute-force-matcher.cc:59-68,80-162) over a train
+    collection: list (per query) of (queryIdx, trainIdx, imgIdx, distance)."""
+    return _matcher(q, trains, masks, k, -1.0, compact)
+
+
+def radius_match(q, trains, max_distance, masks=None, compact=False):
+    """brisk::BruteForceMatcher::radiusMatch (brute-force-matcher.cc:70-78,164-214)."""
+    return _matcher(q, trains, masks, 0, float(max_distance), compact)
+
+
 def bench_detect_describe(imgs, harris=False, thresh=60, octaves=4, radius=30.0, abs_thr=20.0, nthreads=1):
     """-> (seconds, total described keypoints) for imgs [n, h, w] u8."""
     imgs = np.ascontiguousarray(imgs, np.uint8)

@@ -44,6 +44,7 @@
 #include <brisk/brisk-feature-detector.h>
 #include <brisk/harris-score-calculator.h>
 #include <brisk/scale-space-feature-detector.h>
+#include <brisk/brute-force-matcher.h>
 #undef private
 #undef protected
 #include <brisk/internal/harris-scores.h>
@@ -339,10 +340,49 @@ int ref_hamming(const uint8_t* a, const uint8_t* b, int nbytes) {
   return hm(aa, bb, nbytes);
 }
 
+// brisk::BruteForceMatcher itself (brute-force-matcher.cc compiled unmodified against the shim's
+// cv::DescriptorMatcher): knnMatch (radius < 0) or radiusMatch over a train collection with optional
+// per-image masks [nq][nt_i] (masks == NULL: none; masks[i] == NULL: an empty Mat).  Output, as int32 words:
+// number of lists, then per list its length and (queryIdx, trainIdx, imgIdx, distance as float bits) per match.
+// Returns the number of words needed (> cap: nothing beyond cap was written).
+int64_t ref_matcher(const uint8_t* q, int nq, int nbytes, int n_imgs, const uint8_t* const* trains, const int32_t* nts,
+                    const uint8_t* const* masks, int k, float radius, int compact, int32_t* out, int64_t cap) {
+  cv::Mat qm(nq, nbytes, CV_8UC1);
+  if (nq) memcpy(qm.data, q, (size_t)nq * nbytes);
+  std::vector<cv::Mat> coll, mk;
+  for (int i = 0; i < n_imgs; ++i) {
+    cv::Mat t;
+    if (nts[i] > 0) { t.create(nts[i], nbytes, CV_8UC1); memcpy(t.data, trains[i], (size_t)nts[i] * nbytes); }
+    coll.push_back(t);
+    if (masks) {
+      cv::Mat m;
+      if (masks[i] && nts[i] > 0) { m.create(nq, nts[i], CV_8UC1); memcpy(m.data, masks[i], (size_t)nq * nts[i]); }
+      mk.push_back(m);
+    }
+  }
+  brisk::BruteForceMatcher matcher;
+  matcher.add(coll);
+  std::vector<std::vector<cv::DMatch> > res;
+  if (radius < 0) matcher.knnMatch(qm, res, k, cv::_InputArray(mk), compact != 0);
+  else matcher.radiusMatch(qm, res, radius, cv::_InputArray(mk), compact != 0);
+  int64_t pos = 0;
+  auto put = [&](int32_t v) { if (pos < cap) out[pos] = v; ++pos; };
+  put((int32_t)res.size());
+  for (const auto& lst : res) {
+    put((int32_t)lst.size());
+    for (const cv::DMatch& m : lst) {
+      int32_t bits; memcpy(&bits, &m.distance, 4);
+      put(m.queryIdx); put(m.trainIdx); put(m.imgIdx); put(bits);
+    }
+  }
+  return pos;
+}
+
 // Brute-force kNN with the reference distance primitive and the selection rule
 // of BruteForceMatcher::commonKnnMatchImpl (k successive arg-mins, first
-// minimum wins => lowest train index on ties).  The matcher class itself needs
-// cv::DescriptorMatcher and cannot be compiled here.  Rows must be 16-byte
+// minimum wins => lowest train index on ties), multi-threaded over the queries:
+// the CPU baseline of the matcher (ref_matcher above is the single-threaded class
+// itself).  Rows must be 16-byte
 // multiples; q/t need 16-byte alignment (numpy arrays from ctypes are copied).
 int ref_knn(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, int nbytes, int k, int32_t* idx,
             int32_t* dist, int nthreads) {

@@ -106,13 +106,77 @@ struct Mat {
   template <typename T> const T& at(int i, int j) const { return ((const T*)(data + step.buf[0] * i))[j]; }
   template <typename T> T& at(int i) { return ((T*)data)[i]; }
   template <typename T> const T& at(int i) const { return ((const T*)data)[i]; }
+  // header for row i sharing the data (cv::Mat::row)
+  Mat row(int i) const {
+    Mat m;
+    m.rows = 1; m.cols = cols; m.type_ = type_; m.step = step; m.data = data + step.buf[0] * i; m.owner = owner;
+    return m;
+  }
+  // cv::Mat::setTo(Scalar) for the single-channel types the reference uses it on (CV_32S, CV_8U)
+  template <typename S> Mat& setTo(const S& s) {
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cols; ++c) {
+        if ((type_ & 7) == CV_32S) at<int>(r, c) = (int)s.val[0];
+        else if ((type_ & 7) == CV_32F) at<float>(r, c) = (float)s.val[0];
+        else if (esz(type_) == 1) at<unsigned char>(r, c) = (unsigned char)s.val[0];
+        else at<unsigned short>(r, c) = (unsigned short)s.val[0];
+      }
+    return *this;
+  }
 };
+
+struct Scalar {
+  double val[4];
+  Scalar() { val[0] = val[1] = val[2] = val[3] = 0; }
+  static Scalar all(double v) { Scalar s; s.val[0] = s.val[1] = s.val[2] = s.val[3] = v; return s; }
+};
+
+template <typename T> struct DataType;
+template <> struct DataType<unsigned char> { enum { type = CV_8UC1 }; };
+template <> struct DataType<int> { enum { type = CV_32SC1 }; };
+template <> struct DataType<float> { enum { type = CV_32FC1 }; };
+
+// cv::Ptr: the reference only constructs it from a raw pointer and hands it back
+template <typename T>
+struct Ptr : std::shared_ptr<T> {
+  Ptr() {}
+  template <typename Y> Ptr(Y* p) : std::shared_ptr<T>(p) {}
+};
+
+inline int countNonZero(const Mat& m) {
+  int n = 0;
+  for (int r = 0; r < m.rows; ++r)
+    for (int c = 0; c < m.cols; ++c) n += m.at<unsigned char>(r, c) != 0;
+  return n;
+}
+
+// cv::minMaxLoc on a single-channel CV_32S matrix: extreme values and the FIRST location (row-major scan,
+// strict comparisons) at which each is met, as OpenCV's minMaxIdx does.
+inline void minMaxLoc(const Mat& m, double* minVal, double* maxVal, Point* minLoc, Point* maxLoc) {
+  int lo = std::numeric_limits<int>::max(), hi = std::numeric_limits<int>::min();
+  Point plo(-1, -1), phi(-1, -1);
+  for (int r = 0; r < m.rows; ++r)
+    for (int c = 0; c < m.cols; ++c) {
+      const int v = m.at<int>(r, c);
+      if (plo.x < 0 || v < lo) { lo = v; plo = Point(c, r); }
+      if (phi.x < 0 || v > hi) { hi = v; phi = Point(c, r); }
+    }
+  if (minVal) *minVal = lo;
+  if (maxVal) *maxVal = hi;
+  if (minLoc) *minLoc = plo;
+  if (maxLoc) *maxLoc = phi;
+}
+#define CV_DbgAssert(expr) ((void)0)
 
 struct _InputArray {
   Mat m;
+  std::vector<Mat> vec;
   _InputArray() {}
   _InputArray(const Mat& mm) : m(mm) {}
+  _InputArray(const std::vector<Mat>& v) : vec(v) {}
   Mat getMat() const { return m; }
+  void getMatVector(std::vector<Mat>& out) const { out = vec; }
+  bool empty() const { return m.empty() && vec.empty(); }
 };
 struct _OutputArray {
   Mat* p;

@@ -82,6 +82,36 @@ def test_detect_bit_exact(ctx, oracle, golden, thresh, octaves):
         assert kp_equal(det.detect(img, cap=400000), oracle.agast_detect(img, thresh, octaves, cap=1 << 20))
 
 
+@pytest.mark.parametrize("w,h,thresh,octaves", [(752, 480, 60, 5), (752, 480, 45, 6), (1600, 1200, 60, 6), (1920, 1080, 60, 5), (1024, 520, 30, 6)])
+def test_detect_deep_pyramids(ctx, oracle, w, h, thresh, octaves):
+    # 10- and 12-layer pyramids (kMaxLayers paths of the pyramid tiles, corner lists and the chain kernel)
+    img = bb.synthetic_frame(w, h, 4000 + w)
+    det = bb.BriskFeatureDetector(thresh, octaves, ctx=ctx)
+    det.set_corner_capacity(400000)
+    got = det.detect(img, cap=400000)
+    assert kp_equal(got, oracle.agast_detect(img, thresh, octaves, cap=1 << 20))
+    assert got["octave"].max() >= 2 * octaves - 3
+
+
+def test_config4_4k_six_octaves(ctx, oracle):
+    # BASELINE config 4: 3840x2160, 6 octaves (12 layers, 13-bit corner coordinates), detect + describe on two frames of
+    # the bench's own generator settings, bit for bit against the oracle; plus batch invariance
+    frames = np.stack([bb.synthetic_frame(3840, 2160, 3000 + i, n_shapes=4200) for i in range(2)])
+    det = bb.BriskFeatureDetector(60, 6, ctx=ctx)
+    ext = bb.BriskDescriptorExtractor(ctx=ctx)
+    kps, counts, desc = bb.detect_and_compute_batch(det, ext, frames, cap=65536)
+    for f in range(2):
+        k2, d2 = oracle.describe(frames[f], oracle.agast_detect(frames[f], 60, 6, cap=1 << 20))
+        n = counts[f]
+        assert n == len(k2) and n > 10000
+        for fld in ("x", "y", "size", "response", "octave", "class_id"):
+            assert np.array_equal(kps[f, :n][fld], k2[fld]), fld
+        assert np.abs(kps[f, :n]["angle"] - k2["angle"]).max() <= 1e-4
+        assert np.array_equal(desc[f, :n], d2)
+    k1, c1, d1 = bb.detect_and_compute_batch(det, ext, frames[1:2], cap=65536)
+    assert c1[0] == counts[1] and np.array_equal(d1[0, :c1[0]], desc[1, :counts[1]])
+
+
 def test_detect_without_scale_suppression_single_layer(ctx, oracle, ref, golden):
     # suppressScaleNonmaxima = false is defined for one layer only (the reference indexes layer 0's corner list
     # with the other layers' counts, brisk-scale-space.cc:137); there it equals the compiled reference
@@ -326,6 +356,19 @@ def test_capacity_overflow_is_reported(ctx):
     with pytest.raises(bb.BriskError) as e:
         det.detect(img, cap=10)
     assert e.value.code == -4
+    # the fused call reports it too (the border cull must not hide the detector's overflow), with the true count
+    ext = bb.BriskDescriptorExtractor(ctx=ctx)
+    full = len(det.detect(img))
+    with pytest.raises(bb.BriskError) as e:
+        bb.detect_and_compute_batch(det, ext, img[None], cap=full - 1)
+    assert e.value.code == -4
+    kps, counts, desc = bb.detect_and_compute_batch(det, ext, img[None], cap=full)
+    assert 0 < counts[0] <= full
+    import ctypes as C
+    k = np.zeros((1, 16), bb.KP_DTYPE); c = np.zeros(1, np.int32); d = np.zeros((1, 16, 48), np.uint8)
+    rc = ctx._lib.brisk_detect_describe(ctx._h, det._h, ext._h, bb.api._ptr(img), 1, 752, 480, C.c_size_t(752), C.c_size_t(752 * 480), None,
+                                        bb.api._ptr(k), bb.api._ptr(c), 16, bb.api._ptr(d))
+    assert rc == -4 and c[0] == full
     det.set_corner_capacity(64)
     with pytest.raises(bb.BriskError):
         det.detect(img)
@@ -343,6 +386,10 @@ def test_knn_bit_exact(ctx, oracle, nbytes, k):
     i2, d2 = oracle.knn(q, t, k)
     assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
     assert i1[3, 0] == 100 and d1[3, 0] == 0
+    from oracle import ref as r
+    if r.available():  # the reference class itself on a slice of the queries
+        lists = r.knn_match(q[:64], [t], k)
+        assert [[mm[1] for mm in v] for v in lists] == i1[:64].tolist() and [[int(mm[3]) for mm in v] for v in lists] == d1[:64].tolist()
 
 
 def test_reference_match_test_homography(ctx, golden):
@@ -516,10 +563,19 @@ def _tie_rich_descriptors(n, nbytes, seed):
     return d
 
 
+@pytest.fixture
+def matcher_oracle(oracle):
+    """brisk::BruteForceMatcher itself (oracle/_ref, brute-force-matcher.cc compiled unmodified) when the prebuilt
+    library travelled with the snapshot; else its restatement (pinned to it by tests/test_oracle_golden.py)."""
+    from oracle import ref as r
+    return r if r.available() else oracle
+
+
 @pytest.mark.parametrize("nbytes", [48, 64])
-def test_knn_match_collection_masks(ctx, oracle, nbytes):
+def test_knn_match_collection_masks(ctx, matcher_oracle, nbytes):
     # knnMatch over a train collection (one image empty, one mask empty), ties across images, masked-out
-    # queries, fewer allowed rows than k: reference brute-force-matcher.cc:80-162 line by line
+    # queries, fewer allowed rows than k: against the compiled reference class (brute-force-matcher.cc:80-162)
+    oracle = matcher_oracle
     rng = np.random.default_rng(11)
     q = bb.random_descriptors(90, nbytes, 5)
     trains = [bb.random_descriptors(300, nbytes, 6), np.zeros((0, nbytes), np.uint8), bb.random_descriptors(170, nbytes, 7)]
@@ -548,7 +604,8 @@ def test_knn_match_collection_masks(ctx, oracle, nbytes):
 
 
 @pytest.mark.parametrize("nbytes", [48, 64])
-def test_radius_match(ctx, oracle, nbytes):
+def test_radius_match(ctx, matcher_oracle, nbytes):
+    oracle = matcher_oracle
     # radiusMatch: long lists of equal distances (std::sort's permutation is part of the result), masks, two
     # images, compactResult, the capacity retry: reference brute-force-matcher.cc:164-214
     rng = np.random.default_rng(12)

@@ -209,3 +209,51 @@ def test_matcher_restatement_consistency(oracle):
     # fewer candidates than k: the reference pads with (0, last non-empty image, 2147483648.0f)
     short = oracle.knn_match(q[:2], [t[:1], t[:0]], 3)
     assert short[0][1:] == [(0, 0, 0, 2147483648.0)] * 2
+
+
+def _tie_rich(n, nbytes, seed):
+    rng = np.random.default_rng(seed)
+    d = np.zeros((n, nbytes), np.uint8)
+    d[:, :6] = rng.integers(0, 4, (n, 6), dtype=np.uint8) * 17
+    return d
+
+
+@pytest.mark.parametrize("nbytes", [48, 64])
+def test_matcher_vs_ref_class(oracle, ref, nbytes):
+    # the restated selection rules against brisk::BruteForceMatcher ITSELF (brute-force-matcher.cc compiled
+    # unmodified into oracle/_ref): collections with an empty image, masks, masked-out queries, exhausted
+    # candidates (INT_MAX padding), ties across images, compactResult, radius lists with long runs of equal
+    # distances (std::sort's permutation), fewer train rows than k
+    rng = np.random.default_rng(11)
+    q = random_descriptors(90, nbytes, 5)
+    trains = [random_descriptors(300, nbytes, 6), np.zeros((0, nbytes), np.uint8), random_descriptors(170, nbytes, 7)]
+    trains[0][10] = q[3]; trains[2][5] = q[3]; trains[0][200] = q[3]
+    masks = [(rng.random((90, 300)) < 0.7).astype(np.uint8), None, (rng.random((90, 170)) < 0.5).astype(np.uint8)]
+    masks[0][7] = 0; masks[2][7] = 0
+    masks[0][9] = 0; masks[2][9] = 0; masks[2][9, 4] = 1
+    for k in (1, 2, 5, 11):
+        for compact in (False, True):
+            assert oracle.knn_match(q, trains, k, masks, compact) == ref.knn_match(q, trains, k, masks, compact), (k, compact)
+        assert oracle.knn_match(q, trains, k) == ref.knn_match(q, trains, k)
+    full = [masks[0], masks[2]]
+    two = [trains[0], trains[2]]
+    for compact in (False, True):
+        assert oracle.knn_match(q, two, 3, full, compact) == ref.knn_match(q, two, 3, full, compact)
+    assert oracle.knn_match(q[:4], [trains[0][:2]], 3) == ref.knn_match(q[:4], [trains[0][:2]], 3)
+    # single image: the plain kNN restatement / the multi-threaded baseline loop are the class's result too
+    idx, dist = oracle.knn(q, trains[0], 3)
+    lists = ref.knn_match(q, [trains[0]], 3)
+    assert [[m[1] for m in v] for v in lists] == idx.tolist() and [[int(m[3]) for m in v] for v in lists] == dist.tolist()
+    i2, d2 = ref.knn(q, trains[0], 3, nthreads=2)
+    assert np.array_equal(i2, idx) and np.array_equal(d2, dist)
+    # radiusMatch
+    tq = _tie_rich(60, nbytes, 1)
+    tt = [_tie_rich(400, nbytes, 2), _tie_rich(250, nbytes, 3)]
+    for md in (0.0, 1.0, 7.5, 12.0, 1000.0):
+        assert oracle.radius_match(tq, tt, md) == ref.radius_match(tq, tt, md), md
+    rm = [(rng.random((60, 400)) < 0.6).astype(np.uint8), (rng.random((60, 250)) < 0.6).astype(np.uint8)]
+    rm[0][5] = 0; rm[1][5] = 0
+    for compact in (False, True):
+        assert oracle.radius_match(tq, tt, 9.0, rm, compact) == ref.radius_match(tq, tt, 9.0, rm, compact)
+    md = float(nbytes * 8 * 0.44)
+    assert oracle.radius_match(q, [trains[0]], md) == ref.radius_match(q, [trains[0]], md)
