@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Benchmark of the BRISK hot path on B200 (contract: see the task description).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C3|C2|C4|C5]
 
-Workload (BASELINE.json configs[2], "C3"): AGAST/OAST9-16 scale-space detect
+Default workload (BASELINE.json configs[2], "C3"): AGAST/OAST9-16 scale-space detect
 (BriskFeatureDetector(60, 4)) + BRISK2 describe on synthetic 1920x1080 frames.
 One step = one batch of --frames frames per GPU (default 1024, sharded by
 frame across ranks without any collective: weak scaling).  `value` is frames/s
@@ -11,6 +11,11 @@ with the batch resident in HBM; `e2e` is the same call with pinned HOST
 buffers in and out (H2D + D2H inside the timed region).  The reference arm
 (--impl reference) times the unmodified reference (oracle/_ref) on the host
 cores on a bounded sample of the same frames.
+
+The other BASELINE.json configurations print the same schema with --config:
+  C2  256 x 752x480, Harris scale space (octaves 4, radius 30, absThr 20) + BRISK2
+  C4  3840x2160, AGAST(60, 6 octaves) + BRISK2 (descriptor-extraction stress)
+  C5  brute-force Hamming kNN (k = 2), 512-bit rows, train set sharded over the ranks (NCCL all-gather + merge)
 """
 import argparse
 import json
@@ -28,14 +33,25 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "1080p_frames_per_s_detect_describe"
 UNIT = "frames/s"
-W, H = 1920, 1080
-THRESH, OCTAVES = 60, 4
-UNIQUE = 16  # distinct procedurally generated frames; the batch cycles them with per-frame shifts
+
+# BASELINE.json configs[1], [2], [3]: frame size, detector, frames per GPU per step, key-point capacity,
+# distinct generated frames (the batch cycles them with per-copy horizontal shifts), generator arguments
+FRAME_CONFIGS = {
+    "C2": dict(w=752, h=480, frames=256, cap=4096, unique=32, seed=1000, gen={}, harris=True, octaves=4, radius=30.0, abs_thr=20.0,
+               metric="752x480_frames_per_s_harris_detect_describe",
+               workload="C2: HarrisScaleSpaceFeatureDetector(octaves=4, uniformityRadius=30, absThr=20) + BRISK2 describe, 752x480 synthetic frames"),
+    "C3": dict(w=1920, h=1080, frames=1024, cap=12288, unique=16, seed=2000, gen={}, harris=False, thresh=60, octaves=4, metric=METRIC,
+               workload="C3: AGAST(60,4) detect + BRISK2 describe, 1920x1080 synthetic frames"),
+    "C4": dict(w=3840, h=2160, frames=128, cap=49152, unique=4, seed=3000, gen=dict(n_shapes=4200), harris=False, thresh=60, octaves=6,
+               metric="2160p_frames_per_s_detect_describe",
+               workload="C4: AGAST(60, 6 octaves) detect + BRISK2 describe, 3840x2160 synthetic frames (describe stress)"),
+}
 
 
-def unique_frames(seed0, n=UNIQUE):
+def unique_frames(cfg, rank=0):
     from ethzasl_brisk_b200.synthetic import synthetic_frame
-    return np.stack([synthetic_frame(W, H, seed0 + i) for i in range(n)])
+    s0 = cfg["seed"] + rank * cfg["unique"]
+    return np.stack([synthetic_frame(cfg["w"], cfg["h"], s0 + i, **cfg["gen"]) for i in range(cfg["unique"])])
 
 
 def host_cores():
@@ -115,24 +131,13 @@ def pin_to_gpu_numa_node(index):
 
 
 def measured_peaks():
+    """(HBM GB/s, dense int8 TOP/s, source).  The tensor figure is 2 x the measured cuBLAS bf16 burst rate (int8 runs at twice
+    the bf16 rate on the same pipe; no int8 library GEMM was measured)."""
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
-        return json.loads(p.read_text()).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
-
-
-def stage_bytes(n_layers_dims, n_corners, n_kps, desc_bytes=48):
-    """Algorithmic bytes per frame of each stage."""
-    px = [w * h for w, h in n_layers_dims]
-    return {
-        "pyramid": px[0] + sum(px),                 # read L0 once, write every layer (L0 copy included)
-        "detect": sum(px) + 2 * sum(px),            # read u8 layers, write u16 corner maps
-        "lists": 2 * sum(px) + 4 * n_corners,       # read corner maps, write packed corners
-        "nms": 3 * sum(px) + 100 * n_corners,       # touch-map clear + corner-map traffic + per-corner records
-        "integral": px[0] + 4 * (W + 1) * (H + 1),  # SURVEY.md 8d: u8 in, i32 out.  Real traffic is 2 x px[0] in + 16 B per pixel
-                                                    # out (one 2x2 block of the integral image per pixel, for the sampler)
-        "describe": n_kps * (28 * 2 + desc_bytes),  # compulsory HBM only; the gathers hit L2
-    }
+        d = json.loads(p.read_text())
+        return d.get("hbm_gbs", 6650.0), 2.0 * d.get("bf16_tflops", 1590.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 2.0 * 1590.0, "fallback (B200_PROFILING.md)"
 
 
 def layer_dims(w, h, octaves):
@@ -142,28 +147,102 @@ def layer_dims(w, h, octaves):
     return dims[:max(1, 2 * octaves)]
 
 
+def stage_bytes(cfg, n_corners, n_kps, desc_bytes=48):
+    """ALGORITHMIC bytes per frame of each stage: unique bytes in + bytes out (SURVEY.md 8d's per-unit figures; DESIGN.md
+    section 5).  `nms` has no figure in SURVEY (its input is the scoring stage's output): the per-corner records it must read
+    and the key points it writes."""
+    w, h = cfg["w"], cfg["h"]
+    px = [a * b for a, b in layer_dims(w, h, cfg["octaves"])]
+    b = {
+        "pyramid": px[0] + sum(px[1:]),                       # L0 in once (one fused kernel) + every derived layer out
+        "integral": px[0] + 4 * (w + 1) * (h + 1),            # u8 in, (h+1) x (w+1) i32 out
+        "describe": n_kps * (28 * 2 + desc_bytes),            # compulsory HBM only: key point in / out, descriptor out
+    }
+    if cfg["harris"]:
+        b["harris"] = 5 * sum(px)                             # SURVEY 8d: 1 B/px in + 4 B/px scores out, all layers
+    else:
+        b["detect"] = sum(px) + 12 * n_corners                # SURVEY 8d: 1 B/px over all layers + 12 B per emitted corner
+        b["lists"] = 12 * n_corners                           # (the corner lists are part of SURVEY's scoring figure; kept apart: own kernels)
+        b["nms"] = 12 * n_corners + 28 * n_kps                # corner records in, key points out
+    return b
+
+
+def traffic_table():
+    """DRAM bytes per frame of every stage's kernels, from the committed ncu --set full capture of the CURRENT kernels
+    (profiles/r02_dram_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep; dram__bytes_read.sum +
+    dram__bytes_write.sum per launch / frames per launch).  None when the file is absent."""
+    p = ROOT / "profiles" / "r02_dram_traffic.json"
+    if not p.exists():
+        return None
+    return json.loads(p.read_text())
+
+
+LIMITER = {
+    "describe": "L1/L2 sector rate of scattered 16-byte gathers from the integral blocks (not HBM); see profiles/",
+    "nms": "ALU pipe / instruction issue of the per-corner score evaluation and the tie chain (not HBM); see profiles/",
+    "detect": "ALU pipe: packed min/max of the threshold map and the arc test (not HBM); see profiles/",
+    "harris": "the std::sort replay and the sequential uniformity stamping per (frame, layer); see DESIGN.md section 7",
+}
+
+
+def ref_detect_describe(ref, cfg, frame):
+    if cfg["harris"]:
+        k = ref.harris_detect(frame, cfg["octaves"], cfg["radius"], cfg["abs_thr"], -1)
+    else:
+        k = ref.agast_detect(frame, cfg["thresh"], cfg["octaves"], cap=1 << 19)
+    return ref.describe(frame, k)
+
+
+def ref_bench(ref, cfg, frames, nthreads):
+    return ref.bench_detect_describe(frames, cfg["harris"], cfg.get("thresh", 60), cfg["octaves"], cfg.get("radius", 30.0),
+                                     cfg.get("abs_thr", 20.0), nthreads=nthreads)
+
+
 def run_reference(args):
-    """CPU arm: the unmodified reference (oracle/_ref), frame-parallel over the host cores."""
+    """CPU arm: the unmodified reference (oracle/_ref) on the host cores, on a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     from oracle import ref
     cores = host_cores()
-    frames = unique_frames(2000)
-    per_step = min(256, max(UNIQUE, 2 * cores))
-    frames = frames[np.arange(per_step) % UNIQUE]
-    sample = f"{per_step} synthetic 1080p frames per step ({UNIQUE} distinct), {cores} threads (one detector per thread)"
+    if args.config == "C5":
+        import ethzasl_brisk_b200 as bb
+        nq, nt = min(4096, args.knn_q), min(1000000, args.knn_t)
+        q, t = bb.random_descriptors(nq, 64, 5), bb.random_descriptors(nt, 64, 6)
+        for _ in range(min(args.warmup, 1)):
+            ref.knn(q[:64], t, 2, nthreads=cores)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ref.knn(q, t, 2, nthreads=cores)
+        dt = time.perf_counter() - t0
+        value = args.steps * nq * nt / dt / 1e9
+        sample = f"{nq} queries x {nt} train rows per step (uniform random 512-bit rows), k = 2, {cores} threads"
+        line = {"impl": "reference", "metric": "hamming_knn_k2_512bit", "value": value, "unit": "Gcmp/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u8", "data": "synthetic",
+                "config": {"workload": "C5: brute-force Hamming kNN k=2, 512-bit descriptors", "queries": nq, "train": nt},
+                "cpu_baseline": {"value": value, "unit": "Gcmp/s", "cores": cores, "kind": "reference", "sample": sample},
+                "e2e": {"value": value, "unit": "Gcmp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+    cfg = FRAME_CONFIGS[args.config]
+    frames = unique_frames(cfg)
+    px_scale = (1920 * 1080) / (cfg["w"] * cfg["h"])
+    per_step = int(min(256 * max(px_scale, 1), max(cfg["unique"], 2 * cores * max(int(px_scale), 1))))
+    per_step = max(per_step, cores)
+    frames = frames[np.arange(per_step) % cfg["unique"]]
+    sample = f"{per_step} synthetic {cfg['w']}x{cfg['h']} frames per step ({cfg['unique']} distinct), {cores} threads (one detector per thread)"
     for _ in range(args.warmup):
-        ref.bench_detect_describe(frames[:cores], False, THRESH, OCTAVES, nthreads=cores)
+        ref_bench(ref, cfg, frames[:cores], cores)
     t = kp = 0
     for _ in range(args.steps):
-        s, k = ref.bench_detect_describe(frames, False, THRESH, OCTAVES, nthreads=cores)
+        s, k = ref_bench(ref, cfg, frames, cores)
         t += s; kp += k
     value = args.steps * len(frames) / t
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "C3: AGAST(60,4) detect + BRISK2 describe, 1920x1080 synthetic frames", "frames_per_step": len(frames),
+            "config": {"workload": cfg["workload"], "frames_per_step": len(frames),
                        "keypoints_per_frame": kp / (args.steps * len(frames))},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -171,122 +250,136 @@ def run_reference(args):
     return 0
 
 
-def run_gpu(args):
-    import torch
-    import torch.distributed as dist
+class Rig:
+    """Process group, device, clocks and timing helpers shared by the GPU arms."""
 
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+        # stdout carries the one JSON line: NCCL's own output (version banner, INFO lines with the communicator's
+        # nranks) goes to stderr.  At N > 1 INFO is on unless the caller chose a level.
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if self.world > 1:
+            os.environ.setdefault("NCCL_DEBUG", os.environ.get("BENCH_NCCL_DEBUG", "INFO"))
+        torch.cuda.set_device(self.local)
+        self.numa = pin_to_gpu_numa_node(self.local) if self.world > 1 else None
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.current_stream()
+        self.sampler = ClockSampler(self.local)
+        if self.rank == 0:
+            self.sampler.start()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, ctx=None):
+        """K calls bracketed by barrier + synchronize on both sides, CUDA events on the launching stream, max over ranks."""
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        stages, launches = {}, 0
+        for _ in range(steps):
+            fn()
+            if ctx is not None:
+                ms, l = ctx.last_timing()
+                launches += l
+                for k, v in ms.items():
+                    stages[k] = stages.get(k, 0.0) + v
+        e1.record(self.stream)
+        self.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item()), stages, launches
+
+    def finish(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def run_frames(args):
     import ethzasl_brisk_b200 as bb
+    cfg = FRAME_CONFIGS[args.config]
+    rig = Rig(args)
+    torch, dev, world, rank = rig.torch, rig.dev, rig.world, rig.rank
+    W, H = cfg["w"], cfg["h"]
+    n = args.frames or cfg["frames"]
+    cap = args.cap or cfg["cap"]
 
-    # keep stdout to the one JSON line: NCCL prints its version banner to stdout from level WARN upwards
-    if "BENCH_NCCL_DEBUG" in os.environ:
-        os.environ["NCCL_DEBUG"] = os.environ["BENCH_NCCL_DEBUG"]
-    else:
-        os.environ.pop("NCCL_DEBUG", None)
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
-    torch.cuda.set_device(local)
-    numa = pin_to_gpu_numa_node(local) if world > 1 else None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-    n = args.frames
-    cap = args.cap
-
-    # frames: UNIQUE generated frames per rank, cycled with a per-copy horizontal roll so that all n differ
-    uniq = torch.from_numpy(unique_frames(2000 + rank * UNIQUE)).to(dev)
+    # frames: `unique` generated frames per rank, cycled with a per-copy horizontal roll so that all n differ
+    uniq_host = unique_frames(cfg, rank)
+    uniq = torch.from_numpy(uniq_host).to(dev)
+    U = cfg["unique"]
     d_frames = torch.empty((n, H, W), dtype=torch.uint8, device=dev)
     for j in range(n):
-        d_frames[j] = torch.roll(uniq[j % UNIQUE], shifts=(j // UNIQUE) * 5, dims=1)
+        d_frames[j] = torch.roll(uniq[j % U], shifts=(j // U) * 5, dims=1)
     h_frames = torch.empty((n, H, W), dtype=torch.uint8).pin_memory()
     h_frames.copy_(d_frames)
     torch.cuda.synchronize()
 
-    stream = torch.cuda.current_stream()
-    ctx = bb.Context(local, stream=stream.cuda_stream, timing=True, workspace_limit=args.workspace_gb << 30)
-    det = bb.BriskFeatureDetector(THRESH, OCTAVES, ctx=ctx)
+    ctx = bb.Context(rig.local, stream=rig.stream.cuda_stream, timing=True, workspace_limit=args.workspace_gb << 30)
+    if cfg["harris"]:
+        det = bb.ScaleSpaceFeatureDetector(cfg["octaves"], cfg["radius"], cfg["abs_thr"], ctx=ctx)
+    else:
+        det = bb.BriskFeatureDetector(cfg["thresh"], cfg["octaves"], ctx=ctx)
     ext = bb.BriskDescriptorExtractor(ctx=ctx)
     d_out = (torch.empty((n, cap, 7), dtype=torch.float32, device=dev), torch.empty(n, dtype=torch.int32, device=dev),
              torch.empty((n, cap, 48), dtype=torch.uint8, device=dev))
     h_out = (torch.empty((n, cap, 7), dtype=torch.float32).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory(),
              torch.empty((n, cap, 48), dtype=torch.uint8).pin_memory())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        stages, launches = {}, 0
-        for _ in range(steps):
-            fn()
-            ms, l = ctx.last_timing()
-            launches += l
-            for k, v in ms.items():
-                stages[k] = stages.get(k, 0.0) + v
-        e1.record(stream)
-        barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), stages, launches
-
     resident = lambda: bb.detect_and_compute_batch(det, ext, d_frames, cap=cap, out=d_out)
     e2e = lambda: bb.detect_and_compute_batch(det, ext, h_frames, cap=cap, out=h_out)
 
-    # nvidia-smi takes a few hundred ms to deliver its first line: start it before the warm-up, count only the
-    # lines of the two timed regions (resident and host end-to-end)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    # nvidia-smi takes a few hundred ms to deliver its first line: it was started before the warm-up; only the
+    # lines of the two timed regions (resident and host end-to-end) count
     for _ in range(args.warmup):
         resident()
     if rank == 0:
-        sampler.mark()
-    ms_res, stages, launches = timed(resident, args.steps)
+        rig.sampler.mark()
+    ms_res, stages, launches = rig.timed(resident, args.steps, ctx)
     if rank == 0:
-        sampler.pause()
+        rig.sampler.pause()
+    raw_corners = ctx.last_raw_corners()
     counts = d_out[1].cpu().numpy()
     # per-stage device times without cross-stream overlap (same kernels, one stream, stages back to
     # back): these feed the per-kernel roofline numbers; the headline numbers above keep pipelining on
     ctx.set_pipelining(False)
     resident()
-    _, stages_serial, _ = timed(resident, 1)
+    _, stages_serial, _ = rig.timed(resident, 1, ctx)
     ctx.set_pipelining(True)
     for _ in range(max(1, args.warmup // 2)):
         e2e()
     if rank == 0:
-        sampler.mark()
-    ms_e2e, _, _ = timed(e2e, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
+        rig.sampler.mark()
+    ms_e2e, _, _ = rig.timed(e2e, args.steps, ctx)
+    clocks = rig.sampler.stop() if rank == 0 else None
     if getattr(pin_to_gpu_numa_node, "full", None):
-        os.sched_setaffinity(0, pin_to_gpu_numa_node.full)  # the CPU baseline below uses every host core
+        os.sched_setaffinity(0, pin_to_gpu_numa_node.full)  # the CPU legs below use every host core
     hc = h_out[1].numpy()
     assert np.array_equal(hc, counts), "host and device paths disagree"
-    kp_total = int(np.minimum(counts, cap).sum())
+    assert counts.max() <= cap, "key-point capacity exceeded"
+    kp_total = int(counts.sum())
 
-    # secondary metric: brute-force Hamming kNN (k=2), 512-bit descriptors, reduced C5 shape per GPU
-    q = torch.from_numpy(bb.random_descriptors(args.knn_q, 64, 5)).to(dev)
-    t = torch.from_numpy(bb.random_descriptors(args.knn_t, 64, 6 + rank)).to(dev)
-    m = bb.BruteForceMatcher(ctx=ctx)
-    knn_variants = {}
-    for name, variant in (("popc", 0), ("tensor_core", 1)):
-        ctx.set_knn_variant(variant)
-        m.knn(q, t, 2)
-        v_ms, _, _ = timed(lambda: m.knn(q, t, 2), 3)
-        knn_variants[name] = {"Gcmp/s": world * args.knn_q * args.knn_t * 3 / (v_ms * 1e-3) / 1e9, "ms": v_ms / 3}
-    knn_ms = 3 * knn_variants["tensor_core"]["ms"]   # the default path
-    gcmp = knn_variants["tensor_core"]["Gcmp/s"]
+    # secondary metric (C3 only): brute-force Hamming kNN (k = 2), 512-bit descriptors.  One rank: reduced C5 shape.
+    # N ranks: the TRAIN set is sharded over the ranks (each holds --knn-t rows), every rank searches its shard,
+    # NCCL all-gather of the per-shard top-2 keys + merge (distributed.sharded_knn): weak scaling in the train size.
+    secondary = None
+    if args.config == "C3" and not args.no_knn:
+        secondary = knn_measure(args, rig, ctx, bb, args.knn_q, args.knn_t * world, steps=3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        rig.finish()
         return 0
 
     value = world * n * args.steps / (ms_res * 1e-3)
@@ -294,95 +387,186 @@ def run_gpu(args):
     h2d = n * H * W
     d2h = 4 * n + kp_total * (28 + 48)
     # roofline of the dominant stage (device time from CUDA events on the launching stream)
-    peak, peak_src = measured_peaks()
-    dims = layer_dims(W, H, OCTAVES)
-    compute_stages = {k: v for k, v in stages_serial.items() if k in ("pyramid", "detect", "lists", "nms", "integral", "describe")}
+    hbm_peak, _, peak_src = measured_peaks()
+    kps_per_frame = kp_total / n
+    corners_per_frame = raw_corners / n
+    bytes_per_frame = stage_bytes(cfg, corners_per_frame, kps_per_frame)
+    names = ("pyramid", "harris", "integral", "describe") if cfg["harris"] else ("pyramid", "detect", "lists", "nms", "integral", "describe")
+    serial = dict(stages_serial)
+    if cfg["harris"]:
+        serial["harris"] = serial.get("nms", 0.0)  # the Harris kernels run between the NMS stage marks
+        stages["harris"] = stages.get("nms", 0.0)
+    compute_stages = {k: serial.get(k, 0.0) for k in names}
     total_ms = sum(compute_stages.values())
     top = max(compute_stages, key=compute_stages.get)
-    # raw corners per frame are not returned by the API; the measured mean on these frames is ~2.1x the key points
-    kps_per_frame = kp_total / n
-    bytes_per_frame = stage_bytes(dims, int(2.1 * kps_per_frame), int(kps_per_frame))
+    traffic = traffic_table() if args.config == "C3" else None
     stage_report = {}
     for k, v in compute_stages.items():
         gbs = bytes_per_frame[k] * n / (v * 1e-3) / 1e9 if v > 0 else 0.0
-        stage_report[k] = {"ms_per_step": v, "share": v / total_ms if total_ms else 0.0, "algorithmic_GBps": gbs,
-                           "frac_of_hbm_peak": gbs / peak, "ms_per_step_pipelined": stages.get(k, 0.0) / args.steps}
-    roof = {"bound": "hbm", "kernel": top, "achieved": stage_report[top]["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
+        stage_report[k] = {"ms_per_step": v, "share": v / total_ms if total_ms else 0.0, "algorithmic_bytes_per_frame": bytes_per_frame[k],
+                           "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / hbm_peak, "ms_per_step_pipelined": stages.get(k, 0.0) / args.steps}
+        if traffic and k in traffic.get("stages", {}):
+            stage_report[k]["ncu_dram_bytes_per_frame"] = traffic["stages"][k]
+    roof = {"bound": "hbm", "kernel": top, "achieved": stage_report[top]["algorithmic_GBps"], "peak": hbm_peak, "unit": "GB/s",
             "frac": stage_report[top]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
-            "note": "dominant stage by CUDA-event time of a non-pipelined step (stages back to back on one stream); see stages"}
-    # DRAM bytes per frame of the stages' kernels from the committed `ncu --set full` captures (dram__bytes_read.sum +
-    # dram__bytes_write.sum of one launch / frames of that launch); reported for one frame of the dominant stage,
-    # like `achieved`, which is per frame too (algorithmic bytes of n frames / time of n frames)
-    NCU_DRAM_BYTES_PER_FRAME = {"describe": (2.195719e9 + 87.774e6) / 256,        # profiles/r01_ncu_full_top_kernels_v14.txt
-                                "pyramid": (0.354613e9 + 0.626522e9) / 256,       # (inputs partly L2 resident in that capture)
-                                # nms_prefix + nms_checks (v14 capture, 256 frames per launch) + nms_chain (v15 capture, 171 frames
-                                # per launch); refine / compact (a few per cent of the stage's time) were not captured
-                                "nms": (1.080348e9 + 0.191219e9 + 1.312184e9 + 0.260362e9) / 256 + (961.691392e6 + 79.735040e6) / 171}
-    LIMITER = {"describe": "L1/L2 sector rate of scattered 4-byte gathers (ncu: l1tex 77 %, lts 55 % of peak, DRAM 30 %); the "
-                           "integral images of a chunk do not fit L2, so ~8.9 MB per frame come from DRAM although only "
-                           "104 B per key point are compulsory",
-               "nms": "ALU pipe / instruction issue of the per-corner kernels and the tie chain (ncu: ALU 73-79 %)",
-               "detect": "ALU pipe (packed min/max at half rate; ncu: ALU 73 %, DRAM 10 %)"}
-    roof["algorithmic_bytes"] = bytes_per_frame[top] * n
+            "algorithmic_bytes": bytes_per_frame[top] * n,
+            "note": "dominant stage by CUDA-event time of a non-pipelined step (stages back to back on one stream); algorithmic bytes = "
+                    "SURVEY.md 8d per-frame figure x frames per step; see `stages` for every stage"}
+    if traffic and top in traffic.get("stages", {}):
+        roof["traffic"] = traffic["stages"][top] * n
+        roof["traffic_note"] = f"ncu dram__bytes_read.sum + dram__bytes_write.sum per frame x frames of the step (capture: {traffic.get('source')})"
+    if top in LIMITER:
+        roof["limiter"] = LIMITER[top]
     if "integral" in stage_report:  # the block layout trades 3.6x the output bytes for 3.5x fewer gather instructions in describe
         real = 2 * W * H + 16 * W * H
         stage_report["integral"]["hbm_traffic_GBps"] = real * n / (compute_stages["integral"] * 1e-3) / 1e9
-        stage_report["integral"]["hbm_traffic_frac_of_peak"] = stage_report["integral"]["hbm_traffic_GBps"] / peak
+        stage_report["integral"]["hbm_traffic_frac_of_peak"] = stage_report["integral"]["hbm_traffic_GBps"] / hbm_peak
     if stage_report.get("describe", {}).get("ms_per_step", 0) > 0:
-        # describe is gather bound, not HBM bound -- its meaningful rate is key points per second (132 box-filter
-        # samples each); ncu of the round: L1 71 %, L2 51 % of peak, 46 % of the stall samples on dependent global loads
+        # describe is gather bound, not HBM bound -- its meaningful rate is key points per second
         stage_report["describe"]["keypoints_per_s"] = kp_total / (stage_report["describe"]["ms_per_step"] * 1e-3)
-    if top in NCU_DRAM_BYTES_PER_FRAME:
-        roof["traffic"] = NCU_DRAM_BYTES_PER_FRAME[top] * n
-        roof["traffic_note"] = ("ncu dram bytes per frame x frames of the step (captures: profiles/r01_ncu_full_top_kernels_v14.txt, "
-                                "profiles/r01_ncu_full_top_kernels_v15.txt)")
-    if top in LIMITER:
-        roof["limiter"] = LIMITER[top]
 
-    # CPU baseline beside it: the unmodified reference on a bounded sample of the same frames
-    cpu = None
+    # parity of the benched workload itself: randomly chosen frames of the batch (key points + descriptors of the end-to-end
+    # run) against the unmodified reference, and the CPU baseline beside the GPU numbers on a bounded sample of the same frames
+    parity, cpu = None, None
+    try:
+        from oracle import ref
+        if ref.available():
+            rng = np.random.default_rng(12345)
+            pick = sorted(rng.choice(n, size=min(args.parity_frames, n), replace=False).tolist())
+            hk = h_out[0].numpy().view(np.uint8).reshape(n, cap, 28)
+            ok, kp_checked, bad = True, 0, []
+            for f in pick:
+                frame = h_frames[f].numpy()
+                k2, d2 = ref_detect_describe(ref, cfg, frame)
+                m = int(hc[f])
+                k1 = np.frombuffer(hk[f, :m].tobytes(), bb.KP_DTYPE)
+                good = m == len(k2) and all(np.array_equal(k1[fld], k2[fld]) for fld in ("x", "y", "size", "response", "octave", "class_id")) \
+                    and (m == 0 or float(np.abs(k1["angle"] - k2["angle"]).max()) <= 1e-4) and np.array_equal(h_out[2][f, :m].numpy(), d2)
+                ok &= bool(good)
+                kp_checked += m
+                if not good:
+                    bad.append(f)
+            parity = {"parity_checked_frames": len(pick), "parity_ok": ok, "keypoints_checked": kp_checked, "frames": pick, "mismatching_frames": bad,
+                      "against": "oracle/_ref (the unmodified reference), bit-exact key points and descriptors, angle within 1e-4 deg"}
+            cores = host_cores()
+            px_scale = max(1, int((1920 * 1080) / (W * H)))
+            ns = min(256 * px_scale, max(U, 2 * cores * px_scale))
+            sample_frames = uniq_host[np.arange(ns) % U]
+            ref_bench(ref, cfg, sample_frames[:2], min(2, cores))
+            s, _ = ref_bench(ref, cfg, sample_frames, cores)
+            cpu = {"value": len(sample_frames) / s, "unit": UNIT, "cores": cores, "kind": "reference",
+                   "sample": f"{len(sample_frames)} frames drawn from the same {U} distinct {W}x{H} frames, unmodified reference (oracle/_ref), {cores} threads"}
+    except Exception as e:  # the baseline is informative; never fail the bench on it
+        cpu = cpu or {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+
+    line = {"metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": cfg["workload"], "frames_per_gpu_per_step": n,
+                       "global_frames_per_step": world * n, "keypoints_per_frame": kps_per_frame, "raw_corners_per_frame": corners_per_frame,
+                       "parallelism": f"frame-sharded x{world}, no collective", "cpus_per_rank": rig.numa,
+                       "l2": f"inputs ({n * H * W / 1e6:.0f} MB per step) exceed the 126 MB L2; no explicit flush", "kp_capacity": cap},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "roofline": roof, "stages": stage_report, "cpu_baseline": cpu, "clocks": clocks}
+    if parity:
+        line.update({"parity_checked_frames": parity["parity_checked_frames"], "parity_ok": parity["parity_ok"], "parity": parity})
+    if secondary:
+        line["secondary"] = secondary
+    print(json.dumps(line))
+    rig.finish()
+    return 0
+
+
+def knn_measure(args, rig, ctx, bb, nq, nt_total, steps, full_report=False):
+    """Brute-force Hamming 2-NN of nq queries against nt_total 512-bit train rows sharded contiguously over the ranks
+    (rank r draws its shard from seed 6 + r; the global train set is their concatenation).  Collective on all ranks;
+    returns the report on rank 0."""
+    from ethzasl_brisk_b200.distributed import shard_range, sharded_knn
+    torch, dev, world, rank = rig.torch, rig.dev, rig.world, rig.rank
+    begin, end = shard_range(nt_total, rank, world)
+    q = torch.from_numpy(bb.random_descriptors(nq, 64, 5)).to(dev)
+    t = torch.from_numpy(bb.random_descriptors(end - begin, 64, 6 + rank)).to(dev)
+    m = bb.BruteForceMatcher(ctx=ctx)
+    variants, res = {}, None
+    for name, variant in (("popc", 0), ("tensor_core", 1)):
+        if variant == 0 and full_report and not args.knn_popc:
+            continue
+        ctx.set_knn_variant(variant)
+        fn = (lambda: sharded_knn(m, q, t, 2, begin)) if world > 1 else (lambda: m.knn(q, t, 2))
+        res = fn()
+        v_ms, _, _ = rig.timed(fn, steps)
+        variants[name] = {"Gcmp/s": nq * nt_total * steps / (v_ms * 1e-3) / 1e9, "ms": v_ms / steps}
+    best = variants["tensor_core"]   # the default path
+    # end to end: queries and the train shard start in pinned host memory, the result is read back
+    hq, ht = q.cpu().pin_memory(), t.cpu().pin_memory()
+
+    def e2e():
+        qq, tt = hq.to(dev, non_blocking=True), ht.to(dev, non_blocking=True)
+        r = sharded_knn(m, qq, tt, 2, begin) if world > 1 else m.knn(qq, tt, 2)
+        return r[0].cpu(), r[1].cpu()
+    e2e()
+    e_ms, _, _ = rig.timed(e2e, steps)
+    idx, dist_ = (res[0].cpu().numpy(), res[1].cpu().numpy())
+    if rank != 0:
+        return None
+    _, int8_peak, peak_src = measured_peaks()
+    gcmp = best["Gcmp/s"]
+    tops = gcmp * 2 * 512 / 1e3  # 512 MACs = 1024 integer ops per 512-bit comparison on the tensor pipe
+    rep = {"metric": "hamming_knn_k2_512bit", "value": gcmp, "unit": "Gcmp/s", "queries": nq, "train": nt_total, "train_rows_per_rank": end - begin,
+           "ms": best["ms"], "variants": variants, "sharding": (f"train set sharded over {world} ranks, NCCL all-gather of per-shard top-2 keys + merge"
+                                                                 if world > 1 else "one rank, no collective"),
+           "e2e": {"value": nq * nt_total * steps / (e_ms * 1e-3) / 1e9, "unit": "Gcmp/s", "h2d_bytes_per_step": int((nq + end - begin) * 64),
+                   "d2h_bytes_per_step": int(nq * 2 * 8), "ms_per_step": e_ms / steps},
+           "roofline": {"bound": "tensor", "achieved": tops / world, "peak": int8_peak, "unit": "TFLOP/s", "frac": tops / world / int8_peak, "traffic": None,
+                        "peak_source": peak_src + ": 2 x the measured bf16 cuBLAS burst rate (dense int8 runs at twice the bf16 rate)",
+                        "note": "per GPU; integer multiply-adds of the byte-expanded +-1 / 0-1 operands counted like flops (1024 per 512-bit comparison)"}}
+    # parity of the benched result: a random sample of the queries against the reference's own matcher loop on the full train set
     try:
         from oracle import ref
         if ref.available():
             cores = host_cores()
-            sample_frames = uniq.cpu().numpy()[np.arange(min(256, max(UNIQUE, 2 * cores))) % UNIQUE]
-            ref.bench_detect_describe(sample_frames[:2], False, THRESH, OCTAVES, nthreads=min(2, cores))
-            s, _ = ref.bench_detect_describe(sample_frames, False, THRESH, OCTAVES, nthreads=cores)
-            cpu = {"value": len(sample_frames) / s, "unit": UNIT, "cores": cores, "kind": "reference",
-                   "sample": f"{len(sample_frames)} frames drawn from the same {UNIQUE} distinct 1080p frames, unmodified reference (oracle/_ref), {cores} threads"}
-    except Exception as e:  # the baseline is informative; never fail the bench on it
-        cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
-    # ... and of the matcher: the reference's brisk::Hamming primitive in its k-successive-arg-min loop (brute-force-matcher.cc:
-    # 80-162), one std::thread per core over the queries, on a bounded slice of the same descriptors
-    knn_cpu = None
-    try:
-        from oracle import ref
-        if ref.available() and world == 1:
-            cores = host_cores()
-            cq, ct = q[:min(4096, args.knn_q)].cpu().numpy(), t[:min(1000000, args.knn_t)].cpu().numpy()
+            train = np.concatenate([bb.random_descriptors(shard_range(nt_total, r, world)[1] - shard_range(nt_total, r, world)[0], 64, 6 + r)
+                                    for r in range(world)]) if world > 1 else t.cpu().numpy()
+            rng = np.random.default_rng(7)
+            pick = np.sort(rng.choice(nq, size=min(256, nq), replace=False))
+            qs = q.cpu().numpy()[pick]
+            cap_t = min(len(train), max(1, int(4.0e9 // len(pick))))  # bounds the CPU work to a few seconds
+            if cap_t == len(train):
+                i2, d2 = ref.knn(qs, train, 2, nthreads=cores)
+                rep["parity_ok"] = bool(np.array_equal(i2, idx[pick]) and np.array_equal(d2, dist_[pick]))
+                rep["parity_checked_queries"] = int(len(pick))
+            tq = min(4096, nq)
             t0 = time.perf_counter()
-            ref.knn(cq, ct, 2, nthreads=cores)
-            knn_cpu = {"value": len(cq) * len(ct) / (time.perf_counter() - t0) / 1e9, "unit": "Gcmp/s", "cores": cores, "kind": "reference",
-                       "sample": f"{len(cq)} queries x {len(ct)} train rows of the same descriptors, k = 2, {cores} threads"}
+            ref.knn(q.cpu().numpy()[:tq], train[:min(1000000, len(train))], 2, nthreads=cores)
+            rep["cpu_baseline"] = {"value": tq * min(1000000, len(train)) / (time.perf_counter() - t0) / 1e9, "unit": "Gcmp/s", "cores": cores, "kind": "reference",
+                                   "sample": f"{tq} queries x {min(1000000, len(train))} train rows of the same descriptors, k = 2, the reference's Hamming primitive in "
+                                             f"its k-successive-arg-min loop, {cores} threads"}
     except Exception as e:
-        knn_cpu = {"value": None, "unit": "Gcmp/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+        rep["cpu_baseline"] = {"value": None, "unit": "Gcmp/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+    return rep
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic",
-            "config": {"workload": "C3: AGAST(60,4) detect + BRISK2 describe, 1920x1080 synthetic frames", "frames_per_gpu_per_step": n,
-                       "global_frames_per_step": world * n, "keypoints_per_frame": kps_per_frame, "parallelism": f"frame-sharded x{world}, no collective", "cpus_per_rank": numa,
-                       "l2": f"inputs ({n * H * W / 1e6:.0f} MB per step) exceed the 126 MB L2; no explicit flush", "kp_capacity": cap},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "roofline": roof, "stages": stage_report, "cpu_baseline": cpu, "clocks": clocks,
-            "secondary": {"metric": "hamming_knn_k2_512bit", "value": gcmp, "unit": "Gcmp/s", "queries": args.knn_q, "train": args.knn_t,
-                          "ms": knn_ms / 3, "variants": knn_variants, "cpu_baseline": knn_cpu,
-                          "int8_TOPS": gcmp * 1024 / 1e3,
-                          "note": "default = s8 x u8 IMMA (mma.sync m16n8k32) on byte-expanded bits, 512 MACs per comparison; "
-                                  "tensor-pipe activity from ncu is in profiles/"}}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+
+def run_knn(args):
+    """--config C5: the matcher as the headline line (same schema)."""
+    import ethzasl_brisk_b200 as bb
+    rig = Rig(args)
+    ctx = bb.Context(rig.local, stream=rig.stream.cuda_stream, timing=True, workspace_limit=args.workspace_gb << 30)
+    if rig.rank == 0:
+        rig.sampler.mark()
+    rep = knn_measure(args, rig, ctx, bb, args.knn_q, args.knn_t, steps=args.steps, full_report=True)
+    clocks = rig.sampler.stop() if rig.rank == 0 else None
+    if rig.rank == 0:
+        line = {"metric": rep["metric"], "value": rep["value"], "unit": "Gcmp/s", "n_gpus": rig.world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": rep["ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"C5: brute-force Hamming kNN k=2, {args.knn_q} queries x {args.knn_t} train rows, 512-bit, {rep['sharding']}",
+                           "queries": args.knn_q, "train": args.knn_t, "l2": "train set exceeds the 126 MB L2"},
+                "e2e": rep["e2e"], "gpu_launches": 2 * args.steps, "roofline": rep["roofline"], "cpu_baseline": rep.get("cpu_baseline"),
+                "clocks": clocks, "variants": rep["variants"]}
+        for k in ("parity_ok", "parity_checked_queries"):
+            if k in rep:
+                line[k] = rep[k]
+        print(json.dumps(line))
+    rig.finish()
     return 0
 
 
@@ -392,17 +576,27 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames", type=int, default=1024, help="frames per GPU per step")
-    ap.add_argument("--cap", type=int, default=12288, help="key-point capacity per frame")
+    ap.add_argument("--config", default="C3", choices=["C2", "C3", "C4", "C5"])
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the configuration's)")
+    ap.add_argument("--cap", type=int, default=0, help="key-point capacity per frame (default: the configuration's)")
     ap.add_argument("--workspace-gb", type=int, default=32)
-    ap.add_argument("--knn-q", type=int, default=100000)
-    ap.add_argument("--knn-t", type=int, default=1000000)
+    ap.add_argument("--knn-q", type=int, default=None)
+    ap.add_argument("--knn-t", type=int, default=None, help="train rows (C3's secondary metric: per rank; C5: in total)")
+    ap.add_argument("--knn-popc", action="store_true", help="C5: also time the POPC kernel")
+    ap.add_argument("--no-knn", action="store_true", help="C3: skip the secondary matcher metric")
+    ap.add_argument("--parity-frames", type=int, default=8)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.knn_q is None:
+        args.knn_q = 1000000 if args.config == "C5" else 100000
+    if args.knn_t is None:
+        args.knn_t = 10000000 if args.config == "C5" else 1000000
     if args.impl == "reference":
         return run_reference(args)
-    return run_gpu(args)
+    if args.config == "C5":
+        return run_knn(args)
+    return run_frames(args)
 
 
 if __name__ == "__main__":

@@ -105,6 +105,12 @@ class Context:
         self._check(self._lib.brisk_ctx_last_timing(self._h, ms, C.byref(n)))
         return {s: float(ms[i]) for i, s in enumerate(STAGES)}, int(n.value)
 
+    def last_raw_corners(self):
+        """Raw AGAST corners (before NMS) summed over the frames of the last detect call (timing mode)."""
+        n = C.c_int64(0)
+        self._check(self._lib.brisk_ctx_last_raw_corners(self._h, C.byref(n)))
+        return int(n.value)
+
     def sync(self):
         self._check(self._lib.brisk_sync(self._h))
 

@@ -69,6 +69,7 @@ struct brisk_ctx {
   int knn_variant = 1;  // 0: POPC kernel always, 1 (default): tensor-core kernel where it applies (k == 2, 48/64-byte rows)
   float ms[BRISK_STAGE_COUNT] = {};
   int64_t launches = 0;
+  int64_t raw_corners = 0;  // AGAST corners before NMS, summed over the frames of the last call (timing mode only)
   cudaEvent_t ev[2] = {};
   cudaEvent_t entry = nullptr;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
@@ -255,11 +256,11 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
       CU_OK(sl.scales.ensure(c * cap * 4));
     }
     CU_OK(sl.flag.ensure(16));
-    if (sl.h_counts_cap < c + 4) {
+    if (sl.h_counts_cap < 2 * c + 4) {  // counts [c], flags [4], raw corner totals [c] (timing mode)
       if (sl.h_counts) cudaFreeHost(sl.h_counts);
       sl.h_counts = nullptr; sl.h_counts_cap = 0;
-      CU_OK(cudaMallocHost(&sl.h_counts, (c + 4) * sizeof(int32_t)));
-      sl.h_counts_cap = c + 4;
+      CU_OK(cudaMallocHost(&sl.h_counts, (2 * c + 4) * sizeof(int32_t)));
+      sl.h_counts_cap = 2 * c + 4;
     }
   }
   return BRISK_OK;
@@ -401,6 +402,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
   CU_OK(cudaSetDevice(ctx->device));
   memset(ctx->ms, 0, sizeof(ctx->ms));
   ctx->launches = 0;
+  ctx->raw_corners = 0;
   if (n == 0) return BRISK_OK;
   if (det && det->harris) {
     if (det->octaves < 0 || 2 * det->octaves > kMaxLayers) return fail(ctx, BRISK_ERR_UNSUPPORTED, "octaves must be in [0, 6]");
@@ -453,7 +455,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
   for (int si = 0; si < plan.n_slots; ++si) CU_OK(cudaStreamWaitEvent(ctx->slots[si].stream, ctx->entry, 0));
 
   bool truncated = false, corner_overflow = false, internal_error = false, low_score = false;
-  struct Pending { int f0 = 0, c = 0; bool active = false; KeyPoint* d_kps = nullptr; uint8_t* d_desc = nullptr; };
+  struct Pending { int f0 = 0, c = 0; bool active = false, corners = false; KeyPoint* d_kps = nullptr; uint8_t* d_desc = nullptr; };
   Pending pend[2];
 
   // second half of a chunk: wait for its kernels, then copy exactly the produced rows back
@@ -468,6 +470,8 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     else if (flag == 2) internal_error = true;
     else if (flag) corner_overflow = true;
     if (!counts_dev) memcpy(counts + pd.f0, sl.h_counts, (size_t)pd.c * 4);
+    if (pd.corners)
+      for (int f = 0; f < pd.c; ++f) ctx->raw_corners += std::min(sl.h_counts[plan.chunk + 4 + f], plan.ws.corner_cap);
     Timer tm(ctx, &sl);
     tm.mark(7);
     for (int f = 0; f < pd.c; ++f) {
@@ -611,8 +615,13 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     // counts + error flag to pinned host memory; the row copies follow in finish()
     CU_OK(cudaMemcpyAsync(sl.h_counts, d_counts, (size_t)c * 4, cudaMemcpyDeviceToHost, sl.stream));
     CU_OK(cudaMemcpyAsync(sl.h_counts + plan.chunk, sl.flag.p, 8, cudaMemcpyDeviceToHost, sl.stream));
+    // timing mode: the number of raw AGAST corners of every frame (last entry of its layer_start row), for the byte counts of the bench
+    const bool want_corners = ctx->timing && det && !det->harris;
+    if (want_corners)
+      CU_OK(cudaMemcpy2DAsync(sl.h_counts + plan.chunk + 4, 4, ws.layer_start + g.n_layers, (size_t)(kMaxLayers + 1) * 4, 4, (size_t)c,
+                              cudaMemcpyDeviceToHost, sl.stream));
     tm.mark(8);
-    pend[si].f0 = f0; pend[si].c = c; pend[si].active = true; pend[si].d_kps = d_kps; pend[si].d_desc = d_desc;
+    pend[si].f0 = f0; pend[si].c = c; pend[si].active = true; pend[si].corners = want_corners; pend[si].d_kps = d_kps; pend[si].d_desc = d_desc;
     // drain the OTHER slot while this chunk computes
     if (plan.n_slots == 2 && pend[si ^ 1].active) { rc = finish(si ^ 1); if (rc) return rc; }
   }
@@ -731,6 +740,12 @@ int brisk_ctx_last_timing(brisk_ctx* ctx, float* ms, int64_t* launches) {
   if (!ctx) return BRISK_ERR_INVALID;
   if (ms) memcpy(ms, ctx->ms, sizeof(ctx->ms));
   if (launches) *launches = ctx->launches;
+  return BRISK_OK;
+}
+
+int brisk_ctx_last_raw_corners(brisk_ctx* ctx, int64_t* raw_corners) {
+  if (!ctx || !raw_corners) return BRISK_ERR_INVALID;
+  *raw_corners = ctx->raw_corners;
   return BRISK_OK;
 }
 

@@ -70,6 +70,8 @@ int brisk_ctx_enable_timing(brisk_ctx* ctx, int enable);
 enum { BRISK_STAGE_H2D = 0, BRISK_STAGE_PYRAMID, BRISK_STAGE_DETECT, BRISK_STAGE_LISTS, BRISK_STAGE_NMS,
        BRISK_STAGE_INTEGRAL, BRISK_STAGE_DESCRIBE, BRISK_STAGE_D2H, BRISK_STAGE_KNN, BRISK_STAGE_COUNT };
 int brisk_ctx_last_timing(brisk_ctx* ctx, float* ms /* [BRISK_STAGE_COUNT] */, int64_t* launches);
+/* With timing enabled: raw AGAST corners (before scale-space NMS) summed over the frames of the last detect call. */
+int brisk_ctx_last_raw_corners(brisk_ctx* ctx, int64_t* raw_corners);
 
 /* brisk::BriskFeatureDetector(int thresh, int octaves = 3, bool suppressScaleNonmaxima = true)
  * -- reference brisk/include/brisk/brisk-feature-detector.h:51-84. */
