@@ -92,7 +92,7 @@ class Context:
         self._check(self._lib.brisk_ctx_enable_timing(self._h, int(bool(on))))
 
     def set_knn_variant(self, variant):
-        """0: POPC kernel; 1: tensor-core kernel (k == 2, 48/64-byte rows)."""
+        """0: POPC kernel; for k == 2 and 48/64-byte rows 1: mma.sync IMMA kernel, 2 (default): tcgen05 / TMEM / TMA kernel."""
         self._check(self._lib.brisk_ctx_set_knn_variant(self._h, int(variant)))
 
     def set_pipelining(self, on=True):
@@ -139,6 +139,14 @@ class Context:
             out.append(buf[off:off + cw * ch].reshape(ch, cw).copy())
             off += cw * ch
         return out
+
+    def debug_scores(self, img):
+        """Dense FAST 9-16 (the NMS kernels' packed row evaluator) and AGAST 5-8 score planes of one image, threshold 1."""
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w = img.shape
+        a, b = np.zeros((h, w), np.uint8), np.zeros((h, w), np.uint8)
+        self._check(self._lib.brisk_debug_scores(self._h, _ptr(img), w, h, C.c_size_t(w), _ptr(a), _ptr(b)))
+        return a, b
 
     def debug_integral(self, img):
         img = np.ascontiguousarray(img, np.uint8)

@@ -10,7 +10,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libbrisk_b200.so"
-SOURCES = ["pyramid.cu", "detect.cu", "nms.cu", "describe.cu", "hamming.cu", "hamming_mma.cu", "harris.cu", "capi.cu", "pattern.cc"]
+SOURCES = ["pyramid.cu", "detect.cu", "nms.cu", "describe.cu", "hamming.cu", "hamming_mma.cu", "hamming_tc5.cu", "harris.cu", "capi.cu", "pattern.cc"]
 # -fmad=false: the reference is built without FMA contraction and float results
 # are compared bit for bit.  The system g++ is pinned as host
 # compiler (the image's CXX links libstdc++ statically).

@@ -66,7 +66,7 @@ struct brisk_ctx {
   size_t ws_limit = (size_t)8 << 30;
   bool timing = false;
   bool pipelining = true;
-  int knn_variant = 1;  // 0: POPC kernel always, 1 (default): tensor-core kernel where it applies (k == 2, 48/64-byte rows)
+  int knn_variant = 2;  // 0: POPC kernel always; where they apply (k == 2, 48/64-byte rows) 1: mma.sync IMMA kernel, 2 (default): tcgen05 kernel
   float ms[BRISK_STAGE_COUNT] = {};
   int64_t launches = 0;
   int64_t raw_corners = 0;  // AGAST corners before NMS, summed over the frames of the last call (timing mode only)
@@ -74,7 +74,7 @@ struct brisk_ctx {
   cudaEvent_t entry = nullptr;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   Slot slots[2];
-  DevBuf knn_q, knn_t, knn_keys, knn_part, knn_idx, knn_dist, knn_mask, rad_counts, rad_offsets, rad_matches;
+  DevBuf knn_q, knn_t, knn_qx, knn_tx, knn_keys, knn_part, knn_idx, knn_dist, knn_mask, rad_counts, rad_offsets, rad_matches;
 };
 
 struct brisk_detector {
@@ -695,7 +695,7 @@ void brisk_ctx_destroy(brisk_ctx* ctx) {
     if (sl.fork) cudaEventDestroy(sl.fork);
     if (sl.join) cudaEventDestroy(sl.join);
   }
-  DevBuf* bufs[] = {&ctx->knn_q, &ctx->knn_t, &ctx->knn_keys, &ctx->knn_part, &ctx->knn_idx, &ctx->knn_dist,
+  DevBuf* bufs[] = {&ctx->knn_q, &ctx->knn_t, &ctx->knn_qx, &ctx->knn_tx, &ctx->knn_keys, &ctx->knn_part, &ctx->knn_idx, &ctx->knn_dist,
                     &ctx->knn_mask, &ctx->rad_counts, &ctx->rad_offsets, &ctx->rad_matches};
   for (DevBuf* b : bufs) b->release();
   if (ctx->entry) cudaEventDestroy(ctx->entry);
@@ -719,7 +719,7 @@ int brisk_ctx_set_workspace_limit(brisk_ctx* ctx, size_t bytes) {
 }
 
 int brisk_ctx_set_knn_variant(brisk_ctx* ctx, int variant) {
-  if (!ctx || variant < 0 || variant > 1) return BRISK_ERR_INVALID;
+  if (!ctx || variant < 0 || variant > 2) return BRISK_ERR_INVALID;
   ctx->knn_variant = variant;
   return BRISK_OK;
 }
@@ -1141,6 +1141,19 @@ int brisk_debug_nms_ties(brisk_ctx* ctx, int32_t* ties /* [12] of frame 0 of the
 // Hamming matching.
 // ---------------------------------------------------------------------------
 
+// Tensor map over expanded descriptor rows ([rows][kbytes] signed bytes): boxes of 128 rows x 128 bytes, 128B swizzle.
+static int encode_rows_map(brisk_ctx* ctx, const void* base, long long rows, int kbytes, CUtensorMap* map) {
+  cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)std::max<long long>(rows, 128)};
+  cuuint64_t strides[1] = {(cuuint64_t)kbytes};
+  cuuint32_t box[2] = {128, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ctx, BRISK_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return BRISK_OK;
+}
+
 static int knn_keys_impl(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int desc_bytes,
                          int k, int64_t offset, unsigned long long** keys_out, int* kr_out) {
   if (!ctx) return BRISK_ERR_INVALID;
@@ -1160,19 +1173,34 @@ static int knn_keys_impl(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const
     dt = ctx->knn_t.as<uint8_t>();
   }
   const int kr = knn_round_k(k);
-  const bool mma = ctx->knn_variant == 1 && k == 2 && (desc_bytes == 48 || desc_bytes == 64);
-  const int splits = mma ? knn_mma_num_splits(nq, nt) : knn_num_splits(nq, nt);
+  const bool tensor = k == 2 && (desc_bytes == 48 || desc_bytes == 64);
+  const bool mma = ctx->knn_variant == 1 && tensor, tc5 = ctx->knn_variant == 2 && tensor && nq > 0 && nt > 0;
+  const int splits = tc5 ? knn_tc5_num_splits(nq, nt) : (mma ? knn_mma_num_splits(nq, nt) : knn_num_splits(nq, nt));
   CU_OK(ctx->knn_keys.ensure(std::max<size_t>((size_t)nq * kr * 8, 16)));
   if (splits > 1) CU_OK(ctx->knn_part.ensure((size_t)splits * nq * kr * 8));
   if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
-  if (mma)
+  if (tc5) {
+    // descriptor bits -> signed bytes once per call (8x the rows in HBM), then the tcgen05 kernel on TMA-staged tiles
+    CU_OK(ctx->knn_qx.ensure(knn_tc5_expanded_bytes(nq, desc_bytes)));
+    CU_OK(ctx->knn_tx.ensure(knn_tc5_expanded_bytes(nt, desc_bytes)));
+    CU_OK(launch_expand_pm1(dq, nq, desc_bytes, ctx->knn_qx.as<uint8_t>(), ctx->stream));
+    CU_OK(launch_expand_pm1(dt, nt, desc_bytes, ctx->knn_tx.as<uint8_t>(), ctx->stream));
+    CUtensorMap mq, mt;
+    int rc = encode_rows_map(ctx, ctx->knn_qx.p, nq, desc_bytes * 8, &mq);
+    if (rc) return rc;
+    rc = encode_rows_map(ctx, ctx->knn_tx.p, nt, desc_bytes * 8, &mt);
+    if (rc) return rc;
+    CU_OK(launch_hamming_knn2_tc5(mq, nq, mt, nt, desc_bytes, offset, ctx->knn_keys.as<unsigned long long>(),
+                                  ctx->knn_part.as<unsigned long long>(), splits, ctx->stream));
+    ctx->launches = 2;
+  } else if (mma)
     CU_OK(launch_hamming_knn2_mma(dq, nq, dt, nt, desc_bytes, offset, ctx->knn_keys.as<unsigned long long>(),
                                   ctx->knn_part.as<unsigned long long>(), splits, ctx->stream));
   else
     CU_OK(launch_hamming_knn_ex(dq, nq, dt, nt, desc_bytes, k, offset, ctx->knn_keys.as<unsigned long long>(),
                                 ctx->knn_part.as<unsigned long long>(), splits, ctx->stream));
   if (ctx->timing) cudaEventRecord(ctx->ev[1], ctx->stream);
-  ctx->launches = splits > 1 ? 2 : 1;
+  ctx->launches += splits > 1 ? 2 : 1;
   *keys_out = ctx->knn_keys.as<unsigned long long>();
   *kr_out = kr;
   return BRISK_OK;

@@ -1,0 +1,335 @@
+// Brute-force Hamming 2-NN on the 5th-generation tensor cores (sm_100a): tcgen05.mma kind::i8 with TMEM
+// accumulators, operands staged by TMA, top-2 selection straight out of TMEM.
+//
+// Replaces the inner loops of BruteForceMatcher::commonKnnMatchImpl (reference brisk/src/brute-force-matcher.cc:
+// 80-162) and Hamming::SSSE3PopcntofXORed (brisk/include/brisk/internal/hamming-inl.h:85-134) for k = 2 and
+// 48 / 64-byte rows, like hamming_mma.cu (mma.sync IMMA) and hamming.cu (XOR + POPC), which stay as the measured
+// alternatives.
+//
+// Formulation.  Every descriptor bit becomes one signed byte, +1 for a set bit and -1 for a clear one (expanded ONCE
+// per call into HBM, 8 bytes per descriptor byte).  For two rows q, t of K bits,  q . t = K - 2 hamming(q, t),  so the
+// nearest neighbours are the largest dot products and  hamming = (K - q . t) / 2  exactly.
+//
+// Kernel.  A CTA owns 256 queries (two 128-row A tiles, resident in shared memory for the whole kernel: 128 KB for
+// K = 512) and streams its share of the train set in tiles of 128 rows, cut along K into 128-byte chunks (one
+// 16 KB TMA box each, 128B swizzle, K-major) through a six-stage ring.  One thread issues the MMAs: per chunk four
+// K = 32 steps for each A tile, 128 x 128 x 32 each, accumulating in TMEM; the two accumulator sets (2 x 256 columns =
+// all 512 TMEM columns) let the epilogue of tile i overlap the MMAs of tile i + 1.  Eight epilogue warps (one per
+// TMEM lane quadrant and A tile) read the int32 dot products with tcgen05.ld; a thread owns ONE query for the whole
+// kernel, keeps its two best (dot, train index) pairs in registers and only looks closer at a group of 32 columns
+// when the group's maximum beats its current second best (a few dozen times per query over millions of rows).
+// Train rows are met in increasing index order, so a strict comparison reproduces the reference's tie rule (first
+// minimum of a left-to-right scan wins).  Per-split results go to `part` as (hamming << 32 | index) keys, merged by
+// launch_knn_merge like the other variants.
+//
+// Roofline: 512 int8 MACs per 512-bit comparison on the tensor pipe; B traffic from L2 is
+// 128 x 512 B per 256 x 128 comparisons (M = 256 per CTA halves what a single 128-row tile would pull).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace briskb200 {
+
+namespace {
+
+constexpr int kT5M = 128;         // rows of one MMA (= TMEM lanes)
+constexpr int kT5QTiles = 2;      // A tiles per CTA -> 256 queries
+constexpr int kT5N = 128;         // train rows per tile (MMA N)
+constexpr int kT5Chunk = 128;     // bytes of K per shared-memory chunk: one row of a 128B swizzle atom
+constexpr int kT5ChunkBytes = kT5N * kT5Chunk;  // 16 KB (A and B chunks have the same shape)
+constexpr int kT5Stages = 6;
+constexpr int kT5EpiWarps = 8;
+constexpr int kT5Threads = (2 + kT5EpiWarps) * 32;  // warp 0: TMA producer, warp 1: TMEM owner + MMA issuer, 2..9: epilogue
+constexpr int kT5TmemCols = 512;
+constexpr unsigned long long kT5KeyNone = ~0ull;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// Shared-memory matrix descriptor of a K-major operand chunk stored as rows of 128 bytes under the 128B swizzle
+// (what a TMA box of 128 bytes x R rows with CU_TENSOR_MAP_SWIZZLE_128B writes): start address >> 4 in bits 0-13,
+// leading byte offset (unused for swizzled K-major layouts) 1, stride byte offset = 1024 B between 8-row groups in
+// bits 32-45, descriptor version 1 (sm_100) in bits 46-47, layout type 2 = SWIZZLE_128B in bits 61-63.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// Instruction descriptor, kind::i8: D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), both K-major, N >> 3 in bits
+// 17-22, M >> 4 in bits 24-28.
+constexpr uint32_t kT5Idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kT5N >> 3) << 17) | ((uint32_t)(kT5M >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kT5Idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+// All MMAs issued so far by this thread arrive on `bar` when they complete (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// 32 consecutive TMEM columns of the warp's 32 lanes: thread = lane (row), v[j] = column j.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }
+
+}  // namespace
+
+// KC = chunks along K: 4 for 64-byte rows (512 signed bytes), 3 for 48-byte rows.
+template <int KC>
+__global__ void __launch_bounds__(kT5Threads, 1)
+hamming_knn2_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, long long nq,
+                        long long nt, long long rows_per_split, long long train_index_offset,
+                        unsigned long long* __restrict__ part) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // swizzle atoms are 1024-byte aligned
+  uint8_t* sA = smem;                                         // [2 tiles][KC chunks][128 rows x 128 B]
+  uint8_t* sB = sA + kT5QTiles * KC * kT5ChunkBytes;          // [stages][128 rows x 128 B]
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + kT5Stages * kT5ChunkBytes);
+  uint64_t* bar_empty = bar_full + kT5Stages;
+  uint64_t* bar_a = bar_empty + kT5Stages;
+  uint64_t* bar_tfull = bar_a + 1;    // [2] accumulator set ready for the epilogue
+  uint64_t* bar_tempty = bar_tfull + 2;  // [2] accumulator set drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long q0 = (long long)blockIdx.x * (kT5QTiles * kT5M);
+  const long long t_begin = (long long)blockIdx.y * rows_per_split;
+  const long long t_end = min(nt, t_begin + rows_per_split);
+  const int ntiles = t_end > t_begin ? (int)((t_end - t_begin + kT5N - 1) / kT5N) : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < kT5Stages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(bar_a, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], kT5EpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kT5TmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- TMA producer ----
+    if (lane == 0 && ntiles > 0) {
+      mbar_expect_tx(bar_a, kT5QTiles * KC * kT5ChunkBytes);
+      for (int a = 0; a < kT5QTiles; ++a)
+        for (int c = 0; c < KC; ++c) tma_load_2d(sA + (a * KC + c) * kT5ChunkBytes, &map_q, c * kT5Chunk, (int)(q0 + a * kT5M), bar_a);
+      int it = 0;
+      for (int i = 0; i < ntiles; ++i)
+        for (int c = 0; c < KC; ++c, ++it) {
+          const int s = it % kT5Stages;
+          mbar_wait(&bar_empty[s], ((it / kT5Stages) & 1) ^ 1);   // a fresh barrier passes the parity-1 wait
+          mbar_expect_tx(&bar_full[s], kT5ChunkBytes);
+          tma_load_2d(sB + s * kT5ChunkBytes, &map_t, c * kT5Chunk, (int)(t_begin + (long long)i * kT5N), &bar_full[s]);
+        }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer (one thread) ----
+    if (lane == 0 && ntiles > 0) {
+      mbar_wait(bar_a, 0);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      int it = 0;
+      for (int i = 0; i < ntiles; ++i) {
+        const int b = i & 1;
+        mbar_wait(&bar_tempty[b], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int c = 0; c < KC; ++c, ++it) {
+          const int s = it % kT5Stages;
+          mbar_wait(&bar_full[s], (it / kT5Stages) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kT5Chunk / 32; ++k) {
+            const uint64_t bd = umma_desc(b_base + s * kT5ChunkBytes + k * 32);
+#pragma unroll
+            for (int a = 0; a < kT5QTiles; ++a)
+              umma_i8(tmem_base + (uint32_t)(b * 256 + a * kT5N), umma_desc(a_base + (a * KC + c) * kT5ChunkBytes + k * 32), bd,
+                      (c | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&bar_empty[s]);   // the stage is free once these MMAs have read it
+        }
+        umma_commit(&bar_tfull[b]);     // both accumulators of the set are complete
+      }
+    }
+  } else {
+    // ---- epilogue: thread = one query row ----
+    const int quad = warp & 3, a = (warp - 2) >> 2;
+    const int row = a * kT5M + quad * 32 + lane;
+    int d0 = -100000, d1 = -100000;       // two largest dot products so far (d0 >= d1) ...
+    unsigned i0 = 0xffffffffu, i1 = 0xffffffffu;  // ... and their (global) train indices
+    for (int i = 0; i < ntiles; ++i) {
+      const int b = i & 1;
+      mbar_wait(&bar_tfull[b], (i >> 1) & 1);
+      tc_fence_after();
+      const long long tile_base = t_begin + (long long)i * kT5N;
+      const int valid = (int)min((long long)kT5N, t_end - tile_base);
+      const unsigned idx_base = (unsigned)(train_index_offset + tile_base);
+#pragma unroll 1
+      for (int cc = 0; cc < kT5N / 32; ++cc) {
+        int v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * 256 + a * kT5N + cc * 32), v);
+        int m = max3(v[0], v[1], v[2]);
+#pragma unroll
+        for (int j = 3; j + 1 < 32; j += 2) m = max3(m, v[j], v[j + 1]);
+        m = max(m, v[31]);
+        if (m > d1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = cc * 32 + j;
+            if (v[j] > d1 && col < valid) {
+              if (v[j] > d0) { d1 = d0; i1 = i0; d0 = v[j]; i0 = idx_base + col; }
+              else { d1 = v[j]; i1 = idx_base + col; }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[b]);
+    }
+    if (q0 + row < nq) {
+      constexpr int kBits = KC * kT5Chunk;
+      unsigned long long* out = part + ((long long)blockIdx.y * nq + q0 + row) * 2;
+      out[0] = i0 == 0xffffffffu ? kT5KeyNone : ((unsigned long long)((kBits - d0) >> 1) << 32) | i0;
+      out[1] = i1 == 0xffffffffu ? kT5KeyNone : ((unsigned long long)((kBits - d1) >> 1) << 32) | i1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kT5TmemCols) : "memory");
+  }
+}
+
+// Descriptor bits -> signed bytes (+1 / -1), 32 per input word.
+__global__ void __launch_bounds__(256)
+expand_pm1_kernel(const uint32_t* __restrict__ src, long long n_words, uint4* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_words) return;
+  const uint32_t w = __ldg(src + i);
+  uint32_t o[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    // bit j of the nibble -> top bit of byte j (multiply), replicated over the byte (PRMT sign mode): 0x00 / 0xff
+    uint32_t mask;
+    asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(mask) : "r"(((w >> (4 * n)) & 0xfu) * 0x10204080u));
+    o[n] = (mask & 0x01010101u) | ~mask;   // set -> 0x01, clear -> 0xff
+  }
+  dst[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
+  dst[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+size_t knn_tc5_expanded_bytes(long long rows, int desc_bytes) {
+  const long long r = rows < kT5M ? kT5M : rows;   // the tensor map's row extent is at least one box
+  return (size_t)r * desc_bytes * 8;
+}
+
+cudaError_t launch_expand_pm1(const uint8_t* src, long long rows, int desc_bytes, uint8_t* dst, cudaStream_t stream) {
+  const long long n_words = rows * desc_bytes / 4;
+  if (n_words <= 0) return cudaSuccess;
+  expand_pm1_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(src), n_words,
+                                                                             reinterpret_cast<uint4*>(dst));
+  return cudaGetLastError();
+}
+
+// Splits of the train set: enough CTAs for the 148 SMs, then the smallest count whose last wave is >= 95 % full.
+int knn_tc5_num_splits(long long nq, long long nt) {
+  const long long qblocks = (nq + kT5QTiles * kT5M - 1) / (kT5QTiles * kT5M);
+  long long max_splits = (nt + 16 * kT5N - 1) / (16 * kT5N);
+  if (max_splits > 64) max_splits = 64;
+  if (max_splits < 1) max_splits = 1;
+  long long best = 1;
+  double best_eff = 0.0;
+  for (long long s = 1; s <= max_splits; ++s) {
+    const long long ctas = qblocks * s;
+    const long long waves = (ctas + 147) / 148;
+    const double eff = (double)ctas / (double)(waves * 148);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+    if (eff >= 0.95) break;
+  }
+  return (int)best;
+}
+
+template <int KC>
+static cudaError_t launch_tc5(const CUtensorMap& mq, const CUtensorMap& mt, long long nq, long long nt, long long off,
+                              unsigned long long* dst, int splits, long long rows_per_split, cudaStream_t stream) {
+  const size_t smem = (size_t)(kT5QTiles * KC + kT5Stages) * kT5ChunkBytes + 1024 /* alignment */ + 256 /* barriers */;
+  cudaError_t e = cudaFuncSetAttribute(hamming_knn2_tc5_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)((nq + kT5QTiles * kT5M - 1) / (kT5QTiles * kT5M)), splits);
+  hamming_knn2_tc5_kernel<KC><<<grid, kT5Threads, smem, stream>>>(mq, mt, nq, nt, rows_per_split, off, dst);
+  return cudaGetLastError();
+}
+
+// k == 2 only; map_q / map_t: tensor maps over the EXPANDED rows (knn_tc5_encode_map in capi.cu); keys [nq][2];
+// part: scratch [splits][nq][2] (unused when splits == 1).
+cudaError_t launch_hamming_knn2_tc5(const CUtensorMap& map_q, long long nq, const CUtensorMap& map_t, long long nt, int desc_bytes,
+                                    long long train_index_offset, unsigned long long* keys, unsigned long long* part,
+                                    int splits, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  long long rows_per_split = ((nt + splits - 1) / splits + kT5N - 1) / kT5N * kT5N;
+  if (rows_per_split <= 0) rows_per_split = kT5N;
+  unsigned long long* dst = splits == 1 ? keys : part;
+  cudaError_t e;
+  if (nt <= 0) {
+    e = cudaMemsetAsync(keys, 0xff, (size_t)nq * 2 * 8, stream);   // no train rows: every key is "none"
+    return e;
+  }
+  if (desc_bytes == 64) e = launch_tc5<4>(map_q, map_t, nq, nt, train_index_offset, dst, splits, rows_per_split, stream);
+  else if (desc_bytes == 48) e = launch_tc5<3>(map_q, map_t, nq, nt, train_index_offset, dst, splits, rows_per_split, stream);
+  else return cudaErrorInvalidValue;
+  if (e != cudaSuccess) return e;
+  if (splits > 1) e = launch_knn_merge(part, splits, nq, 2, keys, stream);
+  return e;
+}
+
+}  // namespace briskb200

@@ -44,31 +44,48 @@ __device__ __forceinline__ void unpack_corner(uint32_t c, int* x, int* y, int* l
   *x = c & 0x1fff; *y = (c >> 13) & 0x1fff; *layer = c >> 26;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 nms_prefix_kernel(PyramidGeom g, DetectWorkspace ws) {
   const int frame = blockIdx.y, lane = threadIdx.x & 31;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = min(ws.layer_start[(long long)frame * (kMaxLayers + 1) + g.n_layers], ws.corner_cap);
   if (blockIdx.x * blockDim.x >= n) return;
-  bool on = false;
+  bool on = false, tie = false;
+  int x = 0, y = 0, layer = -1;
   if (k < n) {
-    int x, y, layer;
     unpack_corner(ws.corners[(long long)frame * ws.corner_cap + k], &x, &y, &layer);
     const LayerView v = make_view(g, ws, frame, layer);
     uint8_t fwin[25];
+#pragma unroll
+    for (int i = 0; i < 25; ++i) fwin[i] = 0;
     nms_prefix(v, x, y, fwin);
     const uint16_t ev = v.cm[(long long)y * v.pitch + x];
     on = ev & (kCmAccept | kCmTie);
-    if (ev & kCmTie) {
-      // per-layer list of the tying corners (any order) for the chain kernel, in the frame's key-point
-      // scratch, which is free until refine_kernel runs; layer l's list starts at its first corner slot
-      const int pos = atomicAdd(&ws.n_ties[frame * kTieStride + layer], 1);
-      reinterpret_cast<int2*>(ws.kp_tmp + (long long)frame * ws.corner_cap)[ws.layer_start[(long long)frame * (kMaxLayers + 1) + layer] + pos] =
-          make_int2(k, x | (y << 16));
-      uint8_t* dst = ws.fwin + ((long long)frame * ws.corner_cap + k) * 32;
+    tie = ev & kCmTie;
+    if (on) {
+      // the score window: the chain kernel reads all of it (tying corners), refine_kernel its inner 3x3
+      uint32_t wds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-      for (int i = 0; i < 25; ++i) dst[i] = fwin[i];
+      for (int i = 0; i < 25; ++i) wds[i >> 2] |= (uint32_t)fwin[i] << (8 * (i & 3));
+      uint4* dst = reinterpret_cast<uint4*>(ws.fwin + ((long long)frame * ws.corner_cap + k) * 32);
+      dst[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+      dst[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
     }
+  }
+  // per-layer list of the tying corners (any order) for the chain kernel, in the frame's key-point scratch, which
+  // is free until refine_kernel runs; layer l's list starts at its first corner slot.  One atomic per warp and layer
+  // (the corners of a warp are consecutive in the layer-major list: nearly always one layer).
+  unsigned todo = __ballot_sync(0xffffffffu, tie);
+  while (todo) {
+    const int ll = __shfl_sync(0xffffffffu, layer, __ffs(todo) - 1);
+    const unsigned peers = __ballot_sync(0xffffffffu, tie && layer == ll);
+    int base = 0;
+    if (lane == __ffs(peers) - 1) base = atomicAdd(&ws.n_ties[frame * kTieStride + ll], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+    if (tie && layer == ll)
+      reinterpret_cast<int2*>(ws.kp_tmp + (long long)frame * ws.corner_cap)[ws.layer_start[(long long)frame * (kMaxLayers + 1) + ll] + base +
+                                                                             __popc(peers & ((1u << lane) - 1u))] = make_int2(k, x | (y << 16));
+    todo &= ~peers;
   }
   // corners that survive (accepted or tying) go on to the scale checks: compacted (order within a warp
   // kept, warps in any order), so that nms_checks_kernel runs full warps
@@ -221,7 +238,7 @@ __device__ __forceinline__ void warp_mark_above(const LayerView& nb, int layer, 
   if (((above_steps >> 8) & 1) && lane < 9) mark_px(nb, (above_argmax & 0xffff) + lane % 3 - 1, (above_argmax >> 16) + lane / 3 - 1);
 }
 
-__global__ void __launch_bounds__(128, 5)
+__global__ void __launch_bounds__(128, 4)
 nms_checks_kernel(PyramidGeom g, DetectWorkspace ws) {
   const int frame = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -264,9 +281,11 @@ nms_checks_kernel(PyramidGeom g, DetectWorkspace ws) {
 // a pending one is decided and published (one 16-bit store; a concurrent reader may or may not see it,
 // both are fine), the others form the list of the next pass.  The raster-earliest pending corner is
 // always decidable, so every pass makes progress.
-constexpr int kChainThreads = 1024;
+// Two 512-thread CTAs per SM: the passes of one frame (barriers, short lists on the upper layers) leave the SM idle
+// part of the time; a second frame fills those gaps (12.8 -> 9.0 ms per 1024 frames against one 1024-thread CTA).
+constexpr int kChainThreads = 512;
 constexpr int kChainWarps = kChainThreads / 32;
-__global__ void __launch_bounds__(kChainThreads, 1)
+__global__ void __launch_bounds__(kChainThreads, 1024 / kChainThreads)
 nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag) {
   __shared__ FrameViews fv;
   __shared__ int s_next[2];
@@ -346,7 +365,7 @@ refine_kernel(PyramidGeom g, DetectWorkspace ws) {
   if (!(e & kCmAccept) || !(e & kCmChecks)) return;
   const CheckResult r = *reinterpret_cast<const CheckResult*>(ws.checks + slot * 8);
   KeyPoint kp;
-  if (refine_emit1(own, g.n_layers, layer, x, y, r, &kp)) {
+  if (refine_emit1(own, g.n_layers, layer, x, y, r, &kp, ws.fwin + slot * 32)) {
     ws.kp_tmp[slot] = kp;
     ws.kp_valid[slot] = 1;
   }
@@ -541,7 +560,14 @@ dense_scores_kernel(LayerGeom L, const uint8_t* __restrict__ img, uint8_t* __res
   const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
   if (x >= L.w || y >= L.h) return;
   const LayerView v{img, nullptr, nullptr, L.w, L.h, L.pitch, L.scale, L.offset};
-  out916[(long long)y * L.w + x] = in_border(v, x, y) ? 0 : (uint8_t)fastF(v, x, y);
+  // the packed row evaluator of the NMS kernels (fast_packed.cuh), at every alignment: pixel x is lane (x % 6) of the run
+  // starting at x - x % 6 for odd rows, and lane (x % 4) of a four-pixel run for even rows
+  uint32_t f[3];
+  int lane;
+  if (y & 1) { lane = x % 6; fast916_row<3>(img, L.pitch, L.h, x - lane, y, f); }
+  else { lane = x % 4; fast916_row<2>(img, L.pitch, L.h, x - lane, y, f); }
+  const int packed = (int)((f[lane >> 1] >> ((lane & 1) * 16)) & 0xffffu);
+  out916[(long long)y * L.w + x] = in_border(v, x, y) ? 0 : (uint8_t)packed;
   out58[(long long)y * L.w + x] = (uint8_t)score58(v, x, y);
 }
 

@@ -31,6 +31,7 @@
 // very same code on the CPU against the oracle.
 #pragma once
 #include "brisk_math.cuh"
+#include "fast_packed.cuh"
 
 namespace briskb200 {
 
@@ -125,12 +126,32 @@ BRISK_HD void fill_tile(const LayerView& L, int xa, int ya, int xb, int yb, Scor
 #ifdef BRISK_TILE_CHECK
   t->x1 = xb; t->y1 = yb; t->violations = (xb - xa > 3 || yb - ya > 3) ? 1 : 0;
 #endif
+#ifdef __CUDA_ARCH__
+  // device: one packed evaluation per tile row (four pixels at once, fast_packed.cuh); corners keep their T
+#pragma unroll 1
+  for (int y = ya; y <= yb; ++y) {
+    uint32_t f[2];
+    fast916_row<2>(L.img, L.pitch, L.h, xa, y, f);
+    unsigned long long rowbits = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int x = xa + j;
+      if (x > xb || in_border(L, x, y)) continue;
+      const int tt = L.cm[(long long)y * L.pitch + x] & kCmT;
+      const int v = tt ? tt : (int)((f[j >> 1] >> ((j & 1) * 16)) & 0xffu);
+      rowbits |= (unsigned long long)v << (8 * j);
+    }
+    const int i = (y - ya) << 2;
+    if (i < 8) t->lo |= rowbits << (i << 3); else t->hi |= rowbits << ((i & 7) << 3);
+  }
+#else
   for (int y = ya; y <= yb; ++y)
     for (int x = xa; x <= xb; ++x) {
       const int i = ((y - ya) << 2) + (x - xa);
       const unsigned long long v = (unsigned long long)score1(L, x, y);
       if (i < 8) t->lo |= v << (i << 3); else t->hi |= v << ((i & 7) << 3);
     }
+#endif
 }
 
 // BriskLayer::GetAgastScore(float, float, 1) (brisk-layer.cc:147-161): bilinear
@@ -167,11 +188,26 @@ BRISK_HD float patch3x3(const LayerView& L, int x, int y, float* dx, float* dy, 
 // Pixel rectangle of the neighbouring layer that a scan of the patch
 // [x_1,x1]x[y_1,y1] can look up: the 2x2 cells of its float positions, and the
 // 3x3 neighbourhoods of its interior positions / its arg-max.
-BRISK_HD void fill_scan_tile(const LayerView& nb, float x_1, float x1, float y_1, float y1, ScoreTile* t) {
+BRISK_HD void scan_tile_bounds(float x_1, float x1, float y_1, float y1, int* xa, int* ya, int* xb_, int* yb_) {
   const int xb = (int)(x_1 + 1), xe = (int)x1, yb = (int)(y_1 + 1), ye = (int)y1;
   // the arg-max can sit at xb or xe even when the interior is empty (xe < xb); its 3x3 patch is read too
-  fill_tile(nb, imin((int)x_1, imin(xb, xe) - 1), imin((int)y_1, imin(yb, ye) - 1), imax((int)x1 + 1, imax(xe, xb) + 1),
-            imax((int)y1 + 1, imax(ye, yb) + 1), t);
+  *xa = imin((int)x_1, imin(xb, xe) - 1); *ya = imin((int)y_1, imin(yb, ye) - 1);
+  *xb_ = imax((int)x1 + 1, imax(xe, xb) + 1); *yb_ = imax((int)y1 + 1, imax(ye, yb) + 1);
+}
+BRISK_HD void fill_scan_tile(const LayerView& nb, float x_1, float x1, float y_1, float y1, ScoreTile* t) {
+  int xa, ya, xb, yb;
+  scan_tile_bounds(x_1, x1, y_1, y1, &xa, &ya, &xb, &yb);
+  fill_tile(nb, xa, ya, xb, yb, t);
+}
+// The same tile from 16 score bytes computed beforehand (row stride 4, origin = the tile's first pixel; nms.cu's
+// nms_windows_kernel evaluates them with one lane per pixel).
+BRISK_HD void load_scan_tile(const unsigned long long* pre, float x_1, float x1, float y_1, float y1, ScoreTile* t) {
+  int xa, ya, xb, yb;
+  scan_tile_bounds(x_1, x1, y_1, y1, &xa, &ya, &xb, &yb);
+  t->lo = pre[0]; t->hi = pre[1]; t->x0 = xa; t->y0 = ya;
+#ifdef BRISK_TILE_CHECK
+  t->x1 = xb; t->y1 = yb; t->violations = (xb - xa > 3 || yb - ya > 3) ? 1 : 0;
+#endif
 }
 
 // Shared scan of GetScoreMaxAbove (brisk-scale-space.cc:757-863) and
@@ -274,13 +310,14 @@ BRISK_HD void below_patch(int layer, int x, int y, float* x_1, float* x1, float*
 // neighbouring layer.  Pure; the cache footprint of the scan is returned (it matters for the layer above
 // only: look-ups on the layer below land on a layer whose own NMS is already finished).
 BRISK_HD float score_max_side(bool below, const LayerView& nb, int layer, int x, int y, int thr, bool* ismax, float* dx,
-                              float* dy, AboveFootprint* fp, int* tile_violations) {
+                              float* dy, AboveFootprint* fp, int* tile_violations, const unsigned long long* pre = nullptr) {
   *ismax = false;
   float x_1, x1, y_1, y1;
   if (below) below_patch(layer, x, y, &x_1, &x1, &y_1, &y1);
   else above_patch(layer, x, y, &x_1, &x1, &y_1, &y1);
   ScoreTile tile;
-  fill_scan_tile(nb, x_1, x1, y_1, y1, &tile);
+  if (pre) load_scan_tile(pre, x_1, x1, y_1, y1, &tile);
+  else fill_scan_tile(nb, x_1, x1, y_1, y1, &tile);
   float max; int mx = 0, my = 0, steps = 0;
   fp->completed = 0; fp->mx = 0; fp->my = 0;
   const bool ok = scan_patch(below, tile, x_1, x1, y_1, y1, thr + kDropThreshold, &max, &mx, &my, &steps);
@@ -355,48 +392,128 @@ done:
 // stores the FAST scores of the 5x5 neighbourhood (row-major, clipped at 0;
 // entries of border pixels and of corners are unused) for phase 3.
 // ---------------------------------------------------------------------------
-BRISK_HD void nms_prefix(const LayerView& L, int x, int y, uint8_t fwin[25]) {
-  const long long o = (long long)y * L.pitch + x;
-  const int center = L.cm[o] & kCmT;
+// One entry of the 5x5 score window around a corner (row-major, offsets -2..2): on the eight neighbours the value
+// IsMax2D's look-up returns (T at a corner, else the FAST score clipped at 0), on the outer ring the FAST score
+// (0 at corners: their cache byte is their T, which tie_pixel_value takes from the corner map), 0 at the centre
+// and on border pixels.  `t` = corner-map T of the pixel, F = its clipped FAST score (only read where t == 0).
+BRISK_HD int window_value(int wx, int wy, bool border, int t, int F) {
+  if ((wx == 0 && wy == 0) || border) return 0;
+  if (wx >= -1 && wx <= 1 && wy >= -1 && wy <= 1) return t ? t : F;
+  return t ? 0 : F;
+}
+
+BRISK_HD void own_window(const LayerView& L, int x, int y, uint8_t own[25]) {
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+  for (int i = 0; i < 25; ++i) {
+    const int wx = i % 5 - 2, wy = i / 5 - 2;
+    const int qx = x + wx, qy = y + wy;
+    const bool border = in_border(L, qx, qy);
+    const int t = border ? 0 : (L.cm[(long long)qy * L.pitch + qx] & kCmT);
+    const int F = (border || t || (wx == 0 && wy == 0)) ? 0 : fastF(L, qx, qy);
+    own[i] = (uint8_t)window_value(wx, wy, border, t, F);
+  }
+}
+
+// The eight comparisons from the window: corner-map entry of the corner (calls = look-ups made up to and including
+// the first neighbour that exceeds the centre).
+BRISK_HD uint16_t prefix_entry(int center, const uint8_t own[25]) {
   int calls = 8;
   bool tie = false, rejected = false;
-  int f8[8];
 #ifdef __CUDA_ARCH__
-#pragma unroll 1  // one copy of the score code: the kernels are bound by instruction fetch otherwise
+#pragma unroll
 #endif
   for (int j = 0; j < 8; ++j) {
     int dx, dy;
     isMax2dOffset(j, &dx, &dy);
-    const int qx = x + dx, qy = y + dy;
-    int v;
-    if (in_border(L, qx, qy)) v = 0;
-    else {
-      const int t = L.cm[(long long)qy * L.pitch + qx] & kCmT;
-      v = t ? t : fastF(L, qx, qy);
+    const int v = own[(dy + 2) * 5 + dx + 2];
+    if (!rejected) {
+      if (v > center) { calls = j + 1; rejected = true; }
+      else if (v == center) tie = true;
     }
-    f8[j] = v;
-    if (v > center) { calls = j + 1; rejected = true; break; }
-    if (v == center) tie = true;
   }
   uint16_t e = (uint16_t)(center | (calls << kCmCallsShift));
   if (rejected) e |= kCmDecided;
   else if (!tie) e |= (uint16_t)(kCmDecided | kCmAccept);
   else e |= kCmTie;
-  L.cm[o] = e;
-  if (!rejected && tie) {
-#ifdef __CUDA_ARCH__
+  return e;
+}
+
+#ifdef __CUDACC__
+// Rows [r0, r1] of the window (offsets -2..2) from packed row evaluations: six pixels x-2..x+3 per row (one copy of the
+// evaluator's code for all rows; a row's five bytes go to its own 64-bit register, so nothing is indexed dynamically).
+struct OwnWindowRegs { unsigned long long r[5]; };
+__device__ __forceinline__ void own_window_rows(const LayerView& L, int x, int y, int r0, int r1, OwnWindowRegs* w) {
 #pragma unroll 1
-#endif
-    for (int i = 0; i < 25; ++i) {
-      const int wx = i % 5 - 2, wy = i / 5 - 2;
-      const int qx = x + wx, qy = y + wy;
-      int v;
-      if (wx >= -1 && wx <= 1 && wy >= -1 && wy <= 1 && (wx || wy)) v = f8[isMax2dIndex(wx, wy)];
-      else if ((wx == 0 && wy == 0) || in_border(L, qx, qy)) v = 0;
-      else v = (L.cm[(long long)qy * L.pitch + qx] & kCmT) ? 0 : fastF(L, qx, qy);
-      fwin[i] = (uint8_t)v;
+  for (int wy = r0; wy <= r1; ++wy) {
+    const int qy = y + wy;
+    uint32_t f[3];
+    fast916_row<3>(L.img, L.pitch, L.h, x - 2, qy, f);
+    unsigned long long rowv = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int wx = j - 2, qx = x + wx;
+      const bool border = in_border(L, qx, qy);
+      const int t = border ? 0 : (L.cm[(long long)qy * L.pitch + qx] & kCmT);
+      // (wy is only used for "inner 3x3 or not": rows -1..1 all behave like row 0 except for the centre)
+      const int v = window_value(wx, wy == 0 ? 0 : (wy == -1 || wy == 1 ? 1 : 2), border, t, (int)((f[j >> 1] >> ((j & 1) * 16)) & 0xffu));
+      rowv |= (unsigned long long)v << (8 * j);
     }
+    if (wy == -2) w->r[0] = rowv;
+    else if (wy == -1) w->r[1] = rowv;
+    else if (wy == 0) w->r[2] = rowv;
+    else if (wy == 1) w->r[3] = rowv;
+    else w->r[4] = rowv;
   }
+}
+#endif
+
+// Window + corner-map entry of one corner.  Host: the whole window.  Device: the three middle rows first (they hold
+// the eight neighbours); the outer rows only for a corner that ties -- nothing else reads them.
+BRISK_HD void nms_prefix(const LayerView& L, int x, int y, uint8_t fwin[25]) {
+  const long long o = (long long)y * L.pitch + x;
+#ifdef __CUDA_ARCH__
+  OwnWindowRegs w;
+  w.r[0] = w.r[1] = w.r[2] = w.r[3] = w.r[4] = 0;
+  own_window_rows(L, x, y, -1, 1, &w);
+#pragma unroll
+  for (int i = 5; i < 20; ++i) fwin[i] = (uint8_t)(w.r[i / 5] >> (8 * (i % 5)));
+  const uint16_t e = prefix_entry(L.cm[o] & kCmT, fwin);
+  L.cm[o] = e;
+  if (e & kCmTie) {
+    own_window_rows(L, x, y, -2, -2, &w);
+    own_window_rows(L, x, y, 2, 2, &w);
+  }
+#pragma unroll
+  for (int i = 0; i < 25; ++i) fwin[i] = (uint8_t)(w.r[i / 5] >> (8 * (i % 5)));
+#else
+  own_window(L, x, y, fwin);
+  L.cm[o] = prefix_entry(L.cm[o] & kCmT, fwin);
+#endif
+}
+
+// Scores of the two scan tiles of a corner (the layer above: bytes 0..15, the layer below: bytes 16..31, row stride 4
+// from the tile's first pixel; for layer 0 bytes 16..24 hold the nine 5-8 scores of :558-592, s[3 * column + row]).
+// Scalar statement of what nms_windows_kernel computes with one lane per byte.
+BRISK_HD int side_tile_value(const LayerView& below, const LayerView& L, const LayerView& above, int n_layers, int layer, int x, int y,
+                             int i) {
+  const bool lower = i >= 16;
+  const int l = i & 15;
+  if (lower && layer == 0) return l < 9 ? score58(L, x + l / 3 - 1, y + l % 3 - 1) : 0;
+  if (lower ? layer == 0 : layer == n_layers - 1) return 0;
+  float x_1, x1, y_1, y1;
+  if (lower) below_patch(layer, x, y, &x_1, &x1, &y_1, &y1);
+  else above_patch(layer, x, y, &x_1, &x1, &y_1, &y1);
+  int xa, ya, xb, yb;
+  scan_tile_bounds(x_1, x1, y_1, y1, &xa, &ya, &xb, &yb);
+  const int tx = xa + (l & 3), ty = ya + (l >> 2);
+  if (tx > xb || ty > yb) return 0;
+  return score1(lower ? below : above, tx, ty);
+}
+BRISK_HD void side_tiles(const LayerView& below, const LayerView& L, const LayerView& above, int n_layers, int layer, int x, int y,
+                         uint8_t tiles[32]) {
+  for (int i = 0; i < 32; ++i) tiles[i] = n_layers == 1 ? 0 : (uint8_t)side_tile_value(below, L, above, n_layers, layer, x, y, i);
 }
 
 // ---------------------------------------------------------------------------
@@ -416,7 +533,8 @@ struct CheckResult {
 // `center_in` < 0: the corner's own score is its corner-map entry (detection mode); otherwise the caller
 // passes GetAgastScore(x, y, 1) of a point that need not be a corner (provided-key-point mode).
 BRISK_HD bool nms_checks3(const LayerView& below, const LayerView& L, const LayerView& above, int n_layers, int layer, int x,
-                          int y, CheckResult* r, int* tile_violations = nullptr, int center_in = -1) {
+                          int y, CheckResult* r, int* tile_violations = nullptr, int center_in = -1,
+                          const unsigned long long* pre = nullptr /* side_tiles as four 64-bit words */) {
   const int center = center_in >= 0 ? center_in : (L.cm[(long long)y * L.pitch + x] & kCmT);
   r->max_above = 0; r->dxa = 0; r->dya = 0; r->max_below = 0; r->dxb = 0; r->dyb = 0;
   r->above_steps = 0; r->above_argmax = 0;
@@ -431,7 +549,8 @@ BRISK_HD bool nms_checks3(const LayerView& below, const LayerView& L, const Laye
     bool ismax;
     float dx = 0.0f, dy = 0.0f;
     AboveFootprint fp;
-    const float m = score_max_side(side == 1, side == 1 ? below : above, layer, x, y, center, &ismax, &dx, &dy, &fp, tile_violations);
+    const float m = score_max_side(side == 1, side == 1 ? below : above, layer, x, y, center, &ismax, &dx, &dy, &fp, tile_violations,
+                                   pre ? pre + 2 * side : nullptr);
     if (side == 0) {
       r->max_above = m; r->dxa = dx; r->dya = dy;
       r->above_steps = fp.steps | (fp.completed << 8);
@@ -448,7 +567,7 @@ BRISK_HD bool nms_checks3(const LayerView& below, const LayerView& L, const Laye
 #pragma unroll 1
 #endif
   for (int k = 0; k < 9; ++k) {  // s[3 * column + row], the reference's s_<column>_<row>
-    s[k] = score58(L, x + k / 3 - 1, y + k % 3 - 1);
+    s[k] = pre ? (int)((pre[2 + (k >> 3)] >> ((k & 7) << 3)) & 0xffull) : score58(L, x + k / 3 - 1, y + k % 3 - 1);
     best = imax(best, s[k]);
   }
   subpixel2d(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], &r->dxb, &r->dyb);
@@ -457,9 +576,9 @@ BRISK_HD bool nms_checks3(const LayerView& below, const LayerView& L, const Laye
 }
 
 BRISK_HD bool nms_checks(const LayerView* layers, int n_layers, int layer, int x, int y, CheckResult* r,
-                         int* tile_violations = nullptr) {
+                         int* tile_violations = nullptr, const unsigned long long* pre = nullptr) {
   return nms_checks3(layers[layer > 0 ? layer - 1 : 0], layers[layer], layers[layer + 1 < n_layers ? layer + 1 : layer], n_layers,
-                     layer, x, y, r, tile_violations);
+                     layer, x, y, r, tile_violations, -1, pre);
 }
 
 // ---------------------------------------------------------------------------
@@ -621,10 +740,21 @@ BRISK_HD void mark_above(const LayerView* layers, int layer, int x, int y, const
 // checks, and the single / last-layer branches of GetKeypoints :172-256).
 // Returns false when the corner is discarded on the scale axis.
 // ---------------------------------------------------------------------------
-BRISK_HD bool refine_emit1(const LayerView& L, int n_layers, int layer, int x, int y, const CheckResult& r, KeyPoint* kp) {
+// 3x3 patch of the corner's own layer from its score window (own_window): the neighbours' look-up values and T at the centre.
+BRISK_HD float patch3x3_window(const uint8_t own[25], int center, float* dx, float* dy) {
+  int s[9];  // s[3 * column + row]
+  for (int k = 0; k < 9; ++k) s[k] = own[(k % 3 + 1) * 5 + k / 3 + 1];
+  s[4] = center;
+  return subpixel2d(s[0], s[1], s[2], s[3], s[4], s[5], s[6], s[7], s[8], dx, dy);
+}
+
+BRISK_HD bool refine_emit1(const LayerView& L, int n_layers, int layer, int x, int y, const CheckResult& r, KeyPoint* kp,
+                           const uint8_t* own = nullptr) {
   float dxl, dyl;
   int s11;
-  const float max_layer = patch3x3(L, x, y, &dxl, &dyl, &s11);
+  float max_layer;
+  if (own) { s11 = L.cm[(long long)y * L.pitch + x] & kCmT; max_layer = patch3x3_window(own, s11, &dxl, &dyl); }
+  else max_layer = patch3x3(L, x, y, &dxl, &dyl, &s11);
   kp->angle = -1.0f; kp->class_id = -1; kp->octave = layer;
   if (n_layers == 1) {
     kp->x = (float)x + dxl; kp->y = (float)y + dyl; kp->size = 12.0f; kp->response = max_layer; kp->octave = 0;
@@ -672,8 +802,8 @@ BRISK_HD bool refine_emit1(const LayerView& L, int n_layers, int layer, int x, i
   return true;
 }
 BRISK_HD bool refine_emit(const LayerView* layers, int n_layers, int layer, int x, int y, const CheckResult& r,
-                          KeyPoint* kp) {
-  return refine_emit1(layers[layer], n_layers, layer, x, y, r, kp);
+                          KeyPoint* kp, const uint8_t* own = nullptr) {
+  return refine_emit1(layers[layer], n_layers, layer, x, y, r, kp, own);
 }
 
 // ---------------------------------------------------------------------------

@@ -87,19 +87,32 @@ extern "C" int emul_agast_detect_ex(const uint8_t* image, int w, int h, int thre
   int violations = 0;
   // phase 1 + 2 (parallel on the GPU)
   std::vector<std::vector<uint8_t>> fwin(n);
+  std::vector<std::vector<unsigned long long>> tiles(n);
   std::vector<std::vector<CheckResult>> chk(n);
+  // nms_windows_kernel: the 5x5 score window, IsMax2D's comparisons and, for the corners that pass them, the score
+  // tiles of the two neighbouring layers
   for (int i = 0; i < n; ++i) {
     const size_t nc = H[i].cx.size();
     fwin[i].assign(nc * 25, 0);
+    tiles[i].assign(nc * 4, 0);
     chk[i].resize(nc);
     for (size_t k = 0; k < nc; ++k) nms_prefix(V[i], H[i].cx[k], H[i].cy[k], &fwin[i][k * 25]);
   }
   for (int i = 0; i < n; ++i)
     for (size_t k = 0; k < H[i].cx.size(); ++k) {
+      const uint16_t e = H[i].cm[(size_t)H[i].cy[k] * H[i].pitch + H[i].cx[k]];
+      if ((e & kCmDecided) && !(e & kCmAccept)) continue;
+      uint8_t t[32];
+      side_tiles(V[i > 0 ? i - 1 : 0], V[i], V[i + 1 < n ? i + 1 : i], n, i, H[i].cx[k], H[i].cy[k], t);
+      memcpy(&tiles[i][k * 4], t, 32);
+    }
+  // nms_checks_kernel: the scans on the precomputed tiles
+  for (int i = 0; i < n; ++i)
+    for (size_t k = 0; k < H[i].cx.size(); ++k) {
       uint16_t& e = H[i].cm[(size_t)H[i].cy[k] * H[i].pitch + H[i].cx[k]];
       if ((e & kCmDecided) && !(e & kCmAccept)) continue;
       const int v0 = violations;
-      if (nms_checks(V.data(), n, i, H[i].cx[k], H[i].cy[k], &chk[i][k], &violations)) e |= kCmChecks;
+      if (nms_checks(V.data(), n, i, H[i].cx[k], H[i].cy[k], &chk[i][k], &violations, &tiles[i][k * 4])) e |= kCmChecks;
       if (violations != v0 && getenv("EMUL_DEBUG")) fprintf(stderr, "tile violation: layer %d corner (%d,%d) +%d\n", i, H[i].cx[k], H[i].cy[k], violations - v0);  // chk kept either way: footprint
     }
   if (violations) return -200;  // a scan looked outside its score tile
@@ -137,7 +150,7 @@ extern "C" int emul_agast_detect_ex(const uint8_t* image, int w, int h, int thre
       const uint16_t e = H[i].cm[(size_t)H[i].cy[k] * H[i].pitch + H[i].cx[k]];
       if (!(e & kCmAccept) || !(e & kCmChecks)) continue;
       KeyPoint kp;
-      if (!refine_emit(V.data(), n, i, H[i].cx[k], H[i].cy[k], chk[i][k], &kp)) continue;
+      if (!refine_emit(V.data(), n, i, H[i].cx[k], H[i].cy[k], chk[i][k], &kp, &fwin[i][k * 25])) continue;
       if (total < cap) out[total] = kp;
       ++total;
     }

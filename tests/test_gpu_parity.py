@@ -44,6 +44,18 @@ def test_integral_bit_exact(ctx, oracle, w, h):
     assert ctx.debug_integral(white)[-1, -1] == 255 * w * h
 
 
+@pytest.mark.parametrize("w,h", [(752, 480), (641, 479), (131, 67), (500, 333), (97, 200)])
+def test_dense_fast_scores_bit_exact(ctx, oracle, w, h):
+    # the packed row evaluator of the NMS kernels (fast_packed.cuh: pairs of pixels per instruction, word loads at every
+    # alignment) against the oracle's cornerScore on every pixel; also the 5-8 mask
+    rng = np.random.default_rng(w)
+    for img in (bb.synthetic_frame(w, h, 11), rng.integers(0, 256, (h, w), dtype=np.uint8),
+                (rng.integers(0, 3, (h, w)) * 100 + rng.integers(0, 5, (h, w))).astype(np.uint8)):
+        a1, b1 = ctx.debug_scores(img)
+        a2, b2 = oracle.dense_scores(img)
+        assert np.array_equal(a1, a2) and np.array_equal(b1, b2)
+
+
 def test_raw_corners_match_detector_order(ctx, oracle, golden):
     img = golden["image0"]
     det = bb.BriskFeatureDetector(60, 4, ctx=ctx)
@@ -763,20 +775,32 @@ def test_harris_unsupported(ctx):
 
 
 @pytest.mark.parametrize("nbytes", [48, 64])
-def test_knn_tensor_core_variant_matches_popc(oracle, nbytes):
-    # the u8-IMMA variant must return exactly what the POPC kernel returns (ties, missing rows, ragged tiles)
+def test_knn_tensor_core_variants_match_popc(oracle, nbytes):
+    # the tcgen05 kernel (variant 2, the default: kind::i8 MMAs on +-1 bytes, TMEM accumulators, TMA operands) and the
+    # mma.sync IMMA kernel (variant 1) must return exactly what the POPC kernel returns: ties, missing rows, ragged
+    # tiles, one or several train splits, queries / train rows that are no multiple of the tile sizes
     ctx2 = bb.Context(0)
     m = bb.BruteForceMatcher(ctx=ctx2)
-    for nq, nt in ((700, 5000), (129, 257), (5, 1), (300, 50000), (1000, 127)):
+    for nq, nt in ((700, 5000), (129, 257), (5, 1), (300, 50000), (1000, 127), (257, 128), (256, 129), (3000, 70001)):
         q = bb.random_descriptors(nq, nbytes, 5)
         t = bb.random_descriptors(nt, nbytes, 6)
         if nt > 200:
             t[100] = q[3]
             t[200] = q[3]
-        ctx2.set_knn_variant(0)
-        i0, d0 = m.knn(q, t, 2)
-        ctx2.set_knn_variant(1)
-        i1, d1 = m.knn(q, t, 2)
-        assert np.array_equal(i0, i1) and np.array_equal(d0, d1), (nq, nt)
+            t[nt - 1] = q[3]
+            t[150] = q[4]; t[150, 0] ^= 1   # distance 1
+        res = []
+        for variant in (0, 1, 2):
+            ctx2.set_knn_variant(variant)
+            res.append(m.knn(q, t, 2))
+        for variant in (1, 2):
+            assert np.array_equal(res[0][0], res[variant][0]) and np.array_equal(res[0][1], res[variant][1]), (nq, nt, variant)
+    i2, d2 = oracle.knn(q, t, 2)
+    assert np.array_equal(res[2][0], i2) and np.array_equal(res[2][1], d2)
+    # tie-rich rows (few distinct distances): the index tie rule across tiles and splits
+    q = _tie_rich_descriptors(300, nbytes, 1)
+    t = _tie_rich_descriptors(40000, nbytes, 2)
+    ctx2.set_knn_variant(2)
+    i1, d1 = m.knn(q, t, 2)
     i2, d2 = oracle.knn(q, t, 2)
     assert np.array_equal(i1, i2) and np.array_equal(d1, d2)

@@ -18,7 +18,7 @@ def main():
         q = torch.from_numpy(bb.random_descriptors(nq, nbytes, 5)).cuda()
         t = torch.from_numpy(bb.random_descriptors(nt, nbytes, 6)).cuda()
         res = []
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             ctx.set_knn_variant(variant)
             m.knn(q, t, 2)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -32,7 +32,7 @@ def main():
             res.append(r)
             out[f"{nbytes}B_variant{variant}"] = {"ms": ms, "Gcmp/s": nq * nt / ms / 1e6}
         same = all(np.array_equal(np.asarray(a.cpu() if hasattr(a, "cpu") else a), np.asarray(b.cpu() if hasattr(b, "cpu") else b))
-                   for a, b in zip(res[0], res[1]))
+                   for other in res[1:] for a, b in zip(res[0], other))
         out[f"{nbytes}B_identical"] = bool(same)
     print(json.dumps(out))
 
