@@ -1142,10 +1142,10 @@ int brisk_debug_nms_ties(brisk_ctx* ctx, int32_t* ties /* [12] of frame 0 of the
 // ---------------------------------------------------------------------------
 
 // Tensor map over expanded descriptor rows ([rows][kbytes] signed bytes): boxes of 128 rows x 128 bytes, 128B swizzle.
-static int encode_rows_map(brisk_ctx* ctx, const void* base, long long rows, int kbytes, CUtensorMap* map) {
-  cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)std::max<long long>(rows, 128)};
+static int encode_rows_map(brisk_ctx* ctx, const void* base, long long rows, int kbytes, int box_rows, CUtensorMap* map) {
+  cuuint64_t dims[2] = {(cuuint64_t)kbytes, (cuuint64_t)std::max<long long>(rows, box_rows)};
   cuuint64_t strides[1] = {(cuuint64_t)kbytes};
-  cuuint32_t box[2] = {128, 128};
+  cuuint32_t box[2] = {128, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = ctx->encode(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1186,9 +1186,9 @@ static int knn_keys_impl(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const
     CU_OK(launch_expand_pm1(dq, nq, desc_bytes, ctx->knn_qx.as<uint8_t>(), ctx->stream));
     CU_OK(launch_expand_pm1(dt, nt, desc_bytes, ctx->knn_tx.as<uint8_t>(), ctx->stream));
     CUtensorMap mq, mt;
-    int rc = encode_rows_map(ctx, ctx->knn_qx.p, nq, desc_bytes * 8, &mq);
+    int rc = encode_rows_map(ctx, ctx->knn_qx.p, nq, desc_bytes * 8, 128, &mq);
     if (rc) return rc;
-    rc = encode_rows_map(ctx, ctx->knn_tx.p, nt, desc_bytes * 8, &mt);
+    rc = encode_rows_map(ctx, ctx->knn_tx.p, nt, desc_bytes * 8, knn_tc5_tile_rows(), &mt);
     if (rc) return rc;
     CU_OK(launch_hamming_knn2_tc5(mq, nq, mt, nt, desc_bytes, offset, ctx->knn_keys.as<unsigned long long>(),
                                   ctx->knn_part.as<unsigned long long>(), splits, ctx->stream));

@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -36,10 +37,14 @@ namespace {
 
 constexpr int kT5M = 128;         // rows of one MMA (= TMEM lanes)
 constexpr int kT5QTiles = 2;      // A tiles per CTA -> 256 queries
-constexpr int kT5N = 128;         // train rows per tile (MMA N)
+// Train rows per tile (MMA N): 128, or 256 with BRISK_B200_TC5_TILE_ROWS=256 in the environment (kept for measurements).
+static int t5_tile_rows() {
+  static const int rows = [] { const char* e = getenv("BRISK_B200_TC5_TILE_ROWS"); return e && atoi(e) == 256 ? 256 : 128; }();
+  return rows;
+}
 constexpr int kT5Chunk = 128;     // bytes of K per shared-memory chunk: one row of a 128B swizzle atom
-constexpr int kT5ChunkBytes = kT5N * kT5Chunk;  // 16 KB (A and B chunks have the same shape)
-constexpr int kT5Stages = 6;
+constexpr int kT5AChunkBytes = kT5M * kT5Chunk;  // 16 KB
+constexpr int kT5RingBytes = 96 * 1024;          // B ring: 6 stages of 128 train rows or 3 stages of 256
 constexpr int kT5EpiWarps = 8;
 constexpr int kT5Threads = (2 + kT5EpiWarps) * 32;  // warp 0: TMA producer, warp 1: TMEM owner + MMA issuer, 2..9: epilogue
 constexpr int kT5TmemCols = 512;
@@ -84,14 +89,16 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 
 // Instruction descriptor, kind::i8: D = S32 (2 << 4), A = B = signed 8 bit (1 << 7, 1 << 10), both K-major, N >> 3 in bits
 // 17-22, M >> 4 in bits 24-28.
-constexpr uint32_t kT5Idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kT5N >> 3) << 17) | ((uint32_t)(kT5M >> 4) << 24);
+__host__ __device__ constexpr uint32_t t5_idesc(int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kT5M >> 4) << 24);
+}
 
-__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kT5Idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
       : "memory");
 }
 // All MMAs issued so far by this thread arrive on `bar` when they complete (implies tcgen05.fence::before_thread_sync).
@@ -118,15 +125,23 @@ __device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b),
 }  // namespace
 
 // KC = chunks along K: 4 for 64-byte rows (512 signed bytes), 3 for 48-byte rows.
-template <int KC>
+// NT = train rows per tile = N of one MMA.  128 (default): two accumulator sets, the epilogue of tile i runs under the MMAs of
+// tile i + 1.  Every 64-cycle MMA reads 4 KB of A and 4 KB of B from shared memory while TMA writes 2 KB of the next chunk --
+// more than the 128 B / cycle an SM's shared memory delivers, which is what bounds the kernel (measured: tensor pipe 68 %
+// active, 2.75 Tcmp/s at 512 bit, 4.2 Tcmp/s at 384 bit).  256: the same bytes per MAC, and the accumulators of the two A
+// tiles fill all 512 TMEM columns, so the next tile's MMAs wait for the drain (measured: 2.53 / 3.04 Tcmp/s).
+template <int KC, int NT>
 __global__ void __launch_bounds__(kT5Threads, 1)
 hamming_knn2_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, long long nq,
                         long long nt, long long rows_per_split, long long train_index_offset,
                         unsigned long long* __restrict__ part) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);  // swizzle atoms are 1024-byte aligned
+  constexpr int kT5N = NT, kT5ChunkBytes = NT * kT5Chunk, kT5Stages = kT5RingBytes / kT5ChunkBytes;
+  constexpr int kSets = kT5TmemCols / (kT5QTiles * NT);       // accumulator sets in TMEM: 2 (NT = 128) or 1 (NT = 256)
+  constexpr uint32_t kIdesc = t5_idesc(NT);
   uint8_t* sA = smem;                                         // [2 tiles][KC chunks][128 rows x 128 B]
-  uint8_t* sB = sA + kT5QTiles * KC * kT5ChunkBytes;          // [stages][128 rows x 128 B]
+  uint8_t* sB = sA + kT5QTiles * KC * kT5AChunkBytes;         // [stages][NT rows x 128 B]
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + kT5Stages * kT5ChunkBytes);
   uint64_t* bar_empty = bar_full + kT5Stages;
   uint64_t* bar_a = bar_empty + kT5Stages;
@@ -159,9 +174,9 @@ hamming_knn2_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   if (warp == 0) {
     // ---- TMA producer ----
     if (lane == 0 && ntiles > 0) {
-      mbar_expect_tx(bar_a, kT5QTiles * KC * kT5ChunkBytes);
+      mbar_expect_tx(bar_a, kT5QTiles * KC * kT5AChunkBytes);
       for (int a = 0; a < kT5QTiles; ++a)
-        for (int c = 0; c < KC; ++c) tma_load_2d(sA + (a * KC + c) * kT5ChunkBytes, &map_q, c * kT5Chunk, (int)(q0 + a * kT5M), bar_a);
+        for (int c = 0; c < KC; ++c) tma_load_2d(sA + (a * KC + c) * kT5AChunkBytes, &map_q, c * kT5Chunk, (int)(q0 + a * kT5M), bar_a);
       int it = 0;
       for (int i = 0; i < ntiles; ++i)
         for (int c = 0; c < KC; ++c, ++it) {
@@ -179,8 +194,8 @@ hamming_knn2_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       int it = 0;
       for (int i = 0; i < ntiles; ++i) {
-        const int b = i & 1;
-        mbar_wait(&bar_tempty[b], ((i >> 1) & 1) ^ 1);
+        const int b = i % kSets;
+        mbar_wait(&bar_tempty[b], ((i / kSets) & 1) ^ 1);
         tc_fence_after();
         for (int c = 0; c < KC; ++c, ++it) {
           const int s = it % kT5Stages;
@@ -191,8 +206,8 @@ hamming_knn2_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
             const uint64_t bd = umma_desc(b_base + s * kT5ChunkBytes + k * 32);
 #pragma unroll
             for (int a = 0; a < kT5QTiles; ++a)
-              umma_i8(tmem_base + (uint32_t)(b * 256 + a * kT5N), umma_desc(a_base + (a * KC + c) * kT5ChunkBytes + k * 32), bd,
-                      (c | k) != 0 ? 1u : 0u);
+              umma_i8(tmem_base + (uint32_t)((b * kT5QTiles + a) * kT5N), umma_desc(a_base + (a * KC + c) * kT5AChunkBytes + k * 32), bd,
+                      kIdesc, (c | k) != 0 ? 1u : 0u);
           }
           umma_commit(&bar_empty[s]);   // the stage is free once these MMAs have read it
         }
@@ -206,8 +221,8 @@ hamming_knn2_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     int d0 = -100000, d1 = -100000;       // two largest dot products so far (d0 >= d1) ...
     unsigned i0 = 0xffffffffu, i1 = 0xffffffffu;  // ... and their (global) train indices
     for (int i = 0; i < ntiles; ++i) {
-      const int b = i & 1;
-      mbar_wait(&bar_tfull[b], (i >> 1) & 1);
+      const int b = i % kSets;
+      mbar_wait(&bar_tfull[b], (i / kSets) & 1);
       tc_fence_after();
       const long long tile_base = t_begin + (long long)i * kT5N;
       const int valid = (int)min((long long)kT5N, t_end - tile_base);
@@ -215,7 +230,7 @@ hamming_knn2_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 #pragma unroll 1
       for (int cc = 0; cc < kT5N / 32; ++cc) {
         int v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * 256 + a * kT5N + cc * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((b * kT5QTiles + a) * kT5N + cc * 32), v);
         int m = max3(v[0], v[1], v[2]);
 #pragma unroll
         for (int j = 3; j + 1 < 32; j += 2) m = max3(m, v[j], v[j + 1]);
@@ -269,7 +284,7 @@ expand_pm1_kernel(const uint32_t* __restrict__ src, long long n_words, uint4* __
 }
 
 size_t knn_tc5_expanded_bytes(long long rows, int desc_bytes) {
-  const long long r = rows < kT5M ? kT5M : rows;   // the tensor map's row extent is at least one box
+  const long long r = rows < 256 ? 256 : rows;   // the tensor map's row extent is at least one box
   return (size_t)r * desc_bytes * 8;
 }
 
@@ -281,10 +296,12 @@ cudaError_t launch_expand_pm1(const uint8_t* src, long long rows, int desc_bytes
   return cudaGetLastError();
 }
 
+int knn_tc5_tile_rows() { return t5_tile_rows(); }
+
 // Splits of the train set: enough CTAs for the 148 SMs, then the smallest count whose last wave is >= 95 % full.
 int knn_tc5_num_splits(long long nq, long long nt) {
   const long long qblocks = (nq + kT5QTiles * kT5M - 1) / (kT5QTiles * kT5M);
-  long long max_splits = (nt + 16 * kT5N - 1) / (16 * kT5N);
+  long long max_splits = (nt + 16 * 256 - 1) / (16 * 256);
   if (max_splits > 64) max_splits = 64;
   if (max_splits < 1) max_splits = 1;
   long long best = 1;
@@ -299,14 +316,14 @@ int knn_tc5_num_splits(long long nq, long long nt) {
   return (int)best;
 }
 
-template <int KC>
+template <int KC, int NT>
 static cudaError_t launch_tc5(const CUtensorMap& mq, const CUtensorMap& mt, long long nq, long long nt, long long off,
                               unsigned long long* dst, int splits, long long rows_per_split, cudaStream_t stream) {
-  const size_t smem = (size_t)(kT5QTiles * KC + kT5Stages) * kT5ChunkBytes + 1024 /* alignment */ + 256 /* barriers */;
-  cudaError_t e = cudaFuncSetAttribute(hamming_knn2_tc5_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)kT5QTiles * KC * kT5AChunkBytes + kT5RingBytes + 1024 /* alignment */ + 256 /* barriers */;
+  cudaError_t e = cudaFuncSetAttribute(hamming_knn2_tc5_kernel<KC, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   dim3 grid((unsigned)((nq + kT5QTiles * kT5M - 1) / (kT5QTiles * kT5M)), splits);
-  hamming_knn2_tc5_kernel<KC><<<grid, kT5Threads, smem, stream>>>(mq, mt, nq, nt, rows_per_split, off, dst);
+  hamming_knn2_tc5_kernel<KC, NT><<<grid, kT5Threads, smem, stream>>>(mq, mt, nq, nt, rows_per_split, off, dst);
   return cudaGetLastError();
 }
 
@@ -316,16 +333,19 @@ cudaError_t launch_hamming_knn2_tc5(const CUtensorMap& map_q, long long nq, cons
                                     long long train_index_offset, unsigned long long* keys, unsigned long long* part,
                                     int splits, cudaStream_t stream) {
   if (nq <= 0) return cudaSuccess;
-  long long rows_per_split = ((nt + splits - 1) / splits + kT5N - 1) / kT5N * kT5N;
-  if (rows_per_split <= 0) rows_per_split = kT5N;
+  const int tile = t5_tile_rows();
+  long long rows_per_split = ((nt + splits - 1) / splits + tile - 1) / tile * tile;
+  if (rows_per_split <= 0) rows_per_split = tile;
   unsigned long long* dst = splits == 1 ? keys : part;
   cudaError_t e;
   if (nt <= 0) {
     e = cudaMemsetAsync(keys, 0xff, (size_t)nq * 2 * 8, stream);   // no train rows: every key is "none"
     return e;
   }
-  if (desc_bytes == 64) e = launch_tc5<4>(map_q, map_t, nq, nt, train_index_offset, dst, splits, rows_per_split, stream);
-  else if (desc_bytes == 48) e = launch_tc5<3>(map_q, map_t, nq, nt, train_index_offset, dst, splits, rows_per_split, stream);
+  if (desc_bytes == 64 && tile == 256) e = launch_tc5<4, 256>(map_q, map_t, nq, nt, train_index_offset, dst, splits, rows_per_split, stream);
+  else if (desc_bytes == 48 && tile == 256) e = launch_tc5<3, 256>(map_q, map_t, nq, nt, train_index_offset, dst, splits, rows_per_split, stream);
+  else if (desc_bytes == 64) e = launch_tc5<4, 128>(map_q, map_t, nq, nt, train_index_offset, dst, splits, rows_per_split, stream);
+  else if (desc_bytes == 48) e = launch_tc5<3, 128>(map_q, map_t, nq, nt, train_index_offset, dst, splits, rows_per_split, stream);
   else return cudaErrorInvalidValue;
   if (e != cudaSuccess) return e;
   if (splits > 1) e = launch_knn_merge(part, splits, nq, 2, keys, stream);

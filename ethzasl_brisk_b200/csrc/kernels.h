@@ -135,10 +135,12 @@ cudaError_t launch_hamming_knn2_mma(const uint8_t* q, long long nq, const uint8_
                                     int splits, cudaStream_t stream);
 // tcgen05 variant (hamming_tc5.cu): kind::i8 MMAs on +-1 expanded rows, TMEM accumulators, TMA operands; k == 2, 48/64-byte rows.
 // The caller expands both sets (launch_expand_pm1; knn_tc5_expanded_bytes per set) and passes tensor maps over the expanded
-// rows: 2-D, dims {8 * desc_bytes, max(rows, 128)}, box {128, 128}, CU_TENSOR_MAP_SWIZZLE_128B.
+// rows: 2-D, dims {8 * desc_bytes, max(rows, box rows)}, box {128, 128} (queries) / {128, knn_tc5_tile_rows()} (train),
+// CU_TENSOR_MAP_SWIZZLE_128B.
 size_t knn_tc5_expanded_bytes(long long rows, int desc_bytes);
 cudaError_t launch_expand_pm1(const uint8_t* src, long long rows, int desc_bytes, uint8_t* dst, cudaStream_t stream);
 int knn_tc5_num_splits(long long nq, long long nt);
+int knn_tc5_tile_rows();
 cudaError_t launch_hamming_knn2_tc5(const CUtensorMap& map_q, long long nq, const CUtensorMap& map_t, long long nt, int desc_bytes,
                                     long long train_index_offset, unsigned long long* keys, unsigned long long* part,
                                     int splits, cudaStream_t stream);
