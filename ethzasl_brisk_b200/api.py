@@ -125,6 +125,21 @@ class Context:
         except Exception:
             pass
 
+    def _sample16(self, fn, img, dw, dh):
+        a = np.ascontiguousarray(img, np.uint16)
+        h, w = a.shape
+        out = np.zeros((dh(h), dw(w)), np.uint16)
+        self._check(fn(self._h, _ptr(a), w, h, C.c_size_t(2 * w), _ptr(out), C.c_size_t(2 * out.shape[1])))
+        return out
+
+    def halfsample16(self, img):
+        """brisk::Halfsample16 on a CV_16UC1 image -> (h // 2, w // 2) u16."""
+        return self._sample16(self._lib.brisk_halfsample16, img, lambda w: w // 2, lambda h: h // 2)
+
+    def twothirdsample16(self, img):
+        """brisk::Twothirdsample16 on a CV_16UC1 image -> (2 * (h // 3), 2 * (w // 3)) u16."""
+        return self._sample16(self._lib.brisk_twothirdsample16, img, lambda w: 2 * (w // 3), lambda h: 2 * (h // 3))
+
     # --- stage dumps used by the parity tests ---
     def debug_pyramid(self, img, octaves):
         img = np.ascontiguousarray(img, np.uint8)
@@ -395,6 +410,49 @@ class BriskDescriptorExtractor:
                 self.ctx._lib.brisk_extractor_destroy(self._h)
         except Exception:
             pass
+
+
+class HarrisScoreCalculator:
+    """brisk::HarrisScoreCalculator (harris-score-calculator.h:52-90): SetImage computes the integer Harris score map on the
+    GPU; Score(int, int) / Score(double, double) read it the way the reference's inline accessors do; Get2dMaxima lists the
+    8-neighbour maxima in raster order as (score, x, y)."""
+
+    def __init__(self, ctx=None):
+        self.ctx = ctx or default_context()
+        self._img = None
+        self._scores = None
+
+    def SetImage(self, img, initScores=True):
+        self._img = np.ascontiguousarray(img, np.uint8)
+        if initScores:
+            h, w = self._img.shape
+            self._scores = np.zeros((h, w), np.int32)
+            self.ctx._check(self.ctx._lib.brisk_harris_scores(self.ctx._h, _ptr(self._img), w, h, C.c_size_t(w), 0, _ptr(self._scores), None, 0, None))
+
+    def scores(self):
+        return self._scores
+
+    def Score(self, u, v):
+        s = self._scores
+        if isinstance(u, (int, np.integer)) and isinstance(v, (int, np.integer)):
+            return int(s[v, u])
+        ui, vi = int(u), int(v)
+        if ui + 1 >= s.shape[1] or vi + 1 >= s.shape[0] or ui < 0 or vi < 0:
+            return 0.0
+        ru, rv = float(u) - float(ui), float(v) - float(vi)
+        return (1.0 - rv) * ((1.0 - ru) * float(s[vi, ui]) + ru * float(s[vi, ui + 1])) + rv * ((1.0 - ru) * float(s[vi + 1, ui]) + ru * float(s[vi + 1, ui + 1]))
+
+    def Get2dMaxima(self, absoluteThreshold=0, cap=1 << 16):
+        h, w = self._img.shape
+        while True:
+            out = np.zeros((cap, 3), np.int32)
+            n = C.c_int32(0)
+            rc = self.ctx._lib.brisk_harris_scores(self.ctx._h, _ptr(self._img), w, h, C.c_size_t(w), int(absoluteThreshold), None, _ptr(out), cap, C.byref(n))
+            if rc == BRISK_ERR_CAPACITY and n.value > cap:
+                cap = n.value
+                continue
+            self.ctx._check(rc)
+            return out[:n.value].copy()
 
 
 def detect_and_compute_batch(detector, extractor, images, masks=None, cap=16384, out=None, allow_truncation=False):

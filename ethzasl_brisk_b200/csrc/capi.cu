@@ -986,6 +986,89 @@ int brisk_harris_detect_passed(brisk_ctx* ctx, brisk_detector* det, int n, int w
   return BRISK_OK;
 }
 
+int brisk_harris_scores(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, int abs_threshold, int32_t* scores,
+                        int32_t* maxima_sxy, int cap, int32_t* n_maxima) {
+  int rc = check_image_args(ctx, img, 1, w, h, stride, stride * (size_t)h);
+  if (rc) return rc;
+  if (w < 8 || h < 8) return fail(ctx, BRISK_ERR_INVALID, "image too small");
+  if ((maxima_sxy && (cap <= 0 || !n_maxima)) || (scores && is_device_ptr(scores)) || (maxima_sxy && is_device_ptr(maxima_sxy)))
+    return fail(ctx, BRISK_ERR_INVALID, "bad output arguments (host buffers expected)");
+  CU_OK(cudaSetDevice(ctx->device));
+  brisk_detector det{ctx, 0, 0, 1, 0};
+  det.harris = 1; det.radius = 0.0; det.abs_thr = abs_threshold; det.max_kpt = 1;
+  det.corner_cap = maxima_sxy ? cap : 0;
+  Plan plan;
+  rc = make_plan(ctx, &det, nullptr, 1, w, h, 1, &plan, false, false);
+  if (rc) return rc;
+  const PyramidGeom& g = plan.g;
+  Slot& sl = ctx->slots[0];
+  if (!is_device_ptr(img)) CU_OK(sl.tight.ensure((size_t)w * h + 64));
+  CU_OK(cudaEventRecord(ctx->entry, ctx->stream));
+  CU_OK(cudaStreamWaitEvent(sl.stream, ctx->entry, 0));
+  HarrisWorkspace hw = plan.hw;
+  hw.det = slot_ws(plan, sl);
+  hw.scores = sl.h_scores.as<int>(); hw.pts = sl.h_pts.as<HPoint>();
+  CUtensorMap map; int write_l0 = 0; bool staged = false;
+  rc = stage_input(ctx, sl, plan, img, 1, w, h, stride, stride * (size_t)h, &map, &write_l0, &staged);
+  if (rc) return rc;
+  CU_OK(launch_pyramid(map, g, hw.det.pyr, 1, write_l0, sl.stream));
+  CU_OK(cudaMemsetAsync(sl.flag.p, 0, 16, sl.stream));
+  CU_OK(launch_harris_score_maxima(g, hw, 1, abs_threshold, sl.flag.as<int>(), sl.stream));
+  ctx->launches = 5;
+  if (scores) CU_OK(cudaMemcpy2DAsync(scores, (size_t)w * 4, hw.scores + g.L[0].off, (size_t)g.L[0].pitch * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost, sl.stream));
+  int ls[kMaxLayers + 1] = {0};
+  CU_OK(cudaMemcpyAsync(ls, hw.det.layer_start, sizeof(ls), cudaMemcpyDeviceToHost, sl.stream));
+  CU_OK(cudaStreamSynchronize(sl.stream));
+  const int total = ls[1];
+  if (n_maxima) *n_maxima = total;
+  if (maxima_sxy) {
+    const int m = std::min(total, cap);
+    std::vector<HPoint> pts((size_t)std::max(m, 1));
+    if (m > 0) CU_OK(cudaMemcpy(pts.data(), hw.pts, (size_t)m * sizeof(HPoint), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < m; ++i) { maxima_sxy[3 * i] = pts[i].score; maxima_sxy[3 * i + 1] = pts[i].x; maxima_sxy[3 * i + 2] = pts[i].y; }
+    if (total > cap) return fail(ctx, BRISK_ERR_CAPACITY, "more 2-D maxima than the output capacity; n_maxima holds the number needed");
+  }
+  return BRISK_OK;
+}
+
+// Halfsample16 / Twothirdsample16 on host or device buffers (strides in BYTES, like cv::Mat::step).
+static int sample16(brisk_ctx* ctx, int two_third, const uint16_t* src, int w, int h, size_t src_stride, uint16_t* dst, size_t dst_stride) {
+  if (!ctx) return BRISK_ERR_INVALID;
+  const int dw = two_third ? 2 * (w / 3) : w / 2, dh = two_third ? 2 * (h / 3) : h / 2;
+  if (!src || !dst || w <= 0 || h <= 0 || src_stride < (size_t)w * 2 || dst_stride < (size_t)dw * 2 || src_stride % 2 || dst_stride % 2)
+    return fail(ctx, BRISK_ERR_INVALID, "bad 16-bit image arguments");
+  // narrower images never enter the reference's SSE loops: it writes nothing (image-down-sampling.cc:70-75, 407-411)
+  if (two_third ? (w / 3) * 3 < 12 : w < 16) return fail(ctx, BRISK_ERR_UNSUPPORTED, two_third ? "Twothirdsample16 needs at least 12 columns" : "Halfsample16 needs at least 16 columns");
+  if (dw == 0 || dh == 0) return BRISK_OK;
+  CU_OK(cudaSetDevice(ctx->device));
+  const bool sdev = is_device_ptr(src), ddev = is_device_ptr(dst);
+  const uint16_t* ds = src; uint16_t* dd = dst;
+  long long sp = (long long)src_stride / 2, dp = (long long)dst_stride / 2;
+  if (!sdev) {
+    CU_OK(ctx->knn_q.ensure((size_t)w * h * 2));
+    CU_OK(cudaMemcpy2DAsync(ctx->knn_q.p, (size_t)w * 2, src, src_stride, (size_t)w * 2, h, cudaMemcpyHostToDevice, ctx->stream));
+    ds = ctx->knn_q.as<uint16_t>(); sp = w;
+  }
+  if (!ddev) {
+    CU_OK(ctx->knn_t.ensure((size_t)dw * dh * 2));
+    dd = ctx->knn_t.as<uint16_t>(); dp = dw;
+  }
+  if (two_third) CU_OK(launch_twothirdsample16(ds, w, h, sp, dd, dp, ctx->stream));
+  else CU_OK(launch_halfsample16(ds, w, h, sp, dd, dp, ctx->stream));
+  ctx->launches = 1;
+  if (!ddev) CU_OK(cudaMemcpy2DAsync(dst, dst_stride, dd, (size_t)dw * 2, (size_t)dw * 2, dh, cudaMemcpyDeviceToHost, ctx->stream));
+  CU_OK(cudaStreamSynchronize(ctx->stream));
+  return BRISK_OK;
+}
+
+int brisk_halfsample16(brisk_ctx* ctx, const uint16_t* src, int w, int h, size_t src_stride, uint16_t* dst, size_t dst_stride) {
+  return sample16(ctx, 0, src, w, h, src_stride, dst, dst_stride);
+}
+
+int brisk_twothirdsample16(brisk_ctx* ctx, const uint16_t* src, int w, int h, size_t src_stride, uint16_t* dst, size_t dst_stride) {
+  return sample16(ctx, 1, src, w, h, src_stride, dst, dst_stride);
+}
+
 int brisk_debug_pyramid(brisk_ctx* ctx, int octaves, const uint8_t* img, int w, int h, size_t stride, uint8_t* out,
                         int32_t* dims, int* n_layers) {
   int rc = check_image_args(ctx, img, 1, w, h, stride, stride * (size_t)h);

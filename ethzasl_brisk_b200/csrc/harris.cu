@@ -440,17 +440,10 @@ harris_emit_kernel(PyramidGeom g, HarrisLayerParams hp, const int* __restrict__ 
   if (tid == 0) counts[frame] = base;
 }
 
-cudaError_t launch_harris_detect(const PyramidGeom& g, const HarrisWorkspace& hw, int n_frames, double radius, double abs_thr,
-                                 long long max_kpt, KeyPoint* out, int* counts, int kp_cap, int* overflow_flag, cudaStream_t stream) {
-  // layer transforms of ScaleSpaceLayer::Create (scale-space-layer-inl.h:60-182)
-  HarrisLayerParams hp;
-  for (int i = 0; i < g.n_layers; ++i) {
-    const bool octave = (i % 2) == 0;
-    if (octave) { hp.offset_above[i] = -0.25; hp.offset_below[i] = 1.0 / 6.0; hp.scale_above[i] = 2.0 / 3.0; hp.scale_below[i] = 4.0 / 3.0; hp.scale[i] = i == 0 ? 1.0 : pow(2.0, (double)(i / 2)); }
-    else { hp.offset_above[i] = -1.0 / 6.0; hp.offset_below[i] = 0.125; hp.scale_above[i] = 0.75; hp.scale_below[i] = 1.5; hp.scale[i] = pow(2.0, (double)(i / 2)) * 1.5; }
-    hp.offset[i] = i == 0 ? 0.0 : hp.scale[i] * 0.5 - 0.5;
-  }
-  const int thr = (int)abs_thr;
+// HarrisScoreCalculator::InitializeScores + Get2dMaxima on every layer (harris-score-calculator.cc:53-106): score planes and
+// the raster-ordered lists of the 2-D maxima (hw.pts, layer-major; hw.det.layer_start[frame][l] = first slot of layer l).
+cudaError_t launch_harris_score_maxima(const PyramidGeom& g, const HarrisWorkspace& hw, int n_frames, int thr, int* overflow_flag,
+                                       cudaStream_t stream) {
   for (int l = 0; l < g.n_layers; ++l) {
     const LayerGeom& L = g.L[l];
     dim3 grid((L.w + kHsTW - 1) / kHsTW, (L.h + kHsTH - 1) / kHsTH, n_frames);
@@ -468,6 +461,22 @@ cudaError_t launch_harris_detect(const PyramidGeom& g, const HarrisWorkspace& hw
     dim3 grid((L.h + 7) / 8, n_frames);
     harris_maxima_kernel<true><<<grid, 256, 0, stream>>>(L, g.frame_elems, hw.scores, thr, hw.det.rowcnt, hw.det.total_rows, hw.det.row_off[l], hw.pts, hw.det.corner_cap);
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_harris_detect(const PyramidGeom& g, const HarrisWorkspace& hw, int n_frames, double radius, double abs_thr,
+                                 long long max_kpt, KeyPoint* out, int* counts, int kp_cap, int* overflow_flag, cudaStream_t stream) {
+  // layer transforms of ScaleSpaceLayer::Create (scale-space-layer-inl.h:60-182)
+  HarrisLayerParams hp;
+  for (int i = 0; i < g.n_layers; ++i) {
+    const bool octave = (i % 2) == 0;
+    if (octave) { hp.offset_above[i] = -0.25; hp.offset_below[i] = 1.0 / 6.0; hp.scale_above[i] = 2.0 / 3.0; hp.scale_below[i] = 4.0 / 3.0; hp.scale[i] = i == 0 ? 1.0 : pow(2.0, (double)(i / 2)); }
+    else { hp.offset_above[i] = -1.0 / 6.0; hp.offset_below[i] = 0.125; hp.scale_above[i] = 0.75; hp.scale_below[i] = 1.5; hp.scale[i] = pow(2.0, (double)(i / 2)) * 1.5; }
+    hp.offset[i] = i == 0 ? 0.0 : hp.scale[i] * 0.5 - 0.5;
+  }
+  const int thr = (int)abs_thr;
+  cudaError_t e = launch_harris_score_maxima(g, hw, n_frames, thr, overflow_flag, stream);
+  if (e != cudaSuccess) return e;
   dim3 gp((hw.det.corner_cap + 127) / 128, n_frames);
   harris_nms3d_kernel<<<gp, 128, 0, stream>>>(g, hp, hw.scores, hw.det.layer_start, hw.pts, hw.keep, hw.det.corner_cap, thr);
   harris_sort_kernel<<<dim3(g.n_layers, n_frames), kSortThreads, 0, stream>>>(g.n_layers, hw.det.layer_start, hw.pts, hw.keep, hw.sorted, hw.layer_kept, hw.surv, hw.det.corner_cap);

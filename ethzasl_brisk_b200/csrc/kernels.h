@@ -31,6 +31,10 @@ struct DetectWorkspace {
 cudaError_t launch_pyramid(const CUtensorMap& src_map, const PyramidGeom& g, uint8_t* pyr, int n_frames, int write_l0,
                            cudaStream_t stream);
 
+// 16-bit samplers (pitches in elements); the caller checks the reference's size limits (w >= 16 resp. 3 * (w / 3) >= 12).
+cudaError_t launch_halfsample16(const uint16_t* src, int w, int h, long long spitch, uint16_t* dst, long long dpitch, cudaStream_t stream);
+cudaError_t launch_twothirdsample16(const uint16_t* src, int w, int h, long long spitch, uint16_t* dst, long long dpitch, cudaStream_t stream);
+
 // Threshold map + AGAST 9-16 segment test -> corner map + per-row counts.
 // `lower`: lower bound of the threshold map, kLowerThreshold (detection) or 0 (ComputeScale's pyramid).
 cudaError_t launch_agast_detect(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int thresh, cudaStream_t stream,
@@ -75,6 +79,8 @@ struct HarrisWorkspace {
   int occ_w[kMaxLayers], occ_h[kMaxLayers];
 };
 cudaError_t launch_row_scan(const PyramidGeom& g, const DetectWorkspace& ws, int n_frames, int* overflow_flag, cudaStream_t stream);
+cudaError_t launch_harris_score_maxima(const PyramidGeom& g, const HarrisWorkspace& hw, int n_frames, int thr, int* overflow_flag,
+                                       cudaStream_t stream);
 cudaError_t launch_harris_detect(const PyramidGeom& g, const HarrisWorkspace& hw, int n_frames, double radius, double abs_thr,
                                  long long max_kpt, KeyPoint* out, int* counts, int kp_cap, int* overflow_flag, cudaStream_t stream);
 

@@ -202,6 +202,62 @@ pyramid_kernel(const __grid_constant__ CUtensorMap src_map, PyramidGeom g, uint8
   }
 }
 
+// ---------------------------------------------------------------------------
+// 16-bit samplers: Halfsample16 / Twothirdsample16 (reference brisk/src/image-down-sampling.cc:56-139, 394-548).
+// Stand-alone primitives (the reference's own 16-bit extractor path never gets this far: it integrates an empty image,
+// SURVEY.md F10); HBM bound, one output pixel pair per thread, 32-bit coalesced stores.
+// ---------------------------------------------------------------------------
+
+// avg(avg(a, b), avg(sat(sat(c + 1) + 1), d)) with pavgw's rounding-up average (image-down-sampling.cc:117-122).
+__device__ __forceinline__ uint32_t half16_px(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  c = min(min(c + 1u, 65535u) + 1u, 65535u);
+  return (((a + b + 1u) >> 1) + ((c + d + 1u) >> 1) + 1u) >> 1;
+}
+
+__global__ void __launch_bounds__(256)
+halfsample16_kernel(const uint16_t* __restrict__ src, int sw, int sh, long long spitch, uint16_t* __restrict__ dst, long long dpitch) {
+  const int dw = sw / 2, dh = sh / 2;
+  const int r = blockIdx.y;
+  const int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x);   // two output pixels per thread
+  if (r >= dh || c >= dw) return;
+  const uint16_t* s0 = src + (long long)(2 * r) * spitch + 2 * c;
+  const uint16_t* s1 = s0 + spitch;
+  uint16_t* d = dst + (long long)r * dpitch + c;
+  d[0] = (uint16_t)half16_px(s0[0], s0[1], s1[0], s1[1]);
+  if (c + 1 < dw) d[1] = (uint16_t)half16_px(s0[2], s0[3], s1[2], s1[3]);
+}
+
+// One thread per 3x3 source block -> 2x2 outputs: 4:2:2:1 weights, truncating division by 9, then the SIGNED
+// saturation of packssdw (image-down-sampling.cc:503-523): sums above 32767 are stored as 32767.
+__global__ void __launch_bounds__(256)
+twothirdsample16_kernel(const uint16_t* __restrict__ src, int sw, int sh, long long spitch, uint16_t* __restrict__ dst, long long dpitch) {
+  const int bw = sw / 3, bh = sh / 3;
+  const int R = blockIdx.y, T = blockIdx.x * blockDim.x + threadIdx.x;
+  if (R >= bh || T >= bw) return;
+  uint32_t p[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) p[k] = src[(long long)(3 * R + k / 3) * spitch + 3 * T + k % 3];
+  const uint32_t o0 = (4 * p[0] + 2 * p[1] + 2 * p[3] + p[4]) / 9, o1 = (4 * p[2] + 2 * p[1] + 2 * p[5] + p[4]) / 9;
+  const uint32_t o2 = (4 * p[6] + 2 * p[7] + 2 * p[3] + p[4]) / 9, o3 = (4 * p[8] + 2 * p[7] + 2 * p[5] + p[4]) / 9;
+  uint16_t* d = dst + (long long)(2 * R) * dpitch + 2 * T;
+  d[0] = (uint16_t)min(o0, 32767u); d[1] = (uint16_t)min(o1, 32767u);
+  d[dpitch] = (uint16_t)min(o2, 32767u); d[dpitch + 1] = (uint16_t)min(o3, 32767u);
+}
+
+cudaError_t launch_halfsample16(const uint16_t* src, int w, int h, long long spitch, uint16_t* dst, long long dpitch, cudaStream_t stream) {
+  if (w / 2 <= 0 || h / 2 <= 0) return cudaSuccess;
+  dim3 grid((w / 2 + 511) / 512, h / 2);
+  halfsample16_kernel<<<grid, 256, 0, stream>>>(src, w, h, spitch, dst, dpitch);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_twothirdsample16(const uint16_t* src, int w, int h, long long spitch, uint16_t* dst, long long dpitch, cudaStream_t stream) {
+  if (w / 3 <= 0 || h / 3 <= 0) return cudaSuccess;
+  dim3 grid((w / 3 + 255) / 256, h / 3);
+  twothirdsample16_kernel<<<grid, 256, 0, stream>>>(src, w, h, spitch, dst, dpitch);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_pyramid(const CUtensorMap& src_map, const PyramidGeom& g, uint8_t* pyr, int n_frames, int write_l0,
                            cudaStream_t stream) {
   dim3 grid((g.w0 + kTileW - 1) / kTileW, (g.h0 + kTileH - 1) / kTileH, n_frames);

@@ -9,11 +9,18 @@
 #ifndef BRISK_BRISK_H_
 #define BRISK_BRISK_H_
 
+// With BRISK_B200_USE_OPENCV defined (OpenCV 3 headers available) the classes derive from cv::Feature2D /
+// cv::DescriptorMatcher exactly like the reference's (brisk-feature-detector.h:51, brisk-descriptor-extractor.h:54,
+// scale-space-feature-detector.h:63, brisk-feature.h:54, brute-force-matcher.h:54), override the same virtuals with the
+// same cv::InputArray / cv::OutputArray signatures and the cv:: aliases of brisk/brisk.h:56-59 exist, so a
+// cv::Ptr<cv::Feature2D> / cv::Ptr<cv::DescriptorMatcher> holder works unchanged.  Without it the same classes stand
+// alone on the minimal agast::Mat / agast::KeyPoint of <agast/wrap-opencv.h> (the reference's own !HAVE_OPENCV branch).
 #include <algorithm>
 #include <bitset>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -21,32 +28,53 @@
 #include <agast/wrap-opencv.h>
 #include "../brisk_b200.h"
 
+#ifdef BRISK_B200_USE_OPENCV
+#define BRISK_B200_FEATURE2D : public cv::Feature2D
+#else
+#define BRISK_B200_FEATURE2D
+#endif
+
 namespace brisk {
 
 namespace detail {
 inline void check(brisk_ctx* ctx, int rc) {
   if (rc != BRISK_OK) throw std::runtime_error(std::string("brisk_b200: ") + brisk_last_error(ctx));
 }
-// Per-thread context on device BRISK_B200_DEVICE (default 0).
-inline brisk_ctx* context() {
-  struct Holder {
+// Per-thread context on device BRISK_B200_DEVICE (default 0).  Shared ownership: every detector / extractor / calculator
+// keeps the context it created its handles in alive, so objects with static storage duration, or objects destroyed on
+// another thread after their creating thread has exited, never touch a freed context.
+typedef std::shared_ptr<brisk_ctx> ContextPtr;
+inline ContextPtr context_ptr() {
+  static thread_local ContextPtr holder;
+  if (!holder) {
+    const char* d = std::getenv("BRISK_B200_DEVICE");
     brisk_ctx* ctx = nullptr;
-    Holder() {
-      const char* d = std::getenv("BRISK_B200_DEVICE");
-      if (brisk_ctx_create(d ? std::atoi(d) : 0, nullptr, &ctx) != BRISK_OK)
-        throw std::runtime_error("brisk_b200: no usable CUDA device (there is no CPU fallback)");
-    }
-    ~Holder() { brisk_ctx_destroy(ctx); }
-  };
-  static thread_local Holder h;
-  return h.ctx;
+    if (brisk_ctx_create(d ? std::atoi(d) : 0, nullptr, &ctx) != BRISK_OK)
+      throw std::runtime_error("brisk_b200: no usable CUDA device (there is no CPU fallback)");
+    holder.reset(ctx, brisk_ctx_destroy);
+  }
+  return holder;
 }
+inline brisk_ctx* context() { return context_ptr().get(); }
 static_assert(sizeof(agast::KeyPoint) == sizeof(brisk_keypoint), "KeyPoint must match cv::KeyPoint's 28-byte layout");
+
+// The C ABI reads a mask with the image's geometry (same size, row stride and frame pitch).  Returns the pointer to pass:
+// the mask itself when it is laid out like the image, else a repacked copy in `scratch`; throws on a size mismatch
+// (the reference CHECKs the mask size in scale-space-feature-detector.h:113-116 and indexes it by image coordinates in
+// brisk-feature-detector.cc:49-66).
+inline const unsigned char* mask_like_image(const agast::Mat& image, const agast::Mat& mask, std::vector<unsigned char>* scratch) {
+  if (mask.empty()) return nullptr;
+  if (mask.rows != image.rows || mask.cols != image.cols) throw std::runtime_error("brisk_b200: mask size differs from the image size");
+  if ((size_t)mask.step == (size_t)image.step) return mask.data;
+  scratch->assign((size_t)image.step * image.rows, 0);
+  for (int r = 0; r < mask.rows; ++r) std::memcpy(scratch->data() + (size_t)r * (size_t)image.step, mask.data + (size_t)r * (size_t)mask.step, mask.cols);
+  return scratch->data();
+}
 }  // namespace detail
 
 // brisk::BriskFeatureDetector -- reference brisk/include/brisk/brisk-feature-detector.h:51-84,
 // brisk/src/brisk-feature-detector.cc:69-92.
-class BriskFeatureDetector {
+class BriskFeatureDetector BRISK_B200_FEATURE2D {
  public:
   BriskFeatureDetector(int thresh, int octaves_ = 3, bool suppressScaleNonmaxima = true)
       : threshold(thresh), octaves(octaves_), m_suppress(suppressScaleNonmaxima) {}
@@ -57,6 +85,13 @@ class BriskFeatureDetector {
   int threshold;
   int octaves;
 
+#ifdef BRISK_B200_USE_OPENCV
+  // cv::Feature2D::detect() forwards here; the reference's override (brisk-feature-detector.h:69-74): detection only
+  virtual void detectAndCompute(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint>& keypoints,
+                                cv::OutputArray /*descriptors*/, bool /*useProvidedKeypoints*/ = false) {
+    detectImpl(image.getMat(), keypoints, mask.getMat());
+  }
+#else
   // cv::Feature2D::detect
   void detect(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, const agast::Mat& mask = agast::Mat()) const {
     detectImpl(image, keypoints, mask);
@@ -66,14 +101,14 @@ class BriskFeatureDetector {
                                 agast::Mat& /*descriptors*/, bool /*useProvidedKeypoints*/ = false) {
     detectImpl(image, keypoints, mask);
   }
+#endif
   // brisk-feature-detector.cc:87-92: re-examines the passed key points in every pyramid layer and replaces
   // them by the key points the scale-space checks accept (one per accepting layer; octave = layer index).
   // A layer that keeps none of the points is detected on instead, as in the reference (brisk-layer.cc:103-105).
   // With an empty vector the reference detects on every layer (threshold map without lower bound): that case
   // is reported as std::runtime_error here -- call detect().
   void ComputeScale(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints) const {
-    brisk_ctx* ctx = detail::context();
-    ensure(ctx);
+    brisk_ctx* ctx = ensure();
     const int32_t n_in = (int32_t)keypoints.size();
     const int n_layers = octaves == 0 ? 1 : 2 * octaves;
     std::vector<agast::KeyPoint> out((size_t)std::max(1, n_layers * n_in));
@@ -97,14 +132,15 @@ class BriskFeatureDetector {
   virtual void detectImpl(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, const agast::Mat& mask) const {
     keypoints.clear();
     if (image.empty()) return;
-    brisk_ctx* ctx = detail::context();
-    ensure(ctx);
+    brisk_ctx* ctx = ensure();
+    std::vector<unsigned char> mask_scratch;
+    const unsigned char* mask_ptr = detail::mask_like_image(image, mask, &mask_scratch);
     int cap = (int)std::max<long long>(4096, (long long)image.rows * image.cols / 64);
     for (;;) {
       keypoints.resize(cap);
       int32_t count = 0;
       const int rc = brisk_detect(ctx, det_, image.data, 1, image.cols, image.rows, image.step, image.step * image.rows,
-                                  mask.empty() ? nullptr : mask.data, reinterpret_cast<brisk_keypoint*>(keypoints.data()), &count, cap);
+                                  mask_ptr, reinterpret_cast<brisk_keypoint*>(keypoints.data()), &count, cap);
       if (rc == BRISK_ERR_CAPACITY && count > cap) { cap = count; continue; }  // grow and retry
       detail::check(ctx, rc);
       keypoints.resize(count);
@@ -113,24 +149,84 @@ class BriskFeatureDetector {
   }
 
  private:
-  void ensure(brisk_ctx* ctx) const {
-    if (det_ && ctx_ == ctx && cfg_thr_ == threshold && cfg_oct_ == octaves) return;
+  // (re)creates the detector handle in the calling thread's context when the public parameters changed; the handle's
+  // context is kept alive by ctx_
+  brisk_ctx* ensure() const {
+    detail::ContextPtr cur = detail::context_ptr();
+    if (det_ && ctx_ == cur && cfg_thr_ == threshold && cfg_oct_ == octaves) return cur.get();
     if (det_) brisk_detector_destroy(det_);
     det_ = nullptr;
-    detail::check(ctx, brisk_agast_detector_create(ctx, threshold, octaves, m_suppress ? 1 : 0, &det_));
+    detail::check(cur.get(), brisk_agast_detector_create(cur.get(), threshold, octaves, m_suppress ? 1 : 0, &det_));
     if (corner_cap_ > 0) brisk_detector_set_corner_capacity(det_, corner_cap_);
-    ctx_ = ctx; cfg_thr_ = threshold; cfg_oct_ = octaves;
+    ctx_ = cur; cfg_thr_ = threshold; cfg_oct_ = octaves;
+    return cur.get();
   }
   bool m_suppress;
   int corner_cap_ = 0;
+  mutable detail::ContextPtr ctx_;   // declared before det_'s users: released after the destructor body destroyed det_
   mutable brisk_detector* det_ = nullptr;
-  mutable brisk_ctx* ctx_ = nullptr;
   mutable int cfg_thr_ = 0, cfg_oct_ = 0;
 };
 
-// Tag type: the only score calculator of the reference that is usable with the scale-space
-// detector (brisk/include/brisk/harris-score-calculator.h:52-90).
-class HarrisScoreCalculator {};
+// brisk::HarrisScoreCalculator : ScoreCalculator<int> -- reference brisk/include/brisk/harris-score-calculator.h:52-90,
+// internal/score-calculator.h:60-127.  SetImage computes the integer Harris score map (HarrisScoresSSE) on the GPU and keeps
+// it on the host; Score(int, int) / Score(double, double) are the reference's inline accessors on that map; Get2dMaxima
+// lists the 8-neighbour maxima >= absoluteThreshold in raster order.  Also the template argument of
+// ScaleSpaceFeatureDetector, which is the only use the reference itself makes of it.
+class HarrisScoreCalculator {
+ public:
+  typedef int Score_t;
+  struct PointWithScore {  // score-calculator.h:69-91 (USE_SIMPLE_POINT_WITH_SCORE)
+    PointWithScore() : score(0), x(0), y(0) {}
+    PointWithScore(Score_t score_, uint16_t x_, uint16_t y_) : score(score_), x(x_), y(y_) {}
+    Score_t score;
+    uint16_t x, y;
+    bool operator<(const PointWithScore& other) const { return score > other.score; }  // (sic) sorts descending
+  };
+  virtual ~HarrisScoreCalculator() {}
+
+  void SetImage(const agast::Mat& img, bool initScores = true) {
+    _img = img;
+    if (initScores) InitializeScores();
+  }
+  inline double Score(double u, double v) {
+    const int u_int = static_cast<int>(u), v_int = static_cast<int>(v);
+    if (u_int + 1 >= cols_ || v_int + 1 >= rows_ || u_int < 0 || v_int < 0) return 0.0;
+    const double ru = u - static_cast<double>(u_int), rv = v - static_cast<double>(v_int);
+    const double oneMinus_ru = 1.0 - ru, oneMinus_rv = 1.0 - rv;
+    return oneMinus_rv * (oneMinus_ru * at(v_int, u_int) + ru * at(v_int, u_int + 1)) +
+           rv * (oneMinus_ru * at(v_int + 1, u_int) + ru * at(v_int + 1, u_int + 1));
+  }
+  inline Score_t Score(int u, int v) { return at(v, u); }
+  virtual void Get2dMaxima(std::vector<PointWithScore>& points, Score_t absoluteThreshold = 0) {
+    if (_img.empty()) return;
+    detail::ContextPtr ctx = detail::context_ptr();
+    int cap = std::max(4000, _img.rows * _img.cols / 32);
+    for (;;) {
+      std::vector<int32_t> sxy((size_t)cap * 3);
+      int32_t n = 0;
+      const int rc = brisk_harris_scores(ctx.get(), _img.data, _img.cols, _img.rows, _img.step, absoluteThreshold, nullptr, sxy.data(), cap, &n);
+      if (rc == BRISK_ERR_CAPACITY && n > cap) { cap = n; continue; }
+      detail::check(ctx.get(), rc);
+      points.reserve(points.size() + (size_t)n);
+      for (int i = 0; i < n; ++i) points.push_back(PointWithScore(sxy[3 * i], (uint16_t)sxy[3 * i + 1], (uint16_t)sxy[3 * i + 2]));
+      return;
+    }
+  }
+
+ protected:
+  virtual void InitializeScores() {
+    detail::ContextPtr ctx = detail::context_ptr();
+    rows_ = _img.rows; cols_ = _img.cols;
+    _scores.assign((size_t)rows_ * cols_, 0);
+    if (_img.empty()) return;
+    detail::check(ctx.get(), brisk_harris_scores(ctx.get(), _img.data, _img.cols, _img.rows, _img.step, 0, _scores.data(), nullptr, 0, nullptr));
+  }
+  int at(int row, int col) const { return _scores[(size_t)row * cols_ + col]; }
+  agast::Mat _img;             // the image we operate on
+  std::vector<int> _scores;    // calculated scores, rows_ x cols_
+  int rows_ = 0, cols_ = 0;
+};
 
 // brisk::ScaleSpaceFeatureDetector<SCORE_CALCULATOR_T> -- reference
 // brisk/include/brisk/scale-space-feature-detector.h:62-135.  Empty images return silently; the
@@ -138,7 +234,7 @@ class HarrisScoreCalculator {};
 // key points" mode (:103-108): no detection, the passed points with response > 1e6 are re-filtered by the
 // uniformity enforcement / bucketing and returned unrefined (defined for octaves == 0 only).
 template <class SCORE_CALCULATOR_T>
-class ScaleSpaceFeatureDetector {
+class ScaleSpaceFeatureDetector BRISK_B200_FEATURE2D {
  public:
   typedef SCORE_CALCULATOR_T ScoreCalculator_t;
   ScaleSpaceFeatureDetector(size_t octaves, double uniformityRadius, double absoluteThreshold = 0,
@@ -148,15 +244,37 @@ class ScaleSpaceFeatureDetector {
   ScaleSpaceFeatureDetector(const ScaleSpaceFeatureDetector&) = delete;
   ScaleSpaceFeatureDetector& operator=(const ScaleSpaceFeatureDetector&) = delete;
 
-  void detect(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, const agast::Mat& /*mask*/ = agast::Mat()) const {
+  void detect(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, const agast::Mat& mask = agast::Mat()) const {
+    detectImpl(image, keypoints, mask);
+  }
+
+#ifdef BRISK_B200_USE_OPENCV
+  // scale-space-feature-detector.h:92-97: detection only
+  virtual void detectAndCompute(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint>& keypoints,
+                                cv::OutputArray /*descriptors*/, bool /*useProvidedKeypoints*/ = false) {
+    detectImpl(image.getMat(), keypoints, mask.getMat());
+  }
+#else
+  virtual void detectAndCompute(const agast::Mat& image, const agast::Mat& mask, std::vector<agast::KeyPoint>& keypoints,
+                                agast::Mat& /*descriptors*/, bool /*useProvidedKeypoints*/ = false) {
+    detectImpl(image, keypoints, mask);
+  }
+#endif
+
+ protected:
+  // scale-space-feature-detector.h:100-128
+  virtual void detectImpl(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, const agast::Mat& mask = agast::Mat()) const {
     if (image.empty()) return;
-    brisk_ctx* ctx = detail::context();
-    if (!det_ || ctx_ != ctx) {
+    if (!mask.empty() && (mask.rows != image.rows || mask.cols != image.cols))  // the reference CHECKs this (:113-116); the mask itself is unused
+      throw std::runtime_error("brisk_b200: mask size differs from the image size");
+    detail::ContextPtr cur = detail::context_ptr();
+    brisk_ctx* ctx = cur.get();
+    if (!det_ || ctx_ != cur) {
       if (det_) brisk_detector_destroy(det_);
       det_ = nullptr;
       const int64_t mk = _maxNumKpt > (size_t)std::numeric_limits<int64_t>::max() ? -1 : (int64_t)_maxNumKpt;
       detail::check(ctx, brisk_harris_detector_create(ctx, (int)_octaves, _uniformityRadius, _absoluteThreshold, mk, &det_));
-      ctx_ = ctx;
+      ctx_ = cur;
     }
     if (!keypoints.empty()) {  // use the passed key points
       const int32_t n_in = (int32_t)keypoints.size();
@@ -181,26 +299,19 @@ class ScaleSpaceFeatureDetector {
     }
   }
 
-  // scale-space-feature-detector.h:92-97: detection only
-  virtual void detectAndCompute(const agast::Mat& image, const agast::Mat& mask, std::vector<agast::KeyPoint>& keypoints,
-                                agast::Mat& /*descriptors*/, bool /*useProvidedKeypoints*/ = false) {
-    detect(image, keypoints, mask);
-  }
-
- protected:
   size_t _octaves;
   double _uniformityRadius;
   double _absoluteThreshold;
   size_t _maxNumKpt;
 
  private:
+  mutable detail::ContextPtr ctx_;
   mutable brisk_detector* det_ = nullptr;
-  mutable brisk_ctx* ctx_ = nullptr;
 };
 typedef ScaleSpaceFeatureDetector<HarrisScoreCalculator> HarrisScaleSpaceFeatureDetector;
 
 // brisk::BriskDescriptorExtractor -- reference brisk/include/brisk/brisk-descriptor-extractor.h:54-202.
-class BriskDescriptorExtractor {
+class BriskDescriptorExtractor BRISK_B200_FEATURE2D {
  public:
   static const unsigned int kDescriptorLength = 384;
   enum Version { briskV1 = 1, briskV2 = 2 };
@@ -221,13 +332,34 @@ class BriskDescriptorExtractor {
   bool rotationInvariance;
   bool scaleInvariance;
 
-  int descriptorSize() const { ensure(detail::context()); return brisk_extractor_descriptor_size(ext_); }
+  int descriptorSize() const { ensure(); return brisk_extractor_descriptor_size(ext_); }
   int descriptorType() const { return CV_8U; }
 
   // compute(): removes key points too close to the border, writes their angle, fills an N x descriptorSize() matrix
   virtual void compute(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, agast::Mat& descriptors) const {
-    brisk_ctx* ctx = detail::context();
-    ensure(ctx);
+    computeImpl(image, keypoints, descriptors);
+  }
+  virtual void compute(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints,
+                       std::vector<std::bitset<kDescriptorLength> >& descriptors) const {
+    computeImpl(image, keypoints, descriptors);
+  }
+#ifdef BRISK_B200_USE_OPENCV
+  // brisk-descriptor-extractor.h:120-125: extraction only
+  virtual void detectAndCompute(cv::InputArray image, cv::InputArray /*mask*/, std::vector<cv::KeyPoint>& keypoints,
+                                cv::OutputArray descriptors, bool /*useProvidedKeypoints*/ = false) {
+    computeImpl(image.getMat(), keypoints, descriptors.getMatRef());
+  }
+#else
+  virtual void detectAndCompute(const agast::Mat& image, const agast::Mat& /*mask*/, std::vector<agast::KeyPoint>& keypoints,
+                                agast::Mat& descriptors, bool /*useProvidedKeypoints*/ = false) {
+    computeImpl(image, keypoints, descriptors);
+  }
+#endif
+
+ protected:
+  // brisk-descriptor-extractor.cc:589-599
+  virtual void computeImpl(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, agast::Mat& descriptors) const {
+    brisk_ctx* ctx = ensure();
     const int nb = brisk_extractor_descriptor_size(ext_);
     int32_t count = (int32_t)keypoints.size();
     const int cap = std::max<int>(count, 1);
@@ -239,15 +371,10 @@ class BriskDescriptorExtractor {
     descriptors = agast::Mat::zeros(count, nb, CV_8UC1);
     if (count) std::memcpy(descriptors.data, buf.data(), (size_t)count * nb);
   }
-  // cv::Feature2D::detectAndCompute as the reference overrides it (brisk-descriptor-extractor.h:120-125): extraction only
-  virtual void detectAndCompute(const agast::Mat& image, const agast::Mat& /*mask*/, std::vector<agast::KeyPoint>& keypoints,
-                                agast::Mat& descriptors, bool /*useProvidedKeypoints*/ = false) {
-    compute(image, keypoints, descriptors);
-  }
-  virtual void compute(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints,
-                       std::vector<std::bitset<kDescriptorLength> >& descriptors) const {
+  virtual void computeImpl(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints,
+                           std::vector<std::bitset<kDescriptorLength> >& descriptors) const {
     agast::Mat d;
-    compute(image, keypoints, d);
+    computeImpl(image, keypoints, d);
     descriptors.assign(keypoints.size(), std::bitset<kDescriptorLength>());
     for (size_t k = 0; k < keypoints.size(); ++k)
       for (unsigned p = 0; p < kDescriptorLength && p < 8u * d.cols; ++p)
@@ -255,25 +382,27 @@ class BriskDescriptorExtractor {
   }
 
  private:
-  void ensure(brisk_ctx* ctx) const {
-    if (ext_ && ctx_ == ctx && cfg_rot_ == rotationInvariance && cfg_scale_ == scaleInvariance) return;
+  brisk_ctx* ensure() const {
+    detail::ContextPtr cur = detail::context_ptr();
+    if (ext_ && ctx_ == cur && cfg_rot_ == rotationInvariance && cfg_scale_ == scaleInvariance) return cur.get();
     if (ext_) brisk_extractor_destroy(ext_);
     ext_ = nullptr;
-    detail::check(ctx, brisk_extractor_create(ctx, rotationInvariance, scaleInvariance, version_, pattern_scale_,
-                                              fname_.empty() ? nullptr : fname_.c_str(), &ext_));
-    ctx_ = ctx; cfg_rot_ = rotationInvariance; cfg_scale_ = scaleInvariance;
+    detail::check(cur.get(), brisk_extractor_create(cur.get(), rotationInvariance, scaleInvariance, version_, pattern_scale_,
+                                                    fname_.empty() ? nullptr : fname_.c_str(), &ext_));
+    ctx_ = cur; cfg_rot_ = rotationInvariance; cfg_scale_ = scaleInvariance;
+    return cur.get();
   }
   int version_;
   float pattern_scale_;
   std::string fname_;
+  mutable detail::ContextPtr ctx_;
   mutable brisk_extractor* ext_ = nullptr;
-  mutable brisk_ctx* ctx_ = nullptr;
   mutable bool cfg_rot_ = false, cfg_scale_ = false;
 };
 
 // brisk::BriskFeature -- reference brisk/include/brisk/brisk-feature.h:54-114: Harris scale-space
 // detector + BRISK extractor behind one detectAndCompute().
-class BriskFeature {
+class BriskFeature BRISK_B200_FEATURE2D {
  public:
   BriskFeature(size_t octaves, double uniformityRadius, double absoluteThreshold = 0,
                size_t maxNumKpt = std::numeric_limits<size_t>::max(), bool rotationInvariant = true, bool scaleInvariant = true,
@@ -282,25 +411,45 @@ class BriskFeature {
         _briskExtractor(rotationInvariant, scaleInvariant, extractorVersion) {}
   int descriptorSize() const { return _briskExtractor.descriptorSize(); }
   int descriptorType() const { return _briskExtractor.descriptorType(); }
-  void detectAndCompute(const agast::Mat& image, const agast::Mat& mask, std::vector<agast::KeyPoint>& keypoints,
-                        agast::Mat& descriptors, bool useProvidedKeypoints = false) {
+#ifdef BRISK_B200_USE_OPENCV
+  virtual void detectAndCompute(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint>& keypoints,
+                                cv::OutputArray descriptors, bool useProvidedKeypoints = false) {
+    run(image.getMat(), mask.getMat(), keypoints, descriptors.getMatRef(), useProvidedKeypoints);
+  }
+#else
+  virtual void detectAndCompute(const agast::Mat& image, const agast::Mat& mask, std::vector<agast::KeyPoint>& keypoints,
+                                agast::Mat& descriptors, bool useProvidedKeypoints = false) {
+    run(image, mask, keypoints, descriptors, useProvidedKeypoints);
+  }
+#endif
+  virtual ~BriskFeature() {}
+
+ private:
+  void run(const agast::Mat& image, const agast::Mat& mask, std::vector<agast::KeyPoint>& keypoints, agast::Mat& descriptors,
+           bool useProvidedKeypoints) {
     // brisk-feature.h:80-93: the detector runs either way -- on provided key points it re-filters them
     // ("use passed key points") instead of detecting
     if (!useProvidedKeypoints) keypoints.clear();
     _briskDetector.detect(image, keypoints, mask);
     _briskExtractor.compute(image, keypoints, descriptors);
   }
-
- private:
   ScaleSpaceFeatureDetector<HarrisScoreCalculator> _briskDetector;
   BriskDescriptorExtractor _briskExtractor;
 };
 
 // brisk::Hamming -- reference brisk/include/brisk/internal/hamming.h:56-114.
+// NOTE for callers that loop over descriptor pairs (OKVIS-style): one operator() call is one host -> device -> host round
+// trip (~10 us), four orders of magnitude slower than the SSE primitive it replaces.  Use Hamming::distances() (n pairs per
+// call, brisk_hamming_distance) or BruteForceMatcher (all pairs on the device) instead; operator() exists for API parity.
 class Hamming {
  public:
   typedef unsigned char ValueType;
   typedef int ResultType;
+  // n row pairs in one call: out[i] = popcount(a_i xor b_i) over size / 16 whole 128-bit words (host or device pointers)
+  static void distances(const unsigned char* a, const unsigned char* b, int64_t n, int size, int32_t* out) {
+    brisk_ctx* ctx = detail::context();
+    detail::check(ctx, brisk_hamming_distance(ctx, a, b, n, size, out));
+  }
   ResultType operator()(const unsigned char* a, const unsigned char* b, int size) const {
     int32_t d = 0;
     brisk_ctx* ctx = detail::context();
@@ -316,17 +465,49 @@ class Hamming {
   }
 };
 
+#ifdef BRISK_B200_USE_OPENCV
+typedef cv::DMatch DMatch;
+#else
 struct DMatch {  // == cv::DMatch
   int queryIdx = -1, trainIdx = -1, imgIdx = -1;
   float distance = std::numeric_limits<float>::max();
   bool operator<(const DMatch& m) const { return distance < m.distance; }
 };
+#endif
 
 // brisk::BruteForceMatcher -- reference brisk/include/brisk/brute-force-matcher.h:54-94 and
 // brisk/src/brute-force-matcher.cc:59-214, with the cv::DescriptorMatcher conventions it relies on: a train
 // collection (add / clear), per-image masks (query rows x train rows, 0 = pair excluded; an empty mask allows
 // everything), compactResult, knnMatch / radiusMatch / match.  Distances and candidate selection run on the GPU;
 // this class only reshapes the results into the reference's DMatch lists.
+#ifdef BRISK_B200_USE_OPENCV
+class BruteForceMatcher : public cv::DescriptorMatcher {
+ public:
+  explicit BruteForceMatcher(const Hamming& = Hamming()) {}
+  virtual ~BruteForceMatcher() {}
+  virtual bool isMaskSupported() const { return true; }
+  virtual cv::Ptr<cv::DescriptorMatcher> clone(bool emptyTrainData = false) const {
+    BruteForceMatcher* m = new BruteForceMatcher();
+    if (!emptyTrainData)
+      for (const auto& d : trainDescCollection) m->trainDescCollection.push_back(d.clone());
+    return cv::Ptr<cv::DescriptorMatcher>(m);
+  }
+
+ protected:
+  // brute-force-matcher.h:66-75; cv::DescriptorMatcher::knnMatch / radiusMatch / match forward here
+  virtual void knnMatchImpl(cv::InputArray queryDescriptors, std::vector<std::vector<cv::DMatch> >& matches, int k,
+                            cv::InputArrayOfArrays masks = cv::noArray(), bool compactResult = false) {
+    std::vector<cv::Mat> mv;
+    masks.getMatVector(mv);
+    knnImpl(queryDescriptors.getMat(), trainDescCollection, matches, k, mv, compactResult);
+  }
+  virtual void radiusMatchImpl(cv::InputArray queryDescriptors, std::vector<std::vector<cv::DMatch> >& matches, float maxDistance,
+                               cv::InputArrayOfArrays masks = cv::noArray(), bool compactResult = false) {
+    std::vector<cv::Mat> mv;
+    masks.getMatVector(mv);
+    radiusImpl(queryDescriptors.getMat(), trainDescCollection, matches, maxDistance, mv, compactResult);
+  }
+#else
 class BruteForceMatcher {
  public:
   explicit BruteForceMatcher(const Hamming& = Hamming()) {}
@@ -360,6 +541,7 @@ class BruteForceMatcher {
     matches.clear();
     for (const auto& v : knn) matches.insert(matches.end(), v.begin(), v.end());
   }
+#endif  // BRISK_B200_USE_OPENCV
 
  private:
   struct Collection {
@@ -471,12 +653,21 @@ class BruteForceMatcher {
       for (int64_t j = offsets[q]; j < offsets[q + 1]; ++j) matches.back().push_back(make(q, idx[(size_t)j], c.start, (float)dist[(size_t)j]));
     }
   }
+#ifndef BRISK_B200_USE_OPENCV
   std::vector<agast::Mat> train_;
+#endif
 };
 
-// deprecated aliases of the reference (brisk/include/brisk/brisk.h:56-65)
+// deprecated aliases of the reference (brisk/include/brisk/brisk.h:61-65)
 typedef BruteForceMatcher BruteForceMatcherSse;
 typedef Hamming HammingSse;
 
 }  // namespace brisk
+
+#ifdef BRISK_B200_USE_OPENCV
+namespace cv {  // brisk/include/brisk/brisk.h:56-59
+typedef brisk::BriskDescriptorExtractor BriskDescriptorExtractor;
+typedef brisk::BriskFeatureDetector BriskFeatureDetector;
+}  // namespace cv
+#endif
 #endif  // BRISK_BRISK_H_

@@ -142,6 +142,22 @@ int brisk_detect_describe(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* 
                           int h, size_t stride, size_t frame_pitch, const uint8_t* masks, brisk_keypoint* kps,
                           int32_t* counts, int cap, uint8_t* desc);
 
+/* brisk::HarrisScoreCalculator::SetImage (InitializeScores = HarrisScoresSSE) and Get2dMaxima -- reference
+ * brisk/include/brisk/harris-score-calculator.h:52-90, brisk/src/harris-score-calculator.cc:53-106, brisk/src/harris-scores.cc:
+ * 53-279.  One 8-bit image.  scores (nullable): the int32 score map, h x w tightly packed, host memory.  maxima_sxy (nullable):
+ * (score, x, y) triples of the 8-neighbour maxima >= abs_threshold in raster order, at most `cap`; *n_maxima receives the true
+ * number (BRISK_ERR_CAPACITY when it exceeds cap). */
+int brisk_harris_scores(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_t stride, int abs_threshold, int32_t* scores,
+                        int32_t* maxima_sxy, int cap, int32_t* n_maxima);
+
+/* brisk::Halfsample16 / brisk::Twothirdsample16 -- reference brisk/src/image-down-sampling.cc:56-139, 394-548
+ * (declared in brisk/include/brisk/internal/image-down-sampling.h:50-53).  CV_16UC1 images in host or device memory,
+ * strides in bytes; dst is (h / 2) x (w / 2) resp. 2 (h / 3) x 2 (w / 3).  Bit-exact including the reference's quirks
+ * (the doubled +1 on the lower-left pixel of Halfsample16, the signed saturation at 32767 of Twothirdsample16).  Images
+ * narrower than one SSE block (16 resp. 12 columns), which the reference leaves unwritten, are refused. */
+int brisk_halfsample16(brisk_ctx* ctx, const uint16_t* src, int w, int h, size_t src_stride, uint16_t* dst, size_t dst_stride);
+int brisk_twothirdsample16(brisk_ctx* ctx, const uint16_t* src, int w, int h, size_t src_stride, uint16_t* dst, size_t dst_stride);
+
 /* Stage dumps for parity tests: pyramid layers of ONE frame concatenated (tight rows), dims[2*i] =
  * cols, dims[2*i+1] = rows; integral image (h+1)x(w+1) int32; raw corners (x, y, score) of all
  * layers in detection order with layer_counts[n_layers]. */

@@ -55,6 +55,22 @@ def twothirdsample8(img):
     return out
 
 
+def halfsample16(img):
+    img = np.ascontiguousarray(img, np.uint16)
+    h, w = img.shape
+    out = np.zeros((h // 2, w // 2), np.uint16)
+    lib().ref_halfsample16(_p(img), w, h, _p(out))
+    return out
+
+
+def twothirdsample16(img):
+    img = np.ascontiguousarray(img, np.uint16)
+    h, w = img.shape
+    out = np.zeros((2 * (h // 3), 2 * (w // 3)), np.uint16)
+    lib().ref_twothirdsample16(_p(img), w, h, _p(out))
+    return out
+
+
 def layer_dump(img, thresh, lower=10, cap=1 << 20):
     """-> (thrmap u8 HxW, corners int32 [n,3] = x, y, score)"""
     img, w, h = _img(img)

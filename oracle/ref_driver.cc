@@ -128,6 +128,29 @@ int ref_halfsample8(const uint8_t* src, int w, int h, uint8_t* dst) {
   return 0;
 }
 
+// 16-bit samplers (image-down-sampling.cc:56-139,394-548); dst is pre-filled with 0xffff so that pixels the reference does
+// not write (images narrower than one SSE block) show up.
+int ref_halfsample16(const uint16_t* src, int w, int h, uint16_t* dst) {
+  cv::Mat s(h, w, CV_16UC1);
+  memcpy(s.data, src, (size_t)w * h * 2);
+  cv::Mat d(h / 2, w / 2, CV_16UC1);
+  memset(d.data, 0xff, (size_t)(h / 2) * (w / 2) * 2);
+  brisk::Halfsample16(s, d);
+  memcpy(dst, d.data, (size_t)(h / 2) * (w / 2) * 2);
+  return 0;
+}
+
+int ref_twothirdsample16(const uint16_t* src, int w, int h, uint16_t* dst) {
+  cv::Mat s(h, w, CV_16UC1);
+  memcpy(s.data, src, (size_t)w * h * 2);
+  const int dw = 2 * (w / 3), dh = 2 * (h / 3);
+  cv::Mat d(dh, dw, CV_16UC1);
+  memset(d.data, 0xff, (size_t)dh * dw * 2);
+  brisk::Twothirdsample16(s, d);
+  memcpy(dst, d.data, (size_t)dh * dw * 2);
+  return 0;
+}
+
 int ref_twothirdsample8(const uint8_t* src, int w, int h, uint8_t* dst) {
   // The SSE loop may read a few bytes past the last row, so
   // give the source slack.

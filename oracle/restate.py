@@ -51,6 +51,37 @@ def twothirdsample8(img):
     return out
 
 
+def halfsample16(img):
+    """Halfsample16 (image-down-sampling.cc:56-139): per 2x2 block avg(avg(a, b), avg(sat(sat(c + 1) + 1), d)) with the
+    rounding-up average of pavgw; the last SSE block overlaps the one before, so every output pixel follows the same rule.
+    Defined for cols >= 16 (the reference writes nothing otherwise)."""
+    s = np.ascontiguousarray(img, np.uint16).astype(np.int64)
+    h, w = s.shape
+    assert w >= 16
+    hh, ww = h // 2, w // 2
+    a, b = s[0:2 * hh:2, 0:2 * ww:2], s[0:2 * hh:2, 1:2 * ww:2]
+    c, d = s[1:2 * hh:2, 0:2 * ww:2], s[1:2 * hh:2, 1:2 * ww:2]
+    c = np.minimum(np.minimum(c + 1, 65535) + 1, 65535)
+    avg = lambda x, y: (x + y + 1) >> 1
+    return avg(avg(a, b), avg(c, d)).astype(np.uint16)
+
+
+def twothirdsample16(img):
+    """Twothirdsample16 (image-down-sampling.cc:394-548): per 3x3 block the 4:2:2:1 weighted sums of its four 2x2 corners,
+    truncating division by 9, packed with SIGNED saturation (values above 32767 come out as 32767).  Needs cols >= 12."""
+    s = np.ascontiguousarray(img, np.uint16).astype(np.int64)
+    h, w = s.shape
+    assert (w // 3) * 3 >= 12
+    bh, bw = h // 3, w // 3
+    p = lambda r, c: s[r:3 * bh:3, c:3 * bw:3]
+    out = np.zeros((2 * bh, 2 * bw), np.int64)
+    out[0::2, 0::2] = (4 * p(0, 0) + 2 * p(0, 1) + 2 * p(1, 0) + p(1, 1)) // 9
+    out[0::2, 1::2] = (4 * p(0, 2) + 2 * p(0, 1) + 2 * p(1, 2) + p(1, 1)) // 9
+    out[1::2, 0::2] = (4 * p(2, 0) + 2 * p(2, 1) + 2 * p(1, 0) + p(1, 1)) // 9
+    out[1::2, 1::2] = (4 * p(2, 2) + 2 * p(2, 1) + 2 * p(1, 2) + p(1, 1)) // 9
+    return np.minimum(out, 32767).astype(np.uint16)
+
+
 def thrmap(img):
     img, w, h = _img(img)
     out = np.zeros((h, w), np.uint8)

@@ -9,6 +9,10 @@ class Feature2D {
   virtual void detect(InputArray image, std::vector<KeyPoint>& k, InputArray mask = noArray()) {
     detectAndCompute(image, mask, k, noOutArray(), false);
   }
+  // OpenCV 3: compute() is detectAndCompute() on the provided key points
+  virtual void compute(InputArray image, std::vector<KeyPoint>& k, OutputArray descriptors) {
+    detectAndCompute(image, noArray(), k, descriptors, true);
+  }
   virtual int descriptorSize() const { return 0; }
   virtual int descriptorType() const { return 0; }
 };

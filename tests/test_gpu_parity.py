@@ -27,6 +27,29 @@ def test_pyramid_bit_exact(ctx, oracle, w, h):
             assert a.shape == b.shape and np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("w,h", [(752, 480), (641, 479), (16, 8), (17, 9), (33, 21), (1920, 1080)])
+def test_samplers_16bit_bit_exact(ctx, oracle, w, h):
+    # Halfsample16 / Twothirdsample16 (image-down-sampling.cc:56-139, 394-548) incl. their saturation quirks; the oracle's
+    # restatement is pinned to the compiled reference in tests/test_oracle_golden.py
+    rng = np.random.default_rng(w + h)
+    for hi in (65536, 4096, 300):
+        img = rng.integers(0, hi, (h, w)).astype(np.uint16)
+        img[0, 0] = 65535; img[1, 0] = 65535; img[-1, -1] = 65535; img[-2, -1] = 65534
+        assert np.array_equal(ctx.halfsample16(img), oracle.halfsample16(img))
+        assert np.array_equal(ctx.twothirdsample16(img), oracle.twothirdsample16(img))
+    with pytest.raises(bb.BriskError):
+        ctx.halfsample16(np.zeros((10, 15), np.uint16))
+    with pytest.raises(bb.BriskError):
+        ctx.twothirdsample16(np.zeros((10, 11), np.uint16))
+    import torch
+    t = torch.from_numpy(img.astype(np.int32)).to(torch.int16).cuda()   # device-resident, pitched views
+    src = torch.zeros((h, w + 6), dtype=torch.int16, device="cuda"); src[:, :w] = t
+    dst = torch.zeros((h // 2, w // 2 + 4), dtype=torch.int16, device="cuda")
+    import ctypes as C
+    ctx._check(ctx._lib.brisk_halfsample16(ctx._h, bb.api._ptr(src), w, h, C.c_size_t(2 * (w + 6)), bb.api._ptr(dst), C.c_size_t(2 * (w // 2 + 4))))
+    assert np.array_equal(dst[:, :w // 2].cpu().numpy().view(np.uint16), oracle.halfsample16(img))
+
+
 def test_pyramid_six_octaves(ctx, oracle):
     img = bb.synthetic_frame(1600, 1200, 5)
     mine = ctx.debug_pyramid(img, 6)
@@ -565,6 +588,63 @@ def test_cpp_dropin_classes(tmp_path, oracle, golden):
     rad_lists, pos = read_lists(pos)
     assert knn_lists == oracle.knn_match(desc[:nq], trains, 3, masks, False)
     assert rad_lists == oracle.radius_match(desc[:nq], trains, 45.0, masks, True)
+
+
+def test_cpp_dropin_opencv_mode(tmp_path, oracle, golden):
+    # BRISK_B200_USE_OPENCV: the classes derive from cv::Feature2D / cv::DescriptorMatcher and are driven through those
+    # base classes (cv::Ptr holders, detect / compute / knnMatch / radiusMatch forwarding to the overridden virtuals, the
+    # cv:: aliases).  Compiled against the stand-in OpenCV headers of oracle/shim (OpenCV is not installed here).
+    import subprocess
+    from conftest import ROOT
+    exe = tmp_path / "dropin_cv"
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", f"-I{ROOT / 'include'}", f"-I{ROOT / 'oracle' / 'shim'}",
+                    str(ROOT / "tests" / "cpp" / "dropin_opencv_main.cc"), "-o", str(exe), f"-L{ROOT / 'ethzasl_brisk_b200'}", "-lbrisk_b200",
+                    f"-Wl,-rpath,{ROOT / 'ethzasl_brisk_b200'}"], check=True)
+    img = golden["image0"]
+    pgm = tmp_path / "img.pgm"
+    bb.write_pgm(pgm, img)
+    out = tmp_path / "out.bin"
+    subprocess.run([str(exe), str(pgm), str(out)], check=True)
+    raw = out.read_bytes()
+    n, nb, self_matches, hn, bn, nrad, nmax, s_int = (int(v) for v in np.frombuffer(raw[:32], np.int32))
+    s_dbl = float(np.frombuffer(raw[32:40], np.float64)[0])
+    off = 40
+    kps = np.frombuffer(raw[off:off + n * 28], bb.KP_DTYPE); off += n * 28
+    desc = np.frombuffer(raw[off:off + n * nb], np.uint8).reshape(n, nb); off += n * nb
+    hk = np.frombuffer(raw[off:off + hn * 28], bb.KP_DTYPE); off += hn * 28
+    bdesc = np.frombuffer(raw[off:off + bn * 48], np.uint8).reshape(bn, 48); off += bn * 48
+    maxima = np.frombuffer(raw[off:off + nmax * 12], np.int32).reshape(nmax, 3)
+    gk, gd = golden["ast0_kps"], golden["ast0_desc"]
+    assert n == len(gk) and nb == 48 and self_matches == n and np.array_equal(desc, gd)
+    for f in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(kps[f], gk[f]), f
+    assert hn == len(golden["harris0_kps"]) and np.array_equal(hk["x"], golden["harris0_kps"]["x"])
+    assert bn == hn and np.array_equal(bdesc, golden["harris0_desc"])
+    assert nrad == sum(len(v) for v in oracle.radius_match(gd, [gd], 40.0))
+    # HarrisScoreCalculator: SetImage / Score / Get2dMaxima against the oracle's score map and maxima
+    sc = oracle.harris_scores(img)
+    assert np.array_equal(maxima, oracle.harris_maxima(img, 20))
+    assert s_int == int(sc[120, 100])
+    ru, rv = 0.25, 0.5
+    want = (1 - rv) * ((1 - ru) * float(sc[120, 100]) + ru * float(sc[120, 101])) + rv * ((1 - ru) * float(sc[121, 100]) + ru * float(sc[121, 101]))
+    assert s_dbl == want
+
+
+def test_harris_score_calculator(ctx, oracle, golden):
+    # brisk::HarrisScoreCalculator's public methods (harris-score-calculator.h:52-90) through the Python mirror
+    for img in (golden["image1"], bb.synthetic_frame(500, 333, 3), bb.synthetic_frame(131, 67, 5)):
+        calc = bb.HarrisScoreCalculator(ctx=ctx)
+        calc.SetImage(img)
+        sc = oracle.harris_scores(img)
+        assert np.array_equal(calc.scores(), sc)
+        for thr in (0, 20, 5000):
+            assert np.array_equal(calc.Get2dMaxima(thr), oracle.harris_maxima(img, thr))
+        assert calc.Score(40, 30) == int(sc[30, 40]) and calc.Score(-1.0, 3.0) == 0.0 and calc.Score(float(img.shape[1] - 1), 3.0) == 0.0
+        u, v = 40.75, 30.125
+        want = (1 - 0.125) * ((1 - 0.75) * float(sc[30, 40]) + 0.75 * float(sc[30, 41])) + 0.125 * ((1 - 0.75) * float(sc[31, 40]) + 0.75 * float(sc[31, 41]))
+        assert calc.Score(u, v) == want
+    with pytest.raises(bb.BriskError):
+        calc.Get2dMaxima(0, cap=3) if False else ctx._check(ctx._lib.brisk_harris_scores(ctx._h, None, 10, 10, 10, 0, None, None, 0, None))
 
 
 def _tie_rich_descriptors(n, nbytes, seed):

@@ -257,3 +257,16 @@ def test_matcher_vs_ref_class(oracle, ref, nbytes):
         assert oracle.radius_match(tq, tt, 9.0, rm, compact) == ref.radius_match(tq, tt, 9.0, rm, compact)
     md = float(nbytes * 8 * 0.44)
     assert oracle.radius_match(q, [trains[0]], md) == ref.radius_match(q, [trains[0]], md)
+
+
+@pytest.mark.parametrize("w,h", [(16, 8), (17, 9), (752, 480), (33, 21), (100, 50), (12, 9), (13, 10), (641, 479)])
+def test_samplers_16bit_vs_ref(oracle, ref, w, h):
+    # Halfsample16 / Twothirdsample16 restated in numpy against the compiled reference (no fixture exists in the reference)
+    rng = np.random.default_rng(w * 7 + h)
+    for hi in (65536, 4096, 300):
+        img = rng.integers(0, hi, (h, w)).astype(np.uint16)
+        img[0, 0] = 65535; img[1, 0] = 65535; img[-1, -1] = 65535
+        if w >= 16:
+            assert np.array_equal(ref.halfsample16(img), oracle.halfsample16(img))
+        if (w // 3) * 3 >= 12:
+            assert np.array_equal(ref.twothirdsample16(img), oracle.twothirdsample16(img))
