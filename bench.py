@@ -223,7 +223,7 @@ def run_reference(args):
                 "config": {"workload": "C5: brute-force Hamming kNN k=2, 512-bit descriptors", "queries": nq, "train": nt},
                 "cpu_baseline": {"value": value, "unit": "Gcmp/s", "cores": cores, "kind": "reference", "sample": sample},
                 "e2e": {"value": value, "unit": "Gcmp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
     cfg = FRAME_CONFIGS[args.config]
     frames = unique_frames(cfg)
@@ -246,7 +246,7 @@ def run_reference(args):
                        "keypoints_per_frame": kp / (args.steps * len(frames))},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -262,9 +262,8 @@ class Rig:
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
-        # stdout carries the one JSON line: NCCL's own output (version banner, INFO lines with the communicator's
-        # nranks) goes to stderr.  At N > 1 INFO is on unless the caller chose a level.
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL's own output (version banner, INFO lines with the communicator's nranks) ends up on stderr: main() pointed
+        # file descriptor 1 there.  At N > 1 INFO is on unless the caller chose a level.
         if self.world > 1:
             os.environ.setdefault("NCCL_DEBUG", os.environ.get("BENCH_NCCL_DEBUG", "INFO"))
         torch.cuda.set_device(self.local)
@@ -472,7 +471,7 @@ def run_frames(args):
         line.update({"parity_checked_frames": parity["parity_checked_frames"], "parity_ok": parity["parity_ok"], "parity": parity})
     if secondary:
         line["secondary"] = secondary
-    print(json.dumps(line))
+    emit(line)
     rig.finish()
     return 0
 
@@ -488,15 +487,15 @@ def knn_measure(args, rig, ctx, bb, nq, nt_total, steps, full_report=False):
     t = torch.from_numpy(bb.random_descriptors(end - begin, 64, 6 + rank)).to(dev)
     m = bb.BruteForceMatcher(ctx=ctx)
     variants, res = {}, None
-    for name, variant in (("popc", 0), ("tensor_core", 1)):
-        if variant == 0 and full_report and not args.knn_popc:
+    for name, variant in (("popc", 0), ("mma_sync_imma", 1), ("tcgen05", 2)):
+        if variant != 2 and full_report and not args.knn_popc:
             continue
         ctx.set_knn_variant(variant)
         fn = (lambda: sharded_knn(m, q, t, 2, begin)) if world > 1 else (lambda: m.knn(q, t, 2))
         res = fn()
         v_ms, _, _ = rig.timed(fn, steps)
         variants[name] = {"Gcmp/s": nq * nt_total * steps / (v_ms * 1e-3) / 1e9, "ms": v_ms / steps}
-    best = variants["tensor_core"]   # the default path
+    best = variants["tcgen05"]   # the default path: tcgen05.mma kind::i8, TMEM accumulators, TMA operands (hamming_tc5.cu)
     # end to end: queries and the train shard start in pinned host memory, the result is read back
     hq, ht = q.cpu().pin_memory(), t.cpu().pin_memory()
 
@@ -565,12 +564,31 @@ def run_knn(args):
         for k in ("parity_ok", "parity_checked_queries"):
             if k in rep:
                 line[k] = rep[k]
-        print(json.dumps(line))
+        emit(line)
     rig.finish()
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # stdout carries exactly one JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+    # version banner there whatever NCCL_DEBUG_FILE says): point fd 1 at stderr for the whole run and keep the original
+    # stdout for emit().
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -582,7 +600,7 @@ def main():
     ap.add_argument("--workspace-gb", type=int, default=32)
     ap.add_argument("--knn-q", type=int, default=None)
     ap.add_argument("--knn-t", type=int, default=None, help="train rows (C3's secondary metric: per rank; C5: in total)")
-    ap.add_argument("--knn-popc", action="store_true", help="C5: also time the POPC kernel")
+    ap.add_argument("--knn-popc", action="store_true", help="C5: also time the POPC and mma.sync kernels")
     ap.add_argument("--no-knn", action="store_true", help="C3: skip the secondary matcher metric")
     ap.add_argument("--parity-frames", type=int, default=8)
     args = ap.parse_args()

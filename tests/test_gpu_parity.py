@@ -618,8 +618,9 @@ def test_cpp_dropin_opencv_mode(tmp_path, oracle, golden):
     assert n == len(gk) and nb == 48 and self_matches == n and np.array_equal(desc, gd)
     for f in ("x", "y", "size", "response", "octave", "class_id"):
         assert np.array_equal(kps[f], gk[f]), f
-    assert hn == len(golden["harris0_kps"]) and np.array_equal(hk["x"], golden["harris0_kps"]["x"])
-    assert bn == hn and np.array_equal(bdesc, golden["harris0_desc"])
+    # (the fixture's Harris key points are the ones that survive the extractor's border cull: BriskFeature's output)
+    assert bn == len(golden["harris0_kps"]) and np.array_equal(bdesc, golden["harris0_desc"])
+    assert hn >= bn and kp_equal(hk, oracle.harris_detect(img, 0, 30.0, 20.0))
     assert nrad == sum(len(v) for v in oracle.radius_match(gd, [gd], 40.0))
     # HarrisScoreCalculator: SetImage / Score / Get2dMaxima against the oracle's score map and maxima
     sc = oracle.harris_scores(img)
