@@ -6,12 +6,12 @@ fails loudly when libbrisk_b200.so or a GPU is missing (no CPU fallback).
 """
 from . import build
 from .api import (KP_DTYPE, STAGES, BriskDescriptorExtractor, BriskError, BriskFeature, BriskFeatureDetector, BruteForceMatcher,
-                  Context, Hamming, HarrisScaleSpaceFeatureDetector, HarrisScoreCalculator, ScaleSpaceFeatureDetector, default_context,
+                  Context, Hamming, HarrisFeatureDetector, HarrisScaleSpaceFeatureDetector, HarrisScoreCalculator, ScaleSpaceFeatureDetector, default_context,
                   detect_and_compute_batch, lib_path, load_library)
 from .setio import read_pgm, read_set, write_pgm, write_set
 from .synthetic import random_descriptors, synthetic_batch, synthetic_frame
 
 __all__ = ["KP_DTYPE", "STAGES", "BriskDescriptorExtractor", "BriskError", "BriskFeature", "BriskFeatureDetector", "BruteForceMatcher",
-           "HarrisScaleSpaceFeatureDetector", "HarrisScoreCalculator", "ScaleSpaceFeatureDetector",
+           "HarrisFeatureDetector", "HarrisScaleSpaceFeatureDetector", "HarrisScoreCalculator", "ScaleSpaceFeatureDetector",
            "Context", "Hamming", "default_context", "detect_and_compute_batch", "lib_path", "load_library",
            "random_descriptors", "synthetic_batch", "synthetic_frame", "read_pgm", "read_set", "write_pgm", "write_set"]

@@ -412,6 +412,37 @@ class BriskDescriptorExtractor:
             pass
 
 
+class HarrisFeatureDetector:
+    """brisk::HarrisFeatureDetector(radius): the legacy single-scale Harris detector (harris-feature-detector.h:51-82)."""
+
+    def __init__(self, radius, ctx=None):
+        self.ctx = ctx or default_context()
+        self._h = C.c_void_p()
+        self.ctx._check(self.ctx._lib.brisk_harris_legacy_detector_create(self.ctx._h, C.c_double(radius), C.byref(self._h)))
+
+    def set_corner_capacity(self, n):
+        self.ctx._check(self.ctx._lib.brisk_detector_set_corner_capacity(self._h, int(n)))
+
+    def detect_batch(self, images, cap=16384):
+        a, n, h, w, stride, fp = _frames(images)
+        kps = np.zeros((n, cap), KP_DTYPE)
+        counts = np.zeros(n, np.int32)
+        self.ctx._check(self.ctx._lib.brisk_detect(self.ctx._h, self._h, _ptr(a), n, w, h, C.c_size_t(stride), C.c_size_t(fp), None,
+                                                   _ptr(kps), _ptr(counts), int(cap)))
+        return kps, counts
+
+    def detect(self, image, mask=None, cap=65536):
+        kps, counts = self.detect_batch(image, cap=cap)
+        return kps[0, :counts[0]].copy()
+
+    def __del__(self):
+        try:
+            if self._h.value:
+                self.ctx._lib.brisk_detector_destroy(self._h)
+        except Exception:
+            pass
+
+
 class HarrisScoreCalculator:
     """brisk::HarrisScoreCalculator (harris-score-calculator.h:52-90): SetImage computes the integer Harris score map on the
     GPU; Score(int, int) / Score(double, double) read it the way the reference's inline accessors do; Get2dMaxima lists the

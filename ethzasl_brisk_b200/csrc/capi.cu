@@ -81,7 +81,7 @@ struct brisk_detector {
   brisk_ctx* ctx;
   int thresh, octaves, suppress;
   int corner_cap;  // 0 = auto
-  int harris = 0;  // 1: Harris scale-space detector
+  int harris = 0;  // 1: Harris scale-space detector, 2: legacy single-scale HarrisFeatureDetector
   double radius = 0, abs_thr = 0;
   long long max_kpt = -1;
 };
@@ -184,7 +184,11 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
   const bool harris = det && det->harris;
   if (ccap <= 0) ccap = std::min(std::max((int)(((long long)w * h) / (harris ? 10 : 24)), harris ? 8192 : 4096), 1 << 20);
   memset(&plan->hw, 0, sizeof(plan->hw));
-  if (harris && det->radius > 0.0) {
+  if (harris && det->harris == 2) {
+    // harris-feature-detector.cc:313-315: one half-resolution map (+ slack for the clearing stores)
+    plan->hw.occ_h[0] = h / 2 + 32; plan->hw.occ_w[0] = w / 2 + 32;
+    plan->hw.occ_frame_bytes = ((long long)plan->hw.occ_h[0] * plan->hw.occ_w[0] + 64 + 255) / 256 * 256;
+  } else if (harris && det->radius > 0.0) {
     // occupancy maps of EnforceKeyPointUniformity (uniformity-enforcement-inl.h:62-66); none for key-point bucketing
     const float scaling = (float)(15.0 / (double)(float)(det->radius == 0 ? 1.0 : det->radius));
     long long off = 0;
@@ -404,7 +408,12 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
   ctx->launches = 0;
   ctx->raw_corners = 0;
   if (n == 0) return BRISK_OK;
-  if (det && det->harris) {
+  if (det && det->harris == 2) {
+    if (ext) return fail(ctx, BRISK_ERR_INVALID, "the legacy HarrisFeatureDetector has no fused extraction; call detect, then describe");
+    if (!(det->radius > 0.0)) return fail(ctx, BRISK_ERR_INVALID, "HarrisFeatureDetector needs a positive radius");
+    // narrower images never enter the SSE loops of GetCovarEntries (harris-feature-detector.cc:100): all scores stay 0
+    if (w - 2 < 16 || h < 5) return fail(ctx, BRISK_ERR_UNSUPPORTED, "HarrisFeatureDetector needs at least 18 columns and 5 rows");
+  } else if (det && det->harris) {
     if (det->octaves < 0 || 2 * det->octaves > kMaxLayers) return fail(ctx, BRISK_ERR_UNSUPPORTED, "octaves must be in [0, 6]");
     if (!(det->radius > 0.0)) {
       // KeyPointBucketing (key-point-bucketing-inl.h:74-112): the reference reserves maxNumKpt entries up front, so the default
@@ -454,7 +463,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
   CU_OK(cudaEventRecord(ctx->entry, ctx->stream));
   for (int si = 0; si < plan.n_slots; ++si) CU_OK(cudaStreamWaitEvent(ctx->slots[si].stream, ctx->entry, 0));
 
-  bool truncated = false, corner_overflow = false, internal_error = false, low_score = false;
+  bool truncated = false, corner_overflow = false, internal_error = false, low_score = false, occupancy_oob = false;
   struct Pending { int f0 = 0, c = 0; bool active = false, corners = false; KeyPoint* d_kps = nullptr; uint8_t* d_desc = nullptr; };
   Pending pend[2];
 
@@ -467,6 +476,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     CU_OK(cudaStreamSynchronize(sl.stream));
     const int32_t flag = sl.h_counts[plan.chunk];
     if (sl.h_counts[plan.chunk + 1] == 5) low_score = true;
+    else if (flag == 6) occupancy_oob = true;
     else if (flag == 2) internal_error = true;
     else if (flag) corner_overflow = true;
     if (!counts_dev) memcpy(counts + pd.f0, sl.h_counts, (size_t)pd.c * 4);
@@ -572,8 +582,13 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       hw.sorted = sl.h_sorted.as<HPoint>(); hw.layer_kept = sl.h_layer_kept.as<int>(); hw.occ = sl.h_occ.as<uint8_t>();
       hw.surv = sl.h_surv.as<HPoint>(); hw.layer_surv = sl.h_layer_surv.as<int>();
       tm.mark(3); tm.mark(4);
-      CU_OK(launch_harris_detect(g, hw, c, det->radius, det->abs_thr, det->max_kpt, d_kps, d_counts, cap, sl.flag.as<int>(), sl.stream));
-      ctx->launches += 3 * g.n_layers + 5;
+      if (det->harris == 2) {
+        CU_OK(launch_harris_legacy_detect(g, hw, c, det->radius, d_kps, d_counts, cap, sl.flag.as<int>(), sl.stream));
+        ctx->launches += 6;
+      } else {
+        CU_OK(launch_harris_detect(g, hw, c, det->radius, det->abs_thr, det->max_kpt, d_kps, d_counts, cap, sl.flag.as<int>(), sl.stream));
+        ctx->launches += 3 * g.n_layers + 5;
+      }
     } else if (det) {
       CU_OK(launch_agast_detect(g, ws, c, det->thresh, sl.stream));
       ctx->launches += g.n_layers;
@@ -642,6 +657,10 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
   if (low_score)
     return fail(ctx, BRISK_ERR_UNSUPPORTED, "a detected corner scores <= 2 (possible for thresh < 20 only): the reference's score cache does not keep such scores "
                                             "and its result becomes order dependent; not supported");
+  if (occupancy_oob)
+    return fail(ctx, BRISK_ERR_UNSUPPORTED, "HarrisFeatureDetector: a key point's occupancy-map indices leave the map -- the reference indexes it with x as "
+                                            "the row (harris-feature-detector.cc:322-329) and accesses memory out of bounds for this image shape "
+                                            "(landscape images); no defined result to match");
   if (internal_error) return fail(ctx, BRISK_ERR_CUDA, "internal error: tie resolution did not converge");
   if (corner_overflow) return fail(ctx, BRISK_ERR_CAPACITY, "raw corner capacity exceeded; raise it with brisk_detector_set_corner_capacity");
   if (truncated) return fail(ctx, BRISK_ERR_CAPACITY, "key point capacity (cap) exceeded; counts hold the true numbers");
@@ -769,6 +788,14 @@ int brisk_harris_detector_create(brisk_ctx* ctx, int octaves, double uniformity_
   if (!ctx || !out) return BRISK_ERR_INVALID;
   brisk_detector* d = new brisk_detector{ctx, 0, octaves, 1, 0};
   d->harris = 1; d->radius = uniformity_radius; d->abs_thr = absolute_threshold; d->max_kpt = max_kpts < 0 ? -1 : (long long)max_kpts;
+  *out = d;
+  return BRISK_OK;
+}
+
+int brisk_harris_legacy_detector_create(brisk_ctx* ctx, double radius, brisk_detector** out) {
+  if (!ctx || !out) return BRISK_ERR_INVALID;
+  brisk_detector* d = new brisk_detector{ctx, 0, 0, 1, 0};
+  d->harris = 2; d->radius = radius; d->abs_thr = 64; d->max_kpt = -1;
   *out = d;
   return BRISK_OK;
 }

@@ -495,6 +495,173 @@ cudaError_t launch_harris_detect(const PyramidGeom& g, const HarrisWorkspace& hw
 }
 
 // ---------------------------------------------------------------------------
+// Legacy single-scale brisk::HarrisFeatureDetector (reference brisk/src/harris-feature-detector.cc:56-409,
+// brisk/src/vectorized-filters.cc:54-123).  Same building blocks as the scale-space detector with different constants and
+// a few quirks that are part of its results: the covariances lose 4 bits BEFORE the (unnormalised, 16-bit wrapping)
+// binomial smoothing; the response map is shifted by one pixel against the smoothed planes (CornerHarris writes (i, j)
+// from (i, j)); NonmaxSuppress reports x one column to the right of the maximum and uses the fixed threshold 64; the
+// uniformity step sorts by the FLOAT response, indexes its half-resolution occupancy map with x as the row, and tests
+// the int16 cast of the response.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kHsThreads)
+harris_legacy_scores_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restrict__ pyr, int* __restrict__ scores) {
+  __shared__ uint8_t s_img[kHsTH + 4][kHsTW + 4];
+  __shared__ short s_xx[kHsTH + 2][kHsTW + 2], s_yy[kHsTH + 2][kHsTW + 2], s_xy[kHsTH + 2][kHsTW + 2];
+  const int x0 = blockIdx.x * kHsTW, y0 = blockIdx.y * kHsTH, frame = blockIdx.z, tid = threadIdx.x;
+  const uint8_t* img = pyr + (long long)frame * frame_elems + L.off;
+  int* out = scores + (long long)frame * frame_elems + L.off;
+  for (int i = tid; i < (kHsTH + 4) * (kHsTW + 4); i += kHsThreads) {
+    const int r = i / (kHsTW + 4), c = i - r * (kHsTW + 4);
+    const int y = y0 - 2 + r, x = x0 - 2 + c;
+    s_img[r][c] = (y >= 0 && y < L.h && x >= 0 && x < L.w) ? img[(long long)y * L.pitch + x] : 0;
+  }
+  __syncthreads();
+  // GetCovarEntries (:76-196): covariance planes, zero on the image border
+  for (int i = tid; i < (kHsTH + 2) * (kHsTW + 2); i += kHsThreads) {
+    const int r = i / (kHsTW + 2), c = i - r * (kHsTW + 2);  // plane (r, c) <-> pixel (y0-1+r, x0-1+c) <-> s_img[r+1][c+1]
+    const int y = y0 - 1 + r, x = x0 - 1 + c;
+    int xx = 0, yy = 0, xy = 0;
+    if (y >= 1 && y < L.h - 1 && x >= 1 && x < L.w - 1) {
+      int p[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) p[k] = s_img[r + k / 3][c + k % 3];
+      harris_products(p, &xx, &yy, &xy);   // the same Scharr kernel x 8 and pmulhw products ...
+      xx >>= 4; yy >>= 4; xy >>= 4;        // ... then psraw 4 (:146-157)
+    }
+    s_xx[r][c] = (short)xx; s_yy[r][c] = (short)yy; s_xy[r][c] = (short)xy;
+  }
+  __syncthreads();
+  for (int i = tid; i < kHsTH * kHsTW; i += kHsThreads) {
+    const int r = i / kHsTW, c = i - r * kHsTW;
+    const int y = y0 + r, x = x0 + c;
+    if (x >= L.w || y >= L.h) continue;
+    int v = 0;
+    // CornerHarris (:198-268) covers rows [0, h-2) x columns [0, w-2) and reads the smoothed planes AT (y, x), which
+    // FilterGauss3by316S (vectorized-filters.cc:54-123) leaves zero on row 0 / column 0
+    if (y < L.h - 2 && x < L.w - 2 && y >= 1 && x >= 1) {
+      int g[3];
+#pragma unroll
+      for (int pl = 0; pl < 3; ++pl) {
+        const short (*q)[kHsTW + 2] = pl == 0 ? s_xx : (pl == 1 ? s_yy : s_xy);
+        const int sum = 4 * q[r + 1][c + 1] + 2 * (q[r][c + 1] + q[r + 2][c + 1] + q[r + 1][c] + q[r + 1][c + 2]) + q[r][c] + q[r][c + 2] +
+                        q[r + 2][c] + q[r + 2][c + 2];
+        g[pl] = (short)sum;   // paddw wraps
+      }
+      const int tq = (short)((short)((g[0] >> 1) + (g[1] >> 1)) >> 1);
+      v = g[0] * g[1] - g[2] * g[2] - tq * tq;
+    }
+    out[(long long)y * L.pitch + x] = v;
+  }
+}
+
+// NonmaxSuppress (:270-322), warp per row.  Column -1 of a row is the last element of the row before it in the
+// reference's contiguous map -- a column CornerHarris never writes, i.e. 0.
+template <bool FILL>
+__global__ void __launch_bounds__(256)
+harris_legacy_maxima_kernel(LayerGeom L, long long frame_elems, const int* __restrict__ scores, int* __restrict__ rowcnt,
+                            int total_rows, HPoint* __restrict__ pts, int cap) {
+  const int frame = blockIdx.y, lane = threadIdx.x & 31;
+  const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (y >= L.h) return;
+  int* rc = rowcnt + (long long)frame * total_rows + y;
+  if (y < 2 || y >= L.h - 2) { if (!FILL && lane == 0) *rc = 0; return; }
+  const int* row = scores + (long long)frame * frame_elems + L.off + (long long)y * L.pitch;
+  int slot = FILL ? *rc : 0;
+  HPoint* out = pts + (long long)frame * cap;
+  for (int xb = 0; xb < L.w; xb += 32) {
+    const int x = xb + lane;
+    bool m = false;
+    int c = 0;
+    if (x < L.w - 2) {
+      c = row[x];
+      if (c >= 64) {
+        const int* up = row - L.pitch;
+        const int* dn = row + L.pitch;
+        const int l0 = x ? row[x - 1] : 0, l1 = x ? dn[x - 1] : 0, l2 = x ? up[x - 1] : 0;
+        m = !(row[x + 1] > c || l0 > c || dn[x] > c || up[x] > c || dn[x + 1] > c || l1 > c || up[x + 1] > c || l2 > c);
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, m);
+    if (FILL && m) {
+      const int s = slot + __popc(bal & ((1u << lane) - 1));
+      // the key point's response is float(score): sort on the float's value (exact as an int for these magnitudes)
+      if (s < cap) out[s] = HPoint{(int)(float)c, (unsigned short)(x + 1), (unsigned short)y};
+    }
+    slot += __popc(bal);
+  }
+  if (!FILL && lane == 0) *rc = slot;
+}
+
+// EnforceUniformity (:324-393), one CTA per frame, points in std::sort order.
+__global__ void __launch_bounds__(256)
+harris_legacy_uniformity_kernel(int w, int h, double radius, const HPoint* __restrict__ sorted, const int* __restrict__ layer_kept,
+                                uint8_t* __restrict__ occ_all, long long occ_frame_bytes, int cap, KeyPoint* __restrict__ out,
+                                int* __restrict__ counts, int kp_cap, int* __restrict__ error_flag) {
+  __shared__ float s_lut[31 * 31];
+  const int frame = blockIdx.x, tid = threadIdx.x;
+  const int m = layer_kept[frame * kMaxLayers];
+  const HPoint* pts = sorted + (long long)frame * cap;
+  uint8_t* occ = occ_all + (long long)frame * occ_frame_bytes;
+  const int H = h / 2 + 32, W = w / 2 + 32;
+  for (long long i = tid; i < ((long long)H * W + 15) / 16; i += blockDim.x) reinterpret_cast<uint4*>(occ)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 31 * 31; i += blockDim.x) {
+    // SetRadius (:57-72): the mask is centred at (radius / 2, radius / 2) of the 31 x 31 table
+    const int x = i % 31, y = i / 31;
+    const double v = 1 - (double)((radius / 2.0 - x) * (radius / 2.0 - x) + (radius / 2.0 - y) * (radius / 2.0 - y)) /
+                             (double)(radius / 2.0 * radius / 2.0);
+    s_lut[i] = (float)(v > 0.0 ? v : 0.0);
+  }
+  __syncthreads();
+  KeyPoint* dst = out + (long long)frame * kp_cap;
+  int kept = 0;
+  for (int k = 0; k < m; ++k) {
+    const HPoint p = pts[k];
+    const float response = (float)p.score;
+    // (sic) x selects the ROW of the occupancy map, y the column
+    const int cy = (int)((float)(int)p.x / 2 + 16), cx = (int)((float)(int)p.y / 2 + 16);
+    if ((long long)(cy + 15) * W + cx + 16 >= (long long)H * W) {   // the reference's 16-byte accesses would leave the map
+      if (tid == 0) atomicExch(error_flag, 6);
+      break;
+    }
+    const double s0 = (double)occ[(long long)cy * W + cx];
+    const double s1 = s0 * s0;
+    const short r16 = (short)(int)response;   // static_cast<int16_t>(float): cvttss2si, low 16 bits
+    __syncthreads();                          // every thread has read the test byte before anybody stamps
+    if ((double)r16 < s1 * s1) continue;
+    const float nsc = (float)sqrt(sqrt((double)response));
+    for (int c = tid; c < 31 * 31; c += blockDim.x) {
+      const int y = c / 31, x = c - y * 31;
+      uint8_t* o = occ + (long long)(cy + y - 15) * W + cx + x - 15;
+      const int v = (int)*o + ((int)(s_lut[c] * nsc) & 0xff);   // (char)(float * float), then paddusb
+      *o = (uint8_t)(v > 255 ? 255 : v);
+    }
+    if (tid == 0 && kept < kp_cap) dst[kept] = KeyPoint{(float)(int)p.x, (float)(int)p.y, 10.0f, -1.0f, response, 0, -1};
+    ++kept;
+    __syncthreads();
+  }
+  if (tid == 0) counts[frame] = kept;
+}
+
+// hw: scores, pts, keep, sorted, layer_kept, surv (sort scratch), occ with occ_frame_bytes >= (h/2+32) * (w/2+32) + 16.
+cudaError_t launch_harris_legacy_detect(const PyramidGeom& g, const HarrisWorkspace& hw, int n_frames, double radius, KeyPoint* out,
+                                        int* counts, int kp_cap, int* error_flag, cudaStream_t stream) {
+  const LayerGeom& L = g.L[0];
+  dim3 gs((L.w + kHsTW - 1) / kHsTW, (L.h + kHsTH - 1) / kHsTH, n_frames);
+  harris_legacy_scores_kernel<<<gs, kHsThreads, 0, stream>>>(L, g.frame_elems, hw.det.pyr, hw.scores);
+  dim3 gm((L.h + 7) / 8, n_frames);
+  harris_legacy_maxima_kernel<false><<<gm, 256, 0, stream>>>(L, g.frame_elems, hw.scores, hw.det.rowcnt, hw.det.total_rows, hw.pts, hw.det.corner_cap);
+  cudaError_t e = launch_row_scan(g, hw.det, n_frames, error_flag, stream);
+  if (e != cudaSuccess) return e;
+  harris_legacy_maxima_kernel<true><<<gm, 256, 0, stream>>>(L, g.frame_elems, hw.scores, hw.det.rowcnt, hw.det.total_rows, hw.pts, hw.det.corner_cap);
+  e = cudaMemsetAsync(hw.keep, 1, (size_t)n_frames * hw.det.corner_cap, stream);
+  if (e != cudaSuccess) return e;
+  harris_sort_kernel<<<dim3(1, n_frames), kSortThreads, 0, stream>>>(1, hw.det.layer_start, hw.pts, hw.keep, hw.sorted, hw.layer_kept, hw.surv, hw.det.corner_cap);
+  harris_legacy_uniformity_kernel<<<n_frames, 256, 0, stream>>>(L.w, L.h, radius, hw.sorted, hw.layer_kept, hw.occ, hw.occ_frame_bytes, hw.det.corner_cap,
+                                                                 out, counts, kp_cap, error_flag);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // "Use passed key points" (scale-space-feature-detector.h:103-108, scale-space-layer-inl.h:198-208,370-428):
 // detect() on a non-empty vector computes no scores; the points with response > 1e6 are re-filtered by the
 // uniformity enforcement (or the bucketing) and come back unrefined.  One layer only (octaves == 0).

@@ -84,6 +84,11 @@ cudaError_t launch_harris_score_maxima(const PyramidGeom& g, const HarrisWorkspa
 cudaError_t launch_harris_detect(const PyramidGeom& g, const HarrisWorkspace& hw, int n_frames, double radius, double abs_thr,
                                  long long max_kpt, KeyPoint* out, int* counts, int kp_cap, int* overflow_flag, cudaStream_t stream);
 
+// Legacy single-scale HarrisFeatureDetector(radius): one layer; *error_flag = 6 when a point's occupancy indices leave the map
+// (the reference then accesses memory out of bounds: nothing to match), 1 when the maxima exceed corner_cap.
+cudaError_t launch_harris_legacy_detect(const PyramidGeom& g, const HarrisWorkspace& hw, int n_frames, double radius, KeyPoint* out,
+                                        int* counts, int kp_cap, int* error_flag, cudaStream_t stream);
+
 // detect() of the Harris scale-space detector on a non-empty key-point vector ("use passed key points"), one layer:
 // response > 1e6 filter, std::sort replay, uniformity enforcement / bucketing, unrefined output.  *error_flag = 4 when a
 // passed point lies outside the image (or its response does not fit an int).

@@ -310,6 +310,58 @@ class ScaleSpaceFeatureDetector BRISK_B200_FEATURE2D {
 };
 typedef ScaleSpaceFeatureDetector<HarrisScoreCalculator> HarrisScaleSpaceFeatureDetector;
 
+// brisk::HarrisFeatureDetector -- the legacy single-scale detector, reference brisk/include/brisk/harris-feature-detector.h:
+// 51-82, brisk/src/harris-feature-detector.cc:56-409.  The mask is ignored, as in the reference's detectImpl.  Images for which
+// the reference's transposed occupancy indexing leaves its map (landscape shapes) throw std::runtime_error.
+class HarrisFeatureDetector BRISK_B200_FEATURE2D {
+ public:
+  explicit HarrisFeatureDetector(double radius) { SetRadius(radius); }
+  virtual ~HarrisFeatureDetector() { if (det_) brisk_detector_destroy(det_); }
+  HarrisFeatureDetector(const HarrisFeatureDetector&) = delete;
+  HarrisFeatureDetector& operator=(const HarrisFeatureDetector&) = delete;
+  void SetRadius(double radius) { _radius = radius; if (det_) { brisk_detector_destroy(det_); det_ = nullptr; } }
+#ifdef BRISK_B200_USE_OPENCV
+  virtual void detectAndCompute(cv::InputArray image, cv::InputArray mask, std::vector<cv::KeyPoint>& keypoints,
+                                cv::OutputArray /*descriptors*/, bool /*useProvidedKeypoints*/ = false) {
+    detectImpl(image.getMat(), keypoints, mask.getMat());
+  }
+#else
+  void detect(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, const agast::Mat& mask = agast::Mat()) const {
+    detectImpl(image, keypoints, mask);
+  }
+#endif
+
+ protected:
+  virtual void detectImpl(const agast::Mat& image, std::vector<agast::KeyPoint>& keypoints, const agast::Mat& /*mask*/ = agast::Mat()) const {
+    keypoints.resize(0);
+    if (image.empty()) return;
+    detail::ContextPtr cur = detail::context_ptr();
+    brisk_ctx* ctx = cur.get();
+    if (!det_ || ctx_ != cur) {
+      if (det_) brisk_detector_destroy(det_);
+      det_ = nullptr;
+      detail::check(ctx, brisk_harris_legacy_detector_create(ctx, _radius, &det_));
+      ctx_ = cur;
+    }
+    int cap = (int)std::max<long long>(4096, (long long)image.rows * image.cols / 64);
+    for (;;) {
+      keypoints.resize(cap);
+      int32_t count = 0;
+      const int rc = brisk_detect(ctx, det_, image.data, 1, image.cols, image.rows, image.step, image.step * image.rows, nullptr,
+                                  reinterpret_cast<brisk_keypoint*>(keypoints.data()), &count, cap);
+      if (rc == BRISK_ERR_CAPACITY && count > cap) { cap = count; continue; }
+      detail::check(ctx, rc);
+      keypoints.resize(count);
+      return;
+    }
+  }
+  double _radius;
+
+ private:
+  mutable detail::ContextPtr ctx_;
+  mutable brisk_detector* det_ = nullptr;
+};
+
 // brisk::BriskDescriptorExtractor -- reference brisk/include/brisk/brisk-descriptor-extractor.h:54-202.
 class BriskDescriptorExtractor BRISK_B200_FEATURE2D {
  public:

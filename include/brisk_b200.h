@@ -83,6 +83,15 @@ int brisk_agast_detector_create(brisk_ctx* ctx, int thresh, int octaves, int sup
  * detector ignores masks, as the reference's detectImpl does (:100-101). */
 int brisk_harris_detector_create(brisk_ctx* ctx, int octaves, double uniformity_radius, double absolute_threshold,
                                  int64_t max_kpts, brisk_detector** out);
+
+/* brisk::HarrisFeatureDetector(double radius) -- the legacy single-scale detector, reference
+ * brisk/include/brisk/harris-feature-detector.h:51-82, brisk/src/harris-feature-detector.cc:56-409 (covariances, 3x3 binomial
+ * smoothing of brisk/src/vectorized-filters.cc:54-123, response, 8-neighbour maxima >= 64, score-sorted uniformity
+ * enforcement on a half-resolution occupancy map).  Used with brisk_detect() (the mask argument is ignored, as in the
+ * reference); key points come in the order of the uniformity pass: x, y integral, size 10, angle -1, response = score,
+ * octave 0.  The reference indexes its occupancy map with x as the row: images for which that leaves the map (landscape
+ * shapes) are refused with BRISK_ERR_UNSUPPORTED -- the reference accesses memory out of bounds there. */
+int brisk_harris_legacy_detector_create(brisk_ctx* ctx, double radius, brisk_detector** out);
 void brisk_detector_destroy(brisk_detector* det);
 /* Raw-corner capacity per frame (all layers); default scales with the image area. */
 int brisk_detector_set_corner_capacity(brisk_detector* det, int corners_per_frame);

@@ -1433,6 +1433,17 @@ int orc_sort_matches(int32_t* train_idx, int32_t* img_idx, float* distance, int 
   return 0;
 }
 
+// std::sort(keypoints.begin(), keypoints.end(), compareKeypointScore) of harris-feature-detector.cc:50-52,306: descending by the
+// float response, libstdc++'s introsort (the permutation of equal responses is part of the result).  perm: in/out indices.
+int orc_sort_desc_by_response(const float* response, int32_t* perm, int n) {
+  struct K { float r; int32_t i; };
+  std::vector<K> v(n);
+  for (int j = 0; j < n; ++j) v[j] = K{response[perm[j]], perm[j]};
+  std::sort(v.begin(), v.end(), [](K a, K b) { return a.r > b.r; });
+  for (int j = 0; j < n; ++j) perm[j] = v[j].i;
+  return 0;
+}
+
 // All pairwise distances (hamming-inl.h:85-134) of two descriptor sets: out[nq][nt].
 int orc_hamming_matrix(const uint8_t* q, int64_t nq, const uint8_t* t, int64_t nt, int nbytes, int32_t* out) {
   for (int64_t i = 0; i < nq; ++i)

@@ -21,6 +21,7 @@ typedef struct {
 } orc_keypoint; /* == cv::KeyPoint, 28 bytes */
 
 /* image-down-sampling.cc:142-392 / :550-787 */
+int orc_sort_desc_by_response(const float* response, int32_t* perm, int n);
 void orc_halfsample8(const uint8_t* src, int w, int h, uint8_t* dst);
 void orc_twothirdsample8(const uint8_t* src, int w, int h, uint8_t* dst);
 /* brisk-layer.cc:278-598 */

@@ -144,6 +144,16 @@ def harris_detect_passed(img, kps, radius, max_kpt=-1, cap=1 << 18):
     return out[:n].copy()
 
 
+def harris_legacy(img, radius, cap=1 << 18, with_scores=False):
+    """brisk::HarrisFeatureDetector(radius).detect(img) (the legacy single-scale detector) -> key points [, score map]"""
+    img, w, h = _img(img)
+    kps = np.zeros(cap, KP_DTYPE)
+    sc = np.zeros((h, w), np.int32) if with_scores else None
+    n = lib().ref_harris_legacy(_p(img), w, h, C.c_double(radius), _p(sc), _p(kps), cap)
+    assert n <= cap
+    return (kps[:n].copy(), sc) if with_scores else kps[:n].copy()
+
+
 def harris_scores(img):
     img, w, h = _img(img)
     out = np.zeros((h, w), np.int32)

@@ -45,6 +45,10 @@
 #include <brisk/harris-score-calculator.h>
 #include <brisk/scale-space-feature-detector.h>
 #include <brisk/brute-force-matcher.h>
+#include <brisk/harris-feature-detector.h>
+// The legacy detector's stage functions are `__inline__` members defined in its .cc: the unmodified source file is
+// compiled as part of this translation unit (instead of on its own) so that the stage dump below can call them.
+#include <../src/harris-feature-detector.cc>
 #undef private
 #undef protected
 #include <brisk/internal/harris-scores.h>
@@ -281,6 +285,25 @@ int ref_harris_detect_passed(const uint8_t* img, int w, int h, int octaves, doub
   std::vector<cv::KeyPoint> kps;
   ToVec(in, n_in, &kps);
   det.detect(m, kps);
+  return FromVec(kps, out, cap);
+}
+
+// Legacy single-scale brisk::HarrisFeatureDetector(radius) (harris-feature-detector.cc:56-409): detect() on one image.
+// scores (nullable) receives the int32 response map of its CornerHarris stage.
+int ref_harris_legacy(const uint8_t* img, int w, int h, double radius, int32_t* scores, RefKeyPoint* out, int cap) {
+  cv::Mat m = WrapCopy(img, w, h);
+  brisk::HarrisFeatureDetector det(radius);
+  if (scores) {
+    cv::Mat a1, b1, c1, a, b, c, sc;
+    brisk::HarrisFeatureDetector::GetCovarEntries(m, a1, b1, c1);
+    brisk::FilterGauss3by316S(a1, a);
+    brisk::FilterGauss3by316S(b1, b);
+    brisk::FilterGauss3by316S(c1, c);
+    brisk::HarrisFeatureDetector::CornerHarris(a, b, c, sc);
+    memcpy(scores, sc.data, (size_t)w * h * 4);
+  }
+  std::vector<cv::KeyPoint> kps;
+  det.detectImpl(m, kps, cv::Mat());
   return FromVec(kps, out, cap);
 }
 

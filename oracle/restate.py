@@ -317,3 +317,103 @@ def radius_match(q, trains, max_distance, masks=None, compact=False):
                     cur.append((qi, t, img, float(d[qi, t])))
         matches.append(_sorted_matches(cur))
     return matches
+
+
+# ---------------------------------------------------------------------------
+# Legacy single-scale brisk::HarrisFeatureDetector (harris-feature-detector.cc:56-409, vectorized-filters.cc:54-123)
+# ---------------------------------------------------------------------------
+
+def _wrap16(a):
+    return ((a.astype(np.int64) + 32768) % 65536 - 32768).astype(np.int64)
+
+
+def harris_legacy_scores(img):
+    """GetCovarEntries -> FilterGauss3by316S x3 -> CornerHarris (harris-feature-detector.cc:76-268, vectorized-filters.cc:54-123):
+    the int32 response map.  16-bit wrap-around arithmetic as the SSE code has it; rows h-2.. and columns w-2.. stay zero,
+    and so do row 0 / column 0 of the smoothed covariances.  Needs w >= 18 (narrower images never enter the SSE loops)."""
+    s = np.ascontiguousarray(img, np.uint8).astype(np.int64)
+    h, w = s.shape
+    assert w - 2 >= 16 and h >= 3
+    p = lambda dy, dx: s[1 + dy:h - 1 + dy, 1 + dx:w - 1 + dx]
+    dx = _wrap16(24 * p(-1, -1) + 80 * p(0, -1) + 24 * p(1, -1) - 24 * p(-1, 1) - 80 * p(0, 1) - 24 * p(1, 1))
+    dy = _wrap16(24 * p(-1, -1) + 80 * p(-1, 0) + 24 * p(-1, 1) - 24 * p(1, -1) - 80 * p(1, 0) - 24 * p(1, 1))
+    cov = []
+    for a, b in ((dx, dx), (dy, dy), (dy, dx)):
+        c = np.zeros((h, w), np.int64)
+        c[1:h - 1, 1:w - 1] = ((a * b) >> 16) >> 4          # pmulhw, then psraw 4
+        cov.append(c)
+    sm = []
+    for c in cov:
+        g = np.zeros((h, w), np.int64)
+        q = lambda dy, dx: c[1 + dy:h - 1 + dy, 1 + dx:w - 1 + dx]
+        g[1:h - 1, 1:w - 1] = _wrap16(4 * q(0, 0) + 2 * (q(-1, 0) + q(1, 0) + q(0, -1) + q(0, 1)) + q(-1, -1) + q(-1, 1) + q(1, -1) + q(1, 1))
+        sm.append(g)
+    a, b, c = (g[:h - 2, :w - 2] for g in sm)
+    tq = _wrap16(_wrap16((a >> 1) + (b >> 1)) >> 1)
+    out = np.zeros((h, w), np.int64)
+    out[:h - 2, :w - 2] = a * b - c * c - tq * tq
+    return ((out + 2 ** 31) % 2 ** 32 - 2 ** 31).astype(np.int32)
+
+
+def harris_legacy_lut(radius):
+    """SetRadius (harris-feature-detector.cc:57-72): 31 x 31 float mask centred at (radius / 2, radius / 2)."""
+    r = float(radius) / 2.0
+    lut = np.zeros((31, 31), np.float32)
+    for x in range(31):
+        for y in range(31):
+            lut[y, x] = np.float32(max(1 - float((r - x) * (r - x) + (r - y) * (r - y)) / float(r * r), 0.0))
+    return lut
+
+
+def harris_legacy(img, radius):
+    """brisk::HarrisFeatureDetector(radius).detect(img): NonmaxSuppress (:270-322; threshold 64, x reported one column to the
+    right of the maximum) and EnforceUniformity (:324-393; std::sort by response, half-resolution occupancy map indexed
+    with x as the ROW, the int16 cast of the response in the acceptance test).  Raises when the occupancy indices leave the
+    map (the reference then reads / writes out of bounds: landscape images)."""
+    sc = harris_legacy_scores(img).astype(np.int64)
+    h, w = sc.shape
+    flat = sc.ravel()
+    pts = []
+    for j in range(2, h - 2):
+        row = sc[j]
+        c = np.arange(0, w - 2)
+        ctr = row[c]
+        left = np.where(c > 0, row[np.maximum(c - 1, 0)], flat[j * w - 1])            # column -1 is the previous row's last element
+        ok = (ctr >= 64) & (row[c + 1] <= ctr) & (left <= ctr)
+        for dj in (1, -1):
+            r2 = sc[j + dj]
+            l2 = np.where(c > 0, r2[np.maximum(c - 1, 0)], flat[(j + dj) * w - 1])
+            ok &= (r2[c] <= ctr) & (r2[c + 1] <= ctr) & (l2 <= ctr)
+        for cc in np.flatnonzero(ok):
+            pts.append((float(cc + 1), float(j), float(np.float32(ctr[cc]))))
+    n = len(pts)
+    kps = np.zeros(n, KP_DTYPE)
+    if n == 0:
+        return kps
+    resp = np.array([p[2] for p in pts], np.float32)
+    perm = np.arange(n, dtype=np.int32)
+    lib().orc_sort_desc_by_response(_p(resp), _p(perm), n)
+    H, W = h // 2 + 32, w // 2 + 32
+    occ = np.zeros(H * W, np.int64)
+    lut = harris_legacy_lut(radius)
+    keep = []
+    for i in perm:
+        x, y, r = pts[i]
+        cy = int(np.float32(x) / np.float32(2) + np.float32(16))
+        cx = int(np.float32(y) / np.float32(2) + np.float32(16))
+        if (cy + 15) * W + cx + 16 >= H * W:
+            raise ValueError("occupancy index out of bounds (undefined in the reference)")
+        s0 = float(occ[cy * W + cx])
+        r16 = ((int(r) + 32768) % 65536) - 32768                                      # static_cast<int16_t>(float): cvttss2si, low 16 bits
+        if r16 < (s0 * s0) * (s0 * s0):
+            continue
+        nsc = np.float32(np.sqrt(np.sqrt(np.float64(r))))
+        stamp = (lut * nsc).astype(np.float32).astype(np.int64) & 0xff                  # (char)(float * float)
+        for yy in range(31):
+            base = (cy + yy - 15) * W + cx - 15
+            occ[base:base + 31] = np.minimum(occ[base:base + 31] + stamp[yy], 255)
+        keep.append(i)
+    out = np.zeros(len(keep), KP_DTYPE)
+    for o, i in enumerate(keep):
+        out[o] = (pts[i][0], pts[i][1], 10.0, -1.0, pts[i][2], 0, -1)
+    return out

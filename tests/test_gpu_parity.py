@@ -631,6 +631,30 @@ def test_cpp_dropin_opencv_mode(tmp_path, oracle, golden):
     assert s_dbl == want
 
 
+@pytest.mark.parametrize("w,h,radius", [(480, 480, 30.0), (333, 500, 30.0), (400, 401, 20.0), (18, 40, 10.0), (200, 320, 45.0), (131, 167, 7.5),
+                                        (640, 640, 12.0)])
+def test_harris_legacy_detector_bit_exact(ctx, oracle, w, h, radius):
+    # brisk::HarrisFeatureDetector (legacy, single scale): key points in the reference's output order, bit for bit; the
+    # oracle's restatement is pinned to the compiled reference in tests/test_oracle_golden.py
+    det = bb.HarrisFeatureDetector(radius, ctx=ctx)
+    det.set_corner_capacity(w * h // 4)
+    frames = [bb.synthetic_frame(w, h, 7), np.random.default_rng(w).integers(0, 256, (h, w), dtype=np.uint8),
+              (np.random.default_rng(h).integers(0, 3, (h, w)) * 90 + 20).astype(np.uint8)]   # plateaus: equal responses
+    for img in frames:
+        assert kp_equal(det.detect(img), oracle.harris_legacy(img, radius))
+    kps, counts = det.detect_batch(np.stack(frames))
+    for i, img in enumerate(frames):
+        assert kp_equal(kps[i, :counts[i]], oracle.harris_legacy(img, radius))
+
+
+def test_harris_legacy_detector_refuses_undefined_shapes(ctx):
+    # landscape images: the reference's occupancy map is indexed with x as the row and accessed out of bounds
+    with pytest.raises(bb.BriskError, match="occupancy"):
+        bb.HarrisFeatureDetector(30.0, ctx=ctx).detect(bb.synthetic_frame(752, 480, 7))
+    with pytest.raises(bb.BriskError):
+        bb.HarrisFeatureDetector(30.0, ctx=ctx).detect(bb.synthetic_frame(17, 40, 7))
+
+
 def test_harris_score_calculator(ctx, oracle, golden):
     # brisk::HarrisScoreCalculator's public methods (harris-score-calculator.h:52-90) through the Python mirror
     for img in (golden["image1"], bb.synthetic_frame(500, 333, 3), bb.synthetic_frame(131, 67, 5)):

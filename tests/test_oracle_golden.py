@@ -270,3 +270,13 @@ def test_samplers_16bit_vs_ref(oracle, ref, w, h):
             assert np.array_equal(ref.halfsample16(img), oracle.halfsample16(img))
         if (w // 3) * 3 >= 12:
             assert np.array_equal(ref.twothirdsample16(img), oracle.twothirdsample16(img))
+
+
+@pytest.mark.parametrize("w,h,radius", [(480, 480, 30.0), (333, 500, 30.0), (400, 401, 20.0), (18, 40, 10.0), (200, 320, 45.0), (131, 167, 7.5)])
+def test_harris_legacy_vs_ref(oracle, ref, w, h, radius):
+    # the legacy single-scale HarrisFeatureDetector (harris-feature-detector.cc compiled unmodified into oracle/_ref): score
+    # map of its CornerHarris stage and the detected key points (order, coordinates, responses) against the restatement
+    for img in (synthetic_frame(w, h, 7), np.random.default_rng(w).integers(0, 256, (h, w), dtype=np.uint8)):
+        k, sc = ref.harris_legacy(img, radius, with_scores=True)
+        assert np.array_equal(sc, oracle.harris_legacy_scores(img))
+        assert kp_equal(k, oracle.harris_legacy(img, radius))
