@@ -1300,18 +1300,26 @@ static int knn_keys_impl(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const
   if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
   if (tc5) {
     // descriptor bits -> signed bytes once per call (8x the rows in HBM), then the tcgen05 kernel on TMA-staged tiles
-    CU_OK(ctx->knn_qx.ensure(knn_tc5_expanded_bytes(nq, desc_bytes)));
+    const bool ts = knn_tc5_queries_in_tmem() != 0;
     CU_OK(ctx->knn_tx.ensure(knn_tc5_expanded_bytes(nt, desc_bytes)));
-    CU_OK(launch_expand_pm1(dq, nq, desc_bytes, ctx->knn_qx.as<uint8_t>(), ctx->stream));
     CU_OK(launch_expand_pm1(dt, nt, desc_bytes, ctx->knn_tx.as<uint8_t>(), ctx->stream));
     CUtensorMap mq, mt;
-    int rc = encode_rows_map(ctx, ctx->knn_qx.p, nq, desc_bytes * 8, 128, &mq);
+    int rc = encode_rows_map(ctx, ctx->knn_tx.p, nt, desc_bytes * 8, ts ? 128 : knn_tc5_tile_rows(), &mt);
     if (rc) return rc;
-    rc = encode_rows_map(ctx, ctx->knn_tx.p, nt, desc_bytes * 8, knn_tc5_tile_rows(), &mt);
-    if (rc) return rc;
-    CU_OK(launch_hamming_knn2_tc5(mq, nq, mt, nt, desc_bytes, offset, ctx->knn_keys.as<unsigned long long>(),
-                                  ctx->knn_part.as<unsigned long long>(), splits, ctx->stream));
-    ctx->launches = 2;
+    if (ts) {
+      // queries stay packed: the kernel's epilogue threads expand their own row into tensor memory
+      CU_OK(launch_hamming_knn2_tc5ts(dq, nq, mt, nt, desc_bytes, offset, ctx->knn_keys.as<unsigned long long>(),
+                                      ctx->knn_part.as<unsigned long long>(), splits, ctx->stream));
+      ctx->launches = 1;
+    } else {
+      CU_OK(ctx->knn_qx.ensure(knn_tc5_expanded_bytes(nq, desc_bytes)));
+      CU_OK(launch_expand_pm1(dq, nq, desc_bytes, ctx->knn_qx.as<uint8_t>(), ctx->stream));
+      rc = encode_rows_map(ctx, ctx->knn_qx.p, nq, desc_bytes * 8, 128, &mq);
+      if (rc) return rc;
+      CU_OK(launch_hamming_knn2_tc5(mq, nq, mt, nt, desc_bytes, offset, ctx->knn_keys.as<unsigned long long>(),
+                                    ctx->knn_part.as<unsigned long long>(), splits, ctx->stream));
+      ctx->launches = 2;
+    }
   } else if (mma)
     CU_OK(launch_hamming_knn2_mma(dq, nq, dt, nt, desc_bytes, offset, ctx->knn_keys.as<unsigned long long>(),
                                   ctx->knn_part.as<unsigned long long>(), splits, ctx->stream));

@@ -265,6 +265,190 @@ hamming_knn2_tc5_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   }
 }
 
+// ---------------------------------------------------------------------------
+// A-in-TMEM form (tcgen05.mma with the A operand read from tensor memory).  The shared-memory form above is bound by the
+// SM's shared-memory bandwidth: every MMA re-reads its 4 KB A slice.  Here the two query tiles are written into TMEM once,
+// by the epilogue threads themselves (measured alternative, see knn_tc5_queries_in_tmem; thread = query row: it expands its descriptor's bits to +-1 bytes in registers and
+// stores them with tcgen05.st; no expanded copy of the queries in HBM, no A tiles in shared memory), and shared memory
+// only streams B: 4 KB read per 64-cycle MMA plus the TMA refill, 96 B / cycle.  TMEM columns: A tile 0 at 0, A tile 1 at
+// 128 (K / 4 columns each, 4 signed bytes per column), accumulator of tile 0 at 256, of tile 1 at 384 -- ONE accumulator
+// per A tile, yet no MMA ever waits for the epilogue: per train tile the issuer runs all K steps of A tile 0, then all of
+// A tile 1 (the B tile stays in the ring for both), so each accumulator is drained while the other one is being computed.
+// The freed shared memory holds a 13-stage ring (three train tiles in flight).
+// ---------------------------------------------------------------------------
+constexpr int kTsStages = 13;
+
+__device__ __forceinline__ void umma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+      : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+        "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+
+// 4 descriptor bits -> 4 signed bytes (+1 / -1), byte i = bit i
+__device__ __forceinline__ uint32_t pm1_nibble(uint32_t nib) {
+  uint32_t mask;
+  asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(mask) : "r"((nib & 0xfu) * 0x10204080u));
+  return (mask & 0x01010101u) | ~mask;
+}
+
+template <int KC>
+__global__ void __launch_bounds__(kT5Threads, 1)
+hamming_knn2_tc5ts_kernel(const uint8_t* __restrict__ q, const __grid_constant__ CUtensorMap map_t, long long nq, long long nt,
+                          long long rows_per_split, long long train_index_offset, unsigned long long* __restrict__ part) {
+  constexpr int kN = 128, kChunkBytes = kN * kT5Chunk, kDB = KC * 16;   // descriptor bytes per row
+  constexpr uint32_t kIdesc = t5_idesc(kN);
+  constexpr uint32_t kColA = 0, kColD = 256;   // A tile a at kColA + 128 a, accumulator a at kColD + 128 a
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = smem;                                          // [stages][128 rows x 128 B]
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + kTsStages * kChunkBytes);
+  uint64_t* bar_empty = bar_full + kTsStages;
+  uint64_t* bar_a = bar_empty + kTsStages;      // both A tiles are in TMEM
+  uint64_t* bar_tfull = bar_a + 1;              // [2] accumulator of A tile a complete
+  uint64_t* bar_tempty = bar_tfull + 2;         // [2] accumulator of A tile a drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_tempty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long q0 = (long long)blockIdx.x * (kT5QTiles * kT5M);
+  const long long t_begin = (long long)blockIdx.y * rows_per_split;
+  const long long t_end = min(nt, t_begin + rows_per_split);
+  const int ntiles = t_end > t_begin ? (int)((t_end - t_begin + kN - 1) / kN) : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < kTsStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(bar_a, kT5EpiWarps);
+    for (int a = 0; a < 2; ++a) { mbar_init(&bar_tfull[a], 1); mbar_init(&bar_tempty[a], kT5EpiWarps / 2); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kT5TmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- TMA producer: chunk c of tile i goes to ring slot (i * KC + c) % stages ----
+    if (lane == 0) {
+      int it = 0;
+      for (int i = 0; i < ntiles; ++i)
+        for (int c = 0; c < KC; ++c, ++it) {
+          const int s = it % kTsStages;
+          mbar_wait(&bar_empty[s], ((it / kTsStages) & 1) ^ 1);
+          mbar_expect_tx(&bar_full[s], kChunkBytes);
+          tma_load_2d(sB + s * kChunkBytes, &map_t, c * kT5Chunk, (int)(t_begin + (long long)i * kN), &bar_full[s]);
+        }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ----
+    if (lane == 0 && ntiles > 0) {
+      mbar_wait(bar_a, 0);
+      tc_fence_after();
+      const uint32_t b_base = smem_u32(sB);
+      for (int i = 0; i < ntiles; ++i) {
+#pragma unroll 1
+        for (int a = 0; a < kT5QTiles; ++a) {
+          mbar_wait(&bar_tempty[a], (i & 1) ^ 1);
+          tc_fence_after();
+          for (int c = 0; c < KC; ++c) {
+            const int it = i * KC + c, s = it % kTsStages;
+            if (a == 0) { mbar_wait(&bar_full[s], (it / kTsStages) & 1); tc_fence_after(); }
+#pragma unroll
+            for (int k = 0; k < kT5Chunk / 32; ++k)
+              umma_i8_ts(tmem_base + kColD + (uint32_t)(a * kN), tmem_base + kColA + (uint32_t)(a * 128 + (c * 4 + k) * 8),
+                         umma_desc(b_base + s * kChunkBytes + k * 32), kIdesc, (c | k) != 0 ? 1u : 0u);
+            if (a == kT5QTiles - 1) umma_commit(&bar_empty[s]);   // both A tiles have read the chunk
+          }
+          umma_commit(&bar_tfull[a]);
+        }
+      }
+    }
+  } else {
+    // ---- epilogue warps: thread = one query row; first the row goes into TMEM, then the top-2 selection ----
+    const int quad = warp & 3, a = (warp - 2) >> 2;
+    const int row = a * kT5M + quad * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+    {
+      const bool valid = q0 + row < nq;
+      const uint4* src = reinterpret_cast<const uint4*>(q + (q0 + row) * kDB);
+#pragma unroll 1
+      for (int g = 0; g < kDB / 16; ++g) {   // 16 descriptor bytes = 128 bits -> 128 signed bytes = 32 TMEM columns
+        const uint4 bits = valid ? __ldg(src + g) : make_uint4(0, 0, 0, 0);
+        const uint32_t wds[4] = {bits.x, bits.y, bits.z, bits.w};
+        uint32_t v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = valid ? pm1_nibble(wds[j >> 3] >> (4 * (j & 7))) : 0u;
+        tmem_st32(lane_addr + kColA + (uint32_t)(a * 128 + g * 32), v);
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_a);
+    }
+    int d0 = -100000, d1 = -100000;
+    unsigned i0 = 0xffffffffu, i1 = 0xffffffffu;
+    for (int i = 0; i < ntiles; ++i) {
+      mbar_wait(&bar_tfull[a], i & 1);
+      tc_fence_after();
+      const long long tile_base = t_begin + (long long)i * kN;
+      const int valid = (int)min((long long)kN, t_end - tile_base);
+      const unsigned idx_base = (unsigned)(train_index_offset + tile_base);
+#pragma unroll 1
+      for (int cc = 0; cc < kN / 32; ++cc) {
+        int v[32];
+        tmem_ld32(lane_addr + kColD + (uint32_t)(a * kN + cc * 32), v);
+        int m = max3(v[0], v[1], v[2]);
+#pragma unroll
+        for (int j = 3; j + 1 < 32; j += 2) m = max3(m, v[j], v[j + 1]);
+        m = max(m, v[31]);
+        if (m > d1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = cc * 32 + j;
+            if (v[j] > d1 && col < valid) {
+              if (v[j] > d0) { d1 = d0; i1 = i0; d0 = v[j]; i0 = idx_base + col; }
+              else { d1 = v[j]; i1 = idx_base + col; }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[a]);
+    }
+    if (q0 + row < nq) {
+      constexpr int kBits = KC * kT5Chunk;
+      unsigned long long* out = part + ((long long)blockIdx.y * nq + q0 + row) * 2;
+      out[0] = i0 == 0xffffffffu ? kT5KeyNone : ((unsigned long long)((kBits - d0) >> 1) << 32) | i0;
+      out[1] = i1 == 0xffffffffu ? kT5KeyNone : ((unsigned long long)((kBits - d1) >> 1) << 32) | i1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kT5TmemCols) : "memory");
+  }
+}
+
 // Descriptor bits -> signed bytes (+1 / -1), 32 per input word.
 __global__ void __launch_bounds__(256)
 expand_pm1_kernel(const uint32_t* __restrict__ src, long long n_words, uint4* __restrict__ dst) {
@@ -325,6 +509,44 @@ static cudaError_t launch_tc5(const CUtensorMap& mq, const CUtensorMap& mt, long
   dim3 grid((unsigned)((nq + kT5QTiles * kT5M - 1) / (kT5QTiles * kT5M)), splits);
   hamming_knn2_tc5_kernel<KC, NT><<<grid, kT5Threads, smem, stream>>>(mq, mt, nq, nt, rows_per_split, off, dst);
   return cudaGetLastError();
+}
+
+// 0 (default): queries in shared memory (hamming_knn2_tc5_kernel); 1: queries in TMEM (hamming_knn2_tc5ts_kernel,
+// BRISK_B200_TC5_MODE=ts in the environment).  Measured on B200 (100 k x 1 M, k = 2): 2.76 / 2.77 Tcmp/s at 512 bit -- both
+// run into the chip's power limit (SM clock ~1.33 GHz under sustained tensor load, MEASURED_PEAKS.json) -- and 4.18 / 3.37
+// Tcmp/s at 384 bit, where the TMEM form's single accumulator per tile leaves the epilogue too little time.
+int knn_tc5_queries_in_tmem() {
+  static const int ts = [] { const char* e = getenv("BRISK_B200_TC5_MODE"); return e && e[0] == 't' && e[1] == 's' ? 1 : 0; }();
+  return ts;
+}
+
+template <int KC>
+static cudaError_t launch_tc5ts(const uint8_t* q, const CUtensorMap& mt, long long nq, long long nt, long long off,
+                                unsigned long long* dst, int splits, long long rows_per_split, cudaStream_t stream) {
+  const size_t smem = (size_t)kTsStages * 128 * kT5Chunk + 1024 /* alignment */ + 512 /* barriers */;
+  cudaError_t e = cudaFuncSetAttribute(hamming_knn2_tc5ts_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)((nq + kT5QTiles * kT5M - 1) / (kT5QTiles * kT5M)), splits);
+  hamming_knn2_tc5ts_kernel<KC><<<grid, kT5Threads, smem, stream>>>(q, mt, nq, nt, rows_per_split, off, dst);
+  return cudaGetLastError();
+}
+
+// Queries as raw descriptor rows (device, 16-byte aligned), train rows expanded + tensor map with a 128-row box.
+cudaError_t launch_hamming_knn2_tc5ts(const uint8_t* q, long long nq, const CUtensorMap& map_t, long long nt, int desc_bytes,
+                                      long long train_index_offset, unsigned long long* keys, unsigned long long* part,
+                                      int splits, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  if (nt <= 0) return cudaMemsetAsync(keys, 0xff, (size_t)nq * 2 * 8, stream);
+  long long rows_per_split = ((nt + splits - 1) / splits + 127) / 128 * 128;
+  if (rows_per_split <= 0) rows_per_split = 128;
+  unsigned long long* dst = splits == 1 ? keys : part;
+  cudaError_t e;
+  if (desc_bytes == 64) e = launch_tc5ts<4>(q, map_t, nq, nt, train_index_offset, dst, splits, rows_per_split, stream);
+  else if (desc_bytes == 48) e = launch_tc5ts<3>(q, map_t, nq, nt, train_index_offset, dst, splits, rows_per_split, stream);
+  else return cudaErrorInvalidValue;
+  if (e != cudaSuccess) return e;
+  if (splits > 1) e = launch_knn_merge(part, splits, nq, 2, keys, stream);
+  return e;
 }
 
 // k == 2 only; map_q / map_t: tensor maps over the EXPANDED rows (knn_tc5_encode_map in capi.cu); keys [nq][2];

@@ -155,6 +155,11 @@ int knn_tc5_tile_rows();
 cudaError_t launch_hamming_knn2_tc5(const CUtensorMap& map_q, long long nq, const CUtensorMap& map_t, long long nt, int desc_bytes,
                                     long long train_index_offset, unsigned long long* keys, unsigned long long* part,
                                     int splits, cudaStream_t stream);
+// The same with the queries in TMEM (raw descriptor rows in, expanded by the kernel): measured alternative, BRISK_B200_TC5_MODE=ts.
+int knn_tc5_queries_in_tmem();
+cudaError_t launch_hamming_knn2_tc5ts(const uint8_t* q, long long nq, const CUtensorMap& map_t, long long nt, int desc_bytes,
+                                      long long train_index_offset, unsigned long long* keys, unsigned long long* part,
+                                      int splits, cudaStream_t stream);
 // brisk::Hamming::operator() on n pairs of desc_bytes-byte rows: popcount of the XOR over desc_bytes / 16 whole 128-bit words.
 cudaError_t launch_hamming_pairs(const uint8_t* a, const uint8_t* b, long long n, int desc_bytes, int32_t* dist, cudaStream_t stream);
 cudaError_t launch_knn_unpack(const unsigned long long* keys, long long n, int32_t* idx, int32_t* dist, cudaStream_t stream);

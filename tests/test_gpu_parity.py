@@ -909,3 +909,28 @@ def test_knn_tensor_core_variants_match_popc(oracle, nbytes):
     i1, d1 = m.knn(q, t, 2)
     i2, d2 = oracle.knn(q, t, 2)
     assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+
+
+def test_knn_tcgen05_alternative_forms():
+    # the measured alternatives of the tcgen05 kernel -- queries held in tensor memory (BRISK_B200_TC5_MODE=ts) and 256-row
+    # train tiles (BRISK_B200_TC5_TILE_ROWS=256) -- are chosen by environment variables read once per process: run each in
+    # a child process and compare with the POPC kernel
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    code = (
+        "import numpy as np, ethzasl_brisk_b200 as bb\n"
+        "ctx = bb.Context(0); m = bb.BruteForceMatcher(ctx=ctx)\n"
+        "for nb in (48, 64):\n"
+        "    for nq, nt in ((700, 5000), (129, 257), (5, 1), (3000, 70001)):\n"
+        "        q = bb.random_descriptors(nq, nb, 5); t = bb.random_descriptors(nt, nb, 6)\n"
+        "        if nt > 200: t[100] = q[3]; t[200] = q[3]; t[nt - 1] = q[3]\n"
+        "        ctx.set_knn_variant(0); a = m.knn(q, t, 2)\n"
+        "        ctx.set_knn_variant(2); b = m.knn(q, t, 2)\n"
+        "        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (nb, nq, nt)\n"
+        "print('same')\n")
+    for extra in ({"BRISK_B200_TC5_MODE": "ts"}, {"BRISK_B200_TC5_TILE_ROWS": "256"}):
+        env = dict(os.environ, PYTHONPATH=str(ROOT), **extra)
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "same" in r.stdout, (extra, r.stdout[-500:], r.stderr[-1500:])
