@@ -216,11 +216,15 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
   if (!pipelining) max_chunk = std::min<long long>(max_chunk * 2, 32768);  // one slot gets the whole budget
   long long n_chunks = (n + max_chunk - 1) / max_chunk;
   if (n_chunks < 2 && n > 1 && pipelining) n_chunks = 2;
-  // host buffers: the first chunk's upload and the last chunk's download are not hidden behind any
-  // kernel, so cut the batch finer (down to about 150 MB of pixels per chunk, at most 8 chunks)
+  // host buffers: the first chunk's upload and the last chunk's download are not hidden behind any kernel, so cut
+  // the batch finer (down to about 150 MB of pixels per chunk) -- but into at most 4 chunks, and none below 256
+  // frames when the batch allows it: the per-frame kernels (tie chain, compaction, border cull: one CTA per frame,
+  // 296 resident CTAs of the chain kernel) run a 128-frame chunk no faster than a 296-frame one (measured: 8 chunks
+  // of 128 1080p frames cost 12 ms per 1024 frames more than 4 of 256)
   if (host_io && pipelining) {
     const long long by_size = std::max<long long>(1, (long long)n * w * h / (150ll << 20));
-    n_chunks = std::max(n_chunks, std::min<long long>(8, by_size));
+    const long long by_frames = std::max<long long>(2, n / 256);
+    n_chunks = std::max(n_chunks, std::min<long long>(std::min<long long>(4, by_frames), by_size));
   }
   if (n_chunks < 1) n_chunks = 1;
   const long long chunk = std::max<long long>(1, (n + n_chunks - 1) / n_chunks);  // equal-sized chunks, no tiny tail
