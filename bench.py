@@ -265,7 +265,9 @@ class Rig:
         # NCCL's own output (version banner, INFO lines with the communicator's nranks) ends up on stderr: main() pointed
         # file descriptor 1 there.  At N > 1 INFO is on unless the caller chose a level.
         if self.world > 1:
-            os.environ.setdefault("NCCL_DEBUG", os.environ.get("BENCH_NCCL_DEBUG", "INFO"))
+            # INFO (communicator setup lines incl. nranks) unless BENCH_NCCL_DEBUG says otherwise; a preset lower level
+            # (images often export NCCL_DEBUG=WARN / VERSION) would hide them
+            os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "INFO")
         torch.cuda.set_device(self.local)
         self.numa = pin_to_gpu_numa_node(self.local) if self.world > 1 else None
         self.dev = torch.device("cuda", self.local)
