@@ -39,7 +39,9 @@ def build(force=False, verbose=False):
         if not (CSRC / src).exists():
             continue
         obj = obj_dir / (src + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v", "-c", str(CSRC / src), "-o", str(obj)]
+        # BRISK_B200_NVCC_EXTRA: extra flags for tuning experiments (e.g. -DBRISK_DESC_MIN_BLOCKS=5)
+        extra = os.environ.get("BRISK_B200_NVCC_EXTRA", "").split()
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-Xptxas", "-v", "-c", str(CSRC / src), "-o", str(obj)]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, obj, p in procs:
         out, _ = p.communicate()

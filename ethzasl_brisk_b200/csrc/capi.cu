@@ -8,10 +8,12 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
+#include "describe_logic.cuh"
 #include "harris_logic.cuh"
 #include "kernels.h"
 #include "pattern.h"
@@ -823,20 +825,46 @@ int brisk_extractor_create(brisk_ctx* ctx, int rot, int scale, int version, floa
   if (!msg.empty()) { delete ext; return fail(ctx, BRISK_ERR_INVALID, msg); }
   const PatternHost& ph = ext->host;
   if (ph.n_points > 96 || ph.desc_bytes <= 0 || ph.desc_bytes > 256) { delete ext; return fail(ctx, BRISK_ERR_UNSUPPORTED, "pattern too large"); }
+  // Device layouts (the host tables keep the reference's): points as (x, y) pairs, sigma -- which does not depend on the
+  // rotation -- next to the two normalisation constants of its point, long pairs packed into eight bytes.
+  const size_t P = (size_t)ph.n_points, n_long = ph.long_pairs.size() / 4;
+  std::vector<float> xy((size_t)64 * 1024 * P * 2);
+  std::vector<int> consts((size_t)64 * P * 4, 0);
+  for (size_t sc = 0; sc < 64; ++sc)
+    for (size_t th = 0; th < 1024; ++th)
+      for (size_t i = 0; i < P; ++i) {
+        const float* src = &ph.points[((sc * 1024 + th) * P + i) * 3];
+        float* dst = &xy[((sc * 1024 + th) * P + i) * 2];
+        dst[0] = src[0]; dst[1] = src[1];
+        if (memcmp(&src[2], &ph.points[(sc * 1024 * P + i) * 3 + 2], 4) != 0) { delete ext; return fail(ctx, BRISK_ERR_CUDA, "internal error: pattern sigma depends on the rotation"); }
+      }
+  for (size_t sc = 0; sc < 64; ++sc)
+    for (size_t i = 0; i < P; ++i) {
+      int* c = &consts[(sc * P + i) * 4];
+      c[0] = ph.sample_consts[(sc * P + i) * 2]; c[1] = ph.sample_consts[(sc * P + i) * 2 + 1];
+      memcpy(&c[2], &ph.points[(sc * 1024 * P + i) * 3 + 2], 4);
+    }
+  std::vector<int> lpairs(n_long * 2);
+  for (size_t k = 0; k < n_long; ++k) {
+    const int* lp = &ph.long_pairs[4 * k];
+    if (lp[2] < -32768 || lp[2] > 32767 || lp[3] < -32768 || lp[3] > 32767) { delete ext; return fail(ctx, BRISK_ERR_UNSUPPORTED, "pattern with long pairs closer than 1/16 pixel"); }
+    lpairs[2 * k] = lp[0] | (lp[1] << 16);
+    lpairs[2 * k + 1] = (lp[2] & 0xffff) | (int)((unsigned)lp[3] << 16);
+  }
   struct Up { DevBuf* b; const void* src; size_t bytes; };
-  const Up ups[] = {{&ext->points, ph.points.data(), ph.points.size() * 4}, {&ext->size_list, ph.size_list, sizeof(ph.size_list)},
-                    {&ext->short_pairs, ph.short_pairs.data(), ph.short_pairs.size() * 2}, {&ext->long_pairs, ph.long_pairs.data(), ph.long_pairs.size() * 4},
-                    {&ext->breaks, ph.scale_breaks, sizeof(ph.scale_breaks)}, {&ext->consts, ph.sample_consts.data(), ph.sample_consts.size() * 4}};
+  const Up ups[] = {{&ext->points, xy.data(), xy.size() * 4}, {&ext->size_list, ph.size_list, sizeof(ph.size_list)},
+                    {&ext->short_pairs, ph.short_pairs.data(), ph.short_pairs.size() * 2}, {&ext->long_pairs, lpairs.data(), lpairs.size() * 4},
+                    {&ext->breaks, ph.scale_breaks, sizeof(ph.scale_breaks)}, {&ext->consts, consts.data(), consts.size() * 4}};
   for (const Up& u : ups) {
     cudaError_t e = u.b->ensure(std::max<size_t>(u.bytes, 16));
     if (e == cudaSuccess && u.bytes) e = cudaMemcpy(u.b->p, u.src, u.bytes, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { cudaGetLastError(); brisk_extractor_destroy(ext); return fail(ctx, BRISK_ERR_CUDA, cudaGetErrorString(e)); }
   }
   PatternDev& d = ext->dev;
-  d.points = ext->points.as<float>(); d.size_list = ext->size_list.as<unsigned int>();
-  d.short_pairs = ext->short_pairs.as<unsigned short>(); d.long_pairs = ext->long_pairs.as<int>();
+  d.points = ext->points.as<float2>(); d.size_list = ext->size_list.as<unsigned int>();
+  d.short_pairs = ext->short_pairs.as<unsigned short>(); d.long_pairs = ext->long_pairs.as<int2>();
   d.scale_breaks = ext->breaks.as<float>();
-  d.sample_consts = ext->consts.as<int2>();
+  d.sample_consts = ext->consts.as<int4>();
   d.n_points = ph.n_points; d.n_short = (int)ph.short_pairs.size() / 2; d.n_long = (int)ph.long_pairs.size() / 4;
   d.desc_bytes = ph.desc_bytes; d.rot_inv = rot != 0; d.scale_inv = scale != 0; d.basic_scale = ph.basic_scale;
   *out = ext;
@@ -1144,6 +1172,7 @@ int brisk_debug_integral(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_
   if (rc) return rc;
   if (!out) return fail(ctx, BRISK_ERR_INVALID, "null output");
   CU_OK(cudaSetDevice(ctx->device));
+  if (is_device_ptr(img) || is_device_ptr(out)) return fail(ctx, BRISK_ERR_INVALID, "the integral-image check takes host buffers");
   Plan plan;
   rc = make_plan(ctx, nullptr, nullptr, 1, w, h, 1, &plan);
   if (rc) return rc;
@@ -1156,8 +1185,9 @@ int brisk_debug_integral(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_
   if (rc) return rc;
   CU_OK(launch_pyramid(map, plan.g, ws.pyr, 1, write_l0, sl.stream));
   CU_OK(launch_integral(ws.pyr + plan.g.L[0].off, plan.g.frame_elems, plan.g.L[0].pitch, w, h, 1, sl.integral.as<int32_t>(), sl.stream));
-  // the device holds one 2x2 block {S(Y,X), S(Y,X+1), S(Y+1,X), S(Y+1,X+1)} per pixel: rebuild S from the last
-  // components and check that the other three say the same
+  // the device holds one encoded block per pixel (describe_logic.cuh): rebuild S from the d components and check
+  // that the other fields -- a, b, c, the block's own pixel and the pixel one row up / one column right in the tightly
+  // packed image -- say the same
   std::vector<int32_t> blk((size_t)w * h * 4);
   CU_OK(cudaMemcpyAsync(blk.data(), sl.integral.p, blk.size() * 4, cudaMemcpyDeviceToHost, sl.stream));
   CU_OK(cudaStreamSynchronize(sl.stream));
@@ -1165,10 +1195,14 @@ int brisk_debug_integral(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_
   for (size_t i = 0; i < iw * ((size_t)h + 1); ++i) out[i] = 0;
   for (int Y = 0; Y < h; ++Y)
     for (int X = 0; X < w; ++X) out[(size_t)(Y + 1) * iw + X + 1] = blk[((size_t)Y * w + X) * 4 + 3];
+  auto pixel = [&](long long i) { return (i >= 0 && i < (long long)w * h) ? (int)img[(size_t)(i / w) * stride + (size_t)(i % w)] : 0; };
   for (int Y = 0; Y < h; ++Y)
     for (int X = 0; X < w; ++X) {
-      const int32_t* b = &blk[((size_t)Y * w + X) * 4];
-      if (b[0] != out[(size_t)Y * iw + X] || b[1] != out[(size_t)Y * iw + X + 1] || b[2] != out[(size_t)(Y + 1) * iw + X])
+      const int32_t* e = &blk[((size_t)Y * w + X) * 4];
+      const BlockFields b = decode_block(Block4{e[0], e[1], e[2], e[3]});
+      const int up_right = Y ? pixel((long long)(Y - 1) * w + X + 1) : 0;
+      if (b.a != out[(size_t)Y * iw + X] || b.b != out[(size_t)Y * iw + X + 1] || b.c != out[(size_t)(Y + 1) * iw + X] ||
+          b.pix != pixel((long long)Y * w + X) || b.up_right != up_right)
         return fail(ctx, BRISK_ERR_CUDA, "internal error: inconsistent integral-image blocks");
     }
   return BRISK_OK;

@@ -24,10 +24,10 @@ namespace briskb200 {
 // the strip.  Kernel 2 (one CTA per strip, one thread per column) walks down the rows, eight at a time,
 // keeping the running column sums in registers; the eight rows of column sums go through shared memory to
 // the eight warps, each of which turns one row into its prefix sums (eight consecutive columns per lane,
-// then one warp scan) and adds what lies left of the strip.  The result is stored as one 2x2 BLOCK per pixel,
-// block(Y, X) = {S(Y,X), S(Y,X+1), S(Y+1,X), S(Y+1,X+1)} (16 bytes, Y < h, X < w): the descriptor sampler then
-// gets the twelve taps and the two top corner pixels of a box from four 16-byte loads instead of fourteen
-// scattered 4- and 1-byte loads (describe is bound by the L1 sector rate of exactly those gathers).  A thread
+// then one warp scan) and adds what lies left of the strip.  The result is stored as one 16-byte BLOCK per pixel
+// (describe_logic.cuh: the 2x2 neighbourhood S(Y..Y+1, X..X+1) plus the pixels I(Y, X) and I(Y-1, X+1), Y < h, X < w):
+// the descriptor sampler then gets the twelve taps and the four corner pixels of a box from four 16-byte loads
+// instead of sixteen scattered 4- and 1-byte loads (describe is bound by the L1 wavefront rate of exactly those gathers).  A thread
 // builds its blocks from its own column, its left neighbour's (the sum left of the strip for the first thread)
 // and the row before.  Traffic: the image twice (1 byte per pixel each) and 16 bytes per pixel out.
 constexpr int kIntStrip = 256, kIntRows = 8;
@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(kIntStrip)
 integral_strip_kernel(const uint8_t* __restrict__ imgs, long long frame_stride, int pitch, int w, int h,
                       const int32_t* __restrict__ aux, int4* __restrict__ blocks) {
   __shared__ __align__(16) int s_t[2][kIntRows][kIntStrip];
+  __shared__ int s_lf[2][kIntRows];   // left of the strip, rows <= y0 + r: S(y0 + r + 1, strip start)
   const int strip = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int ns = integral_strips(w);
   const int x = strip * kIntStrip + tid;
@@ -78,18 +79,20 @@ integral_strip_kernel(const uint8_t* __restrict__ imgs, long long frame_stride, 
   const int32_t* lp = lft;
   int4* op = blocks + (long long)frame * w * h + x;   // block(y0, x)
   int up_own = 0, up_left = 0;      // S(y0, x + 1) and S(y0, x): the row above the step (row 0 of S is zero)
+  // I(Y - 1, x + 1) of the tightly packed image (the pixel right of the last column is the first of the next row), as
+  // up_right[Y * pitch]; the neighbour thread loaded these bytes one step ago
+  const uint8_t* up_right = imgs + (long long)frame * frame_stride + (x + 1 < w ? x + 1 - pitch : 0);
 #pragma unroll
   for (int r = 0; r < kIntRows; ++r) { v[r] = (in && r < h) ? cp[r * pitch] : 0; l[r] = r < h ? lp[r * ns] : 0; }
   for (int y0 = 0, it = 0; y0 < h; y0 += kIntRows, ++it) {
     int (*t)[kIntStrip] = s_t[it & 1];
     int left_mine = left_run;  // left of the strip, rows <= y0 + warp (the row this thread's warp will finish)
-    int lf[kIntRows];          // left of the strip, rows <= y0 + r: S(y0 + r + 1, strip start)
 #pragma unroll
     for (int r = 0; r < kIntRows; ++r) {
       acc += v[r];             // column sum over rows <= y0 + r
       t[r][tid] = acc;
       left_run += l[r];
-      lf[r] = left_run;
+      if (tid == 0) s_lf[it & 1][r] = left_run;
       if (r <= warp) left_mine += l[r];
     }
     // next step's loads, in flight during the scans
@@ -106,6 +109,9 @@ integral_strip_kernel(const uint8_t* __restrict__ imgs, long long frame_stride, 
       }
     }
     __syncthreads();
+    int ur[kIntRows];
+#pragma unroll
+    for (int r = 0; r < kIntRows; ++r) ur[r] = (in && y0 + r > 0 && y0 + r < h) ? up_right[(long long)(y0 + r) * pitch] : 0;
     {
       // warp `warp` finishes row y0 + warp: eight consecutive columns per lane, serial prefix, warp scan of the totals
       int4* p = reinterpret_cast<int4*>(&t[warp][8 * lane]);
@@ -124,8 +130,11 @@ integral_strip_kernel(const uint8_t* __restrict__ imgs, long long frame_stride, 
     for (int r = 0; r < kIntRows; ++r) {
       if (y0 + r >= h) break;
       const int own = t[r][tid];
-      const int left = tid ? t[r][tid - 1] : lf[r];
-      if (in) op[(long long)r * w] = make_int4(up_left, up_own, left, own);
+      const int left = tid ? t[r][tid - 1] : s_lf[it & 1][r];
+      if (in) {
+        const Block4 e = encode_block(up_left, up_own, left, own, ur[r]);
+        op[(long long)r * w] = make_int4(e.a, e.b, e.c, e.d);
+      }
       up_own = own; up_left = left;
     }
     op += (long long)kIntRows * w;
@@ -230,6 +239,9 @@ describe_cull_kernel(PatternDev pat, int w, int h, const KeyPoint* __restrict__ 
 // --- descriptor: one warp per key point ---
 
 constexpr int kDescWarps = 8;
+#ifndef BRISK_DESC_MIN_BLOCKS
+#define BRISK_DESC_MIN_BLOCKS 5
+#endif
 constexpr int kMaxPoints = 96;
 
 // All pattern points of one key point, spread over the warp.  The sampler is latency bound (16
@@ -237,26 +249,28 @@ constexpr int kMaxPoints = 96;
 // independent gather chains overlap.
 __device__ __forceinline__ void sample_pattern(const PatternDev& pat, const uint8_t* __restrict__ img, int pitch,
                                                const BlockIntegral integ, float kx, float ky,
-                                               const float* __restrict__ pp, int scale, int P, int lane, int* val) {
+                                               const float2* __restrict__ pp, int scale, int P, int lane, int* val) {
+  const int4* cc = pat.sample_consts + scale * P;
   const int i0 = lane, i1 = lane + 32;
   if (i1 < P) {
-    const int2 c0 = pat.sample_consts[scale * P + i0], c1 = pat.sample_consts[scale * P + i1];
-    const float x0 = pp[3 * i0], y0 = pp[3 * i0 + 1], s0 = pp[3 * i0 + 2];
-    const float x1 = pp[3 * i1], y1 = pp[3 * i1 + 1], s1 = pp[3 * i1 + 2];
-    const int v0 = smoothed_intensity_t(img, pitch, integ, kx, ky, x0, y0, s0, c0.x, c0.y);
-    const int v1 = smoothed_intensity_t(img, pitch, integ, kx, ky, x1, y1, s1, c1.x, c1.y);
+    const int4 c0 = cc[i0], c1 = cc[i1];
+    const float2 p0 = pp[i0], p1 = pp[i1];
+    const int v0 = smoothed_intensity_t(img, pitch, integ, kx, ky, p0.x, p0.y, __int_as_float(c0.z), c0.x, c0.y);
+    const int v1 = smoothed_intensity_t(img, pitch, integ, kx, ky, p1.x, p1.y, __int_as_float(c1.z), c1.x, c1.y);
     val[i0] = v0; val[i1] = v1;
   } else if (i0 < P) {
-    const int2 c0 = pat.sample_consts[scale * P + i0];
-    val[i0] = smoothed_intensity_t(img, pitch, integ, kx, ky, pp[3 * i0], pp[3 * i0 + 1], pp[3 * i0 + 2], c0.x, c0.y);
+    const int4 c0 = cc[i0];
+    const float2 p0 = pp[i0];
+    val[i0] = smoothed_intensity_t(img, pitch, integ, kx, ky, p0.x, p0.y, __int_as_float(c0.z), c0.x, c0.y);
   }
   for (int i = lane + 64; i < P; i += 32) {
-    const int2 sc = pat.sample_consts[scale * P + i];
-    val[i] = smoothed_intensity_t(img, pitch, integ, kx, ky, pp[3 * i], pp[3 * i + 1], pp[3 * i + 2], sc.x, sc.y);
+    const int4 sc = cc[i];
+    const float2 pt = pp[i];
+    val[i] = smoothed_intensity_t(img, pitch, integ, kx, ky, pt.x, pt.y, __int_as_float(sc.z), sc.x, sc.y);
   }
 }
 
-__global__ void __launch_bounds__(kDescWarps * 32)
+__global__ void __launch_bounds__(kDescWarps * 32, BRISK_DESC_MIN_BLOCKS)
 describe_kernel(PatternDev pat, const uint8_t* __restrict__ imgs, long long frame_stride, int pitch, int w, int h,
                 const int32_t* __restrict__ integral, const KeyPoint* __restrict__ kps_in, const int* __restrict__ scales,
                 const int* __restrict__ counts, int kp_cap, KeyPoint* __restrict__ kps_out, uint8_t* __restrict__ desc) {
@@ -277,15 +291,15 @@ describe_kernel(PatternDev pat, const uint8_t* __restrict__ imgs, long long fram
   if (pat.rot_inv) {
     if (kp.angle == -1.0f) {
       // un-rotated samples, long-pair gradient (:697-739)
-      const float* pp = pat.points + ((long long)scale * 1024) * P * 3;
+      const float2* pp = pat.points + ((long long)scale * 1024) * P;
       sample_pattern(pat, img, pitch, integ, kp.x, kp.y, pp, scale, P, lane, val);
       __syncwarp();
       int d0 = 0, d1 = 0;
       for (int p = lane; p < pat.n_long; p += 32) {
-        const int4 lp = *reinterpret_cast<const int4*>(pat.long_pairs + 4 * p);
-        const int delta = val[lp.x] - val[lp.y];
-        d0 += delta * lp.z / 1024;
-        d1 += delta * lp.w / 1024;
+        const int2 lp = pat.long_pairs[p];
+        const int delta = val[lp.x & 0xffff] - val[lp.x >> 16];
+        d0 += delta * (int)(short)(lp.y & 0xffff) / 1024;
+        d1 += delta * (lp.y >> 16) / 1024;
       }
 #pragma unroll
       for (int o = 16; o; o >>= 1) { d0 += __shfl_xor_sync(0xffffffffu, d0, o); d1 += __shfl_xor_sync(0xffffffffu, d1, o); }
@@ -297,7 +311,7 @@ describe_kernel(PatternDev pat, const uint8_t* __restrict__ imgs, long long fram
     }
   }
   // samples in the rotated pattern (:755-772)
-  const float* pp = pat.points + ((long long)scale * 1024 + theta) * P * 3;
+  const float2* pp = pat.points + ((long long)scale * 1024 + theta) * P;
   sample_pattern(pat, img, pitch, integ, kp.x, kp.y, pp, scale, P, lane, val);
   __syncwarp();
   // short-pair comparisons -> bits (:538-564); rows are zero-padded to desc_bytes

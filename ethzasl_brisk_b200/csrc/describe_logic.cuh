@@ -23,18 +23,20 @@ BRISK_HD void sampling_constants(float sigma_half, int* scaling, int* scaling2) 
   *scaling2 = (int)((double)((float)*scaling * area) / 1024.0);
 }
 
-// The twelve integral-image taps of the large-box case (:459-484) and the two weighted corner pixels of the
-// box's top row, by name (t1..t12 as in the reference).
+// The twelve integral-image taps of the large-box case (:459-484) and the four weighted corner pixels the reference's
+// pointer walk reads (:447-456), by name (t1..t12 as in the reference).
 struct BoxTaps {
   int t1, t2, t3, t4, t5, t6, t7, t8, t9, t10, t11, t12;
   int p_tl, p_tr;  // I(y_top, x_left), I(y_top, x_left + dx + 1)
+  int p_bl, p_br;  // I(y_top + dy, x_left + 1), I(y_top + dy, x_left + dx + 2): one row up and one column right of the
+                   // geometric bottom corners -- what the reference reads
 };
 
 // Plain (h+1) x (w+1) int32 integral image, row stride iw = w + 1: one load per tap.
 struct PlainIntegral {
   const int32_t* s;
   int iw;
-  BRISK_HD void taps(const uint8_t* p /* &img(y_top, x_left) */, int y_top, int x_left, int dx, int dy, BoxTaps* o) const {
+  BRISK_HD void taps(const uint8_t* p /* &img(y_top, x_left) */, int pitch, int y_top, int x_left, int dx, int dy, BoxTaps* o) const {
     const int32_t* q = s + (long long)y_top * iw + x_left + 1;
     o->t1 = q[0]; o->t2 = q[dx];
     const int32_t* q1 = q + iw;
@@ -44,35 +46,56 @@ struct PlainIntegral {
     const int32_t* q3 = q2 + iw;
     o->t7 = q3[dx]; o->t8 = q3[0];
     o->p_tl = p[0]; o->p_tr = p[dx + 1];
+    const uint8_t* pc = p + (dx + 1) + (long long)dy * pitch + 1;
+    o->p_br = pc[0]; o->p_bl = pc[-(dx + 1)];
   }
 };
 
-// The same integral image stored as one 2x2 block per pixel: block(Y, X) = {S(Y,X), S(Y,X+1), S(Y+1,X), S(Y+1,X+1)}
-// for Y < h, X < w (16 bytes, row stride w blocks).  The twelve taps are three corners each of the four blocks at
-// rows {y_top, y_top+dy+1} x columns {x_left, x_left+dx+1}, and a block also holds the pixel it sits on
-// (I = d - b - c + a): four 16-byte loads replace twelve 4-byte loads and two byte loads.
-struct Block4 { int a, b, c, d; };
+// The same integral image stored as one 16-byte BLOCK per pixel (Y < h, X < w, row stride w blocks) that holds the 2x2
+// neighbourhood a = S(Y,X), b = S(Y,X+1), c = S(Y+1,X), d = S(Y+1,X+1) and two pixels:
+//   word 0 = a,  word 1 = (b - a) | I(Y-1, X+1) << 24,  word 2 = (c - a) | I(Y, X) << 24,  word 3 = d.
+// b - a is a column sum and c - a a row sum (< 2^24 for images up to 65 793 pixels a side).  The twelve taps are three
+// corners each of the four blocks at rows {y_top, y_top+dy+1} x columns {x_left, x_left+dx+1}; the top blocks carry the
+// box's top corner pixels (their own), the bottom blocks the two pixels the reference reads for the bottom corners
+// (one row up, one column right): four 16-byte loads replace twelve 4-byte and four 1-byte loads.  I(Y-1, X+1) is taken
+// from the tightly packed image the reference samples (stride == width), so for X + 1 == w it is I(Y, 0).
+struct Block4 { int a, b, c, d; };   // as stored (encoded)
+struct BlockFields { int a, b, c, d, pix, up_right; };
+BRISK_HD Block4 encode_block(int a, int b, int c, int d, int up_right) {
+  const unsigned pix = (unsigned)(d - b - c + a);
+  return Block4{a, (int)(((unsigned)(b - a) & 0xffffffu) | ((unsigned)up_right << 24)), (int)(((unsigned)(c - a) & 0xffffffu) | (pix << 24)), d};
+}
+BRISK_HD BlockFields decode_block(const Block4& e) {
+  BlockFields f;
+  f.a = e.a;
+  f.b = (int)((unsigned)e.a + ((unsigned)e.b & 0xffffffu));
+  f.c = (int)((unsigned)e.a + ((unsigned)e.c & 0xffffffu));
+  f.d = e.d;
+  f.pix = (int)((unsigned)e.c >> 24);
+  f.up_right = (int)((unsigned)e.b >> 24);
+  return f;
+}
 struct BlockIntegral {
   const Block4* s;
   int bw;  // blocks per row (= image width)
-  BRISK_HD static Block4 load(const Block4* p) {
+  BRISK_HD static BlockFields load(const Block4* p) {
 #ifdef __CUDA_ARCH__
     const int4 v = __ldg(reinterpret_cast<const int4*>(p));
-    return Block4{v.x, v.y, v.z, v.w};
+    return decode_block(Block4{v.x, v.y, v.z, v.w});
 #else
-    return *p;
+    return decode_block(*p);
 #endif
   }
-  BRISK_HD void taps(const uint8_t*, int y_top, int x_left, int dx, int dy, BoxTaps* o) const {
+  BRISK_HD void taps(const uint8_t*, int, int y_top, int x_left, int dx, int dy, BoxTaps* o) const {
     const Block4* r0 = s + (long long)y_top * bw + x_left;
     const Block4* r1 = r0 + (long long)(dy + 1) * bw;
-    const Block4 tl = load(r0), tr = load(r0 + dx + 1), bl = load(r1), br = load(r1 + dx + 1);
+    const BlockFields tl = load(r0), tr = load(r0 + dx + 1), bl = load(r1), br = load(r1 + dx + 1);
     o->t1 = tl.b; o->t11 = tl.c; o->t12 = tl.d;
     o->t2 = tr.a; o->t3 = tr.c; o->t4 = tr.d;
     o->t10 = bl.a; o->t9 = bl.b; o->t8 = bl.d;
     o->t6 = br.a; o->t5 = br.b; o->t7 = br.c;
-    o->p_tl = tl.d - tl.b - tl.c + tl.a;
-    o->p_tr = tr.d - tr.b - tr.c + tr.a;
+    o->p_tl = tl.pix; o->p_tr = tr.pix;
+    o->p_bl = bl.up_right; o->p_br = br.up_right;
   }
 };
 
@@ -104,13 +127,12 @@ BRISK_HD int smoothed_intensity_t(const uint8_t* __restrict__ img, int pitch, co
   const uint8_t* p = img + (long long)y_top * pitch + x_left;
   if (dx + dy > 2) {
     BoxTaps t;
-    integral.taps(p, y_top, x_left, dx, dy, &t);
+    integral.taps(p, pitch, y_top, x_left, dx, dy, &t);
     // four weighted corner pixels; the reference's pointer walk (:447-456)
     // reads the bottom pair one row up and one column right of the geometric
     // corners -- reproduced.
     int v = A * t.p_tl + B * t.p_tr;
-    const uint8_t* pc = p + (dx + 1) + (long long)dy * pitch + 1;
-    v += C * (int)pc[0] + D * (int)pc[-(dx + 1)];
+    v += C * t.p_br + D * t.p_bl;
     // twelve integral-image taps (:459-484)
     const int upper = (t.t3 - t.t2 + t.t1 - t.t12) * r_y_1_i;
     const int middle = (t.t6 - t.t3 + t.t12 - t.t9) * scaling;

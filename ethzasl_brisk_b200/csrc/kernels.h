@@ -100,12 +100,12 @@ cudaError_t launch_dense_scores(const LayerGeom& L, const uint8_t* img, uint8_t*
 
 // Descriptor extraction.
 struct PatternDev {
-  const float* points;  // [64][1024][P][3] x, y, sigma
+  const float2* points;  // [64][1024][P] x, y
   const unsigned int* size_list;  // [64]
   const unsigned short* short_pairs;  // [n_short][2] (i, j)
-  const int* long_pairs;  // [n_long][4] (i, j, wdx, wdy)
+  const int2* long_pairs;  // [n_long] (i | j << 16, wdx & 0xffff | wdy << 16)
   const float* scale_breaks;  // [64] smallest keypoint size mapping to scale index s (s >= 1)
-  const int2* sample_consts;  // [64][P] (scaling, scaling2) of every pattern point
+  const int4* sample_consts;  // [64][P] (scaling, scaling2, bits of sigma / 2, 0) of every pattern point
   int n_points, n_short, n_long, desc_bytes;
   int rot_inv, scale_inv, basic_scale;
 };

@@ -25,14 +25,14 @@ extern "C" int emul_describe(const uint8_t* img, int w, int h, KeyPoint* kps, in
   // tight image with slack: a few reads land one column past the row end / on the row after the last (as in the reference)
   std::vector<uint8_t> tight((size_t)w * h + 64, 0);
   memcpy(tight.data(), img, (size_t)w * h);
-  // S = (h+1) x (w+1) integral image, then one block {S(Y,X), S(Y,X+1), S(Y+1,X), S(Y+1,X+1)} per pixel
+  // S = (h+1) x (w+1) integral image, then one block per pixel: S(Y..Y+1, X..X+1) and the pixel I(Y-1, X+1) of the tight image
   std::vector<int32_t> S((size_t)(w + 1) * (h + 1), 0);
   for (int y = 0; y < h; ++y) { int s = 0; for (int x = 0; x < w; ++x) { s += img[(size_t)y * w + x]; S[(size_t)(y + 1) * (w + 1) + x + 1] = S[(size_t)y * (w + 1) + x + 1] + s; } }
   std::vector<Block4> blocks((size_t)w * h);
   for (int y = 0; y < h; ++y)
     for (int x = 0; x < w; ++x) {
       const int32_t* q = &S[(size_t)y * (w + 1) + x];
-      blocks[(size_t)y * w + x] = Block4{q[0], q[1], q[w + 1], q[w + 2]};
+      blocks[(size_t)y * w + x] = encode_block(q[0], q[1], q[w + 1], q[w + 2], y ? tight[(size_t)(y - 1) * w + x + 1] : 0);
     }
   const BlockIntegral integ{blocks.data(), w};
   // describe_cull_kernel
