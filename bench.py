@@ -339,8 +339,16 @@ def run_frames(args):
              torch.empty((n, cap, 48), dtype=torch.uint8, device=dev))
     h_out = (torch.empty((n, cap, 7), dtype=torch.float32).pin_memory(), torch.empty(n, dtype=torch.int32).pin_memory(),
              torch.empty((n, cap, 48), dtype=torch.uint8).pin_memory())
+    h_out2 = tuple(torch.empty_like(t).pin_memory() for t in h_out)
     resident = lambda: bb.detect_and_compute_batch(det, ext, d_frames, cap=cap, out=d_out)
     e2e = lambda: bb.detect_and_compute_batch(det, ext, h_frames, cap=cap, out=h_out)
+
+    def e2e_streamed(steps):
+        # the streaming form of the same call (brisk_detect_describe_async + brisk_sync): the caller alternates two sets
+        # of host output buffers, so the first upload / last download of a step run under the neighbouring steps' kernels
+        for s_ in range(steps):
+            bb.detect_and_compute_batch(det, ext, h_frames, cap=cap, out=(h_out, h_out2)[s_ % 2], async_=True)
+        ctx.sync()
 
     # nvidia-smi takes a few hundred ms to deliver its first line: it was started before the warm-up; only the
     # lines of the two timed regions (resident and host end-to-end) count
@@ -369,12 +377,15 @@ def run_frames(args):
         e2e()
     if rank == 0:
         rig.sampler.mark()
-    ms_e2e, _, _ = rig.timed(e2e, args.steps, ctx)
+    ms_e2e_blocking, _, _ = rig.timed(e2e, args.steps, ctx)
+    e2e_streamed(2)
+    ms_e2e, _, _ = rig.timed(lambda: e2e_streamed(args.steps), 1)
     clocks = rig.sampler.stop() if rank == 0 else None
     if getattr(pin_to_gpu_numa_node, "full", None):
         os.sched_setaffinity(0, pin_to_gpu_numa_node.full)  # the CPU legs below use every host core
     hc = h_out[1].numpy()
-    assert np.array_equal(hc, counts), "host and device paths disagree"
+    assert np.array_equal(hc, counts) and np.array_equal(h_out2[1].numpy(), counts), "host and device paths disagree"
+    assert torch.equal(h_out[2][-1, :int(counts[-1])], h_out2[2][-1, :int(counts[-1])]), "the two host buffer sets disagree"
     assert counts.max() <= cap, "key-point capacity exceeded"
     kp_total = int(counts.sum())
 
@@ -473,7 +484,9 @@ def run_frames(args):
                        "global_frames_per_step": world * n, "keypoints_per_frame": kps_per_frame, "raw_corners_per_frame": corners_per_frame,
                        "parallelism": f"frame-sharded x{world}, no collective", "cpus_per_rank": rig.numa,
                        "l2": f"inputs ({n * H * W / 1e6:.0f} MB per step) exceed the 126 MB L2; no explicit flush", "kp_capacity": cap},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                    "call": "brisk_detect_describe_async x steps + brisk_sync, pinned host buffers (outputs double-buffered by the caller)",
+                    "blocking_call_value": world * n * args.steps / (ms_e2e_blocking * 1e-3), "blocking_call_ms_per_step": ms_e2e_blocking / args.steps},
             "gpu_launches": launches, "roofline": roof, "stages": stage_report, "cpu_baseline": cpu, "clocks": clocks}
     if parity:
         line.update({"parity_checked_frames": parity["parity_checked_frames"], "parity_ok": parity["parity_ok"], "parity": parity})

@@ -486,11 +486,13 @@ class HarrisScoreCalculator:
             return out[:n.value].copy()
 
 
-def detect_and_compute_batch(detector, extractor, images, masks=None, cap=16384, out=None, allow_truncation=False):
+def detect_and_compute_batch(detector, extractor, images, masks=None, cap=16384, out=None, allow_truncation=False, async_=False):
     """detect() + compute() without leaving the device.
 
     -> (kps [n,cap], counts [n], desc [n,cap,descriptorSize]).  `out` may hold
     preallocated (kps, counts, desc) numpy arrays or torch CUDA tensors.
+    async_=True (brisk_detect_describe_async): the batch's last chunk stays in flight; `images` and `out` must stay
+    alive and untouched until the call after next of the same shape has returned or ctx.sync() was called.
     """
     ctx = detector.ctx
     assert extractor.ctx is ctx
@@ -502,8 +504,9 @@ def detect_and_compute_batch(detector, extractor, images, masks=None, cap=16384,
         desc = np.zeros((n, cap, extractor.descriptorSize()), np.uint8)
     else:
         kps, counts, desc = out
-    rc = ctx._lib.brisk_detect_describe(ctx._h, detector._h, extractor._h, _ptr(a), n, w, h, C.c_size_t(stride), C.c_size_t(fp),
-                                        _ptr(m), _ptr(kps), _ptr(counts), int(cap), _ptr(desc))
+    fn = ctx._lib.brisk_detect_describe_async if async_ else ctx._lib.brisk_detect_describe
+    rc = fn(ctx._h, detector._h, extractor._h, _ptr(a), n, w, h, C.c_size_t(stride), C.c_size_t(fp),
+            _ptr(m), _ptr(kps), _ptr(counts), int(cap), _ptr(desc))
     ctx._check(rc, allow_capacity=allow_truncation)
     return kps, counts, desc
 

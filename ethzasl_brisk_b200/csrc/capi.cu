@@ -76,6 +76,33 @@ struct brisk_ctx {
   cudaEvent_t entry = nullptr;
   PFN_cuTensorMapEncodeTiled_v12000 encode = nullptr;
   Slot slots[2];
+  // brisk_detect_describe_async: the last chunk of the previous asynchronous call, still computing / not yet copied
+  // back, and the status of the asynchronous calls since the last brisk_sync
+  struct CallStatus { bool truncated = false, corner_overflow = false, internal_error = false, low_score = false, occupancy_oob = false; };
+  struct Pending {
+    int f0 = 0, c = 0;
+    bool active = false, corners = false;
+    KeyPoint* d_kps = nullptr; uint8_t* d_desc = nullptr;
+    // where the results go and how the slot's pinned count block is laid out
+    brisk_keypoint* kps = nullptr; int32_t* counts = nullptr; uint8_t* desc = nullptr;
+    int cap = 0, desc_bytes = 0, chunk = 0, corner_cap = 0;
+    bool kps_dev = false, counts_dev = false, desc_dev = false;
+    CallStatus* st = nullptr;
+  };
+  struct AsyncKey {
+    const void *det = nullptr, *ext = nullptr, *masks = nullptr;
+    int n = 0, w = 0, h = 0, cap = 0; size_t stride = 0, frame_pitch = 0;
+    bool imgs_dev = false, kps_dev = false, counts_dev = false, desc_dev = false;
+    bool operator==(const AsyncKey& o) const {
+      return det == o.det && ext == o.ext && (masks != nullptr) == (o.masks != nullptr) && n == o.n && w == o.w && h == o.h && cap == o.cap &&
+             stride == o.stride && frame_pitch == o.frame_pitch && imgs_dev == o.imgs_dev && kps_dev == o.kps_dev &&
+             counts_dev == o.counts_dev && desc_dev == o.desc_dev;
+    }
+  };
+  Pending deferred;
+  int deferred_slot = 0;
+  AsyncKey deferred_key;
+  CallStatus async_status;
   DevBuf knn_q, knn_t, knn_qx, knn_tx, knn_keys, knn_part, knn_idx, knn_dist, knn_mask, rad_counts, rad_offsets, rad_matches;
 };
 
@@ -171,8 +198,13 @@ struct Plan {
 // host_io: the frames come from host memory; any_host: some buffer of the call lives in host memory.  With
 // everything resident on the device there is nothing to overlap and one slot with large chunks is faster
 // (measured: 92 vs 105 ms per 1024 1080p frames), so the two-slot pipeline is only used when copies exist.
+int drain_async(brisk_ctx* ctx);
+
 int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* ext, int n, int w, int h, int cap, Plan* plan,
-              bool host_io = false, bool any_host = true) {
+              bool host_io = false, bool any_host = true, bool two_slots = false) {
+  // the slots' buffers are about to be (re)used: whatever an asynchronous call left in flight is completed first
+  // (run_batch takes a chained call's pending chunk out of the context before it plans)
+  if (ctx->deferred.active) { const int rc = drain_async(ctx); if (rc) return rc; }
   const bool pipelining = ctx->pipelining && any_host;
   const int octaves = det ? det->octaves : 0;
   build_geom(w, h, octaves, &plan->g);
@@ -231,7 +263,7 @@ int make_plan(brisk_ctx* ctx, const brisk_detector* det, const brisk_extractor* 
   if (n_chunks < 1) n_chunks = 1;
   const long long chunk = std::max<long long>(1, (n + n_chunks - 1) / n_chunks);  // equal-sized chunks, no tiny tail
   plan->chunk = (int)chunk;
-  plan->n_slots = (n > plan->chunk && pipelining) ? 2 : 1;
+  plan->n_slots = ((n > plan->chunk || two_slots) && pipelining) ? 2 : 1;  // (asynchronous calls alternate the slots from call to call)
   const size_t c = (size_t)plan->chunk;
   for (int si = 0; si < plan->n_slots; ++si) {
     Slot& sl = ctx->slots[si];
@@ -403,13 +435,98 @@ struct KpLists {
 };
 
 // Core batch driver: detect and/or describe, chunk by chunk.
+// Second half of a chunk: wait for its kernels, then copy exactly the produced rows back (queued on the slot's stream).
+int finish_chunk(brisk_ctx* ctx, int si, brisk_ctx::Pending& pd) {
+  if (!pd.active) return BRISK_OK;
+  Slot& sl = ctx->slots[si];
+  pd.active = false;
+  CU_OK(cudaStreamSynchronize(sl.stream));
+  brisk_ctx::CallStatus& st = *pd.st;
+  const int32_t flag = sl.h_counts[pd.chunk];
+  if (sl.h_counts[pd.chunk + 1] == 5) st.low_score = true;
+  else if (flag == 6) st.occupancy_oob = true;
+  else if (flag == 2) st.internal_error = true;
+  else if (flag) st.corner_overflow = true;
+  if (!pd.counts_dev) memcpy(pd.counts + pd.f0, sl.h_counts, (size_t)pd.c * 4);
+  if (pd.corners)
+    for (int f = 0; f < pd.c; ++f) ctx->raw_corners += std::min(sl.h_counts[pd.chunk + 4 + f], pd.corner_cap);
+  Timer tm(ctx, &sl);
+  tm.mark(7);
+  // The produced rows of the whole chunk go back in ONE strided copy per array (rows = frames, width = the longest
+  // list of the chunk): a few per cent more bytes than frame-by-frame copies of the exact lengths, but 2 DMA
+  // descriptors per chunk instead of 2 per frame (2 x 1024 driver calls per step on the benched workload, per rank).
+  const int cap = pd.cap;
+  int longest = 0;
+  for (int f = 0; f < pd.c; ++f) {
+    if (sl.h_counts[f] > cap) st.truncated = true;
+    longest = std::max(longest, std::min(sl.h_counts[f], cap));
+  }
+  if (longest > 0) {
+    if (!pd.kps_dev)
+      CU_OK(cudaMemcpy2DAsync(pd.kps + (size_t)pd.f0 * cap, (size_t)cap * 28, pd.d_kps, (size_t)cap * 28, (size_t)longest * 28, (size_t)pd.c,
+                              cudaMemcpyDeviceToHost, sl.stream));
+    if (pd.desc && !pd.desc_dev)
+      CU_OK(cudaMemcpy2DAsync(pd.desc + (size_t)pd.f0 * cap * pd.desc_bytes, (size_t)cap * pd.desc_bytes, pd.d_desc, (size_t)cap * pd.desc_bytes,
+                              (size_t)longest * pd.desc_bytes, (size_t)pd.c, cudaMemcpyDeviceToHost, sl.stream));
+  }
+  tm.mark(8);
+  return BRISK_OK;
+}
+
+int report_status(brisk_ctx* ctx, const brisk_ctx::CallStatus& st) {
+  if (st.low_score)
+    return fail(ctx, BRISK_ERR_UNSUPPORTED, "a detected corner scores <= 2 (possible for thresh < 20 only): the reference's score cache does not keep such scores "
+                                            "and its result becomes order dependent; not supported");
+  if (st.occupancy_oob)
+    return fail(ctx, BRISK_ERR_UNSUPPORTED, "HarrisFeatureDetector: a key point's occupancy-map indices leave the map -- the reference indexes it with x as "
+                                            "the row (harris-feature-detector.cc:322-329) and accesses memory out of bounds for this image shape "
+                                            "(landscape images); no defined result to match");
+  if (st.internal_error) return fail(ctx, BRISK_ERR_CUDA, "internal error: tie resolution did not converge");
+  if (st.corner_overflow) return fail(ctx, BRISK_ERR_CAPACITY, "raw corner capacity exceeded; raise it with brisk_detector_set_corner_capacity");
+  if (st.truncated) return fail(ctx, BRISK_ERR_CAPACITY, "key point capacity (cap) exceeded; counts hold the true numbers");
+  return BRISK_OK;
+}
+
+// Completes what brisk_detect_describe_async left in flight and reports the status of the asynchronous calls since the
+// last time.  Every other entry point that uses the slots calls it first.
+int drain_async(brisk_ctx* ctx) {
+  if (ctx->deferred.active) {
+    CU_OK(cudaSetDevice(ctx->device));
+    const int si = ctx->deferred_slot;
+    const int rc = finish_chunk(ctx, si, ctx->deferred);
+    if (rc) return rc;
+    CU_OK(cudaStreamSynchronize(ctx->slots[si].stream));
+  }
+  const brisk_ctx::CallStatus st = ctx->async_status;
+  ctx->async_status = brisk_ctx::CallStatus();
+  return report_status(ctx, st);
+}
+
 int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const uint8_t* imgs, int n, int w, int h,
               size_t stride, size_t frame_pitch, const uint8_t* masks, brisk_keypoint* kps, int32_t* counts, int cap,
-              uint8_t* desc) {
+              uint8_t* desc, bool async = false) {
   int rc = check_image_args(ctx, imgs, n, w, h, stride, frame_pitch);
   if (rc) return rc;
   if (!kps || !counts || cap <= 0 || (ext && !desc)) return fail(ctx, BRISK_ERR_INVALID, "bad output arguments");
   CU_OK(cudaSetDevice(ctx->device));
+  // An asynchronous call chains onto the previous one when it has the same shape (same plan, same buffers): its first
+  // chunk is queued BEFORE the previous call's last chunk is collected, so that upload runs under the previous call's
+  // kernels and the previous download under this call's.  Anything else completes the pending work first.
+  const bool any_host = !is_device_ptr(imgs) || !is_device_ptr(kps) || !is_device_ptr(counts) || (desc && !is_device_ptr(desc)) ||
+                        (masks && !is_device_ptr(masks));
+  if (ctx->timing || !ctx->pipelining || !any_host || n == 0) async = false;
+  brisk_ctx::AsyncKey key;
+  key.det = det; key.ext = ext; key.masks = masks; key.n = n; key.w = w; key.h = h; key.cap = cap; key.stride = stride; key.frame_pitch = frame_pitch;
+  key.imgs_dev = is_device_ptr(imgs); key.kps_dev = is_device_ptr(kps); key.counts_dev = is_device_ptr(counts); key.desc_dev = desc && is_device_ptr(desc);
+  const bool chained = async && ctx->deferred.active && key == ctx->deferred_key;
+  if (!chained) { rc = drain_async(ctx); if (rc) return rc; }
+  // the previous call's last chunk travels with this call from here on; put back if the call fails before touching it
+  brisk_ctx::Pending carried;
+  struct Restore {
+    brisk_ctx* c; brisk_ctx::Pending* p;
+    ~Restore() { if (p->active) c->deferred = *p; }
+  } restore{ctx, &carried};
+  if (chained) { carried = ctx->deferred; ctx->deferred.active = false; }
   memset(ctx->ms, 0, sizeof(ctx->ms));
   ctx->launches = 0;
   ctx->raw_corners = 0;
@@ -449,9 +566,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       if (probe.L[i].w < 8 || probe.L[i].h < 8) return fail(ctx, BRISK_ERR_INVALID, "image too small: every pyramid layer must be at least 8x8");
   }
   Plan plan;
-  const bool any_host = !is_device_ptr(imgs) || !is_device_ptr(kps) || !is_device_ptr(counts) || (desc && !is_device_ptr(desc)) ||
-                        (masks && !is_device_ptr(masks));
-  rc = make_plan(ctx, det, ext, n, w, h, cap, &plan, !is_device_ptr(imgs), any_host);
+  rc = make_plan(ctx, det, ext, n, w, h, cap, &plan, !is_device_ptr(imgs), any_host, async);
   if (rc) return rc;
   const PyramidGeom& g = plan.g;
   const int desc_bytes = ext ? ext->dev.desc_bytes : 0;
@@ -469,46 +584,11 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
   CU_OK(cudaEventRecord(ctx->entry, ctx->stream));
   for (int si = 0; si < plan.n_slots; ++si) CU_OK(cudaStreamWaitEvent(ctx->slots[si].stream, ctx->entry, 0));
 
-  bool truncated = false, corner_overflow = false, internal_error = false, low_score = false, occupancy_oob = false;
-  struct Pending { int f0 = 0, c = 0; bool active = false, corners = false; KeyPoint* d_kps = nullptr; uint8_t* d_desc = nullptr; };
-  Pending pend[2];
-
-  // second half of a chunk: wait for its kernels, then copy exactly the produced rows back
-  auto finish = [&](int si) -> int {
-    Pending& pd = pend[si];
-    if (!pd.active) return BRISK_OK;
-    Slot& sl = ctx->slots[si];
-    pd.active = false;
-    CU_OK(cudaStreamSynchronize(sl.stream));
-    const int32_t flag = sl.h_counts[plan.chunk];
-    if (sl.h_counts[plan.chunk + 1] == 5) low_score = true;
-    else if (flag == 6) occupancy_oob = true;
-    else if (flag == 2) internal_error = true;
-    else if (flag) corner_overflow = true;
-    if (!counts_dev) memcpy(counts + pd.f0, sl.h_counts, (size_t)pd.c * 4);
-    if (pd.corners)
-      for (int f = 0; f < pd.c; ++f) ctx->raw_corners += std::min(sl.h_counts[plan.chunk + 4 + f], plan.ws.corner_cap);
-    Timer tm(ctx, &sl);
-    tm.mark(7);
-    // The produced rows of the whole chunk go back in ONE strided copy per array (rows = frames, width = the longest
-    // list of the chunk): a few per cent more bytes than frame-by-frame copies of the exact lengths, but 2 DMA
-    // descriptors per chunk instead of 2 per frame (2 x 1024 driver calls per step on the benched workload, per rank).
-    int longest = 0;
-    for (int f = 0; f < pd.c; ++f) {
-      if (sl.h_counts[f] > cap) truncated = true;
-      longest = std::max(longest, std::min(sl.h_counts[f], cap));
-    }
-    if (longest > 0) {
-      if (!kps_dev)
-        CU_OK(cudaMemcpy2DAsync(kps + (size_t)pd.f0 * cap, (size_t)cap * 28, pd.d_kps, (size_t)cap * 28, (size_t)longest * 28, (size_t)pd.c,
-                                cudaMemcpyDeviceToHost, sl.stream));
-      if (ext && !desc_dev)
-        CU_OK(cudaMemcpy2DAsync(desc + (size_t)pd.f0 * cap * desc_bytes, (size_t)cap * desc_bytes, pd.d_desc, (size_t)cap * desc_bytes,
-                                (size_t)longest * desc_bytes, (size_t)pd.c, cudaMemcpyDeviceToHost, sl.stream));
-    }
-    tm.mark(8);
-    return BRISK_OK;
-  };
+  brisk_ctx::CallStatus local_status;
+  brisk_ctx::CallStatus* status = async ? &ctx->async_status : &local_status;
+  brisk_ctx::Pending pend[2];
+  if (chained) { pend[ctx->deferred_slot] = carried; carried.active = false; }
+  auto finish = [&](int si) -> int { return finish_chunk(ctx, si, pend[si]); };
   auto collect_timing = [&](int si) {
     if (!ctx->timing) return;
     static const int stage_of[8] = {BRISK_STAGE_H2D, BRISK_STAGE_PYRAMID, BRISK_STAGE_DETECT, BRISK_STAGE_LISTS, BRISK_STAGE_NMS,
@@ -521,15 +601,20 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     }
   };
 
-  int chunk_index = 0;
-  // With host frames the upload of the first chunk is not hidden behind any kernel: start with a quarter chunk.
-  const int first_chunk = (plan.n_slots == 2 && !is_device_ptr(imgs) && n >= 4 * plan.chunk) ? std::max(1, plan.chunk / 4) : plan.chunk;
+  // a chained call starts on the slot the previous call's last chunk does not occupy
+  const int first_index = chained ? (ctx->deferred_slot ^ 1) : 0;
+  int chunk_index = first_index;
+  // With host frames the upload of the first chunk is not hidden behind any kernel (unless the call is chained): start
+  // with a quarter chunk.
+  const int first_chunk = (!chained && plan.n_slots == 2 && !is_device_ptr(imgs) && n >= 4 * plan.chunk) ? std::max(1, plan.chunk / 4) : plan.chunk;
+  int last_slot = 0;
   for (int f0 = 0, step = first_chunk; f0 < n; f0 += step, step = plan.chunk, ++chunk_index) {
     const int si = chunk_index % plan.n_slots;
     Slot& sl = ctx->slots[si];
     // the slot's previous chunk must be fully drained (results copied) before its buffers are reused
     if (pend[si].active) { rc = finish(si); if (rc) return rc; }
-    if (chunk_index >= plan.n_slots) collect_timing(si);
+    if (chunk_index >= first_index + plan.n_slots) collect_timing(si);
+    last_slot = si;
     const int c = std::min(step, n - f0);
     const DetectWorkspace ws = slot_ws(plan, sl);
     KeyPoint* d_kps = kps_dev ? reinterpret_cast<KeyPoint*>(kps) + (size_t)f0 * cap : sl.kps.as<KeyPoint>();
@@ -563,7 +648,7 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     // The two slots overlap COPIES with kernels, not kernels with kernels: kernels of two chunks running side
     // by side slow each other down by more than the overlap gains (measured), so a chunk's kernels start once
     // the other slot's kernels are done, while its upload ran ahead of them and the other's download follows.
-    if (plan.n_slots == 2 && chunk_index > 0) CU_OK(cudaStreamWaitEvent(sl.stream, ctx->slots[si ^ 1].computed, 0));
+    if (plan.n_slots == 2 && (chunk_index > first_index || chained)) CU_OK(cudaStreamWaitEvent(sl.stream, ctx->slots[si ^ 1].computed, 0));
     if (det || write_l0) {
       CU_OK(launch_pyramid(map, g, ws.pyr, c, write_l0, sl.stream));
       ctx->launches += 1;
@@ -651,26 +736,30 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       CU_OK(cudaMemcpy2DAsync(sl.h_counts + plan.chunk + 4, 4, ws.layer_start + g.n_layers, (size_t)(kMaxLayers + 1) * 4, 4, (size_t)c,
                               cudaMemcpyDeviceToHost, sl.stream));
     tm.mark(8);
-    pend[si].f0 = f0; pend[si].c = c; pend[si].active = true; pend[si].corners = want_corners; pend[si].d_kps = d_kps; pend[si].d_desc = d_desc;
+    {
+      brisk_ctx::Pending& pd = pend[si];
+      pd.f0 = f0; pd.c = c; pd.active = true; pd.corners = want_corners; pd.d_kps = d_kps; pd.d_desc = d_desc;
+      pd.kps = kps; pd.counts = counts; pd.desc = ext ? desc : nullptr; pd.cap = cap; pd.desc_bytes = desc_bytes; pd.chunk = plan.chunk;
+      pd.corner_cap = plan.ws.corner_cap; pd.kps_dev = kps_dev; pd.counts_dev = counts_dev; pd.desc_dev = desc_dev; pd.st = status;
+    }
     // drain the OTHER slot while this chunk computes
     if (plan.n_slots == 2 && pend[si ^ 1].active) { rc = finish(si ^ 1); if (rc) return rc; }
+  }
+  if (async) {
+    // everything but the last chunk is collected; that one stays in flight until the next chained call or brisk_sync
+    for (int si = 0; si < plan.n_slots; ++si)
+      if (si != last_slot) { rc = finish(si); if (rc) return rc; }
+    ctx->deferred = pend[last_slot];
+    ctx->deferred_slot = last_slot;
+    ctx->deferred_key = key;
+    return BRISK_OK;
   }
   for (int si = 0; si < plan.n_slots; ++si) { rc = finish(si); if (rc) return rc; }
   for (int si = 0; si < plan.n_slots; ++si) {
     CU_OK(cudaStreamSynchronize(ctx->slots[si].stream));
     collect_timing(si);
   }
-  if (low_score)
-    return fail(ctx, BRISK_ERR_UNSUPPORTED, "a detected corner scores <= 2 (possible for thresh < 20 only): the reference's score cache does not keep such scores "
-                                            "and its result becomes order dependent; not supported");
-  if (occupancy_oob)
-    return fail(ctx, BRISK_ERR_UNSUPPORTED, "HarrisFeatureDetector: a key point's occupancy-map indices leave the map -- the reference indexes it with x as "
-                                            "the row (harris-feature-detector.cc:322-329) and accesses memory out of bounds for this image shape "
-                                            "(landscape images); no defined result to match");
-  if (internal_error) return fail(ctx, BRISK_ERR_CUDA, "internal error: tie resolution did not converge");
-  if (corner_overflow) return fail(ctx, BRISK_ERR_CAPACITY, "raw corner capacity exceeded; raise it with brisk_detector_set_corner_capacity");
-  if (truncated) return fail(ctx, BRISK_ERR_CAPACITY, "key point capacity (cap) exceeded; counts hold the true numbers");
-  return BRISK_OK;
+  return report_status(ctx, local_status);
 }
 
 }  // namespace
@@ -742,8 +831,9 @@ const char* brisk_last_error(const brisk_ctx* ctx) { return ctx ? ctx->err.c_str
 
 int brisk_sync(brisk_ctx* ctx) {
   if (!ctx) return BRISK_ERR_INVALID;
+  const int rc = drain_async(ctx);
   CU_OK(cudaStreamSynchronize(ctx->stream));
-  return BRISK_OK;
+  return rc;
 }
 
 int brisk_ctx_set_workspace_limit(brisk_ctx* ctx, size_t bytes) {
@@ -910,6 +1000,13 @@ int brisk_detect_describe(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* 
                           int32_t* counts, int cap, uint8_t* desc) {
   if (!ctx || !det || !ext || det->ctx != ctx || ext->ctx != ctx) return fail(ctx, BRISK_ERR_INVALID, "detector / extractor do not belong to this context");
   return run_batch(ctx, det, ext, imgs, n, w, h, stride, frame_pitch, masks, kps, counts, cap, desc);
+}
+
+int brisk_detect_describe_async(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const uint8_t* imgs, int n, int w,
+                                int h, size_t stride, size_t frame_pitch, const uint8_t* masks, brisk_keypoint* kps,
+                                int32_t* counts, int cap, uint8_t* desc) {
+  if (!ctx || !det || !ext || det->ctx != ctx || ext->ctx != ctx) return fail(ctx, BRISK_ERR_INVALID, "detector / extractor do not belong to this context");
+  return run_batch(ctx, det, ext, imgs, n, w, h, stride, frame_pitch, masks, kps, counts, cap, desc, true);
 }
 
 int brisk_compute_scale(brisk_ctx* ctx, brisk_detector* det, const uint8_t* imgs, int n, int w, int h, size_t stride,

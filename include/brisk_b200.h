@@ -51,6 +51,8 @@ typedef enum {
 int brisk_ctx_create(int device, void* stream, brisk_ctx** out);
 void brisk_ctx_destroy(brisk_ctx* ctx);
 const char* brisk_last_error(const brisk_ctx* ctx);
+/* Waits for the context's work, collects what brisk_detect_describe_async left in flight and returns the status of
+ * the asynchronous calls since the last brisk_sync. */
 int brisk_sync(brisk_ctx* ctx);
 /* Upper bound on device workspace bytes used per call (frames are processed in
  * chunks that fit); default 8 GiB. */
@@ -150,6 +152,19 @@ int brisk_describe(brisk_ctx* ctx, brisk_extractor* ext, const uint8_t* imgs, in
 int brisk_detect_describe(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const uint8_t* imgs, int n, int w,
                           int h, size_t stride, size_t frame_pitch, const uint8_t* masks, brisk_keypoint* kps,
                           int32_t* counts, int cap, uint8_t* desc);
+
+/* The same call for a caller that streams batches (the reference's callers run detect + compute once per camera frame,
+ * brisk_ros_demo/src/livedemo.cc:458-504): returns once the batch is queued and all but its LAST chunk are back in the
+ * host buffers; that chunk is collected by the next brisk_detect_describe_async call of the same shape -- after it has
+ * queued its own first chunk, so that the upload of batch k+1 runs under the kernels of batch k and the download of
+ * batch k under the kernels of batch k+1 -- or by brisk_sync(), or by any other call on the context.  The outputs of
+ * batch k (and the inputs, which are read until then) must therefore stay untouched until the call after next returns
+ * or brisk_sync() does: alternate between two sets of host buffers.  Errors that only show on the device (capacity,
+ * unsupported data) are reported by brisk_sync() / the call that collects the chunk.  Device buffers, timing mode and
+ * contexts with pipelining switched off fall back to the blocking call. */
+int brisk_detect_describe_async(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const uint8_t* imgs, int n, int w,
+                                int h, size_t stride, size_t frame_pitch, const uint8_t* masks, brisk_keypoint* kps,
+                                int32_t* counts, int cap, uint8_t* desc);
 
 /* brisk::HarrisScoreCalculator::SetImage (InitializeScores = HarrisScoresSSE) and Get2dMaxima -- reference
  * brisk/include/brisk/harris-score-calculator.h:52-90, brisk/src/harris-score-calculator.cc:53-106, brisk/src/harris-scores.cc:

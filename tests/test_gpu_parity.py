@@ -366,6 +366,44 @@ def test_chunked_batch_equals_single_pass(ctx):
         assert np.array_equal(a[0][f, :n], b[0][f, :n]) and np.array_equal(a[2][f, :n], b[2][f, :n])
 
 
+def test_async_calls_chain_and_match_blocking_calls(ctx):
+    # brisk_detect_describe_async: batches streamed through two sets of host buffers; every batch must equal the blocking
+    # call's result, whether a call covers one chunk (slots alternate from call to call) or several
+    det = bb.BriskFeatureDetector(60, 4, ctx=ctx)
+    ext = bb.BriskDescriptorExtractor(ctx=ctx)
+    for n_frames, limit in ((3, None), (7, 64 << 20)):
+        batches = [bb.synthetic_batch(n_frames, 640, 480, 300 + 10 * b) for b in range(5)]
+        want = [bb.detect_and_compute_batch(det, ext, f, cap=4096) for f in batches]
+        actx = bb.Context(0, workspace_limit=limit) if limit else bb.Context(0)
+        adet, aext = bb.BriskFeatureDetector(60, 4, ctx=actx), bb.BriskDescriptorExtractor(ctx=actx)
+        bufs = [(np.zeros((n_frames, 4096), bb.KP_DTYPE), np.zeros(n_frames, np.int32), np.zeros((n_frames, 4096, 48), np.uint8)) for _ in range(2)]
+        got = []
+        for b, frames in enumerate(batches):
+            bb.detect_and_compute_batch(adet, aext, frames, cap=4096, out=bufs[b % 2], async_=True)
+            if b >= 1:   # batch b - 1 is complete once the call for batch b has returned
+                got.append(tuple(x.copy() for x in bufs[(b - 1) % 2]))
+        actx.sync()
+        got.append(tuple(x.copy() for x in bufs[(len(batches) - 1) % 2]))
+        for w, g in zip(want, got):
+            assert np.array_equal(w[1], g[1]) and w[1].min() > 0
+            for f in range(n_frames):
+                n = w[1][f]
+                assert np.array_equal(w[0][f, :n], g[0][f, :n]) and np.array_equal(w[2][f, :n], g[2][f, :n])
+        # a blocking call in between collects the pending chunk first; a shape change does too
+        bb.detect_and_compute_batch(adet, aext, batches[0], cap=4096, out=bufs[0], async_=True)
+        mid = bb.detect_and_compute_batch(adet, aext, batches[1][:2], cap=4096)
+        assert np.array_equal(bufs[0][1], want[0][1]) and np.array_equal(mid[1], want[1][1][:2])
+        n0 = want[0][1][n_frames - 1]
+        assert np.array_equal(bufs[0][2][n_frames - 1, :n0], want[0][2][n_frames - 1, :n0])
+        # device-side errors of an asynchronous call surface at sync
+        small = (np.zeros((n_frames, 16), bb.KP_DTYPE), np.zeros(n_frames, np.int32), np.zeros((n_frames, 16, 48), np.uint8))   # kept alive until the sync
+        bb.detect_and_compute_batch(adet, aext, batches[0], cap=16, out=small, async_=True)
+        with pytest.raises(bb.BriskError) as e:
+            actx.sync()
+        assert e.value.code == -4
+        actx.sync()   # reported once
+
+
 def test_device_resident_inputs_and_outputs(ctx):
     import torch
     frames = bb.synthetic_batch(3, 752, 480, 1000)
