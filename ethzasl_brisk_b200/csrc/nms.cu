@@ -217,17 +217,19 @@ __device__ __forceinline__ int warp_tie_decide(const LayerView& L, int x, int y,
   return verdict;
 }
 
-// mark_above1 spread over the lanes of a warp: the scan visits a (columns x rows) grid of positions
-// in row-major order -- columns x_1, the integers in (x_1, x1], x1; rows alike -- and `steps` of them
-// were evaluated; lane n replays position n.  (The footprint is uniform across the warp.)
-__device__ __forceinline__ void warp_mark_above(const LayerView& nb, int layer, int x, int y, int above_steps, int above_argmax) {
-  const int lane = threadIdx.x & 31;
+// mark_above1 as a strided loop: the scan visits a (columns x rows) grid of positions in row-major order --
+// columns x_1, the integers in (x_1, x1], x1; rows alike -- and `steps` of them were evaluated; position n is
+// replayed by whoever owns n = first, first + stride, ...  (first = lane, stride = 32: one corner spread over a warp,
+// the footprint being uniform across it; first = 0, stride = 1: one thread on its own corner.)
+__device__ __forceinline__ void mark_above_strided(const LayerView& nb, int layer, int x, int y, int above_steps, int above_argmax,
+                                                   int first, int stride) {
   float x_1, x1, y_1, y1;
   above_patch(layer, x, y, &x_1, &x1, &y_1, &y1);
   const int xb = (int)(x_1 + 1), xe = (int)x1, yb = (int)(y_1 + 1), ye = (int)y1;
   const int ncols = imax(xe - xb + 1, 0) + 2, nrows = imax(ye - yb + 1, 0) + 2;
   const int steps = above_steps & 0xff;
-  for (int n = lane; n < steps; n += 32) {
+#pragma unroll 1
+  for (int n = first; n < steps; n += stride) {
     const int c = n % ncols, rr = n / ncols;
     const bool xi = c > 0 && c < ncols - 1, yi = rr > 0 && rr < nrows - 1;
     const float xf = c == 0 ? x_1 : (xi ? (float)(xb + c - 1) : x1);
@@ -235,7 +237,13 @@ __device__ __forceinline__ void warp_mark_above(const LayerView& nb, int layer, 
     if (xi && yi) mark_px(nb, xb + c - 1, yb + rr - 1);
     else mark_cell(nb, xf, yf);
   }
-  if (((above_steps >> 8) & 1) && lane < 9) mark_px(nb, (above_argmax & 0xffff) + lane % 3 - 1, (above_argmax >> 16) + lane / 3 - 1);
+  if ((above_steps >> 8) & 1) {
+#pragma unroll 1
+    for (int q = first; q < 9; q += stride) mark_px(nb, (above_argmax & 0xffff) + q % 3 - 1, (above_argmax >> 16) + q / 3 - 1);
+  }
+}
+__device__ __forceinline__ void warp_mark_above(const LayerView& nb, int layer, int x, int y, int above_steps, int above_argmax) {
+  mark_above_strided(nb, layer, x, y, above_steps, above_argmax, threadIdx.x & 31, 32);
 }
 
 __global__ void __launch_bounds__(128, 4)
@@ -264,15 +272,9 @@ nms_checks_kernel(PyramidGeom g, DetectWorkspace ws) {
     // only read by the chain kernel); tying corners do so once they are resolved.
     mark = (ev & kCmAccept) && g.n_layers > 1 && layer < g.n_layers - 1;
   }
-  // the marks of the warp's corners, one corner at a time with one lane per scan position
-  unsigned todo = __ballot_sync(0xffffffffu, mark);
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const int mx = __shfl_sync(0xffffffffu, x, src), my = __shfl_sync(0xffffffffu, y, src), ml = __shfl_sync(0xffffffffu, layer, src);
-    const int ms = __shfl_sync(0xffffffffu, r.above_steps, src), ma = __shfl_sync(0xffffffffu, r.above_argmax, src);
-    warp_mark_above(make_view(g, ws, frame, ml + 1), ml, mx, my, ms, ma);
-  }
+  // every thread replays its own corner's scan (a few to 25 byte stores): a warp issues the longest of its 32
+  // replays once, where going through the corners one at a time with one lane per position issued all of them
+  if (mark) mark_above_strided(make_view(g, ws, frame, layer + 1), layer, x, y, r.above_steps, r.above_argmax, 0, 1);
 }
 
 // One CTA per frame, layers in order (layer i+1 needs the touch marks that layer i's accepted
