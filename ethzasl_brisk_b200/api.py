@@ -662,7 +662,7 @@ class BruteForceMatcher:
         nonempty = [i for i, t in enumerate(trains) if len(t)]
         if not nonempty:
             return [[] for q in range(len(query)) if not (compactResult and masked_out[q])]
-        idx, dist = self.knn(query, train, k, mask)  # k <= 8: the kernels keep up to 8 candidates per query
+        idx, dist = self.knn(query, train, k, mask)
         for q in range(len(query)):
             if masked_out[q]:
                 if not compactResult:
@@ -678,6 +678,14 @@ class BruteForceMatcher:
                     # minMaxLoc returns location 0 and INT_MAX (as double) is below the float it was just rounded to,
                     # so the last non-empty image wins (brute-force-matcher.cc:138-157)
                     cur.append((q, 0, nonempty[-1], 2147483648.0))
+            if len(cur) > 16:
+                # the reference's final std::sort (brute-force-matcher.cc:160): beyond 16 entries libstdc++'s introsort
+                # permutes entries of equal distance
+                t_ = np.array([m_[1] for m_ in cur], np.int32)
+                i_ = np.array([m_[2] for m_ in cur], np.int32)
+                d_ = np.array([m_[3] for m_ in cur], np.float32)
+                self.ctx._check(self.ctx._lib.brisk_std_sort_matches(C.c_int64(len(cur)), _ptr(t_), _ptr(i_), _ptr(d_)))
+                cur = [(q, int(a), int(b), float(c_)) for a, b, c_ in zip(t_, i_, d_)]
             out.append(cur)
         return out
 

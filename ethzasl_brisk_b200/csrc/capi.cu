@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "describe_logic.cuh"
+#include "gcc_sort.cuh"
 #include "harris_logic.cuh"
 #include "kernels.h"
 #include "pattern.h"
@@ -117,6 +118,7 @@ struct brisk_detector {
 
 struct brisk_extractor {
   brisk_ctx* ctx;
+  int device = 0;  // (kept here: the context may be gone by the time the extractor is destroyed)
   PatternHost host;
   DevBuf points, size_list, short_pairs, long_pairs, breaks, consts;
   PatternDev dev;
@@ -911,6 +913,7 @@ int brisk_extractor_create(brisk_ctx* ctx, int rot, int scale, int version, floa
   CU_OK(cudaSetDevice(ctx->device));
   brisk_extractor* ext = new brisk_extractor;
   ext->ctx = ctx;
+  ext->device = ctx->device;
   const std::string msg = build_pattern(version, pattern_scale, pattern_file, &ext->host);
   if (!msg.empty()) { delete ext; return fail(ctx, BRISK_ERR_INVALID, msg); }
   const PatternHost& ph = ext->host;
@@ -963,7 +966,7 @@ int brisk_extractor_create(brisk_ctx* ctx, int rot, int scale, int version, floa
 
 void brisk_extractor_destroy(brisk_extractor* ext) {
   if (!ext) return;
-  cudaSetDevice(ext->ctx->device);
+  cudaSetDevice(ext->device);
   ext->points.release(); ext->size_list.release(); ext->short_pairs.release(); ext->long_pairs.release(); ext->breaks.release(); ext->consts.release();
   delete ext;
 }
@@ -1411,9 +1414,12 @@ static int encode_rows_map(brisk_ctx* ctx, const void* base, long long rows, int
 static int knn_keys_impl(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int desc_bytes,
                          int k, int64_t offset, unsigned long long** keys_out, int* kr_out) {
   if (!ctx) return BRISK_ERR_INVALID;
-  if (!query || !train || nq < 0 || nt < 0 || k < 1 || k > 8) return fail(ctx, BRISK_ERR_INVALID, "bad kNN arguments (1 <= k <= 8)");
-  if (desc_bytes != 48 && desc_bytes != 64 && desc_bytes != 128) return fail(ctx, BRISK_ERR_UNSUPPORTED, "descriptor size must be 48, 64 or 128 bytes");
+  if (!query || !train || nq < 0 || nt < 0 || k < 1) return fail(ctx, BRISK_ERR_INVALID, "bad kNN arguments");
+  if (desc_bytes < 4 || desc_bytes % 4 || desc_bytes > 496) return fail(ctx, BRISK_ERR_UNSUPPORTED, "descriptor rows must be a multiple of 4 bytes, at most 496");
   if (offset + nt > 0xffffffffll) return fail(ctx, BRISK_ERR_UNSUPPORTED, "train index does not fit 32 bits");
+  if (k > 65536) return fail(ctx, BRISK_ERR_UNSUPPORTED, "k too large");
+  // the extractors' row widths and k <= 8 have their own kernels; anything else takes the general one
+  const bool general = (desc_bytes != 48 && desc_bytes != 64 && desc_bytes != 128) || k > 8;
   CU_OK(cudaSetDevice(ctx->device));
   const uint8_t* dq = query; const uint8_t* dt = train;
   if (!is_device_ptr(query) || (uintptr_t)query % 16) {
@@ -1425,6 +1431,17 @@ static int knn_keys_impl(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const
     CU_OK(ctx->knn_t.ensure(std::max<size_t>((size_t)nt * desc_bytes, 16)));
     CU_OK(cudaMemcpyAsync(ctx->knn_t.p, train, (size_t)nt * desc_bytes, cudaMemcpyDefault, ctx->stream));
     dt = ctx->knn_t.as<uint8_t>();
+  }
+  if (general) {
+    const int kr = knn_any_round_k(k);
+    CU_OK(ctx->knn_keys.ensure(std::max<size_t>((size_t)nq * kr * 8, 16)));
+    if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
+    CU_OK(launch_hamming_knn_any(dq, nq, dt, nt, desc_bytes, k, offset, nullptr, ctx->knn_keys.as<unsigned long long>(), ctx->stream));
+    if (ctx->timing) cudaEventRecord(ctx->ev[1], ctx->stream);
+    ctx->launches = kr / 8;
+    *keys_out = ctx->knn_keys.as<unsigned long long>();
+    *kr_out = kr;
+    return BRISK_OK;
   }
   const int kr = knn_round_k(k);
   const bool tensor = k == 2 && (desc_bytes == 48 || desc_bytes == 64);
@@ -1499,7 +1516,7 @@ int brisk_hamming_knn(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const ui
 static int stage_match_inputs(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt, int desc_bytes,
                               const uint8_t* mask, const uint8_t** dq, const uint8_t** dt, const uint8_t** dm) {
   if (!query || !train || nq < 0 || nt < 0) return fail(ctx, BRISK_ERR_INVALID, "bad matcher arguments");
-  if (desc_bytes != 48 && desc_bytes != 64 && desc_bytes != 128) return fail(ctx, BRISK_ERR_UNSUPPORTED, "descriptor size must be 48, 64 or 128 bytes");
+  if (desc_bytes < 4 || desc_bytes % 4 || desc_bytes > 496) return fail(ctx, BRISK_ERR_UNSUPPORTED, "descriptor rows must be a multiple of 4 bytes, at most 496");
   if (nt > 0x7fffffffll) return fail(ctx, BRISK_ERR_UNSUPPORTED, "train index does not fit 31 bits");
   CU_OK(cudaSetDevice(ctx->device));
   *dq = query; *dt = train; *dm = mask;
@@ -1525,14 +1542,16 @@ int brisk_hamming_knn_masked(brisk_ctx* ctx, const uint8_t* query, int64_t nq, c
                              int k, const uint8_t* mask, int32_t* idx, int32_t* dist) {
   if (!ctx) return BRISK_ERR_INVALID;
   if (!mask) return brisk_hamming_knn(ctx, query, nq, train, nt, desc_bytes, k, idx, dist);
-  if (k < 1 || k > 8) return fail(ctx, BRISK_ERR_INVALID, "bad kNN arguments (1 <= k <= 8)");
+  if (k < 1 || k > 65536) return fail(ctx, BRISK_ERR_INVALID, "bad kNN arguments");
   const uint8_t *dq, *dt, *dm;
   int rc = stage_match_inputs(ctx, query, nq, train, nt, desc_bytes, mask, &dq, &dt, &dm);
   if (rc) return rc;
-  const int kr = knn_round_k(k);
+  const bool general = (desc_bytes != 48 && desc_bytes != 64 && desc_bytes != 128) || k > 8;
+  const int kr = general ? knn_any_round_k(k) : knn_round_k(k);
   CU_OK(ctx->knn_keys.ensure(std::max<size_t>((size_t)nq * kr * 8, 16)));
   if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
-  CU_OK(launch_hamming_knn_masked(dq, nq, dt, nt, desc_bytes, k, dm, ctx->knn_keys.as<unsigned long long>(), ctx->stream));
+  if (general) CU_OK(launch_hamming_knn_any(dq, nq, dt, nt, desc_bytes, k, 0, dm, ctx->knn_keys.as<unsigned long long>(), ctx->stream));
+  else CU_OK(launch_hamming_knn_masked(dq, nq, dt, nt, desc_bytes, k, dm, ctx->knn_keys.as<unsigned long long>(), ctx->stream));
   if (ctx->timing) cudaEventRecord(ctx->ev[1], ctx->stream);
   ctx->launches = 1;
   return knn_emit(ctx, ctx->knn_keys.as<unsigned long long>(), nq, kr, k, idx, dist);
@@ -1580,10 +1599,24 @@ int brisk_hamming_radius(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const
   return BRISK_OK;
 }
 
+// std::sort of one query's DMatch list by distance (brute-force-matcher.cc:160,210), as libstdc++ leaves it: lists of
+// more than 16 entries go through introsort, which permutes entries of equal distance.  Host only.
+int brisk_std_sort_matches(int64_t n, int32_t* train_idx, int32_t* img_idx, float* distance) {
+  if (n < 0 || (n > 0 && (!train_idx || !img_idx || !distance)) || n > 0x7fffffff) return BRISK_ERR_INVALID;
+  struct M { float d; int32_t t, i; };
+  struct Less { bool operator()(const M& a, const M& b) const { return a.d < b.d; } };
+  std::vector<M> v((size_t)n);
+  for (int64_t j = 0; j < n; ++j) v[(size_t)j] = M{distance[j], train_idx[j], img_idx[j]};
+  gs_sort(Less(), v.data(), (int)n);
+  for (int64_t j = 0; j < n; ++j) { distance[j] = v[(size_t)j].d; train_idx[j] = v[(size_t)j].t; img_idx[j] = v[(size_t)j].i; }
+  return BRISK_OK;
+}
+
 int brisk_hamming_knn_keys(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train_shard, int64_t nt,
                            int desc_bytes, int k, int64_t global_train_offset, uint64_t* keys_dev) {
   if (!keys_dev || !is_device_ptr(keys_dev)) return fail(ctx, BRISK_ERR_INVALID, "keys_dev must be device memory");
-  if (k != knn_round_k(k)) return fail(ctx, BRISK_ERR_UNSUPPORTED, "sharded kNN supports k in {1, 2, 4, 8}");
+  if (k != knn_round_k(k) || (desc_bytes != 48 && desc_bytes != 64 && desc_bytes != 128))
+    return fail(ctx, BRISK_ERR_UNSUPPORTED, "sharded kNN supports k in {1, 2, 4, 8} and rows of 48, 64 or 128 bytes");
   unsigned long long* keys = nullptr; int kr = 0;
   int rc = knn_keys_impl(ctx, query, nq, train_shard, nt, desc_bytes, k, global_train_offset, &keys, &kr);
   if (rc) return rc;

@@ -254,6 +254,132 @@ radius_unpack_kernel(const RadiusMatch* __restrict__ m, long long n, int32_t* __
   idx[i] = m[i].idx; dist[i] = m[i].dist;
 }
 
+// ---------------------------------------------------------------------------
+// Any row width, any k.  The reference's matcher takes whatever cv::Mat it is given: rows of `cols` bytes, of which
+// brisk::Hamming compares cols / 16 whole 128-bit words (hamming.h:101-113), and any k (brute-force-matcher.cc:80-162).
+// The kernels above are instantiated for the extractors' widths (48 / 64 / 128 bytes) and k <= 8; everything else goes
+// through these: the queries of a CTA and a tile of train rows in shared memory, one thread per query, the k best in
+// passes of eight (pass p keeps the eight smallest keys above the last key of pass p - 1; keys are unique, they
+// carry the train index).  Rows must be a multiple of 4 bytes, at most 496.
+// ---------------------------------------------------------------------------
+constexpr int kAnyThreads = 128, kAnyTile = 32;
+
+__global__ void __launch_bounds__(kAnyThreads)
+hamming_knn_any_kernel(const uint32_t* __restrict__ q, long long nq, const uint32_t* __restrict__ t, long long nt, int row_words,
+                       int cmp_words, long long train_index_offset, unsigned long long* __restrict__ keys, int kr, int pass,
+                       const uint8_t* __restrict__ mask) {
+  extern __shared__ __align__(16) uint32_t s_any[];
+  uint32_t* s_q = s_any;                                        // [kAnyThreads][cmp_words + 1]
+  uint32_t* s_t = s_any + kAnyThreads * (cmp_words + 1);        // [kAnyTile][cmp_words]
+  const int tid = threadIdx.x;
+  const long long q_first = (long long)blockIdx.x * kAnyThreads, qi = q_first + tid;
+  for (int i = tid; i < kAnyThreads * cmp_words; i += kAnyThreads) {
+    const int r = i / cmp_words, c = i - r * cmp_words;
+    s_q[r * (cmp_words + 1) + c] = q_first + r < nq ? q[(q_first + r) * row_words + c] : 0u;
+  }
+  unsigned long long best[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) best[i] = kKeyNone;
+  const bool bounded = pass > 0;
+  const unsigned long long lower = (bounded && qi < nq) ? keys[qi * kr + 8 * pass - 1] : 0ull;
+  const uint32_t* mine = s_q + tid * (cmp_words + 1);
+  for (long long base = 0; base < nt; base += kAnyTile) {
+    const int rows = (int)min((long long)kAnyTile, nt - base);
+    __syncthreads();
+    for (int i = tid; i < rows * cmp_words; i += kAnyThreads) {
+      const int r = i / cmp_words, c = i - r * cmp_words;
+      s_t[i] = t[(base + r) * row_words + c];
+    }
+    __syncthreads();
+    if (qi >= nq || (bounded && lower == kKeyNone)) continue;   // (no more candidates after a pass that ran short)
+    for (int r = 0; r < rows; ++r) {
+      int d = 0;
+      for (int c = 0; c < cmp_words; ++c) d += __popc(mine[c] ^ s_t[r * cmp_words + c]);
+      const unsigned long long key = ((unsigned long long)(uint32_t)d << 32) | (unsigned long long)(train_index_offset + base + r);
+      if (mask && !mask[qi * nt + base + r]) continue;
+      if (bounded && key <= lower) continue;
+      topk_insert<8>(best, key);
+    }
+  }
+  if (qi < nq) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) keys[qi * kr + 8 * pass + i] = best[i];
+  }
+}
+
+int knn_any_round_k(int k) { return (k + 7) / 8 * 8; }
+
+// keys [nq][knn_any_round_k(k)], ascending per query, kKeyNone where a query runs out of (allowed) train rows.
+cudaError_t launch_hamming_knn_any(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes, int k,
+                                   long long train_index_offset, const uint8_t* mask, unsigned long long* keys, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  if (desc_bytes < 4 || desc_bytes % 4 || desc_bytes > 496 || k < 1) return cudaErrorInvalidValue;
+  const int row_words = desc_bytes / 4, cmp_words = (desc_bytes / 16) * 4, kr = knn_any_round_k(k);
+  const size_t smem = ((size_t)kAnyThreads * (cmp_words + 1) + (size_t)kAnyTile * cmp_words) * 4;
+  cudaError_t e = cudaFuncSetAttribute(hamming_knn_any_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const unsigned grid = (unsigned)((nq + kAnyThreads - 1) / kAnyThreads);
+  for (int pass = 0; pass < kr / 8; ++pass)
+    hamming_knn_any_kernel<<<grid, kAnyThreads, smem, stream>>>(reinterpret_cast<const uint32_t*>(q), nq, reinterpret_cast<const uint32_t*>(t), nt,
+                                                                row_words, cmp_words, train_index_offset, keys, kr, pass, mask);
+  return cudaGetLastError();
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kAnyThreads)
+hamming_radius_any_kernel(const uint32_t* __restrict__ q, long long nq, const uint32_t* __restrict__ t, long long nt, int row_words,
+                          int cmp_words, float max_distance, const uint8_t* __restrict__ mask, long long* __restrict__ counts,
+                          const long long* __restrict__ offsets, RadiusMatch* __restrict__ out, long long capacity) {
+  extern __shared__ __align__(16) uint32_t s_any[];
+  uint32_t* s_q = s_any;
+  uint32_t* s_t = s_any + kAnyThreads * (cmp_words + 1);
+  const int tid = threadIdx.x;
+  const long long q_first = (long long)blockIdx.x * kAnyThreads, qi = q_first + tid;
+  for (int i = tid; i < kAnyThreads * cmp_words; i += kAnyThreads) {
+    const int r = i / cmp_words, c = i - r * cmp_words;
+    s_q[r * (cmp_words + 1) + c] = q_first + r < nq ? q[(q_first + r) * row_words + c] : 0u;
+  }
+  const uint32_t* mine = s_q + tid * (cmp_words + 1);
+  long long n = 0;
+  const long long o = EMIT && qi < nq ? offsets[qi] : 0;
+  for (long long base = 0; base < nt; base += kAnyTile) {
+    const int rows = (int)min((long long)kAnyTile, nt - base);
+    __syncthreads();
+    for (int i = tid; i < rows * cmp_words; i += kAnyThreads) {
+      const int r = i / cmp_words, c = i - r * cmp_words;
+      s_t[i] = t[(base + r) * row_words + c];
+    }
+    __syncthreads();
+    if (qi >= nq) continue;
+    for (int r = 0; r < rows; ++r) {
+      int d = 0;
+      for (int c = 0; c < cmp_words; ++c) d += __popc(mine[c] ^ s_t[r * cmp_words + c]);
+      if ((float)d < max_distance && (!mask || mask[qi * nt + base + r])) {
+        if (EMIT && o + n < capacity) out[o + n] = RadiusMatch{(int)(base + r), d};
+        ++n;
+      }
+    }
+  }
+  if (!EMIT && qi < nq) counts[qi] = n;
+}
+
+static cudaError_t radius_any(int phase, const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes, float max_distance,
+                              const uint8_t* mask, long long* counts, long long* offsets, RadiusMatch* out, long long capacity,
+                              cudaStream_t stream) {
+  if (desc_bytes < 4 || desc_bytes % 4 || desc_bytes > 496) return cudaErrorInvalidValue;
+  const int row_words = desc_bytes / 4, cmp_words = (desc_bytes / 16) * 4;
+  const size_t smem = ((size_t)kAnyThreads * (cmp_words + 1) + (size_t)kAnyTile * cmp_words) * 4;
+  const unsigned grid = (unsigned)((nq + kAnyThreads - 1) / kAnyThreads);
+  const uint32_t* q32 = reinterpret_cast<const uint32_t*>(q);
+  const uint32_t* t32 = reinterpret_cast<const uint32_t*>(t);
+  cudaError_t e = cudaFuncSetAttribute(hamming_radius_any_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(hamming_radius_any_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (phase == 0) hamming_radius_any_kernel<false><<<grid, kAnyThreads, smem, stream>>>(q32, nq, t32, nt, row_words, cmp_words, max_distance, mask, counts, offsets, out, capacity);
+  else hamming_radius_any_kernel<true><<<grid, kAnyThreads, smem, stream>>>(q32, nq, t32, nt, row_words, cmp_words, max_distance, mask, counts, offsets, out, capacity);
+  return cudaGetLastError();
+}
+
 template <int WORDS>
 static cudaError_t radius_words(int phase, const uint8_t* q, long long nq, const uint8_t* t, long long nt, float max_distance,
                                 const uint8_t* mask, long long* counts, long long* offsets, RadiusMatch* out, long long capacity,
@@ -278,7 +404,7 @@ cudaError_t launch_hamming_radius(int phase, const uint8_t* q, long long nq, con
     case 48: e = radius_words<12>(phase, q, nq, t, nt, max_distance, mask, counts, offsets, out, capacity, stream); break;
     case 64: e = radius_words<16>(phase, q, nq, t, nt, max_distance, mask, counts, offsets, out, capacity, stream); break;
     case 128: e = radius_words<32>(phase, q, nq, t, nt, max_distance, mask, counts, offsets, out, capacity, stream); break;
-    default: return cudaErrorInvalidValue;
+    default: e = radius_any(phase, q, nq, t, nt, desc_bytes, max_distance, mask, counts, offsets, out, capacity, stream); break;
   }
   if (e != cudaSuccess) return e;
   if (phase == 0) radius_scan_kernel<<<1, 1024, 0, stream>>>(counts, nq, offsets);

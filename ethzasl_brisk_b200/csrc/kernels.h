@@ -127,6 +127,11 @@ cudaError_t launch_describe(const PatternDev& pat, const uint8_t* imgs, long lon
 // sorted ascending per query, kr = knn_round_k(k) keys per query.
 int knn_num_splits(long long nq, long long nt);
 int knn_round_k(int k);
+// Any row width (a multiple of 4 bytes up to 496; whole 128-bit words are compared) and any k: keys [nq][knn_any_round_k(k)],
+// optional [nq][nt] byte mask.
+int knn_any_round_k(int k);
+cudaError_t launch_hamming_knn_any(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes, int k,
+                                   long long train_index_offset, const uint8_t* mask, unsigned long long* keys, cudaStream_t stream);
 cudaError_t launch_hamming_knn_ex(const uint8_t* q, long long nq, const uint8_t* t, long long nt, int desc_bytes, int k,
                                   long long train_index_offset, unsigned long long* keys, unsigned long long* part,
                                   int splits, cudaStream_t stream);

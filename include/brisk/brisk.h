@@ -675,6 +675,9 @@ class BruteForceMatcher {
           matches.back().push_back(m);
         }
       }
+      // the reference's final std::sort (brute-force-matcher.cc:160): the list is in ascending order already, which
+      // insertion sort (up to 16 entries) keeps; longer lists go through introsort, which permutes equal distances
+      if (matches.back().size() > 16) std::sort(matches.back().begin(), matches.back().end());
     }
   }
   void radiusImpl(const agast::Mat& query, const std::vector<agast::Mat>& train, std::vector<std::vector<DMatch> >& matches,

@@ -209,9 +209,16 @@ int brisk_hamming_distance(brisk_ctx* ctx, const uint8_t* a, const uint8_t* b, i
 
 /* knnMatch(): BruteForceMatcher::commonKnnMatchImpl -- reference brisk/src/brute-force-matcher.cc:80-162
  * (one train collection, no mask).  idx/dist: [nq][k]; ties go to the lowest train index; missing
- * neighbours (nt < k) are -1.  desc_bytes: 48, 64 or 128. */
+ * neighbours (nt < k) are -1.  desc_bytes: any multiple of 4 up to 496 (whole 128-bit words are compared, as brisk::Hamming
+ * does); the extractors' widths (48 / 64 / 128) with k <= 8 run on the tuned kernels (tcgen05 for k = 2), everything else on a
+ * general one that selects the k best in passes of eight. */
 int brisk_hamming_knn(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const uint8_t* train, int64_t nt,
                       int desc_bytes, int k, int32_t* idx, int32_t* dist);
+/* std::sort of one query's match list by distance, entry for entry as libstdc++ (GCC 13) leaves it -- the reference sorts
+ * every list it returns (brute-force-matcher.cc:160,210), and beyond 16 entries introsort permutes equal distances.
+ * knnMatch lists of k > 16 need it (shorter ones come back in that order already); host arrays, no device work. */
+int brisk_std_sort_matches(int64_t n, int32_t* train_idx, int32_t* img_idx, float* distance);
+
 /* knnMatch() with masks: commonKnnMatchImpl's `isPossibleMatch` test -- reference brisk/src/brute-force-matcher.cc:
  * 118-119.  mask: [nq][nt] bytes, 0 = pair excluded (the per-image masks of a train collection side by side, as the
  * train rows are); NULL = no mask.  Queries with fewer than k allowed rows get -1 entries (the host classes turn

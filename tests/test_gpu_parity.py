@@ -917,6 +917,26 @@ def test_harris_unsupported(ctx):
         bb.ScaleSpaceFeatureDetector(0, 0.2, 20.0, ctx=ctx).detect(bb.synthetic_frame(1920, 1080, 1))
 
 
+
+
+def test_matcher_any_width_any_k(ctx, matcher_oracle):
+    # rows the extractors do not produce (multiples of 16 bytes here: the reference reads rows with aligned 128-bit loads) and
+    # k > 8: the general kernel, against the reference's matcher class -- with and without masks, and radiusMatch
+    rng = np.random.default_rng(5)
+    m = bb.BruteForceMatcher(ctx=ctx)
+    for nb, nq, nt, k in ((32, 70, 300, 3), (80, 150, 900, 11), (16, 33, 64, 2), (64, 90, 400, 20), (48, 40, 13, 16), (256, 20, 50, 9), (496, 10, 40, 4)):
+        q = rng.integers(0, 256, (nq, nb), dtype=np.uint8)
+        t = rng.integers(0, 4, (nt, nb), dtype=np.uint8) if nb == 16 else rng.integers(0, 256, (nt, nb), dtype=np.uint8)   # (many ties)
+        got = m.knnMatch(q, [t], k)
+        want = matcher_oracle.knn_match(q, [t], k)
+        assert got == want, (nb, k)
+        mask = (rng.integers(0, 3, (nq, nt)) > 0).astype(np.uint8)
+        mask[::7] = 0
+        assert m.knnMatch(q, [t], k, masks=[mask]) == matcher_oracle.knn_match(q, [t], k, masks=[mask]), (nb, k, "masked")
+        radius = float(np.median(m.knn(q, t, 1)[1])) + 8.0
+        assert m.radiusMatch(q, [t], radius) == matcher_oracle.radius_match(q, [t], radius), (nb, "radius")
+
+
 @pytest.mark.parametrize("nbytes", [48, 64])
 def test_knn_tensor_core_variants_match_popc(oracle, nbytes):
     # the tcgen05 kernel (variant 2, the default: kind::i8 MMAs on +-1 bytes, TMEM accumulators, TMA operands) and the
