@@ -82,6 +82,7 @@ integral_strip_kernel(const uint8_t* __restrict__ imgs, long long frame_stride, 
   // I(Y - 1, x + 1) of the tightly packed image (the pixel right of the last column is the first of the next row), as
   // up_right[Y * pitch]; the neighbour thread loaded these bytes one step ago
   const uint8_t* up_right = imgs + (long long)frame * frame_stride + (x + 1 < w ? x + 1 - pitch : 0);
+  const uint8_t* urp = up_right;   // up_right + y0 * pitch
 #pragma unroll
   for (int r = 0; r < kIntRows; ++r) { v[r] = (in && r < h) ? cp[r * pitch] : 0; l[r] = r < h ? lp[r * ns] : 0; }
   for (int y0 = 0, it = 0; y0 < h; y0 += kIntRows, ++it) {
@@ -110,8 +111,14 @@ integral_strip_kernel(const uint8_t* __restrict__ imgs, long long frame_stride, 
     }
     __syncthreads();
     int ur[kIntRows];
+    if (y0 > 0 && y0 + kIntRows <= h) {
 #pragma unroll
-    for (int r = 0; r < kIntRows; ++r) ur[r] = (in && y0 + r > 0 && y0 + r < h) ? up_right[(long long)(y0 + r) * pitch] : 0;
+      for (int r = 0; r < kIntRows; ++r) ur[r] = in ? urp[r * pitch] : 0;
+    } else {
+#pragma unroll
+      for (int r = 0; r < kIntRows; ++r) ur[r] = (in && y0 + r > 0 && y0 + r < h) ? up_right[(long long)(y0 + r) * pitch] : 0;
+    }
+    urp += kIntRows * pitch;
     {
       // warp `warp` finishes row y0 + warp: eight consecutive columns per lane, serial prefix, warp scan of the totals
       int4* p = reinterpret_cast<int4*>(&t[warp][8 * lane]);
