@@ -245,7 +245,10 @@ describe_cull_kernel(PatternDev pat, int w, int h, const KeyPoint* __restrict__ 
 
 // --- descriptor: one warp per key point ---
 
-constexpr int kDescWarps = 8;
+#ifndef BRISK_DESC_WARPS
+#define BRISK_DESC_WARPS 8
+#endif
+constexpr int kDescWarps = BRISK_DESC_WARPS;
 #ifndef BRISK_DESC_MIN_BLOCKS
 #define BRISK_DESC_MIN_BLOCKS 5
 #endif

@@ -80,7 +80,7 @@ struct BlockIntegral {
   int bw;  // blocks per row (= image width)
   BRISK_HD static BlockFields load(const Block4* p) {
 #ifdef __CUDA_ARCH__
-    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    const int4 v = __ldg(reinterpret_cast<const int4*>(p));   // (L1-allocating on purpose: the boxes of neighbouring pattern points overlap)
     return decode_block(Block4{v.x, v.y, v.z, v.w});
 #else
     return decode_block(*p);

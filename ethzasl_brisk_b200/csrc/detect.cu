@@ -22,7 +22,13 @@ constexpr int kDetStrip = 30;                 // rows per thread: 2 strips of 30
 constexpr int kDetRows = kDetStrip + 6;       // source rows a thread walks (36 = 3 * 12, the unroll period)
 constexpr int kDetSW = kDetTW + 8;            // staged row: [x0-4, x0+TW+4), 4-byte aligned
 constexpr int kDetSH = kDetTH + 6;            // staged rows: [y0-3, y0+TH+3)
-constexpr int kDetQueue = 6144;               // candidate queue (cx | ry << 8); beyond it candidates are tested in place
+#ifndef BRISK_DET_QUEUE
+#define BRISK_DET_QUEUE 6144
+#endif
+#ifndef BRISK_DET_MINB
+#define BRISK_DET_MINB 1
+#endif
+constexpr int kDetQueue = BRISK_DET_QUEUE;               // candidate queue (cx | ry << 8); beyond it candidates are tested in place
 constexpr uint32_t kB2None = 0x3fffu;         // contrast no pixel reaches: "threshold map below the lower bound"
 
 // 9-of-16 segment test of OastDetector9_16::detect on the staged tile (ring of agast/include/agast/oast9-16.h:99-116).
@@ -63,7 +69,7 @@ __device__ __forceinline__ bool segment_test(const uint8_t (*s_img)[kDetSW], int
 // LOWER: lower bound of the threshold map (BriskScaleSpace::kDefaultLowerThreshold = 10 for detection;
 // 0 for the pyramid that BriskFeatureDetector::ComputeScale builds, brisk-feature-detector.cc:90).
 template <int LOWER>
-__global__ void __launch_bounds__(kDetThreads)
+__global__ void __launch_bounds__(kDetThreads, BRISK_DET_MINB)
 agast_detect_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restrict__ pyr, uint16_t* __restrict__ cm,
                     int* __restrict__ rowcnt, int total_rows, int row_off, int thresh) {
   __shared__ __align__(16) uint8_t s_img[kDetSH][kDetSW];
