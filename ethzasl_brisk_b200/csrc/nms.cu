@@ -51,26 +51,54 @@ nms_prefix_kernel(PyramidGeom g, DetectWorkspace ws) {
   const int n = min(ws.layer_start[(long long)frame * (kMaxLayers + 1) + g.n_layers], ws.corner_cap);
   if (blockIdx.x * blockDim.x >= n) return;
   bool on = false, tie = false;
-  int x = 0, y = 0, layer = -1;
+  int x = 0, y = 0, layer = 0;
+  OwnWindowRegs w;
+  w.r[0] = w.r[1] = w.r[2] = w.r[3] = w.r[4] = 0;
   if (k < n) {
     unpack_corner(ws.corners[(long long)frame * ws.corner_cap + k], &x, &y, &layer);
-    const LayerView v = make_view(g, ws, frame, layer);
-    uint8_t fwin[25];
-#pragma unroll
-    for (int i = 0; i < 25; ++i) fwin[i] = 0;
-    nms_prefix(v, x, y, fwin);
-    const uint16_t ev = v.cm[(long long)y * v.pitch + x];
+    const uint16_t ev = nms_prefix_mid(make_view(g, ws, frame, layer), x, y, &w);
     on = ev & (kCmAccept | kCmTie);
     tie = ev & kCmTie;
-    if (on) {
-      // the score window: the chain kernel reads all of it (tying corners), refine_kernel its inner 3x3
-      uint32_t wds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  }
+  // the outer rows (-2 and +2) of the tying corners' windows, which only the tie path reads: two row evaluations per
+  // tying corner, dealt out over the lanes of the warp (item 2 * i + s = row (s ? +2 : -2) of the warp's i-th tying
+  // corner), so that a warp with m ties issues the evaluator's code ceil(2 m / 32) times instead of twice
+  {
+    const unsigned ties = __ballot_sync(0xffffffffu, tie);
+    const int n_items = 2 * __popc(ties);
+    const int my_first = 2 * __popc(ties & ((1u << lane) - 1u));   // item index of this lane's row -2 (if it ties)
+    for (int base = 0; base < n_items; base += 32) {
+      const int item = base + lane;
+      const bool active = item < n_items;
+      const int src = active ? (int)__fns(ties, 0, (item >> 1) + 1) : 0;
+      const int sx = __shfl_sync(0xffffffffu, x, src), sy = __shfl_sync(0xffffffffu, y, src), sl = __shfl_sync(0xffffffffu, layer, src);
+      unsigned long long rowv = 0;
+      if (active) {
+        OwnWindowRegs t;
+        t.r[0] = t.r[4] = 0;
+        const int wy = (item & 1) ? 2 : -2;
+        own_window_rows(make_view(g, ws, frame, sl), sx, sy, wy, wy, &t);
+        rowv = (item & 1) ? t.r[4] : t.r[0];
+      }
+      // hand the rows back to their owners
 #pragma unroll
-      for (int i = 0; i < 25; ++i) wds[i >> 2] |= (uint32_t)fwin[i] << (8 * (i & 3));
-      uint4* dst = reinterpret_cast<uint4*>(ws.fwin + ((long long)frame * ws.corner_cap + k) * 32);
-      dst[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
-      dst[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
+      for (int s = 0; s < 2; ++s) {
+        const int want = my_first + s - base;
+        const bool mine = tie && want >= 0 && want < 32;
+        const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)rowv, mine ? want : 0);
+        const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(rowv >> 32), mine ? want : 0);
+        if (mine) w.r[s ? 4 : 0] = ((unsigned long long)hi << 32) | lo;
+      }
     }
+  }
+  if (on) {
+    // the score window: the chain kernel reads all of it (tying corners), refine_kernel its inner 3x3
+    uint32_t wds[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 25; ++i) wds[i >> 2] |= (uint32_t)((w.r[i / 5] >> (8 * (i % 5))) & 0xffull) << (8 * (i & 3));
+    uint4* dst = reinterpret_cast<uint4*>(ws.fwin + ((long long)frame * ws.corner_cap + k) * 32);
+    dst[0] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+    dst[1] = make_uint4(wds[4], wds[5], wds[6], wds[7]);
   }
   // per-layer list of the tying corners (any order) for the chain kernel, in the frame's key-point scratch, which
   // is free until refine_kernel runs; layer l's list starts at its first corner slot.  One atomic per warp and layer

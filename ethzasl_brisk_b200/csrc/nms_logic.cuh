@@ -469,29 +469,27 @@ __device__ __forceinline__ void own_window_rows(const LayerView& L, int x, int y
 }
 #endif
 
-// Window + corner-map entry of one corner.  Host: the whole window.  Device: the three middle rows first (they hold
-// the eight neighbours); the outer rows only for a corner that ties -- nothing else reads them.
+// Window + corner-map entry of one corner.  Host: the whole window.  Device (nms_prefix_kernel): the three middle rows
+// first (they hold the eight neighbours) with nms_prefix_mid; the outer rows only for corners that tie -- nothing else
+// reads them -- and those are evaluated by the warp together, one row per lane (own_window_rows on the owner's data).
 BRISK_HD void nms_prefix(const LayerView& L, int x, int y, uint8_t fwin[25]) {
   const long long o = (long long)y * L.pitch + x;
-#ifdef __CUDA_ARCH__
-  OwnWindowRegs w;
-  w.r[0] = w.r[1] = w.r[2] = w.r[3] = w.r[4] = 0;
-  own_window_rows(L, x, y, -1, 1, &w);
-#pragma unroll
-  for (int i = 5; i < 20; ++i) fwin[i] = (uint8_t)(w.r[i / 5] >> (8 * (i % 5)));
-  const uint16_t e = prefix_entry(L.cm[o] & kCmT, fwin);
-  L.cm[o] = e;
-  if (e & kCmTie) {
-    own_window_rows(L, x, y, -2, -2, &w);
-    own_window_rows(L, x, y, 2, 2, &w);
-  }
-#pragma unroll
-  for (int i = 0; i < 25; ++i) fwin[i] = (uint8_t)(w.r[i / 5] >> (8 * (i % 5)));
-#else
   own_window(L, x, y, fwin);
   L.cm[o] = prefix_entry(L.cm[o] & kCmT, fwin);
-#endif
 }
+#ifdef __CUDACC__
+__device__ __forceinline__ uint16_t nms_prefix_mid(const LayerView& L, int x, int y, OwnWindowRegs* w) {
+  const long long o = (long long)y * L.pitch + x;
+  w->r[0] = w->r[1] = w->r[2] = w->r[3] = w->r[4] = 0;
+  own_window_rows(L, x, y, -1, 1, w);
+  uint8_t mid[25];
+#pragma unroll
+  for (int i = 0; i < 25; ++i) mid[i] = (i >= 5 && i < 20) ? (uint8_t)(w->r[i / 5] >> (8 * (i % 5))) : (uint8_t)0;
+  const uint16_t e = prefix_entry(L.cm[o] & kCmT, mid);
+  L.cm[o] = e;
+  return e;
+}
+#endif
 
 // Scores of the two scan tiles of a corner (the layer above: bytes 0..15, the layer below: bytes 16..31, row stride 4
 // from the tile's first pixel; for layer 0 bytes 16..24 hold the nine 5-8 scores of :558-592, s[3 * column + row]).
