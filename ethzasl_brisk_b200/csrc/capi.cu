@@ -36,6 +36,14 @@ struct DevBuf {
     if (e == cudaSuccess) cap = bytes;
     return e;
   }
+  // for buffers whose rows are copied out beyond what a kernel wrote (the strided result copies): never hand
+  // uninitialised device memory to the caller
+  cudaError_t ensure_zeroed(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    cudaError_t e = ensure(bytes);
+    if (e == cudaSuccess) e = cudaMemset(p, 0, cap);
+    return e;
+  }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
   template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
 };
@@ -576,9 +584,9 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
   const bool masks_dev = masks && is_device_ptr(masks);
   for (int si = 0; si < plan.n_slots; ++si) {
     Slot& sl = ctx->slots[si];
-    if (!kps_dev) CU_OK(sl.kps.ensure((size_t)plan.chunk * cap * 28));
+    if (!kps_dev) CU_OK(sl.kps.ensure_zeroed((size_t)plan.chunk * cap * 28));
     if (!counts_dev) CU_OK(sl.counts.ensure((size_t)plan.chunk * 4));
-    if (ext && !desc_dev) CU_OK(sl.desc.ensure((size_t)plan.chunk * cap * desc_bytes));
+    if (ext && !desc_dev) CU_OK(sl.desc.ensure_zeroed((size_t)plan.chunk * cap * desc_bytes));
     if (det && masks && !masks_dev) CU_OK(sl.masks.ensure((size_t)plan.chunk * w * h));
     if ((ext && g.L[0].pitch != w) || !is_device_ptr(imgs)) CU_OK(sl.tight.ensure((size_t)plan.chunk * ((size_t)w * h + 64)));
   }

@@ -1,13 +1,15 @@
-# full GPU evidence pass: tests, default bench, the other configurations, launch list, full ncu captures
+# full GPU evidence pass: tests, default bench, the other configurations, launch list, full ncu captures, sanitizer
 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/r02_pytest.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke.log 2>&1
 python bench.py > gpurun_out/r02_bench_C3.json 2> gpurun_out/r02_bench_C3.err
 python bench.py --impl reference --steps 3 > gpurun_out/r02_bench_C3_reference.json 2>> gpurun_out/r02_bench_C3.err
 python bench.py --config C2 --steps 5 > gpurun_out/r02_bench_C2.json 2> gpurun_out/r02_bench_C2.err
 python bench.py --config C4 --steps 3 > gpurun_out/r02_bench_C4.json 2> gpurun_out/r02_bench_C4.err
 python bench.py --config C5 --steps 2 --knn-popc > gpurun_out/r02_bench_C5.json 2> gpurun_out/r02_bench_C5.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --steps 1 --warmup 3 --frames 256 --no-knn --parity-frames 0 > gpurun_out/r02_launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"pyramid_kernel|agast_detect|row_scan|corner_fill|nms_|refine_kernel|compact_kernel|integral_|describe_" -s 60 -c 30 -o gpurun_out/r02_step python tools/profile_step.py 256 2 > gpurun_out/r02_ncu_step.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"tc5_kernel" -c 2 -o gpurun_out/r02_tc5 python tools/knn_timing.py 50000 400000 2 > gpurun_out/r02_ncu_tc5.log 2>&1
-tail -2 gpurun_out/r02_pytest.log; for f in C3 C2 C4 C5; do python -c "
+ncu --set full --clock-control none --import-source on -k regex:"pyramid_kernel|agast_detect|row_scan|corner_fill|nms_|refine_kernel|compact_kernel|integral_|describe_" -s 54 -c 27 -o gpurun_out/r02_step python tools/profile_step.py 128 2 > gpurun_out/r02_ncu_step.log 2>&1
+bash tools/gpu/run_sanitize.sh > gpurun_out/r02_sanitize_summary.txt 2>&1
+tail -2 gpurun_out/r02_pytest.log; tail -1 gpurun_out/r02_smoke.log; for f in C3 C2 C4 C5; do python -c "
 import json,sys; d=json.load(open('gpurun_out/r02_bench_$f.json')); print('$f', round(d['value'],1), d['unit'], 'e2e', round(d['e2e']['value'],1), 'parity', d.get('parity_ok'), 'cpu', d.get('cpu_baseline',{}).get('value'))"; done
+grep -E "rc=|SUMMARY" gpurun_out/r02_sanitize_summary.txt
 ls -la gpurun_out/*.ncu-rep | tail -3
