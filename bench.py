@@ -401,7 +401,19 @@ def run_frames(args):
         return 0
 
     value = world * n * args.steps / (ms_res * 1e-3)
-    e2e_value = world * n * args.steps / (ms_e2e * 1e-3)
+    # end to end through the C ABI with pinned host buffers, both ways a caller can make the call; `value` is the faster
+    # one on this box (streaming wins where the copies hide behind kernels, the blocking call where N ranks saturate the
+    # host's memory system and overlapping steps only adds contention)
+    streamed_value = world * n * args.steps / (ms_e2e * 1e-3)
+    blocking_value = world * n * args.steps / (ms_e2e_blocking * 1e-3)
+    streamed = streamed_value >= blocking_value
+    e2e_value = max(streamed_value, blocking_value)
+    e2e_obj = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * H * W, "d2h_bytes_per_step": 4 * n + kp_total * (28 + 48),
+               "ms_per_step": (ms_e2e if streamed else ms_e2e_blocking) / args.steps,
+               "call": ("brisk_detect_describe_async x steps + brisk_sync (outputs double-buffered by the caller)" if streamed
+                        else "brisk_detect_describe (blocking)") + ", pinned host buffers",
+               "streaming_call_value": streamed_value, "streaming_call_ms_per_step": ms_e2e / args.steps,
+               "blocking_call_value": blocking_value, "blocking_call_ms_per_step": ms_e2e_blocking / args.steps}
     h2d = n * H * W
     d2h = 4 * n + kp_total * (28 + 48)
     # roofline of the dominant stage (device time from CUDA events on the launching stream)
@@ -484,9 +496,7 @@ def run_frames(args):
                        "global_frames_per_step": world * n, "keypoints_per_frame": kps_per_frame, "raw_corners_per_frame": corners_per_frame,
                        "parallelism": f"frame-sharded x{world}, no collective", "cpus_per_rank": rig.numa,
                        "l2": f"inputs ({n * H * W / 1e6:.0f} MB per step) exceed the 126 MB L2; no explicit flush", "kp_capacity": cap},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                    "call": "brisk_detect_describe_async x steps + brisk_sync, pinned host buffers (outputs double-buffered by the caller)",
-                    "blocking_call_value": world * n * args.steps / (ms_e2e_blocking * 1e-3), "blocking_call_ms_per_step": ms_e2e_blocking / args.steps},
+            "e2e": e2e_obj,
             "gpu_launches": launches, "roofline": roof, "stages": stage_report, "cpu_baseline": cpu, "clocks": clocks}
     if parity:
         line.update({"parity_checked_frames": parity["parity_checked_frames"], "parity_ok": parity["parity_ok"], "parity": parity})
