@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/probes/gather_probe tools/probes/gather_probe.cu
 // Micro-benchmark: throughput of scattered 16-byte gathers from a block image (the access pattern of the
 // descriptor sampler: one warp per key point, lanes at scattered offsets inside a window around it) through
 // the load/store path (LDG.128) and through the texture path (tex1Dfetch<int4> / tex2D<int4>).
