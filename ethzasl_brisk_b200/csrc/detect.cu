@@ -61,8 +61,8 @@ __device__ __forceinline__ bool segment_test(const uint8_t (*s_img)[kDetSW], int
 // rows with three more:  out(y) = max3(G(y-1), M7(y), H(y+3)),  G(r) = max3(M3(r-2), M5(r-1), M7(r)),
 // H(r) = max3(M7(r-2), M5(r-1), M3(r)); the short histories live in registers (the loop is unrolled by
 // 12, a multiple of every history depth, so all slots are static).  The 4-point compass pre-test (a
-// 9-arc holds at least two compass points) is done on the pairs as well: at least two compass pixels
-// brighter than c + b  <=>  the second largest exceeds it.  The verdicts are shifted into two 64-bit
+// 9-arc holds two adjacent compass points) is done on the pairs as well: two adjacent compass pixels
+// brighter than c + b  <=>  min(max(left, right), max(up, down)) exceeds it.  The verdicts are shifted into two 64-bit
 // registers (two bits per row) and the threshold-map values go to a byte plane in shared memory; the
 // survivors (a few per cent) are queued once the walk is over, so that the row loop has no divergent path.
 // Phase 2: the queue is processed densely, one candidate per thread, with the full 9-of-16 run test.
@@ -177,9 +177,10 @@ agast_detect_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restric
         for (int h = 0; h < 2; ++h) {
           const uint32_t c = h ? cO : cE, b = h ? bO : bE;
           const uint32_t p0 = h ? lO : lE, p4 = h ? nO : nE, p8 = h ? rO : rE, p12 = h ? P5 : P4;
-          // second largest / second smallest of the four compass pixels
-          const uint32_t h1 = __vmaxu2(p0, p4), l1 = __vminu2(p0, p4), h2 = __vmaxu2(p8, p12), l2 = __vminu2(p8, p12);
-          const uint32_t S2 = __vimax3_u16x2(__vminu2(h1, h2), l1, l2), s2 = __vimin3_u16x2(__vmaxu2(l1, l2), h1, h2);
+          // A 9-arc holds two ADJACENT compass pixels (ring positions 4 apart).  Every horizontal compass pixel is adjacent
+          // to every vertical one, so the best adjacent pair is (best horizontal, best vertical): S2 = the largest value two
+          // adjacent compass pixels both reach, s2 = the smallest value two adjacent ones both stay under.
+          const uint32_t S2 = __vminu2(__vmaxu2(p0, p8), __vmaxu2(p4, p12)), s2 = __vmaxu2(__vminu2(p0, p8), __vminu2(p4, p12));
           // lane test A > B as ((B | 0x8000) - A) losing bit 15 (all values stay below 0x8000)
           const uint32_t bright = ((c + b) | kHi) - S2;   // bit 15 clear <=> S2 > c + b
           const uint32_t dark = ((s2 + b) | kHi) - c;     // bit 15 clear <=> c > s2 + b
