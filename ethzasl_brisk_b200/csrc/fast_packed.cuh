@@ -32,6 +32,32 @@ __device__ __forceinline__ uint32_t packed_pair_at(uint32_t w0, uint32_t w1, uin
   }
 }
 
+// The two extrema that decide a 9-of-16 segment test, on PAIRS of pixels (p[i] = ring pixel i of two pixels in the two
+// 16-bit lanes): *bright = max over the sixteen 9-arcs of the arc's minimum, *dark = min over the arcs of the arc's maximum.
+// A pixel is a corner at contrast b  <=>  bright > c + b or dark < c - b; its score is max(bright - c, c - dark) - 1.
+// Sliding min / max over 9 as windows of 3, then three of those 3 apart.
+__device__ __forceinline__ void arc_extrema16x2(const uint32_t (&p)[16], uint32_t* bright_out, uint32_t* dark_out) {
+  uint32_t lo3[16], hi3[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    lo3[i] = __vimin3_u16x2(p[i], p[(i + 1) & 15], p[(i + 2) & 15]);
+    hi3[i] = __vimax3_u16x2(p[i], p[(i + 1) & 15], p[(i + 2) & 15]);
+  }
+  uint32_t lo9[16], hi9[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    lo9[i] = __vimin3_u16x2(lo3[i], lo3[(i + 3) & 15], lo3[(i + 6) & 15]);
+    hi9[i] = __vimax3_u16x2(hi3[i], hi3[(i + 3) & 15], hi3[(i + 6) & 15]);
+  }
+  uint32_t bright = lo9[15], dark = hi9[15];
+#pragma unroll
+  for (int i = 0; i < 15; i += 3) {
+    bright = __vmaxu2(bright, __vimax3_u16x2(lo9[i], lo9[i + 1], lo9[i + 2]));
+    dark = __vminu2(dark, __vimin3_u16x2(hi9[i], hi9[i + 1], hi9[i + 2]));
+  }
+  *bright_out = bright; *dark_out = dark;
+}
+
 // F (clipped at 0) of the pixels (x + 2q, y) / (x + 2q + 1, y) in the low / high half of out[q], q < NP <= 3.
 // Reads rows y-3..y+3 and columns x-3..x+2NP+2; rows and words outside the plane are clamped, which only changes
 // the scores of pixels within 3 pixels of the image border -- the callers never use those (in_border).
@@ -67,25 +93,8 @@ __device__ __forceinline__ void fast916_row(const uint8_t* __restrict__ img, int
   }
 #pragma unroll
   for (int q = 0; q < NP; ++q) {
-    // arc_contrast16 on pairs: sliding min / max over 9 as windows of 3, then three of those 3 apart
-    uint32_t lo3[16], hi3[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      lo3[i] = __vimin3_u16x2(p[q][i], p[q][(i + 1) & 15], p[q][(i + 2) & 15]);
-      hi3[i] = __vimax3_u16x2(p[q][i], p[q][(i + 1) & 15], p[q][(i + 2) & 15]);
-    }
-    uint32_t lo9[16], hi9[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      lo9[i] = __vimin3_u16x2(lo3[i], lo3[(i + 3) & 15], lo3[(i + 6) & 15]);
-      hi9[i] = __vimax3_u16x2(hi3[i], hi3[(i + 3) & 15], hi3[(i + 6) & 15]);
-    }
-    uint32_t bright = lo9[15], dark = hi9[15];
-#pragma unroll
-    for (int i = 0; i < 15; i += 3) {
-      bright = __vmaxu2(bright, __vimax3_u16x2(lo9[i], lo9[i + 1], lo9[i + 2]));
-      dark = __vminu2(dark, __vimin3_u16x2(hi9[i], hi9[i + 1], hi9[i + 2]));
-    }
+    uint32_t bright, dark;
+    arc_extrema16x2(p[q], &bright, &dark);
     // per lane max(bright - c, c - dark) - 1, clipped at 0; the lanes are biased by 0x8000 so that no borrow crosses them
     constexpr uint32_t kBias = 0x80008000u;
     const uint32_t d1 = (bright | kBias) - c[q], d2 = (c[q] | kBias) - dark;
