@@ -139,7 +139,8 @@ nms_prefix_kernel(PyramidGeom g, DetectWorkspace ws) {
 // neighbourhood, and the scan footprint for warp_mark_above.  Loaded one corner ahead of its use.
 struct TieLoads {
   uint16_t we[2];
-  int F, bmv;
+  unsigned F;  // (lanes >= 25: a byte of the record's padding, never used)
+  int bmv;
   int2 fp;  // CheckResult::above_steps, above_argmax
 };
 
@@ -147,17 +148,17 @@ __device__ __forceinline__ void tie_issue_loads(const LayerView& L, int mode, in
                                                 const float* __restrict__ checks, TieLoads* t) {
   const int lane = threadIdx.x & 31;
   const int ox = lane % 5 - 2, oy = lane / 5 - 2;  // lanes 0..24 <-> 5x5 offsets, row-major
-  t->we[0] = 0; t->we[1] = 0; t->F = 0; t->bmv = 0;
+  t->we[0] = 0; t->we[1] = 0; t->bmv = 0;
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int i = lane + 32 * h;
     const int px = x - 4 + (i & 7), py = y - 4 + (i >> 3);
     if (py >= 3 && px >= 3 && px < L.w - 3 && py < L.h - 3) t->we[h] = L.cm[(long long)py * L.pitch + px];
   }
-  if (lane < 25) {
-    t->F = fwin[lane];
-    if (!in_border(L, x + ox, y + oy)) t->bmv = L.bm[(long long)(y + oy) * L.pitch + x + ox];
-  }
+  // (every lane loads a byte of the corner's 32-byte window record, so that no conversion or merge instruction has to
+  // wait for the load right here: the value is used one corner later)
+  t->F = __ldg(fwin + lane);
+  if (lane < 25 && !in_border(L, x + ox, y + oy)) t->bmv = L.bm[(long long)(y + oy) * L.pitch + x + ox];
   t->fp = mode == kModeMid ? *reinterpret_cast<const int2*>(checks + 6) : make_int2(0, 0);
 }
 
@@ -167,7 +168,7 @@ __device__ __forceinline__ int warp_tie_decide(const LayerView& L, int x, int y,
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int ox = lane % 5 - 2, oy = lane / 5 - 2;  // lanes 0..24 <-> 5x5 offsets, row-major
-  const int F = ld.F;
+  const int F = lane < 25 ? (int)ld.F : 0;
   s_win[lane] = ld.we[0];
   s_win[lane + 32] = ld.we[1];
   // raster-earlier corners of the window (entry 36 is the corner itself): the only entries cache_state looks at
