@@ -1192,7 +1192,7 @@ int brisk_harris_scores(brisk_ctx* ctx, const uint8_t* img, int w, int h, size_t
   CU_OK(launch_harris_score_maxima(g, hw, 1, abs_threshold, sl.flag.as<int>(), sl.stream));
   ctx->launches = 5;
   if (scores) CU_OK(cudaMemcpy2DAsync(scores, (size_t)w * 4, hw.scores + g.L[0].off, (size_t)g.L[0].pitch * 4, (size_t)w * 4, h, cudaMemcpyDeviceToHost, sl.stream));
-  int ls[kMaxLayers + 1] = {0};
+  int ls[2] = {0, 0};   // one layer: its first slot and the total
   CU_OK(cudaMemcpyAsync(ls, hw.det.layer_start, sizeof(ls), cudaMemcpyDeviceToHost, sl.stream));
   CU_OK(cudaStreamSynchronize(sl.stream));
   const int total = ls[1];
