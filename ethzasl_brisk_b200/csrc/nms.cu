@@ -144,9 +144,33 @@ struct TieLoads {
   int2 fp;  // CheckResult::above_steps, above_argmax
 };
 
-__device__ __forceinline__ void tie_issue_loads(const LayerView& L, int mode, int x, int y, const uint8_t* __restrict__ fwin,
-                                                const float* __restrict__ checks, TieLoads* t) {
+// Per-lane offsets (in pixels of the layer's planes) of what a lane fetches for a corner at offset 0: its two entries
+// of the 8x8 corner-map window and its pixel of the 5x5 neighbourhood.  They only change with the layer's pitch.
+struct TieLaneOffsets { int w0, w1, q; };
+__device__ __forceinline__ TieLaneOffsets tie_lane_offsets(int pitch) {
   const int lane = threadIdx.x & 31;
+  TieLaneOffsets o;
+  o.w0 = ((lane >> 3) - 4) * pitch + (lane & 7) - 4;
+  o.w1 = o.w0 + 4 * pitch;                       // entry lane + 32: four rows further down
+  o.q = (lane / 5 - 2) * pitch + lane % 5 - 2;   // (lanes 0..24)
+  return o;
+}
+
+__device__ __forceinline__ void tie_issue_loads(const LayerView& L, const TieLaneOffsets& lo, int mode, int x, int y,
+                                                const uint8_t* __restrict__ fwin, const float* __restrict__ checks, TieLoads* t) {
+  const int lane = threadIdx.x & 31;
+  const int base = y * L.pitch + x;   // (a layer plane is far below 2^31 pixels)
+  // (every lane loads a byte of the corner's 32-byte window record, so that no conversion or merge instruction has to
+  // wait for the load right here: the value is used one corner later)
+  t->F = __ldg(fwin + lane);
+  t->fp = mode == kModeMid ? *reinterpret_cast<const int2*>(checks + 6) : make_int2(0, 0);
+  if (x >= 7 && y >= 7 && x < L.w - 7 && y < L.h - 7) {
+    // interior corner (uniform across the warp): the whole 8x8 window and the 5x5 neighbourhood lie inside the border
+    t->we[0] = L.cm[base + lo.w0];
+    t->we[1] = L.cm[base + lo.w1];
+    t->bmv = lane < 25 ? L.bm[base + lo.q] : 0;
+    return;
+  }
   const int ox = lane % 5 - 2, oy = lane / 5 - 2;  // lanes 0..24 <-> 5x5 offsets, row-major
   t->we[0] = 0; t->we[1] = 0; t->bmv = 0;
 #pragma unroll
@@ -155,11 +179,7 @@ __device__ __forceinline__ void tie_issue_loads(const LayerView& L, int mode, in
     const int px = x - 4 + (i & 7), py = y - 4 + (i >> 3);
     if (py >= 3 && px >= 3 && px < L.w - 3 && py < L.h - 3) t->we[h] = L.cm[(long long)py * L.pitch + px];
   }
-  // (every lane loads a byte of the corner's 32-byte window record, so that no conversion or merge instruction has to
-  // wait for the load right here: the value is used one corner later)
-  t->F = __ldg(fwin + lane);
   if (lane < 25 && !in_border(L, x + ox, y + oy)) t->bmv = L.bm[(long long)(y + oy) * L.pitch + x + ox];
-  t->fp = mode == kModeMid ? *reinterpret_cast<const int2*>(checks + 6) : make_int2(0, 0);
 }
 
 template <int mode>
@@ -333,6 +353,7 @@ nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag
   for (int layer = 0; layer < g.n_layers; ++layer) {
     const int mode = g.n_layers == 1 ? kModeSingle : (layer == g.n_layers - 1 ? kModeLast : kModeMid);
     const LayerView& L = fv.v[layer];
+    const TieLaneOffsets lane_off = tie_lane_offsets(L.pitch);
     int n = ws.n_ties[frame * kTieStride + layer];
     const int2* cur = lists + ls[layer];
     for (int pass = 0; n > 0; ++pass) {
@@ -343,11 +364,11 @@ nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag
       int2 ent = warp < n ? cur[warp] : make_int2(0, 0);
       int2 ent1 = warp + kChainWarps < n ? cur[warp + kChainWarps] : make_int2(0, 0);
       TieLoads ld;
-      if (warp < n) tie_issue_loads(L, mode, ent.y & 0xffff, ent.y >> 16, ws.fwin + (fslot + ent.x) * 32, ws.checks + (fslot + ent.x) * 8, &ld);
+      if (warp < n) tie_issue_loads(L, lane_off, mode, ent.y & 0xffff, ent.y >> 16, ws.fwin + (fslot + ent.x) * 32, ws.checks + (fslot + ent.x) * 8, &ld);
       for (int i = warp; i < n; i += kChainWarps) {
         TieLoads ld1;
         int2 ent2 = make_int2(0, 0);
-        if (i + kChainWarps < n) tie_issue_loads(L, mode, ent1.y & 0xffff, ent1.y >> 16, ws.fwin + (fslot + ent1.x) * 32, ws.checks + (fslot + ent1.x) * 8, &ld1);
+        if (i + kChainWarps < n) tie_issue_loads(L, lane_off, mode, ent1.y & 0xffff, ent1.y >> 16, ws.fwin + (fslot + ent1.x) * 32, ws.checks + (fslot + ent1.x) * 8, &ld1);
         if (i + 2 * kChainWarps < n) ent2 = cur[i + 2 * kChainWarps];
         const int x = ent.y & 0xffff, y = ent.y >> 16;
         const int verdict = mode == kModeMid ? warp_tie_decide<kModeMid>(L, x, y, ld, s_win[warp])
