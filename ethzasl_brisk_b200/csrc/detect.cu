@@ -109,14 +109,18 @@ agast_detect_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restric
   uint16_t* cmap = cm + (long long)frame * frame_elems + L.off;
   const int tid = threadIdx.x;
 
-  // stage tile + halo (zero outside the image; such pixels never reach a valid output)
+  // stage tile + halo (zero outside the image; such pixels never reach a valid output) with asynchronous copies: all of a
+  // thread's 34 words are in flight at once, and the tables below are set up while they arrive (with register-staged
+  // loads, four at a time, a fifth of the kernel's stall samples sat on the stores behind them)
   for (int i = tid; i < kDetSH * (kDetSW / 4); i += kDetThreads) {
     const int r = i / (kDetSW / 4), c = i - r * (kDetSW / 4);
     const int y = y0 - 3 + r, x = x0 - 4 + 4 * c;
-    uint32_t v = 0;
-    if (y >= 0 && y < L.h && x >= 0 && x < L.pitch) v = *reinterpret_cast<const uint32_t*>(img + (long long)y * L.pitch + x);
-    *reinterpret_cast<uint32_t*>(&s_img[r][4 * c]) = v;
+    const bool inside = y >= 0 && y < L.h && x >= 0 && x < L.pitch;
+    const uint8_t* src = inside ? img + (long long)y * L.pitch + x : img;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&s_img[r][4 * c]);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(inside ? 4 : 0) : "memory");   // src-size 0: zero fill
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   {
     // ast-detector.h:62-68 and oast9-16.cc:86-100: no corner where T < (thresh * lower) / 100, else
     // b = (clamp(T, lower, upper) * thresh) / 100
@@ -129,6 +133,7 @@ agast_detect_kernel(LayerGeom L, long long frame_elems, const uint8_t* __restric
   for (int i = tid; i < kDetQueue / 2; i += kDetThreads) reinterpret_cast<uint32_t*>(s_queue)[i] = 0xffffffffu;
   if (tid == 0) s_count = 0;
   if (tid < kDetTH) s_rows[tid] = 0;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
 
   {
