@@ -664,10 +664,11 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
       ctx->launches += 1;
     }
     tm.mark(2);
-    // The integral image only needs layer 0: with a detector in front of the extractor it is built on a side
-    // stream while the detector's kernels run (the tie chain and the per-corner kernels are ALU bound, the integral
-    // image is bandwidth bound).  Not when stage times are being collected.
-    const bool integral_aside = det && ext && !ctx->timing;
+    // The integral image only needs layer 0, so it could be built on a side stream while the detector's kernels run
+    // (BRISK_B200_INTEGRAL_ASIDE=1).  That paid in round 1; with the present kernels it is 1 % slower for resident
+    // batches and even end to end, so the default builds it in line, right before the descriptor kernel.
+    static const bool aside_wanted = getenv("BRISK_B200_INTEGRAL_ASIDE") && atoi(getenv("BRISK_B200_INTEGRAL_ASIDE")) == 1;
+    const bool integral_aside = aside_wanted && det && ext && !ctx->timing;
     if (integral_aside) {
       CU_OK(cudaEventRecord(sl.fork, sl.stream));
       CU_OK(cudaStreamWaitEvent(sl.side, sl.fork, 0));
