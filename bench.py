@@ -352,8 +352,7 @@ def run_frames(args):
 
     # nvidia-smi takes a few hundred ms to deliver its first line: it was started before the warm-up; only the
     # lines of the two timed regions (resident and host end-to-end) count
-    # The headline regions run the library the way a caller does: no per-stage events (with them the integral image is
-    # built in line instead of on its side stream under the detector's kernels).  Stage times come from a separate pass.
+    # The headline regions run the library the way a caller does: no per-stage events.  Stage times come from a separate pass.
     ctx.enable_timing(False)
     for _ in range(args.warmup):
         resident()

@@ -371,3 +371,19 @@ def test_matcher_collection_host_logic():
     _, _, _, _, mask, masked_out = m._collection(q, None, [masks[0], masks[2]])
     assert masked_out.tolist() == [False, True, False, False]
     assert m.isMaskSupported()
+
+
+def test_std_sort_matches_replays_libstdcxx(oracle):
+    # brisk_std_sort_matches (host only): the reference's final std::sort of a match list (brute-force-matcher.cc:160,210);
+    # beyond 16 entries introsort permutes equal distances -- compared with the very std::sort call of the oracle
+    from ethzasl_brisk_b200.api import _ptr, load_library
+    lib = load_library()
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 5, 16, 17, 33, 100, 1000):
+        d = np.sort(rng.integers(150, 150 + max(2, n // 6), n)).astype(np.float32)   # many equal distances, ascending as selected
+        t = rng.permutation(n).astype(np.int32)
+        i = rng.integers(0, 3, n).astype(np.int32)
+        want = oracle._sorted_matches([(7, int(a), int(b), float(c)) for a, b, c in zip(t, i, d)])
+        assert lib.brisk_std_sort_matches(C.c_int64(n), _ptr(t), _ptr(i), _ptr(d)) == 0
+        assert [(7, int(a), int(b), float(c)) for a, b, c in zip(t, i, d)] == want, n
+    assert lib.brisk_std_sort_matches(C.c_int64(-1), None, None, None) != 0
