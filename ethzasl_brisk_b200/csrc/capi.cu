@@ -816,6 +816,7 @@ int brisk_ctx_create(int device, void* stream, brisk_ctx** out) {
 void brisk_ctx_destroy(brisk_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
+  if (ctx->deferred.active) drain_async(ctx);   // an asynchronous call's last chunk still goes to the caller's buffers
   cudaStreamSynchronize(ctx->stream);
   for (Slot& sl : ctx->slots) {
     if (sl.stream) cudaStreamSynchronize(sl.stream);
