@@ -350,6 +350,7 @@ corner_fill_kernel(LayerGeom L, int layer, long long frame_elems, const uint16_t
     const int x = xb + 8 * lane;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (x < L.pitch) v = *reinterpret_cast<const uint4*>(row + x);
+    if (!__ballot_sync(0xffffffffu, (v.x | v.y | v.z | v.w) != 0)) continue;   // 256 empty entries: the common case
     const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
     uint32_t m8 = 0;
 #pragma unroll
