@@ -44,7 +44,13 @@ __device__ __forceinline__ void unpack_corner(uint32_t c, int* x, int* y, int* l
   *x = c & 0x1fff; *y = (c >> 13) & 0x1fff; *layer = c >> 26;
 }
 
-__global__ void __launch_bounds__(128, 4)
+#ifndef BRISK_PREFIX_MINB
+#define BRISK_PREFIX_MINB 5
+#endif
+#ifndef BRISK_CHECKS_MINB
+#define BRISK_CHECKS_MINB 5
+#endif
+__global__ void __launch_bounds__(128, BRISK_PREFIX_MINB)
 nms_prefix_kernel(PyramidGeom g, DetectWorkspace ws) {
   const int frame = blockIdx.y, lane = threadIdx.x & 31;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -295,7 +301,7 @@ __device__ __forceinline__ void warp_mark_above(const LayerView& nb, int layer, 
   mark_above_strided(nb, layer, x, y, above_steps, above_argmax, threadIdx.x & 31, 32);
 }
 
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, BRISK_CHECKS_MINB)
 nms_checks_kernel(PyramidGeom g, DetectWorkspace ws) {
   const int frame = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
