@@ -340,7 +340,10 @@ nms_checks_kernel(PyramidGeom g, DetectWorkspace ws) {
 // always decidable, so every pass makes progress.
 // Two 512-thread CTAs per SM: the passes of one frame (barriers, short lists on the upper layers) leave the SM idle
 // part of the time; a second frame fills those gaps (12.8 -> 9.0 ms per 1024 frames against one 1024-thread CTA).
-constexpr int kChainThreads = 512;
+#ifndef BRISK_CHAIN_THREADS
+#define BRISK_CHAIN_THREADS 512
+#endif
+constexpr int kChainThreads = BRISK_CHAIN_THREADS;
 constexpr int kChainWarps = kChainThreads / 32;
 __global__ void __launch_bounds__(kChainThreads, 1024 / kChainThreads)
 nms_chain_kernel(PyramidGeom g, DetectWorkspace ws, int* __restrict__ error_flag) {
