@@ -77,7 +77,8 @@ struct brisk_ctx {
   size_t ws_limit = (size_t)8 << 30;
   bool timing = false;
   bool pipelining = true;
-  int knn_variant = 2;  // 0: POPC kernel always; where they apply (k == 2, 48/64-byte rows) 1: mma.sync IMMA kernel, 2 (default): tcgen05 kernel
+  int knn_variant = 3;  // 0: POPC kernel always; where they apply (k == 2, 48/64-byte rows) 1: mma.sync IMMA kernel, 2: tcgen05 kind::i8 kernel,
+                        // 3 (default): tcgen05 kind::mxf4 (FP4) kernel for 64-byte rows, the kind::i8 one for 48-byte rows
   float ms[BRISK_STAGE_COUNT] = {};
   int64_t launches = 0;
   int64_t raw_corners = 0;  // AGAST corners before NMS, summed over the frames of the last call (timing mode only)
@@ -855,7 +856,7 @@ int brisk_ctx_set_workspace_limit(brisk_ctx* ctx, size_t bytes) {
 }
 
 int brisk_ctx_set_knn_variant(brisk_ctx* ctx, int variant) {
-  if (!ctx || variant < 0 || variant > 2) return BRISK_ERR_INVALID;
+  if (!ctx || variant < 0 || variant > 3) return BRISK_ERR_INVALID;
   ctx->knn_variant = variant;
   return BRISK_OK;
 }
@@ -1455,12 +1456,27 @@ static int knn_keys_impl(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const
   }
   const int kr = knn_round_k(k);
   const bool tensor = k == 2 && (desc_bytes == 48 || desc_bytes == 64);
-  const bool mma = ctx->knn_variant == 1 && tensor, tc5 = ctx->knn_variant == 2 && tensor && nq > 0 && nt > 0;
-  const int splits = tc5 ? knn_tc5_num_splits(nq, nt) : (mma ? knn_mma_num_splits(nq, nt) : knn_num_splits(nq, nt));
+  const bool mx4 = ctx->knn_variant == 3 && k == 2 && desc_bytes == 64 && nq > 0 && nt > 0;   // FP4 form: 64-byte rows only
+  const bool mma = ctx->knn_variant == 1 && tensor, tc5 = (ctx->knn_variant == 2 || (ctx->knn_variant == 3 && !mx4)) && tensor && nq > 0 && nt > 0;
+  const int splits = (tc5 || mx4) ? knn_tc5_num_splits(nq, nt) : (mma ? knn_mma_num_splits(nq, nt) : knn_num_splits(nq, nt));
   CU_OK(ctx->knn_keys.ensure(std::max<size_t>((size_t)nq * kr * 8, 16)));
   if (splits > 1) CU_OK(ctx->knn_part.ensure((size_t)splits * nq * kr * 8));
   if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);
-  if (tc5) {
+  if (mx4) {
+    // descriptor bits -> E2M1 +-1.0 once per call (4x the rows in HBM), then the block-scaled FP4 tcgen05 kernel
+    CU_OK(ctx->knn_tx.ensure(knn_tc5mx_expanded_bytes(nt, desc_bytes)));
+    CU_OK(launch_expand_e2m1(dt, nt, desc_bytes, ctx->knn_tx.as<uint8_t>(), ctx->stream));
+    CU_OK(ctx->knn_qx.ensure(knn_tc5mx_expanded_bytes(nq, desc_bytes)));
+    CU_OK(launch_expand_e2m1(dq, nq, desc_bytes, ctx->knn_qx.as<uint8_t>(), ctx->stream));
+    CUtensorMap mq, mt;
+    int rc = encode_rows_map(ctx, ctx->knn_tx.p, nt, desc_bytes * 4, knn_tc5mx_tile_rows(), &mt);
+    if (rc) return rc;
+    rc = encode_rows_map(ctx, ctx->knn_qx.p, nq, desc_bytes * 4, 128, &mq);
+    if (rc) return rc;
+    CU_OK(launch_hamming_knn2_tc5mx(mq, nq, mt, nt, desc_bytes, offset, ctx->knn_keys.as<unsigned long long>(),
+                                    ctx->knn_part.as<unsigned long long>(), splits, ctx->stream));
+    ctx->launches = 2;
+  } else if (tc5) {
     // descriptor bits -> signed bytes once per call (8x the rows in HBM), then the tcgen05 kernel on TMA-staged tiles
     const bool ts = knn_tc5_queries_in_tmem() != 0;
     CU_OK(ctx->knn_tx.ensure(knn_tc5_expanded_bytes(nt, desc_bytes)));

@@ -449,6 +449,244 @@ hamming_knn2_tc5ts_kernel(const uint8_t* __restrict__ q, const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------
+// FP4 form (tcgen05.mma kind::mxf4.block_scale): every descriptor bit becomes one E2M1 value, +1.0 (0x2) for a set bit and
+// -1.0 (0xA) for a clear one, two per byte -- half the operand bytes of the signed-byte form and K = 64 per instruction at
+// the same issue cost, which is what matters for a kernel that sits on the chip's power limit.  The block scale factors
+// the instruction insists on are all 1.0 (UE8M0 0x7F): their TMEM region is filled with that byte once per CTA, so their
+// layout does not matter.  Accumulators are FP32 (exact: |dot| <= 512).  Train tiles of 96 rows: four accumulators of 96
+// columns leave 128 TMEM columns for the scale factors.  64-byte rows only (K = 512 = two 128-byte chunks of 256 values).
+// ---------------------------------------------------------------------------
+#ifndef BRISK_MX_N
+#define BRISK_MX_N 96
+#endif
+constexpr int kMxN = BRISK_MX_N, kMxColSF = 4 * kMxN;   // accumulators at 0 .. 4 N - 1, scale factors behind them (N = 96: 384 .. 511)
+constexpr int kMxSfCols = (512 - kMxColSF) / 2;      // columns per scale-factor operand
+static_assert(kMxN % 32 == 0 && kMxColSF + 64 <= 512, "the epilogue reads groups of 32 columns; the scale factors need room");
+
+// Instruction descriptor, block-scaled kinds (cute/arch/mma_sm100_desc.hpp InstrDescriptorBlockScaled): A = B = E2M1, which is
+// format 1 for kind::mxf4 (1 << 7, 1 << 10; 5 is its code under kind::mxf8f6f4), both K-major, N >> 3 in bits 17-22, scale format UE8M0 (1 << 23), M >> 4 in bits 24-28, scale-factor ids 0, K = 64.
+__host__ __device__ constexpr uint32_t mx_idesc(int n) {
+  return (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(kT5M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate,
+                                          uint32_t sfa_tmem, uint32_t sfb_tmem) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+      : "memory");
+}
+
+template <int KC>
+__global__ void __launch_bounds__(kT5Threads, 1)
+hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, long long nq,
+                          long long nt, long long rows_per_split, long long train_index_offset,
+                          unsigned long long* __restrict__ part) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  constexpr int kN = kMxN, kChunkBytes = kN * kT5Chunk, kStages = kT5RingBytes / kChunkBytes;   // 8 stages of 12 KB
+  constexpr uint32_t kIdesc = mx_idesc(kN);
+  uint8_t* sA = smem;                                         // [2 tiles][KC chunks][128 rows x 128 B]
+  uint8_t* sB = sA + kT5QTiles * KC * kT5AChunkBytes;         // [stages][96 rows x 128 B]
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + kStages * kChunkBytes);
+  uint64_t* bar_empty = bar_full + kStages;
+  uint64_t* bar_a = bar_empty + kStages;
+  uint64_t* bar_tfull = bar_a + 1;       // [2] accumulator set ready for the epilogue
+  uint64_t* bar_tempty = bar_tfull + 2;  // [2] accumulator set drained
+  uint64_t* bar_sf = bar_tempty + 2;     // scale factors written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_sf + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long q0 = (long long)blockIdx.x * (kT5QTiles * kT5M);
+  const long long t_begin = (long long)blockIdx.y * rows_per_split;
+  const long long t_end = min(nt, t_begin + rows_per_split);
+  const int ntiles = t_end > t_begin ? (int)((t_end - t_begin + kN - 1) / kN) : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+    mbar_init(bar_a, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], kT5EpiWarps); }
+    mbar_init(bar_sf, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kT5TmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- TMA producer ----
+    if (lane == 0 && ntiles > 0) {
+      mbar_expect_tx(bar_a, kT5QTiles * KC * kT5AChunkBytes);
+      for (int a = 0; a < kT5QTiles; ++a)
+        for (int c = 0; c < KC; ++c) tma_load_2d(sA + (a * KC + c) * kT5AChunkBytes, &map_q, c * kT5Chunk, (int)(q0 + a * kT5M), bar_a);
+      int it = 0;
+      for (int i = 0; i < ntiles; ++i)
+        for (int c = 0; c < KC; ++c, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&bar_empty[s], ((it / kStages) & 1) ^ 1);
+          mbar_expect_tx(&bar_full[s], kChunkBytes);
+          tma_load_2d(sB + s * kChunkBytes, &map_t, c * kT5Chunk, (int)(t_begin + (long long)i * kN), &bar_full[s]);
+        }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer (one thread) ----
+    if (lane == 0 && ntiles > 0) {
+      mbar_wait(bar_a, 0);
+      mbar_wait(bar_sf, 0);
+      tc_fence_after();
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      const uint32_t sfa = tmem_base + kMxColSF, sfb = tmem_base + kMxColSF + kMxSfCols;
+      int it = 0;
+      for (int i = 0; i < ntiles; ++i) {
+        const int b = i & 1;
+        mbar_wait(&bar_tempty[b], ((i >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int c = 0; c < KC; ++c, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&bar_full[s], (it / kStages) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < kT5Chunk / 32; ++k) {   // 32 bytes = 64 values per instruction
+            const uint64_t bd = umma_desc(b_base + s * kChunkBytes + k * 32);
+#pragma unroll
+            for (int a = 0; a < kT5QTiles; ++a)
+              umma_mxf4(tmem_base + (uint32_t)((b * kT5QTiles + a) * kN), umma_desc(a_base + (a * KC + c) * kT5AChunkBytes + k * 32), bd,
+                        kIdesc, (c | k) != 0 ? 1u : 0u, sfa, sfb);
+          }
+          umma_commit(&bar_empty[s]);
+        }
+        umma_commit(&bar_tfull[b]);
+      }
+    }
+  } else {
+    // ---- epilogue: thread = one query row ----
+    const int quad = warp & 3, a = (warp - 2) >> 2;
+    const int row = a * kT5M + quad * 32 + lane;
+    if (a == 0) {
+      // scale factors: 1.0 everywhere (UE8M0 0x7f), all 128 lanes x 128 columns of the region
+      uint32_t ones[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) ones[j] = 0x7f7f7f7fu;
+#pragma unroll
+      for (int j = 0; j < (512 - kMxColSF) / 32; ++j) tmem_st32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kMxColSF + 32 * j), ones);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_sf);
+    }
+    float d0 = -1.0e9f, d1 = -1.0e9f;     // two largest dot products so far (d0 >= d1) ...
+    unsigned i0 = 0xffffffffu, i1 = 0xffffffffu;  // ... and their (global) train indices
+    for (int i = 0; i < ntiles; ++i) {
+      const int b = i & 1;
+      mbar_wait(&bar_tfull[b], (i >> 1) & 1);
+      tc_fence_after();
+      const long long tile_base = t_begin + (long long)i * kN;
+      const int valid = (int)min((long long)kN, t_end - tile_base);
+      const unsigned idx_base = (unsigned)(train_index_offset + tile_base);
+#pragma unroll 1
+      for (int cc = 0; cc < kN / 32; ++cc) {
+        int vi[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((b * kT5QTiles + a) * kN + cc * 32), vi);
+        float m = fmaxf(fmaxf(__int_as_float(vi[0]), __int_as_float(vi[1])), __int_as_float(vi[2]));
+#pragma unroll
+        for (int j = 3; j + 1 < 32; j += 2) m = fmaxf(fmaxf(m, __int_as_float(vi[j])), __int_as_float(vi[j + 1]));
+        m = fmaxf(m, __int_as_float(vi[31]));
+        if (m > d1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = cc * 32 + j;
+            const float v = __int_as_float(vi[j]);
+            if (v > d1 && col < valid) {
+              if (v > d0) { d1 = d0; i1 = i0; d0 = v; i0 = idx_base + col; }
+              else { d1 = v; i1 = idx_base + col; }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_tempty[b]);
+    }
+    if (q0 + row < nq) {
+      constexpr int kBits = KC * kT5Chunk * 2;   // two values per byte
+      unsigned long long* out = part + ((long long)blockIdx.y * nq + q0 + row) * 2;
+      out[0] = i0 == 0xffffffffu ? kT5KeyNone : ((unsigned long long)((kBits - (int)d0) >> 1) << 32) | i0;
+      out[1] = i1 == 0xffffffffu ? kT5KeyNone : ((unsigned long long)((kBits - (int)d1) >> 1) << 32) | i1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kT5TmemCols) : "memory");
+  }
+}
+
+// Descriptor bits -> E2M1 values (+1.0 = 0x2 for a set bit, -1.0 = 0xA for a clear one), bit i of a byte in nibble i:
+// four output bytes per input byte.
+__global__ void __launch_bounds__(256)
+expand_e2m1_kernel(const uint32_t* __restrict__ src, long long n_words, uint4* __restrict__ dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_words) return;
+  const uint32_t w = __ldg(src + i);
+  uint32_t o[4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const uint32_t byte = (w >> (8 * n)) & 0xffu;
+    // bit i -> bit 4 i + 3 (the sign of nibble i): spread the byte's bits four apart
+    uint32_t sp = (byte | (byte << 12)) & 0x000f000fu;   // bits 0..3 | bits 4..7 at 16
+    sp = (sp | (sp << 6)) & 0x03030303u;                 // two bits per byte
+    sp = (sp | (sp << 3)) & 0x11111111u;                 // one bit per nibble
+    o[n] = 0x22222222u | ((~sp & 0x11111111u) << 3);     // set -> 0x2, clear -> 0xA
+  }
+  dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+size_t knn_tc5mx_expanded_bytes(long long rows, int desc_bytes) {
+  const long long r = rows < 256 ? 256 : rows;
+  return (size_t)r * desc_bytes * 4;
+}
+int knn_tc5mx_tile_rows() { return kMxN; }
+
+cudaError_t launch_expand_e2m1(const uint8_t* src, long long rows, int desc_bytes, uint8_t* dst, cudaStream_t stream) {
+  const long long n_words = rows * desc_bytes / 4;
+  if (n_words <= 0) return cudaSuccess;
+  expand_e2m1_kernel<<<(unsigned)((n_words + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(src), n_words,
+                                                                              reinterpret_cast<uint4*>(dst));
+  return cudaGetLastError();
+}
+
+// k == 2, 64-byte rows; map_q (128-row boxes) / map_t (96-row boxes): tensor maps over the E2M1-expanded rows (256 bytes each).
+cudaError_t launch_hamming_knn2_tc5mx(const CUtensorMap& map_q, long long nq, const CUtensorMap& map_t, long long nt, int desc_bytes,
+                                      long long train_index_offset, unsigned long long* keys, unsigned long long* part,
+                                      int splits, cudaStream_t stream) {
+  if (nq <= 0) return cudaSuccess;
+  if (desc_bytes != 64) return cudaErrorInvalidValue;
+  if (nt <= 0) return cudaMemsetAsync(keys, 0xff, (size_t)nq * 2 * 8, stream);
+  long long rows_per_split = ((nt + splits - 1) / splits + kMxN - 1) / kMxN * kMxN;
+  if (rows_per_split <= 0) rows_per_split = kMxN;
+  unsigned long long* dst = splits == 1 ? keys : part;
+  constexpr int KC = 2;
+  const size_t smem = (size_t)kT5QTiles * KC * kT5AChunkBytes + kT5RingBytes + 1024 /* alignment */ + 512 /* barriers */;
+  cudaError_t e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  dim3 grid((unsigned)((nq + kT5QTiles * kT5M - 1) / (kT5QTiles * kT5M)), splits);
+  hamming_knn2_tc5mx_kernel<KC><<<grid, kT5Threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (splits > 1) e = launch_knn_merge(part, splits, nq, 2, keys, stream);
+  return e;
+}
+
 // Descriptor bits -> signed bytes (+1 / -1), 32 per input word.
 __global__ void __launch_bounds__(256)
 expand_pm1_kernel(const uint32_t* __restrict__ src, long long n_words, uint4* __restrict__ dst) {

@@ -162,6 +162,14 @@ cudaError_t launch_hamming_knn2_tc5(const CUtensorMap& map_q, long long nq, cons
                                     int splits, cudaStream_t stream);
 // The same with the queries in TMEM (raw descriptor rows in, expanded by the kernel): measured alternative, BRISK_B200_TC5_MODE=ts.
 int knn_tc5_queries_in_tmem();
+// FP4 form (tcgen05.mma kind::mxf4.block_scale, E2M1 +-1.0 operands, unit scale factors): 64-byte rows, k = 2, train tiles
+// of knn_tc5mx_tile_rows() rows; operands expanded to 4 bits per descriptor bit (256 bytes per row).
+size_t knn_tc5mx_expanded_bytes(long long rows, int desc_bytes);
+int knn_tc5mx_tile_rows();
+cudaError_t launch_expand_e2m1(const uint8_t* src, long long rows, int desc_bytes, uint8_t* dst, cudaStream_t stream);
+cudaError_t launch_hamming_knn2_tc5mx(const CUtensorMap& map_q, long long nq, const CUtensorMap& map_t, long long nt, int desc_bytes,
+                                      long long train_index_offset, unsigned long long* keys, unsigned long long* part,
+                                      int splits, cudaStream_t stream);
 cudaError_t launch_hamming_knn2_tc5ts(const uint8_t* q, long long nq, const CUtensorMap& map_t, long long nt, int desc_bytes,
                                       long long train_index_offset, unsigned long long* keys, unsigned long long* part,
                                       int splits, cudaStream_t stream);

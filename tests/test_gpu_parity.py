@@ -939,8 +939,9 @@ def test_matcher_any_width_any_k(ctx, matcher_oracle):
 
 @pytest.mark.parametrize("nbytes", [48, 64])
 def test_knn_tensor_core_variants_match_popc(oracle, nbytes):
-    # the tcgen05 kernel (variant 2, the default: kind::i8 MMAs on +-1 bytes, TMEM accumulators, TMA operands) and the
-    # mma.sync IMMA kernel (variant 1) must return exactly what the POPC kernel returns: ties, missing rows, ragged
+    # the tcgen05 kernels (variant 3, the default: kind::mxf4 MMAs on +-1.0 E2M1 values for 64-byte rows; variant 2: kind::i8
+    # MMAs on +-1 bytes; TMEM accumulators, TMA operands) and the mma.sync IMMA kernel (variant 1) must return exactly what
+    # the POPC kernel returns: ties, missing rows, ragged
     # tiles, one or several train splits, queries / train rows that are no multiple of the tile sizes
     ctx2 = bb.Context(0)
     m = bb.BruteForceMatcher(ctx=ctx2)
@@ -953,20 +954,21 @@ def test_knn_tensor_core_variants_match_popc(oracle, nbytes):
             t[nt - 1] = q[3]
             t[150] = q[4]; t[150, 0] ^= 1   # distance 1
         res = []
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3):
             ctx2.set_knn_variant(variant)
             res.append(m.knn(q, t, 2))
-        for variant in (1, 2):
+        for variant in (1, 2, 3):
             assert np.array_equal(res[0][0], res[variant][0]) and np.array_equal(res[0][1], res[variant][1]), (nq, nt, variant)
     i2, d2 = oracle.knn(q, t, 2)
     assert np.array_equal(res[2][0], i2) and np.array_equal(res[2][1], d2)
     # tie-rich rows (few distinct distances): the index tie rule across tiles and splits
     q = _tie_rich_descriptors(300, nbytes, 1)
     t = _tie_rich_descriptors(40000, nbytes, 2)
-    ctx2.set_knn_variant(2)
-    i1, d1 = m.knn(q, t, 2)
     i2, d2 = oracle.knn(q, t, 2)
-    assert np.array_equal(i1, i2) and np.array_equal(d1, d2)
+    for variant in (2, 3):
+        ctx2.set_knn_variant(variant)
+        i1, d1 = m.knn(q, t, 2)
+        assert np.array_equal(i1, i2) and np.array_equal(d1, d2), variant
 
 
 def test_knn_tcgen05_alternative_forms():

@@ -18,7 +18,7 @@ def main():
         q = torch.from_numpy(bb.random_descriptors(nq, nbytes, 5)).cuda()
         t = torch.from_numpy(bb.random_descriptors(nt, nbytes, 6)).cuda()
         res = []
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3):
             ctx.set_knn_variant(variant)
             m.knn(q, t, 2)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -51,11 +51,11 @@ def main():
     m = bb.BruteForceMatcher(ctx=ctx)
     for nb in (48, 64):
         q, t = bb.random_descriptors(300, nb, 1), bb.random_descriptors(9000, nb, 2)
-        for variant in (0, 1, 2):
+        for variant in (0, 1, 2, 3):
             ctx.set_knn_variant(variant)
             idx, dist = m.knn(q, t, 2)
-        print(f"knn {nb} bytes, three kernels:", int(dist.sum()))
-    ctx.set_knn_variant(2)
+        print(f"knn {nb} bytes, four kernels:", int(dist.sum()))
+    ctx.set_knn_variant(3)
     q, t = bb.random_descriptors(100, 64, 3), bb.random_descriptors(700, 64, 4)
     idx, dist = m.knn(q, t, 5)
     tm = (np.arange(100)[:, None] + np.arange(700)[None, :]) % 3 != 0
