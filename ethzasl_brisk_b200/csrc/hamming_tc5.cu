@@ -457,13 +457,12 @@ hamming_knn2_tc5ts_kernel(const uint8_t* __restrict__ q, const __grid_constant__
 // layout does not matter.  Accumulators are FP32 (exact: |dot| <= 512).  Train tiles of 96 rows: four accumulators of 96
 // columns leave 128 TMEM columns for the scale factors.  64-byte rows only (K = 512 = two 128-byte chunks of 256 values).
 // ---------------------------------------------------------------------------
-#ifndef BRISK_MX_N
-#define BRISK_MX_N 96
-#endif
-constexpr int kMxN = BRISK_MX_N, kMxColSF = 4 * kMxN;   // accumulators at 0 .. 4 N - 1, scale factors behind them (N = 96: 384 .. 511)
-constexpr int kMxSfCols = (512 - kMxColSF) / 2;      // columns per scale-factor operand
-static_assert(kMxN % 32 == 0 && kMxColSF + 64 <= 512, "the epilogue reads groups of 32 columns; the scale factors need room");
-
+// Two schedules.  ALT = false: train tiles of 96 rows, two accumulator sets of two (one per query tile), the epilogue of
+// tile i under the MMAs of tile i + 1 (4 x 96 columns + 128 for the scale factors).  ALT = true: train tiles of 192 rows, ONE
+// accumulator per query tile; per train tile the issuer runs all K steps of query tile 0, then all of query tile 1, so that
+// each accumulator is drained while the other one is computed (2 x 192 columns + 128).  The wide tile reads the 4 KB A slice
+// once per 128 x 192 x 64 instruction instead of once per 128 x 96 x 64: 10 KB of shared memory per 96 tensor cycles
+// instead of 7 KB per 48, which is what the narrow form is bound by.
 // Instruction descriptor, block-scaled kinds (cute/arch/mma_sm100_desc.hpp InstrDescriptorBlockScaled): A = B = E2M1, which is
 // format 1 for kind::mxf4 (1 << 7, 1 << 10; 5 is its code under kind::mxf8f6f4), both K-major, N >> 3 in bits 17-22, scale format UE8M0 (1 << 23), M >> 4 in bits 24-28, scale-factor ids 0, K = 64.
 __host__ __device__ constexpr uint32_t mx_idesc(int n) {
@@ -480,14 +479,16 @@ __device__ __forceinline__ void umma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint
       : "memory");
 }
 
-template <int KC>
+template <int KC, int NT, bool ALT>
 __global__ void __launch_bounds__(kT5Threads, 1)
 hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, long long nq,
                           long long nt, long long rows_per_split, long long train_index_offset,
                           unsigned long long* __restrict__ part) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  constexpr int kN = kMxN, kChunkBytes = kN * kT5Chunk, kStages = kT5RingBytes / kChunkBytes;   // 8 stages of 12 KB
+  constexpr int kN = NT, kChunkBytes = kN * kT5Chunk, kStages = kT5RingBytes / kChunkBytes;   // 8 stages of 12 KB / 4 of 24 KB
+  constexpr int kMxColSF = (ALT ? 2 : 4) * kN;   // accumulators in front, scale factors behind them
+  static_assert(kN % 32 == 0 && kMxColSF + 128 <= 512, "the epilogue reads groups of 32 columns; the scale factors need room");
   constexpr uint32_t kIdesc = mx_idesc(kN);
   uint8_t* sA = smem;                                         // [2 tiles][KC chunks][128 rows x 128 B]
   uint8_t* sB = sA + kT5QTiles * KC * kT5AChunkBytes;         // [stages][96 rows x 128 B]
@@ -508,7 +509,7 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
     mbar_init(bar_a, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], kT5EpiWarps); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], ALT ? kT5EpiWarps / 2 : kT5EpiWarps); }
     mbar_init(bar_sf, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -544,27 +545,47 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       mbar_wait(bar_sf, 0);
       tc_fence_after();
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-      const uint32_t sfa = tmem_base + kMxColSF, sfb = tmem_base + kMxColSF + kMxSfCols;
-      int it = 0;
-      for (int i = 0; i < ntiles; ++i) {
-        const int b = i & 1;
-        mbar_wait(&bar_tempty[b], ((i >> 1) & 1) ^ 1);
-        tc_fence_after();
-        for (int c = 0; c < KC; ++c, ++it) {
-          const int s = it % kStages;
-          mbar_wait(&bar_full[s], (it / kStages) & 1);
-          tc_fence_after();
+      const uint32_t sfa = tmem_base + kMxColSF, sfb = tmem_base + kMxColSF + 64;
+      if (ALT) {
+        for (int i = 0; i < ntiles; ++i) {
+#pragma unroll 1
+          for (int a = 0; a < kT5QTiles; ++a) {
+            mbar_wait(&bar_tempty[a], (i & 1) ^ 1);
+            tc_fence_after();
+            for (int c = 0; c < KC; ++c) {
+              const int it = i * KC + c, s = it % kStages;
+              if (a == 0) { mbar_wait(&bar_full[s], (it / kStages) & 1); tc_fence_after(); }
 #pragma unroll
-          for (int k = 0; k < kT5Chunk / 32; ++k) {   // 32 bytes = 64 values per instruction
-            const uint64_t bd = umma_desc(b_base + s * kChunkBytes + k * 32);
-#pragma unroll
-            for (int a = 0; a < kT5QTiles; ++a)
-              umma_mxf4(tmem_base + (uint32_t)((b * kT5QTiles + a) * kN), umma_desc(a_base + (a * KC + c) * kT5AChunkBytes + k * 32), bd,
-                        kIdesc, (c | k) != 0 ? 1u : 0u, sfa, sfb);
+              for (int k = 0; k < kT5Chunk / 32; ++k)
+                umma_mxf4(tmem_base + (uint32_t)(a * kN), umma_desc(a_base + (a * KC + c) * kT5AChunkBytes + k * 32),
+                          umma_desc(b_base + s * kChunkBytes + k * 32), kIdesc, (c | k) != 0 ? 1u : 0u, sfa, sfb);
+              if (a == kT5QTiles - 1) umma_commit(&bar_empty[s]);   // both query tiles have read the chunk
+            }
+            umma_commit(&bar_tfull[a]);
           }
-          umma_commit(&bar_empty[s]);
         }
-        umma_commit(&bar_tfull[b]);
+      } else {
+        int it = 0;
+        for (int i = 0; i < ntiles; ++i) {
+          const int b = i & 1;
+          mbar_wait(&bar_tempty[b], ((i >> 1) & 1) ^ 1);
+          tc_fence_after();
+          for (int c = 0; c < KC; ++c, ++it) {
+            const int s = it % kStages;
+            mbar_wait(&bar_full[s], (it / kStages) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < kT5Chunk / 32; ++k) {   // 32 bytes = 64 values per instruction
+              const uint64_t bd = umma_desc(b_base + s * kChunkBytes + k * 32);
+#pragma unroll
+              for (int a = 0; a < kT5QTiles; ++a)
+                umma_mxf4(tmem_base + (uint32_t)((b * kT5QTiles + a) * kN), umma_desc(a_base + (a * KC + c) * kT5AChunkBytes + k * 32), bd,
+                          kIdesc, (c | k) != 0 ? 1u : 0u, sfa, sfb);
+            }
+            umma_commit(&bar_empty[s]);
+          }
+          umma_commit(&bar_tfull[b]);
+        }
       }
     }
   } else {
@@ -577,7 +598,7 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
 #pragma unroll
       for (int j = 0; j < 32; ++j) ones[j] = 0x7f7f7f7fu;
 #pragma unroll
-      for (int j = 0; j < (512 - kMxColSF) / 32; ++j) tmem_st32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kMxColSF + 32 * j), ones);
+      for (int j = 0; j < 4; ++j) tmem_st32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(kMxColSF + 32 * j), ones);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
@@ -586,16 +607,17 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     float d0 = -1.0e9f, d1 = -1.0e9f;     // two largest dot products so far (d0 >= d1) ...
     unsigned i0 = 0xffffffffu, i1 = 0xffffffffu;  // ... and their (global) train indices
     for (int i = 0; i < ntiles; ++i) {
-      const int b = i & 1;
-      mbar_wait(&bar_tfull[b], (i >> 1) & 1);
+      const int b = ALT ? a : (i & 1);                       // barrier pair: per query tile / per accumulator set
+      mbar_wait(&bar_tfull[b], ALT ? (i & 1) : ((i >> 1) & 1));
       tc_fence_after();
       const long long tile_base = t_begin + (long long)i * kN;
       const int valid = (int)min((long long)kN, t_end - tile_base);
       const unsigned idx_base = (unsigned)(train_index_offset + tile_base);
+      const uint32_t acc_col = ALT ? (uint32_t)(a * kN) : (uint32_t)((b * kT5QTiles + a) * kN);
 #pragma unroll 1
       for (int cc = 0; cc < kN / 32; ++cc) {
         int vi[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((b * kT5QTiles + a) * kN + cc * 32), vi);
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc_col + (uint32_t)(cc * 32), vi);
         float m = fmaxf(fmaxf(__int_as_float(vi[0]), __int_as_float(vi[1])), __int_as_float(vi[2]));
 #pragma unroll
         for (int j = 3; j + 1 < 32; j += 2) m = fmaxf(fmaxf(m, __int_as_float(vi[j])), __int_as_float(vi[j + 1]));
@@ -655,7 +677,11 @@ size_t knn_tc5mx_expanded_bytes(long long rows, int desc_bytes) {
   const long long r = rows < 256 ? 256 : rows;
   return (size_t)r * desc_bytes * 4;
 }
-int knn_tc5mx_tile_rows() { return kMxN; }
+// Train rows per tile: 192 (default, one accumulator per query tile) or 96 (BRISK_B200_TC5MX_TILE_ROWS=96: two accumulator sets).
+int knn_tc5mx_tile_rows() {
+  static const int rows = [] { const char* e = getenv("BRISK_B200_TC5MX_TILE_ROWS"); return e && atoi(e) == 96 ? 96 : 192; }();
+  return rows;
+}
 
 cudaError_t launch_expand_e2m1(const uint8_t* src, long long rows, int desc_bytes, uint8_t* dst, cudaStream_t stream) {
   const long long n_words = rows * desc_bytes / 4;
@@ -672,15 +698,23 @@ cudaError_t launch_hamming_knn2_tc5mx(const CUtensorMap& map_q, long long nq, co
   if (nq <= 0) return cudaSuccess;
   if (desc_bytes != 64) return cudaErrorInvalidValue;
   if (nt <= 0) return cudaMemsetAsync(keys, 0xff, (size_t)nq * 2 * 8, stream);
-  long long rows_per_split = ((nt + splits - 1) / splits + kMxN - 1) / kMxN * kMxN;
-  if (rows_per_split <= 0) rows_per_split = kMxN;
+  const int tile = knn_tc5mx_tile_rows();
+  long long rows_per_split = ((nt + splits - 1) / splits + tile - 1) / tile * tile;
+  if (rows_per_split <= 0) rows_per_split = tile;
   unsigned long long* dst = splits == 1 ? keys : part;
   constexpr int KC = 2;
   const size_t smem = (size_t)kT5QTiles * KC * kT5AChunkBytes + kT5RingBytes + 1024 /* alignment */ + 512 /* barriers */;
-  cudaError_t e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
   dim3 grid((unsigned)((nq + kT5QTiles * kT5M - 1) / (kT5QTiles * kT5M)), splits);
-  hamming_knn2_tc5mx_kernel<KC><<<grid, kT5Threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst);
+  cudaError_t e;
+  if (tile == 192) {
+    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 192, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hamming_knn2_tc5mx_kernel<KC, 192, true><<<grid, kT5Threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst);
+  } else {
+    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hamming_knn2_tc5mx_kernel<KC, 96, false><<<grid, kT5Threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst);
+  }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (splits > 1) e = launch_knn_merge(part, splits, nq, 2, keys, stream);
