@@ -1456,7 +1456,7 @@ static int knn_keys_impl(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const
   }
   const int kr = knn_round_k(k);
   const bool tensor = k == 2 && (desc_bytes == 48 || desc_bytes == 64);
-  const bool mx4 = ctx->knn_variant == 3 && k == 2 && desc_bytes == 64 && nq > 0 && nt > 0;   // FP4 form: 64-byte rows only
+  const bool mx4 = ctx->knn_variant == 3 && tensor && nq > 0 && nt > 0;   // FP4 form
   const bool mma = ctx->knn_variant == 1 && tensor, tc5 = (ctx->knn_variant == 2 || (ctx->knn_variant == 3 && !mx4)) && tensor && nq > 0 && nt > 0;
   const int splits = (tc5 || mx4) ? knn_tc5_num_splits(nq, nt) : (mma ? knn_mma_num_splits(nq, nt) : knn_num_splits(nq, nt));
   CU_OK(ctx->knn_keys.ensure(std::max<size_t>((size_t)nq * kr * 8, 16)));

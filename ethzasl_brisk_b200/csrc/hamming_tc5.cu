@@ -455,7 +455,8 @@ hamming_knn2_tc5ts_kernel(const uint8_t* __restrict__ q, const __grid_constant__
 // the same issue cost, which is what matters for a kernel that sits on the chip's power limit.  The block scale factors
 // the instruction insists on are all 1.0 (UE8M0 0x7F): their TMEM region is filled with that byte once per CTA, so their
 // layout does not matter.  Accumulators are FP32 (exact: |dot| <= 512).  Train tiles of 96 rows: four accumulators of 96
-// columns leave 128 TMEM columns for the scale factors.  64-byte rows only (K = 512 = two 128-byte chunks of 256 values).
+// columns leave 128 TMEM columns for the scale factors.  64-byte rows: K = 512 = two 128-byte chunks of 256 values; 48-byte rows:
+// K = 384, the second chunk half zero-filled by TMA.
 // ---------------------------------------------------------------------------
 // Two schedules.  ALT = false: train tiles of 96 rows, two accumulator sets of two (one per query tile), the epilogue of
 // tile i under the MMAs of tile i + 1 (4 x 96 columns + 128 for the scale factors).  ALT = true: train tiles of 192 rows, ONE
@@ -483,7 +484,7 @@ template <int KC, int NT, bool ALT>
 __global__ void __launch_bounds__(kT5Threads, 1)
 hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, long long nq,
                           long long nt, long long rows_per_split, long long train_index_offset,
-                          unsigned long long* __restrict__ part) {
+                          unsigned long long* __restrict__ part, int k_bits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int kN = NT, kChunkBytes = kN * kT5Chunk, kStages = kT5RingBytes / kChunkBytes;   // 8 stages of 12 KB / 4 of 24 KB
@@ -546,6 +547,8 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       tc_fence_after();
       const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
       const uint32_t sfa = tmem_base + kMxColSF, sfb = tmem_base + kMxColSF + 64;
+      // K steps of 64 values in the last chunk: 4, or 2 for 48-byte rows (the rest of that chunk is TMA's zero fill)
+      const int last_steps = (k_bits - (KC - 1) * kT5Chunk * 2 + 63) / 64;
       if (ALT) {
         for (int i = 0; i < ntiles; ++i) {
 #pragma unroll 1
@@ -555,8 +558,9 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
             for (int c = 0; c < KC; ++c) {
               const int it = i * KC + c, s = it % kStages;
               if (a == 0) { mbar_wait(&bar_full[s], (it / kStages) & 1); tc_fence_after(); }
-#pragma unroll
-              for (int k = 0; k < kT5Chunk / 32; ++k)
+              const int steps = c == KC - 1 ? last_steps : kT5Chunk / 32;
+#pragma unroll 4
+              for (int k = 0; k < steps; ++k)
                 umma_mxf4(tmem_base + (uint32_t)(a * kN), umma_desc(a_base + (a * KC + c) * kT5AChunkBytes + k * 32),
                           umma_desc(b_base + s * kChunkBytes + k * 32), kIdesc, (c | k) != 0 ? 1u : 0u, sfa, sfb);
               if (a == kT5QTiles - 1) umma_commit(&bar_empty[s]);   // both query tiles have read the chunk
@@ -574,8 +578,9 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
             const int s = it % kStages;
             mbar_wait(&bar_full[s], (it / kStages) & 1);
             tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < kT5Chunk / 32; ++k) {   // 32 bytes = 64 values per instruction
+            const int steps = c == KC - 1 ? last_steps : kT5Chunk / 32;
+#pragma unroll 4
+            for (int k = 0; k < steps; ++k) {   // 32 bytes = 64 values per instruction
               const uint64_t bd = umma_desc(b_base + s * kChunkBytes + k * 32);
 #pragma unroll
               for (int a = 0; a < kT5QTiles; ++a)
@@ -639,10 +644,11 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       if (lane == 0) mbar_arrive(&bar_tempty[b]);
     }
     if (q0 + row < nq) {
-      constexpr int kBits = KC * kT5Chunk * 2;   // two values per byte
+      // k_bits = descriptor bits: 512, or 384 for 48-byte rows, whose 192 expanded bytes end in the middle of the second
+      // chunk -- the tensor map is 192 bytes wide and TMA fills the rest of the box with zeros, which are E2M1 0.0
       unsigned long long* out = part + ((long long)blockIdx.y * nq + q0 + row) * 2;
-      out[0] = i0 == 0xffffffffu ? kT5KeyNone : ((unsigned long long)((kBits - (int)d0) >> 1) << 32) | i0;
-      out[1] = i1 == 0xffffffffu ? kT5KeyNone : ((unsigned long long)((kBits - (int)d1) >> 1) << 32) | i1;
+      out[0] = i0 == 0xffffffffu ? kT5KeyNone : ((unsigned long long)((k_bits - (int)d0) >> 1) << 32) | i0;
+      out[1] = i1 == 0xffffffffu ? kT5KeyNone : ((unsigned long long)((k_bits - (int)d1) >> 1) << 32) | i1;
     }
   }
   tc_fence_before();
@@ -691,12 +697,13 @@ cudaError_t launch_expand_e2m1(const uint8_t* src, long long rows, int desc_byte
   return cudaGetLastError();
 }
 
-// k == 2, 64-byte rows; map_q (128-row boxes) / map_t (96-row boxes): tensor maps over the E2M1-expanded rows (256 bytes each).
+// k == 2, 64- or 48-byte rows; map_q (128-row boxes) / map_t (tile-row boxes): tensor maps over the E2M1-expanded rows (256 / 192
+// bytes each).
 cudaError_t launch_hamming_knn2_tc5mx(const CUtensorMap& map_q, long long nq, const CUtensorMap& map_t, long long nt, int desc_bytes,
                                       long long train_index_offset, unsigned long long* keys, unsigned long long* part,
                                       int splits, cudaStream_t stream) {
   if (nq <= 0) return cudaSuccess;
-  if (desc_bytes != 64) return cudaErrorInvalidValue;
+  if (desc_bytes != 64 && desc_bytes != 48) return cudaErrorInvalidValue;
   if (nt <= 0) return cudaMemsetAsync(keys, 0xff, (size_t)nq * 2 * 8, stream);
   const int tile = knn_tc5mx_tile_rows();
   long long rows_per_split = ((nt + splits - 1) / splits + tile - 1) / tile * tile;
@@ -709,11 +716,11 @@ cudaError_t launch_hamming_knn2_tc5mx(const CUtensorMap& map_q, long long nq, co
   if (tile == 192) {
     e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 192, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hamming_knn2_tc5mx_kernel<KC, 192, true><<<grid, kT5Threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst);
+    hamming_knn2_tc5mx_kernel<KC, 192, true><<<grid, kT5Threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
   } else {
     e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hamming_knn2_tc5mx_kernel<KC, 96, false><<<grid, kT5Threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst);
+    hamming_knn2_tc5mx_kernel<KC, 96, false><<<grid, kT5Threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
