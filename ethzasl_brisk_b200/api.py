@@ -93,7 +93,7 @@ class Context:
 
     def set_knn_variant(self, variant):
         """0: POPC kernel; for k == 2 and 48/64-byte rows 1: mma.sync IMMA kernel, 2: tcgen05 kind::i8 kernel, 3 (default): tcgen05
-        kind::mxf4 (FP4, +-1.0 operands) for 64-byte rows and the kind::i8 kernel for 48-byte rows."""
+        kind::mxf4 (FP4, +-1.0 operands)."""
         self._check(self._lib.brisk_ctx_set_knn_variant(self._h, int(variant)))
 
     def set_pipelining(self, on=True):

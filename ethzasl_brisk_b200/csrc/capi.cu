@@ -78,7 +78,7 @@ struct brisk_ctx {
   bool timing = false;
   bool pipelining = true;
   int knn_variant = 3;  // 0: POPC kernel always; where they apply (k == 2, 48/64-byte rows) 1: mma.sync IMMA kernel, 2: tcgen05 kind::i8 kernel,
-                        // 3 (default): tcgen05 kind::mxf4 (FP4) kernel for 64-byte rows, the kind::i8 one for 48-byte rows
+                        // 3 (default): tcgen05 kind::mxf4 (FP4) kernel
   float ms[BRISK_STAGE_COUNT] = {};
   int64_t launches = 0;
   int64_t raw_corners = 0;  // AGAST corners before NMS, summed over the frames of the last call (timing mode only)
@@ -1458,7 +1458,7 @@ static int knn_keys_impl(brisk_ctx* ctx, const uint8_t* query, int64_t nq, const
   const bool tensor = k == 2 && (desc_bytes == 48 || desc_bytes == 64);
   const bool mx4 = ctx->knn_variant == 3 && tensor && nq > 0 && nt > 0;   // FP4 form
   const bool mma = ctx->knn_variant == 1 && tensor, tc5 = (ctx->knn_variant == 2 || (ctx->knn_variant == 3 && !mx4)) && tensor && nq > 0 && nt > 0;
-  const int splits = (tc5 || mx4) ? knn_tc5_num_splits(nq, nt) : (mma ? knn_mma_num_splits(nq, nt) : knn_num_splits(nq, nt));
+  const int splits = mx4 ? knn_tc5_num_splits(nq, nt, knn_tc5mx_query_tiles()) : tc5 ? knn_tc5_num_splits(nq, nt) : (mma ? knn_mma_num_splits(nq, nt) : knn_num_splits(nq, nt));
   CU_OK(ctx->knn_keys.ensure(std::max<size_t>((size_t)nq * kr * 8, 16)));
   if (splits > 1) CU_OK(ctx->knn_part.ensure((size_t)splits * nq * kr * 8));
   if (ctx->timing) cudaEventRecord(ctx->ev[0], ctx->stream);

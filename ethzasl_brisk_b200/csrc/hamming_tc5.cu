@@ -480,29 +480,30 @@ __device__ __forceinline__ void umma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint
       : "memory");
 }
 
-template <int KC, int NT, bool ALT>
-__global__ void __launch_bounds__(kT5Threads, 1)
+template <int KC, int NT, bool ALT, int QT>
+__global__ void __launch_bounds__((2 + 4 * QT) * 32, 1)
 hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, long long nq,
                           long long nt, long long rows_per_split, long long train_index_offset,
                           unsigned long long* __restrict__ part, int k_bits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int kN = NT, kChunkBytes = kN * kT5Chunk, kStages = kT5RingBytes / kChunkBytes;   // 8 stages of 12 KB / 4 of 24 KB
-  constexpr int kMxColSF = (ALT ? 2 : 4) * kN;   // accumulators in front, scale factors behind them
+  constexpr int kMxColSF = (ALT ? QT : 2 * QT) * kN;   // accumulators in front, scale factors behind them
+  static_assert(ALT || QT == 2, "two accumulator sets only with two query tiles");
   static_assert(kN % 32 == 0 && kMxColSF + 128 <= 512, "the epilogue reads groups of 32 columns; the scale factors need room");
   constexpr uint32_t kIdesc = mx_idesc(kN);
   uint8_t* sA = smem;                                         // [2 tiles][KC chunks][128 rows x 128 B]
-  uint8_t* sB = sA + kT5QTiles * KC * kT5AChunkBytes;         // [stages][96 rows x 128 B]
+  uint8_t* sB = sA + QT * KC * kT5AChunkBytes;         // [stages][96 rows x 128 B]
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(sB + kStages * kChunkBytes);
   uint64_t* bar_empty = bar_full + kStages;
   uint64_t* bar_a = bar_empty + kStages;
-  uint64_t* bar_tfull = bar_a + 1;       // [2] accumulator set ready for the epilogue
-  uint64_t* bar_tempty = bar_tfull + 2;  // [2] accumulator set drained
-  uint64_t* bar_sf = bar_tempty + 2;     // scale factors written
+  uint64_t* bar_tfull = bar_a + 1;       // [2 sets | QT tiles] accumulator ready for the epilogue
+  uint64_t* bar_tempty = bar_tfull + 4;  // ... drained
+  uint64_t* bar_sf = bar_tempty + 4;     // scale factors written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_sf + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long q0 = (long long)blockIdx.x * (kT5QTiles * kT5M);
+  const long long q0 = (long long)blockIdx.x * (QT * kT5M);
   const long long t_begin = (long long)blockIdx.y * rows_per_split;
   const long long t_end = min(nt, t_begin + rows_per_split);
   const int ntiles = t_end > t_begin ? (int)((t_end - t_begin + kN - 1) / kN) : 0;
@@ -510,7 +511,7 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
     mbar_init(bar_a, 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], ALT ? kT5EpiWarps / 2 : kT5EpiWarps); }
+    for (int b = 0; b < (ALT ? QT : 2); ++b) { mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], ALT ? 4 : 4 * QT); }
     mbar_init(bar_sf, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -527,8 +528,8 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   if (warp == 0) {
     // ---- TMA producer ----
     if (lane == 0 && ntiles > 0) {
-      mbar_expect_tx(bar_a, kT5QTiles * KC * kT5AChunkBytes);
-      for (int a = 0; a < kT5QTiles; ++a)
+      mbar_expect_tx(bar_a, QT * KC * kT5AChunkBytes);
+      for (int a = 0; a < QT; ++a)
         for (int c = 0; c < KC; ++c) tma_load_2d(sA + (a * KC + c) * kT5AChunkBytes, &map_q, c * kT5Chunk, (int)(q0 + a * kT5M), bar_a);
       int it = 0;
       for (int i = 0; i < ntiles; ++i)
@@ -552,7 +553,7 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       if (ALT) {
         for (int i = 0; i < ntiles; ++i) {
 #pragma unroll 1
-          for (int a = 0; a < kT5QTiles; ++a) {
+          for (int a = 0; a < QT; ++a) {
             mbar_wait(&bar_tempty[a], (i & 1) ^ 1);
             tc_fence_after();
             for (int c = 0; c < KC; ++c) {
@@ -563,7 +564,7 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
               for (int k = 0; k < steps; ++k)
                 umma_mxf4(tmem_base + (uint32_t)(a * kN), umma_desc(a_base + (a * KC + c) * kT5AChunkBytes + k * 32),
                           umma_desc(b_base + s * kChunkBytes + k * 32), kIdesc, (c | k) != 0 ? 1u : 0u, sfa, sfb);
-              if (a == kT5QTiles - 1) umma_commit(&bar_empty[s]);   // both query tiles have read the chunk
+              if (a == QT - 1) umma_commit(&bar_empty[s]);   // both query tiles have read the chunk
             }
             umma_commit(&bar_tfull[a]);
           }
@@ -583,8 +584,8 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
             for (int k = 0; k < steps; ++k) {   // 32 bytes = 64 values per instruction
               const uint64_t bd = umma_desc(b_base + s * kChunkBytes + k * 32);
 #pragma unroll
-              for (int a = 0; a < kT5QTiles; ++a)
-                umma_mxf4(tmem_base + (uint32_t)((b * kT5QTiles + a) * kN), umma_desc(a_base + (a * KC + c) * kT5AChunkBytes + k * 32), bd,
+              for (int a = 0; a < QT; ++a)
+                umma_mxf4(tmem_base + (uint32_t)((b * QT + a) * kN), umma_desc(a_base + (a * KC + c) * kT5AChunkBytes + k * 32), bd,
                           kIdesc, (c | k) != 0 ? 1u : 0u, sfa, sfb);
             }
             umma_commit(&bar_empty[s]);
@@ -618,7 +619,7 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       const long long tile_base = t_begin + (long long)i * kN;
       const int valid = (int)min((long long)kN, t_end - tile_base);
       const unsigned idx_base = (unsigned)(train_index_offset + tile_base);
-      const uint32_t acc_col = ALT ? (uint32_t)(a * kN) : (uint32_t)((b * kT5QTiles + a) * kN);
+      const uint32_t acc_col = ALT ? (uint32_t)(a * kN) : (uint32_t)((b * QT + a) * kN);
 #pragma unroll 1
       for (int cc = 0; cc < kN / 32; ++cc) {
         int vi[32];
@@ -683,10 +684,17 @@ size_t knn_tc5mx_expanded_bytes(long long rows, int desc_bytes) {
   const long long r = rows < 256 ? 256 : rows;
   return (size_t)r * desc_bytes * 4;
 }
-// Train rows per tile: 192 (default, one accumulator per query tile) or 96 (BRISK_B200_TC5MX_TILE_ROWS=96: two accumulator sets).
+// Query tiles of 128 rows per CTA: 2 (default), or 3 with BRISK_B200_TC5MX_QTILES=3 (384 queries share every train tile
+// a CTA pulls from L2; three accumulators of 128 columns, twelve epilogue warps).
+int knn_tc5mx_query_tiles() {
+  static const int qt = [] { const char* e = getenv("BRISK_B200_TC5MX_QTILES"); return e && atoi(e) == 3 ? 3 : 2; }();
+  return qt;
+}
+// Train rows per tile: 192 (default, one accumulator per query tile), 96 (BRISK_B200_TC5MX_TILE_ROWS=96: two accumulator
+// sets) or 128 with three query tiles.
 int knn_tc5mx_tile_rows() {
   static const int rows = [] { const char* e = getenv("BRISK_B200_TC5MX_TILE_ROWS"); return e && atoi(e) == 96 ? 96 : 192; }();
-  return rows;
+  return knn_tc5mx_query_tiles() == 3 ? 128 : rows;
 }
 
 cudaError_t launch_expand_e2m1(const uint8_t* src, long long rows, int desc_bytes, uint8_t* dst, cudaStream_t stream) {
@@ -705,22 +713,27 @@ cudaError_t launch_hamming_knn2_tc5mx(const CUtensorMap& map_q, long long nq, co
   if (nq <= 0) return cudaSuccess;
   if (desc_bytes != 64 && desc_bytes != 48) return cudaErrorInvalidValue;
   if (nt <= 0) return cudaMemsetAsync(keys, 0xff, (size_t)nq * 2 * 8, stream);
-  const int tile = knn_tc5mx_tile_rows();
+  const int tile = knn_tc5mx_tile_rows(), qt = knn_tc5mx_query_tiles();
   long long rows_per_split = ((nt + splits - 1) / splits + tile - 1) / tile * tile;
   if (rows_per_split <= 0) rows_per_split = tile;
   unsigned long long* dst = splits == 1 ? keys : part;
   constexpr int KC = 2;
-  const size_t smem = (size_t)kT5QTiles * KC * kT5AChunkBytes + kT5RingBytes + 1024 /* alignment */ + 512 /* barriers */;
-  dim3 grid((unsigned)((nq + kT5QTiles * kT5M - 1) / (kT5QTiles * kT5M)), splits);
+  const size_t smem = (size_t)qt * KC * kT5AChunkBytes + kT5RingBytes + 1024 /* alignment */ + 512 /* barriers */;
+  dim3 grid((unsigned)((nq + qt * kT5M - 1) / (qt * kT5M)), splits);
+  const int threads = (2 + 4 * qt) * 32;
   cudaError_t e;
-  if (tile == 192) {
-    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 192, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (qt == 3) {
+    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 128, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hamming_knn2_tc5mx_kernel<KC, 192, true><<<grid, kT5Threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
+    hamming_knn2_tc5mx_kernel<KC, 128, true, 3><<<grid, threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
+  } else if (tile == 192) {
+    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 192, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hamming_knn2_tc5mx_kernel<KC, 192, true, 2><<<grid, threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
   } else {
-    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 96, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 96, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hamming_knn2_tc5mx_kernel<KC, 96, false><<<grid, kT5Threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
+    hamming_knn2_tc5mx_kernel<KC, 96, false, 2><<<grid, threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
@@ -762,8 +775,9 @@ cudaError_t launch_expand_pm1(const uint8_t* src, long long rows, int desc_bytes
 int knn_tc5_tile_rows() { return t5_tile_rows(); }
 
 // Splits of the train set: enough CTAs for the 148 SMs, then the smallest count whose last wave is >= 95 % full.
-int knn_tc5_num_splits(long long nq, long long nt) {
-  const long long qblocks = (nq + kT5QTiles * kT5M - 1) / (kT5QTiles * kT5M);
+int knn_tc5_num_splits(long long nq, long long nt, int query_tiles) {
+  if (query_tiles <= 0) query_tiles = kT5QTiles;
+  const long long qblocks = (nq + query_tiles * kT5M - 1) / (query_tiles * kT5M);
   long long max_splits = (nt + 16 * 256 - 1) / (16 * 256);
   if (max_splits > 64) max_splits = 64;
   if (max_splits < 1) max_splits = 1;

@@ -155,7 +155,7 @@ cudaError_t launch_hamming_knn2_mma(const uint8_t* q, long long nq, const uint8_
 // CU_TENSOR_MAP_SWIZZLE_128B.
 size_t knn_tc5_expanded_bytes(long long rows, int desc_bytes);
 cudaError_t launch_expand_pm1(const uint8_t* src, long long rows, int desc_bytes, uint8_t* dst, cudaStream_t stream);
-int knn_tc5_num_splits(long long nq, long long nt);
+int knn_tc5_num_splits(long long nq, long long nt, int query_tiles = 0);
 int knn_tc5_tile_rows();
 cudaError_t launch_hamming_knn2_tc5(const CUtensorMap& map_q, long long nq, const CUtensorMap& map_t, long long nt, int desc_bytes,
                                     long long train_index_offset, unsigned long long* keys, unsigned long long* part,
@@ -166,6 +166,7 @@ int knn_tc5_queries_in_tmem();
 // of knn_tc5mx_tile_rows() rows; operands expanded to 4 bits per descriptor bit (256 bytes per row).
 size_t knn_tc5mx_expanded_bytes(long long rows, int desc_bytes);
 int knn_tc5mx_tile_rows();
+int knn_tc5mx_query_tiles();
 cudaError_t launch_expand_e2m1(const uint8_t* src, long long rows, int desc_bytes, uint8_t* dst, cudaStream_t stream);
 cudaError_t launch_hamming_knn2_tc5mx(const CUtensorMap& map_q, long long nq, const CUtensorMap& map_t, long long nt, int desc_bytes,
                                       long long train_index_offset, unsigned long long* keys, unsigned long long* part,

@@ -59,7 +59,7 @@ int brisk_sync(brisk_ctx* ctx);
 int brisk_ctx_set_workspace_limit(brisk_ctx* ctx, size_t bytes);
 /* Matcher kernel for unmasked k == 2 searches over 48- or 64-byte rows (everything else runs XOR + POPC tiles); results are
  * identical: 0 = XOR + POPC always, 1 = mma.sync IMMA on byte-expanded bits, 2 = tcgen05.mma kind::i8 (TMEM accumulators, TMA
- * operands), 3 (default) = tcgen05.mma kind::mxf4 on +-1.0 E2M1 values for 64-byte rows and variant 2 for 48-byte rows. */
+ * operands), 3 (default) = tcgen05.mma kind::mxf4 on +-1.0 E2M1 values. */
 int brisk_ctx_set_knn_variant(brisk_ctx* ctx, int variant);
 /* Chunks of a batch normally alternate between two streams so that copies and serial kernel tails
  * of one chunk overlap the kernels of the other (default on).  Off: one stream, stages back to back
