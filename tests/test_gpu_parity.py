@@ -972,8 +972,8 @@ def test_knn_tensor_core_variants_match_popc(oracle, nbytes):
 
 
 def test_knn_tcgen05_alternative_forms():
-    # the measured alternatives of the tcgen05 kernel -- queries held in tensor memory (BRISK_B200_TC5_MODE=ts) and 256-row
-    # train tiles (BRISK_B200_TC5_TILE_ROWS=256) -- are chosen by environment variables read once per process: run each in
+    # the measured alternatives of the tcgen05 kernels -- queries held in tensor memory (BRISK_B200_TC5_MODE=ts), 256-row
+    # train tiles (BRISK_B200_TC5_TILE_ROWS=256), and the FP4 kernel's 96-row and three-query-tile schedules -- are chosen by environment variables read once per process: run each in
     # a child process and compare with the POPC kernel
     import os
     import subprocess
@@ -987,10 +987,13 @@ def test_knn_tcgen05_alternative_forms():
         "        q = bb.random_descriptors(nq, nb, 5); t = bb.random_descriptors(nt, nb, 6)\n"
         "        if nt > 200: t[100] = q[3]; t[200] = q[3]; t[nt - 1] = q[3]\n"
         "        ctx.set_knn_variant(0); a = m.knn(q, t, 2)\n"
-        "        ctx.set_knn_variant(2); b = m.knn(q, t, 2)\n"
-        "        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (nb, nq, nt)\n"
+        "        for v in (2, 3):\n"
+        "            ctx.set_knn_variant(v); b = m.knn(q, t, 2)\n"
+        "            assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]), (nb, nq, nt, v)\n"
         "print('same')\n")
-    for extra in ({"BRISK_B200_TC5_MODE": "ts"}, {"BRISK_B200_TC5_TILE_ROWS": "256"}):
+    # (the last two select other schedules of the FP4 kernel, variant 3)
+    for extra in ({"BRISK_B200_TC5_MODE": "ts"}, {"BRISK_B200_TC5_TILE_ROWS": "256"}, {"BRISK_B200_TC5MX_TILE_ROWS": "96"},
+                  {"BRISK_B200_TC5MX_QTILES": "3"}):
         env = dict(os.environ, PYTHONPATH=str(ROOT), **extra)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "same" in r.stdout, (extra, r.stdout[-500:], r.stderr[-1500:])
