@@ -119,6 +119,19 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int v[32]) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// The same load without the wait (several in flight), and the wait for all of a thread's outstanding loads.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, int v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ int max3(int a, int b, int c) { return max(max(a, b), c); }
 
@@ -466,6 +479,10 @@ hamming_knn2_tc5ts_kernel(const uint8_t* __restrict__ q, const __grid_constant__
 // instead of 7 KB per 48, which is what the narrow form is bound by.
 // Instruction descriptor, block-scaled kinds (cute/arch/mma_sm100_desc.hpp InstrDescriptorBlockScaled): A = B = E2M1, which is
 // format 1 for kind::mxf4 (1 << 7, 1 << 10; 5 is its code under kind::mxf8f6f4), both K-major, N >> 3 in bits 17-22, scale format UE8M0 (1 << 23), M >> 4 in bits 24-28, scale-factor ids 0, K = 64.
+#ifndef BRISK_MX_RING_KB
+#define BRISK_MX_RING_KB 96
+#endif
+constexpr int kMxRingBytes2 = BRISK_MX_RING_KB * 1024;   // B ring of the two-query-tile forms (A tiles take 64 KB)
 __host__ __device__ constexpr uint32_t mx_idesc(int n) {
   return (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(kT5M >> 4) << 24);
 }
@@ -487,7 +504,8 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
                           unsigned long long* __restrict__ part, int k_bits) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  constexpr int kN = NT, kChunkBytes = kN * kT5Chunk, kStages = kT5RingBytes / kChunkBytes;   // 8 stages of 12 KB / 4 of 24 KB
+  constexpr int kRing = QT == 2 ? kMxRingBytes2 : kT5RingBytes;
+  constexpr int kN = NT, kChunkBytes = kN * kT5Chunk, kStages = kRing / kChunkBytes;   // 24 KB (192 rows), 12 KB (96) or 16 KB (128) per stage
   constexpr int kMxColSF = (ALT ? QT : 2 * QT) * kN;   // accumulators in front, scale factors behind them
   static_assert(ALT || QT == 2, "two accumulator sets only with two query tiles");
   static_assert(kN % 32 == 0 && kMxColSF + 128 <= 512, "the epilogue reads groups of 32 columns; the scale factors need room");
@@ -620,22 +638,33 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       const int valid = (int)min((long long)kN, t_end - tile_base);
       const unsigned idx_base = (unsigned)(train_index_offset + tile_base);
       const uint32_t acc_col = ALT ? (uint32_t)(a * kN) : (uint32_t)((b * QT + a) * kN);
+      // groups of 32 columns, kBatch of them loaded before one wait: the loads' latencies overlap (with one load per wait
+      // the epilogue of a 192-column accumulator took twice the time of the eight MMAs that hide it)
+      constexpr int kGroups = kN / 32, kBatch = kGroups % 3 == 0 ? 3 : 2;
+      static_assert(kGroups % kBatch == 0, "whole batches");
 #pragma unroll 1
-      for (int cc = 0; cc < kN / 32; ++cc) {
-        int vi[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc_col + (uint32_t)(cc * 32), vi);
-        float m = fmaxf(fmaxf(__int_as_float(vi[0]), __int_as_float(vi[1])), __int_as_float(vi[2]));
+      for (int c0 = 0; c0 < kGroups; c0 += kBatch) {
+        int vi[kBatch][32];
 #pragma unroll
-        for (int j = 3; j + 1 < 32; j += 2) m = fmaxf(fmaxf(m, __int_as_float(vi[j])), __int_as_float(vi[j + 1]));
-        m = fmaxf(m, __int_as_float(vi[31]));
-        if (m > d1) {
+        for (int u = 0; u < kBatch; ++u)
+          tmem_ld32_issue(tmem_base + ((uint32_t)(quad * 32) << 16) + acc_col + (uint32_t)((c0 + u) * 32), vi[u]);
+        tmem_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int col = cc * 32 + j;
-            const float v = __int_as_float(vi[j]);
-            if (v > d1 && col < valid) {
-              if (v > d0) { d1 = d0; i1 = i0; d0 = v; i0 = idx_base + col; }
-              else { d1 = v; i1 = idx_base + col; }
+        for (int u = 0; u < kBatch; ++u) {
+          const int cc = c0 + u;
+          float m = fmaxf(fmaxf(__int_as_float(vi[u][0]), __int_as_float(vi[u][1])), __int_as_float(vi[u][2]));
+#pragma unroll
+          for (int j = 3; j + 1 < 32; j += 2) m = fmaxf(fmaxf(m, __int_as_float(vi[u][j])), __int_as_float(vi[u][j + 1]));
+          m = fmaxf(m, __int_as_float(vi[u][31]));
+          if (m > d1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = cc * 32 + j;
+              const float v = __int_as_float(vi[u][j]);
+              if (v > d1 && col < valid) {
+                if (v > d0) { d1 = d0; i1 = i0; d0 = v; i0 = idx_base + col; }
+                else { d1 = v; i1 = idx_base + col; }
+              }
             }
           }
         }
@@ -718,7 +747,7 @@ cudaError_t launch_hamming_knn2_tc5mx(const CUtensorMap& map_q, long long nq, co
   if (rows_per_split <= 0) rows_per_split = tile;
   unsigned long long* dst = splits == 1 ? keys : part;
   constexpr int KC = 2;
-  const size_t smem = (size_t)qt * KC * kT5AChunkBytes + kT5RingBytes + 1024 /* alignment */ + 512 /* barriers */;
+  const size_t smem = (size_t)qt * KC * kT5AChunkBytes + (qt == 2 ? kMxRingBytes2 : kT5RingBytes) + 1024 /* alignment */ + 512 /* barriers */;
   dim3 grid((unsigned)((nq + qt * kT5M - 1) / (qt * kT5M)), splits);
   const int threads = (2 + 4 * qt) * 32;
   cudaError_t e;
