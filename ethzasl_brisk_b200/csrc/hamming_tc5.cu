@@ -497,8 +497,8 @@ __device__ __forceinline__ void umma_mxf4(uint32_t d_tmem, uint64_t a_desc, uint
       : "memory");
 }
 
-template <int KC, int NT, bool ALT, int QT>
-__global__ void __launch_bounds__((2 + 4 * QT) * 32, 1)
+template <int KC, int NT, bool ALT, int QT, int EW>
+__global__ void __launch_bounds__((2 + EW * QT) * 32, 1)
 hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_t, long long nq,
                           long long nt, long long rows_per_split, long long train_index_offset,
                           unsigned long long* __restrict__ part, int k_bits) {
@@ -508,6 +508,7 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   constexpr int kN = NT, kChunkBytes = kN * kT5Chunk, kStages = kRing / kChunkBytes;   // 24 KB (192 rows), 12 KB (96) or 16 KB (128) per stage
   constexpr int kMxColSF = (ALT ? QT : 2 * QT) * kN;   // accumulators in front, scale factors behind them
   static_assert(ALT || QT == 2, "two accumulator sets only with two query tiles");
+  static_assert(EW == 4 || (EW == 8 && ALT && kN % 64 == 0), "eight epilogue warps per query tile: two per lane quadrant, half the columns each");
   static_assert(kN % 32 == 0 && kMxColSF + 128 <= 512, "the epilogue reads groups of 32 columns; the scale factors need room");
   constexpr uint32_t kIdesc = mx_idesc(kN);
   uint8_t* sA = smem;                                         // [2 tiles][KC chunks][128 rows x 128 B]
@@ -519,6 +520,7 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   uint64_t* bar_tempty = bar_tfull + 4;  // ... drained
   uint64_t* bar_sf = bar_tempty + 4;     // scale factors written
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_sf + 1);
+  float4* s_merge = reinterpret_cast<float4*>(((uintptr_t)(tmem_slot + 1) + 15) & ~(uintptr_t)15);   // [QT * 128] (EW == 8)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long q0 = (long long)blockIdx.x * (QT * kT5M);
@@ -529,7 +531,7 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
     mbar_init(bar_a, 1);
-    for (int b = 0; b < (ALT ? QT : 2); ++b) { mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], ALT ? 4 : 4 * QT); }
+    for (int b = 0; b < (ALT ? QT : 2); ++b) { mbar_init(&bar_tfull[b], 1); mbar_init(&bar_tempty[b], ALT ? EW : 4 * QT); }
     mbar_init(bar_sf, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -614,9 +616,11 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
     }
   } else {
     // ---- epilogue: thread = one query row ----
-    const int quad = warp & 3, a = (warp - 2) >> 2;
+    // EW warps per query tile: one per TMEM lane quadrant (warp % 4), and with EW == 8 two per quadrant that split the columns
+    const int quad = warp & 3, a = (warp - 2) / EW, half = EW == 8 ? (((warp - 2) >> 2) & 1) : 0;
+    constexpr int kCols = kN / (EW / 4);   // accumulator columns a thread looks at
     const int row = a * kT5M + quad * 32 + lane;
-    if (a == 0) {
+    if (a == 0 && half == 0) {
       // scale factors: 1.0 everywhere (UE8M0 0x7f), all 128 lanes x 128 columns of the region
       uint32_t ones[32];
 #pragma unroll
@@ -637,43 +641,80 @@ hamming_knn2_tc5mx_kernel(const __grid_constant__ CUtensorMap map_q, const __gri
       const long long tile_base = t_begin + (long long)i * kN;
       const int valid = (int)min((long long)kN, t_end - tile_base);
       const unsigned idx_base = (unsigned)(train_index_offset + tile_base);
-      const uint32_t acc_col = ALT ? (uint32_t)(a * kN) : (uint32_t)((b * QT + a) * kN);
-      // groups of 32 columns, kBatch of them loaded before one wait: the loads' latencies overlap (with one load per wait
+      const uint32_t acc_col = (ALT ? (uint32_t)(a * kN) : (uint32_t)((b * QT + a) * kN)) + (uint32_t)(half * kCols);
+      const int col_first = half * kCols;
+      // groups of 32 columns; several loads are issued before a wait so that their latencies overlap (with one load per wait
       // the epilogue of a 192-column accumulator took twice the time of the eight MMAs that hide it)
-      constexpr int kGroups = kN / 32, kBatch = kGroups % 3 == 0 ? 3 : 2;
-      static_assert(kGroups % kBatch == 0, "whole batches");
-#pragma unroll 1
-      for (int c0 = 0; c0 < kGroups; c0 += kBatch) {
-        int vi[kBatch][32];
+      const uint32_t acc_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc_col;
+      auto process = [&](const int (&vv)[32], int cc) {
+        float m = fmaxf(fmaxf(__int_as_float(vv[0]), __int_as_float(vv[1])), __int_as_float(vv[2]));
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u)
-          tmem_ld32_issue(tmem_base + ((uint32_t)(quad * 32) << 16) + acc_col + (uint32_t)((c0 + u) * 32), vi[u]);
-        tmem_wait_ld();
+        for (int j = 3; j + 1 < 32; j += 2) m = fmaxf(fmaxf(m, __int_as_float(vv[j])), __int_as_float(vv[j + 1]));
+        m = fmaxf(m, __int_as_float(vv[31]));
+        if (m > d1) {
 #pragma unroll
-        for (int u = 0; u < kBatch; ++u) {
-          const int cc = c0 + u;
-          float m = fmaxf(fmaxf(__int_as_float(vi[u][0]), __int_as_float(vi[u][1])), __int_as_float(vi[u][2]));
-#pragma unroll
-          for (int j = 3; j + 1 < 32; j += 2) m = fmaxf(fmaxf(m, __int_as_float(vi[u][j])), __int_as_float(vi[u][j + 1]));
-          m = fmaxf(m, __int_as_float(vi[u][31]));
-          if (m > d1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = cc * 32 + j;
-              const float v = __int_as_float(vi[u][j]);
-              if (v > d1 && col < valid) {
-                if (v > d0) { d1 = d0; i1 = i0; d0 = v; i0 = idx_base + col; }
-                else { d1 = v; i1 = idx_base + col; }
-              }
+          for (int j = 0; j < 32; ++j) {
+            const int col = col_first + cc * 32 + j;
+            const float v = __int_as_float(vv[j]);
+            if (v > d1 && col < valid) {
+              if (v > d0) { d1 = d0; i1 = i0; d0 = v; i0 = idx_base + col; }
+              else { d1 = v; i1 = idx_base + col; }
             }
           }
+        }
+      };
+      constexpr int kGroups = kCols / 32;
+      if (kGroups == 3) {
+        // two loads in flight at any time (64 data registers): g0 g1 | wait | use g0, reload its registers with g2, use g1 | wait | use g2
+        int va[32], vb[32];
+        tmem_ld32_issue(acc_addr, va);
+        tmem_ld32_issue(acc_addr + 32, vb);
+        tmem_wait_ld();
+        process(va, 0);
+        tmem_ld32_issue(acc_addr + 64, va);
+        process(vb, 1);
+        tmem_wait_ld();
+        process(va, 2);
+      } else {
+        constexpr int kBatch = kGroups % 3 == 0 ? 3 : 2;
+        static_assert(kGroups % kBatch == 0, "whole batches");
+#pragma unroll 1
+        for (int c0 = 0; c0 < kGroups; c0 += kBatch) {
+          int vi[kBatch][32];
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) tmem_ld32_issue(acc_addr + (uint32_t)((c0 + u) * 32), vi[u]);
+          tmem_wait_ld();
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) process(vi[u], c0 + u);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_tempty[b]);
     }
-    if (q0 + row < nq) {
+    if (EW == 8) {
+      // the two threads of a row merge their pairs: (dot, index) candidates ordered by larger dot, then lower index --
+      // the order in which a single left-to-right scan would have met them
+      if (half == 1) s_merge[row] = make_float4(d0, __uint_as_float(i0), d1, __uint_as_float(i1));
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * QT * 32) : "memory");
+      if (half == 0) {
+        const float4 o = s_merge[row];
+        const float e0 = o.x, e1 = o.z;
+        const unsigned j0 = __float_as_uint(o.y), j1 = __float_as_uint(o.w);
+        auto before = [](float da, unsigned ia, float db, unsigned ib) { return da > db || (da == db && ia < ib); };
+        // merge two sorted pairs (d0,i0) >= (d1,i1) and (e0,j0) >= (e1,j1)
+        float r0, r1; unsigned k0, k1;
+        if (before(d0, i0, e0, j0)) {
+          r0 = d0; k0 = i0;
+          if (before(d1, i1, e0, j0)) { r1 = d1; k1 = i1; } else { r1 = e0; k1 = j0; }
+        } else {
+          r0 = e0; k0 = j0;
+          if (before(e1, j1, d0, i0)) { r1 = e1; k1 = j1; } else { r1 = d0; k1 = i0; }
+        }
+        d0 = r0; i0 = k0; d1 = r1; i1 = k1;
+      }
+    }
+    if (half == 0 && q0 + row < nq) {
       // k_bits = descriptor bits: 512, or 384 for 48-byte rows, whose 192 expanded bytes end in the middle of the second
       // chunk -- the tensor map is 192 bytes wide and TMA fills the rest of the box with zeros, which are E2M1 0.0
       unsigned long long* out = part + ((long long)blockIdx.y * nq + q0 + row) * 2;
@@ -743,26 +784,36 @@ cudaError_t launch_hamming_knn2_tc5mx(const CUtensorMap& map_q, long long nq, co
   if (desc_bytes != 64 && desc_bytes != 48) return cudaErrorInvalidValue;
   if (nt <= 0) return cudaMemsetAsync(keys, 0xff, (size_t)nq * 2 * 8, stream);
   const int tile = knn_tc5mx_tile_rows(), qt = knn_tc5mx_query_tiles();
+  // epilogue warps per query tile: 4, one per TMEM lane quadrant.  BRISK_B200_TC5MX_EPI_WARPS=8 selects two per quadrant (half the
+  // columns each, pairs merged through shared memory): measured 4.2 against 4.6 Tcmp/s -- the epilogue is bound by what TMEM
+  // delivers (every 4-byte accumulator is read once: 64 B per cycle and SM is 4.6 T comparisons per second), not by its warps.
+  static const int epi_env = [] { const char* e = getenv("BRISK_B200_TC5MX_EPI_WARPS"); return e ? atoi(e) : 0; }();
+  const int ew = (qt == 2 && tile == 192 && epi_env == 8) ? 8 : 4;
   long long rows_per_split = ((nt + splits - 1) / splits + tile - 1) / tile * tile;
   if (rows_per_split <= 0) rows_per_split = tile;
   unsigned long long* dst = splits == 1 ? keys : part;
   constexpr int KC = 2;
-  const size_t smem = (size_t)qt * KC * kT5AChunkBytes + (qt == 2 ? kMxRingBytes2 : kT5RingBytes) + 1024 /* alignment */ + 512 /* barriers */;
+  const size_t smem = (size_t)qt * KC * kT5AChunkBytes + (qt == 2 ? kMxRingBytes2 : kT5RingBytes) + 1024 /* alignment */ + 512 /* barriers */ +
+                      4096 + 64 /* merge scratch of the eight-warp epilogue */;
   dim3 grid((unsigned)((nq + qt * kT5M - 1) / (qt * kT5M)), splits);
-  const int threads = (2 + 4 * qt) * 32;
+  const int threads = (2 + ew * qt) * 32;
   cudaError_t e;
   if (qt == 3) {
-    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 128, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 128, true, 3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hamming_knn2_tc5mx_kernel<KC, 128, true, 3><<<grid, threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
+    hamming_knn2_tc5mx_kernel<KC, 128, true, 3, 4><<<grid, threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
+  } else if (tile == 192 && ew == 8) {
+    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 192, true, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hamming_knn2_tc5mx_kernel<KC, 192, true, 2, 8><<<grid, threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
   } else if (tile == 192) {
-    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 192, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 192, true, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hamming_knn2_tc5mx_kernel<KC, 192, true, 2><<<grid, threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
+    hamming_knn2_tc5mx_kernel<KC, 192, true, 2, 4><<<grid, threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
   } else {
-    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 96, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    e = cudaFuncSetAttribute(hamming_knn2_tc5mx_kernel<KC, 96, false, 2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    hamming_knn2_tc5mx_kernel<KC, 96, false, 2><<<grid, threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
+    hamming_knn2_tc5mx_kernel<KC, 96, false, 2, 4><<<grid, threads, smem, stream>>>(map_q, map_t, nq, nt, rows_per_split, train_index_offset, dst, desc_bytes * 8);
   }
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;

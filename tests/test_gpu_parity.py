@@ -993,7 +993,7 @@ def test_knn_tcgen05_alternative_forms():
         "print('same')\n")
     # (the last two select other schedules of the FP4 kernel, variant 3)
     for extra in ({"BRISK_B200_TC5_MODE": "ts"}, {"BRISK_B200_TC5_TILE_ROWS": "256"}, {"BRISK_B200_TC5MX_TILE_ROWS": "96"},
-                  {"BRISK_B200_TC5MX_QTILES": "3"}):
+                  {"BRISK_B200_TC5MX_QTILES": "3"}, {"BRISK_B200_TC5MX_EPI_WARPS": "8"}):
         env = dict(os.environ, PYTHONPATH=str(ROOT), **extra)
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0 and "same" in r.stdout, (extra, r.stdout[-500:], r.stderr[-1500:])
