@@ -387,3 +387,72 @@ def test_std_sort_matches_replays_libstdcxx(oracle):
         assert lib.brisk_std_sort_matches(C.c_int64(n), _ptr(t), _ptr(i), _ptr(d)) == 0
         assert [(7, int(a), int(b), float(c)) for a, b, c in zip(t, i, d)] == want, n
     assert lib.brisk_std_sort_matches(C.c_int64(-1), None, None, None) != 0
+
+
+@pytest.fixture(scope="module")
+def emul_packed():
+    src = ROOT / "tests" / "host_emul" / "emul_packed.cc"
+    lib = ROOT / "tests" / "host_emul" / "libemul_packed.so"
+    deps = [src] + list((ROOT / "ethzasl_brisk_b200" / "csrc").glob("*.cuh"))
+    if not lib.exists() or any(d.stat().st_mtime > lib.stat().st_mtime for d in deps):
+        subprocess.run(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", str(lib), str(src)], check=True)
+    return C.CDLL(str(lib))
+
+
+def test_packed_fast_rows_on_the_host(emul_packed, oracle):
+    # fast_packed.cuh (two pixels per register, 16-bit lanes) compiled for the host with the SIMD intrinsics restated in
+    # C++: dense scores of fast916_row<1..3> at every alignment against the oracle's cornerScore
+    rng = np.random.default_rng(4)
+    for w, h in ((67, 41), (96, 33), (131, 29)):
+        for img in (synthetic_frame(w, h, 9), rng.integers(0, 256, (h, w), dtype=np.uint8),
+                    (rng.integers(0, 3, (h, w)) * 100 + rng.integers(0, 5, (h, w))).astype(np.uint8)):
+            want, _ = oracle.dense_scores(img)
+            pitch = (w + 15) // 16 * 16
+            padded = np.zeros((h, pitch), np.uint8)
+            padded[:, :w] = img
+            for np_ in (1, 2, 3):
+                got = np.zeros((h, w), np.uint8)
+                emul_packed.emul_packed_scores(padded.ctypes.data_as(C.c_void_p), w, h, pitch, np_, got.ctypes.data_as(C.c_void_p))
+                assert np.array_equal(got[3:-3, 3:-3], want[3:-3, 3:-3]), (w, h, np_)
+
+
+def test_packed_segment_and_compass_tests_on_the_host(emul_packed):
+    # the detector's second phase on pairs (largest arc minimum / smallest arc maximum against c +- b) equals the bit-mask
+    # 9-of-16 run test, and its compass pre-test (two ADJACENT compass pixels beyond c +- b) never loses a corner
+    rng = np.random.default_rng(8)
+
+    def is_corner(ring, c, b):
+        br = [int(v) > c + b for v in ring]
+        dk = [int(v) < c - b for v in ring]
+        return any(all(m[(s + j) % 16] for j in range(9)) for m in (br, dk) for s in range(16))
+
+    n_corner = 0
+    for trial in range(4000):
+        base = int(rng.integers(0, 256))
+        kind = trial % 4
+        rings = []
+        for _ in range(2):
+            if kind == 0:
+                ring = rng.integers(0, 256, 16)
+            elif kind == 1:   # a bright or dark arc of random length on a flat background
+                ring = np.full(16, base) + rng.integers(-3, 4, 16)
+                s0, ln = int(rng.integers(0, 16)), int(rng.integers(6, 13))
+                ring[[(s0 + j) % 16 for j in range(ln)]] += int(rng.choice([-1, 1])) * int(rng.integers(20, 120))
+            else:
+                ring = base + rng.integers(-40, 41, 16)
+            rings.append(np.clip(ring, 0, 255).astype(np.uint8))
+        cs = [int(np.clip(base + rng.integers(-5, 6), 0, 255)) for _ in range(2)]
+        bs = [int(rng.integers(1, 140)) for _ in range(2)]
+        got = emul_packed.emul_packed_segment_pair(rings[0].ctypes.data_as(C.c_void_p), cs[0], bs[0], rings[1].ctypes.data_as(C.c_void_p), cs[1], bs[1])
+        want = [is_corner(rings[k], cs[k], bs[k]) for k in range(2)]
+        assert [bool(got & 1), bool(got & 2)] == want, (trial, rings, cs, bs)
+        n_corner += sum(want)
+        comp = [np.ascontiguousarray(r[[0, 4, 8, 12]]) for r in rings]   # left, up, right, down
+        flags = emul_packed.emul_packed_compass_pair(comp[0].ctypes.data_as(C.c_void_p), cs[0], bs[0], comp[1].ctypes.data_as(C.c_void_p), cs[1], bs[1])
+        for k in range(2):
+            v = [int(x) for x in comp[k]]
+            adjacent = any((v[i] > cs[k] + bs[k] and v[(i + 1) % 4] > cs[k] + bs[k]) or (v[i] < cs[k] - bs[k] and v[(i + 1) % 4] < cs[k] - bs[k])
+                           for i in range(4))
+            assert bool(flags & (1 << k)) == adjacent, (trial, k)
+            assert adjacent or not want[k]   # the pre-test is a necessary condition
+    assert n_corner > 200
