@@ -247,4 +247,14 @@ BRISK_HD float refine1d(int kind, float s_05, float s0, float s05, float* max) {
   return r;
 }
 
+// Eight descriptor bits -> eight E2M1 values in one 32-bit word, bit i of the byte in nibble i: +1.0 (0x2) for a set bit,
+// -1.0 (0xA) for a clear one (the operands of the FP4 matcher, hamming_tc5.cu).
+BRISK_HD uint32_t e2m1_expand_byte(uint32_t byte) {
+  // bit i -> bit 4 i: spread the byte's bits four apart
+  uint32_t sp = (byte | (byte << 12)) & 0x000f000fu;   // bits 0..3 | bits 4..7 at 16
+  sp = (sp | (sp << 6)) & 0x03030303u;                 // two bits per byte
+  sp = (sp | (sp << 3)) & 0x11111111u;                 // one bit per nibble
+  return 0x22222222u | ((~sp & 0x11111111u) << 3);     // set -> 0x2, clear -> 0xA (the sign bit of the nibble)
+}
+
 }  // namespace briskb200

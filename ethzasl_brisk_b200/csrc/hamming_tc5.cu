@@ -29,6 +29,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "brisk_math.cuh"
 #include "kernels.h"
 
 namespace briskb200 {
@@ -739,14 +740,7 @@ expand_e2m1_kernel(const uint32_t* __restrict__ src, long long n_words, uint4* _
   const uint32_t w = __ldg(src + i);
   uint32_t o[4];
 #pragma unroll
-  for (int n = 0; n < 4; ++n) {
-    const uint32_t byte = (w >> (8 * n)) & 0xffu;
-    // bit i -> bit 4 i + 3 (the sign of nibble i): spread the byte's bits four apart
-    uint32_t sp = (byte | (byte << 12)) & 0x000f000fu;   // bits 0..3 | bits 4..7 at 16
-    sp = (sp | (sp << 6)) & 0x03030303u;                 // two bits per byte
-    sp = (sp | (sp << 3)) & 0x11111111u;                 // one bit per nibble
-    o[n] = 0x22222222u | ((~sp & 0x11111111u) << 3);     // set -> 0x2, clear -> 0xA
-  }
+  for (int n = 0; n < 4; ++n) o[n] = e2m1_expand_byte((w >> (8 * n)) & 0xffu);
   dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 

@@ -85,3 +85,6 @@ extern "C" int emul_packed_compass_pair(const uint8_t* compass0, int c0, int b0,
   const uint32_t cand = ~(bright & dark) & kHi;
   return (int)((cand >> 15 & 1u) | (cand >> 30 & 2u));
 }
+
+// Descriptor byte -> eight E2M1 nibbles (brisk_math.cuh, the operand expansion of the FP4 matcher).
+extern "C" uint32_t emul_e2m1_expand_byte(uint32_t byte) { return e2m1_expand_byte(byte); }

@@ -456,3 +456,19 @@ def test_packed_segment_and_compass_tests_on_the_host(emul_packed):
             assert bool(flags & (1 << k)) == adjacent, (trial, k)
             assert adjacent or not want[k]   # the pre-test is a necessary condition
     assert n_corner > 200
+
+
+def test_fp4_operand_expansion_on_the_host(emul_packed):
+    # every descriptor byte: bit i -> nibble i = 0x2 (+1.0 in E2M1) when set, 0xA (-1.0) when clear; the dot product of two
+    # expanded rows is K - 2 hamming, which is what the FP4 matcher turns back into distances
+    emul_packed.emul_e2m1_expand_byte.restype = C.c_uint32
+    val = {0x2: 1.0, 0xA: -1.0}
+    words = [emul_packed.emul_e2m1_expand_byte(C.c_uint32(b)) for b in range(256)]
+    for b, w in enumerate(words):
+        for i in range(8):
+            assert (w >> (4 * i)) & 0xF == (0x2 if (b >> i) & 1 else 0xA), (b, i)
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        x, y = int(rng.integers(0, 256)), int(rng.integers(0, 256))
+        dot = sum(val[(words[x] >> (4 * i)) & 0xF] * val[(words[y] >> (4 * i)) & 0xF] for i in range(8))
+        assert dot == 8 - 2 * bin(x ^ y).count("1")
