@@ -481,6 +481,8 @@ int finish_chunk(brisk_ctx* ctx, int si, brisk_ctx::Pending& pd) {
                               (size_t)longest * pd.desc_bytes, (size_t)pd.c, cudaMemcpyDeviceToHost, sl.stream));
   }
   tm.mark(8);
+  // the asynchronous call waits for exactly these copies before it returns (not for whatever is queued behind them)
+  CU_OK(cudaEventRecord(sl.done, sl.stream));
   return BRISK_OK;
 }
 
@@ -761,6 +763,11 @@ int run_batch(brisk_ctx* ctx, brisk_detector* det, brisk_extractor* ext, const u
     // everything but the last chunk is collected; that one stays in flight until the next chained call or brisk_sync
     for (int si = 0; si < plan.n_slots; ++si)
       if (si != last_slot) { rc = finish(si); if (rc) return rc; }
+    // everything collected so far -- the previous call's last chunk and this call's chunks but the last -- is in the
+    // caller's buffers when the call returns: wait for the result copies of the other slot, and for those this slot issued
+    // before its last chunk was queued behind them (the event is re-recorded by every collected chunk, so it stands for
+    // the latest one; a slot that never collected anything has an unrecorded event, which counts as complete)
+    for (int si = 0; si < plan.n_slots; ++si) CU_OK(cudaEventSynchronize(ctx->slots[si].done));
     ctx->deferred = pend[last_slot];
     ctx->deferred_slot = last_slot;
     ctx->deferred_key = key;
